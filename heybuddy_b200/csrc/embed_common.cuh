@@ -1,0 +1,50 @@
+// Speech-embedding conv stack: layer table + model handle shared by the fp32 and tcgen05 paths.
+#pragma once
+#include "hb_common.cuh"
+#include <cuda_fp16.h>
+
+namespace hb {
+
+struct ConvLayer {
+    int kh, kw, cin, cout;
+    int same;        // 1: SAME padding on the freq axis (kw/2 each side); 0: VALID
+    int leaky;       // LeakyReLU(0.2) after the conv
+    int pool_t, pool_f;  // max-pool after the layer (1,1 = none)
+};
+
+// Mirrors heybuddy_b200/spec.py EMBEDDING_LAYERS.
+static const ConvLayer kLayers[kNumConv] = {
+    {1, 3, 1, 24, 1, 1, 1, 1},  {3, 1, 24, 24, 0, 1, 1, 1}, {1, 3, 24, 24, 1, 1, 1, 1}, {3, 1, 24, 24, 0, 1, 2, 2},
+    {1, 3, 24, 48, 1, 1, 1, 1}, {3, 1, 48, 48, 0, 1, 1, 1}, {1, 3, 48, 48, 1, 1, 1, 1}, {3, 1, 48, 48, 0, 1, 1, 2},
+    {1, 3, 48, 72, 1, 1, 1, 1}, {3, 1, 72, 72, 0, 1, 1, 1}, {1, 3, 72, 72, 1, 1, 1, 1}, {3, 1, 72, 72, 0, 1, 2, 2},
+    {1, 3, 72, 96, 1, 1, 1, 1}, {3, 1, 96, 96, 0, 1, 1, 1}, {1, 3, 96, 96, 1, 1, 1, 1}, {3, 1, 96, 96, 0, 1, 2, 2},
+    {1, 2, 96, 96, 0, 1, 1, 1}, {3, 1, 96, 96, 0, 1, 1, 1}, {1, 1, 96, 96, 0, 1, 1, 1}, {3, 1, 96, 96, 0, 0, 1, 1},
+};
+
+inline int64_t layer_weight_floats(const ConvLayer& l) { return (int64_t)l.kh * l.kw * l.cin * l.cout; }
+inline int64_t total_weight_floats() {
+    int64_t n = 0;
+    for (int i = 0; i < kNumConv; ++i) n += layer_weight_floats(kLayers[i]) + kLayers[i].cout;
+    return n;
+}
+
+}  // namespace hb
+
+struct hb_embed_model {
+    float* w32 = nullptr;              // packed fp32 [layer: kernel HWIO, bias]
+    int64_t w_off[hb::kNumConv];       // float offset of each layer's kernel
+    int64_t b_off[hb::kNumConv];       // float offset of each layer's bias
+    void* tc = nullptr;                // tensor-core path's repacked weights (embed_tc.cu)
+    int device = 0;
+};
+
+namespace hb {
+// embed_tc.cu
+int tc_prepare(hb_embed_model* m, const float* weights_host);
+void tc_release(hb_embed_model* m);
+int64_t tc_workspace_bytes(int B, int F);
+int tc_embed_clips(const hb_embed_model* m, const float* mel_dev, int B, int F, const int32_t* slot_offsets_host,
+                   int n_slots, float* out_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t stream);
+int64_t tc_activation(const hb_embed_model* m, const float* mel_dev, int B, int F, int layer, float* out_dev,
+                      int64_t out_capacity, void* workspace_dev, int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace hb

@@ -1,0 +1,158 @@
+/*
+ * heybuddy_b200 -- C-ABI of the B200-native featurization hot path.
+ *
+ * The reference (therealadityashankar/hey-buddy) has no FFI: its boundary is the
+ * Python "ring 1" model callable (src/python/heybuddy/util/onnx_util.py:83-96,
+ * InferenceSession.run) and the stock PyTorch / torchaudio / speechbrain ops the
+ * hot path calls.  Each entry point below replaces one of those call sites and is
+ * what a ctypes stub on the reference side binds.
+ *
+ * Conventions
+ *   - every function returns 0 (HB_OK) or a negative HB_ERR_* code; the message is
+ *     available from hb_last_error() (thread-local);
+ *   - pointers named *_dev are device pointers on the current CUDA device, pointers
+ *     named *_host are host pointers; the caller owns every buffer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous on that stream and re-entrant across streams;
+ *   - no torch types, no global state except immutable constant tables and the
+ *     explicit model handles.
+ */
+#ifndef HEYBUDDY_B200_H
+#define HEYBUDDY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_INVALID (-1)
+#define HB_ERR_CUDA (-2)
+#define HB_ERR_UNSUPPORTED (-3)
+
+#define HB_ABI_VERSION 1
+
+/* Precision mode of the embedding conv stack. */
+#define HB_EMBED_FP32 0 /* CUDA-core fp32 direct convolution (parity mode)          */
+#define HB_EMBED_F16 1  /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators */
+
+typedef struct hb_embed_model hb_embed_model; /* device-resident conv weights */
+typedef struct hb_mlp_model hb_mlp_model;     /* device-resident classifier   */
+
+/* ---- library ---------------------------------------------------------------------- */
+int hb_abi_version(void);
+const char* hb_last_error(void);
+/* Fills the constant tables (Hann window, FFT twiddles, mel filterbank) on the current
+ * device.  hann_host: f32[512] (periodic Hann(400) zero-padded), melfb_host: f32[257*32]
+ * row-major [bin][mel].  Must be called once per device before hb_mel_f32. */
+int hb_init_tables(const float* hann_host, const float* melfb_host);
+
+/* ---- K6: log-mel spectrogram ----------------------------------------------------------
+ * Replaces MelSpectrogramModel.__call__ -> ORT session.run(mel-spectrogram.onnx)
+ * (src/python/heybuddy/spectrogram.py:23-32) including the `/10 + 2` post-scale.
+ *   audio_dev  f32 [B][audio_row_stride], first T samples of each row are used
+ *   scale      multiplied into every sample on load (32767 for the Python path,
+ *              embeddings.py:182; 1 if the caller already scaled)
+ *   mel_dev    f32 [B][F][32], F = hb_mel_frames(T) = 1 + (T-512)/160
+ */
+int hb_mel_frames(int T);
+int hb_mel_f32(const float* audio_dev, int64_t audio_row_stride, float scale, float* mel_dev,
+               int B, int T, void* stream);
+
+/* ---- K7: speech-embedding conv stack ----------------------------------------------------
+ * Replaces SpeechEmbeddingModel.__call__ -> ORT session.run(speech-embedding.onnx)
+ * (src/python/heybuddy/embeddings.py:32-42).
+ *
+ * hb_embed_create: weights_host is the 20 conv layers packed in table order, each as
+ * kernel f32[kh][kw][cin][cout] followed by bias f32[cout] (274,440 floats).
+ */
+int hb_embed_create(hb_embed_model** out, const float* weights_host, int64_t n_floats);
+int hb_embed_destroy(hb_embed_model* m);
+int64_t hb_embed_num_params(void);
+
+/* Ring-1 shape: n windows f32 [n][76][32] -> f32 [n][96]. */
+int64_t hb_embed_windows_workspace_bytes(int n, int mode);
+int hb_embed_windows(const hb_embed_model* m, int mode, const float* windows_dev, float* out_dev,
+                     int n, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Whole-clip shape (fully convolutional): mel f32 [B][F][32] ->
+ * f32 [B][n_slots][96] where slot s is the embedding of frames
+ * [slot_offsets[s], slot_offsets[s]+76).  Offsets must be multiples of 4 and
+ * offset + 76 <= F.  Evaluated once per clip instead of once per window. */
+int64_t hb_embed_clips_workspace_bytes(int B, int F, int mode);
+int hb_embed_clips(const hb_embed_model* m, int mode, const float* mel_dev, int B, int F,
+                   const int32_t* slot_offsets_host, int n_slots, float* out_dev,
+                   void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* Parity hook: runs conv layers 0..layer (0..19) fully convolutionally over mel
+ * f32 [B][F][32] and writes the activation after that layer (after its pool; pool phase 0)
+ * as f32 NHWC [B][T_l][F_l][C_l] into out_dev (capacity in floats).  Returns the number of
+ * floats written, or <0.  Same workspace size as hb_embed_clips. */
+int64_t hb_embed_activation(const hb_embed_model* m, int mode, const float* mel_dev, int B, int F, int layer,
+                            float* out_dev, int64_t out_capacity, void* workspace_dev, int64_t workspace_bytes,
+                            void* stream);
+
+/* ---- K1-K4: fused augmentation ------------------------------------------------------------
+ * Replaces, for one augmentation batch (execute_augment_batch,
+ * src/python/heybuddy/dataset/augmented.py:363-392): torch_audiomentations
+ * AddColoredNoise + Gain (per_batch), torchaudio.functional.add_noise, and
+ * speechbrain reverberate -- in that order.
+ */
+typedef struct hb_augment_draws {
+    int32_t apply_colored; /* K1 drawn for this batch                               */
+    float colored_snr_db;  /* one SNR for the whole batch (mode="per_batch")          */
+    int32_t apply_gain;    /* K2                                                    */
+    float gain_db;
+    int32_t apply_background; /* K3 (per-clip SNRs come in a separate array)          */
+    int32_t apply_reverb;     /* K4 (RIR spectrum comes in a separate array)          */
+} hb_augment_draws;
+
+/* Spectrum of the rotated RIR for the exact-length circular convolution, computed once
+ * per batch: kernel_dev f32[T] (rotated, zero padded) -> spec_dev f32[2*(T/2+1)]. */
+int hb_rir_spectrum(const float* kernel_dev, float* spec_dev, int T, void* stream);
+int hb_augment_f32(const float* clips_dev,        /* f32 [B][T] length-fixed clips          */
+                   const float* noise_dev,        /* f32 [B][T] background rows or NULL      */
+                   const float* noise_snr_db_dev, /* f32 [B] or NULL                         */
+                   const float* colored_base_dev, /* f32 [16000] unit-RMS pattern or NULL    */
+                   const float* rir_spec_dev,     /* from hb_rir_spectrum or NULL            */
+                   const hb_augment_draws* draws_host, float* out_dev, int B, int T, void* stream);
+
+/* a1: int16/ragged clips -> length-fixed f32 [B][T] (to_target_length,
+ * augmented.py:200-232).  samples_dev: concatenated int16 samples; offsets_host[B+1];
+ * pad_before_host[B] from the draw table. */
+int hb_fix_length_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                      float* out_dev, int B, int T, void* stream);
+
+/* ---- K8: wake-word classifier ---------------------------------------------------------------
+ * Replaces WakeWordMLPModel.forward (src/python/heybuddy/wakeword.py:334-348) and the
+ * loss/backward/Adam of WakeWordTrainer.train_epoch (trainer.py:405-462).
+ * params are packed in state_dict order (heybuddy_b200/spec.py classifier_param_shapes).
+ */
+int64_t hb_mlp_num_params(void);
+int hb_mlp_create(hb_mlp_model** out, const float* params_host, int64_t n_floats);
+int hb_mlp_destroy(hb_mlp_model* m);
+int hb_mlp_get_params(const hb_mlp_model* m, float* params_host, int64_t n_floats);
+int hb_mlp_set_params(hb_mlp_model* m, const float* params_host, int64_t n_floats);
+int64_t hb_mlp_workspace_bytes(int B, int training);
+/* x_dev f32 [B][1536] -> prob_dev f32 [B]. */
+int hb_mlp_forward(const hb_mlp_model* m, const float* x_dev, float* prob_dev, int B,
+                   void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* One training step: forward, high-loss selection, weighted BCE (mean over selected
+ * rows), backward, and -- unless fewer than min_selected rows were selected -- Adam.
+ * stats_dev f32[4] = {loss, n_selected, stepped(0/1), high_loss_rate}. */
+int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B,
+                      float lr, float negative_weight, float high_loss_threshold, int min_selected,
+                      float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* Gradients of the last hb_mlp_train_step (packed like params), for parity tests. */
+int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats);
+
+/* config 5: M models evaluated on the same inputs.  x_dev [B][1536] -> prob_dev [M][B]. */
+int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const float* x_dev, float* prob_dev, int B,
+                         void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEYBUDDY_B200_H */

@@ -1,0 +1,191 @@
+"""GPU: speech-embedding conv stack (hb_embed_windows / hb_embed_clips / SpeechEmbeddings) vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from heybuddy_b200 import spec
+from oracle import embed as oembed
+from oracle import mel as omel
+from oracle import pipeline as opipe
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (north star: embeddings within 1e-3 relative; a stated tolerance for reduced-precision operands).
+#   fp32  CUDA-core parity mode: max|err| <= 1e-4 * max|ref|   (observed ~1e-6)
+#   f16   tcgen05, fp16 operands (11-bit mantissa = TF32-class) with fp32 accumulation:
+#         ||err||_2 <= 1e-3 * ||ref||_2  and  max|err| <= 2e-3 * max|ref|
+#         (CPU emulation of the operand rounding gives 3.2e-4 / 6.2e-4 on white-noise clips)
+TOL = {"fp32": dict(max=1e-4, l2=1e-4), "f16": dict(max=2e-3, l2=1e-3)}
+PRECISIONS = ["fp32", "f16"]
+
+
+def _assert_close(got, want, precision):
+    assert got.shape == want.shape
+    err = got.astype(np.float64) - want.astype(np.float64)
+    emax = np.abs(err).max() / np.abs(want).max()
+    el2 = np.linalg.norm(err) / np.linalg.norm(want)
+    assert emax <= TOL[precision]["max"] and el2 <= TOL[precision]["l2"], f"{precision}: max {emax:.3e} l2 {el2:.3e}"
+
+
+def _mel(seed, n, frames):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = 512 + 160 * (frames - 1)
+    audio = (0.1 * rng.standard_normal((n, t))).clip(-1, 1).astype(np.float32) * np.float32(spec.AUDIO_SCALE)
+    return omel.mel_spectrogram(audio)
+
+
+def _skip_if_not_built(m):
+    """A precision mode that is not compiled in fails loudly (NativeError); skip its parity cases."""
+    from heybuddy_b200 import _native
+
+    try:
+        m.run_windows_device(torch.zeros((1, 76, 32), device="cuda"))
+    except _native.NativeError as exc:
+        if "not built" in str(exc):
+            pytest.skip(str(exc))
+        raise
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return spec.init_embedding_weights()
+
+
+@pytest.fixture(scope="module", params=PRECISIONS)
+def model(request, cuda_device):
+    from heybuddy_b200.embeddings import SpeechEmbeddingModel
+
+    m = SpeechEmbeddingModel(device_id=0, precision=request.param, load=True)
+    _skip_if_not_built(m)
+    return m
+
+
+def test_ring1_windows(model, weights):
+    """The reference's model callable: f32 [n,76,32,1] -> [n,96] (embeddings.py:32-42)."""
+    m = _mel(1, 37, 76)[..., None]
+    got = model(m)
+    assert got.shape == (37, 96)
+    _assert_close(got, oembed.speech_embedding_model(m, weights, dtype=torch.float64), model.precision)
+    # batch of one keeps its batch axis (reference quirk fixed)
+    assert model(m[:1]).shape == (1, 96)
+    raw = super(type(model), model).__call__(input_1=m[:3])[0]
+    assert raw.shape == (3, 1, 1, 96)
+
+
+def test_zero_input_shape_contract(model, weights):
+    """speech-embedding.ts:53-71: zeros [100,32] -> [4,96]."""
+    z = torch.zeros((1, 100, 32), device="cuda")
+    out = model.run_clips_device(z, [0, 8, 16, 24]).cpu().numpy()
+    assert out.shape == (1, 4, 96)
+    want = oembed.embed_strip(np.zeros((1, 100, 32), np.float32), weights, dtype=torch.float64)
+    _assert_close(out, want, model.precision)
+
+
+@pytest.mark.parametrize("layer", [0, 1, 3, 4, 7, 8, 11, 12, 15, 16, 17, 18, 19])
+def test_layer_activations(model, weights, layer):
+    """Per-layer parity over a 141-frame strip (fully convolutional evaluation)."""
+    m = _mel(2, 3, 141)
+    got = model.activation_device(torch.from_numpy(m).cuda(), layer).cpu().numpy()
+    # oracle activation after `layer`
+    import torch.nn.functional as F
+    x = torch.from_numpy(m).double()[:, None]
+    for li, (name, kh, kw, cin, cout, pad, act, pool) in enumerate(spec.EMBEDDING_LAYERS[:layer + 1]):
+        w = torch.from_numpy(weights[f"{name}.weight"]).double().permute(3, 2, 0, 1)
+        x = F.conv2d(x, w, torch.from_numpy(weights[f"{name}.bias"]).double(), padding=(0, kw // 2) if pad == "same" else 0)
+        if act:
+            x = F.leaky_relu(x, spec.LEAKY_SLOPE)
+        if pool:
+            x = F.max_pool2d(x, pool, pool)
+    want = x.permute(0, 2, 3, 1).numpy()
+    _assert_close(got, want, model.precision)
+
+
+def test_clip_slots_match_windows(model, weights):
+    """hb_embed_clips on 141 frames == the model applied to each of the 16 reference windows."""
+    m = _mel(3, 5, 141)
+    offs = spec.embedding_frame_offsets(spec.CLIP_SAMPLES)
+    got = model.run_clips_device(torch.from_numpy(m).cuda(), offs).cpu().numpy()
+    want = np.stack([oembed.speech_embedding_model(m[:, o:o + 76, :, None], weights, dtype=torch.float64) for o in offs], axis=1)
+    assert got.shape == (5, 16, 96)
+    _assert_close(got, want, model.precision)
+    # and against the kernel's own windowed evaluation: same arithmetic per output -> tight
+    win = np.stack([m[:, o:o + 76] for o in offs], axis=1).reshape(-1, 76, 32)
+    own = model.run_windows_device(torch.from_numpy(win).cuda()).cpu().numpy().reshape(5, 16, 96)
+    np.testing.assert_allclose(got, own, rtol=0, atol=1e-5 * np.abs(want).max() if model.precision == "fp32" else 2e-3 * np.abs(want).max())
+
+
+def test_bad_slot_offsets_raise(model):
+    from heybuddy_b200 import _native
+
+    z = torch.zeros((1, 141, 32), device="cuda")
+    with pytest.raises(_native.NativeError):
+        model.run_clips_device(z, [2], )       # not a multiple of 4
+    with pytest.raises(_native.NativeError):
+        model.run_clips_device(z, [68])        # 68 + 76 > 141
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_speech_embeddings_reference_contract(cuda_device, weights, precision):
+    """tests/test_embeddings.py of the reference, plus values against the oracle pipeline."""
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+
+    se = SpeechEmbeddings(device_id=0, precision=precision)
+    _skip_if_not_built(se.embeddings)
+    torch.manual_seed(0)
+    audio = torch.randn((17280,)).clamp(-1, 1)
+    keep = audio.clone()
+    emb, spectro = se(audio, return_spectrograms=True)
+    assert spectro.shape == (1, 100, 32) and emb.shape == (1, 4, 96)
+    assert torch.equal(audio, keep), "the caller's tensor must not be scaled in place"
+    audio = torch.randn((23040,)).clamp(-1, 1)
+    emb, spectro = se(audio, return_spectrograms=True)
+    assert spectro.shape == (1, 420, 32) and emb.shape == (1, 16, 96)
+    want_e, want_s = opipe.speech_embeddings(
+        audio.numpy(), omel.mel_spectrogram, lambda w: oembed.speech_embedding_model(w, weights, dtype=torch.float64),
+        return_spectrograms=True)
+    _assert_close(emb, want_e, precision)
+    assert np.abs(spectro - want_s).max() <= 1e-4 * max(1.0, np.abs(want_s).max())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_speech_embeddings_batch_list_int16_and_golden(cuda_device, golden_dir, precision):
+    """List input (truncated to the shortest), int16 input, and the fixture produced by the reference's own code."""
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+
+    se = SpeechEmbeddings(device_id=0, precision=precision)
+    _skip_if_not_built(se.embeddings)
+    g = np.load(os.path.join(golden_dir, "pipeline_order.npz"))
+    rng = np.random.Generator(np.random.PCG64(int(g["seed"])))
+    clips = (0.1 * rng.standard_normal((3, spec.CLIP_SAMPLES))).clip(-1, 1).astype(np.float32)
+    got = se([torch.from_numpy(c.copy()) for c in clips])
+    _assert_close(got, g["embeddings"], precision)
+    # ragged list: items are truncated to the shortest (audio_util.py:90-101)
+    ragged = [clips[0], np.concatenate([clips[1], clips[1][:500]])]
+    np.testing.assert_allclose(se(ragged), got[:2], atol=1e-6)
+    # int16 clip == its float/32768 version
+    i16 = (clips[2] * 32767).astype(np.int16)
+    np.testing.assert_allclose(se(i16), se(i16.astype(np.float32) / 32768.0), atol=1e-6)
+    # config 1 geometry: 2 s clips -> 8 audio windows -> 32 embeddings
+    two_s = (0.1 * rng.standard_normal((2, 32000))).clip(-1, 1).astype(np.float32)
+    e, s = se(two_s, return_spectrograms=True)
+    assert e.shape == (2, 32, 96) and s.shape == (2, 836, 32)
+    with pytest.raises(ValueError):
+        se(np.zeros(1000, dtype=np.float32))  # shorter than one audio window
+
+
+def test_nan_repair(cuda_device):
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+
+    se = SpeechEmbeddings(device_id=0, precision="fp32", seed=0)
+    rng = np.random.default_rng(0)
+    clips = (0.1 * rng.standard_normal((3, spec.CLIP_SAMPLES))).astype(np.float32)
+    clips[1, 100] = np.nan
+    raw = se(clips, remove_nan=False)
+    assert np.isnan(raw[1]).any() and not np.isnan(raw[0]).any()
+    fixed = se(clips, remove_nan=True)
+    assert not np.isnan(fixed).any()
+    assert any(np.array_equal(fixed[1], raw[k]) for k in (0, 2))
+    allnan = np.full((2, spec.CLIP_SAMPLES), np.nan, dtype=np.float32)
+    assert np.array_equal(se(allnan), np.zeros((2, 16, 96), np.float32))
