@@ -31,15 +31,24 @@ class NativeError(RuntimeError):
     """Raised when a C-ABI call returns a negative status."""
 
 
-class hb_augment_draws(ctypes.Structure):
+class hb_clip_aug(ctypes.Structure):
     _fields_ = [
-        ("apply_colored", ctypes.c_int32),
+        ("noise_offset", ctypes.c_int64),
+        ("colored_index", ctypes.c_int32),
+        ("rir_index", ctypes.c_int32),
         ("colored_snr_db", ctypes.c_float),
-        ("apply_gain", ctypes.c_int32),
-        ("gain_db", ctypes.c_float),
-        ("apply_background", ctypes.c_int32),
-        ("apply_reverb", ctypes.c_int32),
+        ("gain", ctypes.c_float),
+        ("noise_snr_db", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
     ]
+
+
+# numpy view of the same 32-byte record
+CLIP_AUG_DTYPE = np.dtype([
+    ("noise_offset", "<i8"), ("colored_index", "<i4"), ("rir_index", "<i4"),
+    ("colored_snr_db", "<f4"), ("gain", "<f4"), ("noise_snr_db", "<f4"), ("reserved", "<i4"),
+])
+assert CLIP_AUG_DTYPE.itemsize == ctypes.sizeof(hb_clip_aug) == 32
 
 
 def lib_path() -> str:
@@ -51,6 +60,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     sig = {
         "hb_abi_version": (c_int, []),
         "hb_last_error": (ctypes.c_char_p, []),
+        "hb_launch_count": (c_i64, []),
         "hb_init_tables": (c_int, [c_vp, c_vp]),
         "hb_mel_frames": (c_int, [c_int]),
         "hb_mel_f32": (c_int, [c_vp, c_i64, c_f, c_vp, c_int, c_int, c_vp]),
@@ -62,8 +72,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_embed_clips_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
         "hb_embed_clips": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_vp]),
         "hb_embed_activation": (c_i64, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
-        "hb_rir_spectrum": (c_int, [c_vp, c_vp, c_int, c_vp]),
-        "hb_augment_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(hb_augment_draws), c_vp, c_int, c_int, c_vp]),
+        "hb_rir_spectrum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_augment_clips_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_fix_length_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_mlp_num_params": (c_i64, []),
         "hb_mlp_create": (c_int, [ctypes.POINTER(c_vp), c_vp, c_i64]),

@@ -3,8 +3,11 @@
 
 #include <stdarg.h>
 
+#include <atomic>
+
 namespace hb {
 static thread_local char g_error[1024] = "";
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -16,3 +19,4 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int hb_abi_version(void) { return HB_ABI_VERSION; }
 extern "C" const char* hb_last_error(void) { return hb::g_error; }
+extern "C" int64_t hb_launch_count(void) { return hb::g_launches.load(); }

@@ -1,5 +1,427 @@
-// K1-K4 placeholder -- filled in by the augmentation milestone.
+// K1-K4: fused augmentation -- coloured/white noise at a batch SNR, gain, background noise at a
+// per-clip SNR, and room-impulse-response reverb -- one kernel, one CTA per clip, the clip
+// resident in shared memory from the first load to the final store.
+//
+// Replaces the library calls of execute_augment_batch (reference
+// src/python/heybuddy/dataset/augmented.py:363-392): torch_audiomentations AddColoredNoise +
+// Gain (mode="per_batch"), torchaudio.functional.add_noise, speechbrain reverberate.
+// Arithmetic spec: SURVEY.md A.3 / oracle/augment.py.
+//
+// Reverb = circular convolution of exactly T samples (speechbrain convolve1d(use_fft=True) on
+// the rotated RIR), computed with an exact-length real FFT: the T real samples are packed into
+// M = T/2 complex points, transformed by a mixed-radix (4,2,3,5) Stockham FFT that ping-pongs
+// between two M-point shared-memory buffers, untangled / multiplied by the precomputed RIR
+// spectrum / re-tangled in one pointwise pass, and transformed back by the same forward FFT
+// under conjugation.  No zero padding: T = 23040 = 2 * (4^4 * 3^2 * 5).
+//
+// HBM traffic per clip: read clip (4T) + read noise row (4T, when drawn) + read coloured base
+// (64 KB, L2-resident per batch) + RIR spectrum (4T+8, L2-resident per batch) + write 4T.
 #include "hb_common.cuh"
-extern "C" int hb_rir_spectrum(const float*, float*, int, void*) { hb::set_error("augment not built yet"); return HB_ERR_UNSUPPORTED; }
-extern "C" int hb_augment_f32(const float*, const float*, const float*, const float*, const float*, const hb_augment_draws*, float*, int, int, void*) { hb::set_error("augment not built yet"); return HB_ERR_UNSUPPORTED; }
-extern "C" int hb_fix_length_i16(const int16_t*, const int64_t*, const int32_t*, float*, int, int, void*) { hb::set_error("augment not built yet"); return HB_ERR_UNSUPPORTED; }
+
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace hb {
+
+constexpr int kAugThreads = 512;
+constexpr int kMaxPasses = 12;
+constexpr int kColoredBase = 16000;
+constexpr int kMaxT = 23040;
+
+struct FftPlan {
+    int M;                 // complex points (T / 2)
+    int n_passes;
+    int radix[kMaxPasses];
+    const float2* tw_m;    // exp(-2 pi i k / M), k in [0, M)
+    const float2* tw_t;    // exp(-2 pi i k / T), k in [0, M]
+};
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // -i a
+__device__ __forceinline__ float2 mul_pos_i(float2 a) { return make_float2(-a.y, a.x); }  // +i a
+
+template <int R>
+__device__ __forceinline__ void dft(float2* v);
+
+template <>
+__device__ __forceinline__ void dft<2>(float2* v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<3>(float2* v) {
+    const float2 t1 = cadd(v[1], v[2]);
+    const float2 m1 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+    const float2 t2 = cscale(csub(v[1], v[2]), 0.86602540378443864676f);
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(m1, mul_neg_i(t2));
+    v[2] = cadd(m1, mul_pos_i(t2));
+}
+template <>
+__device__ __forceinline__ void dft<4>(float2* v) {
+    const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+    const float2 a2 = cadd(v[1], v[3]), a3 = csub(v[1], v[3]);
+    v[0] = cadd(a0, a2);
+    v[2] = csub(a0, a2);
+    v[1] = cadd(a1, mul_neg_i(a3));
+    v[3] = cadd(a1, mul_pos_i(a3));
+}
+template <>
+__device__ __forceinline__ void dft<5>(float2* v) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    const float2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    const float2 p1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    const float2 p2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    const float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+    const float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(p1, mul_neg_i(q1));
+    v[4] = cadd(p1, mul_pos_i(q1));
+    v[2] = cadd(p2, mul_neg_i(q2));
+    v[3] = cadd(p2, mul_pos_i(q2));
+}
+
+// One Stockham autosort pass of radix R over M points (forward transform).
+template <int R>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int M, int Ns,
+                                         const float2* __restrict__ tw) {
+    const int nb = M / R;
+    const int tw_step = M / (Ns * R);
+    for (int j = threadIdx.x; j < nb; j += kAugThreads) {
+        const int k = j % Ns;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[j + r * nb];
+        if (k != 0) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], __ldg(tw + r * k * tw_step));
+        }
+        dft<R>(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[base + r * Ns] = v[r];
+    }
+    __syncthreads();
+}
+
+// Runs the whole plan from `a` (ping-ponging with `b`); returns the buffer holding the result.
+__device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const FftPlan& plan) {
+    int Ns = 1;
+    for (int p = 0; p < plan.n_passes; ++p) {
+        const int R = plan.radix[p];
+        if (R == 4) fft_pass<4>(a, b, plan.M, Ns, plan.tw_m);
+        else if (R == 2) fft_pass<2>(a, b, plan.M, Ns, plan.tw_m);
+        else if (R == 3) fft_pass<3>(a, b, plan.M, Ns, plan.tw_m);
+        else fft_pass<5>(a, b, plan.M, Ns, plan.tw_m);
+        Ns *= R;
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();  // protect scratch reuse
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < kAugThreads / 32) ? scratch[threadIdx.x] : 0.f;
+    if (warp == 0) {
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// X[k], X[M-k] of the real signal from Z = FFT_M(x_even + i x_odd); w = exp(-2 pi i k / T).
+__device__ __forceinline__ void untangle(float2 A, float2 B, float2 w, float2* Xk, float2* Xmk) {
+    const float2 E = cscale(cadd(A, cconj(B)), 0.5f);
+    const float2 O = mul_neg_i(cscale(csub(A, cconj(B)), 0.5f));
+    const float2 wO = cmulf(w, O);
+    *Xk = cadd(E, wO);
+    // X[M-k] = conj(E) + W^{M-k} conj(O),  W^{M-k} = -conj(w)
+    *Xmk = csub(cconj(E), cconj(wO));
+}
+
+// ------------------------------------------------------------------------------------------------
+// RIR spectrum: kernels f32 [n][T] -> H f32 [n][M+1][2]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAugThreads, 1)
+rir_spectrum_kernel(const float* __restrict__ kernels, float2* __restrict__ spec, int T, FftPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int M = plan.M;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+    float2* buf1 = buf0 + M;
+    const float* src = kernels + (int64_t)blockIdx.x * T;
+    for (int i = threadIdx.x; i < M; i += kAugThreads) buf0[i] = make_float2(src[2 * i], src[2 * i + 1]);
+    __syncthreads();
+    const float2* Z = fft_forward(buf0, buf1, plan);
+    float2* H = spec + (int64_t)blockIdx.x * (M + 1);
+    for (int k = threadIdx.x; k <= M / 2; k += kAugThreads) {
+        if (k == 0) {
+            H[0] = make_float2(Z[0].x + Z[0].y, 0.f);
+            H[M] = make_float2(Z[0].x - Z[0].y, 0.f);
+        } else {
+            float2 Xk, Xmk;
+            untangle(Z[k], Z[M - k], __ldg(plan.tw_t + k), &Xk, &Xmk);
+            H[k] = Xk;
+            H[M - k] = Xmk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused per-clip augmentation
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAugThreads, 1)
+augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_bank,
+               const float* __restrict__ colored_bases, const float2* __restrict__ rir_specs,
+               const hb_clip_aug* __restrict__ params, float* __restrict__ out, int T, FftPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float scratch[40];
+    const int M = plan.M;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+    float2* buf1 = buf0 + M;
+    float* x = reinterpret_cast<float*>(buf0);
+    float* nz = reinterpret_cast<float*>(buf1);
+    const int tid = threadIdx.x;
+    const hb_clip_aug p = params[blockIdx.x];
+    const float* src = clips + (int64_t)blockIdx.x * T;
+    float* dst = out + (int64_t)blockIdx.x * T;
+    const bool has_colored = p.colored_index >= 0 && colored_bases != nullptr;
+    const bool has_noise = p.noise_offset >= 0 && noise_bank != nullptr;
+    const bool has_rir = p.rir_index >= 0 && rir_specs != nullptr;
+
+    // ---- load clip (128-bit loads; T is even, rows are 16-byte aligned when T % 4 == 0) --------
+    float sumsq = 0.f;
+    if ((T & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* x4 = reinterpret_cast<float4*>(x);
+        for (int i = tid; i < T / 4; i += kAugThreads) {
+            const float4 v = __ldg(s4 + i);
+            x4[i] = v;
+            sumsq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+    } else {
+        for (int i = tid; i < T; i += kAugThreads) {
+            const float v = __ldg(src + i);
+            x[i] = v;
+            sumsq += v * v;
+        }
+    }
+    // prefetch the noise row into the second buffer while the clip is being processed
+    float nsq = 0.f;
+    if (has_noise) {
+        const float* nsrc = noise_bank + p.noise_offset;
+        if ((T & 3) == 0 && ((reinterpret_cast<uintptr_t>(nsrc) & 15) == 0)) {
+            const float4* s4 = reinterpret_cast<const float4*>(nsrc);
+            float4* n4 = reinterpret_cast<float4*>(nz);
+            for (int i = tid; i < T / 4; i += kAugThreads) {
+                const float4 v = __ldg(s4 + i);
+                n4[i] = v;
+                nsq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        } else {
+            for (int i = tid; i < T; i += kAugThreads) {
+                const float v = __ldg(nsrc + i);
+                nz[i] = v;
+                nsq += v * v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- K1 coloured noise + K2 gain ---------------------------------------------------------------
+    if (has_colored) {
+        const float rms = sqrtf(block_sum(sumsq, scratch) / (float)T);
+        const float a = rms / exp10f(p.colored_snr_db * 0.05f);
+        const float* base = colored_bases + (int64_t)p.colored_index * kColoredBase;
+        for (int i = tid; i < T; i += kAugThreads) x[i] = (x[i] + a * __ldg(base + (i % kColoredBase))) * p.gain;
+        __syncthreads();
+    } else if (p.gain != 1.0f) {
+        for (int i = tid; i < T; i += kAugThreads) x[i] *= p.gain;
+        __syncthreads();
+    }
+
+    // ---- K3 background noise at the per-clip SNR -------------------------------------------------------
+    if (has_noise) {
+        float e = 0.f;
+        for (int i = tid; i < T; i += kAugThreads) e += x[i] * x[i];
+        const float e_s = block_sum(e, scratch);
+        const float e_n = block_sum(nsq, scratch);
+        const float orig = 10.0f * (log10f(e_s) - log10f(e_n));
+        const float scale = exp10f((orig - p.noise_snr_db) * 0.05f);
+        for (int i = tid; i < T; i += kAugThreads) x[i] = fmaf(scale, nz[i], x[i]);
+        __syncthreads();
+    }
+
+    if (!has_rir) {
+        for (int i = tid; i < T; i += kAugThreads) dst[i] = x[i];
+        return;
+    }
+
+    // ---- K4 reverb -------------------------------------------------------------------------------------
+    float a = 0.f;
+    for (int i = tid; i < T; i += kAugThreads) a += fabsf(x[i]);
+    const float amp_x = block_sum(a, scratch) / (float)T;
+
+    float2* Z = fft_forward(buf0, buf1, plan);
+    float2* other = (Z == buf0) ? buf1 : buf0;
+    const float2* H = rir_specs + (int64_t)p.rir_index * (M + 1);
+    // untangle -> multiply -> re-tangle, conjugated so the forward FFT inverts it
+    for (int k = tid; k <= M / 2; k += kAugThreads) {
+        if (k == 0) {
+            const float x0 = Z[0].x + Z[0].y, xm = Z[0].x - Z[0].y;
+            const float y0 = x0 * __ldg(&H[0]).x, ym = xm * __ldg(&H[M]).x;
+            Z[0] = make_float2(0.5f * (y0 + ym), -0.5f * (y0 - ym));
+        } else {
+            const float2 w = __ldg(plan.tw_t + k);
+            float2 Xk, Xmk;
+            untangle(Z[k], Z[M - k], w, &Xk, &Xmk);
+            const float2 Yk = cmulf(Xk, __ldg(&H[k]));
+            const float2 Ymk = cmulf(Xmk, __ldg(&H[M - k]));
+            const float2 Ye = cscale(cadd(Yk, cconj(Ymk)), 0.5f);
+            const float2 Yo = cmulf(cscale(csub(Yk, cconj(Ymk)), 0.5f), cconj(w));
+            // Z'[k] = Ye + i Yo ; Z'[M-k] = conj(Ye) + i Yo2, Yo2 = (Ymk - conj(Yk))/2 * conj(W^{M-k}) = conj(Yo)
+            const float2 zk = cadd(Ye, mul_pos_i(Yo));
+            const float2 zmk = cadd(cconj(Ye), mul_pos_i(cconj(Yo)));
+            Z[k] = cconj(zk);
+            if (k != M - k) Z[M - k] = cconj(zmk);
+        }
+    }
+    __syncthreads();
+    float2* Yc = fft_forward(Z, other, plan);   // = conj(M * z'), z' = y_even + i y_odd
+    float* y = reinterpret_cast<float*>(Yc);
+    const float inv_m = 1.0f / (float)M;
+    float ay = 0.f;
+    for (int i = tid; i < M; i += kAugThreads) {
+        const float2 v = Yc[i];
+        const float re = v.x * inv_m, im = -v.y * inv_m;
+        Yc[i] = make_float2(re, im);
+        ay += fabsf(re) + fabsf(im);
+    }
+    const float amp_y = block_sum(ay, scratch) / (float)T;
+    const float g = amp_x / (amp_y + 1e-14f);
+    for (int i = tid; i < T; i += kAugThreads) dst[i] = y[i] * g;
+}
+
+__global__ void fix_length_kernel(const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
+                                  const int32_t* __restrict__ pad_before, float* __restrict__ out, int T) {
+    const int b = blockIdx.x;
+    const int64_t s0 = offsets[b];
+    const int n = (int)(offsets[b + 1] - s0);
+    const int pad = n >= T ? 0 : pad_before[b];
+    float* dst = out + (int64_t)b * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const int j = i - pad;
+        dst[i] = (j >= 0 && j < n) ? (float)samples[s0 + j] * (1.0f / 32768.0f) : 0.f;
+    }
+}
+
+// ---- host-side plan cache ---------------------------------------------------------------------------
+struct PlanKey {
+    int dev, T;
+    bool operator<(const PlanKey& o) const { return dev != o.dev ? dev < o.dev : T < o.T; }
+};
+static std::map<PlanKey, FftPlan> g_plans;
+static std::mutex g_plan_mutex;
+
+static int get_plan(int T, FftPlan* out) {
+    HB_REQUIRE(T >= 4 && T % 2 == 0 && T <= kMaxT, "augment: T=%d unsupported (even, <= %d)", T, kMaxT);
+    int dev = 0;
+    HB_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto it = g_plans.find({dev, T});
+    if (it != g_plans.end()) {
+        *out = it->second;
+        return HB_OK;
+    }
+    FftPlan plan;
+    plan.M = T / 2;
+    plan.n_passes = 0;
+    int n = plan.M;
+    const int order[4] = {4, 2, 3, 5};
+    for (int r : order)
+        while (n % r == 0) {
+            HB_REQUIRE(plan.n_passes < kMaxPasses, "augment: too many FFT passes for T=%d", T);
+            plan.radix[plan.n_passes++] = r;
+            n /= r;
+        }
+    HB_REQUIRE(n == 1, "augment: T/2=%d must factor into 2,3,5 for the exact-length FFT", plan.M);
+    std::vector<float2> twm(plan.M), twt(plan.M + 1);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < plan.M; ++k) {
+        twm[k].x = (float)cos(two_pi * k / plan.M);
+        twm[k].y = (float)-sin(two_pi * k / plan.M);
+    }
+    for (int k = 0; k <= plan.M; ++k) {
+        twt[k].x = (float)cos(two_pi * k / T);
+        twt[k].y = (float)-sin(two_pi * k / T);
+    }
+    float2 *d_m = nullptr, *d_t = nullptr;
+    HB_CUDA_OK(cudaMalloc(&d_m, twm.size() * sizeof(float2)));
+    HB_CUDA_OK(cudaMalloc(&d_t, twt.size() * sizeof(float2)));
+    HB_CUDA_OK(cudaMemcpy(d_m, twm.data(), twm.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    HB_CUDA_OK(cudaMemcpy(d_t, twt.data(), twt.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    plan.tw_m = d_m;
+    plan.tw_t = d_t;
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
+    g_plans[{dev, T}] = plan;
+    *out = plan;
+    return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_rir_spectrum(const float* kernels_dev, float* spec_dev, int n, int T, void* stream) {
+    HB_REQUIRE(kernels_dev && spec_dev && n >= 0, "hb_rir_spectrum: bad argument");
+    if (n == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(T, &plan);
+    if (rc) return rc;
+    const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
+    rir_spectrum_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(kernels_dev, reinterpret_cast<float2*>(spec_dev), T, plan);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_bank_dev, const float* colored_bases_dev,
+                                    const float* rir_spec_bank_dev, const hb_clip_aug* params_dev, float* out_dev, int n,
+                                    int T, void* stream) {
+    HB_REQUIRE(clips_dev && params_dev && out_dev && n >= 0, "hb_augment_clips_f32: bad argument");
+    if (n == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(T, &plan);
+    if (rc) return rc;
+    const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
+    augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
+                                                                     reinterpret_cast<const float2*>(rir_spec_bank_dev),
+                                                                     params_dev, out_dev, T, plan);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+extern "C" int hb_fix_length_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                                 float* out_dev, int n, int T, void* stream) {
+    HB_REQUIRE(samples_dev && offsets_dev && pad_before_dev && out_dev && n >= 0 && T > 0, "hb_fix_length_i16: bad argument");
+    if (n == 0) return HB_OK;
+    fix_length_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(samples_dev, offsets_dev, pad_before_dev, out_dev, T);
+    HB_LAUNCHED();
+    return HB_OK;
+}

@@ -88,8 +88,10 @@ __global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ 
         const int b = (int)(r / To);
         float m = -INFINITY;
         for (int dt = 0; dt < pt; ++dt)
-            for (int df = 0; df < pf; ++df)
-                m = fmaxf(m, x[(((int64_t)b * T + to * pt + phase + dt) * F + fo * pf + df) * C + c]);
+            for (int df = 0; df < pf; ++df) {
+                const float v = x[(((int64_t)b * T + to * pt + phase + dt) * F + fo * pf + df) * C + c];
+                m = (v > m || v != v) ? v : m;  // NaN-propagating max, like torch.max_pool2d
+            }
         y[i] = m;
     }
 }
@@ -127,7 +129,7 @@ static int launch_conv(const hb_embed_model* m, int li, const float* x, float* y
     const size_t smem = (size_t)(kRowsPerBlock + L.kh - 1) * (F + 2 * a.padw) * L.cin * sizeof(float);
     dim3 grid(ceil_div(a.To, kRowsPerBlock), n);
     conv_rows_kernel<<<grid, kConvThreads, smem, st>>>(a);
-    HB_CUDA_OK(cudaGetLastError());
+    HB_LAUNCHED();
     return HB_OK;
 }
 
@@ -139,7 +141,7 @@ static int launch_pool(const float* x, float* y, int n, int T, int F, int C, int
     if (total <= 0) return HB_OK;
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16);
     maxpool_kernel<<<blocks, 256, 0, st>>>(x, y, n, T, F, C, pt, pf, phase, *To, *Fo);
-    HB_CUDA_OK(cudaGetLastError());
+    HB_LAUNCHED();
     return HB_OK;
 }
 
@@ -247,7 +249,7 @@ int fp32_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, co
     if (total > 0) {
         const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
         gather_slots_kernel<<<blocks, 256, 0, st>>>(tmp[0], tmp[1], J[0], J[1], slot_m_dev, n_slots, out, B);
-        HB_CUDA_OK(cudaGetLastError());
+        HB_LAUNCHED();
     }
     return HB_OK;
 }

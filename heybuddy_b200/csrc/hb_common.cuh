@@ -5,12 +5,15 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/heybuddy_b200.h"
 
 namespace hb {
 
 // Thread-local last-error string behind hb_last_error().
 void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;  // kernels launched by this library (hb_launch_count)
 
 #define HB_CUDA_OK(expr)                                                                  \
     do {                                                                                  \
@@ -19,6 +22,13 @@ void set_error(const char* fmt, ...);
             hb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
             return HB_ERR_CUDA;                                                           \
         }                                                                                 \
+    } while (0)
+
+// Checks a kernel launch and counts it.
+#define HB_LAUNCHED()                        \
+    do {                                     \
+        HB_CUDA_OK(cudaGetLastError());      \
+        hb::g_launches.fetch_add(1);         \
     } while (0)
 
 #define HB_REQUIRE(cond, ...)                    \

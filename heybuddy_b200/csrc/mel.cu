@@ -162,7 +162,7 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
         float acc = 0.f;
 #pragma unroll 8
         for (int k = 0; k < kMelBand; ++k) acc = fmaf(pw[k], s.fb[k * kMels + lane], acc);
-        mel[((int64_t)clip * F + f) * kMels + lane] = log10f(fmaxf(acc, 1e-10f)) + 2.0f;
+        mel[((int64_t)clip * F + f) * kMels + lane] = log10f(acc < 1e-10f ? 1e-10f : acc) + 2.0f;  // NaN-propagating clamp, like np.maximum / torch.clamp
         __syncwarp();
     }
 }
@@ -221,6 +221,6 @@ extern "C" int hb_mel_f32(const float* audio_dev, int64_t audio_row_stride, floa
     HB_REQUIRE((int64_t)B * chunks < (1ll << 31), "hb_mel_f32: B=%d too large for one launch", B);
     mel_kernel<<<B * chunks, kMelThreads, sizeof(MelSmem), (cudaStream_t)stream>>>(audio_dev, audio_row_stride, scale,
                                                                                      mel_dev, T, F, chunks);
-    HB_CUDA_OK(cudaGetLastError());
+    HB_LAUNCHED();
     return HB_OK;
 }

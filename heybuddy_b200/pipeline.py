@@ -1,0 +1,266 @@
+"""
+The fused featurization pipeline: ragged int16 clips -> length fix -> augmentation -> log-mel ->
+speech embeddings, everything resident on one GPU between the first H2D copy and the final D2H of
+the ``[n, 16, 96]`` embeddings.
+
+This is what ``TrainingFeaturesGenerator.generate`` (reference dataset/features.py:360-490) does
+with a python loop per clip, a D2H per clip and one ORT call per 32 items; here a chunk of
+augmentation batches is five kinds of kernel launches on one stream:
+
+    hb_fix_length_i16 -> hb_augment_clips_f32 -> hb_mel_f32 -> hb_embed_clips (trunk + tail)
+
+``featurize_host`` adds the pinned-memory H2D / D2H copies on a second stream so chunk i+1 uploads
+while chunk i computes (double buffering).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from heybuddy_b200 import _native, spec
+from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+from heybuddy_b200.dataset.draws import DrawTable
+from heybuddy_b200.embeddings import SpeechEmbeddings
+
+__all__ = ["FeaturizePipeline", "RaggedClips", "DeviceChunk"]
+
+
+@dataclass
+class RaggedClips:
+    """n int16 clips as one concatenated sample array + offsets (the shape TTS output arrives in)."""
+    samples: np.ndarray   # int16 [total]
+    offsets: np.ndarray   # int64 [n + 1]
+    pinned: Optional["object"] = None  # optional torch int16 tensor over the same samples in pinned host memory
+
+    @classmethod
+    def from_list(cls, clips: Sequence[np.ndarray]) -> "RaggedClips":
+        lengths = np.array([c.shape[0] for c in clips], dtype=np.int64)
+        for c in clips:
+            if c.dtype != np.int16:
+                raise TypeError("RaggedClips holds int16 clips (Piper's output type, piper/pretrained.py:406-408)")
+        return cls(np.concatenate(clips) if len(clips) else np.zeros(0, np.int16),
+                   np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64))
+
+    def __len__(self) -> int:
+        return int(self.offsets.shape[0] - 1)
+
+    @property
+    def lengths(self) -> np.ndarray:
+        return np.diff(self.offsets)
+
+    def slice(self, lo: int, hi: int) -> "RaggedClips":
+        o = self.offsets[lo:hi + 1]
+        return RaggedClips(self.samples[o[0]:o[-1]], (o - o[0]).astype(np.int64),
+                           self.pinned[int(o[0]):int(o[-1])] if self.pinned is not None else None)
+
+    def pin(self) -> "RaggedClips":
+        """Moves the samples into pinned host memory so uploads need no staging copy."""
+        import torch
+
+        t = torch.from_numpy(self.samples).pin_memory()
+        return RaggedClips(t.numpy(), self.offsets, t)
+
+
+@dataclass
+class DeviceChunk:
+    """One chunk's device-resident inputs (what ``value`` in bench.py times over)."""
+    samples: "object"       # cuda int16 [total]
+    offsets: "object"       # cuda int64 [n + 1]
+    pad_before: "object"    # cuda int32 [n]
+    params: "object"        # cuda uint8 [n, 32]  (hb_clip_aug records)
+    bases: Optional["object"]  # cuda f32 [k, 16000] coloured patterns or None
+    n: int
+
+
+class FeaturizePipeline:
+    def __init__(self, augment: Optional[AugmentedAudioGenerator], speech: SpeechEmbeddings, device_id: Optional[int] = None):
+        self.augment = augment
+        self.speech = speech
+        self.device = _native.require_cuda(device_id if device_id is not None else speech.spectrogram.device_id)
+        self.t = spec.CLIP_SAMPLES if augment is None else augment.target_num_samples
+        self.slot_offsets = np.asarray(spec.embedding_frame_offsets(self.t), dtype=np.int32)
+        self._bufs: Dict[Tuple[str, int], "object"] = {}
+        self.stage_ms: Dict[str, float] = {}
+        self._events: List[Tuple[str, object, object]] = []
+        self.profile = False
+
+    # -- host-side packing -------------------------------------------------------------------------
+    def pack_params(self, table: DrawTable) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
+        """Draw table -> (pad_before i32[n], hb_clip_aug records, coloured bases f32[k,16000] | None)."""
+        aug = self.augment
+        bases = [d.colored_base for d in table.batches if d.colored_apply]
+        slots, k = [], 0
+        for d in table.batches:
+            slots.append(k if d.colored_apply else -1)
+            k += int(d.colored_apply)
+        params = aug.clip_params(table.batches, table.noise_clip_cursor, table.rir_index, slots)
+        pads = np.concatenate([d.pad_before for d in table.batches]).astype(np.int32)
+        return pads, params, (np.stack(bases) if bases else None)
+
+    def upload(self, clips: RaggedClips, table: DrawTable) -> DeviceChunk:
+        import torch
+
+        pads, params, bases = self.pack_params(table)
+        dev = self.device
+        return DeviceChunk(
+            samples=torch.from_numpy(clips.samples).to(dev), offsets=torch.from_numpy(clips.offsets).to(dev),
+            pad_before=torch.from_numpy(pads).to(dev),
+            params=torch.from_numpy(params.view(np.uint8).reshape(len(clips), -1)).to(dev),
+            bases=torch.from_numpy(bases).to(dev) if bases is not None else None, n=len(clips))
+
+    # -- device path -----------------------------------------------------------------------------------
+    def _buf(self, name: str, shape, dtype):
+        import torch
+
+        key = (name, int(np.prod(shape)))
+        buf = self._bufs.get(key)
+        if buf is None or buf.dtype != dtype:
+            for k in [k for k in self._bufs if k[0] == name]:
+                del self._bufs[k]
+            buf = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = buf
+        return buf.view(shape)
+
+    def _mark(self, name: str):
+        import torch
+
+        if not self.profile:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self._events.append((name, ev))
+        return ev
+
+    def collect_stage_times(self) -> Dict[str, float]:
+        """Sums CUDA-event durations per stage since the last call (events are on the compute stream)."""
+        out: Dict[str, float] = {}
+        for (n0, e0), (n1, e1) in zip(self._events[:-1], self._events[1:]):
+            if n1 == "begin":
+                continue
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._events = []
+        return out
+
+    def run_device(self, chunk: DeviceChunk, out=None, keep_audio: bool = False):
+        """Device-resident chunk -> cuda f32 ``[n, 16, 96]`` embeddings (optionally also the augmented audio)."""
+        import torch
+
+        lib = _native.load()
+        n, t, dev = chunk.n, self.t, self.device
+        aug = self.augment
+        with torch.cuda.device(dev):
+            st = _native.stream_ptr(dev)
+            self._mark("begin")
+            fixed = self._buf("fixed", (n, t), torch.float32)
+            _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                                                fixed.data_ptr(), n, t, st), "hb_fix_length_i16")
+            self._mark("fix_length")
+            audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
+            nb, rb = aug.noise_bank, aug.rir_bank
+            _native.check(lib.hb_augment_clips_f32(
+                fixed.data_ptr(), nb.stream.data_ptr() if nb is not None else None,
+                chunk.bases.data_ptr() if chunk.bases is not None else None,
+                rb.spec.data_ptr() if rb is not None else None,
+                chunk.params.data_ptr(), audio.data_ptr(), n, t, st), "hb_augment_clips_f32")
+            self._mark("augment")
+            mel = self._buf("mel", (n, spec.mel_frames(t), spec.N_MELS), torch.float32)
+            self.speech.spectrogram.run_device(audio, scale=spec.AUDIO_SCALE, out=mel)
+            self._mark("mel")
+            if out is None:
+                out = torch.empty((n, self.slot_offsets.size, spec.EMB_DIM), dtype=torch.float32, device=dev)
+            self.speech.embeddings.run_clips_device(mel, self.slot_offsets, out=out)
+            self._mark("embed")
+        return (out, audio) if keep_audio else out
+
+    # -- host path (the call a user makes) -----------------------------------------------------------------
+    def featurize_host(self, clips: RaggedClips, tables: Sequence[DrawTable], chunk_clips: int, out: Optional[np.ndarray] = None):
+        """
+        Host int16 clips -> host f32 ``[n, 16, 96]``.  ``tables[i]`` holds the draws of chunk i
+        (``chunk_clips`` clips each, a multiple of the augmentation batch size).  Uploads run on a side
+        stream from pinned staging buffers, double-buffered against the compute stream; the result comes
+        back through a pinned buffer.  Returns (embeddings, h2d_bytes, d2h_bytes).
+        """
+        import torch
+
+        n = len(clips)
+        dev = self.device
+        n_slots = self.slot_offsets.size
+        if out is None:
+            out = np.empty((n, n_slots, spec.EMB_DIM), dtype=np.float32)
+        if ("copy_stream", 0) not in self._bufs:
+            self._bufs[("copy_stream", 0)] = torch.cuda.Stream(device=dev)
+        copy_stream = self._bufs[("copy_stream", 0)]
+        compute = torch.cuda.current_stream(dev)
+        h2d = d2h = 0
+        staged = []
+        pending = None  # (result device tensor, pinned host tensor, lo, hi, event)
+
+        def stage(ci: int):
+            nonlocal h2d
+            lo, hi = ci * chunk_clips, min(n, (ci + 1) * chunk_clips)
+            part = clips.slice(lo, hi)
+            pads, params, bases = self.pack_params(tables[ci])
+            slot = ci % 2
+            host = {}
+            for name, arr in (("samples", part.samples), ("offsets", part.offsets), ("pads", pads),
+                              ("params", params.view(np.uint8).reshape(hi - lo, -1)), ("bases", bases)):
+                if arr is None:
+                    host[name] = None
+                    continue
+                if name == "samples" and part.pinned is not None:
+                    host[name] = (part.pinned, arr.shape)  # already pinned: DMA straight from the caller's buffer
+                    continue
+                key = (f"pin_{name}_{slot}", 0)
+                pin = self._bufs.get(key)
+                if pin is None or pin.numel() < arr.size or pin.dtype != torch.from_numpy(arr[:0]).dtype:
+                    pin = torch.empty(max(arr.size, 1), dtype=torch.from_numpy(arr[:0]).dtype).pin_memory()
+                    self._bufs[key] = pin
+                pin[:arr.size].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)))
+                host[name] = (pin, arr.shape)
+            with torch.cuda.stream(copy_stream):
+                devs = {}
+                for name, v in host.items():
+                    if v is None:
+                        devs[name] = None
+                        continue
+                    pin, shape = v
+                    cnt = int(np.prod(shape))
+                    d = torch.empty(cnt, dtype=pin.dtype, device=dev)
+                    d.copy_(pin[:cnt], non_blocking=True)
+                    h2d += cnt * pin.element_size()
+                    devs[name] = d.view(shape)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return DeviceChunk(devs["samples"], devs["offsets"], devs["pads"], devs["params"], devs["bases"], hi - lo), ev, lo, hi
+
+        n_chunks = (n + chunk_clips - 1) // chunk_clips
+        nxt = stage(0) if n_chunks else None
+        for ci in range(n_chunks):
+            chunk, ev, lo, hi = nxt
+            nxt = stage(ci + 1) if ci + 1 < n_chunks else None
+            compute.wait_event(ev)
+            for v in (chunk.samples, chunk.offsets, chunk.pad_before, chunk.params, chunk.bases):
+                if v is not None:
+                    v.record_stream(compute)
+            emb = self.run_device(chunk)
+            key = (f"pin_out_{ci % 2}", 0)
+            pin = self._bufs.get(key)
+            if pin is None or pin.numel() < emb.numel():
+                pin = torch.empty(emb.numel(), dtype=torch.float32).pin_memory()
+                self._bufs[key] = pin
+            if pending is not None:
+                p_pin, p_lo, p_hi, p_ev = pending
+                p_ev.synchronize()
+                out[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
+            pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
+            d2h += emb.numel() * 4
+            done = torch.cuda.Event()
+            done.record(compute)
+            pending = (pin, lo, hi, done)
+        if pending is not None:
+            p_pin, p_lo, p_hi, p_ev = pending
+            p_ev.synchronize()
+            out[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
+        return out, h2d, d2h

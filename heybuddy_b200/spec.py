@@ -204,6 +204,28 @@ def embedding_macs_per_window(t_in: int = EMB_WINDOW, f_in: int = N_MELS) -> int
     return macs
 
 
+def embedding_macs_per_clip(frames: int = 141, f_in: int = N_MELS) -> int:
+    """
+    MACs of the fully-convolutional evaluation of one clip (``hb_embed_clips``): conv2d..conv2d_15 once over
+    the whole ``frames``-frame strip, then the last 2x2 pool and block 5 once per pool phase (window offsets
+    = 0 and 4 mod 8).  This is the algorithmic work behind ``roofline.achieved`` in bench.py.
+    """
+    macs = 0
+    t, f = frames, f_in
+    for li, (_, kh, kw, cin, cout, pad, _act, pool) in enumerate(EMBEDDING_LAYERS[:16]):
+        if pad == "valid":
+            t, f = t - kh + 1, f - kw + 1
+        macs += t * f * cout * kh * kw * cin
+        if pool is not None and li != 15:
+            t, f = t // pool[0], f // pool[1]
+    for phase in (0, 1):
+        tp, fp = (t - phase) // 2, f // 2
+        for (_, kh, kw, cin, cout, pad, _act, pool) in EMBEDDING_LAYERS[16:]:
+            tp, fp = tp - kh + 1, fp - kw + 1
+            macs += tp * fp * cout * kh * kw * cin
+    return macs
+
+
 def embedding_num_params() -> int:
     return sum(kh * kw * cin * cout + cout for (_, kh, kw, cin, cout, *_r) in EMBEDDING_LAYERS)
 

@@ -42,10 +42,12 @@ class MelSpectrogramModel(PretrainedNativeModel):
         f = spec.mel_frames(t)
         if out is None:
             out = torch.empty((b, f, spec.N_MELS), dtype=torch.float32, device=audio_dev.device)
+        if b == 0 or f == 0:
+            return out
         lib = _native.load()
         with torch.cuda.device(audio_dev.device):
             _native.check(
-                lib.hb_mel_f32(audio_dev.data_ptr(), audio_dev.stride(0), float(scale), out.data_ptr(), b, t,
+                lib.hb_mel_f32(audio_dev.data_ptr(), audio_dev.stride(0) if b > 1 else t, float(scale), out.data_ptr(), b, t,
                                _native.stream_ptr(audio_dev.device)),
                 "hb_mel_f32",
             )

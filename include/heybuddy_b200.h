@@ -44,6 +44,9 @@ typedef struct hb_mlp_model hb_mlp_model;     /* device-resident classifier   */
 /* ---- library ---------------------------------------------------------------------- */
 int hb_abi_version(void);
 const char* hb_last_error(void);
+/* Number of kernels this library has launched in this process (all streams); bench.py reports the
+ * per-step delta as "gpu_launches". */
+int64_t hb_launch_count(void);
 /* Fills the constant tables (Hann window, FFT twiddles, mel filterbank) on the current
  * device.  hann_host: f32[512] (periodic Hann(400) zero-padded), melfb_host: f32[257*32]
  * row-major [bin][mel].  Must be called once per device before hb_mel_f32. */
@@ -95,35 +98,39 @@ int64_t hb_embed_activation(const hb_embed_model* m, int mode, const float* mel_
                             void* stream);
 
 /* ---- K1-K4: fused augmentation ------------------------------------------------------------
- * Replaces, for one augmentation batch (execute_augment_batch,
- * src/python/heybuddy/dataset/augmented.py:363-392): torch_audiomentations
- * AddColoredNoise + Gain (per_batch), torchaudio.functional.add_noise, and
- * speechbrain reverberate -- in that order.
+ * Replaces, per clip of an augmentation batch (execute_augment_batch,
+ * src/python/heybuddy/dataset/augmented.py:363-392): torch_audiomentations AddColoredNoise
+ * (:107-115) and Gain (:116-120) in mode="per_batch", torchaudio.functional.add_noise
+ * (:272-276) and speechbrain reverberate (:388-392) -- in that order, one kernel, the clip
+ * resident in shared memory.  Batch semantics (one coloured pattern / gain / RIR per batch,
+ * consecutive noise rows) live in the per-clip descriptors the host fills from the draw table.
  */
-typedef struct hb_augment_draws {
-    int32_t apply_colored; /* K1 drawn for this batch                               */
-    float colored_snr_db;  /* one SNR for the whole batch (mode="per_batch")          */
-    int32_t apply_gain;    /* K2                                                    */
-    float gain_db;
-    int32_t apply_background; /* K3 (per-clip SNRs come in a separate array)          */
-    int32_t apply_reverb;     /* K4 (RIR spectrum comes in a separate array)          */
-} hb_augment_draws;
+typedef struct hb_clip_aug {
+    int64_t noise_offset;  /* first sample of this clip's noise row in noise_bank_dev; < 0: no background */
+    int32_t colored_index; /* row of colored_bases_dev ([n][16000] unit-RMS patterns);   < 0: none        */
+    int32_t rir_index;     /* row of rir_spec_bank_dev ([n][T/2+1] complex spectra);     < 0: no reverb   */
+    float colored_snr_db;
+    float gain;            /* linear factor 10^(dB/20); 1 when Gain was not drawn                          */
+    float noise_snr_db;
+    int32_t reserved;
+} hb_clip_aug;
 
-/* Spectrum of the rotated RIR for the exact-length circular convolution, computed once
- * per batch: kernel_dev f32[T] (rotated, zero padded) -> spec_dev f32[2*(T/2+1)]. */
-int hb_rir_spectrum(const float* kernel_dev, float* spec_dev, int T, void* stream);
-int hb_augment_f32(const float* clips_dev,        /* f32 [B][T] length-fixed clips          */
-                   const float* noise_dev,        /* f32 [B][T] background rows or NULL      */
-                   const float* noise_snr_db_dev, /* f32 [B] or NULL                         */
-                   const float* colored_base_dev, /* f32 [16000] unit-RMS pattern or NULL    */
-                   const float* rir_spec_dev,     /* from hb_rir_spectrum or NULL            */
-                   const hb_augment_draws* draws_host, float* out_dev, int B, int T, void* stream);
+/* Spectra of rotated RIRs for the exact-length circular convolution (once per RIR bank):
+ * kernels_dev f32 [n][T] (rotated so the peak is at lag 0, zero padded; augment host code)
+ * -> spec_dev f32 [n][T/2+1][2].  T must be even with T/2 = 2^a 3^b 5^c and T <= 23040. */
+int hb_rir_spectrum(const float* kernels_dev, float* spec_dev, int n, int T, void* stream);
+int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-fixed clips            */
+                         const float* noise_bank_dev,     /* f32 noise stream or NULL                  */
+                         const float* colored_bases_dev,  /* f32 [..][16000] or NULL                   */
+                         const float* rir_spec_bank_dev,  /* from hb_rir_spectrum or NULL              */
+                         const hb_clip_aug* params_dev,   /* [n] device array                          */
+                         float* out_dev, int n, int T, void* stream);
 
-/* a1: int16/ragged clips -> length-fixed f32 [B][T] (to_target_length,
- * augmented.py:200-232).  samples_dev: concatenated int16 samples; offsets_host[B+1];
- * pad_before_host[B] from the draw table. */
+/* a1: int16 ragged clips -> length-fixed f32 [n][T] (to_target_length, augmented.py:200-232):
+ * /32768, front-truncate when longer than T, otherwise zero-pad with pad_before[b] zeros on
+ * the left.  samples_dev: concatenated int16 samples; offsets_dev i64[n+1]; pad_before_dev i32[n]. */
 int hb_fix_length_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
-                      float* out_dev, int B, int T, void* stream);
+                      float* out_dev, int n, int T, void* stream);
 
 /* ---- K8: wake-word classifier ---------------------------------------------------------------
  * Replaces WakeWordMLPModel.forward (src/python/heybuddy/wakeword.py:334-348) and the

@@ -17,7 +17,7 @@ def declared_symbols():
 
 def test_header_declares_the_hot_path():
     syms = declared_symbols()
-    for must in ("hb_mel_f32", "hb_embed_clips", "hb_embed_windows", "hb_augment_f32", "hb_mlp_forward", "hb_mlp_train_step"):
+    for must in ("hb_mel_f32", "hb_embed_clips", "hb_embed_windows", "hb_augment_clips_f32", "hb_mlp_forward", "hb_mlp_train_step"):
         assert must in syms
 
 

