@@ -184,48 +184,34 @@ static int run_fp32(const hb_embed_model* m, const float* mel, int B, int F, int
     return HB_OK;
 }
 
-int fp32_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, const int32_t* slot_offsets_host,
-                     int n_slots, float* out, void* ws, int64_t ws_bytes, cudaStream_t st) {
-    HB_REQUIRE(ws_bytes >= fp32_workspace_bytes(B, F), "hb_embed: workspace too small (%lld < %lld)",
-               (long long)ws_bytes, (long long)fp32_workspace_bytes(B, F));
-    float* bufA = reinterpret_cast<float*>(ws);
-    float* bufB = bufA + fp32_buf_floats(B, F);
-    const int64_t tail_floats = (int64_t)B * (F / 8 + 2) * kEmbDim;
-    float* tmp[2] = {bufB + fp32_buf_floats(B, F), bufB + fp32_buf_floats(B, F) + tail_floats};
-    int* slot_m_dev = reinterpret_cast<int*>(tmp[1] + tail_floats);
+// Last 2x2 max-pool (both phases) + block 5 (conv2d_16..19) + slot gather, from the pre-pool conv2d_15 output
+// f32 [B][T15][4][96].  Window offset 8j uses pool phase 0 position j, offset 8j+4 pool phase 1 position j.
+int fp32_tail_from_l15(const hb_embed_model* m, const float* pre_pool, int B, int T15, const int32_t* slot_offsets_host,
+                       int n_slots, float* out, float* scratch, int64_t scratch_floats, cudaStream_t st) {
+    const int64_t rows = T15 / 2 + 1;
+    const int64_t tail_floats = (int64_t)B * rows * kEmbDim;
+    HB_REQUIRE(scratch_floats >= 6 * tail_floats + 1024, "hb_embed: tail scratch too small (%lld < %lld)",
+               (long long)scratch_floats, (long long)(6 * tail_floats + 1024));
+    float* tmp[2] = {scratch, scratch + tail_floats};
+    float* s0 = scratch + 2 * tail_floats;
+    float* s1 = s0 + 2 * tail_floats;
+    int* slot_m_dev = reinterpret_cast<int*>(s1 + 2 * tail_floats);
 
     bool need_phase[2] = {false, false};
     std::vector<int> slot_m(n_slots);
+    HB_REQUIRE(n_slots <= 1024, "hb_embed_clips: too many slots (%d)", n_slots);
     for (int s = 0; s < n_slots; ++s) {
         const int off = slot_offsets_host[s];
-        HB_REQUIRE(off >= 0 && off % 4 == 0 && off + kEmbWindow <= F,
-                   "hb_embed_clips: slot offset %d invalid for F=%d (must be a multiple of 4, offset+76 <= F)", off, F);
+        HB_REQUIRE(off >= 0 && off % 4 == 0, "hb_embed_clips: slot offset %d must be a non-negative multiple of 4", off);
         slot_m[s] = off / 4;
         need_phase[slot_m[s] & 1] = true;
     }
-    HB_REQUIRE(n_slots * (int)sizeof(int) <= 4096, "hb_embed_clips: too many slots (%d)", n_slots);
     HB_CUDA_OK(cudaMemcpyAsync(slot_m_dev, slot_m.data(), n_slots * sizeof(int), cudaMemcpyHostToDevice, st));
-
-    // shared trunk: conv2d .. conv2d_15 (pre-pool)
-    const float* act; int T, Fq, C;
-    // run up to layer 14, then layer 15 conv without its pool so both phases can pool from it
-    int rc = run_fp32(m, mel, B, F, 14, 0, bufA, bufB, &act, &T, &Fq, &C, st);
-    if (rc) return rc;
-    float* free_buf = (act == bufA) ? bufB : bufA;
-    int T15, F15;
-    rc = launch_conv(m, 15, act, free_buf, B, T, Fq, &T15, &F15, st);
-    if (rc) return rc;
-    const float* pre_pool = free_buf;           // [B][T15][4][96]
-    float* scratch = (free_buf == bufA) ? bufB : bufA;  // trunk input no longer needed
     int J[2] = {0, 0};
     for (int p = 0; p < 2; ++p) {
         if (!need_phase[p]) continue;
-        // pool -> conv2d_16 -> 17 -> 18 -> 19, ping-ponging inside `scratch`
-        const int64_t half = fp32_buf_floats(B, F) / 2;
-        float* s0 = scratch;
-        float* s1 = scratch + half;
         int To, Fo;
-        rc = launch_pool(pre_pool, s0, B, T15, F15, kEmbDim, 2, 2, p, &To, &Fo, st);
+        int rc = launch_pool(pre_pool, s0, B, T15, 4, kEmbDim, 2, 2, p, &To, &Fo, st);
         if (rc) return rc;
         int Tc = To, Fc = Fo;
         const float* c = s0;
@@ -252,6 +238,29 @@ int fp32_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, co
         HB_LAUNCHED();
     }
     return HB_OK;
+}
+
+int fp32_pool_public(const float* x, float* y, int n, int T, int F, int C, int pt, int pf, int phase, cudaStream_t st) {
+    int To, Fo;
+    return launch_pool(x, y, n, T, F, C, pt, pf, phase, &To, &Fo, st);
+}
+
+int fp32_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, const int32_t* slot_offsets_host,
+                     int n_slots, float* out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    HB_REQUIRE(ws_bytes >= fp32_workspace_bytes(B, F), "hb_embed: workspace too small (%lld < %lld)",
+               (long long)ws_bytes, (long long)fp32_workspace_bytes(B, F));
+    float* bufA = reinterpret_cast<float*>(ws);
+    float* bufB = bufA + fp32_buf_floats(B, F);
+    // shared trunk: conv2d .. conv2d_14, then conv2d_15 without its pool so both phases can pool from it
+    const float* act; int T, Fq, C;
+    int rc = run_fp32(m, mel, B, F, 14, 0, bufA, bufB, &act, &T, &Fq, &C, st);
+    if (rc) return rc;
+    float* free_buf = (act == bufA) ? bufB : bufA;
+    int T15, F15;
+    rc = launch_conv(m, 15, act, free_buf, B, T, Fq, &T15, &F15, st);
+    if (rc) return rc;
+    float* scratch = (free_buf == bufA) ? bufB : bufA;  // the trunk's input is no longer needed
+    return fp32_tail_from_l15(m, free_buf, B, T15, slot_offsets_host, n_slots, out, scratch, fp32_buf_floats(B, F), st);
 }
 
 int64_t fp32_activation(const hb_embed_model* m, const float* mel, int B, int F, int layer, float* out,
@@ -330,6 +339,10 @@ extern "C" int hb_embed_clips(const hb_embed_model* m, int mode, const float* me
                               int64_t workspace_bytes, void* stream) {
     HB_REQUIRE(m && mel_dev && out_dev && workspace_dev && slot_offsets_host, "hb_embed_clips: null pointer");
     HB_REQUIRE(B >= 0 && F >= kEmbWindow && n_slots > 0, "hb_embed_clips: bad shape B=%d F=%d n_slots=%d", B, F, n_slots);
+    for (int s = 0; s < n_slots; ++s)
+        HB_REQUIRE(slot_offsets_host[s] >= 0 && slot_offsets_host[s] % 4 == 0 && slot_offsets_host[s] + kEmbWindow <= F,
+                   "hb_embed_clips: slot offset %d invalid for F=%d (must be a multiple of 4, offset+76 <= F)",
+                   slot_offsets_host[s], F);
     HB_REQUIRE(B <= 65535, "hb_embed_clips: B=%d exceeds one launch", B);
     if (B == 0) return HB_OK;
     if (mode == HB_EMBED_FP32)

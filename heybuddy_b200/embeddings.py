@@ -28,7 +28,7 @@ from heybuddy_b200.util import PretrainedNativeModel, audio_to_bct_tensor, logge
 
 __all__ = ["SpeechEmbeddingModel", "SpeechEmbeddings", "get_speech_embeddings", "DEFAULT_EMBED_PRECISION"]
 
-DEFAULT_EMBED_PRECISION = os.environ.get("HEYBUDDY_B200_EMBED_PRECISION", "fp32")
+DEFAULT_EMBED_PRECISION = os.environ.get("HEYBUDDY_B200_EMBED_PRECISION", "f16")
 # clips per device chunk of the fused path (bounds the activation workspace)
 DEFAULT_CLIP_CHUNK = int(os.environ.get("HEYBUDDY_B200_CLIP_CHUNK", "1024"))
 
