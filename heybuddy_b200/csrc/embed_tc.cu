@@ -50,10 +50,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -66,6 +66,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             return;
         }
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -293,30 +302,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
         const TcLayer L = a.layers[l];
         unsigned char* wcur = (l & 1) ? wbuf1 : wbuf0;
         if (warp == 0) {
-            if (lane == 0) {
-                mbar_wait(&hdr.wbar[l & 1], (uint32_t)((l >> 1) & 1));
+            // Warp-uniform issue loop: every lane computes the same descriptors (so they live in uniform registers)
+            // and one elected lane issues the tcgen05 instructions.
+            mbar_wait(&hdr.wbar[l & 1], (uint32_t)((l >> 1) & 1));
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(128, L.n);
+            const uint32_t a_base = smem_u32(cur), b_base = smem_u32(wcur);
+            const int ksteps = L.cin_chunks / 2;
+            const uint64_t a_hi = make_desc(0, chunk_stride, 128), b_hi = make_desc(0, (uint32_t)L.n * 16, 128);
+            const uint32_t b_tap_stride = (uint32_t)(L.cin_chunks * L.n * 16);
+            const uint32_t b_k_stride = (uint32_t)(2 * L.n * 16);
+            for (int mt = 0; mt < a.n_mt; ++mt) {
+                const int it = tile_counter + mt;
+                const int slot = it % kSlots;
+                if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
                 tc_fence_after();
-                const uint32_t idesc = make_idesc(128, L.n);
-                const uint32_t a_base = smem_u32(cur), b_base = smem_u32(wcur);
-                const int ksteps = L.cin_chunks / 2;
-                for (int mt = 0; mt < a.n_mt; ++mt) {
-                    const int it = tile_counter + mt;
-                    const int slot = it % kSlots;
-                    if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kSlotCols);
-                    uint32_t acc = 0;
-                    for (int tap = 0; tap < 3; ++tap) {
-                        const int shift = L.is_time ? tap * S : tap - 1;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t a_addr = a_base + (uint32_t)(2 * ks) * chunk_stride + (uint32_t)((mt * 128 + shift) * 16);
-                            const uint32_t b_addr = b_base + (uint32_t)((tap * L.cin_chunks + 2 * ks) * L.n * 16);
-                            umma_f16(d_tmem, make_desc(a_addr, chunk_stride, 128), make_desc(b_addr, (uint32_t)L.n * 16, 128), idesc, acc);
-                            acc = 1;
-                        }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kSlotCols);
+                uint32_t acc = 0;
+                for (int tap = 0; tap < 3; ++tap) {
+                    const int shift = L.is_time ? tap * S : tap - 1;
+                    uint32_t a_addr = a_base + (uint32_t)((mt * 128 + shift) * 16);
+                    uint32_t b_addr = b_base + (uint32_t)tap * b_tap_stride;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+                        const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
+                        if (elect_one()) umma_f16(d_tmem, ad, bd, idesc, acc);
+                        acc = 1;
+                        a_addr += 2 * chunk_stride;
+                        b_addr += b_k_stride;
                     }
-                    umma_commit(&hdr.tmem_full[slot]);
                 }
+                if (elect_one()) umma_commit(&hdr.tmem_full[slot]);
             }
             __syncwarp();
         } else if (warp == 1) {
