@@ -1,0 +1,291 @@
+"""
+``WakeWordMLPModel`` -- B200 replacement of the reference's default classifier
+(``heybuddy/wakeword.py:171-348``; ``DEFAULT_ARCHITECTURE = "perceptron"``, constants.py:73).
+
+Same constructor defaults, ``from_file`` / ``state_dict`` / ``load_state_dict`` with the reference's
+parameter names (== the ONNX initializer names of ``src/ts/models/*.onnx``), ``__call__(x[B,16,96]) ->
+[B,1]`` probabilities, ``predict(audio)`` through ``SpeechEmbeddings``.  Forward, backward and Adam run
+in the hand-written kernels of ``csrc/classifier.cu`` through ``hb_mlp_*``; there is no torch.nn graph.
+
+Only the default architecture (layer_dim 96, 2 layers, gating, no half layers) is built: the
+transformer classifier and the half-layer variant are outside the north-star path.
+Dropout(0.1) on the input is train-only in the reference; the fused training step runs without it
+(parity configuration).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from heybuddy_b200 import _native, spec
+from heybuddy_b200.constants import *  # noqa: F401,F403
+from heybuddy_b200.util import audio_to_bct_tensor
+
+__all__ = ["WakeWordMLPModel", "MultiWakeWordModel", "pack_classifier_params", "unpack_classifier_params"]
+
+
+def pack_classifier_params(params: Dict[str, Any]) -> np.ndarray:
+    parts = []
+    for name, shape in spec.classifier_param_shapes():
+        v = params[name]
+        v = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+        assert tuple(v.shape) == shape, (name, v.shape, shape)
+        parts.append(np.ascontiguousarray(v, dtype=np.float32).ravel())
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+def unpack_classifier_params(flat: np.ndarray) -> Dict[str, np.ndarray]:
+    out, off = {}, 0
+    for name, shape in spec.classifier_param_shapes():
+        n = int(np.prod(shape))
+        out[name] = flat[off:off + n].reshape(shape).copy()
+        off += n
+    assert off == flat.size
+    return out
+
+
+class WakeWordMLPModel:
+    """The default wake-word classifier: (batch, 16, 96) speech embeddings -> probability."""
+
+    def __init__(
+        self,
+        input_shape: Tuple[int, int] = (16, 96),
+        layer_dim: int = DEFAULT_LAYER_DIM,
+        num_layers: int = DEFAULT_LAYERS,
+        use_gating: bool = DEFAULT_USE_GATING,
+        use_half_layers: bool = DEFAULT_USE_HALF_LAYERS,
+        dropout: float = 0.1,
+        activation: Optional[str] = "silu",
+        device_id: Optional[int] = None,
+        seed: int = 5002,
+    ) -> None:
+        if (tuple(input_shape), layer_dim, num_layers, use_gating, use_half_layers, activation) != ((16, 96), 96, 2, True, False, "silu"):
+            raise NotImplementedError("only the default perceptron architecture (16x96 -> 96, 2 layers, gated, silu) is built")
+        self.input_shape = tuple(input_shape)
+        self.input_features = input_shape[0] * input_shape[1]
+        self.dropout = dropout
+        self.device_id = device_id
+        self.training = False
+        self._handle = None
+        self._workspace = None
+        self._host_params = pack_classifier_params(spec.init_classifier_weights(seed))
+
+    # -- device plumbing ---------------------------------------------------------------------------
+    @property
+    def device(self):
+        return _native.require_cuda(self.device_id)
+
+    def _ensure(self):
+        if self._handle is None:
+            import torch
+
+            lib = _native.load()
+            h = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                _native.check(lib.hb_mlp_create(ctypes.byref(h), self._host_params.ctypes.data, self._host_params.size), "hb_mlp_create")
+            self._handle = h
+        return self._handle
+
+    def _ws(self, nbytes: int):
+        import torch
+
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _native.load().hb_mlp_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # -- torch.nn.Module-like surface ------------------------------------------------------------------
+    def to(self, device=None, **_: Any) -> "WakeWordMLPModel":
+        import torch
+
+        if device is not None:
+            d = torch.device(device)
+            if d.type != "cuda":
+                raise _native.NativeError("heybuddy_b200 has no CPU path")
+            self.device_id = d.index
+        return self
+
+    def best(self) -> "WakeWordMLPModel":
+        return self
+
+    def eval(self) -> "WakeWordMLPModel":
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True) -> "WakeWordMLPModel":
+        self.training = mode
+        return self
+
+    def _flat_params(self) -> np.ndarray:
+        if self._handle is None:
+            return self._host_params.copy()
+        import torch
+
+        flat = np.empty_like(self._host_params)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _native.check(_native.load().hb_mlp_get_params(self._handle, flat.ctypes.data, flat.size), "hb_mlp_get_params")
+        return flat
+
+    def state_dict(self) -> Dict[str, Any]:
+        import torch
+
+        return {k: torch.from_numpy(v) for k, v in unpack_classifier_params(self._flat_params()).items()}
+
+    def load_state_dict(self, state_dict: Dict[str, Any], strict: bool = True) -> None:
+        names = [n for n, _ in spec.classifier_param_shapes()]
+        if strict and set(state_dict.keys()) != set(names):
+            raise KeyError(f"state_dict keys differ: missing {set(names) - set(state_dict)}, unexpected {set(state_dict) - set(names)}")
+        cur = unpack_classifier_params(self._flat_params())
+        cur.update({k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items() if k in cur})
+        self._host_params = pack_classifier_params(cur)
+        if self._handle is not None:
+            import torch
+
+            with torch.cuda.device(self.device):
+                _native.check(_native.load().hb_mlp_set_params(self._handle, self._host_params.ctypes.data, self._host_params.size),
+                              "hb_mlp_set_params")
+
+    def gradients(self) -> Dict[str, np.ndarray]:
+        """Parameter gradients of the last ``train_step`` (parity hook)."""
+        import torch
+
+        flat = np.empty_like(self._host_params)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _native.check(_native.load().hb_mlp_get_grads(self._ensure(), flat.ctypes.data, flat.size), "hb_mlp_get_grads")
+        return unpack_classifier_params(flat)
+
+    @classmethod
+    def from_file(cls, path: str, device: Optional[Any] = None) -> "WakeWordMLPModel":
+        """Loads a reference ``.pt`` state dict (torch.save(state_dict), trainer.py:186-198) or an ``.npz``."""
+        if path.endswith(".npz"):
+            with np.load(path) as z:
+                sd = {k: z[k] for k in z.files}
+        else:
+            import torch
+
+            sd = torch.load(path, weights_only=True, map_location="cpu")
+        model = cls()
+        model.load_state_dict(sd)
+        if device is not None:
+            model.to(device)
+        return model
+
+    def save_onnx(self, path: str, opset_version: int = 19) -> None:
+        raise NotImplementedError("ONNX export belongs to the browser runtime, outside the B200 hot path (SURVEY.md 2 #21)")
+
+    # -- forward -----------------------------------------------------------------------------------------
+    def forward_device(self, x, out=None):
+        """cuda f32 ``[B,16,96]`` (or ``[B,1536]``) -> cuda f32 ``[B,1]`` probabilities."""
+        import torch
+
+        x = x.reshape(x.shape[0], -1).contiguous()
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape[1] == self.input_features
+        b = x.shape[0]
+        if out is None:
+            out = torch.empty((b, 1), dtype=torch.float32, device=x.device)
+        lib = _native.load()
+        with torch.cuda.device(x.device):
+            nbytes = lib.hb_mlp_workspace_bytes(b, 0)
+            ws = self._ws(nbytes)
+            _native.check(lib.hb_mlp_forward(self._ensure(), x.data_ptr(), out.data_ptr(), b, ws.data_ptr(), ws.numel(),
+                                             _native.stream_ptr(x.device)), "hb_mlp_forward")
+        return out
+
+    def __call__(self, x):
+        import torch
+
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return self.forward_device(x.to(self.device, dtype=torch.float32))
+
+    forward = __call__
+
+    def train_step(self, x, y, lr: float, negative_weight: float = 1.0, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD,
+                   min_selected: int = 128):
+        """
+        One reference training step (trainer.py:405-462) fused on the device: forward, high-loss selection,
+        weighted BCE (mean over the selected rows), backward and -- when at least ``min_selected`` rows were
+        selected -- Adam.  Returns (probabilities cuda [B,1], stats cuda f32[4] = loss, n_selected, stepped, high_loss_rate).
+        """
+        import torch
+
+        x = x.reshape(x.shape[0], -1).contiguous()
+        assert x.is_cuda and x.dtype == torch.float32 and y.is_cuda and y.dtype == torch.int64
+        b = x.shape[0]
+        prob = torch.empty((b, 1), dtype=torch.float32, device=x.device)
+        stats = torch.empty(4, dtype=torch.float32, device=x.device)
+        lib = _native.load()
+        with torch.cuda.device(x.device):
+            nbytes = lib.hb_mlp_workspace_bytes(b, 1)
+            ws = self._ws(nbytes)
+            _native.check(lib.hb_mlp_train_step(self._ensure(), x.data_ptr(), y.data_ptr(), b, float(lr), float(negative_weight),
+                                                float(high_loss_threshold), int(min_selected), prob.data_ptr(), stats.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _native.stream_ptr(x.device)), "hb_mlp_train_step")
+        return prob, stats
+
+    # -- inference mixin (wakeword.py:129-169) ---------------------------------------------------------------
+    @property
+    def speech_embeddings(self):
+        from heybuddy_b200.embeddings import get_speech_embeddings
+
+        if not hasattr(self, "_speech_embeddings"):
+            self._speech_embeddings = get_speech_embeddings(device_id=self.device.index or 0)
+        return self._speech_embeddings
+
+    def predict(self, audio: Any, threshold: float = 0.5, embedding_spectrogram_batch_size: int = 32, embedding_batch_size: int = 32,
+                return_scores: bool = False, min_frames: int = 23040) -> Union[Tuple[bool, ...], Tuple[float, ...]]:
+        """Predicts on one or more audio clips (centre-pads to ``min_frames``, wakeword.py:141-156)."""
+        import torch
+
+        audio_tensor, _ = audio_to_bct_tensor(audio, sample_rate=16000)
+        n, c, t = audio_tensor.shape
+        if t < min_frames:
+            pad = min_frames - t
+            left = int(pad / 2)
+            audio_tensor = torch.cat([torch.zeros(n, c, left, dtype=audio_tensor.dtype), audio_tensor,
+                                      torch.zeros(n, c, pad - left, dtype=audio_tensor.dtype)], dim=-1)
+        emb = self.speech_embeddings(audio_tensor, embedding_batch_size=embedding_batch_size,
+                                     spectrogram_batch_size=embedding_spectrogram_batch_size)
+        preds = self(emb).cpu().numpy()
+        return tuple(preds.flatten()) if return_scores else tuple((preds > threshold).flatten())
+
+
+class MultiWakeWordModel:
+    """
+    BASELINE config 5: N wake-word models evaluated on the same rolling ``[16, 96]`` embedding buffer
+    (browser semantics, src/ts/src/hey-buddy.ts:350-413; the Python reference runs one thread per model and
+    re-featurizes per model, util/model_util.py:62-93).  Featurize once, then ``hb_mlp_forward_multi``.
+    """
+
+    def __init__(self, models: List[WakeWordMLPModel]):
+        assert models
+        self.models = models
+        self._ws = None
+
+    def __call__(self, x):
+        """cuda f32 ``[B,16,96]`` -> cuda f32 ``[M, B]``."""
+        import torch
+
+        x = x.reshape(x.shape[0], -1).contiguous()
+        b, m = x.shape[0], len(self.models)
+        out = torch.empty((m, b), dtype=torch.float32, device=x.device)
+        lib = _native.load()
+        handles = (ctypes.c_void_p * m)(*[mod._ensure() for mod in self.models])
+        with torch.cuda.device(x.device):
+            nbytes = lib.hb_mlp_workspace_bytes(b, 0)
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+            _native.check(lib.hb_mlp_forward_multi(handles, m, x.data_ptr(), out.data_ptr(), b, self._ws.data_ptr(), self._ws.numel(),
+                                                   _native.stream_ptr(x.device)), "hb_mlp_forward_multi")
+        return out

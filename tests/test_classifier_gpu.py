@@ -1,0 +1,150 @@
+"""GPU: classifier forward / training step (hb_mlp_*) vs the reference-generated fixtures and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from heybuddy_b200 import spec
+from oracle import classifier as ocls
+
+pytestmark = pytest.mark.gpu
+
+# north star: classifier logits within 1e-3.  Probabilities are compared at rtol 1e-3 (+ tiny atol), logits of
+# the oracle vs log(p/(1-p)) of the kernel output at atol 1e-3; gradients at 2e-3 relative to each tensor's max.
+LOGIT_ATOL = 1e-3
+
+
+def _golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "classifier_hey_buddy.npz"))
+    params = {k[len("param::"):]: g[k] for k in g.files if k.startswith("param::")}
+    rng = np.random.Generator(np.random.PCG64(int(g["x_seed"])))
+    x = rng.standard_normal((64, 16, 96)).astype(np.float32)
+    x[:16] += 0.5 * rng.standard_normal((1, 1, 96)).astype(np.float32)
+    y = np.zeros(64, dtype=np.int64)
+    y[:16] = 1
+    return g, params, x, y
+
+
+def test_forward_matches_reference_fixture(cuda_device, golden_dir):
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    g, params, x, y = _golden(golden_dir)
+    model = WakeWordMLPModel(device_id=0)
+    model.load_state_dict(params)
+    p = model(x).cpu().numpy()
+    assert p.shape == (64, 1)
+    np.testing.assert_allclose(p, g["prob"], rtol=1e-3, atol=1e-7)
+    logit = np.log(p / (1 - p))
+    want = ocls.forward(x, params, return_logits=True)
+    assert np.abs(logit - want).max() < LOGIT_ATOL
+    # the browser self-test input (wake-word.ts:35-50): zeros -> the known answer computed with the reference class
+    zero = np.load(os.path.join(golden_dir, "classifier_zero_answers.npz"))
+    np.testing.assert_allclose(model(np.zeros((1, 16, 96), np.float32)).item(), float(zero["hey_buddy"]), rtol=1e-3)
+    # state dict round trip keeps the reference's key names
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec.classifier_param_shapes()]
+    np.testing.assert_array_equal(sd["mlp_in.gate.weight"].numpy(), params["mlp_in.gate.weight"])
+
+
+def test_train_step_matches_reference_fixture(cuda_device, golden_dir):
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    g, params, x, y = _golden(golden_dir)
+    model = WakeWordMLPModel(device_id=0)
+    model.load_state_dict(params)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    # lr = 0: gradients only
+    prob, stats = model.train_step(xt, yt, lr=0.0, negative_weight=float(g["negative_weight"]),
+                                   high_loss_threshold=float(g["threshold"]), min_selected=1)
+    loss, n_sel, stepped, rate = stats.tolist()
+    assert int(n_sel) == int(g["n_selected"]) and stepped == 1.0
+    np.testing.assert_allclose(loss, float(g["loss"]), rtol=1e-4)
+    np.testing.assert_allclose(rate, int(g["n_selected"]) / 64.0, rtol=1e-6)
+    grads = model.gradients()
+    for k in g.files:
+        if k.startswith("grad::"):
+            want = g[k]
+            assert np.abs(grads[k[6:]] - want).max() <= 2e-3 * np.abs(want).max() + 1e-9, k
+        elif k.startswith("gradnorm::"):
+            np.testing.assert_allclose(np.linalg.norm(grads[k[10:]]), float(g[k]), rtol=1e-3, err_msg=k)
+    # full gradient check of every tensor against torch autograd (float64 oracle)
+    _, _, _, want_all = ocls.forward_backward_torch(x, y, params, float(g["negative_weight"]), float(g["threshold"]))
+    for k, want in want_all.items():
+        assert np.abs(grads[k] - want).max() <= 2e-3 * np.abs(want).max() + 1e-9, k
+
+
+def test_adam_update_and_skip_rule(cuda_device, golden_dir):
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    g, params, x, y = _golden(golden_dir)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    # reference torch.optim.Adam on the oracle gradients, two steps
+    ref = torch.nn.ParameterDict({k.replace(".", "_"): torch.nn.Parameter(torch.tensor(v, dtype=torch.float64)) for k, v in params.items()})
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    cur = {k: v.copy() for k, v in params.items()}
+    model = WakeWordMLPModel(device_id=0)
+    model.load_state_dict(params)
+    for _ in range(2):
+        _, _, _, grads = ocls.forward_backward_torch(x, y, cur, 1.0, 1e-4)
+        for k in params:
+            ref[k.replace(".", "_")].grad = torch.tensor(grads[k])
+        opt.step()
+        cur = {k: ref[k.replace(".", "_")].detach().numpy().astype(np.float32) for k in params}
+        model.train_step(xt, yt, lr=1e-3, negative_weight=1.0, min_selected=1)
+    got = {k: v.numpy() for k, v in model.state_dict().items()}
+    for k in params:
+        # Adam normalises each element's update to ~lr whatever the gradient's size, so an element whose gradient is
+        # ~0 may move by up to lr per step in either direction under fp32-vs-fp64 noise: bound those, match the rest.
+        diff = np.abs(got[k] - cur[k])
+        tol = 2e-5 + 1e-3 * np.abs(cur[k] - params[k]).max()
+        assert (diff <= tol).mean() >= 0.999, k
+        assert diff.max() <= 2 * 2 * 1e-3, k
+    # fewer than min_selected rows -> no update at all (trainer.py:451-458)
+    before = model.state_dict()
+    _, stats = model.train_step(xt, yt, lr=1e-1, negative_weight=1.0, min_selected=10_000)
+    assert stats[2].item() == 0.0
+    after = model.state_dict()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+
+
+def test_config4_batch_and_multi_model(cuda_device):
+    """Batch 4096 (186 pos + 186 adv + 3724 neg) forward vs the oracle; 7 models evaluated on one buffer."""
+    from heybuddy_b200.wakeword import MultiWakeWordModel, WakeWordMLPModel
+
+    rng = np.random.Generator(np.random.PCG64(4001))
+    x = rng.standard_normal((4096, 16, 96)).astype(np.float32)
+    x[:186] += 0.5 * rng.standard_normal((1, 1, 96)).astype(np.float32)
+    models = [WakeWordMLPModel(device_id=0, seed=5002 + i) for i in range(7)]
+    xt = torch.from_numpy(x).cuda()
+    got = MultiWakeWordModel(models)(xt).cpu().numpy()
+    assert got.shape == (7, 4096)
+    for i in (0, 3, 6):
+        want = ocls.forward(x[:512], spec.init_classifier_weights(5002 + i))[:, 0]
+        np.testing.assert_allclose(got[i, :512], want, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(models[2](xt).cpu().numpy()[:, 0], got[2], rtol=1e-6)
+
+
+def test_training_reduces_loss_and_lr_schedule(cuda_device):
+    from heybuddy_b200.trainer import WakeWordTrainer, get_learning_rate
+
+    for step in (0, 10, 999, 1000, 2666, 2667, 4000, 4999):
+        np.testing.assert_allclose(get_learning_rate(step, 1000, 1666, 5000), ocls.learning_rate(step, 1000, 1666, 5000), rtol=1e-12)
+    rng = np.random.Generator(np.random.PCG64(7))
+    direction = rng.standard_normal((1, 1, 96)).astype(np.float32)
+
+    def batches():
+        while True:
+            x = rng.standard_normal((1024, 16, 96)).astype(np.float32)
+            y = np.zeros(1024, dtype=np.int64)
+            y[:128] = 1
+            x[:128] += 0.7 * direction
+            yield torch.from_numpy(x), torch.from_numpy(y)
+
+    trainer = WakeWordTrainer(device_id=0)
+    trainer.train_epoch(batches(), num_steps=60, learning_rate=2e-3, validation=None)
+    loss = trainer.history["loss"]
+    assert np.mean(loss[-10:]) < 0.6 * np.mean(loss[:5])
+    metrics = trainer.evaluate(batches(), max_batches=2)
+    assert metrics["recall"] > 0.9 and metrics["false_positive_rate"] < 0.1
