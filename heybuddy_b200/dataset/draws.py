@@ -14,7 +14,7 @@ by a seeded host RNG in the reference's call order (augmented.py:314-392):
     background coin (augmented.py:383)                 -> noise stream advance -> rand(B) SNRs (:269-270)
     reverb coin (augmented.py:387)                     -> RIR advance
 
-Batch g's draws come from ``Generator(PCG64([seed, g]))`` so the table does not depend on how
+Batch g's draws come from ``Generator(PCG64([seed, g, stream]))`` so the table does not depend on how
 batches are sharded over ranks; the stateful cursors (noise stream position, RIR index) are prefix
 sums over the table.  The oracle (tests) and the CUDA kernel consume the same table.
 """
@@ -92,18 +92,25 @@ class BatchDraw:
 
 
 def draw_batch(seed: int, index: int, lengths: Sequence[int], cfg: AugmentConfig,
-               have_background: bool = True, have_reverb: bool = True) -> BatchDraw:
-    """The draws of augmentation batch ``index`` (clip lengths ``lengths``), in the reference's order."""
-    rng = np.random.Generator(np.random.PCG64([int(seed), int(index)]))
+               have_background: bool = True, have_reverb: bool = True, light: bool = False) -> BatchDraw:
+    """
+    The draws of augmentation batch ``index`` (clip lengths ``lengths``), in the reference's order.
+    ``light`` skips building the coloured pattern (only the coins are needed to advance the stream cursors).
+    """
+    # two sub-streams per batch: the pad offsets consume a length-dependent number of draws, the batch-level
+    # coins must not depend on them (any rank can then replay the coins of earlier batches without their clips)
+    rng_pad = np.random.Generator(np.random.PCG64([int(seed), int(index), 1]))
+    rng = np.random.Generator(np.random.PCG64([int(seed), int(index), 0]))
     b = len(lengths)
     d = BatchDraw(index=index, pad_before=np.array(
-        [pad_before_for(int(n), cfg.target_samples, rng) for n in lengths], dtype=np.int32))
+        [pad_before_for(int(n), cfg.target_samples, rng_pad) for n in lengths], dtype=np.int32))
     # coloured noise
     if rng.random() < cfg.colored_noise_prob:
         d.colored_apply = True
         d.colored_snr_db = float(rng.uniform(cfg.colored_noise_min_snr_db, cfg.colored_noise_max_snr_db))
         d.colored_f_decay = float(rng.uniform(cfg.colored_noise_min_f_decay, cfg.colored_noise_max_f_decay))
-        d.colored_base = colored_noise_base(rng.standard_normal(spec.COLORED_BASE_SAMPLES), d.colored_f_decay)
+        gauss = rng.standard_normal(spec.COLORED_BASE_SAMPLES)
+        d.colored_base = None if light else colored_noise_base(gauss, d.colored_f_decay)
     # gain
     if rng.random() < cfg.gain_prob:
         d.gain_apply = True

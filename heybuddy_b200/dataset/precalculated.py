@@ -1,0 +1,130 @@
+"""
+``PrecalculatedDatasetIterator`` -- the ``.npy`` memmap store of precomputed ``[N, 16, 96]`` embeddings
+(reference ``heybuddy/dataset/precalculated.py:365-574``).
+
+Same on-disk format (``np.save`` v1.0, C order, ``<f4``; ``np.load(mmap_mode="r")``), same ``take(n)`` with a
+shuffled index and wrap-around reshuffle, ``from_array``, ``metadata``, ``__len__``.  Fixed on purpose:
+``from_array(..., directory=X)`` re-opens from X (the reference re-opens from the default directory,
+precalculated.py:482-491), index bookkeeping is guarded by the lock the reference declares but never takes
+(``take`` is called from many batcher threads), shuffling is seedable.  The hosted multi-GB negative sets and
+the BERT-token ``exclude_phrase`` filter need network downloads and are outside the hot path.
+"""
+from __future__ import annotations
+
+import os
+from threading import Lock
+from typing import Any, Dict, Iterator, Optional
+
+import numpy as np
+
+__all__ = ["PrecalculatedDatasetIterator", "LOCAL_DIR", "open_shared_memmap"]
+
+LOCAL_DIR = os.environ.get(
+    "HEYBUDDY_B200_PRECALCULATED_DIR",
+    os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "precalculated")),
+)
+
+
+def open_shared_memmap(path: str, shape, rank: int = 0, barrier=None, dtype=np.float32) -> np.memmap:
+    """
+    A pre-sized ``.npy`` every rank writes its own row range into: rank 0 creates it
+    (``np.lib.format.open_memmap(mode="w+")``), everybody else opens it ``r+`` after the barrier.
+    """
+    if rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        mm = np.lib.format.open_memmap(path, mode="w+", dtype=dtype, shape=tuple(shape))
+        mm.flush()
+    if barrier is not None:
+        barrier()
+    if rank != 0:
+        mm = np.lib.format.open_memmap(path, mode="r+")
+        assert tuple(mm.shape) == tuple(shape), (mm.shape, shape)
+    return mm
+
+
+class PrecalculatedDatasetIterator:
+    """An extensible dataset iterator over precalculated features."""
+
+    def __init__(self, name: str, directory: Optional[str] = None, exclude_phrase: Optional[str] = None, ordered: bool = False,
+                 labeled: bool = False, use_mem_map: bool = True, shuffle: bool = True, data: Optional[np.ndarray] = None,
+                 seed: Optional[int] = None) -> None:
+        self.lock = Lock()
+        self.directory = directory or LOCAL_DIR
+        self.name = name
+        if exclude_phrase is not None:
+            raise NotImplementedError("exclude_phrase needs the hub BERT tokenizer (outside the hot path)")
+        self.exclude_phrase = exclude_phrase
+        self.index = 0
+        self.total_taken = 0
+        self.ordered = ordered
+        self.labeled = labeled
+        self.use_mem_map = use_mem_map
+        self._rng = np.random.default_rng(seed)
+        if data is not None:
+            self._precalculated = data
+        if not os.path.exists(self.precalculated_path):
+            raise FileNotFoundError(f"Could not find precalculated features at {self.precalculated_path}.")
+        if shuffle and not ordered:
+            self.shuffle()
+
+    @property
+    def precalculated_path(self) -> str:
+        return os.path.join(self.directory, f"{self.name}.npy")
+
+    @property
+    def precalculated(self) -> np.ndarray:
+        if not hasattr(self, "_precalculated"):
+            self._precalculated = np.load(self.precalculated_path, **({"mmap_mode": "r"} if self.use_mem_map else {}))
+        return self._precalculated
+
+    @property
+    def indexes(self) -> np.ndarray:
+        if not hasattr(self, "_indexes"):
+            self._indexes = np.arange(len(self.precalculated))
+        return self._indexes
+
+    @classmethod
+    def from_array(cls, array: np.ndarray, name: str, directory: Optional[str] = None, ordered: bool = False,
+                   keep_in_memory: bool = False, **kwargs: Any) -> "PrecalculatedDatasetIterator":
+        """Saves the features to ``<directory>/<name>.npy`` and opens them."""
+        directory = directory or LOCAL_DIR
+        os.makedirs(directory, exist_ok=True)
+        np.save(os.path.join(directory, f"{name}.npy"), array)
+        return cls(name, directory=directory, data=array if keep_in_memory else None, ordered=ordered, **kwargs)
+
+    def shuffle(self) -> "PrecalculatedDatasetIterator":
+        if not self.ordered:
+            self._rng.shuffle(self.indexes)
+        return self
+
+    def take(self, n: int) -> np.ndarray:
+        """The next ``n`` samples -> ``[n, 16, 96]``; wraps around with a reshuffle (precalculated.py:501-536)."""
+        with self.lock:
+            batch = self.precalculated[self.indexes[self.index:self.index + n]]
+            if batch.shape[0] < n:
+                self.index = n - batch.shape[0]
+                self.shuffle()
+                batch = np.concatenate([batch, self.precalculated[self.indexes[:self.index]]])
+            else:
+                self.index += n
+            if self.labeled:
+                batch = batch[:, :-1]
+            self.total_taken += n
+        return np.asarray(batch)
+
+    def iterate(self) -> Iterator[np.ndarray]:
+        while True:
+            yield self.take(1)
+
+    def metadata(self) -> Dict[str, Any]:
+        return {"name": self.name, "path": self.precalculated_path, "shape": self.precalculated.shape,
+                "ordered": self.ordered, "labeled": self.labeled, "use_mem_map": self.use_mem_map}
+
+    def __len__(self) -> int:
+        return int(self.precalculated.shape[0])
+
+    def __iter__(self) -> Iterator[np.ndarray]:
+        return self.iterate()
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(num_samples={len(self)})"

@@ -1,0 +1,122 @@
+"""GPU: TrainingFeaturesGenerator / FeaturizePipeline end to end vs the oracle, caching, and rank sharding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from heybuddy_b200 import spec
+from oracle import augment as oaug
+from oracle import embed as oembed
+from oracle import mel as omel
+from oracle import pipeline as opipe
+
+pytestmark = pytest.mark.gpu
+
+
+def _banks(rng):
+    noise = (rng.standard_normal((40, 30000)) * 0.2).astype(np.float32)
+    rirs = []
+    for _ in range(6):
+        ln = int(rng.integers(3200, 24000))
+        r = np.exp(-np.arange(ln) / rng.uniform(300, 3000)) * rng.standard_normal(ln)
+        r[int(rng.integers(0, 200))] = 4.0
+        rirs.append(r.astype(np.float32))
+    return noise, rirs
+
+
+def test_reference_shape_contract(cuda_device):
+    """tests/test_feature_generator.py:4-10 of the reference: TrainingFeaturesGenerator()(1).shape == (1, 16, 96)."""
+    from heybuddy_b200.dataset.features import TrainingFeaturesGenerator
+
+    samples = TrainingFeaturesGenerator()(1)
+    assert samples.shape == (1, 16, 96) and samples.dtype == np.float32 and np.isfinite(samples).all()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("f16", 4e-3)])
+def test_generator_matches_oracle_pipeline(cuda_device, precision, tol):
+    """Augment -> mel -> embed through the public generator vs the oracle run with the same draw table."""
+    from heybuddy_b200.dataset.draws import DrawTable
+    from heybuddy_b200.dataset.features import SyntheticSpeechSource, TrainingFeaturesGenerator
+
+    rng = np.random.default_rng(3)
+    noise, rirs = _banks(rng)
+    gen = TrainingFeaturesGenerator(device_id=0, use_autoconfigure=False, augment_batch_size=8, augment_background_dataset=noise,
+                                    augment_impulse_dataset=rirs, precision=precision, seed=2004, source=SyntheticSpeechSource(9))
+    got = gen(40)
+    assert got.shape == (40, 16, 96)
+    # oracle: same clips, same table
+    pipe, aug = gen._pipeline(True)
+    clips = SyntheticSpeechSource(9)(40)
+    table = DrawTable.build([c.shape[0] for c in clips], aug.cfg, 2004, aug.noise_bank.clip_lengths, len(aug.rir_bank))
+    stream = aug.noise_bank.stream.cpu().numpy()
+    audio, i0 = [], 0
+    for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
+        b = len(d.pad_before)
+        fixed = np.stack([oaug.to_target_length(c, int(p)) for c, p in zip(clips[i0:i0 + b], d.pad_before)])
+        off = aug.noise_bank.offset_of_clip(ncur) if d.background_apply else 0
+        audio.append(oaug.augment_batch(
+            fixed, colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
+            gain_db=d.gain_db if d.gain_apply else None,
+            noise=stream[off:off + b * spec.CLIP_SAMPLES].reshape(b, -1) if d.background_apply else None, noise_snr_db=d.noise_snr_db,
+            rir=aug.rir_bank.kernels_host[ridx] if d.reverb_apply else None))
+        i0 += b
+    weights = spec.init_embedding_weights()
+    want = opipe.speech_embeddings([a for a in np.concatenate(audio)], omel.mel_spectrogram,
+                                   lambda w: oembed.speech_embedding_model(w, weights, dtype=torch.float64))
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err < tol, err
+
+
+def test_sharding_is_world_size_independent(cuda_device, tmp_path):
+    """Two ranks writing their row ranges of one .npy give bit-identical rows to a single-rank run."""
+    from heybuddy_b200.dataset.features import TrainingFeaturesGenerator
+    from heybuddy_b200.dataset.precalculated import PrecalculatedDatasetIterator
+
+    rng = np.random.default_rng(4)
+    noise, rirs = _banks(rng)
+    kw = dict(device_id=0, use_autoconfigure=False, augment_batch_size=16, augment_background_dataset=noise,
+              augment_impulse_dataset=rirs, seed=77, sample_batch_size=32)
+    single = TrainingFeaturesGenerator(**kw)(100)
+    path = str(tmp_path / "hello_world.npy")
+    ranges = []
+    for rank in (0, 1):  # rank 0 creates the file; ranks run one after the other here, concurrently under torchrun
+        ranges.append(TrainingFeaturesGenerator(rank=rank, world_size=2, **kw).generate_sharded(100, path))
+    assert ranges == [(0, 64), (64, 100)]
+    sharded = np.load(path, mmap_mode="r")
+    np.testing.assert_array_equal(np.asarray(sharded), single)
+    it = PrecalculatedDatasetIterator("hello_world", directory=str(tmp_path))
+    assert it.take(3).shape == (3, 16, 96)
+
+
+def test_cache_reuse_and_extend(cuda_device, tmp_path):
+    """features.py:686-760: enough cached rows -> reused; fewer -> the missing rows are generated and the file rewritten."""
+    from heybuddy_b200.dataset.features import TrainingFeaturesGenerator
+    from heybuddy_b200.dataset.training import WakeWordTrainingDatasetIterator
+
+    kw = dict(directory=str(tmp_path), device_id=0, use_autoconfigure=False, augment_batch_size=8)
+    pos, adv = TrainingFeaturesGenerator.get_training_features("Hello World", 24, 16, **kw)
+    assert sorted(os.listdir(tmp_path)) == ["hello_world.npy", "hello_world_adv.npy"]
+    assert len(pos) == 24 and len(adv) == 16
+    first = np.asarray(pos.precalculated).copy()
+    mtime = os.path.getmtime(tmp_path / "hello_world.npy")
+    pos2, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 16, 16, **kw)
+    assert len(pos2) == 24 and os.path.getmtime(tmp_path / "hello_world.npy") == mtime
+    pos3, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 40, 16, **kw)
+    assert len(pos3) == 40
+    np.testing.assert_array_equal(np.asarray(pos3.precalculated)[:24], first)
+    val = TrainingFeaturesGenerator.get_validation_features("Hello World", 8, **kw)
+    assert len(val) == 8 and os.path.exists(tmp_path / "hello_world_val.npy")
+    tst, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 8, 8, testing=True, **kw)
+    assert os.path.exists(tmp_path / "hello_world_tst.npy") and os.path.exists(tmp_path / "hello_world_tst_adv.npy")
+    # the training-dataset iterator on top (tests/test_training_dataset_generator.py of the reference)
+    tr = WakeWordTrainingDatasetIterator.default("Hello World", num_positive_samples=24, num_adversarial_samples=16, positive_per_batch=4,
+                                                 adversarial_per_batch=4, num_batch_threads=2, **kw)
+    seen = 0
+    for i, (x, y) in enumerate(tr):
+        assert tuple(x.shape) == (8, 16, 96) and y.tolist() == [1, 1, 1, 1, 0, 0, 0, 0]
+        seen += 1
+        if i > 12:
+            break
+    tr.stop()
+    assert seen > 12
