@@ -295,7 +295,8 @@ class TrainingFeaturesGenerator:
     # -- reference classmethods ----------------------------------------------------------------------------------
     @classmethod
     def default(cls, wake_phrase: str, adversarial: bool = False, **kwargs: Any) -> "TrainingFeaturesGenerator":
-        return cls(use_autoconfigure=True, tts_text=wake_phrase, tts_adversarial=adversarial, **kwargs)
+        kwargs.setdefault("use_autoconfigure", True)
+        return cls(tts_text=wake_phrase, tts_adversarial=adversarial, **kwargs)
 
     @classmethod
     def get_wake_phrase_file_name(cls, wake_phrase: str, testing: bool = False) -> str:
