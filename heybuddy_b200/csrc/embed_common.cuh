@@ -43,6 +43,8 @@ namespace hb {
 int64_t fp32_workspace_bytes(int B, int F);
 int fp32_tail_from_l15(const hb_embed_model* m, const float* pre_pool, int B, int T15, const int32_t* slot_offsets_host,
                        int n_slots, float* out, float* scratch, int64_t scratch_floats, cudaStream_t st);
+int fp32_gather_slots(const float* tmp0, const float* tmp1, int J0, int J1, const int* slot_m_dev, int n_slots, float* out, int B,
+                      cudaStream_t st);
 int fp32_pool_public(const float* x, float* y, int n, int T, int F, int C, int pt, int pf, int phase, cudaStream_t st);
 // embed_tc.cu
 int tc_prepare(hb_embed_model* m, const float* weights_host);

@@ -240,6 +240,16 @@ int fp32_tail_from_l15(const hb_embed_model* m, const float* pre_pool, int B, in
     return HB_OK;
 }
 
+int fp32_gather_slots(const float* tmp0, const float* tmp1, int J0, int J1, const int* slot_m_dev, int n_slots, float* out, int B,
+                      cudaStream_t st) {
+    const int64_t total = (int64_t)B * n_slots * kEmbDim;
+    if (total <= 0) return HB_OK;
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
+    gather_slots_kernel<<<blocks, 256, 0, st>>>(tmp0, tmp1, J0, J1, slot_m_dev, n_slots, out, B);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
 int fp32_pool_public(const float* x, float* y, int n, int T, int F, int C, int pt, int pf, int phase, cudaStream_t st) {
     int To, Fo;
     return launch_pool(x, y, n, T, F, C, pt, pf, phase, &To, &Fo, st);

@@ -4,26 +4,28 @@
 // src/python/heybuddy/embeddings.py:32-42).  Layer table: embed_common.cuh / spec.py.
 //
 // Design (DESIGN.md "embedding conv stack"):
-//  * Every conv of blocks 1-4 is 1x3 (freq, SAME) or 3x1 (time, VALID).  With activations stored
-//    position-major -- position q = 1 + row*(F+1) + f, one shared zero pad column per row -- a tap
-//    is a pure shift of the position index (+-1 for freq, +0/S/2S for time, S = F+1), so the
-//    implicit GEMM   D[q, cout] = sum_tap sum_cin X[q + shift(tap), cin] * W[tap, cin, cout]
-//    needs no im2col: the A operand of tap `t` is the SAME shared-memory buffer addressed through a
-//    UMMA descriptor whose start address is moved by shift(t) * 16 bytes.
-//  * Shared-memory layout of an activation buffer: [channel chunk of 8][position][8 x fp16]; in
-//    UMMA terms a K-major, no-swizzle canonical layout: core matrix = 8 positions x 16 B
-//    (contiguous 128 B), SBO = 128 B (next 8 positions), LBO = P_alloc * 16 B (next 8 channels).
-//  * One CTA owns a tile (a clip's time slice, rows independent between clips) and runs the four
-//    convs of a block back to back with the activations ping-ponging between two shared-memory
-//    buffers: M = 128 positions per tcgen05.mma, N = Cout (32/48/80/96; 24 and 72 are zero padded),
-//    K = 16 per instruction (kind::f16, fp16 operands, fp32 accumulation in TMEM).
-//  * Warp roles: warp 0 = MMA issuer (one elected thread) + TMEM allocator, warp 1 = weight loader
-//    (cp.async.bulk of the next layer's pre-packed B operand, double buffered, mbarrier tx-count),
-//    warps 2-9 = epilogue (tcgen05.ld -> +bias -> LeakyReLU -> fp16 -> st.shared into the next
-//    layer's A buffer).  Four TMEM accumulator slots let MMA of tile i+1.. overlap the epilogue of
-//    tile i.  Max-pool + store to global (fp16, chunk-major) closes the block.
-//  * conv2d (Cin = 1) is CUDA-core work fused into block 1's prologue; the last 2x2 pool (two
-//    phases) and block 5 (1.6 % of the MACs) run on the fp32 CUDA-core kernels of embed_fp32.cu.
+//  * Every conv is 1xk (freq) or kx1 (time).  Activations live in shared memory position-major --
+//    position q = 1 + row*(F+1) + f with one shared zero pad column per row -- as
+//    [channel chunk of 8][position][8 x fp16], which is the K-major, no-swizzle canonical UMMA
+//    layout (core matrix = 8 positions x 16 B, SBO = 128 B, LBO = P_alloc*16 B).  A conv tap is a
+//    pure shift of the position index, i.e. a shift of the descriptor start address: no im2col.
+//  * Orientation: D^T[cout, position] = sum_tap W_tap^T[cout, cin] X^T[cin, position + shift].
+//    A = weights (M = 128 rows, cout zero padded / aliased), B = activations with N = 256 positions
+//    per tcgen05.mma (kind::f16, fp16 operands, fp32 accumulation in TMEM).  Measured on B200
+//    (scripts/micro/umma_bench.cu): an SS tcgen05.mma costs max(141, N/2 + 43) cycles whatever M is,
+//    so the small dimension (cout = 24..96) must sit in M and the long one (positions) in N: N = 256
+//    keeps the tensor pipe busy 128 of every 171 cycles, N = cout <= 96 at most 48 of 141.
+//  * One CTA owns a tile (a time slice of one clip, or 6 whole clips for the tail) and runs the block's
+//    convs back to back, activations ping-ponging between two shared-memory buffers, the next layer's
+//    pre-packed weights arriving by cp.async.bulk (mbarrier tx-count) while the current layer computes.
+//  * Warp roles: warp 0 = MMA issuer (warp-uniform loop, one elected lane) + TMEM allocator, warp 1 =
+//    weight loader, warps 2-9 = epilogue.  The accumulator is transposed (lane = channel, column =
+//    position): tcgen05.ld.16x256b hands thread t channel t/4 (+8) x positions 2(t%4), +1, which is
+//    exactly the fragment stmatrix.m8n8.trans wants -> +bias, LeakyReLU, fp16, and one stmatrix writes
+//    8 positions x 8 channels (16 B rows) straight into the next layer's operand buffer.  Two 256-column
+//    TMEM slots overlap the MMAs of tile i+1 with the epilogue of tile i.
+//  * conv2d (Cin = 1) is CUDA-core work fused into block 1's prologue; the last 2x2 max-pool (both
+//    phases) is fused into the tail block's loader; block 5 runs on the same kernel, 6 clips per CTA.
 #include "embed_common.cuh"
 
 #include <vector>
@@ -133,42 +135,65 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// 16 TMEM lanes x 16 fp32 columns (16x256b.x2): thread t gets, for each 8-column group g,
+//   v[4g+0], v[4g+1] = lane (t/4),     columns 8g + 2(t%4), +1
+//   v[4g+2], v[4g+3] = lane (t/4) + 8, same columns          (verified by scripts/micro/ldst_layout.cu)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void stmatrix_x2_trans(uint32_t row_addr, uint32_t a, uint32_t b) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(row_addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void stmatrix_x1_trans(uint32_t row_addr, uint32_t a) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x1.trans.shared.b16 [%0], {%1};" ::"r"(row_addr), "r"(a) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block configuration
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcThreads = 320;   // warp 0 MMA, warp 1 loader, warps 2..9 epilogue
-constexpr int kSlots = 4;         // TMEM accumulator slots
-constexpr int kSlotCols = 96;     // columns per slot (max N)
+constexpr int kSlots = 2;         // TMEM accumulator slots
+constexpr int kTileN = 256;       // positions per tcgen05.mma / accumulator slot columns
 constexpr int kTmemCols = 512;
 constexpr int kMaxTcLayers = 4;
 
 struct TcLayer {
     int cin_chunks;   // padded Cin / 8
-    int n;            // padded Cout
-    int is_time;      // taps shift by S (time conv) instead of 1 (freq conv)
-    int w_bytes;      // packed B operand bytes (3 taps)
+    int n_out;        // padded Cout
+    int ntaps;
+    int tap_rows[3];  // shift in rows (multiples of S)
+    int tap_cols[3];  // shift in positions within the row
+    int leaky;
+    int w_rows;       // rows of one (tap, k chunk) region of the packed A operand (128 = explicit, < 128 = aliased)
+    int w_bytes;      // packed A operand bytes
     int64_t w_off;    // byte offset in the packed weight buffer
     int bias_off;     // float offset in the packed bias buffer
+    signed char chunk_of[4][4];  // output-channel chunk held by (TMEM lane quadrant, octet); -1 = none
 };
 
 struct TcBlockArgs {
-    const void* in;        // block 1: mel f32 [clips][T_in][32]; else fp16 chunk-major [clips][cin_chunks][T_in][F][8]
-    __half* out;           // fp16 chunk-major [clips][out_chunks][T_out][F_out][8]
+    const void* in;        // in_mode 0: mel f32 [clips][in_T][32]; 1/2: fp16 chunk-major [clips][in_chunks][in_T][in_F][8]
+    void* out;             // out_mode 0: fp16 chunk-major [clips][out_chunks][T_out][F_out][8]; 1: f32 [clips][rows_valid][96]
     const unsigned char* w_packed;
     const float* bias_packed;
-    const float* l0_w;     // block 1 only: conv2d kernel f32 [3][24] + bias [24]
-    __half* dbg;           // optional activation dump [tiles][chunks][P_alloc][8]
-    int dbg_layer;         // tc layer index within the block to dump (-1: none; 100: the block-1 conv2d output)
-    int n_clips, T_in, T_out;
-    int F, S;              // input freq bins, S = F + 1
-    int pool_t, pool_f;
-    int tiles_per_clip;    // time tiles per clip
-    int rows_out;          // pre-pool output rows per tile (multiple of pool_t)
-    int Tt;                // input rows per tile = rows_out + 4 (block 1: + 4 as well: two time convs)
-    int n_mt, P_alloc;     // M tiles per layer, allocated positions per chunk
-    int n_layers;
-    int ch_alloc;          // chunks allocated per activation buffer
-    int w_buf_bytes;       // bytes of one weight buffer
+    const float* l0_w;     // in_mode 0: conv2d kernel f32 [3][24] + bias [24]
+    __half* dbg;           // optional activation dump [ctas][chunks][P_alloc][8]
+    int dbg_layer;         // layer index within the block to dump (-1: none; 100: the staged input)
+    int in_mode, out_mode;
+    int n_clips, in_T, in_F, in_chunks;
+    int T_out;             // out_mode 0: pooled rows per clip; out_mode 1: valid rows per clip
+    int F, S;              // freq bins of the block's activations, S = F + 1
+    int pool_t, pool_f, pool_phase;
+    int tiles_per_clip, rows_out, Tt, segs;
+    int n_nt, P_alloc, n_layers, ch_alloc, w_buf_bytes;
     TcLayer layers[kMaxTcLayers];
 };
 
@@ -189,31 +214,33 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool kFirstBlock>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     TcSmemHeader& hdr = *reinterpret_cast<TcSmemHeader*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P_alloc = a.P_alloc;
     const uint32_t chunk_stride = (uint32_t)P_alloc * 16u;               // bytes between channel chunks
-    unsigned char* wbuf0 = smem + ((sizeof(TcSmemHeader) + 127) & ~127);
+    // per-position table: bit 0 = zero this position (pad column / position 0), bits 1.. = output row + 1 (out_mode 1)
+    int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + ((sizeof(TcSmemHeader) + 15) & ~15));
+    unsigned char* wbuf0 = smem + ((sizeof(TcSmemHeader) + 2 * P_alloc + 127 + 16) & ~127);
     unsigned char* wbuf1 = wbuf0 + a.w_buf_bytes;
     unsigned char* act0 = wbuf1 + a.w_buf_bytes + 128;                    // +128: guard for the position -1 read
     unsigned char* act1 = act0 + (size_t)a.ch_alloc * chunk_stride + 128;
-    float* mel_tile = reinterpret_cast<float*>(act1 + (size_t)a.ch_alloc * chunk_stride);  // block 1 only
+    float* mel_tile = reinterpret_cast<float*>(act1 + (size_t)a.ch_alloc * chunk_stride);  // in_mode 0 only
 
-    const int clip = blockIdx.x / a.tiles_per_clip;
-    const int tile = blockIdx.x - clip * a.tiles_per_clip;
-    const int row0_out = tile * a.rows_out;        // first pre-pool output row of this tile (block-local time)
-    const int row0_in = row0_out;                  // convs are top aligned: output row r reads input rows r..r+4
+    int clip0, tile;
+    if (a.segs > 1) { clip0 = blockIdx.x * a.segs; tile = 0; }
+    else { clip0 = blockIdx.x / a.tiles_per_clip; tile = blockIdx.x - clip0 * a.tiles_per_clip; }
+    const int row0 = tile * a.rows_out;            // convs are top aligned: output row r reads input rows r..r+4
     const int S = a.S, F = a.F, Tt = a.Tt;
-    const int P = 1 + Tt * S;
+    const int seg_pos = Tt * S;
+    const int P = 1 + a.segs * seg_pos;
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&hdr.tmem_full[i], 1);
-            mbar_init(&hdr.tmem_empty[i], 4);
+            mbar_init(&hdr.tmem_empty[i], 8);
         }
         mbar_init(&hdr.wbar[0], 1);
         mbar_init(&hdr.wbar[1], 1);
@@ -222,10 +249,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kTmemCols);
     for (int i = tid; i < a.n_layers * 96; i += kTcThreads) {
         const int l = i / 96, c = i - l * 96;
-        hdr.bias[i] = (c < a.layers[l].n) ? a.bias_packed[a.layers[l].bias_off + c] : 0.f;
+        hdr.bias[i] = (c < a.layers[l].n_out) ? a.bias_packed[a.layers[l].bias_off + c] : 0.f;
     }
-    if (kFirstBlock)
+    if (a.in_mode == 0)
         for (int i = tid; i < 3 * 24 + 24; i += kTcThreads) hdr.l0[i] = a.l0_w[i];
+    for (int q = tid; q < P_alloc; q += kTcThreads) {
+        int v = 1;
+        if (q >= 1 && q < P) {
+            const int rem = (q - 1) % seg_pos, seg = (q - 1) / seg_pos;
+            const int r = rem / S, f = rem - r * S;
+            v = (f >= F) ? 1 : 0;
+            if (a.out_mode == 1 && f == 0 && r < a.T_out && clip0 + seg < a.n_clips) v |= (seg * a.T_out + r + 1) << 1;
+        }
+        pos_tab[q] = (int16_t)v;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -238,12 +275,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     }
 
     // ---- stage the input tile into act0 ------------------------------------------------------------------
-    if (kFirstBlock) {
-        // mel rows [row0_in, row0_in + Tt) -> shared (zero beyond the clip), then conv2d (Cin = 1) on CUDA cores
-        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip * a.T_in * kMels;
+    if (a.in_mode == 0) {
+        // mel rows [row0, row0 + Tt) -> shared (zero beyond the clip), then conv2d (Cin = 1) on CUDA cores
+        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip0 * a.in_T * kMels;
         for (int i = tid; i < Tt * kMels; i += kTcThreads) {
             const int r = i / kMels;
-            mel_tile[i] = (row0_in + r < a.T_in) ? __ldg(mel + (int64_t)(row0_in + r) * kMels + (i - r * kMels)) : 0.f;
+            mel_tile[i] = (row0 + r < a.in_T) ? __ldg(mel + (int64_t)(row0 + r) * kMels + (i - r * kMels)) : 0.f;
         }
         __syncthreads();
         for (int q = tid; q < P_alloc; q += kTcThreads) {
@@ -275,13 +312,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
         }
     } else {
         const uint4* in = reinterpret_cast<const uint4*>(a.in);
-        const int cin_chunks = a.layers[0].cin_chunks;
-        for (int i = tid; i < cin_chunks * P_alloc; i += kTcThreads) {
+        const int in_chunks = a.in_chunks;
+        for (int i = tid; i < in_chunks * P_alloc; i += kTcThreads) {
             const int ch = i / P_alloc, q = i - ch * P_alloc;
-            const int r = (q - 1) / S, f = (q - 1) - r * S;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (q >= 1 && q < P && f < F && row0_in + r < a.T_in)
-                v = __ldg(in + (((int64_t)clip * cin_chunks + ch) * a.T_in + row0_in + r) * F + f);
+            if (q >= 1 && q < P) {
+                const int seg = (q - 1) / seg_pos, rem = (q - 1) - seg * seg_pos;
+                const int r = rem / S, f = rem - r * S;
+                const int clip = clip0 + seg;
+                if (f < F && clip < a.n_clips) {
+                    const uint4* base = in + ((int64_t)clip * in_chunks + ch) * a.in_T * a.in_F;
+                    if (a.in_mode == 1) {
+                        if (row0 + r < a.in_T) v = __ldg(base + (int64_t)(row0 + r) * a.in_F + f);
+                    } else {  // 2x2 max-pool with a time phase while loading (the two pool phases feed window offsets 0 / 4 mod 8)
+                        const int tr = 2 * r + a.pool_phase;
+                        if (tr + 1 < a.in_T) {
+                            const uint4 x0 = __ldg(base + (int64_t)tr * a.in_F + 2 * f), x1 = __ldg(base + (int64_t)tr * a.in_F + 2 * f + 1);
+                            const uint4 x2 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f), x3 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f + 1);
+                            const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
+                            const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
+                            const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
+                            __half2 m[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) m[j] = __hmax2_nan(__hmax2_nan(h0[j], h1[j]), __hmax2_nan(h2[j], h3[j]));
+                            v = *reinterpret_cast<uint4*>(m);
+                        }
+                    }
+                }
+            }
             *reinterpret_cast<uint4*>(act0 + ch * chunk_stride + (size_t)q * 16) = v;
         }
     }
@@ -299,37 +358,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     unsigned char* nxt = act1;
     int tile_counter = 0;   // accumulator-slot uses so far (same sequence on the MMA and epilogue sides)
     for (int l = 0; l < a.n_layers; ++l) {
-        const TcLayer L = a.layers[l];
+        const TcLayer& L = a.layers[l];
         unsigned char* wcur = (l & 1) ? wbuf1 : wbuf0;
+        const bool last_f32 = (a.out_mode == 1 && l == a.n_layers - 1);
         if (warp == 0) {
-            // Warp-uniform issue loop: every lane computes the same descriptors (so they live in uniform registers)
-            // and one elected lane issues the tcgen05 instructions.
+            // Warp-uniform issue loop: every lane computes the same descriptors (uniform registers), one elected lane issues.
             mbar_wait(&hdr.wbar[l & 1], (uint32_t)((l >> 1) & 1));
             tc_fence_after();
-            const uint32_t idesc = make_idesc(128, L.n);
-            const uint32_t a_base = smem_u32(cur), b_base = smem_u32(wcur);
+            const uint32_t idesc = make_idesc(128, kTileN);
+            const uint32_t w_base = smem_u32(wcur), x_base = smem_u32(cur);
             const int ksteps = L.cin_chunks / 2;
-            const uint64_t a_hi = make_desc(0, chunk_stride, 128), b_hi = make_desc(0, (uint32_t)L.n * 16, 128);
-            const uint32_t b_tap_stride = (uint32_t)(L.cin_chunks * L.n * 16);
-            const uint32_t b_k_stride = (uint32_t)(2 * L.n * 16);
-            for (int mt = 0; mt < a.n_mt; ++mt) {
-                const int it = tile_counter + mt;
+            const uint32_t w_region = (uint32_t)L.w_rows * 16u;   // bytes of one (tap, k chunk) region = LBO of A
+            const uint64_t a_hi = make_desc(0, w_region, 128), b_hi = make_desc(0, chunk_stride, 128);
+            for (int nt = 0; nt < a.n_nt; ++nt) {
+                const int it = tile_counter + nt;
                 const int slot = it % kSlots;
                 if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kSlotCols);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
                 uint32_t acc = 0;
-                for (int tap = 0; tap < 3; ++tap) {
-                    const int shift = L.is_time ? tap * S : tap - 1;
-                    uint32_t a_addr = a_base + (uint32_t)((mt * 128 + shift) * 16);
-                    uint32_t b_addr = b_base + (uint32_t)tap * b_tap_stride;
+                for (int tap = 0; tap < L.ntaps; ++tap) {
+                    const int shift = L.tap_rows[tap] * S + L.tap_cols[tap];
+                    uint32_t w_addr = w_base + (uint32_t)(tap * L.cin_chunks) * w_region;
+                    uint32_t x_addr = x_base + (uint32_t)((nt * kTileN + shift) * 16);
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-                        const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
+                        const uint64_t ad = a_hi | (uint64_t)((w_addr >> 4) & 0x3FFF);
+                        const uint64_t bd = b_hi | (uint64_t)((x_addr >> 4) & 0x3FFF);
                         if (elect_one()) umma_f16(d_tmem, ad, bd, idesc, acc);
                         acc = 1;
-                        a_addr += 2 * chunk_stride;
-                        b_addr += b_k_stride;
+                        w_addr += 2 * w_region;
+                        x_addr += 2 * chunk_stride;
                     }
                 }
                 if (elect_one()) umma_commit(&hdr.tmem_full[slot]);
@@ -338,40 +396,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
         } else if (warp == 1) {
             // prefetch the next layer's weights into the other buffer (its last readers finished before this layer began)
             if (lane == 0 && l + 1 < a.n_layers) {
-                const TcLayer Ln = a.layers[l + 1];
+                const TcLayer& Ln = a.layers[l + 1];
                 unsigned char* wn = ((l + 1) & 1) ? wbuf1 : wbuf0;
                 mbar_expect_tx(&hdr.wbar[(l + 1) & 1], (uint32_t)Ln.w_bytes);
                 bulk_g2s(wn, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[(l + 1) & 1]);
             }
             __syncwarp();
         } else {
-            const int e = warp - 2;           // 0..7
-            const int group = e >> 2;         // even / odd tiles
-            const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+            const int e = warp - 2;            // 0..7
+            const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+            const int half_n = e >> 2;         // which 128 columns of every 256-column tile
             const float* bias = hdr.bias + l * 96;
-            for (int mt = group; mt < a.n_mt; mt += 2) {
-                const int it = tile_counter + mt;
+            const uint32_t nxt_base = smem_u32(nxt);
+            for (int nt = 0; nt < a.n_nt; ++nt) {
+                const int it = tile_counter + nt;
                 const int slot = it % kSlots;
                 mbar_wait(&hdr.tmem_full[slot], (uint32_t)((it / kSlots) & 1));
                 tc_fence_after();
-                const int q = mt * 128 + quad * 32 + lane;
-                const int r = (q - 1) / S, f = (q - 1) - r * S;
-                const bool is_pad = (q < 1) || (f >= F);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * kSlotCols);
-                unsigned char* dst = nxt + (size_t)q * 16;
-                for (int c0 = 0; c0 < L.n; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)c0, v);
-                    uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float x0 = leaky(v[2 * j] + bias[c0 + 2 * j]);
-                        float x1 = leaky(v[2 * j + 1] + bias[c0 + 2 * j + 1]);
-                        if (is_pad) { x0 = 0.f; x1 = 0.f; }
-                        pk[j] = pack_half2(x0, x1);
+                for (int h = 0; h < 2; ++h) {
+                    const int c0 = L.chunk_of[quad][2 * h], c1 = L.chunk_of[quad][2 * h + 1];
+                    if (c0 < 0 && c1 < 0) continue;
+                    const float b0 = c0 >= 0 ? bias[c0 * 8 + (lane >> 2)] : 0.f;
+                    const float b1 = c1 >= 0 ? bias[c1 * 8 + (lane >> 2)] : 0.f;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + half_n * 128);
+                    for (int g2 = 0; g2 < 8; ++g2) {   // 16 columns per load
+                        float v[8];
+                        tmem_ld_16x256b_x2(taddr + (uint32_t)(g2 * 16), v);
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const int pbase = nt * kTileN + half_n * 128 + g2 * 16 + g * 8;   // first of 8 positions
+                            const int p = pbase + 2 * (lane & 3);
+                            float x00 = v[4 * g + 0] + b0, x01 = v[4 * g + 1] + b0, x10 = v[4 * g + 2] + b1, x11 = v[4 * g + 3] + b1;
+                            if (L.leaky) { x00 = leaky(x00); x01 = leaky(x01); x10 = leaky(x10); x11 = leaky(x11); }
+                            const int t0 = pos_tab[p], t1 = pos_tab[p + 1];
+                            if (!last_f32) {
+                                if (t0 & 1) { x00 = 0.f; x10 = 0.f; }
+                                if (t1 & 1) { x01 = 0.f; x11 = 0.f; }
+                                const uint32_t ra = pack_half2(x00, x01), rb = pack_half2(x10, x11);
+                                // row addresses: lanes 0-7 -> chunk c0, lanes 8-15 -> chunk c1 (position pbase + lane%8)
+                                const int cc = (lane & 8) ? c1 : c0;
+                                const uint32_t addr = nxt_base + (uint32_t)(cc < 0 ? 0 : cc) * chunk_stride + (uint32_t)((pbase + (lane & 7)) * 16);
+                                if (c0 >= 0 && c1 >= 0) stmatrix_x2_trans(addr, ra, rb);
+                                else if (c0 >= 0) stmatrix_x1_trans(addr, ra);
+                                else stmatrix_x1_trans(nxt_base + (uint32_t)c1 * chunk_stride + (uint32_t)((pbase + (lane & 7)) * 16), rb);
+                            } else {
+                                float* o = reinterpret_cast<float*>(a.out);
+                                const int ch_a = c0 * 8 + (lane >> 2), ch_b = c1 * 8 + (lane >> 2);
+                                if (t0 >> 1) {
+                                    const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
+                                    if (c0 >= 0) o[row * kEmbDim + ch_a] = x00;
+                                    if (c1 >= 0) o[row * kEmbDim + ch_b] = x10;
+                                }
+                                if (t1 >> 1) {
+                                    const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
+                                    if (c0 >= 0) o[row * kEmbDim + ch_a] = x01;
+                                    if (c1 >= 0) o[row * kEmbDim + ch_b] = x11;
+                                }
+                            }
+                        }
                     }
-                    *reinterpret_cast<uint4*>(dst + (size_t)(c0 >> 3) * chunk_stride) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(dst + (size_t)((c0 >> 3) + 1) * chunk_stride) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -379,7 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             }
             fence_proxy_async();
         }
-        tile_counter += a.n_mt;
+        tile_counter += a.n_nt;
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -392,11 +476,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     }
 
     // ---- max-pool + store (fp16 chunk-major [clip][chunk][T_out][F_out][8]) -----------------------------------
-    {
-        const int out_chunks = a.layers[a.n_layers - 1].n / 8;
+    if (a.out_mode == 0) {
+        const int out_chunks = a.layers[a.n_layers - 1].n_out / 8;
         const int Fo = F / a.pool_f;
         const int rows_p = a.rows_out / a.pool_t;           // pooled rows this tile produces
-        const int rowp0 = row0_out / a.pool_t;
+        const int rowp0 = row0 / a.pool_t;
         const int total = out_chunks * rows_p * Fo;
         for (int i = tid; i < total; i += kTcThreads) {
             const int ch = i / (rows_p * Fo);
@@ -419,7 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             o.y = *reinterpret_cast<uint32_t*>(&m[1]);
             o.z = *reinterpret_cast<uint32_t*>(&m[2]);
             o.w = *reinterpret_cast<uint32_t*>(&m[3]);
-            reinterpret_cast<uint4*>(a.out)[(((int64_t)clip * out_chunks + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
+            reinterpret_cast<uint4*>(a.out)[(((int64_t)clip0 * out_chunks + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
         }
     }
     __syncthreads();
@@ -441,7 +525,7 @@ __global__ void chunked_to_nhwc_kernel(const __half* __restrict__ in, float* __r
     }
 }
 
-// debug dump [tiles][chunks][P_alloc][8] -> f32 NHWC [clips][T][F][C] keeping rows < rows_valid of every tile
+// debug dump [ctas][chunks][P_alloc][8] -> f32 NHWC [clips][T][F][C] keeping rows < rows_out of every tile
 __global__ void dump_to_nhwc_kernel(const __half* __restrict__ dbg, float* __restrict__ out, int clips, int tiles_per_clip,
                                     int chunks, int P_alloc, int S, int F, int rows_out, int T, int C) {
     const int64_t total = (int64_t)clips * T * F * C;
@@ -466,26 +550,28 @@ __global__ void dump_to_nhwc_kernel(const __half* __restrict__ dbg, float* __res
 struct TcBlockPlan {
     int first_layer;      // conv index of the first tensor-core layer of the block
     int n_layers;
-    int F;                // input freq bins
+    int F;                // freq bins of the block's activations
     int cin_pad;          // padded input channels of the first tc layer
     int c_pad;            // padded channels inside the block
     int c_real;           // real output channels
     int pool_t, pool_f;
-    int rows_out_max;     // pre-pool output rows per tile (upper bound)
+    int rows_out_max;     // pre-pool output rows per tile (upper bound, sized for shared memory)
+    int spread;           // 1: output chunks spread over the four TMEM lane quadrants (explicit 128-row A operand)
 };
-// block 1: conv2d (CUDA cores) + conv2d_1..3;  block 2: conv2d_4..7;  block 3: conv2d_8..11;  block 4: conv2d_12..15 (no pool here)
-static const TcBlockPlan kPlans[4] = {
-    {1, 3, 32, 32, 32, 24, 2, 2, 36},
-    {4, 4, 16, 32, 48, 48, 1, 2, 32},
-    {8, 4, 8, 48, 80, 72, 2, 2, 30},
-    {12, 4, 4, 80, 96, 96, 1, 1, 32},
+// block 1: conv2d (CUDA cores) + conv2d_1..3;  2: conv2d_4..7;  3: conv2d_8..11;  4: conv2d_12..15 (pool deferred);  5: conv2d_16..19
+static const TcBlockPlan kPlans[5] = {
+    {1, 3, 32, 32, 32, 24, 2, 2, 26, 1},
+    {4, 4, 16, 32, 48, 48, 1, 2, 26, 1},
+    {8, 4, 8, 48, 80, 72, 2, 2, 24, 0},
+    {12, 4, 4, 80, 96, 96, 1, 1, 32, 0},
+    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0},
 };
 
 struct TcWeights {
     unsigned char* w_packed = nullptr;
     float* bias_packed = nullptr;
     float* l0 = nullptr;
-    TcLayer layers[16];   // indexed by conv index 1..15
+    TcLayer layers[kNumConv];   // indexed by conv index 1..19
 };
 
 static inline int pad_c(int c) { return c == 24 ? 32 : (c == 72 ? 80 : c); }
@@ -502,30 +588,52 @@ int tc_prepare(hb_embed_model* m, const float* weights_host) {
         b_off[i] = off;
         off += kLayers[i].cout;
     }
-    for (int li = 1; li <= 15; ++li) {
-        const ConvLayer& L = kLayers[li];
-        const int cin_p = pad_c(L.cin), n_p = pad_c(L.cout);
-        TcLayer t;
-        t.cin_chunks = cin_p / 8;
-        t.n = n_p;
-        t.is_time = (L.kh == 3);
-        t.w_bytes = 3 * cin_p * n_p * 2;
-        t.w_off = (int64_t)packed.size() * 2;
-        t.bias_off = (int)bias.size();
-        // B operand, K-major no-swizzle canonical layout: [tap][k chunk][n][8]
-        const float* w = weights_host + w_off[li];  // [kh][kw][cin][cout]; exactly one of kh,kw is 3
-        for (int tap = 0; tap < 3; ++tap)
-            for (int kc = 0; kc < cin_p / 8; ++kc)
-                for (int n = 0; n < n_p; ++n)
-                    for (int j = 0; j < 8; ++j) {
-                        const int ci = kc * 8 + j;
-                        float v = 0.f;
-                        if (ci < L.cin && n < L.cout) v = w[((int64_t)tap * L.cin + ci) * L.cout + n];
-                        packed.push_back(__float2half_rn(v));
+    for (int b = 0; b < 5; ++b) {
+        const TcBlockPlan& p = kPlans[b];
+        for (int li = p.first_layer; li < p.first_layer + p.n_layers; ++li) {
+            const ConvLayer& L = kLayers[li];
+            const int cin_p = pad_c(L.cin), n_p = pad_c(L.cout);
+            TcLayer t;
+            t.cin_chunks = cin_p / 8;
+            t.n_out = n_p;
+            t.ntaps = L.kh * L.kw;
+            for (int tap = 0; tap < 3; ++tap) { t.tap_rows[tap] = 0; t.tap_cols[tap] = 0; }
+            for (int tap = 0; tap < t.ntaps; ++tap) {
+                if (L.kh > 1) t.tap_rows[tap] = tap;                    // time conv, VALID, top aligned
+                else t.tap_cols[tap] = L.same ? tap - L.kw / 2 : tap;   // freq conv: SAME is centred, VALID starts at 0
+            }
+            t.leaky = L.leaky;
+            const int n_chunks = n_p / 8;
+            for (int q = 0; q < 4; ++q)
+                for (int o = 0; o < 4; ++o) t.chunk_of[q][o] = -1;
+            for (int j = 0; j < n_chunks; ++j) {
+                if (p.spread) t.chunk_of[j % 4][j / 4] = (signed char)j;
+                else t.chunk_of[j / 4][j % 4] = (signed char)j;
+            }
+            t.w_rows = p.spread ? 128 : n_p;
+            while ((packed.size() * 2) % 128) packed.push_back(__float2half_rn(0.f));
+            t.w_off = (int64_t)packed.size() * 2;
+            t.bias_off = (int)bias.size();
+            // A operand, K-major no-swizzle canonical layout: [tap][k chunk][row][8 k values]
+            const float* w = weights_host + w_off[li];  // [kh][kw][cin][cout]; tap = kh*kw index
+            for (int tap = 0; tap < t.ntaps; ++tap)
+                for (int kc = 0; kc < cin_p / 8; ++kc)
+                    for (int r = 0; r < t.w_rows; ++r) {
+                        const int chunk = t.chunk_of[r / 32][(r % 32) / 8];
+                        const int co = chunk < 0 ? -1 : chunk * 8 + r % 8;
+                        for (int j = 0; j < 8; ++j) {
+                            const int ci = kc * 8 + j;
+                            float v = 0.f;
+                            if (co >= 0 && co < L.cout && ci < L.cin) v = w[((int64_t)tap * L.cin + ci) * L.cout + co];
+                            packed.push_back(__float2half_rn(v));
+                        }
                     }
-        for (int n = 0; n < n_p; ++n) bias.push_back(n < L.cout ? weights_host[b_off[li] + n] : 0.f);
-        tw->layers[li] = t;
+            t.w_bytes = (int)((int64_t)packed.size() * 2 - t.w_off);
+            for (int n = 0; n < n_p; ++n) bias.push_back(n < L.cout ? weights_host[b_off[li] + n] : 0.f);
+            tw->layers[li] = t;
+        }
     }
+    for (int i = 0; i < 1024; ++i) packed.push_back(__float2half_rn(0.f));  // slack for aliased row reads
     HB_CUDA_OK(cudaMalloc(&tw->w_packed, packed.size() * 2));
     HB_CUDA_OK(cudaMemcpy(tw->w_packed, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     HB_CUDA_OK(cudaMalloc(&tw->bias_packed, bias.size() * sizeof(float)));
@@ -546,14 +654,27 @@ void tc_release(hb_embed_model* m) {
     m->tc = nullptr;
 }
 
-// geometry of one block launch for clips of T_in input rows
+// geometry of one block launch
 struct TcGeom {
-    int T_in, T_pre, T_out;      // input rows, pre-pool output rows (T_in - 4), pooled rows
-    int tiles_per_clip, rows_out, Tt, n_mt, P_alloc, ch_alloc, w_buf_bytes;
+    int T_in, T_pre, T_out;      // input rows, pre-pool output rows, rows the block writes per clip
+    int tiles_per_clip, rows_out, Tt, segs, n_nt, P_alloc, ch_alloc, w_buf_bytes, grid;
     size_t smem;
 };
 
-static TcGeom tc_geometry(int b, int T_in, const TcWeights* tw) {
+static size_t tc_smem_bytes(const TcGeom& g, bool first) {
+    return ((sizeof(TcSmemHeader) + 2 * (size_t)g.P_alloc + 127 + 16) & ~(size_t)127) + 2 * (size_t)g.w_buf_bytes +
+           2 * (128 + (size_t)g.ch_alloc * g.P_alloc * 16) + (first ? (size_t)g.Tt * kMels * sizeof(float) : 0) + 128;
+}
+
+static int tc_w_buf_bytes(int b, const TcWeights* tw) {
+    const TcBlockPlan& p = kPlans[b];
+    int w = 0;
+    for (int l = 0; l < p.n_layers; ++l) w = std::max(w, tw->layers[p.first_layer + l].w_bytes);
+    return (w + 127) & ~127;
+}
+
+// trunk blocks 0..3 for clips of T_in input rows
+static TcGeom tc_geometry(int b, int T_in, int B, const TcWeights* tw) {
     const TcBlockPlan& p = kPlans[b];
     TcGeom g;
     g.T_in = T_in;
@@ -563,24 +684,44 @@ static TcGeom tc_geometry(int b, int T_in, const TcWeights* tw) {
     g.tiles_per_clip = std::max(1, ceil_div(need, p.rows_out_max));
     g.rows_out = ceil_div(ceil_div(need, g.tiles_per_clip), p.pool_t) * p.pool_t;
     g.Tt = g.rows_out + 4;
+    g.segs = 1;
     const int S = p.F + 1;
     const int P = 1 + g.Tt * S;
-    g.n_mt = ceil_div(P, 128);
-    g.P_alloc = g.n_mt * 128 + 2 * S + 8;
+    g.n_nt = ceil_div(P, kTileN);
+    g.P_alloc = g.n_nt * kTileN + 2 * S + 8;
     g.ch_alloc = std::max(p.cin_pad, p.c_pad) / 8;
-    g.w_buf_bytes = 0;
-    for (int l = 0; l < p.n_layers; ++l) g.w_buf_bytes = std::max(g.w_buf_bytes, tw->layers[p.first_layer + l].w_bytes);
-    g.w_buf_bytes = (g.w_buf_bytes + 127) & ~127;
-    g.smem = ((sizeof(TcSmemHeader) + 127) & ~127) + 2 * (size_t)g.w_buf_bytes + 2 * (128 + (size_t)g.ch_alloc * g.P_alloc * 16) +
-             (b == 0 ? (size_t)g.Tt * kMels * sizeof(float) : 0) + 128;
+    g.w_buf_bytes = tc_w_buf_bytes(b, tw);
+    g.grid = B * g.tiles_per_clip;
+    g.smem = tc_smem_bytes(g, b == 0);
     return g;
 }
 
-// per-block global activation sizes (fp16 elements per clip) for F input frames
-static void tc_chain(int F, const TcWeights* tw, TcGeom g[4]) {
+// tail block: pooled rows per clip Tt = T15 / 2, several clips per CTA
+static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
+    const TcBlockPlan& p = kPlans[4];
+    TcGeom g;
+    g.T_in = T15;
+    g.Tt = T15 / 2;
+    g.T_pre = g.Tt - 4;
+    g.T_out = g.T_pre;
+    g.tiles_per_clip = 1;
+    g.rows_out = g.T_out;
+    const int S = p.F + 1;
+    g.segs = std::max(1, (kTileN - 1) / (g.Tt * S));
+    const int P = 1 + g.segs * g.Tt * S;
+    g.n_nt = ceil_div(P, kTileN);
+    g.P_alloc = g.n_nt * kTileN + 2 * S + 8;
+    g.ch_alloc = p.c_pad / 8;
+    g.w_buf_bytes = tc_w_buf_bytes(4, tw);
+    g.grid = ceil_div(B, g.segs);
+    g.smem = tc_smem_bytes(g, false);
+    return g;
+}
+
+static void tc_chain(int F, int B, const TcWeights* tw, TcGeom g[4]) {
     int T = F;
     for (int b = 0; b < 4; ++b) {
-        g[b] = tc_geometry(b, T, tw);
+        g[b] = tc_geometry(b, T, B, tw);
         T = g[b].T_out;
     }
 }
@@ -590,13 +731,29 @@ static int64_t block_out_halves(int b, const TcGeom& g) {
     return (int64_t)(p.c_pad / 8) * g.T_out * (p.F / p.pool_f) * 8;
 }
 
-int64_t tc_workspace_bytes(int B, int F) {
-    // fp16 activations between blocks + f32 conv2d_15 output + tail scratch; bounded generously by the fp32 path's size
-    return fp32_workspace_bytes(B, F);
+static int64_t tc_act_bytes(int B, const TcGeom g[4]) {
+    int64_t max_halves = 0;
+    for (int b = 0; b < 4; ++b) max_halves = std::max(max_halves, block_out_halves(b, g[b]));
+    return ((int64_t)B * max_halves * 2 + 255) & ~255ll;
 }
 
-static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const void* in, __half* out, int B, __half* dbg,
-                        int dbg_layer, cudaStream_t st) {
+int64_t tc_workspace_bytes(int B, int F) {
+    // two fp16 ping-pong activation buffers + two f32 tail outputs + slot table
+    if (F < kEmbWindow || B <= 0) return 4096;
+    TcWeights dummy;   // geometry only needs the per-layer byte counts; recompute them from the layer table
+    for (int b = 0; b < 5; ++b)
+        for (int li = kPlans[b].first_layer; li < kPlans[b].first_layer + kPlans[b].n_layers; ++li) {
+            const ConvLayer& L = kLayers[li];
+            dummy.layers[li].w_bytes = L.kh * L.kw * pad_c(L.cin) * (kPlans[b].spread ? 128 : pad_c(L.cout)) * 2;
+        }
+    TcGeom g[4];
+    tc_chain(F, B, &dummy, g);
+    const int64_t tail_rows = std::max(1, g[3].T_out / 2);
+    return 2 * tc_act_bytes(B, g) + 2 * (((int64_t)B * tail_rows * kEmbDim * 4 + 255) & ~255ll) + 8192;
+}
+
+static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const void* in, void* out, int B, int in_chunks, int in_F,
+                        int pool_phase, __half* dbg, int dbg_layer, cudaStream_t st) {
     const TcWeights* tw = reinterpret_cast<const TcWeights*>(m->tc);
     const TcBlockPlan& p = kPlans[b];
     TcBlockArgs a;
@@ -607,31 +764,36 @@ static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const v
     a.l0_w = tw->l0;
     a.dbg = dbg;
     a.dbg_layer = dbg_layer;
+    a.in_mode = b == 0 ? 0 : (b == 4 ? 2 : 1);
+    a.out_mode = b == 4 ? 1 : 0;
     a.n_clips = B;
-    a.T_in = g.T_in;
+    a.in_T = g.T_in;
+    a.in_F = in_F;
+    a.in_chunks = in_chunks;
     a.T_out = g.T_out;
     a.F = p.F;
     a.S = p.F + 1;
     a.pool_t = p.pool_t;
     a.pool_f = p.pool_f;
+    a.pool_phase = pool_phase;
     a.tiles_per_clip = g.tiles_per_clip;
     a.rows_out = g.rows_out;
     a.Tt = g.Tt;
-    a.n_mt = g.n_mt;
+    a.segs = g.segs;
+    a.n_nt = g.n_nt;
     a.P_alloc = g.P_alloc;
     a.n_layers = p.n_layers;
     a.ch_alloc = g.ch_alloc;
     a.w_buf_bytes = g.w_buf_bytes;
     for (int l = 0; l < p.n_layers; ++l) a.layers[l] = tw->layers[p.first_layer + l];
     HB_REQUIRE(g.smem <= 227 * 1024, "tc block %d needs %zu bytes of shared memory", b, g.smem);
-    const int grid = B * g.tiles_per_clip;
-    if (b == 0) {
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        tc_block_kernel<true><<<grid, kTcThreads, g.smem, st>>>(a);
-    } else {
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        tc_block_kernel<false><<<grid, kTcThreads, g.smem, st>>>(a);
+    HB_REQUIRE(g.P_alloc < 16383 && g.n_nt * kTileN < 32000, "tc block %d: tile too large", b);
+    static size_t configured = 0;
+    if (g.smem > configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = 227 * 1024;
     }
+    tc_block_kernel<<<g.grid, kTcThreads, g.smem, st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }
@@ -649,33 +811,38 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     HB_REQUIRE(tw != nullptr, "tc weights missing");
     HB_REQUIRE(ws_bytes >= tc_workspace_bytes(B, F), "hb_embed: workspace too small");
     TcGeom g[4];
-    tc_chain(F, tw, g);
-    // workspace carve-up: two fp16 ping-pong activation buffers, then f32 pre-pool conv2d_15 output, then tail scratch
-    int64_t max_halves = 0;
-    for (int b = 0; b < 4; ++b) max_halves = std::max(max_halves, block_out_halves(b, g[b]));
-    const int64_t act_bytes = ((int64_t)B * max_halves * 2 + 255) & ~255ll;
+    tc_chain(F, B, tw, g);
+    const int64_t act_bytes = tc_act_bytes(B, g);
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     __half* hA = reinterpret_cast<__half*>(base);
     __half* hB = reinterpret_cast<__half*>(base + act_bytes);
-    float* l15 = reinterpret_cast<float*>(base + 2 * act_bytes);
     const int T15 = g[3].T_out;
-    const int64_t l15_floats = (int64_t)B * T15 * 4 * kEmbDim;
-    float* scratch = l15 + l15_floats;
-    const int64_t scratch_floats = (ws_bytes - 2 * act_bytes) / 4 - l15_floats;
-    HB_REQUIRE(scratch_floats > 0, "hb_embed: workspace too small for the tail");
+    const TcGeom gt = tc_tail_geometry(T15, B, tw);
+    const int64_t tail_bytes = (((int64_t)B * std::max(1, T15 / 2) * kEmbDim * 4) + 255) & ~255ll;
+    float* tmp[2] = {reinterpret_cast<float*>(base + 2 * act_bytes), reinterpret_cast<float*>(base + 2 * act_bytes + tail_bytes)};
+    int* slot_m_dev = reinterpret_cast<int*>(base + 2 * act_bytes + 2 * tail_bytes);
+
+    bool need_phase[2] = {false, false};
+    std::vector<int> slot_m(n_slots);
+    HB_REQUIRE(n_slots <= 1024, "hb_embed_clips: too many slots (%d)", n_slots);
+    const int J[2] = {T15 / 2 - 4, (T15 - 1) / 2 - 4};
+    for (int s = 0; s < n_slots; ++s) {
+        slot_m[s] = slot_offsets_host[s] / 4;
+        const int p = slot_m[s] & 1, j = slot_m[s] >> 1;
+        need_phase[p] = true;
+        HB_REQUIRE(j < J[p], "hb_embed_clips: slot %d (offset %d) beyond the strip (phase %d has %d outputs)", s,
+                   slot_offsets_host[s], p, J[p]);
+    }
+    HB_CUDA_OK(cudaMemcpyAsync(slot_m_dev, slot_m.data(), n_slots * sizeof(int), cudaMemcpyHostToDevice, st));
 
     int rc;
-    if ((rc = launch_block(m, 0, g[0], mel, hA, B, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 1, g[1], hA, hB, B, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 2, g[2], hB, hA, B, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 3, g[3], hA, hB, B, nullptr, -1, st))) return rc;
-    {
-        const int64_t total = l15_floats;
-        const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
-        chunked_to_nhwc_kernel<<<blocks, 256, 0, st>>>(hB, l15, B, 12, T15, 4, kEmbDim);
-        HB_LAUNCHED();
-    }
-    return fp32_tail_from_l15(m, l15, B, T15, slot_offsets_host, n_slots, out, scratch, scratch_floats, st);
+    if ((rc = launch_block(m, 0, g[0], mel, hA, B, 0, kMels, 0, nullptr, -1, st))) return rc;
+    if ((rc = launch_block(m, 1, g[1], hA, hB, B, 4, 16, 0, nullptr, -1, st))) return rc;
+    if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc;
+    if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc;
+    for (int p = 0; p < 2; ++p)
+        if (need_phase[p] && (rc = launch_block(m, 4, gt, hB, tmp[p], B, 12, 4, p, nullptr, -1, st))) return rc;
+    return fp32_gather_slots(tmp[0], tmp[1], gt.T_out, gt.T_out, slot_m_dev, n_slots, out, B, st);
 }
 
 int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, int layer, float* out, int64_t cap,
@@ -686,20 +853,20 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         return HB_ERR_INVALID;
     }
     if (layer > 15) {
-        set_error("hb_embed_activation(f16): layers 16..19 run on the fp32 tail; query them in fp32 mode");
+        set_error("hb_embed_activation(f16): conv2d_16..19 are fused with the slot gather; compare the final embeddings instead");
         return HB_ERR_UNSUPPORTED;
     }
     TcGeom g[4];
-    tc_chain(F, tw, g);
-    int64_t max_halves = 0;
-    for (int b = 0; b < 4; ++b) max_halves = std::max(max_halves, block_out_halves(b, g[b]));
-    const int64_t act_bytes = ((int64_t)B * max_halves * 2 + 255) & ~255ll;
+    tc_chain(F, B, tw, g);
+    const int64_t act_bytes = tc_act_bytes(B, g);
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     __half* bufs[2] = {reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + act_bytes)};
-    __half* dbg = reinterpret_cast<__half*>(base + 2 * act_bytes);
     const int target_block = layer < 4 ? 0 : (layer < 8 ? 1 : (layer < 12 ? 2 : 3));
+    static const int in_chunks[4] = {0, 4, 6, 10}, in_F[4] = {kMels, 16, 8, 4};
     const void* in = mel;
     int which = 0;
+    int64_t result = HB_ERR_INVALID;
+    void* dbg_mem = nullptr;
     for (int b = 0; b <= target_block; ++b) {
         const TcBlockPlan& p = kPlans[b];
         const bool last = (b == target_block);
@@ -707,62 +874,58 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         int dbg_layer = -1;
         if (last && layer != last_layer_of_block) dbg_layer = (layer == 0) ? 100 : layer - p.first_layer;
         if (dbg_layer >= 0) {
-            const int64_t need = (int64_t)B * g[b].tiles_per_clip * g[b].ch_alloc * g[b].P_alloc * 16;
-            if (2 * act_bytes + need > ws_bytes) {
-                set_error("hb_embed_activation(f16): workspace too small for the debug dump");
-                return HB_ERR_INVALID;
-            }
+            const int64_t need = (int64_t)g[b].grid * g[b].ch_alloc * g[b].P_alloc * 16;
+            if (cudaMalloc(&dbg_mem, need) != cudaSuccess) { set_error("hb_embed_activation: debug allocation failed"); return HB_ERR_CUDA; }
         }
-        int rc = launch_block(m, b, g[b], in, bufs[which], B, dbg_layer >= 0 ? dbg : nullptr, dbg_layer, st);
-        if (rc) return rc;
+        int rc = launch_block(m, b, g[b], in, bufs[which], B, in_chunks[b], in_F[b], 0, reinterpret_cast<__half*>(dbg_mem), dbg_layer, st);
+        if (rc) { if (dbg_mem) cudaFree(dbg_mem); return rc; }
         if (last) {
             int T, Fq, C;
             if (dbg_layer >= 0) {
-                // rows valid after this layer: time convs done so far inside the block shrink T
-                int t_convs = 0;
+                int t_convs = 0;   // time convs done so far inside the block shrink the valid rows
                 for (int li = (b == 0 ? 0 : p.first_layer); li <= layer; ++li) t_convs += (kLayers[li].kh == 3);
                 T = g[b].T_in - 2 * t_convs;
                 Fq = p.F;
                 C = kLayers[layer].cout;
                 const int64_t n = (int64_t)B * T * Fq * C;
-                if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
+                if (n > cap) { set_error("hb_embed_activation: output capacity too small"); cudaFree(dbg_mem); return HB_ERR_INVALID; }
                 const int blocks = (int)std::min<int64_t>(ceil_div64(n, 256), 148 * 8);
-                dump_to_nhwc_kernel<<<blocks, 256, 0, st>>>(dbg, out, B, g[b].tiles_per_clip, g[b].ch_alloc, g[b].P_alloc, p.F + 1,
-                                                            Fq, g[b].rows_out, T, C);
-                if (cudaGetLastError() != cudaSuccess) { set_error("dump kernel launch failed"); return HB_ERR_CUDA; }
-                if (cudaStreamSynchronize(st) != cudaSuccess || check_timeout() != HB_OK) return HB_ERR_CUDA;
-                return n;
-            }
-            T = g[b].T_out;
-            Fq = p.F / p.pool_f;
-            C = p.c_real;
-            if (b == 3) {
+                dump_to_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<__half*>(dbg_mem), out, B, g[b].tiles_per_clip, g[b].ch_alloc,
+                                                            g[b].P_alloc, p.F + 1, Fq, g[b].rows_out, T, C);
+                result = n;
+            } else if (b == 3) {
                 // conv2d_15 "after its pool" = 2x2 pool phase 0 of the pre-pool output
+                T = g[b].T_out;
                 const int64_t n_pre = (int64_t)B * T * 4 * kEmbDim;
-                float* pre = reinterpret_cast<float*>(dbg);
-                if (2 * act_bytes + n_pre * 4 > ws_bytes) { set_error("workspace too small"); return HB_ERR_INVALID; }
+                if (cudaMalloc(&dbg_mem, n_pre * 4) != cudaSuccess) { set_error("hb_embed_activation: allocation failed"); return HB_ERR_CUDA; }
+                float* pre = reinterpret_cast<float*>(dbg_mem);
                 const int blocks = (int)std::min<int64_t>(ceil_div64(n_pre, 256), 148 * 8);
                 chunked_to_nhwc_kernel<<<blocks, 256, 0, st>>>(bufs[which], pre, B, 12, T, 4, kEmbDim);
-                const int To = T / 2;
-                const int64_t n = (int64_t)B * To * 2 * kEmbDim;
-                if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
+                const int64_t n = (int64_t)B * (T / 2) * 2 * kEmbDim;
+                if (n > cap) { set_error("hb_embed_activation: output capacity too small"); cudaFree(dbg_mem); return HB_ERR_INVALID; }
                 int rc2 = fp32_pool_public(pre, out, B, T, 4, kEmbDim, 2, 2, 0, st);
-                if (rc2) return rc2;
-                if (cudaStreamSynchronize(st) != cudaSuccess || check_timeout() != HB_OK) return HB_ERR_CUDA;
-                return n;
+                if (rc2) { cudaFree(dbg_mem); return rc2; }
+                result = n;
+            } else {
+                T = g[b].T_out;
+                Fq = p.F / p.pool_f;
+                C = p.c_real;
+                const int64_t n = (int64_t)B * T * Fq * C;
+                if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
+                const int blocks = (int)std::min<int64_t>(ceil_div64(n, 256), 148 * 8);
+                chunked_to_nhwc_kernel<<<blocks, 256, 0, st>>>(bufs[which], out, B, p.c_pad / 8, T, Fq, C);
+                result = n;
             }
-            const int64_t n = (int64_t)B * T * Fq * C;
-            if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
-            const int blocks = (int)std::min<int64_t>(ceil_div64(n, 256), 148 * 8);
-            chunked_to_nhwc_kernel<<<blocks, 256, 0, st>>>(bufs[which], out, B, p.c_pad / 8, T, Fq, C);
-            if (cudaGetLastError() != cudaSuccess) { set_error("convert kernel launch failed"); return HB_ERR_CUDA; }
-            if (cudaStreamSynchronize(st) != cudaSuccess || check_timeout() != HB_OK) return HB_ERR_CUDA;
-            return n;
+            const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+            if (dbg_mem) cudaFree(dbg_mem);
+            if (!ok) { set_error("hb_embed_activation: kernel failed"); return HB_ERR_CUDA; }
+            if (check_timeout() != HB_OK) return HB_ERR_CUDA;
+            return result;
         }
         in = bufs[which];
         which ^= 1;
     }
-    return HB_ERR_INVALID;
+    return result;
 }
 
 }  // namespace hb
