@@ -36,6 +36,8 @@ namespace hb {
 // PTX wrappers (sm_100a)
 // ------------------------------------------------------------------------------------------------
 __device__ unsigned int g_tc_timeout = 0;  // set when a barrier wait gave up (never hang the GPU)
+__device__ long long g_tc_times[8][16];    // phase timestamps of the first 8 CTAs of the last launch (profiling aid)
+#define TC_STAMP(i) do { if (tid == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -84,6 +86,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -149,8 +156,28 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 lanes x 64 columns as two 32-column loads in flight under one wait: eight 8-column groups, v[4g..4g+3] as above.
+// Loads and wait live in ONE asm statement so no consumer can be scheduled before the wait.
+__device__ __forceinline__ void tmem_ld_16x256b_64cols(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr), "r"(taddr + 32u)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void stmatrix_x2_trans(uint32_t row_addr, uint32_t a, uint32_t b) {
     asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(row_addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void stmatrix_x1_trans(uint32_t row_addr, uint32_t a) {
     asm volatile("stmatrix.sync.aligned.m8n8.x1.trans.shared.b16 [%0], {%1};" ::"r"(row_addr), "r"(a) : "memory");
@@ -159,7 +186,8 @@ __device__ __forceinline__ void stmatrix_x1_trans(uint32_t row_addr, uint32_t a)
 // ------------------------------------------------------------------------------------------------
 // Block configuration
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 320;   // warp 0 MMA, warp 1 loader, warps 2..9 epilogue
+constexpr int kTcThreads = 576;   // warp 0 MMA, warp 1 loader, warps 2..17 epilogue (4 per TMEM lane quadrant)
+constexpr int kEpiWarps = 16;
 constexpr int kSlots = 2;         // TMEM accumulator slots
 constexpr int kTileN = 256;       // positions per tcgen05.mma / accumulator slot columns
 constexpr int kTmemCols = 512;
@@ -207,7 +235,8 @@ struct TcSmemHeader {
     float l0[3 * 24 + 24 + 8];
 };
 
-__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeaky * v; }
+// LeakyReLU(0.2) as max(v, 0.2 v) (slope < 1); NaN propagates
+__device__ __forceinline__ float leaky(float v) { return fmaxf(v, kLeaky * v); }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -236,11 +265,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     const int seg_pos = Tt * S;
     const int P = 1 + a.segs * seg_pos;
 
+    TC_STAMP(0);
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&hdr.tmem_full[i], 1);
-            mbar_init(&hdr.tmem_empty[i], 8);
+            mbar_init(&hdr.tmem_empty[i], kEpiWarps);
         }
         mbar_init(&hdr.wbar[0], 1);
         mbar_init(&hdr.wbar[1], 1);
@@ -267,6 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr.tmem_base;
+    TC_STAMP(1);
 
     // first layer's weights start streaming while the input tile is staged
     if (warp == 1 && lane == 0) {
@@ -283,34 +314,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             mel_tile[i] = (row0 + r < a.in_T) ? __ldg(mel + (int64_t)(row0 + r) * kMels + (i - r * kMels)) : 0.f;
         }
         __syncthreads();
-        for (int q = tid; q < P_alloc; q += kTcThreads) {
-            const int r = (q - 1) / S, f = (q - 1) - r * S;
-            const bool real = q >= 1 && q < P && f < F;
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-            if (real) {
-                m1 = mel_tile[r * kMels + f];
-                m0 = f > 0 ? mel_tile[r * kMels + f - 1] : 0.f;
-                m2 = f < F - 1 ? mel_tile[r * kMels + f + 1] : 0.f;
-            }
+        // thread -> one 8-channel chunk (its 24 weights + 8 biases live in registers) of every 80th position
+        {
+            const int ch = tid & 3, q0 = tid >> 2;
+            float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch * 8 + j;
+                w0[j] = ch < 3 ? hdr.l0[c] : 0.f;
+                w1[j] = ch < 3 ? hdr.l0[24 + c] : 0.f;
+                w2[j] = ch < 3 ? hdr.l0[48 + c] : 0.f;
+                bb[j] = ch < 3 ? hdr.l0[72 + c] : 0.f;
+            }
+            for (int q = q0; q < P_alloc; q += kTcThreads / 4) {
+                const int r = (q - 1) / S, f = (q - 1) - r * S;
+                const bool real = q >= 1 && q < P && f < F && ch < 3;
                 uint4 pk = make_uint4(0, 0, 0, 0);
-                if (real && ch < 3) {
+                if (real) {
+                    const float m1 = mel_tile[r * kMels + f];
+                    const float m0 = f > 0 ? mel_tile[r * kMels + f - 1] : 0.f;
+                    const float m2 = f < F - 1 ? mel_tile[r * kMels + f + 1] : 0.f;
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int c = ch * 8 + j;
-                        float acc = fmaf(m0, hdr.l0[c], 0.f);
-                        acc = fmaf(m1, hdr.l0[24 + c], acc);
-                        acc = fmaf(m2, hdr.l0[48 + c], acc);
-                        v[j] = leaky(acc + hdr.l0[72 + c]);
+                        float acc = fmaf(m0, w0[j], 0.f);
+                        acc = fmaf(m1, w1[j], acc);
+                        acc = fmaf(m2, w2[j], acc);
+                        v[j] = leaky(acc + bb[j]);
                     }
                     pk = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
                 }
                 *reinterpret_cast<uint4*>(act0 + ch * chunk_stride + (size_t)q * 16) = pk;
             }
         }
+    } else if (a.in_mode == 1) {
+        // plain chunk-major copy: every 16-byte position record goes global -> shared with cp.async (no register
+        // round trip, all copies of the tile in flight at once); pads / rows beyond the clip are zero-filled
+        const uint4* in = reinterpret_cast<const uint4*>(a.in) + (int64_t)clip0 * a.in_chunks * a.in_T * a.in_F;
+        const int total = a.in_chunks * P_alloc;
+        int ch = tid / P_alloc, q = tid - ch * P_alloc;           // running (chunk, position) of this thread
+        const int dch = kTcThreads / P_alloc, dq = kTcThreads - dch * P_alloc;
+        for (int i = tid; i < total; i += kTcThreads) {
+            const int r = (q - 1) / S, f = (q - 1) - r * S;
+            const bool real = q >= 1 && q < P && f < F && row0 + r < a.in_T;
+            const uint4* src = real ? in + ((int64_t)ch * a.in_T + row0 + r) * a.in_F + f : in;
+            cp_async16(act0 + ch * chunk_stride + (size_t)q * 16, src, real ? 16u : 0u);
+            q += dq; ch += dch;
+            if (q >= P_alloc) { q -= P_alloc; ++ch; }
+        }
+        cp_async_wait_all();
     } else {
+        // tail: 2x2 max-pool with a time phase while loading (the two pool phases feed window offsets 0 / 4 mod 8)
         const uint4* in = reinterpret_cast<const uint4*>(a.in);
         const int in_chunks = a.in_chunks;
         for (int i = tid; i < in_chunks * P_alloc; i += kTcThreads) {
@@ -320,25 +374,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 const int seg = (q - 1) / seg_pos, rem = (q - 1) - seg * seg_pos;
                 const int r = rem / S, f = rem - r * S;
                 const int clip = clip0 + seg;
-                if (f < F && clip < a.n_clips) {
+                const int tr = 2 * r + a.pool_phase;
+                if (f < F && clip < a.n_clips && tr + 1 < a.in_T) {
                     const uint4* base = in + ((int64_t)clip * in_chunks + ch) * a.in_T * a.in_F;
-                    if (a.in_mode == 1) {
-                        if (row0 + r < a.in_T) v = __ldg(base + (int64_t)(row0 + r) * a.in_F + f);
-                    } else {  // 2x2 max-pool with a time phase while loading (the two pool phases feed window offsets 0 / 4 mod 8)
-                        const int tr = 2 * r + a.pool_phase;
-                        if (tr + 1 < a.in_T) {
-                            const uint4 x0 = __ldg(base + (int64_t)tr * a.in_F + 2 * f), x1 = __ldg(base + (int64_t)tr * a.in_F + 2 * f + 1);
-                            const uint4 x2 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f), x3 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f + 1);
-                            const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
-                            const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
-                            const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
-                            __half2 m[4];
+                    const uint4 x0 = __ldg(base + (int64_t)tr * a.in_F + 2 * f), x1 = __ldg(base + (int64_t)tr * a.in_F + 2 * f + 1);
+                    const uint4 x2 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f), x3 = __ldg(base + (int64_t)(tr + 1) * a.in_F + 2 * f + 1);
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
+                    const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
+                    __half2 m[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) m[j] = __hmax2_nan(__hmax2_nan(h0[j], h1[j]), __hmax2_nan(h2[j], h3[j]));
-                            v = *reinterpret_cast<uint4*>(m);
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j) m[j] = __hmax2_nan(__hmax2_nan(h0[j], h1[j]), __hmax2_nan(h2[j], h3[j]));
+                    v = *reinterpret_cast<uint4*>(m);
                 }
             }
             *reinterpret_cast<uint4*>(act0 + ch * chunk_stride + (size_t)q * 16) = v;
@@ -352,11 +400,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
+    TC_STAMP(2);
 
     // ---- the block's tensor-core layers ---------------------------------------------------------------------
     unsigned char* cur = act0;
     unsigned char* nxt = act1;
     int tile_counter = 0;   // accumulator-slot uses so far (same sequence on the MMA and epilogue sides)
+    long long prof_wait = 0, prof_work = 0;   // profiling aid (first 8 CTAs): epilogue warp 2 / MMA warp 0
     for (int l = 0; l < a.n_layers; ++l) {
         const TcLayer& L = a.layers[l];
         unsigned char* wcur = (l & 1) ? wbuf1 : wbuf0;
@@ -365,6 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             // Warp-uniform issue loop: every lane computes the same descriptors (uniform registers), one elected lane issues.
             mbar_wait(&hdr.wbar[l & 1], (uint32_t)((l >> 1) & 1));
             tc_fence_after();
+            const long long ti0 = clock64();
             const uint32_t idesc = make_idesc(128, kTileN);
             const uint32_t w_base = smem_u32(wcur), x_base = smem_u32(cur);
             const int ksteps = L.cin_chunks / 2;
@@ -373,7 +424,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             for (int nt = 0; nt < a.n_nt; ++nt) {
                 const int it = tile_counter + nt;
                 const int slot = it % kSlots;
+                const long long tw0 = clock64();
                 if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
+                prof_wait += clock64() - tw0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
                 uint32_t acc = 0;
@@ -392,6 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 }
                 if (elect_one()) umma_commit(&hdr.tmem_full[slot]);
             }
+            prof_work += clock64() - ti0;
             __syncwarp();
         } else if (warp == 1) {
             // prefetch the next layer's weights into the other buffer (its last readers finished before this layer began)
@@ -403,56 +457,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             }
             __syncwarp();
         } else {
-            const int e = warp - 2;            // 0..7
+            const int e = warp - 2;            // 0..15
             const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-            const int half_n = e >> 2;         // which 128 columns of every 256-column tile
+            const int part = e >> 2;           // which 64 columns of every 256-column tile
             const float* bias = hdr.bias + l * 96;
             const uint32_t nxt_base = smem_u32(nxt);
             for (int nt = 0; nt < a.n_nt; ++nt) {
                 const int it = tile_counter + nt;
                 const int slot = it % kSlots;
+                const long long te0 = clock64();
                 mbar_wait(&hdr.tmem_full[slot], (uint32_t)((it / kSlots) & 1));
+                const long long te1 = clock64();
+                prof_wait += te1 - te0;
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int c0 = L.chunk_of[quad][2 * h], c1 = L.chunk_of[quad][2 * h + 1];
-                    if (c0 < 0 && c1 < 0) continue;
-                    const float b0 = c0 >= 0 ? bias[c0 * 8 + (lane >> 2)] : 0.f;
+                    if (c0 < 0) continue;   // octets are filled in order: c1 >= 0 implies c0 >= 0
+                    const float b0 = bias[c0 * 8 + (lane >> 2)];
                     const float b1 = c1 >= 0 ? bias[c1 * 8 + (lane >> 2)] : 0.f;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + half_n * 128);
-                    for (int g2 = 0; g2 < 8; ++g2) {   // 16 columns per load
-                        float v[8];
-                        tmem_ld_16x256b_x2(taddr + (uint32_t)(g2 * 16), v);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + part * 64);
+                    const int pos0 = nt * kTileN + part * 64;
+                    float v[32];
+                    tmem_ld_16x256b_64cols(taddr, v);
+                    if (!last_f32) {
+                        // stmatrix row addresses.  Two chunks: x4 = [c0 | c1 | c0 (+8 positions) | c1 (+8 positions)], lanes
+                        // 8m..8m+7 address matrix m.  One chunk: x2 = [c0 | c0 (+8 positions)].
+                        const int m = lane >> 3;
+                        const uint32_t row_addr = c1 >= 0
+                            ? nxt_base + (uint32_t)((m & 1) ? c1 : c0) * chunk_stride + (uint32_t)((pos0 + (m >> 1) * 8 + (lane & 7)) * 16)
+                            : nxt_base + (uint32_t)c0 * chunk_stride + (uint32_t)((pos0 + (m & 1) * 8 + (lane & 7)) * 16);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int pbase = nt * kTileN + half_n * 128 + g2 * 16 + g * 8;   // first of 8 positions
-                            const int p = pbase + 2 * (lane & 3);
-                            float x00 = v[4 * g + 0] + b0, x01 = v[4 * g + 1] + b0, x10 = v[4 * g + 2] + b1, x11 = v[4 * g + 3] + b1;
-                            if (L.leaky) { x00 = leaky(x00); x01 = leaky(x01); x10 = leaky(x10); x11 = leaky(x11); }
+                        for (int g = 0; g < 8; g += 2) {   // two 8-position groups per store
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                x[j] = v[4 * g + j] + ((j & 2) ? b1 : b0);
+                                if (L.leaky) x[j] = leaky(x[j]);
+                            }
+                            const uint32_t ra = pack_half2(x[0], x[1]), rb = pack_half2(x[2], x[3]);
+                            const uint32_t rc = pack_half2(x[4], x[5]), rd = pack_half2(x[6], x[7]);
+                            if (c1 >= 0) stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rb, rc, rd);
+                            else stmatrix_x2_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rc);
+                        }
+                    } else {
+                        float* o = reinterpret_cast<float*>(a.out);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const int p = pos0 + g * 8 + 2 * (lane & 3);
                             const int t0 = pos_tab[p], t1 = pos_tab[p + 1];
-                            if (!last_f32) {
-                                if (t0 & 1) { x00 = 0.f; x10 = 0.f; }
-                                if (t1 & 1) { x01 = 0.f; x11 = 0.f; }
-                                const uint32_t ra = pack_half2(x00, x01), rb = pack_half2(x10, x11);
-                                // row addresses: lanes 0-7 -> chunk c0, lanes 8-15 -> chunk c1 (position pbase + lane%8)
-                                const int cc = (lane & 8) ? c1 : c0;
-                                const uint32_t addr = nxt_base + (uint32_t)(cc < 0 ? 0 : cc) * chunk_stride + (uint32_t)((pbase + (lane & 7)) * 16);
-                                if (c0 >= 0 && c1 >= 0) stmatrix_x2_trans(addr, ra, rb);
-                                else if (c0 >= 0) stmatrix_x1_trans(addr, ra);
-                                else stmatrix_x1_trans(nxt_base + (uint32_t)c1 * chunk_stride + (uint32_t)((pbase + (lane & 7)) * 16), rb);
-                            } else {
-                                float* o = reinterpret_cast<float*>(a.out);
-                                const int ch_a = c0 * 8 + (lane >> 2), ch_b = c1 * 8 + (lane >> 2);
-                                if (t0 >> 1) {
-                                    const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
-                                    if (c0 >= 0) o[row * kEmbDim + ch_a] = x00;
-                                    if (c1 >= 0) o[row * kEmbDim + ch_b] = x10;
-                                }
-                                if (t1 >> 1) {
-                                    const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
-                                    if (c0 >= 0) o[row * kEmbDim + ch_a] = x01;
-                                    if (c1 >= 0) o[row * kEmbDim + ch_b] = x11;
-                                }
+                            const int ch_a = c0 * 8 + (lane >> 2), ch_b = c1 * 8 + (lane >> 2);
+                            if (t0 >> 1) {
+                                const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
+                                o[row * kEmbDim + ch_a] = v[4 * g + 0] + b0;
+                                if (c1 >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 2] + b1;
+                            }
+                            if (t1 >> 1) {
+                                const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
+                                o[row * kEmbDim + ch_a] = v[4 * g + 1] + b0;
+                                if (c1 >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 3] + b1;
                             }
                         }
                     }
@@ -460,6 +523,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hdr.tmem_empty[slot]);
+                prof_work += clock64() - te1;
             }
             fence_proxy_async();
         }
@@ -467,12 +531,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        TC_STAMP(3 + 2 * l);
         unsigned char* t = cur; cur = nxt; nxt = t;
+        // The epilogue does not mask the pad column (and position 0): their values only ever feed pad outputs, except
+        // through a conv with column taps (freq SAME padding) -- zero them right before such a layer.
+        if (l + 1 < a.n_layers && (a.layers[l + 1].tap_cols[0] != 0 || a.layers[l + 1].tap_cols[1] != 0 || a.layers[l + 1].tap_cols[2] != 0)) {
+            const int n_pad = a.segs * Tt + 1, chunks = L.n_out / 8;
+            for (int i = tid; i < n_pad * chunks; i += kTcThreads) {
+                const int ch = i / n_pad, k = i - ch * n_pad;
+                const int q = k == 0 ? 0 : k * S;   // position 0, then the pad column 1 + (k-1)*S + F = k*S of every row
+                *reinterpret_cast<uint4*>(cur + (size_t)ch * chunk_stride + (size_t)q * 16) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
         if (a.dbg != nullptr && a.dbg_layer == l) {
             for (int i = tid; i < a.ch_alloc * P_alloc; i += kTcThreads)
                 reinterpret_cast<uint4*>(a.dbg)[(int64_t)blockIdx.x * a.ch_alloc * P_alloc + i] =
                     *reinterpret_cast<const uint4*>(cur + (size_t)(i / P_alloc) * chunk_stride + (size_t)(i % P_alloc) * 16);
         }
+        TC_STAMP(4 + 2 * l);
     }
 
     // ---- max-pool + store (fp16 chunk-major [clip][chunk][T_out][F_out][8]) -----------------------------------
@@ -506,8 +584,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             reinterpret_cast<uint4*>(a.out)[(((int64_t)clip0 * out_chunks + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
         }
     }
+    if (blockIdx.x < 8 && lane == 0) {
+        if (warp == 2) { g_tc_times[blockIdx.x][13] = prof_wait; g_tc_times[blockIdx.x][14] = prof_work; }
+        if (warp == 0) g_tc_times[blockIdx.x][15] = prof_wait;
+    }
     __syncthreads();
+    TC_STAMP(11);
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+    TC_STAMP(12);
 }
 
 // fp16 chunk-major [clips][chunks][T][F][8] -> f32 NHWC [clips][T][F][C] (C real channels <= chunks*8)
@@ -929,3 +1013,8 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
 }
 
 }  // namespace hb
+
+// profiling aid (not part of the public header): phase timestamps of the first 8 CTAs of the last tc block launch
+extern "C" int hb_debug_tc_times(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, hb::g_tc_times, sizeof(long long) * 8 * 16) == cudaSuccess ? 0 : -2;
+}
