@@ -183,12 +183,43 @@ __device__ __forceinline__ void stmatrix_x1_trans(uint32_t row_addr, uint32_t a)
     asm volatile("stmatrix.sync.aligned.m8n8.x1.trans.shared.b16 [%0], {%1};" ::"r"(row_addr), "r"(a) : "memory");
 }
 
+// LeakyReLU(0.2) as max(v, 0.2 v) (slope < 1); NaN propagates
+__device__ __forceinline__ float leaky(float v) { return fmaxf(v, kLeaky * v); }
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Epilogue of one 64-column sub-block of one accumulator tile for one 16-lane half:
+// TMEM (lane = channel, column = position) -> +bias -> LeakyReLU -> fp16 -> stmatrix.trans into the next layer's
+// [chunk][position][8] operand buffer.  kTwo: the half holds two 8-channel chunks (else only octet 0 is real).
+template <bool kTwo, bool kLeaky>
+__device__ __forceinline__ void epilogue_sub(uint32_t taddr, uint32_t row_addr, float b0, float b1) {
+    float v[32];
+    tmem_ld_16x256b_64cols(taddr, v);
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) {   // two 8-position groups per store
+        float x0 = v[4 * g + 0] + b0, x1 = v[4 * g + 1] + b0, x4 = v[4 * g + 4] + b0, x5 = v[4 * g + 5] + b0;
+        if (kLeaky) { x0 = leaky(x0); x1 = leaky(x1); x4 = leaky(x4); x5 = leaky(x5); }
+        const uint32_t ra = pack_half2(x0, x1), rc = pack_half2(x4, x5);
+        if (kTwo) {
+            float x2 = v[4 * g + 2] + b1, x3 = v[4 * g + 3] + b1, x6 = v[4 * g + 6] + b1, x7 = v[4 * g + 7] + b1;
+            if (kLeaky) { x2 = leaky(x2); x3 = leaky(x3); x6 = leaky(x6); x7 = leaky(x7); }
+            stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, pack_half2(x2, x3), rc, pack_half2(x6, x7));
+        } else {
+            stmatrix_x2_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block configuration
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 576;   // warp 0 MMA, warp 1 loader, warps 2..17 epilogue (4 per TMEM lane quadrant)
-constexpr int kEpiWarps = 16;
-constexpr int kSlots = 2;         // TMEM accumulator slots
+// Two launch shapes: "wide"  = 576 threads (16 epilogue warps), 1 CTA/SM, 2 accumulator slots, double-buffered weights;
+//                    "twin"  = 320 threads (8 epilogue warps), 2 CTAs/SM (each 256 TMEM columns, 1 slot, single weight
+//                              buffer) -- the co-resident CTA fills the other's staging / epilogue / store phases.
+constexpr int kMaxSlots = 2;      // TMEM accumulator slots
 constexpr int kTileN = 256;       // positions per tcgen05.mma / accumulator slot columns
 constexpr int kTmemCols = 512;
 constexpr int kMaxTcLayers = 4;
@@ -222,12 +253,13 @@ struct TcBlockArgs {
     int pool_t, pool_f, pool_phase;
     int tiles_per_clip, rows_out, Tt, segs;
     int n_nt, P_alloc, n_layers, ch_alloc, w_buf_bytes;
+    int n_slots, tmem_cols, w_double;   // launch shape (see kMaxSlots)
     TcLayer layers[kMaxTcLayers];
 };
 
 struct TcSmemHeader {
-    uint64_t tmem_full[kSlots];
-    uint64_t tmem_empty[kSlots];
+    uint64_t tmem_full[kMaxSlots];
+    uint64_t tmem_empty[kMaxSlots];
     uint64_t wbar[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -235,15 +267,13 @@ struct TcSmemHeader {
     float l0[3 * 24 + 24 + 8];
 };
 
-// LeakyReLU(0.2) as max(v, 0.2 v) (slope < 1); NaN propagates
-__device__ __forceinline__ float leaky(float v) { return fmaxf(v, kLeaky * v); }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockArgs a) {
+template <int kTcThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const TcBlockArgs a) {
+    constexpr int kEpiWarps = kTcThreads / 32 - 2;   // 8 or 16: kEpiWarps / 4 warps per TMEM lane quadrant
+    constexpr int kColsPerWarp = kTileN / (kEpiWarps / 4);
+    const int kSlots = a.n_slots;
+    const uint32_t kTmemCols = (uint32_t)a.tmem_cols;
     extern __shared__ __align__(128) unsigned char smem[];
     TcSmemHeader& hdr = *reinterpret_cast<TcSmemHeader*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     // per-position table: bit 0 = zero this position (pad column / position 0), bits 1.. = output row + 1 (out_mode 1)
     int16_t* pos_tab = reinterpret_cast<int16_t*>(smem + ((sizeof(TcSmemHeader) + 15) & ~15));
     unsigned char* wbuf0 = smem + ((sizeof(TcSmemHeader) + 2 * P_alloc + 127 + 16) & ~127);
-    unsigned char* wbuf1 = wbuf0 + a.w_buf_bytes;
+    unsigned char* wbuf1 = a.w_double ? wbuf0 + a.w_buf_bytes : wbuf0;
     unsigned char* act0 = wbuf1 + a.w_buf_bytes + 128;                    // +128: guard for the position -1 read
     unsigned char* act1 = act0 + (size_t)a.ch_alloc * chunk_stride + 128;
     float* mel_tile = reinterpret_cast<float*>(act1 + (size_t)a.ch_alloc * chunk_stride);  // in_mode 0 only
@@ -283,15 +313,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     }
     if (a.in_mode == 0)
         for (int i = tid; i < 3 * 24 + 24; i += kTcThreads) hdr.l0[i] = a.l0_w[i];
-    for (int q = tid; q < P_alloc; q += kTcThreads) {
-        int v = 1;
-        if (q >= 1 && q < P) {
-            const int rem = (q - 1) % seg_pos, seg = (q - 1) / seg_pos;
-            const int r = rem / S, f = rem - r * S;
-            v = (f >= F) ? 1 : 0;
-            if (a.out_mode == 1 && f == 0 && r < a.T_out && clip0 + seg < a.n_clips) v |= (seg * a.T_out + r + 1) << 1;
+    if (a.out_mode == 1) {
+        for (int q = tid; q < P_alloc; q += kTcThreads) {
+            int v = 1;
+            if (q >= 1 && q < P) {
+                const int rem = (q - 1) % seg_pos, seg = (q - 1) / seg_pos;
+                const int r = rem / S, f = rem - r * S;
+                v = (f >= F) ? 1 : 0;
+                if (f == 0 && r < a.T_out && clip0 + seg < a.n_clips) v |= (seg * a.T_out + r + 1) << 1;
+            }
+            pos_tab[q] = (int16_t)v;
         }
-        pos_tab[q] = (int16_t)v;
     }
     tc_fence_before();
     __syncthreads();
@@ -314,9 +346,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             mel_tile[i] = (row0 + r < a.in_T) ? __ldg(mel + (int64_t)(row0 + r) * kMels + (i - r * kMels)) : 0.f;
         }
         __syncthreads();
-        // thread -> one 8-channel chunk (its 24 weights + 8 biases live in registers) of every 80th position
+        // lane -> (8-channel chunk = lane & 3, its 24 weights + 8 biases in registers; freq bins (lane >> 2) + 8 j);
+        // warp -> rows.  F == 32 here, so one warp row-pass covers the 32 bins with no index division.
         {
-            const int ch = tid & 3, q0 = tid >> 2;
+            const int ch = lane & 3;
             float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -326,25 +359,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 w2[j] = ch < 3 ? hdr.l0[48 + c] : 0.f;
                 bb[j] = ch < 3 ? hdr.l0[72 + c] : 0.f;
             }
-            for (int q = q0; q < P_alloc; q += kTcThreads / 4) {
-                const int r = (q - 1) / S, f = (q - 1) - r * S;
-                const bool real = q >= 1 && q < P && f < F && ch < 3;
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                if (real) {
-                    const float m1 = mel_tile[r * kMels + f];
-                    const float m0 = f > 0 ? mel_tile[r * kMels + f - 1] : 0.f;
-                    const float m2 = f < F - 1 ? mel_tile[r * kMels + f + 1] : 0.f;
-                    float v[8];
+            unsigned char* dst_ch = act0 + ch * chunk_stride;
+            for (int r = warp; r < Tt; r += kTcThreads / 32) {
+                const float* mrow = mel_tile + r * kMels;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float acc = fmaf(m0, w0[j], 0.f);
-                        acc = fmaf(m1, w1[j], acc);
-                        acc = fmaf(m2, w2[j], acc);
-                        v[j] = leaky(acc + bb[j]);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int f = (lane >> 2) + 8 * j4;
+                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    if (ch < 3) {
+                        const float m1 = mrow[f];
+                        const float m0 = f > 0 ? mrow[f - 1] : 0.f;
+                        const float m2 = f < kMels - 1 ? mrow[f + 1] : 0.f;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float acc = fmaf(m0, w0[j], 0.f);
+                            acc = fmaf(m1, w1[j], acc);
+                            acc = fmaf(m2, w2[j], acc);
+                            v[j] = leaky(acc + bb[j]);
+                        }
+                        pk = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
                     }
-                    pk = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(dst_ch + (size_t)(1 + r * S + f) * 16) = pk;
                 }
-                *reinterpret_cast<uint4*>(act0 + ch * chunk_stride + (size_t)q * 16) = pk;
+            }
+            // position 0, the pad column of every row, and the positions past the tile: zeros
+            for (int i = tid; i < 4 * (Tt + 1 + (P_alloc - P)); i += kTcThreads) {
+                const int c = i & 3, k = i >> 2;
+                const int q = k == 0 ? 0 : (k <= Tt ? k * S : P + (k - Tt - 1));
+                *reinterpret_cast<uint4*>(act0 + c * chunk_stride + (size_t)q * 16) = make_uint4(0, 0, 0, 0);
             }
         }
     } else if (a.in_mode == 1) {
@@ -406,16 +449,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
     unsigned char* cur = act0;
     unsigned char* nxt = act1;
     int tile_counter = 0;   // accumulator-slot uses so far (same sequence on the MMA and epilogue sides)
-    long long prof_wait = 0, prof_work = 0;   // profiling aid (first 8 CTAs): epilogue warp 2 / MMA warp 0
     for (int l = 0; l < a.n_layers; ++l) {
         const TcLayer& L = a.layers[l];
         unsigned char* wcur = (l & 1) ? wbuf1 : wbuf0;
+        const int wb = a.w_double ? (l & 1) : 0;                        // barrier of this layer's weight buffer
+        const uint32_t wpar = a.w_double ? (uint32_t)((l >> 1) & 1) : (uint32_t)(l & 1);
         const bool last_f32 = (a.out_mode == 1 && l == a.n_layers - 1);
         if (warp == 0) {
             // Warp-uniform issue loop: every lane computes the same descriptors (uniform registers), one elected lane issues.
-            mbar_wait(&hdr.wbar[l & 1], (uint32_t)((l >> 1) & 1));
+            mbar_wait(&hdr.wbar[wb], wpar);
             tc_fence_after();
-            const long long ti0 = clock64();
             const uint32_t idesc = make_idesc(128, kTileN);
             const uint32_t w_base = smem_u32(wcur), x_base = smem_u32(cur);
             const int ksteps = L.cin_chunks / 2;
@@ -424,9 +467,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             for (int nt = 0; nt < a.n_nt; ++nt) {
                 const int it = tile_counter + nt;
                 const int slot = it % kSlots;
-                const long long tw0 = clock64();
                 if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
-                prof_wait += clock64() - tw0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
                 uint32_t acc = 0;
@@ -445,11 +486,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 }
                 if (elect_one()) umma_commit(&hdr.tmem_full[slot]);
             }
-            prof_work += clock64() - ti0;
             __syncwarp();
         } else if (warp == 1) {
             // prefetch the next layer's weights into the other buffer (its last readers finished before this layer began)
-            if (lane == 0 && l + 1 < a.n_layers) {
+            if (lane == 0 && l + 1 < a.n_layers && a.w_double) {
                 const TcLayer& Ln = a.layers[l + 1];
                 unsigned char* wn = ((l + 1) & 1) ? wbuf1 : wbuf0;
                 mbar_expect_tx(&hdr.wbar[(l + 1) & 1], (uint32_t)Ln.w_bytes);
@@ -457,65 +497,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             }
             __syncwarp();
         } else {
-            const int e = warp - 2;            // 0..15
+            const int e = warp - 2;            // 0..kEpiWarps-1
             const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-            const int part = e >> 2;           // which 64 columns of every 256-column tile
+            const int part = e >> 2;           // which kColsPerWarp columns of every 256-column tile
             const float* bias = hdr.bias + l * 96;
             const uint32_t nxt_base = smem_u32(nxt);
+            // per-layer invariants of this warp: chunks held by its two 16-lane halves, their biases, stmatrix row addresses
+            int c0[2], c1[2];
+            float bb0[2], bb1[2];
+            uint32_t rows[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                c0[h] = L.chunk_of[quad][2 * h];
+                c1[h] = L.chunk_of[quad][2 * h + 1];
+                bb0[h] = c0[h] >= 0 ? bias[c0[h] * 8 + (lane >> 2)] : 0.f;
+                bb1[h] = c1[h] >= 0 ? bias[c1[h] * 8 + (lane >> 2)] : 0.f;
+                // Two chunks: x4 = [c0 | c1 | c0 (+8 positions) | c1 (+8 positions)], lanes 8m..8m+7 address matrix m.
+                // One chunk: x2 = [c0 | c0 (+8 positions)].
+                const int m = lane >> 3;
+                rows[h] = c1[h] >= 0
+                    ? nxt_base + (uint32_t)((m & 1) ? c1[h] : c0[h]) * chunk_stride + (uint32_t)(((m >> 1) * 8 + (lane & 7)) * 16)
+                    : nxt_base + (uint32_t)(c0[h] < 0 ? 0 : c0[h]) * chunk_stride + (uint32_t)(((m & 1) * 8 + (lane & 7)) * 16);
+            }
             for (int nt = 0; nt < a.n_nt; ++nt) {
                 const int it = tile_counter + nt;
                 const int slot = it % kSlots;
-                const long long te0 = clock64();
                 mbar_wait(&hdr.tmem_full[slot], (uint32_t)((it / kSlots) & 1));
-                const long long te1 = clock64();
-                prof_wait += te1 - te0;
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int c0 = L.chunk_of[quad][2 * h], c1 = L.chunk_of[quad][2 * h + 1];
-                    if (c0 < 0) continue;   // octets are filled in order: c1 >= 0 implies c0 >= 0
-                    const float b0 = bias[c0 * 8 + (lane >> 2)];
-                    const float b1 = c1 >= 0 ? bias[c1 * 8 + (lane >> 2)] : 0.f;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + part * 64);
-                    const int pos0 = nt * kTileN + part * 64;
-                    float v[32];
-                    tmem_ld_16x256b_64cols(taddr, v);
-                    if (!last_f32) {
-                        // stmatrix row addresses.  Two chunks: x4 = [c0 | c1 | c0 (+8 positions) | c1 (+8 positions)], lanes
-                        // 8m..8m+7 address matrix m.  One chunk: x2 = [c0 | c0 (+8 positions)].
-                        const int m = lane >> 3;
-                        const uint32_t row_addr = c1 >= 0
-                            ? nxt_base + (uint32_t)((m & 1) ? c1 : c0) * chunk_stride + (uint32_t)((pos0 + (m >> 1) * 8 + (lane & 7)) * 16)
-                            : nxt_base + (uint32_t)c0 * chunk_stride + (uint32_t)((pos0 + (m & 1) * 8 + (lane & 7)) * 16);
-#pragma unroll
-                        for (int g = 0; g < 8; g += 2) {   // two 8-position groups per store
-                            float x[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                x[j] = v[4 * g + j] + ((j & 2) ? b1 : b0);
-                                if (L.leaky) x[j] = leaky(x[j]);
+                    if (c0[h] < 0) continue;   // octets are filled in order: c1 >= 0 implies c0 >= 0
+                    for (int sub = 0; sub < kColsPerWarp / 64; ++sub) {
+                        const int col = part * kColsPerWarp + sub * 64;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + col);
+                        const int pos0 = nt * kTileN + col;
+                        if (!last_f32) {
+                            const uint32_t ra = rows[h] + (uint32_t)(pos0 * 16);
+                            if (c1[h] >= 0) {
+                                if (L.leaky) epilogue_sub<true, true>(taddr, ra, bb0[h], bb1[h]);
+                                else epilogue_sub<true, false>(taddr, ra, bb0[h], bb1[h]);
+                            } else {
+                                if (L.leaky) epilogue_sub<false, true>(taddr, ra, bb0[h], bb1[h]);
+                                else epilogue_sub<false, false>(taddr, ra, bb0[h], bb1[h]);
                             }
-                            const uint32_t ra = pack_half2(x[0], x[1]), rb = pack_half2(x[2], x[3]);
-                            const uint32_t rc = pack_half2(x[4], x[5]), rd = pack_half2(x[6], x[7]);
-                            if (c1 >= 0) stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rb, rc, rd);
-                            else stmatrix_x2_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rc);
-                        }
-                    } else {
-                        float* o = reinterpret_cast<float*>(a.out);
+                        } else {
+                            // final layer of the tail: f32 rows [clip][row][96] of the valid positions (no activation)
+                            float v[32];
+                            tmem_ld_16x256b_64cols(taddr, v);
+                            float* o = reinterpret_cast<float*>(a.out);
+                            const int ch_a = c0[h] * 8 + (lane >> 2), ch_b = c1[h] * 8 + (lane >> 2);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const int p = pos0 + g * 8 + 2 * (lane & 3);
-                            const int t0 = pos_tab[p], t1 = pos_tab[p + 1];
-                            const int ch_a = c0 * 8 + (lane >> 2), ch_b = c1 * 8 + (lane >> 2);
-                            if (t0 >> 1) {
-                                const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
-                                o[row * kEmbDim + ch_a] = v[4 * g + 0] + b0;
-                                if (c1 >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 2] + b1;
-                            }
-                            if (t1 >> 1) {
-                                const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
-                                o[row * kEmbDim + ch_a] = v[4 * g + 1] + b0;
-                                if (c1 >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 3] + b1;
+                            for (int g = 0; g < 8; ++g) {
+                                const int p = pos0 + g * 8 + 2 * (lane & 3);
+                                const int t0 = pos_tab[p], t1 = pos_tab[p + 1];
+                                if (t0 >> 1) {
+                                    const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
+                                    o[row * kEmbDim + ch_a] = v[4 * g + 0] + bb0[h];
+                                    if (c1[h] >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 2] + bb1[h];
+                                }
+                                if (t1 >> 1) {
+                                    const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
+                                    o[row * kEmbDim + ch_a] = v[4 * g + 1] + bb0[h];
+                                    if (c1[h] >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 3] + bb1[h];
+                                }
                             }
                         }
                     }
@@ -523,7 +567,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hdr.tmem_empty[slot]);
-                prof_work += clock64() - te1;
             }
             fence_proxy_async();
         }
@@ -532,6 +575,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
         __syncthreads();
         tc_fence_after();
         TC_STAMP(3 + 2 * l);
+        if (!a.w_double && warp == 1 && lane == 0 && l + 1 < a.n_layers) {
+            // single weight buffer: this layer's MMAs are complete (barrier above), refill it for the next layer
+            const TcLayer& Ln = a.layers[l + 1];
+            mbar_expect_tx(&hdr.wbar[0], (uint32_t)Ln.w_bytes);
+            bulk_g2s(wbuf0, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[0]);
+        }
         unsigned char* t = cur; cur = nxt; nxt = t;
         // The epilogue does not mask the pad column (and position 0): their values only ever feed pad outputs, except
         // through a conv with column taps (freq SAME padding) -- zero them right before such a layer.
@@ -583,10 +632,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_block_kernel(const TcBlockAr
             o.w = *reinterpret_cast<uint32_t*>(&m[3]);
             reinterpret_cast<uint4*>(a.out)[(((int64_t)clip0 * out_chunks + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
         }
-    }
-    if (blockIdx.x < 8 && lane == 0) {
-        if (warp == 2) { g_tc_times[blockIdx.x][13] = prof_wait; g_tc_times[blockIdx.x][14] = prof_work; }
-        if (warp == 0) g_tc_times[blockIdx.x][15] = prof_wait;
     }
     __syncthreads();
     TC_STAMP(11);
@@ -641,14 +686,15 @@ struct TcBlockPlan {
     int pool_t, pool_f;
     int rows_out_max;     // pre-pool output rows per tile (upper bound, sized for shared memory)
     int spread;           // 1: output chunks spread over the four TMEM lane quadrants (explicit 128-row A operand)
+    int twin;             // 1: "twin" launch shape (2 CTAs/SM), 0: "wide" (1 CTA/SM)
 };
 // block 1: conv2d (CUDA cores) + conv2d_1..3;  2: conv2d_4..7;  3: conv2d_8..11;  4: conv2d_12..15 (pool deferred);  5: conv2d_16..19
 static const TcBlockPlan kPlans[5] = {
-    {1, 3, 32, 32, 32, 24, 2, 2, 26, 1},
-    {4, 4, 16, 32, 48, 48, 1, 2, 26, 1},
-    {8, 4, 8, 48, 80, 72, 2, 2, 24, 0},
-    {12, 4, 4, 80, 96, 96, 1, 1, 32, 0},
-    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0},
+    {1, 3, 32, 32, 32, 24, 2, 2, 10, 1, 1},
+    {4, 4, 16, 32, 48, 48, 1, 2, 11, 1, 1},
+    {8, 4, 8, 48, 80, 72, 2, 2, 24, 0, 0},
+    {12, 4, 4, 80, 96, 96, 1, 1, 32, 0, 0},
+    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0, 0},
 };
 
 struct TcWeights {
@@ -741,12 +787,12 @@ void tc_release(hb_embed_model* m) {
 // geometry of one block launch
 struct TcGeom {
     int T_in, T_pre, T_out;      // input rows, pre-pool output rows, rows the block writes per clip
-    int tiles_per_clip, rows_out, Tt, segs, n_nt, P_alloc, ch_alloc, w_buf_bytes, grid;
+    int tiles_per_clip, rows_out, Tt, segs, n_nt, P_alloc, ch_alloc, w_buf_bytes, grid, twin;
     size_t smem;
 };
 
 static size_t tc_smem_bytes(const TcGeom& g, bool first) {
-    return ((sizeof(TcSmemHeader) + 2 * (size_t)g.P_alloc + 127 + 16) & ~(size_t)127) + 2 * (size_t)g.w_buf_bytes +
+    return ((sizeof(TcSmemHeader) + 2 * (size_t)g.P_alloc + 127 + 16) & ~(size_t)127) + (g.twin ? 1 : 2) * (size_t)g.w_buf_bytes +
            2 * (128 + (size_t)g.ch_alloc * g.P_alloc * 16) + (first ? (size_t)g.Tt * kMels * sizeof(float) : 0) + 128;
 }
 
@@ -776,6 +822,7 @@ static TcGeom tc_geometry(int b, int T_in, int B, const TcWeights* tw) {
     g.ch_alloc = std::max(p.cin_pad, p.c_pad) / 8;
     g.w_buf_bytes = tc_w_buf_bytes(b, tw);
     g.grid = B * g.tiles_per_clip;
+    g.twin = p.twin;
     g.smem = tc_smem_bytes(g, b == 0);
     return g;
 }
@@ -797,6 +844,7 @@ static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
     g.P_alloc = g.n_nt * kTileN + 2 * S + 8;
     g.ch_alloc = p.c_pad / 8;
     g.w_buf_bytes = tc_w_buf_bytes(4, tw);
+    g.twin = 0;
     g.grid = ceil_div(B, g.segs);
     g.smem = tc_smem_bytes(g, false);
     return g;
@@ -869,15 +917,21 @@ static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const v
     a.n_layers = p.n_layers;
     a.ch_alloc = g.ch_alloc;
     a.w_buf_bytes = g.w_buf_bytes;
+    a.n_slots = g.twin ? 1 : 2;
+    a.tmem_cols = g.twin ? 256 : 512;
+    a.w_double = g.twin ? 0 : 1;
     for (int l = 0; l < p.n_layers; ++l) a.layers[l] = tw->layers[p.first_layer + l];
-    HB_REQUIRE(g.smem <= 227 * 1024, "tc block %d needs %zu bytes of shared memory", b, g.smem);
+    HB_REQUIRE(g.smem <= (size_t)(g.twin ? 113 : 227) * 1024, "tc block %d needs %zu bytes of shared memory", b, g.smem);
     HB_REQUIRE(g.P_alloc < 16383 && g.n_nt * kTileN < 32000, "tc block %d: tile too large", b);
-    static size_t configured = 0;
-    if (g.smem > configured) {
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<576, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
     }
-    tc_block_kernel<<<g.grid, kTcThreads, g.smem, st>>>(a);
+    if (g.twin) tc_block_kernel<320, 2><<<g.grid, 320, g.smem, st>>>(a);
+    else tc_block_kernel<576, 1><<<g.grid, 576, g.smem, st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -23,5 +23,4 @@ for layer, label in ((3, "block1"), (7, "block2"), (11, "block3"), (15, "block4"
     nl = 3 if label == "block1" else 4
     print(label, "total", (t[:, 12] - t[:, 0]).mean())
     cols = [0, 1] + list(range(2, 2 + 2 * nl))
-    print("   ", {names[c]: int(d[:, c].mean()) for c in cols}, "store", int((t[:, 11] - t[:, 2 + 2 * nl]).mean()), "dealloc", int(d[:, 11].mean()),
-          "| epi warp2: wait", int(t[:, 13].mean()), "work", int(t[:, 14].mean()), "| mma wait-empty", int(t[:, 15].mean()))
+    print("   ", {names[c]: int(d[:, c].mean()) for c in cols}, "store", int((t[:, 11] - t[:, 2 + 2 * nl]).mean()), "dealloc", int(d[:, 11].mean()))
