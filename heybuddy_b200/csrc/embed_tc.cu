@@ -220,7 +220,6 @@ __device__ __forceinline__ void epilogue_sub(uint32_t taddr, uint32_t row_addr, 
 //                    "twin"  = 320 threads (8 epilogue warps), 2 CTAs/SM (each 256 TMEM columns, 1 slot, single weight
 //                              buffer) -- the co-resident CTA fills the other's staging / epilogue / store phases.
 constexpr int kMaxSlots = 2;      // TMEM accumulator slots
-constexpr int kTileN = 256;       // positions per tcgen05.mma / accumulator slot columns
 constexpr int kTmemCols = 512;
 constexpr int kMaxTcLayers = 4;
 
@@ -268,7 +267,8 @@ struct TcSmemHeader {
 };
 
 
-template <int kTcThreads, int kMinBlocks>
+// kTileN = positions per tcgen05.mma = accumulator slot columns (256, or 128 for the small late blocks)
+template <int kTcThreads, int kMinBlocks, int kTileN>
 __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const TcBlockArgs a) {
     constexpr int kEpiWarps = kTcThreads / 32 - 2;   // 8 or 16: kEpiWarps / 4 warps per TMEM lane quadrant
     constexpr int kColsPerWarp = kTileN / (kEpiWarps / 4);
@@ -687,14 +687,15 @@ struct TcBlockPlan {
     int rows_out_max;     // pre-pool output rows per tile (upper bound, sized for shared memory)
     int spread;           // 1: output chunks spread over the four TMEM lane quadrants (explicit 128-row A operand)
     int twin;             // 1: "twin" launch shape (2 CTAs/SM), 0: "wide" (1 CTA/SM)
+    int tile_n;           // positions per MMA / accumulator slot (256 or 128)
 };
 // block 1: conv2d (CUDA cores) + conv2d_1..3;  2: conv2d_4..7;  3: conv2d_8..11;  4: conv2d_12..15 (pool deferred);  5: conv2d_16..19
 static const TcBlockPlan kPlans[5] = {
-    {1, 3, 32, 32, 32, 24, 2, 2, 10, 1, 1},
-    {4, 4, 16, 32, 48, 48, 1, 2, 11, 1, 1},
-    {8, 4, 8, 48, 80, 72, 2, 2, 24, 0, 0},
-    {12, 4, 4, 80, 96, 96, 1, 1, 32, 0, 0},
-    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0, 0},
+    {1, 3, 32, 32, 32, 24, 2, 2, 10, 1, 1, 256},
+    {4, 4, 16, 32, 48, 48, 1, 2, 11, 1, 1, 256},
+    {8, 4, 8, 48, 80, 72, 2, 2, 10, 0, 1, 128},
+    {12, 4, 4, 80, 96, 96, 1, 1, 21, 0, 1, 128},
+    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0, 1, 128},
 };
 
 struct TcWeights {
@@ -787,7 +788,7 @@ void tc_release(hb_embed_model* m) {
 // geometry of one block launch
 struct TcGeom {
     int T_in, T_pre, T_out;      // input rows, pre-pool output rows, rows the block writes per clip
-    int tiles_per_clip, rows_out, Tt, segs, n_nt, P_alloc, ch_alloc, w_buf_bytes, grid, twin;
+    int tiles_per_clip, rows_out, Tt, segs, n_nt, P_alloc, ch_alloc, w_buf_bytes, grid, twin, tile_n;
     size_t smem;
 };
 
@@ -817,8 +818,9 @@ static TcGeom tc_geometry(int b, int T_in, int B, const TcWeights* tw) {
     g.segs = 1;
     const int S = p.F + 1;
     const int P = 1 + g.Tt * S;
-    g.n_nt = ceil_div(P, kTileN);
-    g.P_alloc = g.n_nt * kTileN + 2 * S + 8;
+    g.tile_n = p.tile_n;
+    g.n_nt = ceil_div(P, g.tile_n);
+    g.P_alloc = g.n_nt * g.tile_n + 2 * S + 8;
     g.ch_alloc = std::max(p.cin_pad, p.c_pad) / 8;
     g.w_buf_bytes = tc_w_buf_bytes(b, tw);
     g.grid = B * g.tiles_per_clip;
@@ -838,13 +840,14 @@ static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
     g.tiles_per_clip = 1;
     g.rows_out = g.T_out;
     const int S = p.F + 1;
-    g.segs = std::max(1, (kTileN - 1) / (g.Tt * S));
+    g.tile_n = p.tile_n;
+    g.segs = std::max(1, (g.tile_n - 1) / (g.Tt * S));
     const int P = 1 + g.segs * g.Tt * S;
-    g.n_nt = ceil_div(P, kTileN);
-    g.P_alloc = g.n_nt * kTileN + 2 * S + 8;
+    g.n_nt = ceil_div(P, g.tile_n);
+    g.P_alloc = g.n_nt * g.tile_n + 2 * S + 8;
     g.ch_alloc = p.c_pad / 8;
     g.w_buf_bytes = tc_w_buf_bytes(4, tw);
-    g.twin = 0;
+    g.twin = p.twin;
     g.grid = ceil_div(B, g.segs);
     g.smem = tc_smem_bytes(g, false);
     return g;
@@ -917,21 +920,25 @@ static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const v
     a.n_layers = p.n_layers;
     a.ch_alloc = g.ch_alloc;
     a.w_buf_bytes = g.w_buf_bytes;
-    a.n_slots = g.twin ? 1 : 2;
     a.tmem_cols = g.twin ? 256 : 512;
+    a.n_slots = a.tmem_cols / g.tile_n;
     a.w_double = g.twin ? 0 : 1;
     for (int l = 0; l < p.n_layers; ++l) a.layers[l] = tw->layers[p.first_layer + l];
     HB_REQUIRE(g.smem <= (size_t)(g.twin ? 113 : 227) * 1024, "tc block %d needs %zu bytes of shared memory", b, g.smem);
-    HB_REQUIRE(g.P_alloc < 16383 && g.n_nt * kTileN < 32000, "tc block %d: tile too large", b);
+    HB_REQUIRE(g.P_alloc < 16383 && g.n_nt * g.tile_n < 32000, "tc block %d: tile too large", b);
+    HB_REQUIRE(!(g.tile_n == 128 && !g.twin), "tc block %d: 128-position tiles are built for the twin shape only", b);
     static bool configured = false;
     if (!configured) {
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<576, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<576, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        HB_CUDA_OK(cudaFuncSetAttribute(tc_block_kernel<320, 2, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    if (g.twin) tc_block_kernel<320, 2><<<g.grid, 320, g.smem, st>>>(a);
-    else tc_block_kernel<576, 1><<<g.grid, 576, g.smem, st>>>(a);
+    if (g.twin && g.tile_n == 128) tc_block_kernel<320, 2, 128><<<g.grid, 320, g.smem, st>>>(a);
+    else if (g.twin) tc_block_kernel<320, 2, 256><<<g.grid, 320, g.smem, st>>>(a);
+    else tc_block_kernel<576, 1, 256><<<g.grid, 576, g.smem, st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }
