@@ -39,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CHUNK = int(os.environ.get("HB_BENCH_CHUNK", "8192"))       # clips per GPU per step
+E2E_SUB = int(os.environ.get("HB_BENCH_E2E_SUB", "2048"))   # e2e: sub-chunk pipelined H2D / compute / D2H inside a step
 POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cycled through
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
@@ -294,6 +295,19 @@ def main():
     pool_clips = [make_sources(CHUNK, 2001 + 97 * rank + i, device).pin() for i in range(POOL)]
     pool_tables = [aug.next_table(c.lengths) for c in pool_clips]
     pool_dev = [pipe.upload(c, t) for c, t in zip(pool_clips, pool_tables)]
+    # the same draws cut into sub-chunk tables for the pipelined host path (tables are per chunk of whole batches)
+    sub = min(E2E_SUB, CHUNK)
+    assert sub % AUG_BATCH == 0 and CHUNK % sub == 0
+    bps = sub // AUG_BATCH
+    from heybuddy_b200.dataset.draws import DrawTable
+    pool_subtables = []
+    for t in pool_tables:
+        parts = []
+        for lo in range(0, len(t.batches), bps):
+            d = DrawTable(cfg=t.cfg, seed=t.seed)
+            d.batches, d.noise_clip_cursor, d.rir_index = t.batches[lo:lo + bps], t.noise_clip_cursor[lo:lo + bps], t.rir_index[lo:lo + bps]
+            parts.append(d)
+        pool_subtables.append(parts)
     out_dev = torch.empty((CHUNK, 16, spec.EMB_DIM), dtype=torch.float32, device=device)
     torch.cuda.synchronize()
 
@@ -325,12 +339,12 @@ def main():
     # ---- e2e: host buffers through the public API, copies inside the timed region -----------------------------
     host_out = np.empty((CHUNK, 16, spec.EMB_DIM), dtype=np.float32)
     for i in range(min(args.warmup, 2)):
-        pipe.featurize_host(pool_clips[i % POOL], [pool_tables[i % POOL]], CHUNK, out=host_out)
+        pipe.featurize_host(pool_clips[i % POOL], pool_subtables[i % POOL], sub, out=host_out)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(args.steps):
-        _, a, b = pipe.featurize_host(pool_clips[(args.warmup + i) % POOL], [pool_tables[(args.warmup + i) % POOL]], CHUNK, out=host_out)
+        _, a, b = pipe.featurize_host(pool_clips[(args.warmup + i) % POOL], pool_subtables[(args.warmup + i) % POOL], sub, out=host_out)
         h2d += a
         d2h += b
     barrier()
@@ -375,7 +389,7 @@ def main():
             "dtype": "f16 operands / f32 accumulate (embed), f32 (augment, mel)" if precision == "f16" else "f32",
             "data": "synthetic", "config": workload_config(precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "api": "FeaturizePipeline.featurize_host (pinned int16 clips in, f32 [n,16,96] out)"},
+                    "api": f"FeaturizePipeline.featurize_host (pinned int16 clips in, f32 [n,16,96] out, {sub}-clip sub-chunks pipelined)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
