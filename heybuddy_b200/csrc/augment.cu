@@ -26,7 +26,7 @@
 
 namespace hb {
 
-constexpr int kAugThreads = 512;
+constexpr int kAugThreads = 1024;
 constexpr int kMaxPasses = 12;
 constexpr int kColoredBase = 16000;
 constexpr int kMaxT = 23040;
@@ -37,6 +37,8 @@ struct FftPlan {
     int radix[kMaxPasses];
     const float2* tw_m;    // exp(-2 pi i k / M), k in [0, M)
     const float2* tw_t;    // exp(-2 pi i k / T), k in [0, M]
+    int tw_lo;             // two-level twiddle split: exp(-2 pi i m / M) = hi[m / tw_lo] * lo[m % tw_lo]
+    int tw_hi;             // number of hi entries (tw_hi * tw_lo >= M)
 };
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
@@ -93,10 +95,24 @@ __device__ __forceinline__ void dft<5>(float2* v) {
     v[3] = cadd(p2, mul_pos_i(q2));
 }
 
+constexpr int kTwMax = 128;   // entries per twiddle level kept in shared memory
+
+struct TwTables {
+    float2 hi[kTwMax];
+    float2 lo[kTwMax];
+};
+
+// exp(-2 pi i m / M) from the two-level table: one shared-memory pair + one complex multiply instead of a
+// scattered global load per butterfly input.
+__device__ __forceinline__ float2 twiddle(const TwTables& t, int m, int lo_n) {
+    const int h = m / lo_n;
+    return cmulf(t.hi[h], t.lo[m - h * lo_n]);
+}
+
 // One Stockham autosort pass of radix R over M points (forward transform).
 template <int R>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int M, int Ns,
-                                         const float2* __restrict__ tw) {
+                                         const TwTables& tw, int lo_n) {
     const int nb = M / R;
     const int tw_step = M / (Ns * R);
     for (int j = threadIdx.x; j < nb; j += kAugThreads) {
@@ -105,8 +121,14 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = in[j + r * nb];
         if (k != 0) {
+            const float2 w1 = twiddle(tw, k * tw_step, lo_n);
+            float2 w = w1;
+            v[1] = cmulf(v[1], w);
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], __ldg(tw + r * k * tw_step));
+            for (int r = 2; r < R; ++r) {
+                w = cmulf(w, w1);   // w1^r
+                v[r] = cmulf(v[r], w);
+            }
         }
         dft<R>(v);
         const int base = (j - k) * R + k;
@@ -117,14 +139,14 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
 }
 
 // Runs the whole plan from `a` (ping-ponging with `b`); returns the buffer holding the result.
-__device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const FftPlan& plan) {
+__device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const FftPlan& plan, const TwTables& tw) {
     int Ns = 1;
     for (int p = 0; p < plan.n_passes; ++p) {
         const int R = plan.radix[p];
-        if (R == 4) fft_pass<4>(a, b, plan.M, Ns, plan.tw_m);
-        else if (R == 2) fft_pass<2>(a, b, plan.M, Ns, plan.tw_m);
-        else if (R == 3) fft_pass<3>(a, b, plan.M, Ns, plan.tw_m);
-        else fft_pass<5>(a, b, plan.M, Ns, plan.tw_m);
+        if (R == 4) fft_pass<4>(a, b, plan.M, Ns, tw, plan.tw_lo);
+        else if (R == 2) fft_pass<2>(a, b, plan.M, Ns, tw, plan.tw_lo);
+        else if (R == 3) fft_pass<3>(a, b, plan.M, Ns, tw, plan.tw_lo);
+        else fft_pass<5>(a, b, plan.M, Ns, tw, plan.tw_lo);
         Ns *= R;
         float2* t = a; a = b; b = t;
     }
@@ -165,10 +187,13 @@ rir_spectrum_kernel(const float* __restrict__ kernels, float2* __restrict__ spec
     const int M = plan.M;
     float2* buf0 = reinterpret_cast<float2*>(smem_raw);
     float2* buf1 = buf0 + M;
+    __shared__ TwTables tw;
+    for (int i = threadIdx.x; i < plan.tw_hi; i += kAugThreads) tw.hi[i] = plan.tw_m[i * plan.tw_lo];
+    for (int i = threadIdx.x; i < plan.tw_lo; i += kAugThreads) tw.lo[i] = plan.tw_m[i];
     const float* src = kernels + (int64_t)blockIdx.x * T;
     for (int i = threadIdx.x; i < M; i += kAugThreads) buf0[i] = make_float2(src[2 * i], src[2 * i + 1]);
     __syncthreads();
-    const float2* Z = fft_forward(buf0, buf1, plan);
+    const float2* Z = fft_forward(buf0, buf1, plan, tw);
     float2* H = spec + (int64_t)blockIdx.x * (M + 1);
     for (int k = threadIdx.x; k <= M / 2; k += kAugThreads) {
         if (k == 0) {
@@ -192,6 +217,7 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
                const hb_clip_aug* __restrict__ params, float* __restrict__ out, int T, FftPlan plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float scratch[40];
+    __shared__ TwTables tw;
     const int M = plan.M;
     float2* buf0 = reinterpret_cast<float2*>(smem_raw);
     float2* buf1 = buf0 + M;
@@ -204,6 +230,10 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
     const bool has_colored = p.colored_index >= 0 && colored_bases != nullptr;
     const bool has_noise = p.noise_offset >= 0 && noise_bank != nullptr;
     const bool has_rir = p.rir_index >= 0 && rir_specs != nullptr;
+    if (has_rir) {
+        for (int i = tid; i < plan.tw_hi; i += kAugThreads) tw.hi[i] = __ldg(plan.tw_m + i * plan.tw_lo);
+        for (int i = tid; i < plan.tw_lo; i += kAugThreads) tw.lo[i] = __ldg(plan.tw_m + i);
+    }
 
     // ---- load clip (128-bit loads; T is even, rows are 16-byte aligned when T % 4 == 0) --------
     float sumsq = 0.f;
@@ -278,7 +308,7 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
     for (int i = tid; i < T; i += kAugThreads) a += fabsf(x[i]);
     const float amp_x = block_sum(a, scratch) / (float)T;
 
-    float2* Z = fft_forward(buf0, buf1, plan);
+    float2* Z = fft_forward(buf0, buf1, plan, tw);
     float2* other = (Z == buf0) ? buf1 : buf0;
     const float2* H = rir_specs + (int64_t)p.rir_index * (M + 1);
     // untangle -> multiply -> re-tangle, conjugated so the forward FFT inverts it
@@ -303,7 +333,7 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
         }
     }
     __syncthreads();
-    float2* Yc = fft_forward(Z, other, plan);   // = conj(M * z'), z' = y_even + i y_odd
+    float2* Yc = fft_forward(Z, other, plan, tw);   // = conj(M * z'), z' = y_even + i y_odd
     float* y = reinterpret_cast<float*>(Yc);
     const float inv_m = 1.0f / (float)M;
     float ay = 0.f;
@@ -361,6 +391,10 @@ static int get_plan(int T, FftPlan* out) {
             n /= r;
         }
     HB_REQUIRE(n == 1, "augment: T/2=%d must factor into 2,3,5 for the exact-length FFT", plan.M);
+    plan.tw_lo = 1;
+    while (plan.tw_lo * plan.tw_lo < plan.M) ++plan.tw_lo;          // ceil(sqrt(M)): 108 for M = 11520
+    plan.tw_hi = (plan.M + plan.tw_lo - 1) / plan.tw_lo;
+    HB_REQUIRE(plan.tw_lo <= kTwMax && plan.tw_hi <= kTwMax, "augment: twiddle tables too small for T=%d", T);
     std::vector<float2> twm(plan.M), twt(plan.M + 1);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k = 0; k < plan.M; ++k) {
