@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                 const int rem = (q - 1) % seg_pos, seg = (q - 1) / seg_pos;
                 const int r = rem / S, f = rem - r * S;
                 v = (f >= F) ? 1 : 0;
-                if (f == 0 && r < a.T_out && clip0 + seg < a.n_clips) v |= (seg * a.T_out + r + 1) << 1;
+                if (f == 0 && r < a.rows_out && row0 + r < a.T_out && clip0 + seg < a.n_clips) v |= (seg * 64 + r + 1) << 1;
             }
             pos_tab[q] = (int16_t)v;
         }
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                 const int seg = (q - 1) / seg_pos, rem = (q - 1) - seg * seg_pos;
                 const int r = rem / S, f = rem - r * S;
                 const int clip = clip0 + seg;
-                const int tr = 2 * r + a.pool_phase;
+                const int tr = 2 * (row0 + r) + a.pool_phase;
                 if (f < F && clip < a.n_clips && tr + 1 < a.in_T) {
                     const uint4* base = in + ((int64_t)clip * in_chunks + ch) * a.in_T * a.in_F;
                     const uint4 x0 = __ldg(base + (int64_t)tr * a.in_F + 2 * f), x1 = __ldg(base + (int64_t)tr * a.in_F + 2 * f + 1);
@@ -551,12 +551,14 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                                 const int p = pos0 + g * 8 + 2 * (lane & 3);
                                 const int t0 = pos_tab[p], t1 = pos_tab[p + 1];
                                 if (t0 >> 1) {
-                                    const int64_t row = (int64_t)clip0 * a.T_out + (t0 >> 1) - 1;
+                                    const int sr = (t0 >> 1) - 1;   // seg * 64 + local row
+                                    const int64_t row = (int64_t)(clip0 + (sr >> 6)) * a.T_out + row0 + (sr & 63);
                                     o[row * kEmbDim + ch_a] = v[4 * g + 0] + bb0[h];
                                     if (c1[h] >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 2] + bb1[h];
                                 }
                                 if (t1 >> 1) {
-                                    const int64_t row = (int64_t)clip0 * a.T_out + (t1 >> 1) - 1;
+                                    const int sr = (t1 >> 1) - 1;
+                                    const int64_t row = (int64_t)(clip0 + (sr >> 6)) * a.T_out + row0 + (sr & 63);
                                     o[row * kEmbDim + ch_a] = v[4 * g + 1] + bb0[h];
                                     if (c1[h] >= 0) o[row * kEmbDim + ch_b] = v[4 * g + 3] + bb1[h];
                                 }
@@ -829,26 +831,37 @@ static TcGeom tc_geometry(int b, int T_in, int B, const TcWeights* tw) {
     return g;
 }
 
-// tail block: pooled rows per clip Tt = T15 / 2, several clips per CTA
+// tail block: pooled rows per clip = T15 / 2; several whole clips per CTA when they fit one tile, else time tiles
 static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
     const TcBlockPlan& p = kPlans[4];
     TcGeom g;
     g.T_in = T15;
-    g.Tt = T15 / 2;
-    g.T_pre = g.Tt - 4;
-    g.T_out = g.T_pre;
-    g.tiles_per_clip = 1;
-    g.rows_out = g.T_out;
+    const int rows = T15 / 2;              // pooled rows per clip (phase 0; phase 1 may have one fewer valid)
+    g.T_pre = rows - 4;
+    g.T_out = g.T_pre;                     // valid output rows per clip (two VALID time convs)
     const int S = p.F + 1;
     g.tile_n = p.tile_n;
-    g.segs = std::max(1, (g.tile_n - 1) / (g.Tt * S));
+    const int max_rows = std::min(63, (g.tile_n - 1) / S);    // rows that fit one accumulator tile (and the 6-bit row code)
+    if (rows <= max_rows) {
+        g.tiles_per_clip = 1;
+        g.rows_out = g.T_out;
+        g.Tt = rows;
+        g.segs = std::max(1, (g.tile_n - 1) / (g.Tt * S));
+        g.grid = ceil_div(B, g.segs);
+    } else {
+        g.segs = 1;
+        const int per = max_rows - 4;
+        g.tiles_per_clip = ceil_div(g.T_out, per);
+        g.rows_out = ceil_div(g.T_out, g.tiles_per_clip);
+        g.Tt = g.rows_out + 4;
+        g.grid = B * g.tiles_per_clip;
+    }
     const int P = 1 + g.segs * g.Tt * S;
     g.n_nt = ceil_div(P, g.tile_n);
     g.P_alloc = g.n_nt * g.tile_n + 2 * S + 8;
     g.ch_alloc = p.c_pad / 8;
     g.w_buf_bytes = tc_w_buf_bytes(4, tw);
     g.twin = p.twin;
-    g.grid = ceil_div(B, g.segs);
     g.smem = tc_smem_bytes(g, false);
     return g;
 }
