@@ -187,6 +187,11 @@ class FeaturizePipeline:
         n = len(clips)
         dev = self.device
         n_slots = self.slot_offsets.size
+        # ``out`` may be a pinned CPU torch tensor: the D2H then lands in it directly (no staging copy on the host)
+        out_t = out if (out is not None and hasattr(out, "is_pinned")) else None
+        if out_t is not None:
+            assert out_t.is_pinned() and tuple(out_t.shape) == (n, n_slots, spec.EMB_DIM) and out_t.dtype == torch.float32
+            out = out_t.numpy()
         if out is None:
             out = np.empty((n, n_slots, spec.EMB_DIM), dtype=np.float32)
         if ("copy_stream", 0) not in self._bufs:
@@ -194,7 +199,7 @@ class FeaturizePipeline:
         copy_stream = self._bufs[("copy_stream", 0)]
         compute = torch.cuda.current_stream(dev)
         h2d = d2h = 0
-        staged = []
+        stage_events = [None, None]
         pending = None  # (result device tensor, pinned host tensor, lo, hi, event)
 
         def stage(ci: int):
@@ -203,6 +208,9 @@ class FeaturizePipeline:
             part = clips.slice(lo, hi)
             pads, params, bases = self.pack_params(tables[ci])
             slot = ci % 2
+            prev = stage_events[slot]
+            if prev is not None:
+                prev.synchronize()   # the H2D that last read this slot's pinned staging buffers must have finished
             host = {}
             for name, arr in (("samples", part.samples), ("offsets", part.offsets), ("pads", pads),
                               ("params", params.view(np.uint8).reshape(hi - lo, -1)), ("bases", bases)):
@@ -233,6 +241,7 @@ class FeaturizePipeline:
                     devs[name] = d.view(shape)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+            stage_events[slot] = ev
             return DeviceChunk(devs["samples"], devs["offsets"], devs["pads"], devs["params"], devs["bases"], hi - lo), ev, lo, hi
 
         n_chunks = (n + chunk_clips - 1) // chunk_clips
@@ -245,6 +254,10 @@ class FeaturizePipeline:
                 if v is not None:
                     v.record_stream(compute)
             emb = self.run_device(chunk)
+            if out_t is not None:
+                out_t[lo:hi].copy_(emb, non_blocking=True)
+                d2h += emb.numel() * 4
+                continue
             key = (f"pin_out_{ci % 2}", 0)
             pin = self._bufs.get(key)
             if pin is None or pin.numel() < emb.numel():
@@ -263,4 +276,6 @@ class FeaturizePipeline:
             p_pin, p_lo, p_hi, p_ev = pending
             p_ev.synchronize()
             out[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
+        if out_t is not None:
+            compute.synchronize()
         return out, h2d, d2h
