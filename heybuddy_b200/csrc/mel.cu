@@ -1,168 +1,171 @@
-// K6: fused STFT-power -> 32-bin mel (dense fp32 projection) -> log10 + 2.
+// K6: fused STFT-power -> 32-bin mel (banded fp32 projection) -> log10 + 2.
 //
 // Replaces the ORT run of mel-spectrogram.onnx behind MelSpectrogramModel.__call__
 // (reference src/python/heybuddy/spectrogram.py:23-32).  Arithmetic spec: SURVEY.md A.4 /
 // heybuddy_b200/spec.py.
 //
-// Layout: one CTA per (clip, 16-frame chunk).  The chunk's 2912 samples are staged once in
-// shared memory with coalesced 128-bit loads (each sample is reused by 3.2 frames).  Each of
-// the 8 warps owns 2 frames: 512-point real FFT computed as a 256-point complex Stockham
-// radix-4 FFT in the warp's private shared-memory ping-pong buffers, power of bins [2,122)
-// (the only filterbank rows that are non-zero for 60..3800 Hz), then the [120 x 32] mel
-// projection as a dense fp32 product (lane m owns mel bin m), log10, +2, one coalesced
-// 128-byte store per frame.
+// Layout: a warp owns TWO frames at a time (half-warp h = lane / 16 -> frame 2p + h) and keeps the
+// whole 512-point real FFT in registers:
+//   * the frame is packed into 256 complex points z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); lane l
+//     loads the 16 points n = l + 16 i straight from global memory (a half-warp reads 128
+//     contiguous bytes per i; every sample is re-read by 3.2 frames out of L1),
+//   * 256 = 16 x 16: a 16-point DFT in registers (two radix-4 levels), the W256^(l k1) twiddles
+//     (16 register constants per lane), ONE 16 x 16 transpose through padded shared memory, a second
+//     16-point DFT -> lane l holds X[l + 16 k2],
+//   * the real-FFT untangle pairs X[k] with X[256 - k], which lives in lane 16 - l: one shuffle,
+//   * power of bins [2, 122) goes to shared memory; lane m = mel bin m sums its own <= 16-tap band of
+//     the triangular filterbank (each FFT bin feeds at most two mel bins, so the dense [120 x 32]
+//     product is 88 % zeros), log10, + 2, one coalesced 128-byte store per frame.
+// The previous version (radix-4 Stockham in shared memory + dense projection) was shared-memory
+// wavefront bound: l1tex 94 % busy, 536 wavefronts per frame (profiles/README.md); this one needs ~100.
 //
-// Roofline: HBM-bound on paper (92,160 B in + 18,048 B out per 23040-sample clip); the FFT
-// makes it FP32/shared-memory-bound in practice.
+// Roofline: HBM-bound on paper (92,160 B in + 18,048 B out per 23040-sample clip).
 #include "hb_common.cuh"
 
 namespace hb {
 
+constexpr int kMelTaps = 16;         // widest supported filterbank band (the 60..3800 Hz HTK bank needs 15)
+
 struct MelTables {
-    float window[kWinLength];        // Hann(400); the 56-sample zero pads are implicit
+    float2 win2[256];                // (w[2n], w[2n+1]) of the 512-sample padded Hann window
     float2 w256[256];                // exp(-2 pi i k / 256)
-    float2 w512[129];                // exp(-2 pi i k / 512), k = 0..128
-    float fb[kMelBand * kMels];      // filterbank rows [2,122) x 32
+    float2 w512[128];                // exp(-2 pi i k / 512), k = 0..127
+    float fbw[kMelTaps * kMels];     // banded filterbank: fbw[j][m] = fb[lo[m] + j][m]
+    int lo[kMels];                   // first FFT bin of mel bin m
 };
 
 __device__ MelTables g_mel_tables;
 static bool g_tables_ready[64] = {false};
 
-constexpr int kFramesPerCta = 16;
 constexpr int kMelThreads = 256;
 constexpr int kMelWarps = kMelThreads / 32;
-constexpr int kFramesPerWarp = kFramesPerCta / kMelWarps;  // 2
-constexpr int kChunkSamples = (kFramesPerCta - 1) * kHop + kNFFT;  // 2912
+constexpr int kTrStride = 17;        // float2 row stride of the transpose tile: conflict-free both ways
 
 struct MelSmem {
-    float fb[kMelBand * kMels];          // 15360 B
-    float window[kWinLength];            // 1600 B
-    float2 w256[256];                    // 2048 B
-    float2 w512[132];                    // 1056 B (129 used)
-    float samples[kChunkSamples];        // 11648 B
-    float2 fft[kMelWarps][2][256];       // 32768 B
-    float power[kMelWarps][128];         // 4096 B
+    float2 win2[256];
+    float2 w512[128];
+    float fbw[kMelTaps * kMels];
+    int lo[kMels];
+    float2 tr[kMelWarps][2][16 * kTrStride];
+    float power[kMelWarps][2][128];  // bins [0,128); hb_init_tables checks lo + kMelTaps <= 128
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// One Stockham radix-4 pass over 256 complex points; lane handles butterflies j = lane, lane + 32.
-template <int NS>
-__device__ __forceinline__ void stockham_r4(const float2* __restrict__ in, float2* __restrict__ out,
-                                            const float2* __restrict__ w256, int lane) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int j = lane + 32 * h;
-        const int k = j & (NS - 1);
-        float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
-        if (NS > 1) {
-            constexpr int step = 64 / NS;
-            v1 = cmul(v1, w256[k * step]);
-            v2 = cmul(v2, w256[2 * k * step]);
-            v3 = cmul(v3, w256[3 * k * step]);
-        }
-        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-        const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-        const float2 a3 = make_float2(v1.x - v3.x, v1.y - v3.y);
-        const int d = ((j - k) << 2) + k;  // (j / NS) * NS * 4 + k
-        out[d] = make_float2(a0.x + a2.x, a0.y + a2.y);
-        out[d + NS] = make_float2(a1.x + a3.y, a1.y - a3.x);      // a1 - i a3
-        out[d + 2 * NS] = make_float2(a0.x - a2.x, a0.y - a2.y);
-        out[d + 3 * NS] = make_float2(a1.x - a3.y, a1.y + a3.x);  // a1 + i a3
-    }
-    __syncwarp();
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+    const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+    const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+    const float2 a3 = make_float2(v1.x - v3.x, v1.y - v3.y);
+    v0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+    v1 = make_float2(a1.x + a3.y, a1.y - a3.x);      // a1 - i a3
+    v2 = make_float2(a0.x - a2.x, a0.y - a2.y);
+    v3 = make_float2(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
 }
 
-__global__ void __launch_bounds__(kMelThreads)
+// Forward 16-point DFT in registers.  Input v[n]; output X[k] is left at v[rev16(k)], rev16(k) = 4 (k % 4) + k / 4.
+__host__ __device__ constexpr int rev16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dft4(v[a], v[a + 4], v[a + 8], v[a + 12]);   // v[a + 4 kb] = Y[a][kb]
+    // Y[a][kb] *= W16^(a kb)
+    v[5] = cmul(v[5], make_float2(c1, -s1));                 // W^1
+    v[6] = make_float2(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));       // W^2 = (h, -h)
+    v[7] = cmul(v[7], make_float2(s1, -c1));                 // W^3
+    v[9] = make_float2(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));       // W^2
+    v[10] = make_float2(v[10].y, -v[10].x);                  // W^4 = -i
+    v[11] = make_float2(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y)); // W^6 = (-h, -h)
+    v[13] = cmul(v[13], make_float2(s1, -c1));               // W^3
+    v[14] = make_float2(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y)); // W^6
+    v[15] = cmul(v[15], make_float2(-c1, s1));               // W^9 = -W^1
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) dft4(v[4 * kb], v[4 * kb + 1], v[4 * kb + 2], v[4 * kb + 3]);  // v[4 kb + ka] = X[kb + 4 ka]
+}
+
+__global__ void __launch_bounds__(kMelThreads, 2)
 mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, float* __restrict__ mel,
-           int T, int F, int chunks_per_clip) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
+           int B, int F, int pairs_per_clip) {
+    __shared__ MelSmem s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int clip = blockIdx.x / chunks_per_clip;
-    const int frame0 = (blockIdx.x - clip * chunks_per_clip) * kFramesPerCta;
-    const int sample0 = frame0 * kHop;
-
-    // ---- stage tables + samples -----------------------------------------------------------
-    for (int i = tid; i < kMelBand * kMels; i += kMelThreads) s.fb[i] = g_mel_tables.fb[i];
-    for (int i = tid; i < kWinLength; i += kMelThreads) s.window[i] = g_mel_tables.window[i];
-    for (int i = tid; i < 256; i += kMelThreads) s.w256[i] = g_mel_tables.w256[i];
-    for (int i = tid; i < 129; i += kMelThreads) s.w512[i] = g_mel_tables.w512[i];
-    {
-        const float* src = audio + (int64_t)clip * row_stride + sample0;
-        const int avail = min(kChunkSamples, T - sample0);
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-        if (vec_ok) {
-            const int nvec = avail >> 2;
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            for (int i = tid; i < nvec; i += kMelThreads) {
-                float4 v = __ldg(src4 + i);
-                s.samples[4 * i + 0] = v.x * scale;
-                s.samples[4 * i + 1] = v.y * scale;
-                s.samples[4 * i + 2] = v.z * scale;
-                s.samples[4 * i + 3] = v.w * scale;
-            }
-            for (int i = (nvec << 2) + tid; i < avail; i += kMelThreads) s.samples[i] = __ldg(src + i) * scale;
-        } else {
-            for (int i = tid; i < avail; i += kMelThreads) s.samples[i] = __ldg(src + i) * scale;
-        }
-    }
+    const int h = lane >> 4, l = lane & 15;
+    for (int i = tid; i < 256; i += kMelThreads) s.win2[i] = g_mel_tables.win2[i];
+    for (int i = tid; i < 128; i += kMelThreads) s.w512[i] = g_mel_tables.w512[i];
+    for (int i = tid; i < kMelTaps * kMels; i += kMelThreads) s.fbw[i] = g_mel_tables.fbw[i];
+    if (tid < kMels) s.lo[tid] = g_mel_tables.lo[tid];
+    for (int i = tid; i < kMelWarps * 2 * 128; i += kMelThreads) (&s.power[0][0][0])[i] = 0.f;
+    float2 tw[16];                                   // W256^(l k1)
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) tw[k1] = g_mel_tables.w256[(l * k1) & 255];
     __syncthreads();
+    const int my_lo = s.lo[lane];
+    float2* tr = s.tr[warp][h];
+    float* pw = s.power[warp][h];
+    const bool vec_ok = ((row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(audio) & 7) == 0);
+    const int64_t n_pairs = (int64_t)B * pairs_per_clip;
+    const int64_t warp_stride = (int64_t)gridDim.x * kMelWarps;
 
-    float2* buf0 = s.fft[warp][0];
-    float2* buf1 = s.fft[warp][1];
-    float* pw = s.power[warp];
+    for (int64_t p = (int64_t)blockIdx.x * kMelWarps + warp; p < n_pairs; p += warp_stride) {
+        const int clip = (int)(p / pairs_per_clip);
+        const int f0 = (int)(p - (int64_t)clip * pairs_per_clip) * 2;
+        const int f = min(f0 + h, F - 1);            // an odd F repeats the last frame in the idle half-warp
+        const float* x = audio + (int64_t)clip * row_stride + (int64_t)f * kHop;
 
-    for (int fi = 0; fi < kFramesPerWarp; ++fi) {
-        const int fl = warp * kFramesPerWarp + fi;  // frame within the chunk
-        const int f = frame0 + fl;
-        if (f >= F) break;  // warp-uniform
-        const float* x = s.samples + fl * kHop;
-
-        // z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); the window is zero outside [56, 456)
+        // z[i] = point n = l + 16 i; the window is zero outside samples [56, 456) = points [28, 228)
+        float2 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int n = lane + 32 * i;
-            const int i0 = 2 * n - kWinPad;
-            float2 z = make_float2(0.f, 0.f);
-            if (i0 >= 0 && i0 < kWinLength) {  // 56 and 400 are even, so both samples share the test
-                const float2 xv = *reinterpret_cast<const float2*>(x + 2 * n);
-                z.x = xv.x * s.window[i0];
-                z.y = xv.y * s.window[i0 + 1];
-            }
-            buf0[n] = z;
-        }
-        __syncwarp();
-        stockham_r4<1>(buf0, buf1, s.w256, lane);
-        stockham_r4<4>(buf1, buf0, s.w256, lane);
-        stockham_r4<16>(buf0, buf1, s.w256, lane);
-        stockham_r4<64>(buf1, buf0, s.w256, lane);
-
-        // real-FFT post-processing + power for bins [2, 122) -> pw[0..120)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = lane + 32 * i;
-            if (k >= kMelBinLo && k < kMelBinHi) {
-                const float2 a = buf0[k];
-                const float2 b = buf0[256 - k];
-                const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (A + conj B)/2
-                const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (A - conj B)/2
-                const float2 o = make_float2(d.y, -d.x);                                 // -i d
-                const float2 wo = cmul(s.w512[k], o);
-                const float re = e.x + wo.x, im = e.y + wo.y;
-                pw[k - kMelBinLo] = re * re + im * im;
+        for (int i = 0; i < 16; ++i) {
+            const int n = l + 16 * i;
+            v[i] = make_float2(0.f, 0.f);
+            if (i >= 1 && i <= 14 && n >= kWinPad / 2 && n < (kWinPad + kWinLength) / 2) {
+                float2 xv;
+                if (vec_ok) xv = __ldg(reinterpret_cast<const float2*>(x) + n);
+                else xv = make_float2(__ldg(x + 2 * n), __ldg(x + 2 * n + 1));
+                const float2 w = s.win2[n];
+                v[i] = make_float2(xv.x * scale * w.x, xv.y * scale * w.y);
             }
         }
+        dft16(v);                                     // v[rev16(k1)] = sum_i z[l + 16 i] W16^(i k1)
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) tr[l * kTrStride + k1] = (k1 == 0) ? v[rev16(k1)] : cmul(v[rev16(k1)], tw[k1]);
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = tr[n1 * kTrStride + l];
+        dft16(v);                                     // v[rev16(k2)] = X[l + 16 k2]
+
+        // real-FFT untangle + power, bins k = l + 16 k2 < 128 (only [2, 122) is read back)
+        const int partner = ((16 - l) & 15) + 16 * h;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+            const float2 a = v[rev16(k2)];
+            float2 b;
+            b.x = __shfl_sync(0xffffffffu, v[rev16(15 - k2)].x, partner);
+            b.y = __shfl_sync(0xffffffffu, v[rev16(15 - k2)].y, partner);
+            if (l == 0) b = v[rev16((16 - k2) & 15)];  // X[256 - 16 k2] is in this lane (k2 = 0 -> bin 0, unused)
+            const int k = l + 16 * k2;
+            const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (A + conj B)/2
+            const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (A - conj B)/2
+            const float2 o = make_float2(d.y, -d.x);                                 // -i d
+            const float2 wo = cmul(s.w512[k], o);
+            const float re = e.x + wo.x, im = e.y + wo.y;
+            pw[k] = re * re + im * im;
+        }
         __syncwarp();
 
-        // dense [120 x 32] projection: lane = mel bin
-        float acc = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < kMelBand; ++k) acc = fmaf(pw[k], s.fb[k * kMels + lane], acc);
-        mel[((int64_t)clip * F + f) * kMels + lane] = log10f(acc < 1e-10f ? 1e-10f : acc) + 2.0f;  // NaN-propagating clamp, like np.maximum / torch.clamp
+        // banded projection: lane = mel bin, both frames of the pair
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const float* q = s.power[warp][hh] + my_lo;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMelTaps; ++j) acc = fmaf(q[j], s.fbw[j * kMels + lane], acc);
+            const int fo = f0 + hh;
+            if (fo < F)   // NaN-propagating clamp, like np.maximum / torch.clamp
+                mel[((int64_t)clip * F + fo) * kMels + lane] = log10f(acc < 1e-10f ? 1e-10f : acc) + 2.0f;
+        }
         __syncwarp();
     }
 }
@@ -176,31 +179,36 @@ extern "C" int hb_mel_frames(int T) { return T < kNFFT ? 0 : 1 + (T - kNFFT) / k
 extern "C" int hb_init_tables(const float* hann_host, const float* melfb_host) {
     HB_REQUIRE(hann_host && melfb_host, "hb_init_tables: null table");
     static MelTables t;  // host staging
-    for (int i = 0; i < kWinLength; ++i) t.window[i] = hann_host[kWinPad + i];
     for (int i = 0; i < kNFFT; ++i)
         if (i < kWinPad || i >= kWinPad + kWinLength)
             HB_REQUIRE(hann_host[i] == 0.f, "hb_init_tables: window must be zero outside [56,456)");
+    for (int n = 0; n < 256; ++n) t.win2[n] = make_float2(hann_host[2 * n], hann_host[2 * n + 1]);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k = 0; k < 256; ++k) {
         t.w256[k].x = (float)cos(two_pi * k / 256.0);
         t.w256[k].y = (float)-sin(two_pi * k / 256.0);
     }
-    for (int k = 0; k <= 128; ++k) {
+    for (int k = 0; k < 128; ++k) {
         t.w512[k].x = (float)cos(two_pi * k / 512.0);
         t.w512[k].y = (float)-sin(two_pi * k / 512.0);
     }
-    for (int k = 0; k < 257; ++k)
-        for (int m = 0; m < kMels; ++m) {
-            const float v = melfb_host[k * kMels + m];
-            if (k >= kMelBinLo && k < kMelBinHi) {
-                t.fb[(k - kMelBinLo) * kMels + m] = v;
-            } else {
-                HB_REQUIRE(v == 0.f, "hb_init_tables: filterbank row %d outside the compiled band [%d,%d) is non-zero",
-                           k, kMelBinLo, kMelBinHi);
-            }
+    for (int m = 0; m < kMels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < 257; ++k) {
+            if (melfb_host[k * kMels + m] == 0.f) continue;
+            HB_REQUIRE(k >= kMelBinLo && k < kMelBinHi,
+                       "hb_init_tables: filterbank row %d outside the compiled band [%d,%d) is non-zero", k, kMelBinLo, kMelBinHi);
+            if (first < 0) first = k;
+            last = k;
         }
+        if (first < 0) first = last = kMelBinLo;
+        HB_REQUIRE(last - first < kMelTaps, "hb_init_tables: mel bin %d spans %d FFT bins, at most %d supported", m,
+                   last - first + 1, kMelTaps);
+        if (first + kMelTaps > 128) first = 128 - kMelTaps;   // keep the tap window inside the power row
+        t.lo[m] = first;
+        for (int j = 0; j < kMelTaps; ++j) t.fbw[j * kMels + m] = (first + j <= last) ? melfb_host[(first + j) * kMels + m] : 0.f;
+    }
     HB_CUDA_OK(cudaMemcpyToSymbol(g_mel_tables, &t, sizeof(MelTables)));
-    HB_CUDA_OK(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MelSmem)));
     int dev = 0;
     HB_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64) g_tables_ready[dev] = true;
@@ -217,10 +225,14 @@ extern "C" int hb_mel_f32(const float* audio_dev, int64_t audio_row_stride, floa
     HB_REQUIRE(dev < 64 && g_tables_ready[dev], "hb_mel_f32: hb_init_tables has not been called on device %d", dev);
     const int F = hb_mel_frames(T);
     if (B == 0 || F == 0) return HB_OK;
-    const int chunks = ceil_div(F, kFramesPerCta);
-    HB_REQUIRE((int64_t)B * chunks < (1ll << 31), "hb_mel_f32: B=%d too large for one launch", B);
-    mel_kernel<<<B * chunks, kMelThreads, sizeof(MelSmem), (cudaStream_t)stream>>>(audio_dev, audio_row_stride, scale,
-                                                                                     mel_dev, T, F, chunks);
+    const int pairs = ceil_div(F, 2);
+    const int64_t n_pairs = (int64_t)B * pairs;
+    static int n_sm[64] = {0};
+    if (n_sm[dev] == 0) HB_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
+    // persistent warps: two CTAs per SM, each warp strides over (clip, frame pair) items
+    const int64_t want = (n_pairs + kMelWarps - 1) / kMelWarps;
+    const int grid = (int)(want < 2 * n_sm[dev] ? want : 2 * n_sm[dev]);
+    mel_kernel<<<grid, kMelThreads, 0, (cudaStream_t)stream>>>(audio_dev, audio_row_stride, scale, mel_dev, B, F, pairs);
     HB_LAUNCHED();
     return HB_OK;
 }
