@@ -348,6 +348,353 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
     for (int i = tid; i < T; i += kAugThreads) dst[i] = y[i] * g;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused per-clip augmentation, T = 23040 (the 1.44 s clip of the featurization path)
+// ------------------------------------------------------------------------------------------------
+// Same arithmetic as augment_kernel, restructured around the FFT: M = 11520 = 16 * 16 * 9 * 5 with the
+// butterflies held in registers, so the reverb costs 7 shared-memory passes instead of 15:
+//     forward  R16 (Ns 1) -> R16 (Ns 16) -> R9 (Ns 256)
+//     middle   R5 (Ns 2304) + untangle * H + re-tangle + transposed R5, in registers: the last forward pass leaves
+//              X[k + 2304 r] of butterfly k in one thread and X[M - k - 2304 r] in butterfly 2304 - k, so a thread
+//              that owns both butterflies owns every (k, M - k) pair it needs
+//     inverse  transposed R9 -> R16 -> R16 (the FFT matrix is symmetric: running the transposed passes in
+//              reverse order on conjugated data is the inverse transform, natural order in and out)
+// 768 threads: 720 radix-16 butterflies per pass (94 % of the threads busy), 1280 radix-9, 1153 middle tasks.
+// Shared-memory index i lives at i + i / 32 (float2 units) so the stride-16 stores of the first pass (and the
+// stride-16 loads of the last) are conflict-free.
+constexpr int kFastT = 23040;
+constexpr int kFastM = kFastT / 2;
+constexpr int kFastThreads = 768;
+constexpr int kFastBuf = kFastM + kFastM / 32;     // skewed float2 slots per buffer
+
+__device__ __forceinline__ int sk(int i) { return i + (i >> 5); }
+
+template <int R> __host__ __device__ constexpr int out_idx(int k) { return k; }                 // where dftr<R> leaves X[k]
+template <> __host__ __device__ constexpr int out_idx<16>(int k) { return 4 * (k & 3) + (k >> 2); }
+template <> __host__ __device__ constexpr int out_idx<9>(int k) { return 3 * (k % 3) + k / 3; }
+
+template <int R>
+__device__ __forceinline__ void dftr(float2 (&v)[R]);
+
+template <>
+__device__ __forceinline__ void dftr<5>(float2 (&v)[5]) { dft<5>(v); }
+
+__device__ __forceinline__ void dft3r(float2& v0, float2& v1, float2& v2) {
+    const float2 t1 = cadd(v1, v2);
+    const float2 m1 = make_float2(v0.x - 0.5f * t1.x, v0.y - 0.5f * t1.y);
+    const float2 t2 = cscale(csub(v1, v2), 0.86602540378443864676f);
+    v0 = cadd(v0, t1);
+    v1 = cadd(m1, mul_neg_i(t2));
+    v2 = cadd(m1, mul_pos_i(t2));
+}
+__device__ __forceinline__ void dft4r(float2& v0, float2& v1, float2& v2, float2& v3) {
+    const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2);
+    const float2 a2 = cadd(v1, v3), a3 = csub(v1, v3);
+    v0 = cadd(a0, a2);
+    v2 = csub(a0, a2);
+    v1 = cadd(a1, mul_neg_i(a3));
+    v3 = cadd(a1, mul_pos_i(a3));
+}
+
+template <>
+__device__ __forceinline__ void dftr<9>(float2 (&v)[9]) {
+    // 9 = 3 x 3: v[a + 3 kb] = Y[a][kb], twiddles W9^(a kb), then v[3 kb + ka] = X[kb + 3 ka]
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dft3r(v[a], v[a + 3], v[a + 6]);
+    v[4] = cmulf(v[4], make_float2(0.76604444311897803520f, -0.64278760968653932632f));   // W9^1
+    v[5] = cmulf(v[5], make_float2(0.17364817766693034885f, -0.98480775301220805937f));   // W9^2
+    v[7] = cmulf(v[7], make_float2(0.17364817766693034885f, -0.98480775301220805937f));   // W9^2
+    v[8] = cmulf(v[8], make_float2(-0.93969262078590838405f, -0.34202014332566873304f));  // W9^4
+#pragma unroll
+    for (int kb = 0; kb < 3; ++kb) dft3r(v[3 * kb], v[3 * kb + 1], v[3 * kb + 2]);
+}
+
+template <>
+__device__ __forceinline__ void dftr<16>(float2 (&v)[16]) {
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) dft4r(v[a], v[a + 4], v[a + 8], v[a + 12]);
+    v[5] = cmulf(v[5], make_float2(c1, -s1));
+    v[6] = make_float2(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));
+    v[7] = cmulf(v[7], make_float2(s1, -c1));
+    v[9] = make_float2(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));
+    v[10] = mul_neg_i(v[10]);
+    v[11] = make_float2(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y));
+    v[13] = cmulf(v[13], make_float2(s1, -c1));
+    v[14] = make_float2(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y));
+    v[15] = cmulf(v[15], make_float2(-c1, s1));
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) dft4r(v[4 * kb], v[4 * kb + 1], v[4 * kb + 2], v[4 * kb + 3]);
+}
+
+// w[r] = w1^r, r = 1..R-1, multiplication depth <= log2(R) + 2
+template <int R>
+__device__ __forceinline__ void powers(float2 w1, float2 (&w)[R]) {
+    w[0] = make_float2(1.f, 0.f);
+    w[1] = w1;
+#pragma unroll
+    for (int r = 2; r < R; ++r) w[r] = (r & 1) ? cmulf(w[r - 1], w1) : cmulf(w[r / 2], w[r / 2]);
+}
+
+// forward Stockham pass: gather in[j + r nb], input-side twiddles, DFT, scatter out[(j - k) R + k + r Ns]
+template <int R, int NS>
+__device__ __forceinline__ void fast_pass_fwd(const float2* __restrict__ in, float2* __restrict__ out, const TwTables& tw,
+                                              int lo_n) {
+    constexpr int nb = kFastM / R;
+    constexpr int step = kFastM / (NS * R);
+    for (int j = threadIdx.x; j < nb; j += kFastThreads) {
+        const int k = j % NS;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[sk(j + r * nb)];
+        if (NS > 1) {
+            float2 w[R];
+            powers<R>(twiddle(tw, k * step, lo_n), w);
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], w[r]);
+        }
+        dftr<R>(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[sk(base + r * NS)] = v[out_idx<R>(r)];
+    }
+    __syncthreads();
+}
+
+// the transpose of fast_pass_fwd<R, NS>: gather in[(j - k) R + k + r Ns], DFT, output-side twiddles, scatter out[j + r nb]
+template <int R, int NS>
+__device__ __forceinline__ void fast_pass_bwd(const float2* __restrict__ in, float2* __restrict__ out, const TwTables& tw,
+                                              int lo_n) {
+    constexpr int nb = kFastM / R;
+    constexpr int step = kFastM / (NS * R);
+    for (int j = threadIdx.x; j < nb; j += kFastThreads) {
+        const int k = j % NS;
+        const int base = (j - k) * R + k;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[sk(base + r * NS)];
+        dftr<R>(v);
+        if (NS > 1) {
+            float2 w[R];
+            powers<R>(twiddle(tw, k * step, lo_n), w);
+            out[sk(j)] = v[out_idx<R>(0)];
+#pragma unroll
+            for (int r = 1; r < R; ++r) out[sk(j + r * nb)] = cmulf(v[out_idx<R>(r)], w[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) out[sk(j + r * nb)] = v[out_idx<R>(r)];
+        }
+    }
+    __syncthreads();
+}
+
+// (Z[k], Z[M-k]) -> conj of the re-tangled (Z'[k], Z'[M-k]) after multiplying the real spectrum by H
+__device__ __forceinline__ void pair_update(float2& zk, float2& zmk, int k, const float2* __restrict__ H,
+                                            const float2* __restrict__ tw_t) {
+    const float2 w = __ldg(tw_t + k);
+    float2 Xk, Xmk;
+    untangle(zk, zmk, w, &Xk, &Xmk);
+    const float2 Yk = cmulf(Xk, __ldg(H + k));
+    const float2 Ymk = cmulf(Xmk, __ldg(H + (kFastM - k)));
+    const float2 Ye = cscale(cadd(Yk, cconj(Ymk)), 0.5f);
+    const float2 Yo = cmulf(cscale(csub(Yk, cconj(Ymk)), 0.5f), cconj(w));
+    zk = cconj(cadd(Ye, mul_pos_i(Yo)));
+    zmk = cconj(cadd(cconj(Ye), mul_pos_i(cconj(Yo))));
+}
+
+// last forward pass (R5, Ns = 2304) + spectrum product + first inverse pass, in place
+__device__ __forceinline__ void fast_middle(float2* __restrict__ buf, const float2* __restrict__ H,
+                                            const float2* __restrict__ tw_t, const TwTables& tw, int lo_n) {
+    constexpr int NS = kFastM / 5;   // 2304 = nb
+    for (int t = threadIdx.x; t <= NS / 2; t += kFastThreads) {
+        float2 a[5], b[5], wa[5], wb[5];
+        const int ja = t, jb = (t == 0) ? 0 : NS - t;
+        powers<5>(twiddle(tw, ja, lo_n), wa);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) a[r] = buf[sk(ja + r * NS)];
+#pragma unroll
+        for (int r = 1; r < 5; ++r) a[r] = cmulf(a[r], wa[r]);
+        dftr<5>(a);
+        if (t == 0) {
+            // butterfly 0 pairs with itself: (r, 5 - r); bin 0 carries DC and Nyquist
+            const float x0 = a[0].x + a[0].y, xm = a[0].x - a[0].y;
+            const float y0 = x0 * __ldg(&H[0]).x, ym = xm * __ldg(&H[kFastM]).x;
+            a[0] = make_float2(0.5f * (y0 + ym), -0.5f * (y0 - ym));
+            pair_update(a[1], a[4], NS, H, tw_t);
+            pair_update(a[2], a[3], 2 * NS, H, tw_t);
+        } else if (t == NS / 2) {
+            // butterfly 1152 pairs with itself: (r, 4 - r); r = 2 is bin M / 2
+            pair_update(a[0], a[4], t, H, tw_t);
+            pair_update(a[1], a[3], t + NS, H, tw_t);
+            float2 dup = a[2];
+            pair_update(a[2], dup, t + 2 * NS, H, tw_t);
+        } else {
+            // W_M^(2304 - t) = W5 * conj(W_M^t)
+            powers<5>(cmulf(make_float2(0.30901699437494742410f, -0.95105651629515357212f), cconj(wa[1])), wb);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) b[r] = buf[sk(jb + r * NS)];
+#pragma unroll
+            for (int r = 1; r < 5; ++r) b[r] = cmulf(b[r], wb[r]);
+            dftr<5>(b);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) pair_update(a[r], b[4 - r], t + r * NS, H, tw_t);
+            dftr<5>(b);
+            buf[sk(jb)] = b[0];
+#pragma unroll
+            for (int r = 1; r < 5; ++r) buf[sk(jb + r * NS)] = cmulf(b[r], wb[r]);
+        }
+        dftr<5>(a);
+        buf[sk(ja)] = a[0];
+#pragma unroll
+        for (int r = 1; r < 5; ++r) buf[sk(ja + r * NS)] = cmulf(a[r], wa[r]);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float block_sum_n(float v, float* scratch, int n_warps) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();  // protect scratch reuse
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = (lane < n_warps) ? scratch[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__global__ void __launch_bounds__(kFastThreads, 1)
+augment_fast_kernel(const float* __restrict__ clips, const float* __restrict__ noise_bank,
+                    const float* __restrict__ colored_bases, const float2* __restrict__ rir_specs,
+                    const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float scratch[40];
+    __shared__ TwTables tw;
+    constexpr int T = kFastT, M = kFastM, NT = kFastThreads, NW = kFastThreads / 32;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);   // skewed: point n at sk(n)
+    float2* buf1 = buf0 + kFastBuf;
+    const int tid = threadIdx.x;
+    const hb_clip_aug p = params[blockIdx.x];
+    const float2* src = reinterpret_cast<const float2*>(clips + (int64_t)blockIdx.x * T);
+    float2* dst = reinterpret_cast<float2*>(out + (int64_t)blockIdx.x * T);
+    const bool has_colored = p.colored_index >= 0 && colored_bases != nullptr;
+    const bool has_noise = p.noise_offset >= 0 && noise_bank != nullptr;
+    const bool has_rir = p.rir_index >= 0 && rir_specs != nullptr;
+    if (has_rir) {
+        for (int i = tid; i < plan.tw_hi; i += NT) tw.hi[i] = __ldg(plan.tw_m + i * plan.tw_lo);
+        for (int i = tid; i < plan.tw_lo; i += NT) tw.lo[i] = __ldg(plan.tw_m + i);
+    }
+
+    // ---- load the clip and (prefetch) its noise row; both stay in shared memory ------------------------
+    float sumsq = 0.f, nsq = 0.f;
+#pragma unroll 5
+    for (int n = tid; n < M; n += NT) {
+        const float2 v = __ldg(src + n);
+        buf0[sk(n)] = v;
+        sumsq += v.x * v.x + v.y * v.y;
+    }
+    if (has_noise) {
+        const float* nsrc = noise_bank + p.noise_offset;
+        if ((reinterpret_cast<uintptr_t>(nsrc) & 7) == 0) {
+            const float2* n2 = reinterpret_cast<const float2*>(nsrc);
+#pragma unroll 5
+            for (int n = tid; n < M; n += NT) {
+                const float2 v = __ldg(n2 + n);
+                buf1[n] = v;
+                nsq += v.x * v.x + v.y * v.y;
+            }
+        } else {
+            for (int n = tid; n < M; n += NT) {
+                const float2 v = make_float2(__ldg(nsrc + 2 * n), __ldg(nsrc + 2 * n + 1));
+                buf1[n] = v;
+                nsq += v.x * v.x + v.y * v.y;
+            }
+        }
+    }
+
+    // every thread only ever touches its own points n = tid + i NT until the FFT: no barriers needed in between
+    // ---- K1 coloured noise + K2 gain ---------------------------------------------------------------
+    if (has_colored) {
+        const float rms = sqrtf(block_sum_n(sumsq, scratch, NW) / (float)T);
+        const float a = rms / exp10f(p.colored_snr_db * 0.05f);
+        const float* base = colored_bases + (int64_t)p.colored_index * kColoredBase;
+        for (int n = tid; n < M; n += NT) {
+            const float2 c = __ldg(reinterpret_cast<const float2*>(base + ((2 * n) % kColoredBase)));
+            float2 v = buf0[sk(n)];
+            v.x = (v.x + a * c.x) * p.gain;
+            v.y = (v.y + a * c.y) * p.gain;
+            buf0[sk(n)] = v;
+        }
+    } else if (p.gain != 1.0f) {
+        for (int n = tid; n < M; n += NT) {
+            float2 v = buf0[sk(n)];
+            v.x *= p.gain;
+            v.y *= p.gain;
+            buf0[sk(n)] = v;
+        }
+    }
+
+    // ---- K3 background noise at the per-clip SNR -------------------------------------------------------
+    if (has_noise) {
+        float e = 0.f;
+        for (int n = tid; n < M; n += NT) {
+            const float2 v = buf0[sk(n)];
+            e += v.x * v.x + v.y * v.y;
+        }
+        const float e_s = block_sum_n(e, scratch, NW);
+        const float e_n = block_sum_n(nsq, scratch, NW);
+        const float orig = 10.0f * (log10f(e_s) - log10f(e_n));
+        const float scale = exp10f((orig - p.noise_snr_db) * 0.05f);
+        for (int n = tid; n < M; n += NT) {
+            float2 v = buf0[sk(n)];
+            const float2 z = buf1[n];
+            v.x = fmaf(scale, z.x, v.x);
+            v.y = fmaf(scale, z.y, v.y);
+            buf0[sk(n)] = v;
+        }
+    }
+
+    if (!has_rir) {
+        for (int n = tid; n < M; n += NT) dst[n] = buf0[sk(n)];
+        return;
+    }
+
+    // ---- K4 reverb -------------------------------------------------------------------------------------
+    float a = 0.f;
+    for (int n = tid; n < M; n += NT) {
+        const float2 v = buf0[sk(n)];
+        a += fabsf(v.x) + fabsf(v.y);
+    }
+    const float amp_x = block_sum_n(a, scratch, NW) / (float)T;   // its barriers also publish buf0 and tw
+
+    const float2* H = rir_specs + (int64_t)p.rir_index * (M + 1);
+    const int lo_n = plan.tw_lo;
+    fast_pass_fwd<16, 1>(buf0, buf1, tw, lo_n);
+    fast_pass_fwd<16, 16>(buf1, buf0, tw, lo_n);
+    fast_pass_fwd<9, 256>(buf0, buf1, tw, lo_n);
+    fast_middle(buf1, H, plan.tw_t, tw, lo_n);
+    fast_pass_bwd<9, 256>(buf1, buf0, tw, lo_n);
+    fast_pass_bwd<16, 16>(buf0, buf1, tw, lo_n);
+    fast_pass_bwd<16, 1>(buf1, buf0, tw, lo_n);      // buf0 = conj(M * (y_even + i y_odd)), natural order
+
+    const float inv_m = 1.0f / (float)M;
+    float ay = 0.f;
+    float2 y[M / NT];
+#pragma unroll
+    for (int i = 0; i < M / NT; ++i) {
+        const float2 v = buf0[sk(tid + i * NT)];
+        y[i] = make_float2(v.x * inv_m, -v.y * inv_m);
+        ay += fabsf(y[i].x) + fabsf(y[i].y);
+    }
+    const float amp_y = block_sum_n(ay, scratch, NW) / (float)T;
+    const float g = amp_x / (amp_y + 1e-14f);
+#pragma unroll
+    for (int i = 0; i < M / NT; ++i) dst[tid + i * NT] = make_float2(y[i].x * g, y[i].y * g);
+}
+
 __global__ void fix_length_kernel(const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
                                   const int32_t* __restrict__ pad_before, float* __restrict__ out, int T) {
     const int b = blockIdx.x;
@@ -414,6 +761,7 @@ static int get_plan(int T, FftPlan* out) {
     plan.tw_t = d_t;
     HB_CUDA_OK(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     g_plans[{dev, T}] = plan;
     *out = plan;
     return HB_OK;
@@ -443,10 +791,18 @@ extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_b
     FftPlan plan;
     int rc = get_plan(T, &plan);
     if (rc) return rc;
-    const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
-    augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
-                                                                     reinterpret_cast<const float2*>(rir_spec_bank_dev),
-                                                                     params_dev, out_dev, T, plan);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(clips_dev) | reinterpret_cast<uintptr_t>(out_dev) |
+                           reinterpret_cast<uintptr_t>(colored_bases_dev)) & 7) == 0;
+    if (T == kFastT && aligned) {
+        augment_fast_kernel<<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+            clips_dev, noise_bank_dev, colored_bases_dev, reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev,
+            out_dev, plan);
+    } else {
+        const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
+        augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
+                                                                         reinterpret_cast<const float2*>(rir_spec_bank_dev),
+                                                                         params_dev, out_dev, T, plan);
+    }
     HB_LAUNCHED();
     return HB_OK;
 }
