@@ -35,7 +35,7 @@ struct hb_embed_model {
     int64_t w_off[hb::kNumConv];       // float offset of each layer's kernel
     int64_t b_off[hb::kNumConv];       // float offset of each layer's bias
     void* tc = nullptr;                // tensor-core path's repacked weights (embed_tc.cu)
-    void* tcg = nullptr;               // block 1's Toeplitz-packed weights (embed_tcg.cu)
+    void* tcg = nullptr;               // blocks 1-2: Toeplitz-packed weights (embed_tcg.cu)
     int device = 0;
 };
 
@@ -55,10 +55,12 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel_dev, int B, int F, 
                    int n_slots, float* out_dev, void* workspace_dev, int64_t workspace_bytes, cudaStream_t stream);
 int64_t tc_activation(const hb_embed_model* m, const float* mel_dev, int B, int F, int layer, float* out_dev,
                       int64_t out_capacity, void* workspace_dev, int64_t workspace_bytes, cudaStream_t stream);
-// embed_tcg.cu (block 1, four positions per accumulator column)
+// embed_tcg.cu (blocks 1 and 2, several positions per accumulator column)
 int tcg_prepare(hb_embed_model* m, const float* weights_host);
 void tcg_release(hb_embed_model* m);
 int tcg_block1(const hb_embed_model* m, const float* mel_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st);
+int tcg_block2(const hb_embed_model* m, const __half* in_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
                cudaStream_t st);
 int tcg_check_timeout();
 }  // namespace hb

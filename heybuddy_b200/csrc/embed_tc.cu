@@ -822,7 +822,7 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
 
     int rc;
     if ((rc = tcg_block1(m, mel, hA, B, F, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 1, g[1], hA, hB, B, 4, 16, 0, nullptr, -1, st))) return rc;
+    if ((rc = tcg_block2(m, hA, hB, B, g[1].T_in, nullptr, -1, st))) return rc;
     if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc;
     if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc;
     for (int p = 0; p < 2; ++p)
@@ -858,25 +858,30 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         const int last_layer_of_block = p.first_layer + p.n_layers - 1;
         int dbg_layer = -1;
         if (last && layer != last_layer_of_block) dbg_layer = (layer == 0) ? 100 : layer - p.first_layer;
-        if (b == 0) {
-            // block 1 runs on the grouped kernel (embed_tcg.cu), which dumps f32 NHWC directly
+        if (b <= 1) {
+            // blocks 1-2 run on the grouped kernels (embed_tcg.cu), which dump f32 NHWC directly
+            const __half* in_h = reinterpret_cast<const __half*>(in);
             if (dbg_layer >= 0) {
-                const int T = (layer == 0) ? g[0].T_in : g[0].T_in - 2;
-                const int64_t n = (int64_t)B * T * kMels * 24;
+                int t_convs = 0;
+                for (int li = (b == 0 ? 0 : p.first_layer); li <= layer; ++li) t_convs += (kLayers[li].kh == 3);
+                const int T = g[b].T_in - 2 * t_convs;
+                const int64_t n = (int64_t)B * T * p.F * kLayers[layer].cout;
                 if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
-                int rc = tcg_block1(m, mel, bufs[which], B, F, out, dbg_layer, st);
+                int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, out, dbg_layer, st)
+                                : tcg_block2(m, in_h, bufs[which], B, g[1].T_in, out, dbg_layer, st);
                 if (rc) return rc;
                 if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("hb_embed_activation: kernel failed"); return HB_ERR_CUDA; }
                 if (check_timeout() != HB_OK) return HB_ERR_CUDA;
                 return n;
             }
-            int rc = tcg_block1(m, mel, bufs[which], B, F, nullptr, -1, st);
+            int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, nullptr, -1, st)
+                            : tcg_block2(m, in_h, bufs[which], B, g[1].T_in, nullptr, -1, st);
             if (rc) return rc;
         } else if (dbg_layer >= 0) {
             const int64_t need = (int64_t)g[b].grid * g[b].ch_alloc * g[b].P_alloc * 16;
             if (cudaMalloc(&dbg_mem, need) != cudaSuccess) { set_error("hb_embed_activation: debug allocation failed"); return HB_ERR_CUDA; }
         }
-        if (b > 0) {
+        if (b > 1) {
             int rc = launch_block(m, b, g[b], in, bufs[which], B, in_chunks[b], in_F[b], 0, reinterpret_cast<__half*>(dbg_mem), dbg_layer, st);
             if (rc) { if (dbg_mem) cudaFree(dbg_mem); return rc; }
         }

@@ -1,28 +1,29 @@
-// K7, block 1 (conv2d .. conv2d_3 + 2x2 max-pool): tcgen05 implicit GEMMs with FOUR output positions per column.
+// K7, blocks 1 and 2 (conv2d .. conv2d_3 + 2x2 pool; conv2d_4 .. conv2d_7 + 1x2 pool): tcgen05 implicit GEMMs with
+// G = 4 (24 channels) or G = 2 (48 channels) output positions per accumulator column.
 //
 // Why a second kernel: an SS tcgen05.mma costs max(141, N/2 + 43) cycles whatever M is (scripts/micro/umma_bench.cu),
 // and block 1 has only 24 channels, so the one-position-per-column form of embed_tc.cu fills 24 of the 128 M rows
-// and pays 6 MMAs (3 taps x K = 32) per 256 positions.  Here M carries (sub-position i = 0..3, cout = 24) = 96
-// rows: a column is a group of four adjacent positions ALONG THE CONV AXIS, K runs over the six input positions the
-// group touches (6 x 24 = 144 = nine K = 16 steps) and the A operand is the banded Toeplitz matrix of the 3-tap
-// kernel (zeros where a tap does not connect).  9 MMAs per 1024 positions instead of 24: block 1 needs 162 MMAs
-// per 1.44 s clip instead of 504, and a third of the epilogue calls.
+// and pays 6 MMAs (3 taps x K = 32) per 256 positions.  Here M carries (sub-position i = 0..G-1, cout) = 96
+// rows: a column is a group of G adjacent positions ALONG THE CONV AXIS, K runs over the G + 2 input positions the
+// group touches (block 1: 6 x 24 = 144 = nine K = 16 steps) and the A operand is the banded Toeplitz matrix of the
+// 3-tap kernel (zeros where a tap does not connect).  Block 1: 9 MMAs per 1024 positions instead of 24, 162 MMAs
+// per 1.44 s clip instead of 504, and a third of the epilogue calls; block 2 (G = 2): 12 per 512 instead of 18.
 //
 // Layouts (all [plane][column][8 x fp16], 16-byte records, one plane per (phase, 8-channel chunk), 4096 B planes):
-//   T (input of a time conv):  plane (t mod 4, chunk), column (t div 4) * 32 + pi(f),  pi(f) = (f mod 4) * 8 + f div 4
-//   F (input of the freq conv): plane (f mod 4, chunk), column 1 + 9 t + f div 4  (group 8 of every row and column 0
-//                               are the zero SAME padding)
-//   P (pre-pool output):        [chunk][t * 32 + pi(f)]
+//   T (input of a time conv):  plane (t mod G, chunk), column (t div G) * F + pi(f),  pi(f) = (f mod G) * 8 + f div G
+//   F (input of a freq conv):  plane (f mod G, chunk), column 1 + 9 t + f div G  (group 8 of every row and column 0
+//                              are the zero SAME padding; F / G = 8 in both blocks)
+//   P (pre-pool output):       [chunk][t * F + pi(f)]
 // A K step is two K chunks = two plane addresses: the UMMA descriptor's (start, LBO) pair expresses any of them, so
 // there is still no im2col.  The permutation pi makes every stmatrix of the epilogue (8 consecutive columns x 8
 // channels) land on 128 contiguous bytes in either target layout.  The tile's single activation buffer is rewritten
 // in place: a layer has one accumulator tile (N = 256 columns), so all of its MMAs have completed (tcgen05.commit)
 // before the first epilogue store.
 //
-// Tile = 28 input rows of one clip -> 24 conv2d_3 rows -> 12 pooled rows; twin launch shape (320 threads, 2 CTAs/SM,
-// 256 TMEM columns each) like embed_tc.cu.  Warp 0 issues MMAs, warp 1 streams the next layer's weights as soon as
+// Tile = 28 (block 1) / 26 (block 2) input rows of one clip -> 24 / 22 output rows; twin launch shape (320 threads,
+// 2 CTAs/SM, 256 TMEM columns each) like embed_tc.cu.  Warp 0 issues MMAs, warp 1 streams the next layer's weights as soon as
 // the current MMAs have completed and zeroes the SAME padding, warps 2-9 run the epilogue (TMEM lane quadrant q holds
-// sub-position i = q: rows 32 q + 8 chunk + channel).
+// row chunks 3 q .. 3 q + 2 of the 12 (sub-position, 8-channel chunk) row chunks).
 //
 // NaN note: the zero Toeplitz entries multiply neighbouring positions of the same tile, so a non-finite activation
 // reaches up to 3 more positions of its own clip than in the reference arithmetic (0 * inf); finite data is unaffected.
@@ -36,50 +37,67 @@ namespace {
 
 constexpr int kGThreads = 320;
 constexpr int kGEpiWarps = 8;
-constexpr int kGTt = 28;            // input rows per tile
-constexpr int kGRowsOut = 24;       // conv2d_3 rows per tile (pre-pool)
-constexpr int kGC = 24;             // channels
-constexpr int kGPlane = 4096;       // bytes per plane
-constexpr int kGPlanes = 12;
+constexpr int kGPlane = 4096;       // bytes per plane (256 columns)
+constexpr int kGPlanes = 12;        // G * channel chunks
 constexpr int kGActBytes = kGPlanes * kGPlane;
-constexpr int kGPlainPlane = kGTt * 32 * 16;     // layout P bytes per chunk
-constexpr int kGWBytes = 18 * 128 * 16;          // one layer's A operand: [K chunk 18][row 128][8]
 constexpr int kGTmemCols = 256;
+constexpr int kGMaxLayers = 4;
+
+// G positions per column, CC 8-channel chunks (G * CC = 12 row chunks = 96 M rows), F freq bins (F / G = 8), TT input rows
+// per tile (multiple of G), NL tensor-core layers alternating freq / time, CIN0 input chunks of the first layer.
+template <int G_, int CC_, int F_, int TT_, int NL_, bool FIRST_FREQ_, int CIN0_, int POOL_T_, bool MEL_IN_, int OUT_CH_, int CONV0_>
+struct GCfg {
+    static constexpr int G = G_, CC = CC_, F = F_, TT = TT_, NL = NL_, CIN0 = CIN0_, POOL_T = POOL_T_, OUT_CH = OUT_CH_;
+    static constexpr bool FIRST_FREQ = FIRST_FREQ_, MEL_IN = MEL_IN_;
+    static constexpr int CONV0 = CONV0_;                       // conv index (layer table) of the first tensor-core layer
+    static constexpr int C = CC * 8;
+    static constexpr int N_TIME = FIRST_FREQ ? NL / 2 : (NL + 1) / 2;
+    static constexpr int ROWS_OUT = TT - 2 * N_TIME;
+    static constexpr int W_MAX = (G + 2) * CC * 2048;          // largest A operand: [K chunk][row 128][8]
+    static constexpr int PLAIN = TT * F * 16;                  // layout P bytes per chunk
+    static_assert(G * CC == kGPlanes && F / G == 8 && TT % G == 0 && (TT / G) * F <= 256 && TT * 9 <= 256, "tile shape");
+    static_assert(CC * PLAIN <= kGActBytes && ROWS_OUT % POOL_T == 0, "tile shape");
+    __host__ __device__ static constexpr bool is_freq(int l) { return ((l & 1) == 0) == FIRST_FREQ; }
+    __host__ __device__ static constexpr int cin(int l) { return l == 0 ? CIN0 : CC; }
+    __host__ __device__ static constexpr int kchunks(int l) { return (G + 2) * cin(l); }
+    __host__ __device__ static constexpr int w_bytes(int l) { return kchunks(l) * 2048; }
+    __host__ __device__ static constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
+    __host__ __device__ static constexpr int pi(int f) { return (f % G) * 8 + f / G; }
+    // byte offset (within the activation buffer, relative to column n = 0) of K chunk kk of layer l
+    __host__ __device__ static constexpr uint32_t koff(int l, int kk) {
+        const int ci = cin(l), ord = kk / ci, c = kk - ord * ci;
+        if (is_freq(l)) {                                       // input offsets df = 0 .. G-1, G, -1
+            const int fm = ord < G ? ord : (ord == G ? 0 : G - 1);
+            const int sh = ord < G ? 1 : (ord == G ? 2 : 0);    // 1 + column shift (column 0 is the guard)
+            return (uint32_t)((fm * ci + c) * kGPlane + sh * 16);
+        }
+        return (uint32_t)(((ord % G) * ci + c) * kGPlane + (ord / G) * F * 16);   // dt = ord
+    }
+};
+using Cfg1 = GCfg<4, 3, 32, 28, 3, false, 3, 2, true, 4, 1>;    // conv2d (CUDA cores) + conv2d_1..3, pool 2x2
+using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4>;    // conv2d_4..7, pool 1x2
 
 struct GArgs {
-    const float* mel;             // f32 [clips][in_T][32]
-    __half* out;                  // fp16 chunk-major [clips][4][T_out][16][8] (chunk 3 = zero padding to K = 32)
-    const unsigned char* w;       // 3 layers x kGWBytes
-    const float* bias;            // 3 x 24
-    const float* l0_w;            // conv2d kernel f32 [3][24] + bias [24]
-    float* dbg;                   // optional f32 NHWC [clips][dbg_T][32][24] activation dump
-    int dbg_layer;                // -1 none, 100 = conv2d output, 0 / 1 = conv2d_1 / conv2d_2 output
+    const void* in;               // MEL_IN: mel f32 [clips][in_T][32]; else fp16 chunk-major [clips][in_chunks][in_T][F][8]
+    __half* out;                  // fp16 chunk-major [clips][OUT_CH][T_out][F / 2][8]
+    const unsigned char* w;       // packed A operands of the NL layers
+    const float* bias;            // NL x C
+    const float* l0_w;            // MEL_IN: conv2d kernel f32 [3][24] + bias [24]
+    float* dbg;                   // optional f32 NHWC [clips][dbg_T][F][C] activation dump
+    int dbg_layer;                // -1 none, 100 = staged input (MEL_IN: conv2d output), l = output of tensor-core layer l
     int dbg_T;
-    int n_clips, in_T, T_out, tiles_per_clip;
+    int n_clips, in_T, in_chunks, T_out, tiles_per_clip;
 };
 
+template <class Cfg>
 struct GSmemHeader {
     uint64_t tmem_full, tmem_empty, wbar;
     uint32_t tmem_base;
     uint32_t pad[1];
-    float bias[3 * kGC];
+    float bias[kGMaxLayers * 48];
     float l0[3 * 24 + 24 + 8];
-    uint16_t tab[3][256];         // column -> ((byte offset >> 4) << 1) | invalid, per layer
+    uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
 };
-
-__host__ __device__ constexpr int pi_f(int f) { return (f & 3) * 8 + (f >> 2); }
-
-// byte offset (within the activation buffer) of K chunk kk of a time / freq layer, relative to column n = 0
-__device__ __forceinline__ uint32_t koff_time(int kk) {
-    const int dt = kk / 3, c = kk - dt * 3;
-    return (uint32_t)(((dt & 3) * 3 + c) * kGPlane + (dt >> 2) * 32 * 16);
-}
-__device__ __forceinline__ uint32_t koff_freq(int kk) {
-    const int ord = kk / 3, c = kk - ord * 3;                 // df = 0, 1, 2, 3, 4, -1
-    const int fm = ord < 4 ? ord : (ord == 4 ? 0 : 3);
-    const int sh = ord < 4 ? 1 : (ord == 4 ? 2 : 0);          // 1 + column shift (column 0 is the guard)
-    return (uint32_t)((fm * 3 + c) * kGPlane + sh * 16);
-}
 
 template <bool kTwo>
 __device__ __forceinline__ void g_epilogue(uint32_t taddr, const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,
@@ -103,17 +121,19 @@ __device__ __forceinline__ void g_epilogue(uint32_t taddr, const uint16_t* __res
     }
 }
 
-__global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a) {
+template <class Cfg>
+__global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) {
+    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C;
     extern __shared__ __align__(128) unsigned char smem[];
-    GSmemHeader& hdr = *reinterpret_cast<GSmemHeader*>(smem);
+    GSmemHeader<Cfg>& hdr = *reinterpret_cast<GSmemHeader<Cfg>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char* wbuf = smem + ((sizeof(GSmemHeader) + 127) & ~127);
-    unsigned char* act = wbuf + kGWBytes;
+    unsigned char* wbuf = smem + ((sizeof(GSmemHeader<Cfg>) + 127) & ~127);
+    unsigned char* act = wbuf + Cfg::W_MAX;
     unsigned char* dump = act + kGActBytes + 512;             // 512 B finite guard for reads past the last plane
-    float* mel_tile = reinterpret_cast<float*>(dump + 128);
+    float* mel_tile = reinterpret_cast<float*>(dump + 128);   // MEL_IN only
 
     const int clip = blockIdx.x / a.tiles_per_clip, tile = blockIdx.x - clip * a.tiles_per_clip;
-    const int row0 = tile * kGRowsOut;
+    const int row0 = tile * Cfg::ROWS_OUT;
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
@@ -123,46 +143,44 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kGTmemCols);
-    for (int i = tid; i < 3 * kGC; i += kGThreads) hdr.bias[i] = a.bias[i];
-    for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
-    for (int i = tid; i < 3 * 256; i += kGThreads) {
+    for (int i = tid; i < NL * C; i += kGThreads) hdr.bias[(i / C) * 48 + i % C] = a.bias[i];
+    if (Cfg::MEL_IN)
+        for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
+    for (int i = tid; i < NL * 256; i += kGThreads) {
         const int l = i >> 8, n = i & 255;
         int off, valid;
-        if (l == 1) {
-            // freq layer, column n = 9 t + fg -> layout T: plane (t mod 4, .), column (t div 4) * 32 + (i * 8 +) fg
+        if (Cfg::is_freq(l)) {
+            // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
             const int t = n / 9, fg = n - t * 9;
-            valid = fg < 8 && t < kGTt;
-            off = (t & 3) * 3 * kGPlane + ((t >> 2) * 32 + fg) * 16;
+            valid = fg < 8 && t < TT;
+            off = (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16;
         } else {
-            const int tq = n >> 5, pf = n & 31;
-            valid = tq < kGTt / 4;
-            if (l == 0) off = (pf >> 3) * 3 * kGPlane + (1 + 36 * tq + (pf & 7)) * 16;   // -> layout F
-            else off = (128 * tq + pf) * 16;                                              // -> layout P
+            const int tq = n / F, pf = n - tq * F;
+            valid = tq < TT / G;
+            if (l < NL - 1) off = (pf >> 3) * CC * kGPlane + (1 + 9 * G * tq + (pf & 7)) * 16;   // -> layout F
+            else off = (G * tq * F + pf) * 16;                                                    // -> layout P
         }
         hdr.tab[l][n] = (uint16_t)(valid ? ((off >> 4) << 1) : 1);
     }
+    // everything the MMAs may read must be finite: clear the activation buffer and its guard
+    for (int i = tid; i < (kGActBytes + 512) / 16; i += kGThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr.tmem_base;
 
     if (warp == 1 && lane == 0) {
-        mbar_expect_tx(&hdr.wbar, (uint32_t)kGWBytes);
-        bulk_g2s(wbuf, a.w, (uint32_t)kGWBytes, &hdr.wbar);
+        mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
+        bulk_g2s(wbuf, a.w, (uint32_t)Cfg::w_bytes(0), &hdr.wbar);
     }
 
-    // ---- stage: mel rows -> conv2d (Cin = 1, CUDA cores) -> layout T ---------------------------------------
-    {
-        const float* mel = a.mel + (int64_t)clip * a.in_T * kMels;
-        for (int i = tid; i < kGTt * kMels; i += kGThreads) {
+    // ---- stage the input tile -----------------------------------------------------------------------------
+    if (Cfg::MEL_IN) {
+        // mel rows -> conv2d (Cin = 1, CUDA cores) -> layout T
+        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip * a.in_T * kMels;
+        for (int i = tid; i < TT * kMels; i += kGThreads) {
             const int r = i / kMels;
             mel_tile[i] = (row0 + r < a.in_T) ? __ldg(mel + (int64_t)(row0 + r) * kMels + (i - r * kMels)) : 0.f;
-        }
-        // the rows past the tile (t = 28..31) only feed outputs that are dropped, but must be finite
-        for (int i = tid; i < kGPlanes * 32 + 32; i += kGThreads) {
-            unsigned char* p = i < kGPlanes * 32 ? act + (i >> 5) * kGPlane + ((kGTt / 4) * 32 + (i & 31)) * 16
-                                                 : act + kGActBytes + (i - kGPlanes * 32) * 16;
-            *reinterpret_cast<uint4*>(p) = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
         const int ch = lane & 3;
@@ -176,9 +194,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
             bb[j] = ch < 3 ? hdr.l0[72 + c] : 0.f;
         }
         if (ch < 3) {
-            for (int r = warp; r < kGTt; r += kGThreads / 32) {
+            for (int r = warp; r < TT; r += kGThreads / 32) {
                 const float* mrow = mel_tile + r * kMels;
-                unsigned char* dst = act + ((r & 3) * 3 + ch) * kGPlane + (r >> 2) * 32 * 16;
+                unsigned char* dst = act + ((r % G) * Cfg::CIN0 + ch) * kGPlane + (r / G) * F * 16;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     const int f = (lane >> 2) + 8 * j4;
@@ -193,39 +211,55 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
                         acc = fmaf(m2, w2[j], acc);
                         v[j] = leaky(acc + bb[j]);
                     }
-                    *reinterpret_cast<uint4*>(dst + pi_f(f) * 16) =
+                    *reinterpret_cast<uint4*>(dst + Cfg::pi(f) * 16) =
                         make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
                 }
             }
         }
+    } else {
+        // fp16 chunk-major rows [row0, row0 + TT) -> layout F (the first layer is a freq conv), 16-byte cp.async records
+        static_assert(Cfg::MEL_IN || Cfg::FIRST_FREQ, "global-input blocks start with a freq conv");
+        const uint4* in = reinterpret_cast<const uint4*>(a.in) + (int64_t)clip * a.in_chunks * a.in_T * F;
+        for (int i = tid; i < Cfg::CIN0 * TT * F; i += kGThreads) {
+            const int c = i / (TT * F), rem = i - c * (TT * F);
+            const int t = rem / F, f = rem - t * F;
+            if (row0 + t < a.in_T)
+                cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + 9 * t + f / G) * 16,
+                           in + ((int64_t)c * a.in_T + row0 + t) * F + f, 16u);
+        }
+        cp_async_wait_all();
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
 
-    auto dump_layout_t = [&](int t_layer) {
-        // f32 NHWC dump of the tile's rows from layout T (profiling / parity hook only)
-        for (int i = tid; i < kGRowsOut * 32 * kGC; i += kGThreads) {
-            const int c = i % kGC, f = (i / kGC) & 31, t = i / (kGC * 32);
-            if (row0 + t >= t_layer) continue;
-            const __half* p = reinterpret_cast<const __half*>(act + ((t & 3) * 3 + (c >> 3)) * kGPlane + ((t >> 2) * 32 + pi_f(f)) * 16);
-            a.dbg[(((int64_t)clip * t_layer + row0 + t) * 32 + f) * kGC + c] = __half2float(p[c & 7]);
+    // f32 NHWC dump of the tile's rows from layout T / F (parity hook only)
+    auto dump_act = [&](bool layout_f, int cc_planes) {
+        for (int i = tid; i < Cfg::ROWS_OUT * F * C; i += kGThreads) {
+            const int c = i % C, f = (i / C) % F, t = i / (C * F);
+            if (row0 + t >= a.dbg_T || (c >> 3) >= cc_planes) continue;
+            const unsigned char* p = layout_f ? act + ((f % G) * cc_planes + (c >> 3)) * kGPlane + (1 + 9 * t + f / G) * 16
+                                              : act + ((t % G) * cc_planes + (c >> 3)) * kGPlane + ((t / G) * F + Cfg::pi(f)) * 16;
+            a.dbg[(((int64_t)clip * a.dbg_T + row0 + t) * F + f) * C + c] = __half2float(reinterpret_cast<const __half*>(p)[c & 7]);
         }
     };
-    if (a.dbg != nullptr && a.dbg_layer == 100) dump_layout_t(a.dbg_T);
+    if (a.dbg != nullptr && a.dbg_layer == 100) dump_act(Cfg::FIRST_FREQ, Cfg::CIN0);
 
-    // ---- conv2d_1 (time), conv2d_2 (freq), conv2d_3 (time) ---------------------------------------------------
+    // ---- the block's tensor-core layers ------------------------------------------------------------------------
     const uint32_t act_u32 = smem_u32(act), w_u32 = smem_u32(wbuf);
-    for (int l = 0; l < 3; ++l) {
-        const bool freq = (l == 1);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        constexpr int kDummy = 0; (void)kDummy;
+        const bool freq = Cfg::is_freq(l);
+        const bool last = (l == NL - 1);
         if (warp == 0) {
             mbar_wait(&hdr.wbar, (uint32_t)(l & 1));
             if (l > 0) mbar_wait(&hdr.tmem_empty, (uint32_t)((l - 1) & 1));
             tc_fence_after();
             const uint32_t idesc = make_idesc(128, 256);
+            const int ksteps = Cfg::kchunks(l) / 2;
 #pragma unroll 1
-            for (int j = 0; j < 9; ++j) {
-                const uint32_t o0 = freq ? koff_freq(2 * j) : koff_time(2 * j);
-                const uint32_t o1 = freq ? koff_freq(2 * j + 1) : koff_time(2 * j + 1);
+            for (int j = 0; j < ksteps; ++j) {
+                const uint32_t o0 = Cfg::koff(l, 2 * j), o1 = Cfg::koff(l, 2 * j + 1);
                 const uint64_t ad = make_desc(w_u32 + (uint32_t)(2 * j) * 2048u, 2048u, 128u);
                 const uint64_t bd = make_desc(act_u32 + o0, o1 - o0, 128u);
                 if (elect_one()) umma_f16(tmem_base, ad, bd, idesc, j > 0 ? 1u : 0u);
@@ -235,14 +269,14 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
         } else if (warp == 1) {
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
             mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
-            if (lane == 0 && l < 2) {
-                mbar_expect_tx(&hdr.wbar, (uint32_t)kGWBytes);
-                bulk_g2s(wbuf, a.w + (size_t)(l + 1) * kGWBytes, (uint32_t)kGWBytes, &hdr.wbar);
+            if (lane == 0 && !last) {
+                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(l + 1));
+                bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), (uint32_t)Cfg::w_bytes(l + 1), &hdr.wbar);
             }
-            if (l == 0) {
-                // layout F zero padding: column 0 and group 8 of every row, in all 12 planes
-                for (int i = lane; i < kGPlanes * (kGTt + 1); i += 32) {
-                    const int pl = i / (kGTt + 1), k = i - pl * (kGTt + 1);
+            if (!freq && !last) {
+                // the epilogue is writing layout F: zero its SAME padding (column 0 and group 8 of every row, all planes)
+                for (int i = lane; i < kGPlanes * (TT + 1); i += 32) {
+                    const int pl = i / (TT + 1), k = i - pl * (TT + 1);
                     const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
                     *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
                 }
@@ -250,23 +284,24 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
             fence_proxy_async();
             __syncwarp();
         } else {
-            const int e = warp - 2, quad = warp & 3, part = e >> 2;   // quad = sub-position i, part = column half
-            const float* bias = hdr.bias + l * kGC;
+            const int e = warp - 2, quad = warp & 3, part = e >> 2;   // TMEM lane quadrant, column half
+            const float* bias = hdr.bias + l * 48;
             const uint16_t* tab = hdr.tab[l];
             const int m = lane >> 3;
-            // byte offset of (sub-position quad, chunk cc) in the layer's target layout
-            const uint32_t g2_unit = l == 0 ? 9u * 16u : (l == 1 ? 128u : 512u);
-            const uint32_t cc_stride = l == 2 ? (uint32_t)kGPlainPlane : (uint32_t)kGPlane;
+            // (sub-position i, chunk cc) -> byte offset in the layer's target layout
+            const uint32_t i_unit = freq ? 128u : (last ? (uint32_t)(F * 16) : 9u * 16u);
+            const uint32_t cc_unit = last ? (uint32_t)Cfg::PLAIN : (uint32_t)kGPlane;
             const uint32_t dump_lane = smem_u32(dump) + (uint32_t)((lane & 7) * 16);
             mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int cc_lane = h == 0 ? (m & 1) : 2;                       // chunk this lane's stmatrix rows belong to
+                const int rc0 = 3 * quad + 2 * h;                                // row chunk of octet 0 of this 16-lane half
+                const int rc_lane = h == 0 ? rc0 + (m & 1) : rc0;               // row chunk this lane's stmatrix rows belong to
                 const int pg = h == 0 ? (m >> 1) : (m & 1);                     // +8 column group of this lane's matrix
-                const uint32_t base_lane = act_u32 + (uint32_t)quad * g2_unit + (uint32_t)cc_lane * cc_stride;
-                const float b0 = bias[(2 * h) * 8 + (lane >> 2)];
-                const float b1 = h == 0 ? bias[8 + (lane >> 2)] : 0.f;
+                const uint32_t base_lane = act_u32 + (uint32_t)(rc_lane / CC) * i_unit + (uint32_t)(rc_lane % CC) * cc_unit;
+                const float b0 = bias[(rc0 % CC) * 8 + (lane >> 2)];
+                const float b1 = h == 0 ? bias[((rc0 + 1) % CC) * 8 + (lane >> 2)] : 0.f;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const int col = part * 128 + sub * 64;
@@ -284,45 +319,39 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (a.dbg != nullptr && a.dbg_layer == l) {
-            if (l == 0) {
-                for (int i = tid; i < kGRowsOut * 32 * kGC; i += kGThreads) {
-                    const int c = i % kGC, f = (i / kGC) & 31, t = i / (kGC * 32);
-                    if (row0 + t >= a.dbg_T) continue;
-                    const __half* p = reinterpret_cast<const __half*>(act + ((f & 3) * 3 + (c >> 3)) * kGPlane + (1 + 9 * t + (f >> 2)) * 16);
-                    a.dbg[(((int64_t)clip * a.dbg_T + row0 + t) * 32 + f) * kGC + c] = __half2float(p[c & 7]);
-                }
-            } else if (l == 1) {
-                dump_layout_t(a.dbg_T);
-            }
-        }
+        if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
 
-    // ---- 2x2 max-pool + store (fp16 chunk-major [clip][4][T_out][16][8]) --------------------------------------
+    // ---- max-pool + store (fp16 chunk-major [clip][OUT_CH][T_out][F / 2][8]) -----------------------------------
     {
-        constexpr int rows_p = kGRowsOut / 2;
+        constexpr int PT = Cfg::POOL_T, Fo = F / 2;
+        constexpr int rows_p = Cfg::ROWS_OUT / PT;
         const int rowp0 = tile * rows_p;
         uint4* out = reinterpret_cast<uint4*>(a.out);
-        for (int i = tid; i < 4 * rows_p * 16; i += kGThreads) {
-            const int ch = i / (rows_p * 16);
-            const int rem = i - ch * rows_p * 16;
-            const int rp = rem >> 4, fo = rem & 15;
+        for (int i = tid; i < Cfg::OUT_CH * rows_p * Fo; i += kGThreads) {
+            const int ch = i / (rows_p * Fo);
+            const int rem = i - ch * rows_p * Fo;
+            const int rp = rem / Fo, fo = rem - rp * Fo;
             if (rowp0 + rp >= a.T_out) continue;
             uint4 o = make_uint4(0, 0, 0, 0);
-            if (ch < 3) {
-                const unsigned char* base = act + ch * kGPlainPlane + (2 * rp) * 32 * 16 + pi_f(2 * fo) * 16;
+            if (ch < CC) {
+                const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(2 * fo) * 16;   // pi(2 fo + 1) = pi(2 fo) + 8
                 const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + 8 * 16);
-                const uint4 x2 = *reinterpret_cast<const uint4*>(base + 32 * 16), x3 = *reinterpret_cast<const uint4*>(base + 40 * 16);
                 const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
                 const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
-                const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
                 __half2 mx[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(__hmax2_nan(h0[j], h1[j]), __hmax2_nan(h2[j], h3[j]));
+                for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(h0[j], h1[j]);
+                if (PT == 2) {
+                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + (F + 8) * 16);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
+                    const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(mx[j], __hmax2_nan(h2[j], h3[j]));
+                }
                 o = *reinterpret_cast<uint4*>(mx);
             }
-            out[(((int64_t)clip * 4 + ch) * a.T_out + rowp0 + rp) * 16 + fo] = o;
+            out[(((int64_t)clip * Cfg::OUT_CH + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
         }
     }
     __syncthreads();
@@ -330,18 +359,92 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block1_kernel(const GArgs a)
 }
 
 struct GWeights {
-    unsigned char* w = nullptr;
-    float* bias = nullptr;
+    unsigned char* w[2] = {nullptr, nullptr};
+    float* bias[2] = {nullptr, nullptr};
     float* l0 = nullptr;
 };
 
+template <class Cfg>
 size_t tcg_smem_bytes() {
-    return ((sizeof(GSmemHeader) + 127) & ~(size_t)127) + kGWBytes + kGActBytes + 512 + 128 + kGTt * kMels * sizeof(float) + 128;
+    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 +
+           (Cfg::MEL_IN ? Cfg::TT * kMels * sizeof(float) : 0) + 128;
+}
+
+// Banded Toeplitz A operands of the block's layers: [layer][K chunk][row 128][8 cin]; row = 32 q + 8 o + channel holds row
+// chunk rc = 3 q + o (o < 3) = (sub-position rc / CC, channel chunk rc % CC).
+template <class Cfg>
+int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const std::vector<int64_t>& b_off, unsigned char** w_dev,
+             float** bias_dev) {
+    constexpr int G = Cfg::G, CC = Cfg::CC;
+    std::vector<__half> packed((size_t)Cfg::w_off(Cfg::NL) / 2, __float2half_rn(0.f));
+    std::vector<float> bias((size_t)Cfg::NL * Cfg::C);
+    for (int l = 0; l < Cfg::NL; ++l) {
+        const int li = Cfg::CONV0 + l;
+        const ConvLayer& L = kLayers[li];
+        const bool freq = Cfg::is_freq(l);
+        HB_REQUIRE(L.cin == Cfg::cin(l) * 8 && L.cout == Cfg::C && L.kh * L.kw == 3 && L.leaky && (L.kw == 3) == freq,
+                   "tcg: unexpected layer table entry for conv2d_%d", li);
+        const float* w = weights_host + w_off[li];            // [tap][cin][cout]
+        const int ci_chunks = Cfg::cin(l);
+        for (int kk = 0; kk < Cfg::kchunks(l); ++kk) {
+            const int ord = kk / ci_chunks, c = kk % ci_chunks;
+            const int d = freq ? (ord <= G ? ord : -1) : ord;  // input offset within the group: df (freq) or dt (time)
+            if (kk & 1) HB_REQUIRE(Cfg::koff(l, kk) > Cfg::koff(l, kk - 1), "tcg: K chunk pair %d of layer %d is not address-ordered", kk / 2, l);
+            for (int row = 0; row < 128; ++row) {
+                const int q = row >> 5, o = (row >> 3) & 3, r = row & 7;
+                if (o >= 3) continue;
+                const int rc = 3 * q + o, i = rc / CC, cc = rc % CC;
+                const int tap = freq ? d - i + 1 : d - i;
+                if (tap < 0 || tap > 2) continue;
+                for (int e = 0; e < 8; ++e)
+                    packed[(size_t)Cfg::w_off(l) / 2 + ((size_t)kk * 128 + row) * 8 + e] =
+                        __float2half_rn(w[((int64_t)tap * L.cin + c * 8 + e) * L.cout + cc * 8 + r]);
+            }
+        }
+        for (int n = 0; n < Cfg::C; ++n) bias[(size_t)l * Cfg::C + n] = weights_host[b_off[li] + n];
+    }
+    HB_CUDA_OK(cudaMalloc(w_dev, packed.size() * 2));
+    HB_CUDA_OK(cudaMemcpy(*w_dev, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    HB_CUDA_OK(cudaMalloc(bias_dev, bias.size() * sizeof(float)));
+    HB_CUDA_OK(cudaMemcpy(*bias_dev, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return HB_OK;
+}
+
+template <class Cfg>
+int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __half* out, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st) {
+    GArgs a;
+    a.in = in;
+    a.out = out;
+    a.w = gw->w[which];
+    a.bias = gw->bias[which];
+    a.l0_w = gw->l0;
+    a.dbg = dbg;
+    a.dbg_layer = dbg ? dbg_layer : -1;
+    int t_convs = 0;   // time convs up to and including the dumped layer shrink its valid rows
+    if (dbg && dbg_layer != 100)
+        for (int l = 0; l <= dbg_layer && l < Cfg::NL; ++l) t_convs += !Cfg::is_freq(l);
+    a.dbg_T = in_T - 2 * t_convs;
+    a.n_clips = B;
+    a.in_T = in_T;
+    a.in_chunks = in_chunks;
+    a.T_out = (in_T - 2 * Cfg::N_TIME) / Cfg::POOL_T;
+    const int rows_needed = dbg ? a.dbg_T : Cfg::POOL_T * a.T_out;
+    a.tiles_per_clip = std::max(1, ceil_div(rows_needed, Cfg::ROWS_OUT));
+    HB_REQUIRE((int64_t)B * a.tiles_per_clip < (1ll << 31), "tcg: grid too large");
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(tcg_block_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg_smem_bytes<Cfg>()));
+        HB_CUDA_OK(cudaFuncSetAttribute(tcg_block_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    tcg_block_kernel<Cfg><<<B * a.tiles_per_clip, kGThreads, tcg_smem_bytes<Cfg>(), st>>>(a);
+    HB_LAUNCHED();
+    return HB_OK;
 }
 
 }  // namespace
 
-// Pack conv2d_1..3 as banded Toeplitz A operands: [layer][K chunk 18][row 128][8 cin], row = 32 i + 8 chunk + channel.
 int tcg_prepare(hb_embed_model* m, const float* weights_host) {
     GWeights* gw = new GWeights();
     std::vector<int64_t> w_off(kNumConv), b_off(kNumConv);
@@ -352,44 +455,22 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
         b_off[i] = off;
         off += kLayers[i].cout;
     }
-    std::vector<__half> packed((size_t)3 * kGWBytes / 2, __float2half_rn(0.f));
-    std::vector<float> bias(3 * kGC);
-    for (int l = 0; l < 3; ++l) {
-        const ConvLayer& L = kLayers[1 + l];
-        HB_REQUIRE(L.cin == kGC && L.cout == kGC && L.kh * L.kw == 3 && L.leaky, "tcg: unexpected layer table for conv2d_%d", 1 + l);
-        const bool freq = (L.kw == 3);
-        HB_REQUIRE(freq == (l == 1), "tcg: conv2d_%d orientation", 1 + l);
-        const float* w = weights_host + w_off[1 + l];            // [tap][cin][cout]
-        for (int kk = 0; kk < 18; ++kk) {
-            const int ord = kk / 3, c = kk % 3;
-            const int d = freq ? (ord < 5 ? ord : -1) : ord;       // input offset within the group: df (freq) or dt (time)
-            for (int row = 0; row < 128; ++row) {
-                const int i = row >> 5, cc = (row >> 3) & 3, r = row & 7;
-                if (cc >= 3) continue;
-                const int tap = freq ? d - i + 1 : d - i;
-                if (tap < 0 || tap > 2) continue;
-                for (int e = 0; e < 8; ++e)
-                    packed[(((size_t)l * 18 + kk) * 128 + row) * 8 + e] =
-                        __float2half_rn(w[((int64_t)tap * kGC + c * 8 + e) * kGC + cc * 8 + r]);
-            }
-        }
-        for (int n = 0; n < kGC; ++n) bias[l * kGC + n] = weights_host[b_off[1 + l] + n];
-    }
-    HB_CUDA_OK(cudaMalloc(&gw->w, packed.size() * 2));
-    HB_CUDA_OK(cudaMemcpy(gw->w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
-    HB_CUDA_OK(cudaMalloc(&gw->bias, bias.size() * sizeof(float)));
-    HB_CUDA_OK(cudaMemcpy(gw->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    m->tcg = gw;
+    int rc;
+    if ((rc = tcg_pack<Cfg1>(weights_host, w_off, b_off, &gw->w[0], &gw->bias[0]))) return rc;
+    if ((rc = tcg_pack<Cfg2>(weights_host, w_off, b_off, &gw->w[1], &gw->bias[1]))) return rc;
     HB_CUDA_OK(cudaMalloc(&gw->l0, (3 * 24 + 24) * sizeof(float)));
     HB_CUDA_OK(cudaMemcpy(gw->l0, weights_host + w_off[0], (3 * 24 + 24) * sizeof(float), cudaMemcpyHostToDevice));
-    m->tcg = gw;
     return HB_OK;
 }
 
 void tcg_release(hb_embed_model* m) {
     GWeights* gw = reinterpret_cast<GWeights*>(m->tcg);
     if (!gw) return;
-    cudaFree(gw->w);
-    cudaFree(gw->bias);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(gw->w[i]);
+        cudaFree(gw->bias[i]);
+    }
     cudaFree(gw->l0);
     delete gw;
     m->tcg = nullptr;
@@ -401,37 +482,22 @@ int tcg_block1(const hb_embed_model* m, const float* mel, __half* out, int B, in
                cudaStream_t st) {
     const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
     HB_REQUIRE(gw != nullptr, "tcg weights missing");
-    GArgs a;
-    a.mel = mel;
-    a.out = out;
-    a.w = gw->w;
-    a.bias = gw->bias;
-    a.l0_w = gw->l0;
-    a.dbg = dbg;
-    a.dbg_layer = dbg ? dbg_layer : -1;
-    a.dbg_T = dbg_layer == 100 ? in_T : (dbg_layer == 0 || dbg_layer == 1 ? in_T - 2 : in_T - 4);
-    a.n_clips = B;
-    a.in_T = in_T;
-    a.T_out = (in_T - 4) / 2;
-    // cover every row a dump may ask for (in_T for the conv2d output), i.e. ceil(in_T / 24) tiles when dumping
-    const int rows_needed = dbg ? a.dbg_T : 2 * a.T_out;
-    a.tiles_per_clip = std::max(1, ceil_div(rows_needed, kGRowsOut));
-    HB_REQUIRE((int64_t)B * a.tiles_per_clip < (1ll << 31), "tcg: grid too large");
-    static bool configured = false;
-    if (!configured) {
-        HB_CUDA_OK(cudaFuncSetAttribute(tcg_block1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg_smem_bytes()));
-        HB_CUDA_OK(cudaFuncSetAttribute(tcg_block1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
-    }
-    tcg_block1_kernel<<<B * a.tiles_per_clip, kGThreads, tcg_smem_bytes(), st>>>(a);
-    HB_LAUNCHED();
-    return HB_OK;
+    return tcg_launch<Cfg1>(gw, 0, mel, 0, out, B, in_T, dbg, dbg_layer, st);
+}
+
+// block 1 output fp16 [B][4][in_T][16][8] -> conv2d_7 output after its 1x2 pool, fp16 chunk-major [B][6][in_T - 4][8][8].
+// dbg != nullptr: dump the activation after conv2d_4 / 5 / 6 (dbg_layer 0 / 1 / 2) as f32 NHWC [B][rows][16][48].
+int tcg_block2(const hb_embed_model* m, const __half* in, __half* out, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st) {
+    const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
+    HB_REQUIRE(gw != nullptr, "tcg weights missing");
+    return tcg_launch<Cfg2>(gw, 1, in, 4, out, B, in_T, dbg, dbg_layer, st);
 }
 
 int tcg_check_timeout() {
     unsigned int flag = 0;
     HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
-    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (block 1): an mbarrier wait timed out (pipeline bug)");
+    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (blocks 1-2): an mbarrier wait timed out (pipeline bug)");
     return HB_OK;
 }
 
