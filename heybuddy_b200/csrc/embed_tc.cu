@@ -28,6 +28,7 @@
 //    phases) is fused into the tail block's loader; block 5 runs on the same kernel, 6 clips per CTA.
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace hb {
@@ -823,7 +824,9 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     int rc;
     if ((rc = tcg_block1(m, mel, hA, B, F, nullptr, -1, st))) return rc;
     if ((rc = tcg_block2(m, hA, hB, B, g[1].T_in, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc;
+    static const bool b3_old = getenv("HB_B3_OLD") != nullptr;   // A/B switch while tuning
+    if (b3_old) { if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc; }
+    else if ((rc = tcg_block3(m, hB, hA, B, g[2].T_in, nullptr, -1, st))) return rc;
     if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc;
     for (int p = 0; p < 2; ++p)
         if (need_phase[p] && (rc = launch_block(m, 4, gt, hB, tmp[p], B, 12, 4, p, nullptr, -1, st))) return rc;
@@ -858,8 +861,8 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         const int last_layer_of_block = p.first_layer + p.n_layers - 1;
         int dbg_layer = -1;
         if (last && layer != last_layer_of_block) dbg_layer = (layer == 0) ? 100 : layer - p.first_layer;
-        if (b <= 1) {
-            // blocks 1-2 run on the grouped kernels (embed_tcg.cu), which dump f32 NHWC directly
+        if (b <= 2) {
+            // blocks 1-3 run on the grouped kernels (embed_tcg.cu), which dump f32 NHWC directly
             const __half* in_h = reinterpret_cast<const __half*>(in);
             if (dbg_layer >= 0) {
                 int t_convs = 0;
@@ -868,20 +871,22 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
                 const int64_t n = (int64_t)B * T * p.F * kLayers[layer].cout;
                 if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
                 int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, out, dbg_layer, st)
-                                : tcg_block2(m, in_h, bufs[which], B, g[1].T_in, out, dbg_layer, st);
+                       : b == 1 ? tcg_block2(m, in_h, bufs[which], B, g[1].T_in, out, dbg_layer, st)
+                                : tcg_block3(m, in_h, bufs[which], B, g[2].T_in, out, dbg_layer, st);
                 if (rc) return rc;
                 if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("hb_embed_activation: kernel failed"); return HB_ERR_CUDA; }
                 if (check_timeout() != HB_OK) return HB_ERR_CUDA;
                 return n;
             }
             int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, nullptr, -1, st)
-                            : tcg_block2(m, in_h, bufs[which], B, g[1].T_in, nullptr, -1, st);
+                   : b == 1 ? tcg_block2(m, in_h, bufs[which], B, g[1].T_in, nullptr, -1, st)
+                            : tcg_block3(m, in_h, bufs[which], B, g[2].T_in, nullptr, -1, st);
             if (rc) return rc;
         } else if (dbg_layer >= 0) {
             const int64_t need = (int64_t)g[b].grid * g[b].ch_alloc * g[b].P_alloc * 16;
             if (cudaMalloc(&dbg_mem, need) != cudaSuccess) { set_error("hb_embed_activation: debug allocation failed"); return HB_ERR_CUDA; }
         }
-        if (b > 1) {
+        if (b > 2) {
             int rc = launch_block(m, b, g[b], in, bufs[which], B, in_chunks[b], in_F[b], 0, reinterpret_cast<__half*>(dbg_mem), dbg_layer, st);
             if (rc) { if (dbg_mem) cudaFree(dbg_mem); return rc; }
         }
@@ -942,6 +947,8 @@ extern "C" int hb_debug_tc_fine(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, hb::g_tc_fine, sizeof(long long) * 8 * 48) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+extern "C" int hb_debug_tcg_times(long long* out_host) { return hb::tcg_debug_times(out_host); }
 
 extern "C" int hb_debug_tc_times(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, hb::g_tc_times, sizeof(long long) * 8 * 16) == cudaSuccess ? 0 : -2;

@@ -38,7 +38,7 @@ namespace {
 constexpr int kGThreads = 320;
 constexpr int kGEpiWarps = 8;
 constexpr int kGPlane = 4096;       // bytes per plane (256 columns)
-constexpr int kGPlanes = 12;        // G * channel chunks
+constexpr int kGPlanes = 12;        // planes allocated (G * channel chunks <= 12)
 constexpr int kGActBytes = kGPlanes * kGPlane;
 constexpr int kGTmemCols = 256;
 constexpr int kGMaxLayers = 4;
@@ -53,29 +53,39 @@ struct GCfg {
     static constexpr int C = CC * 8;
     static constexpr int N_TIME = FIRST_FREQ ? NL / 2 : (NL + 1) / 2;
     static constexpr int ROWS_OUT = TT - 2 * N_TIME;
-    static constexpr int W_MAX = (G + 2) * CC * 2048;          // largest A operand: [K chunk][row 128][8]
+    static constexpr int W_MAX = (((G + 2) * CC + 1) & ~1) * 2048;   // largest A operand: [K chunk][row 128][8]
     static constexpr int PLAIN = TT * F * 16;                  // layout P bytes per chunk
-    static_assert(G * CC == kGPlanes && F / G == 8 && TT % G == 0 && (TT / G) * F <= 256 && TT * 9 <= 256, "tile shape");
+    static constexpr int RC = G * CC;                          // row chunks (sub-position, channel chunk); rows = 8 RC <= 96
+    static_assert(RC <= kGPlanes && F / G == 8 && TT % G == 0 && (TT / G) * F <= 256 && TT * 9 <= 256, "tile shape");
     static_assert(CC * PLAIN <= kGActBytes && ROWS_OUT % POOL_T == 0, "tile shape");
     __host__ __device__ static constexpr bool is_freq(int l) { return ((l & 1) == 0) == FIRST_FREQ; }
     __host__ __device__ static constexpr int cin(int l) { return l == 0 ? CIN0 : CC; }
-    __host__ __device__ static constexpr int kchunks(int l) { return (G + 2) * cin(l); }
+    __host__ __device__ static constexpr int kreal(int l) { return (G + 2) * cin(l); }            // real K chunks
+    __host__ __device__ static constexpr int kchunks(int l) { return (kreal(l) + 1) & ~1; }        // padded to whole K = 16 steps
     __host__ __device__ static constexpr int w_bytes(int l) { return kchunks(l) * 2048; }
     __host__ __device__ static constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
     __host__ __device__ static constexpr int pi(int f) { return (f % G) * 8 + f / G; }
+    // K chunk kk = c * (G + 2) + ord (channel chunk major).  ord -> input offset d within the group: time d = dt = ord;
+    // freq d = df: 0 .. G, -1 (G >= 2) or -1, 0, 1 (G = 1) -- orders that keep every K-step pair address-ordered.
+    __host__ __device__ static constexpr int kd(int l, int kk) {
+        const int ord = kk % (G + 2);
+        return !is_freq(l) ? ord : (G == 1 ? ord - 1 : (ord <= G ? ord : -1));
+    }
     // byte offset (within the activation buffer, relative to column n = 0) of K chunk kk of layer l
     __host__ __device__ static constexpr uint32_t koff(int l, int kk) {
-        const int ci = cin(l), ord = kk / ci, c = kk - ord * ci;
-        if (is_freq(l)) {                                       // input offsets df = 0 .. G-1, G, -1
-            const int fm = ord < G ? ord : (ord == G ? 0 : G - 1);
-            const int sh = ord < G ? 1 : (ord == G ? 2 : 0);    // 1 + column shift (column 0 is the guard)
+        if (kk >= kreal(l)) return koff(l, kk - 1) + 16;       // zero-weight pad chunk: any finite column
+        const int ci = cin(l), c = kk / (G + 2), d = kd(l, kk);
+        if (is_freq(l)) {
+            const int fm = ((d % G) + G) % G;
+            const int sh = d < 0 ? 0 : (d >= G ? 2 : 1);        // 1 + column shift (column 0 is the guard)
             return (uint32_t)((fm * ci + c) * kGPlane + sh * 16);
         }
-        return (uint32_t)(((ord % G) * ci + c) * kGPlane + (ord / G) * F * 16);   // dt = ord
+        return (uint32_t)(((d % G) * ci + c) * kGPlane + (d / G) * F * 16);
     }
 };
 using Cfg1 = GCfg<4, 3, 32, 28, 3, false, 3, 2, true, 4, 1>;    // conv2d (CUDA cores) + conv2d_1..3, pool 2x2
 using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4>;    // conv2d_4..7, pool 1x2
+using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
 
 struct GArgs {
     const void* in;               // MEL_IN: mel f32 [clips][in_T][32]; else fp16 chunk-major [clips][in_chunks][in_T][F][8]
@@ -94,7 +104,7 @@ struct GSmemHeader {
     uint64_t tmem_full, tmem_empty, wbar;
     uint32_t tmem_base;
     uint32_t pad[1];
-    float bias[kGMaxLayers * 48];
+    float bias[kGMaxLayers * 72];
     float l0[3 * 24 + 24 + 8];
     uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
 };
@@ -121,6 +131,26 @@ __device__ __forceinline__ void g_epilogue(uint32_t taddr, const uint16_t* __res
     }
 }
 
+// All MMAs of layer l: descriptor = base + compile-time immediates (start address >> 4 in bits [0,14), LBO >> 4 in [16,30)).
+template <class Cfg, int L, int J>
+__device__ __forceinline__ void issue_steps(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
+    if constexpr (J < Cfg::kchunks(L) / 2) {
+        constexpr uint32_t o0 = Cfg::koff(L, 2 * J), o1 = Cfg::koff(L, 2 * J + 1);
+        static_assert(o1 > o0 && ((o1 - o0) >> 4) < 0x4000, "K chunk pair must be address-ordered");
+        constexpr uint64_t a_inc = (uint64_t)((2 * J * 2048) >> 4);
+        constexpr uint64_t b_inc = (uint64_t)(o0 >> 4) | ((uint64_t)((o1 - o0) >> 4) << 16);
+        umma_f16(d_tmem, a_base + a_inc, b_base + b_inc, idesc, J > 0 ? 1u : 0u);
+        issue_steps<Cfg, L, J + 1>(d_tmem, a_base, b_base, idesc);
+    }
+}
+template <class Cfg>
+__device__ __forceinline__ void issue_layer(int l, uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
+    if (l == 0) issue_steps<Cfg, 0, 0>(d_tmem, a_base, b_base, idesc);
+    else if (l == 1) issue_steps<Cfg, 1, 0>(d_tmem, a_base, b_base, idesc);
+    else if (l == 2) issue_steps<Cfg, 2, 0>(d_tmem, a_base, b_base, idesc);
+    else if (Cfg::NL > 3) issue_steps<Cfg, (Cfg::NL > 3 ? 3 : 0), 0>(d_tmem, a_base, b_base, idesc);
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) {
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C;
@@ -135,6 +165,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     const int clip = blockIdx.x / a.tiles_per_clip, tile = blockIdx.x - clip * a.tiles_per_clip;
     const int row0 = tile * Cfg::ROWS_OUT;
 
+    TC_STAMP(0);
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&hdr.tmem_full, 1);
@@ -143,7 +174,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kGTmemCols);
-    for (int i = tid; i < NL * C; i += kGThreads) hdr.bias[(i / C) * 48 + i % C] = a.bias[i];
+    for (int i = tid; i < NL * C; i += kGThreads) hdr.bias[(i / C) * 72 + i % C] = a.bias[i];
     if (Cfg::MEL_IN)
         for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
     for (int i = tid; i < NL * 256; i += kGThreads) {
@@ -168,6 +199,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr.tmem_base;
+    TC_STAMP(1);
 
     if (warp == 1 && lane == 0) {
         mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
@@ -231,6 +263,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
+    TC_STAMP(2);
 
     // f32 NHWC dump of the tile's rows from layout T / F (parity hook only)
     auto dump_act = [&](bool layout_f, int cc_planes) {
@@ -251,20 +284,23 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         constexpr int kDummy = 0; (void)kDummy;
         const bool freq = Cfg::is_freq(l);
         const bool last = (l == NL - 1);
+#define TCG_FINE(i) do { if (l == 1 && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
         if (warp == 0) {
+            TCG_FINE(9);
             mbar_wait(&hdr.wbar, (uint32_t)(l & 1));
+            TCG_FINE(10);
             if (l > 0) mbar_wait(&hdr.tmem_empty, (uint32_t)((l - 1) & 1));
             tc_fence_after();
-            const uint32_t idesc = make_idesc(128, 256);
-            const int ksteps = Cfg::kchunks(l) / 2;
-#pragma unroll 1
-            for (int j = 0; j < ksteps; ++j) {
-                const uint32_t o0 = Cfg::koff(l, 2 * j), o1 = Cfg::koff(l, 2 * j + 1);
-                const uint64_t ad = make_desc(w_u32 + (uint32_t)(2 * j) * 2048u, 2048u, 128u);
-                const uint64_t bd = make_desc(act_u32 + o0, o1 - o0, 128u);
-                if (elect_one()) umma_f16(tmem_base, ad, bd, idesc, j > 0 ? 1u : 0u);
+            // One elected lane issues the whole layer; l and j are compile-time, so every descriptor is an immediate
+            // (an issue loop that computes offsets at run time is slower than the MMAs it feeds).
+            if (elect_one()) {
+                constexpr uint32_t idesc = make_idesc(128, 256);
+                const uint64_t a_base = make_desc(w_u32, 2048u, 128u);
+                const uint64_t b_base = make_desc(act_u32, 0u, 128u);
+                issue_layer<Cfg>(l, tmem_base, a_base, b_base, idesc);
+                umma_commit(&hdr.tmem_full);   // same thread: the commit tracks the MMAs this thread issued
             }
-            if (elect_one()) umma_commit(&hdr.tmem_full);
+            TCG_FINE(11);
             __syncwarp();
         } else if (warp == 1) {
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
@@ -285,7 +321,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             __syncwarp();
         } else {
             const int e = warp - 2, quad = warp & 3, part = e >> 2;   // TMEM lane quadrant, column half
-            const float* bias = hdr.bias + l * 48;
+            const float* bias = hdr.bias + l * 72;
             const uint16_t* tab = hdr.tab[l];
             const int m = lane >> 3;
             // (sub-position i, chunk cc) -> byte offset in the layer's target layout
@@ -294,9 +330,11 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             const uint32_t dump_lane = smem_u32(dump) + (uint32_t)((lane & 7) * 16);
             mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
             tc_fence_after();
+            if (warp == 2) TCG_FINE(12);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int rc0 = 3 * quad + 2 * h;                                // row chunk of octet 0 of this 16-lane half
+                if (rc0 >= Cfg::RC) continue;
                 const int rc_lane = h == 0 ? rc0 + (m & 1) : rc0;               // row chunk this lane's stmatrix rows belong to
                 const int pg = h == 0 ? (m >> 1) : (m & 1);                     // +8 column group of this lane's matrix
                 const uint32_t base_lane = act_u32 + (uint32_t)(rc_lane / CC) * i_unit + (uint32_t)(rc_lane % CC) * cc_unit;
@@ -315,10 +353,12 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr.tmem_empty);
             fence_proxy_async();
+            if (warp == 2) TCG_FINE(13); else if (warp == 9) TCG_FINE(14);
         }
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        TC_STAMP(3 + l);
         if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
 
@@ -335,15 +375,16 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             if (rowp0 + rp >= a.T_out) continue;
             uint4 o = make_uint4(0, 0, 0, 0);
             if (ch < CC) {
-                const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(2 * fo) * 16;   // pi(2 fo + 1) = pi(2 fo) + 8
-                const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + 8 * 16);
+                constexpr int dpi = (Cfg::pi(1) - Cfg::pi(0)) * 16;   // pi(2 fo + 1) - pi(2 fo), in bytes
+                const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(2 * fo) * 16;
+                const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + dpi);
                 const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
                 const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
                 __half2 mx[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(h0[j], h1[j]);
                 if (PT == 2) {
-                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + (F + 8) * 16);
+                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + dpi);
                     const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
                     const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
 #pragma unroll
@@ -355,12 +396,14 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         }
     }
     __syncthreads();
+    TC_STAMP(7);
     if (warp == 0) tmem_dealloc(tmem_base, kGTmemCols);
+    TC_STAMP(8);
 }
 
 struct GWeights {
-    unsigned char* w[2] = {nullptr, nullptr};
-    float* bias[2] = {nullptr, nullptr};
+    unsigned char* w[3] = {nullptr, nullptr, nullptr};
+    float* bias[3] = {nullptr, nullptr, nullptr};
     float* l0 = nullptr;
 };
 
@@ -385,15 +428,14 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
         HB_REQUIRE(L.cin == Cfg::cin(l) * 8 && L.cout == Cfg::C && L.kh * L.kw == 3 && L.leaky && (L.kw == 3) == freq,
                    "tcg: unexpected layer table entry for conv2d_%d", li);
         const float* w = weights_host + w_off[li];            // [tap][cin][cout]
-        const int ci_chunks = Cfg::cin(l);
         for (int kk = 0; kk < Cfg::kchunks(l); ++kk) {
-            const int ord = kk / ci_chunks, c = kk % ci_chunks;
-            const int d = freq ? (ord <= G ? ord : -1) : ord;  // input offset within the group: df (freq) or dt (time)
+            const int c = kk / (G + 2), d = Cfg::kd(l, kk);    // channel chunk, input offset within the group (df or dt)
             if (kk & 1) HB_REQUIRE(Cfg::koff(l, kk) > Cfg::koff(l, kk - 1), "tcg: K chunk pair %d of layer %d is not address-ordered", kk / 2, l);
+            if (kk >= Cfg::kreal(l)) continue;                  // zero pad chunk
             for (int row = 0; row < 128; ++row) {
                 const int q = row >> 5, o = (row >> 3) & 3, r = row & 7;
-                if (o >= 3) continue;
                 const int rc = 3 * q + o, i = rc / CC, cc = rc % CC;
+                if (o >= 3 || rc >= Cfg::RC) continue;
                 const int tap = freq ? d - i + 1 : d - i;
                 if (tap < 0 || tap > 2) continue;
                 for (int e = 0; e < 8; ++e)
@@ -459,6 +501,7 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
     int rc;
     if ((rc = tcg_pack<Cfg1>(weights_host, w_off, b_off, &gw->w[0], &gw->bias[0]))) return rc;
     if ((rc = tcg_pack<Cfg2>(weights_host, w_off, b_off, &gw->w[1], &gw->bias[1]))) return rc;
+    if ((rc = tcg_pack<Cfg3>(weights_host, w_off, b_off, &gw->w[2], &gw->bias[2]))) return rc;
     HB_CUDA_OK(cudaMalloc(&gw->l0, (3 * 24 + 24) * sizeof(float)));
     HB_CUDA_OK(cudaMemcpy(gw->l0, weights_host + w_off[0], (3 * 24 + 24) * sizeof(float), cudaMemcpyHostToDevice));
     return HB_OK;
@@ -467,7 +510,7 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
 void tcg_release(hb_embed_model* m) {
     GWeights* gw = reinterpret_cast<GWeights*>(m->tcg);
     if (!gw) return;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         cudaFree(gw->w[i]);
         cudaFree(gw->bias[i]);
     }
@@ -494,10 +537,24 @@ int tcg_block2(const hb_embed_model* m, const __half* in, __half* out, int B, in
     return tcg_launch<Cfg2>(gw, 1, in, 4, out, B, in_T, dbg, dbg_layer, st);
 }
 
+// block 2 output fp16 [B][6][in_T][8][8] -> conv2d_11 output after its 2x2 pool, fp16 chunk-major [B][10][(in_T - 4) / 2][4][8]
+// (chunk 9 = zero padding to K = 80).  dbg: activation after conv2d_8 / 9 / 10 (dbg_layer 0 / 1 / 2), f32 NHWC [B][rows][8][72].
+int tcg_block3(const hb_embed_model* m, const __half* in, __half* out, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st) {
+    const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
+    HB_REQUIRE(gw != nullptr, "tcg weights missing");
+    return tcg_launch<Cfg3>(gw, 2, in, 6, out, B, in_T, dbg, dbg_layer, st);
+}
+
+// profiling aid: phase timestamps (start, setup, staged, layers.., stored, dealloc) of the first 8 CTAs of the last launch
+int tcg_debug_times(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, g_tc_times, sizeof(long long) * 8 * 16) == cudaSuccess ? 0 : -2;
+}
+
 int tcg_check_timeout() {
     unsigned int flag = 0;
     HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
-    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (blocks 1-2): an mbarrier wait timed out (pipeline bug)");
+    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (blocks 1-3): an mbarrier wait timed out (pipeline bug)");
     return HB_OK;
 }
 
