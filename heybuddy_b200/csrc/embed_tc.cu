@@ -281,34 +281,40 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
             mbar_wait(&hdr.wbar[wb], wpar);
             tc_fence_after();
             TC_FINE(0, 1);
-            const uint32_t idesc = make_idesc(128, kTileN);
-            const uint32_t w_base = smem_u32(wcur), x_base = smem_u32(cur);
-            const int ksteps = L.cin_chunks / 2;
-            const uint32_t w_region = (uint32_t)L.w_rows * 16u;   // bytes of one (tap, k chunk) region = LBO of A
-            const uint64_t a_hi = make_desc(0, w_region, 128), b_hi = make_desc(0, chunk_stride, 128);
-            for (int nt = 0; nt < a.n_nt; ++nt) {
-                const int it = tile_counter + nt;
-                const int slot = it % kSlots;
-                if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
-                tc_fence_after();
-                TC_FINE(0, 2 + 2 * nt);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
-                uint32_t acc = 0;
-                for (int tap = 0; tap < L.ntaps; ++tap) {
-                    const int shift = L.tap_rows[tap] * S + L.tap_cols[tap];
-                    uint32_t w_addr = w_base + (uint32_t)(tap * L.cin_chunks) * w_region;
-                    uint32_t x_addr = x_base + (uint32_t)((nt * kTileN + shift) * 16);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ad = a_hi | (uint64_t)((w_addr >> 4) & 0x3FFF);
-                        const uint64_t bd = b_hi | (uint64_t)((x_addr >> 4) & 0x3FFF);
-                        if (elect_one()) umma_f16(d_tmem, ad, bd, idesc, acc);
-                        acc = 1;
-                        w_addr += 2 * w_region;
-                        x_addr += 2 * chunk_stride;
+            // One elected lane issues the whole layer (a lean loop: the issue path must not be slower than the MMAs it feeds:
+            // an N = 256 MMA takes 128 cycles, scripts/micro/umma_swizzle.cu).
+            if (elect_one()) {
+                const uint32_t idesc = make_idesc(128, kTileN);
+                const int ksteps = L.cin_chunks / 2;
+                const uint32_t w_region16 = (uint32_t)L.w_rows;                // (bytes of one (tap, k chunk) region = LBO of A) >> 4
+                const uint64_t a_hi = make_desc(0, w_region16 * 16u, 128), b_hi = make_desc(0, chunk_stride, 128);
+                const uint32_t w_base16 = smem_u32(wcur) >> 4, x_base16 = smem_u32(cur) >> 4, chunk16 = chunk_stride >> 4;
+                int shift[3];
+                for (int tap = 0; tap < 3; ++tap) shift[tap] = L.tap_rows[tap] * S + L.tap_cols[tap];
+                const int ntaps = L.ntaps, cin_chunks = L.cin_chunks;
+                for (int nt = 0; nt < a.n_nt; ++nt) {
+                    const int it = tile_counter + nt;
+                    const int slot = it % kSlots;
+                    if (it >= kSlots) mbar_wait(&hdr.tmem_empty[slot], (uint32_t)(((it / kSlots) - 1) & 1));
+                    tc_fence_after();
+                    TC_FINE(0, 2 + 2 * nt);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap) {
+                        if (tap >= ntaps) break;
+                        uint32_t w16 = w_base16 + (uint32_t)(tap * cin_chunks) * w_region16;
+                        uint32_t x16 = x_base16 + (uint32_t)(nt * kTileN + shift[tap]);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            umma_f16(d_tmem, a_hi | (uint64_t)w16, b_hi | (uint64_t)x16, idesc, acc);
+                            acc = 1;
+                            w16 += 2 * w_region16;
+                            x16 += 2 * chunk16;
+                        }
                     }
+                    umma_commit(&hdr.tmem_full[slot]);
+                    TC_FINE(0, 3 + 2 * nt);
                 }
-                if (elect_one()) umma_commit(&hdr.tmem_full[slot]);
-                TC_FINE(0, 3 + 2 * nt);
             }
             __syncwarp();
         } else if (warp == 1) {
