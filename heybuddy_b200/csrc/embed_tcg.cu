@@ -93,6 +93,7 @@ struct GArgs {
     const unsigned char* w;       // packed A operands of the NL layers
     const float* bias;            // NL x C
     const float* l0_w;            // MEL_IN: conv2d kernel f32 [3][24] + bias [24]
+    const uint16_t* tab;          // [NL][256] column -> ((byte offset >> 4) << 1) | invalid of every layer's epilogue
     float* dbg;                   // optional f32 NHWC [clips][dbg_T][F][C] activation dump
     int dbg_layer;                // -1 none, 100 = staged input (MEL_IN: conv2d output), l = output of tensor-core layer l
     int dbg_T;
@@ -106,24 +107,23 @@ struct GSmemHeader {
     uint32_t pad[1];
     float bias[kGMaxLayers * 72];
     float l0[3 * 24 + 24 + 8];
-    uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
+    alignas(16) uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
 };
 
+// bias + LeakyReLU + fp16 + stmatrix of one 16-lane x 64-column fragment (already in registers)
 template <bool kTwo>
-__device__ __forceinline__ void g_epilogue(uint32_t taddr, const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,
+__device__ __forceinline__ void g_epilogue(const uint32_t (&r)[32], const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,
                                            uint32_t dump_lane, float b0, float b1) {
-    float v[32];
-    tmem_ld_16x256b_64cols(taddr, v);
 #pragma unroll
     for (int g = 0; g < 8; g += 2) {
         const uint32_t e = tab[n_lane + 8 * g];
         const uint32_t addr = (e & 1u) ? dump_lane : base_lane + ((e >> 1) << 4);
-        const float x0 = leaky(v[4 * g + 0] + b0), x1 = leaky(v[4 * g + 1] + b0);
-        const float x4 = leaky(v[4 * g + 4] + b0), x5 = leaky(v[4 * g + 5] + b0);
+        const float x0 = leaky(__uint_as_float(r[4 * g + 0]) + b0), x1 = leaky(__uint_as_float(r[4 * g + 1]) + b0);
+        const float x4 = leaky(__uint_as_float(r[4 * g + 4]) + b0), x5 = leaky(__uint_as_float(r[4 * g + 5]) + b0);
         const uint32_t ra = pack_half2(x0, x1), rc = pack_half2(x4, x5);
         if (kTwo) {
-            const float x2 = leaky(v[4 * g + 2] + b1), x3 = leaky(v[4 * g + 3] + b1);
-            const float x6 = leaky(v[4 * g + 6] + b1), x7 = leaky(v[4 * g + 7] + b1);
+            const float x2 = leaky(__uint_as_float(r[4 * g + 2]) + b1), x3 = leaky(__uint_as_float(r[4 * g + 3]) + b1);
+            const float x6 = leaky(__uint_as_float(r[4 * g + 6]) + b1), x7 = leaky(__uint_as_float(r[4 * g + 7]) + b1);
             stmatrix_x4_trans(addr, ra, pack_half2(x2, x3), rc, pack_half2(x6, x7));
         } else {
             stmatrix_x2_trans(addr, ra, rc);
@@ -166,6 +166,17 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     const int row0 = tile * Cfg::ROWS_OUT;
 
     TC_STAMP(0);
+    // MEL_IN: the tile's mel rows start their trip from global memory now and land in shared memory after the setup barrier
+    constexpr int kMelPerThread = (TT * kMels + kGThreads - 1) / kGThreads;
+    float mel_reg[Cfg::MEL_IN ? kMelPerThread : 1];
+    if (Cfg::MEL_IN) {
+        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip * a.in_T * kMels;
+#pragma unroll
+        for (int k = 0; k < kMelPerThread; ++k) {
+            const int i = tid + k * kGThreads, r = i / kMels;
+            mel_reg[k] = (i < TT * kMels && row0 + r < a.in_T) ? __ldg(mel + (int64_t)row0 * kMels + i) : 0.f;
+        }
+    }
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&hdr.tmem_full, 1);
@@ -177,22 +188,8 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     for (int i = tid; i < NL * C; i += kGThreads) hdr.bias[(i / C) * 72 + i % C] = a.bias[i];
     if (Cfg::MEL_IN)
         for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
-    for (int i = tid; i < NL * 256; i += kGThreads) {
-        const int l = i >> 8, n = i & 255;
-        int off, valid;
-        if (Cfg::is_freq(l)) {
-            // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
-            const int t = n / 9, fg = n - t * 9;
-            valid = fg < 8 && t < TT;
-            off = (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16;
-        } else {
-            const int tq = n / F, pf = n - tq * F;
-            valid = tq < TT / G;
-            if (l < NL - 1) off = (pf >> 3) * CC * kGPlane + (1 + 9 * G * tq + (pf & 7)) * 16;   // -> layout F
-            else off = (G * tq * F + pf) * 16;                                                    // -> layout P
-        }
-        hdr.tab[l][n] = (uint16_t)(valid ? ((off >> 4) << 1) : 1);
-    }
+    for (int i = tid; i < NL * 256 / 8; i += kGThreads)       // epilogue scatter tables, precomputed on the host (tcg_tables)
+        reinterpret_cast<uint4*>(&hdr.tab[0][0])[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
     // everything the MMAs may read must be finite: clear the activation buffer and its guard
     for (int i = tid; i < (kGActBytes + 512) / 16; i += kGThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
@@ -209,11 +206,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     // ---- stage the input tile -----------------------------------------------------------------------------
     if (Cfg::MEL_IN) {
         // mel rows -> conv2d (Cin = 1, CUDA cores) -> layout T
-        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip * a.in_T * kMels;
-        for (int i = tid; i < TT * kMels; i += kGThreads) {
-            const int r = i / kMels;
-            mel_tile[i] = (row0 + r < a.in_T) ? __ldg(mel + (int64_t)(row0 + r) * kMels + (i - r * kMels)) : 0.f;
-        }
+#pragma unroll
+        for (int k = 0; k < kMelPerThread; ++k)
+            if (tid + k * kGThreads < TT * kMels) mel_tile[tid + k * kGThreads] = mel_reg[k];
         __syncthreads();
         const int ch = lane & 3;
         float w0[8], w1[8], w2[8], bb[8];
@@ -330,23 +325,30 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
             tc_fence_after();
             if (warp == 2) TCG_FINE(12);
+            // four fragments per warp: (16-lane half h, 64-column sub); the TMEM load of fragment k + 1 is in flight while
+            // fragment k is converted and stored
+            uint32_t frag[2][32];
+            auto frag_addr = [&](int k) {
+                const int h = k >> 1, sub = k & 1;
+                return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(part * 128 + sub * 64);
+            };
+            const int n_frag = (3 * quad + 2 < Cfg::RC) ? 4 : ((3 * quad < Cfg::RC) ? 2 : 0);   // rows of half 1 / half 0 exist?
+            if (n_frag > 0) tmem_ld_16x256b_64cols_issue(frag_addr(0), frag[0]);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int k = 0; k < 4; ++k) {
+                if (k >= n_frag) break;
+                const int h = k >> 1, sub = k & 1;
+                tmem_ld_wait_32(frag[k & 1]);
+                if (k + 1 < n_frag) tmem_ld_16x256b_64cols_issue(frag_addr(k + 1), frag[(k + 1) & 1]);
                 const int rc0 = 3 * quad + 2 * h;                                // row chunk of octet 0 of this 16-lane half
-                if (rc0 >= Cfg::RC) continue;
                 const int rc_lane = h == 0 ? rc0 + (m & 1) : rc0;               // row chunk this lane's stmatrix rows belong to
                 const int pg = h == 0 ? (m >> 1) : (m & 1);                     // +8 column group of this lane's matrix
                 const uint32_t base_lane = act_u32 + (uint32_t)(rc_lane / CC) * i_unit + (uint32_t)(rc_lane % CC) * cc_unit;
                 const float b0 = bias[(rc0 % CC) * 8 + (lane >> 2)];
                 const float b1 = h == 0 ? bias[((rc0 + 1) % CC) * 8 + (lane >> 2)] : 0.f;
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int col = part * 128 + sub * 64;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)col;
-                    const int n_lane = col + 8 * pg + (lane & 7);
-                    if (h == 0) g_epilogue<true>(taddr, tab, n_lane, base_lane, dump_lane, b0, b1);
-                    else g_epilogue<false>(taddr, tab, n_lane, base_lane, dump_lane, b0, b1);
-                }
+                const int n_lane = part * 128 + sub * 64 + 8 * pg + (lane & 7);
+                if (h == 0) g_epilogue<true>(frag[k & 1], tab, n_lane, base_lane, dump_lane, b0, b1);
+                else g_epilogue<false>(frag[k & 1], tab, n_lane, base_lane, dump_lane, b0, b1);
             }
             tc_fence_before();
             __syncwarp();
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
 struct GWeights {
     unsigned char* w[3] = {nullptr, nullptr, nullptr};
     float* bias[3] = {nullptr, nullptr, nullptr};
+    uint16_t* tab[3] = {nullptr, nullptr, nullptr};
     float* l0 = nullptr;
 };
 
@@ -412,11 +415,35 @@ size_t tcg_smem_bytes() {
            (Cfg::MEL_IN ? Cfg::TT * kMels * sizeof(float) : 0) + 128;
 }
 
+// Epilogue scatter table of layer l: accumulator column n -> byte offset of its first output record in the layer's target
+// layout (the per-row-chunk part is added by the epilogue), or "invalid" for columns that are padding.
+template <class Cfg>
+void tcg_tables(std::vector<uint16_t>& tab) {
+    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL;
+    tab.assign((size_t)NL * 256, 1);
+    for (int l = 0; l < NL; ++l)
+        for (int n = 0; n < 256; ++n) {
+            int off, valid;
+            if (Cfg::is_freq(l)) {
+                // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
+                const int t = n / 9, fg = n - t * 9;
+                valid = fg < 8 && t < TT;
+                off = (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16;
+            } else {
+                const int tq = n / F, pf = n - tq * F;
+                valid = tq < TT / G;
+                if (l < NL - 1) off = (pf >> 3) * CC * kGPlane + (1 + 9 * G * tq + (pf & 7)) * 16;   // -> layout F
+                else off = (G * tq * F + pf) * 16;                                                    // -> layout P
+            }
+            if (valid) tab[(size_t)l * 256 + n] = (uint16_t)((off >> 4) << 1);
+        }
+}
+
 // Banded Toeplitz A operands of the block's layers: [layer][K chunk][row 128][8 cin]; row = 32 q + 8 o + channel holds row
 // chunk rc = 3 q + o (o < 3) = (sub-position rc / CC, channel chunk rc % CC).
 template <class Cfg>
 int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const std::vector<int64_t>& b_off, unsigned char** w_dev,
-             float** bias_dev) {
+             float** bias_dev, uint16_t** tab_dev) {
     constexpr int G = Cfg::G, CC = Cfg::CC;
     std::vector<__half> packed((size_t)Cfg::w_off(Cfg::NL) / 2, __float2half_rn(0.f));
     std::vector<float> bias((size_t)Cfg::NL * Cfg::C);
@@ -448,6 +475,10 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
     HB_CUDA_OK(cudaMemcpy(*w_dev, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     HB_CUDA_OK(cudaMalloc(bias_dev, bias.size() * sizeof(float)));
     HB_CUDA_OK(cudaMemcpy(*bias_dev, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<uint16_t> tab;
+    tcg_tables<Cfg>(tab);
+    HB_CUDA_OK(cudaMalloc(tab_dev, tab.size() * sizeof(uint16_t)));
+    HB_CUDA_OK(cudaMemcpy(*tab_dev, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     return HB_OK;
 }
 
@@ -460,6 +491,7 @@ int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __h
     a.w = gw->w[which];
     a.bias = gw->bias[which];
     a.l0_w = gw->l0;
+    a.tab = gw->tab[which];
     a.dbg = dbg;
     a.dbg_layer = dbg ? dbg_layer : -1;
     int t_convs = 0;   // time convs up to and including the dumped layer shrink its valid rows
@@ -498,9 +530,9 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
     }
     m->tcg = gw;
     int rc;
-    if ((rc = tcg_pack<Cfg1>(weights_host, w_off, b_off, &gw->w[0], &gw->bias[0]))) return rc;
-    if ((rc = tcg_pack<Cfg2>(weights_host, w_off, b_off, &gw->w[1], &gw->bias[1]))) return rc;
-    if ((rc = tcg_pack<Cfg3>(weights_host, w_off, b_off, &gw->w[2], &gw->bias[2]))) return rc;
+    if ((rc = tcg_pack<Cfg1>(weights_host, w_off, b_off, &gw->w[0], &gw->bias[0], &gw->tab[0]))) return rc;
+    if ((rc = tcg_pack<Cfg2>(weights_host, w_off, b_off, &gw->w[1], &gw->bias[1], &gw->tab[1]))) return rc;
+    if ((rc = tcg_pack<Cfg3>(weights_host, w_off, b_off, &gw->w[2], &gw->bias[2], &gw->tab[2]))) return rc;
     HB_CUDA_OK(cudaMalloc(&gw->l0, (3 * 24 + 24) * sizeof(float)));
     HB_CUDA_OK(cudaMemcpy(gw->l0, weights_host + w_off[0], (3 * 24 + 24) * sizeof(float), cudaMemcpyHostToDevice));
     return HB_OK;
@@ -512,6 +544,7 @@ void tcg_release(hb_embed_model* m) {
     for (int i = 0; i < 3; ++i) {
         cudaFree(gw->w[i]);
         cudaFree(gw->bias[i]);
+        cudaFree(gw->tab[i]);
     }
     cudaFree(gw->l0);
     delete gw;
