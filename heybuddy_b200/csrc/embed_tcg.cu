@@ -53,15 +53,19 @@ struct GCfg {
     static constexpr int C = CC * 8;
     static constexpr int N_TIME = FIRST_FREQ ? NL / 2 : (NL + 1) / 2;
     static constexpr int ROWS_OUT = TT - 2 * N_TIME;
-    static constexpr int W_MAX = (((G + 2) * CC + 1) & ~1) * 2048;   // largest A operand: [K chunk][row 128][8]
+    static constexpr int W_MAX = (((G + 2) * CC + 2) & ~1) * 2048;   // largest A operand: [K chunk][row 128][8]
     static constexpr int PLAIN = TT * F * 16;                  // layout P bytes per chunk
     static constexpr int RC = G * CC;                          // row chunks (sub-position, channel chunk); rows = 8 RC <= 96
     static_assert(RC <= kGPlanes && F / G == 8 && TT % G == 0 && (TT / G) * F <= 256 && TT * 9 <= 256, "tile shape");
     static_assert(CC * PLAIN <= kGActBytes && ROWS_OUT % POOL_T == 0, "tile shape");
     __host__ __device__ static constexpr bool is_freq(int l) { return ((l & 1) == 0) == FIRST_FREQ; }
     __host__ __device__ static constexpr int cin(int l) { return l == 0 ? CIN0 : CC; }
-    __host__ __device__ static constexpr int kreal(int l) { return (G + 2) * cin(l); }            // real K chunks
-    __host__ __device__ static constexpr int kchunks(int l) { return (kreal(l) + 1) & ~1; }        // padded to whole K = 16 steps
+    __host__ __device__ static constexpr int kreal(int l) { return (G + 2) * cin(l); }            // K chunks of the conv itself
+    // + one "ones" chunk that carries the bias (A row = [bias_hi, bias_lo, 0..], B record = [1, 1, 0..]), padded to whole K = 16 steps
+    __host__ __device__ static constexpr int kchunks(int l) { return (kreal(l) + 2) & ~1; }
+    // the constant ones plane: a spare plane when the block uses fewer than 12, else right after the buffer's guard + dump slots
+    static constexpr int ONES_OFF = RC < kGPlanes ? RC * kGPlane : kGActBytes + 512 + 128;
+    static constexpr int EXTRA_SMEM = RC < kGPlanes ? 0 : kGPlane + 64;
     __host__ __device__ static constexpr int w_bytes(int l) { return kchunks(l) * 2048; }
     __host__ __device__ static constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
     __host__ __device__ static constexpr int pi(int f) { return (f % G) * 8 + f / G; }
@@ -73,7 +77,7 @@ struct GCfg {
     }
     // byte offset (within the activation buffer, relative to column n = 0) of K chunk kk of layer l
     __host__ __device__ static constexpr uint32_t koff(int l, int kk) {
-        if (kk >= kreal(l)) return koff(l, kk - 1) + 16;       // zero-weight pad chunk: any finite column
+        if (kk >= kreal(l)) return (uint32_t)(ONES_OFF + (kk - kreal(l)) * 16);   // ones chunk, then a zero-weight pad chunk
         const int ci = cin(l), c = kk / (G + 2), d = kd(l, kk);
         if (is_freq(l)) {
             const int fm = ((d % G) + G) % G;
@@ -105,26 +109,28 @@ struct GSmemHeader {
     uint64_t tmem_full, tmem_empty, wbar;
     uint32_t tmem_base;
     uint32_t pad[1];
-    float bias[kGMaxLayers * 72];
     float l0[3 * 24 + 24 + 8];
     alignas(16) uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
 };
 
-// bias + LeakyReLU + fp16 + stmatrix of one 16-lane x 64-column fragment (already in registers)
+// fp16 pair of LeakyReLU(a), LeakyReLU(b), activation in fp32 before the rounding.  (Doing max(h, 0.2 h) on the packed pair
+// saves 2 of 5 instructions but rounds the negative side twice; measured gain 0.4 % -- not taken.)
+__device__ __forceinline__ uint32_t leaky_half2(float a, float b) { return pack_half2(leaky(a), leaky(b)); }
+
+// LeakyReLU + fp16 + stmatrix of one 16-lane x 64-column fragment (already in registers; the bias came through the MMA)
 template <bool kTwo>
 __device__ __forceinline__ void g_epilogue(const uint32_t (&r)[32], const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,
-                                           uint32_t dump_lane, float b0, float b1) {
+                                           uint32_t dump_lane) {
 #pragma unroll
     for (int g = 0; g < 8; g += 2) {
         const uint32_t e = tab[n_lane + 8 * g];
         const uint32_t addr = (e & 1u) ? dump_lane : base_lane + ((e >> 1) << 4);
-        const float x0 = leaky(__uint_as_float(r[4 * g + 0]) + b0), x1 = leaky(__uint_as_float(r[4 * g + 1]) + b0);
-        const float x4 = leaky(__uint_as_float(r[4 * g + 4]) + b0), x5 = leaky(__uint_as_float(r[4 * g + 5]) + b0);
-        const uint32_t ra = pack_half2(x0, x1), rc = pack_half2(x4, x5);
+        const uint32_t ra = leaky_half2(__uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1]));
+        const uint32_t rc = leaky_half2(__uint_as_float(r[4 * g + 4]), __uint_as_float(r[4 * g + 5]));
         if (kTwo) {
-            const float x2 = leaky(__uint_as_float(r[4 * g + 2]) + b1), x3 = leaky(__uint_as_float(r[4 * g + 3]) + b1);
-            const float x6 = leaky(__uint_as_float(r[4 * g + 6]) + b1), x7 = leaky(__uint_as_float(r[4 * g + 7]) + b1);
-            stmatrix_x4_trans(addr, ra, pack_half2(x2, x3), rc, pack_half2(x6, x7));
+            const uint32_t rb = leaky_half2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+            const uint32_t rd = leaky_half2(__uint_as_float(r[4 * g + 6]), __uint_as_float(r[4 * g + 7]));
+            stmatrix_x4_trans(addr, ra, rb, rc, rd);
         } else {
             stmatrix_x2_trans(addr, ra, rc);
         }
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     unsigned char* wbuf = smem + ((sizeof(GSmemHeader<Cfg>) + 127) & ~127);
     unsigned char* act = wbuf + Cfg::W_MAX;
     unsigned char* dump = act + kGActBytes + 512;             // 512 B finite guard for reads past the last plane
-    float* mel_tile = reinterpret_cast<float*>(dump + 128);   // MEL_IN only
+    float* mel_tile = reinterpret_cast<float*>(dump + 128 + Cfg::EXTRA_SMEM);   // MEL_IN only
 
     const int clip = blockIdx.x / a.tiles_per_clip, tile = blockIdx.x - clip * a.tiles_per_clip;
     const int row0 = tile * Cfg::ROWS_OUT;
@@ -185,13 +191,15 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kGTmemCols);
-    for (int i = tid; i < NL * C; i += kGThreads) hdr.bias[(i / C) * 72 + i % C] = a.bias[i];
     if (Cfg::MEL_IN)
         for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
     for (int i = tid; i < NL * 256 / 8; i += kGThreads)       // epilogue scatter tables, precomputed on the host (tcg_tables)
         reinterpret_cast<uint4*>(&hdr.tab[0][0])[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
     // everything the MMAs may read must be finite: clear the activation buffer and its guard
     for (int i = tid; i < (kGActBytes + 512) / 16; i += kGThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    if (Cfg::RC < kGPlanes) __syncthreads();                  // the ones plane is one of the planes just cleared
+    for (int i = tid; i < 256 + 2; i += kGThreads)            // [1, 1, 0, 0, 0, 0, 0, 0] per column: the bias K chunk's B operand
+        *reinterpret_cast<uint4*>(act + Cfg::ONES_OFF + i * 16) = make_uint4(0x3c003c00u, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             }
             if (!freq && !last) {
                 // the epilogue is writing layout F: zero its SAME padding (column 0 and group 8 of every row, all planes)
-                for (int i = lane; i < kGPlanes * (TT + 1); i += 32) {
+                for (int i = lane; i < Cfg::RC * (TT + 1); i += 32) {
                     const int pl = i / (TT + 1), k = i - pl * (TT + 1);
                     const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
                     *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
@@ -315,7 +323,6 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             __syncwarp();
         } else {
             const int e = warp - 2, quad = warp & 3, part = e >> 2;   // TMEM lane quadrant, column half
-            const float* bias = hdr.bias + l * 72;
             const uint16_t* tab = hdr.tab[l];
             const int m = lane >> 3;
             // (sub-position i, chunk cc) -> byte offset in the layer's target layout
@@ -344,11 +351,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
                 const int rc_lane = h == 0 ? rc0 + (m & 1) : rc0;               // row chunk this lane's stmatrix rows belong to
                 const int pg = h == 0 ? (m >> 1) : (m & 1);                     // +8 column group of this lane's matrix
                 const uint32_t base_lane = act_u32 + (uint32_t)(rc_lane / CC) * i_unit + (uint32_t)(rc_lane % CC) * cc_unit;
-                const float b0 = bias[(rc0 % CC) * 8 + (lane >> 2)];
-                const float b1 = h == 0 ? bias[((rc0 + 1) % CC) * 8 + (lane >> 2)] : 0.f;
                 const int n_lane = part * 128 + sub * 64 + 8 * pg + (lane & 7);
-                if (h == 0) g_epilogue<true>(frag[k & 1], tab, n_lane, base_lane, dump_lane, b0, b1);
-                else g_epilogue<false>(frag[k & 1], tab, n_lane, base_lane, dump_lane, b0, b1);
+                if (h == 0) g_epilogue<true>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
+                else g_epilogue<false>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -411,7 +416,7 @@ struct GWeights {
 
 template <class Cfg>
 size_t tcg_smem_bytes() {
-    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 +
+    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 + Cfg::EXTRA_SMEM +
            (Cfg::MEL_IN ? Cfg::TT * kMels * sizeof(float) : 0) + 128;
 }
 
@@ -457,7 +462,21 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
         for (int kk = 0; kk < Cfg::kchunks(l); ++kk) {
             const int c = kk / (G + 2), d = Cfg::kd(l, kk);    // channel chunk, input offset within the group (df or dt)
             if (kk & 1) HB_REQUIRE(Cfg::koff(l, kk) > Cfg::koff(l, kk - 1), "tcg: K chunk pair %d of layer %d is not address-ordered", kk / 2, l);
-            if (kk >= Cfg::kreal(l)) continue;                  // zero pad chunk
+            if (kk == Cfg::kreal(l)) {
+                // ones chunk: bias as an fp16 hi + lo pair (the B record is [1, 1, 0..]), exact to ~2^-22
+                for (int row = 0; row < 128; ++row) {
+                    const int q = row >> 5, o = (row >> 3) & 3, r = row & 7;
+                    const int rc = 3 * q + o, cc = rc % CC;
+                    if (o >= 3 || rc >= Cfg::RC) continue;
+                    const float b = weights_host[b_off[li] + cc * 8 + r];
+                    const __half hi = __float2half_rn(b);
+                    const size_t at = (size_t)Cfg::w_off(l) / 2 + ((size_t)kk * 128 + row) * 8;
+                    packed[at] = hi;
+                    packed[at + 1] = __float2half_rn(b - __half2float(hi));
+                }
+                continue;
+            }
+            if (kk > Cfg::kreal(l)) continue;                   // zero pad chunk
             for (int row = 0; row < 128; ++row) {
                 const int q = row >> 5, o = (row >> 3) & 3, r = row & 7;
                 const int rc = 3 * q + o, i = rc / CC, cc = rc % CC;
