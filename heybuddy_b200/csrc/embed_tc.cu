@@ -73,6 +73,7 @@ struct TcBlockArgs {
     int tiles_per_clip, rows_out, Tt, segs;
     int n_nt, P_alloc, n_layers, ch_alloc, w_buf_bytes;
     int n_slots, tmem_cols, w_double;   // launch shape (see kMaxSlots)
+    int in_place;          // 1: one activation buffer rewritten in place (only with a single accumulator tile per layer)
     TcLayer layers[kMaxTcLayers];
 };
 
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
     unsigned char* wbuf0 = smem + ((sizeof(TcSmemHeader) + 2 * P_alloc + 127 + 16) & ~127);
     unsigned char* wbuf1 = a.w_double ? wbuf0 + a.w_buf_bytes : wbuf0;
     unsigned char* act0 = wbuf1 + a.w_buf_bytes + 128;                    // +128: guard for the position -1 read
-    unsigned char* act1 = act0 + (size_t)a.ch_alloc * chunk_stride + 128;
+    // in place: a layer with one accumulator tile has completed all its MMAs (tcgen05.commit) before the first epilogue store
+    unsigned char* act1 = a.in_place ? act0 : act0 + (size_t)a.ch_alloc * chunk_stride + 128;
     float* mel_tile = reinterpret_cast<float*>(act1 + (size_t)a.ch_alloc * chunk_stride);  // in_mode 0 only
 
     int clip0, tile;
@@ -529,8 +531,8 @@ static const TcBlockPlan kPlans[5] = {
     {1, 3, 32, 32, 32, 24, 2, 2, 10, 1, 1, 256},
     {4, 4, 16, 32, 48, 48, 1, 2, 11, 1, 1, 256},
     {8, 4, 8, 48, 80, 72, 2, 2, 10, 0, 1, 128},
-    {12, 4, 4, 80, 96, 96, 1, 1, 21, 0, 1, 128},
-    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0, 1, 128},
+    {12, 4, 4, 80, 96, 96, 1, 1, 26, 0, 1, 256},
+    {16, 4, 2, 96, 96, 96, 1, 1, 0, 0, 1, 256},
 };
 
 struct TcWeights {
@@ -629,8 +631,9 @@ struct TcGeom {
 };
 
 static size_t tc_smem_bytes(const TcGeom& g, bool first) {
+    const int bufs = g.n_nt == 1 ? 1 : 2;   // a single accumulator tile per layer -> in-place activations
     return ((sizeof(TcSmemHeader) + 2 * (size_t)g.P_alloc + 127 + 16) & ~(size_t)127) + (g.twin ? 1 : 2) * (size_t)g.w_buf_bytes +
-           2 * (128 + (size_t)g.ch_alloc * g.P_alloc * 16) + (first ? (size_t)g.Tt * kMels * sizeof(float) : 0) + 128;
+           bufs * (128 + (size_t)g.ch_alloc * g.P_alloc * 16) + 128 + (first ? (size_t)g.Tt * kMels * sizeof(float) : 0) + 128;
 }
 
 static int tc_w_buf_bytes(int b, const TcWeights* tw) {
@@ -770,6 +773,7 @@ static int launch_block(const hb_embed_model* m, int b, const TcGeom& g, const v
     a.tmem_cols = g.twin ? 256 : 512;
     a.n_slots = a.tmem_cols / g.tile_n;
     a.w_double = g.twin ? 0 : 1;
+    a.in_place = g.n_nt == 1 ? 1 : 0;
     for (int l = 0; l < p.n_layers; ++l) a.layers[l] = tw->layers[p.first_layer + l];
     HB_REQUIRE(g.smem <= (size_t)(g.twin ? 113 : 227) * 1024, "tc block %d needs %zu bytes of shared memory", b, g.smem);
     HB_REQUIRE(g.P_alloc < 16383 && g.n_nt * g.tile_n < 32000, "tc block %d: tile too large", b);
