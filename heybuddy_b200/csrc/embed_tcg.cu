@@ -168,21 +168,25 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     unsigned char* dump = act + kGActBytes + 512;             // 512 B finite guard for reads past the last plane
     float* mel_tile = reinterpret_cast<float*>(dump + 128 + Cfg::EXTRA_SMEM);   // MEL_IN only
 
-    const int clip = blockIdx.x / a.tiles_per_clip, tile = blockIdx.x - clip * a.tiles_per_clip;
-    const int row0 = tile * Cfg::ROWS_OUT;
+    // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... -- TMEM, barriers, tables and the ones plane are set up
+    // once; mbarrier phases simply keep counting across tiles.
+    const int n_tiles = a.n_clips * a.tiles_per_clip;
 
     TC_STAMP(0);
-    // MEL_IN: the tile's mel rows start their trip from global memory now and land in shared memory after the setup barrier
+    // MEL_IN: a tile's mel rows start their trip from global memory one tile ahead and wait in registers
     constexpr int kMelPerThread = (TT * kMels + kGThreads - 1) / kGThreads;
     float mel_reg[Cfg::MEL_IN ? kMelPerThread : 1];
-    if (Cfg::MEL_IN) {
-        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)clip * a.in_T * kMels;
+    auto prefetch_mel = [&](int tile_id) {
+        if (!Cfg::MEL_IN || tile_id >= n_tiles) return;
+        const int pc = tile_id / a.tiles_per_clip, pr0 = (tile_id - pc * a.tiles_per_clip) * Cfg::ROWS_OUT;
+        const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)pc * a.in_T * kMels;
 #pragma unroll
         for (int k = 0; k < kMelPerThread; ++k) {
             const int i = tid + k * kGThreads, r = i / kMels;
-            mel_reg[k] = (i < TT * kMels && row0 + r < a.in_T) ? __ldg(mel + (int64_t)row0 * kMels + i) : 0.f;
+            mel_reg[k] = (i < TT * kMels && pr0 + r < a.in_T) ? __ldg(mel + (int64_t)pr0 * kMels + i) : 0.f;
         }
-    }
+    };
+    prefetch_mel(blockIdx.x);
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&hdr.tmem_full, 1);
@@ -210,6 +214,13 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
         bulk_g2s(wbuf, a.w, (uint32_t)Cfg::w_bytes(0), &hdr.wbar);
     }
+    const uint32_t act_u32 = smem_u32(act), w_u32 = smem_u32(wbuf);
+
+    uint32_t ph = 0;   // layers processed so far by this CTA = phase index of tmem_full / wbar (tmem_empty lags by one)
+    for (int tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const bool first_tile = (tile_id == (int)blockIdx.x);
+    const int clip = tile_id / a.tiles_per_clip, tile = tile_id - clip * a.tiles_per_clip;
+    const int row0 = tile * Cfg::ROWS_OUT;
 
     // ---- stage the input tile -----------------------------------------------------------------------------
     if (Cfg::MEL_IN) {
@@ -218,6 +229,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         for (int k = 0; k < kMelPerThread; ++k)
             if (tid + k * kGThreads < TT * kMels) mel_tile[tid + k * kGThreads] = mel_reg[k];
         __syncthreads();
+        prefetch_mel(tile_id + (int)gridDim.x);
         const int ch = lane & 3;
         float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
@@ -254,18 +266,27 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         // fp16 chunk-major rows [row0, row0 + TT) -> layout F (the first layer is a freq conv), 16-byte cp.async records
         static_assert(Cfg::MEL_IN || Cfg::FIRST_FREQ, "global-input blocks start with a freq conv");
         const uint4* in = reinterpret_cast<const uint4*>(a.in) + (int64_t)clip * a.in_chunks * a.in_T * F;
+        if (!first_tile) {
+            // the buffer holds the previous tile's layout P: restore layout F's zero padding (column 0, group 8 of every row)
+            for (int i = tid; i < G * Cfg::CIN0 * (TT + 1); i += kGThreads) {
+                const int pl = i / (TT + 1), k = i - pl * (TT + 1);
+                const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
+                *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
         for (int i = tid; i < Cfg::CIN0 * TT * F; i += kGThreads) {
             const int c = i / (TT * F), rem = i - c * (TT * F);
             const int t = rem / F, f = rem - t * F;
-            if (row0 + t < a.in_T)
-                cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + 9 * t + f / G) * 16,
-                           in + ((int64_t)c * a.in_T + row0 + t) * F + f, 16u);
+            // rows past the clip are zero-filled (src-size 0): they only feed outputs that are dropped, but must be finite
+            const bool real = row0 + t < a.in_T;
+            cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + 9 * t + f / G) * 16,
+                       real ? in + ((int64_t)c * a.in_T + row0 + t) * F + f : in, real ? 16u : 0u);
         }
         cp_async_wait_all();
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
-    TC_STAMP(2);
+    if (first_tile) TC_STAMP(2);
 
     // f32 NHWC dump of the tile's rows from layout T / F (parity hook only)
     auto dump_act = [&](bool layout_f, int cc_planes) {
@@ -280,18 +301,17 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     if (a.dbg != nullptr && a.dbg_layer == 100) dump_act(Cfg::FIRST_FREQ, Cfg::CIN0);
 
     // ---- the block's tensor-core layers ------------------------------------------------------------------------
-    const uint32_t act_u32 = smem_u32(act), w_u32 = smem_u32(wbuf);
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
+    for (int l = 0; l < NL; ++l, ++ph) {
         constexpr int kDummy = 0; (void)kDummy;
         const bool freq = Cfg::is_freq(l);
         const bool last = (l == NL - 1);
-#define TCG_FINE(i) do { if (l == 1 && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
+#define TCG_FINE(i) do { if (l == 1 && first_tile && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
         if (warp == 0) {
             TCG_FINE(9);
-            mbar_wait(&hdr.wbar, (uint32_t)(l & 1));
+            mbar_wait(&hdr.wbar, ph & 1u);
             TCG_FINE(10);
-            if (l > 0) mbar_wait(&hdr.tmem_empty, (uint32_t)((l - 1) & 1));
+            if (ph > 0) mbar_wait(&hdr.tmem_empty, (ph - 1) & 1u);
             tc_fence_after();
             // One elected lane issues the whole layer; l and j are compile-time, so every descriptor is an immediate
             // (an issue loop that computes offsets at run time is slower than the MMAs it feeds).
@@ -306,10 +326,14 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             __syncwarp();
         } else if (warp == 1) {
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
-            mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
+            mbar_wait(&hdr.tmem_full, ph & 1u);
             if (lane == 0 && !last) {
                 mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(l + 1));
                 bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), (uint32_t)Cfg::w_bytes(l + 1), &hdr.wbar);
+            } else if (lane == 0 && tile_id + (int)gridDim.x < n_tiles) {
+                // the next tile's first layer: its weights arrive under this tile's last epilogue, store and next staging
+                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
+                bulk_g2s(wbuf, a.w, (uint32_t)Cfg::w_bytes(0), &hdr.wbar);
             }
             if (!freq && !last) {
                 // the epilogue is writing layout F: zero its SAME padding (column 0 and group 8 of every row, all planes)
@@ -329,7 +353,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             const uint32_t i_unit = freq ? 128u : (last ? (uint32_t)(F * 16) : 9u * 16u);
             const uint32_t cc_unit = last ? (uint32_t)Cfg::PLAIN : (uint32_t)kGPlane;
             const uint32_t dump_lane = smem_u32(dump) + (uint32_t)((lane & 7) * 16);
-            mbar_wait(&hdr.tmem_full, (uint32_t)(l & 1));
+            mbar_wait(&hdr.tmem_full, ph & 1u);
             tc_fence_after();
             if (warp == 2) TCG_FINE(12);
             // four fragments per warp: (16-lane half h, 64-column sub); the TMEM load of fragment k + 1 is in flight while
@@ -364,7 +388,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        TC_STAMP(3 + l);
+        if (first_tile) TC_STAMP(3 + l);
         if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
 
@@ -401,8 +425,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             out[(((int64_t)clip * Cfg::OUT_CH + ch) * a.T_out + rowp0 + rp) * Fo + fo] = o;
         }
     }
-    __syncthreads();
-    TC_STAMP(7);
+    __syncthreads();   // the store has read the buffer: the next tile may stage into it
+    if (first_tile) TC_STAMP(7);
+    }                  // tile loop
     if (warp == 0) tmem_dealloc(tmem_base, kGTmemCols);
     TC_STAMP(8);
 }
@@ -530,7 +555,15 @@ int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __h
         HB_CUDA_OK(cudaFuncSetAttribute(tcg_block_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    tcg_block_kernel<Cfg><<<B * a.tiles_per_clip, kGThreads, tcg_smem_bytes<Cfg>(), st>>>(a);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        HB_CUDA_OK(cudaGetDevice(&dev));
+        HB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int64_t n_tiles = (int64_t)B * a.tiles_per_clip;
+    const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)n_sm);     // persistent: two CTAs per SM stride over the tiles
+    tcg_block_kernel<Cfg><<<grid, kGThreads, tcg_smem_bytes<Cfg>(), st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }
