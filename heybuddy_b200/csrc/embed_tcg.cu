@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kGThreads = 320;
 constexpr int kGEpiWarps = 8;
-constexpr int kGPlane = 4096;       // bytes per plane (256 columns)
+constexpr int kGPlane = 4096 + 32;  // bytes per plane: 256 columns + a 32-byte skew so that chunk planes start in different banks
 constexpr int kGPlanes = 12;        // planes allocated (G * channel chunks <= 12)
 constexpr int kGActBytes = kGPlanes * kGPlane;
 constexpr int kGTmemCols = 256;
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
                 unsigned char* dst = act + ((r % G) * Cfg::CIN0 + ch) * kGPlane + (r / G) * F * 16;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
-                    const int f = (lane >> 2) + 8 * j4;
+                    // a quarter-warp's 8 stores = 3 chunk planes (32-byte skew) x the records pi(f), pi(f + 4) = pi(f) + 1:
+                    // six different 16-byte bank groups
+                    const int f = (lane >> 3) + 4 * ((lane >> 2) & 1) + 8 * j4;
                     const float m1 = mrow[f];
                     const float m0 = f > 0 ? mrow[f - 1] : 0.f;
                     const float m2 = f < kMels - 1 ? mrow[f + 1] : 0.f;
