@@ -179,35 +179,58 @@ class FeaturizePipeline:
         """
         Host int16 clips -> host f32 ``[n, 16, 96]``.  ``tables[i]`` holds the draws of chunk i
         (``chunk_clips`` clips each, a multiple of the augmentation batch size).  Uploads run on a side
-        stream from pinned staging buffers, double-buffered against the compute stream; the result comes
-        back through a pinned buffer.  Returns (embeddings, h2d_bytes, d2h_bytes).
+        stream from pinned staging buffers, double-buffered against the compute stream; results drain on a
+        third stream.  ``out`` may be a numpy array or a pinned CPU torch tensor (the D2H then lands in it
+        directly).  Returns (embeddings, h2d_bytes, d2h_bytes).
+        """
+        n_slots = self.slot_offsets.size
+        if out is None:
+            out = np.empty((len(clips), n_slots, spec.EMB_DIM), dtype=np.float32)
+        h2d, d2h = self.featurize_stream([(clips, tables, out)], chunk_clips)
+        return (out.numpy() if hasattr(out, "is_pinned") else out), h2d, d2h
+
+    def featurize_stream(self, items, chunk_clips: int):
+        """
+        Streaming form of :meth:`featurize_host`: ``items`` is a sequence of ``(clips, tables, out)`` host datasets
+        (``out``: numpy array or pinned CPU torch tensor ``[len(clips), 16, 96]``).  The upload of the next chunk --
+        of the same or of the next item -- always overlaps the compute of the current one, so a long run pays the
+        pipeline fill (first H2D) and drain (last D2H) once, not once per item.  Returns (h2d_bytes, d2h_bytes).
         """
         import torch
 
-        n = len(clips)
         dev = self.device
         n_slots = self.slot_offsets.size
-        # ``out`` may be a pinned CPU torch tensor: the D2H then lands in it directly (no staging copy on the host)
-        out_t = out if (out is not None and hasattr(out, "is_pinned")) else None
-        if out_t is not None:
-            assert out_t.is_pinned() and tuple(out_t.shape) == (n, n_slots, spec.EMB_DIM) and out_t.dtype == torch.float32
-            out = out_t.numpy()
-        if out is None:
-            out = np.empty((n, n_slots, spec.EMB_DIM), dtype=np.float32)
-        if ("copy_stream", 0) not in self._bufs:
-            self._bufs[("copy_stream", 0)] = torch.cuda.Stream(device=dev)
+        for key in ("copy_stream", "d2h_stream"):
+            if (key, 0) not in self._bufs:
+                self._bufs[(key, 0)] = torch.cuda.Stream(device=dev)
         copy_stream = self._bufs[("copy_stream", 0)]
+        d2h_stream = self._bufs[("d2h_stream", 0)]     # results drain on their own stream, off the compute stream's critical path
         compute = torch.cuda.current_stream(dev)
         h2d = d2h = 0
         stage_events = [None, None]
-        pending = None  # (result device tensor, pinned host tensor, lo, hi, event)
 
-        def stage(ci: int):
+        work = []   # (item index, chunk index, lo, hi)
+        sinks = []  # per item: (numpy view, pinned torch tensor or None)
+        for ii, (clips, tables, out) in enumerate(items):
+            n = len(clips)
+            out_t = out if hasattr(out, "is_pinned") else None
+            if out_t is not None:
+                assert out_t.is_pinned() and tuple(out_t.shape) == (n, n_slots, spec.EMB_DIM) and out_t.dtype == torch.float32
+            else:
+                assert tuple(out.shape) == (n, n_slots, spec.EMB_DIM) and out.dtype == np.float32
+            sinks.append((out if out_t is None else out_t.numpy(), out_t))
+            n_chunks = (n + chunk_clips - 1) // chunk_clips
+            assert len(tables) >= n_chunks, "one draw table per chunk"
+            for ci in range(n_chunks):
+                work.append((ii, ci, ci * chunk_clips, min(n, (ci + 1) * chunk_clips)))
+
+        def stage(k: int):
             nonlocal h2d
-            lo, hi = ci * chunk_clips, min(n, (ci + 1) * chunk_clips)
+            ii, ci, lo, hi = work[k]
+            clips, tables, _ = items[ii]
             part = clips.slice(lo, hi)
             pads, params, bases = self.pack_params(tables[ci])
-            slot = ci % 2
+            slot = k % 2
             prev = stage_events[slot]
             if prev is not None:
                 prev.synchronize()   # the H2D that last read this slot's pinned staging buffers must have finished
@@ -242,40 +265,49 @@ class FeaturizePipeline:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             stage_events[slot] = ev
-            return DeviceChunk(devs["samples"], devs["offsets"], devs["pads"], devs["params"], devs["bases"], hi - lo), ev, lo, hi
+            return DeviceChunk(devs["samples"], devs["offsets"], devs["pads"], devs["params"], devs["bases"], hi - lo), ev
 
-        n_chunks = (n + chunk_clips - 1) // chunk_clips
-        nxt = stage(0) if n_chunks else None
-        for ci in range(n_chunks):
-            chunk, ev, lo, hi = nxt
-            nxt = stage(ci + 1) if ci + 1 < n_chunks else None
+        pending = None  # staged path: (pinned buffer, numpy sink, lo, hi, event)
+
+        def drain():
+            nonlocal pending
+            if pending is not None:
+                p_pin, p_sink, p_lo, p_hi, p_ev = pending
+                p_ev.synchronize()
+                p_sink[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
+                pending = None
+
+        nxt = stage(0) if work else None
+        for k in range(len(work)):
+            chunk, ev = nxt
+            ii, ci, lo, hi = work[k]
+            nxt = stage(k + 1) if k + 1 < len(work) else None
             compute.wait_event(ev)
             for v in (chunk.samples, chunk.offsets, chunk.pad_before, chunk.params, chunk.bases):
                 if v is not None:
                     v.record_stream(compute)
             emb = self.run_device(chunk)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            d2h_stream.wait_event(ready)
+            emb.record_stream(d2h_stream)
+            sink, out_t = sinks[ii]
+            d2h += emb.numel() * 4
             if out_t is not None:
-                out_t[lo:hi].copy_(emb, non_blocking=True)
-                d2h += emb.numel() * 4
+                with torch.cuda.stream(d2h_stream):
+                    out_t[lo:hi].copy_(emb, non_blocking=True)
                 continue
-            key = (f"pin_out_{ci % 2}", 0)
+            key = (f"pin_out_{k % 2}", 0)
             pin = self._bufs.get(key)
             if pin is None or pin.numel() < emb.numel():
                 pin = torch.empty(emb.numel(), dtype=torch.float32).pin_memory()
                 self._bufs[key] = pin
-            if pending is not None:
-                p_pin, p_lo, p_hi, p_ev = pending
-                p_ev.synchronize()
-                out[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
-            pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
-            d2h += emb.numel() * 4
-            done = torch.cuda.Event()
-            done.record(compute)
-            pending = (pin, lo, hi, done)
-        if pending is not None:
-            p_pin, p_lo, p_hi, p_ev = pending
-            p_ev.synchronize()
-            out[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
-        if out_t is not None:
-            compute.synchronize()
-        return out, h2d, d2h
+            drain()   # the previous chunk's pinned buffer (the other slot) -> its numpy sink
+            with torch.cuda.stream(d2h_stream):
+                pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(d2h_stream)
+            pending = (pin, sink, lo, hi, done)
+        drain()
+        d2h_stream.synchronize()
+        return h2d, d2h

@@ -22,7 +22,7 @@ for lo in range(0, len(table.batches), bps):
     d = DrawTable(cfg=table.cfg, seed=table.seed)
     d.batches, d.noise_clip_cursor, d.rir_index = table.batches[lo:lo + bps], table.noise_clip_cursor[lo:lo + bps], table.rir_index[lo:lo + bps]
     parts.append(d)
-out = np.empty((8192, 16, 96), np.float32)
+out = torch.empty((8192, 16, 96), dtype=torch.float32).pin_memory()
 for _ in range(2):
     pipe.featurize_host(clips, parts, sub, out=out)
 torch.cuda.synchronize()
