@@ -375,7 +375,8 @@ def main():
         achieved_tflops = flops_per_clip * CHUNK * args.steps / (embed_ms * 1e-3) / 1e12 if embed_ms > 0 else None
         tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0 if not peaks else peaks.get("bf16_tflops", 1590.0)))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        stage_bytes = {"fix_length": 0, "augment": 276480, "mel": 110208}
+        # augment = length fix + K1-K4 in one kernel: int16 source (28,800 B on average) + noise row + f32 result
+        stage_bytes = {"augment": 28800 + 92160 + 92160, "mel": 110208}
         stages = {}
         for name, ms in stage_ms.items():
             entry = {"ms_per_step": ms / args.steps, "share": ms / max(sum(stage_ms.values()), 1e-9)}

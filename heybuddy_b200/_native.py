@@ -75,6 +75,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_rir_spectrum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_augment_clips_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_fix_length_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_augment_clips_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_mlp_num_params": (c_i64, []),
         "hb_mlp_create": (c_int, [ctypes.POINTER(c_vp), c_vp, c_i64]),
         "hb_mlp_destroy": (c_int, [c_vp]),

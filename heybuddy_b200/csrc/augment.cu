@@ -566,8 +566,12 @@ __device__ __forceinline__ float block_sum_n(float v, float* scratch, int n_warp
     return scratch[32];
 }
 
+// kI16: the length fix (a1: /32768, front-truncate or left-pad by pad_before) is fused into the load -- the clip comes
+// straight from the ragged int16 samples and the f32 [n][T] intermediate never exists in HBM.
+template <bool kI16>
 __global__ void __launch_bounds__(kFastThreads, 1)
-augment_fast_kernel(const float* __restrict__ clips, const float* __restrict__ noise_bank,
+augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
+                    const int32_t* __restrict__ pad_before, const float* __restrict__ noise_bank,
                     const float* __restrict__ colored_bases, const float2* __restrict__ rir_specs,
                     const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -578,7 +582,7 @@ augment_fast_kernel(const float* __restrict__ clips, const float* __restrict__ n
     float2* buf1 = buf0 + kFastBuf;
     const int tid = threadIdx.x;
     const hb_clip_aug p = params[blockIdx.x];
-    const float2* src = reinterpret_cast<const float2*>(clips + (int64_t)blockIdx.x * T);
+    const float2* src = kI16 ? nullptr : reinterpret_cast<const float2*>(clips + (int64_t)blockIdx.x * T);
     float2* dst = reinterpret_cast<float2*>(out + (int64_t)blockIdx.x * T);
     const bool has_colored = p.colored_index >= 0 && colored_bases != nullptr;
     const bool has_noise = p.noise_offset >= 0 && noise_bank != nullptr;
@@ -590,11 +594,27 @@ augment_fast_kernel(const float* __restrict__ clips, const float* __restrict__ n
 
     // ---- load the clip and (prefetch) its noise row; both stay in shared memory ------------------------
     float sumsq = 0.f, nsq = 0.f;
+    if (kI16) {
+        const int64_t s0 = offsets[blockIdx.x];
+        const int len = (int)(offsets[blockIdx.x + 1] - s0);
+        const int pad = len >= T ? 0 : pad_before[blockIdx.x];
+        const int16_t* s = samples + s0 - pad;
 #pragma unroll 5
-    for (int n = tid; n < M; n += NT) {
-        const float2 v = __ldg(src + n);
-        buf0[sk(n)] = v;
-        sumsq += v.x * v.x + v.y * v.y;
+        for (int n = tid; n < M; n += NT) {
+            const int j = 2 * n - pad;
+            float2 v;
+            v.x = (j >= 0 && j < len) ? (float)__ldg(s + 2 * n) * (1.0f / 32768.0f) : 0.f;
+            v.y = (j + 1 >= 0 && j + 1 < len) ? (float)__ldg(s + 2 * n + 1) * (1.0f / 32768.0f) : 0.f;
+            buf0[sk(n)] = v;
+            sumsq += v.x * v.x + v.y * v.y;
+        }
+    } else {
+#pragma unroll 5
+        for (int n = tid; n < M; n += NT) {
+            const float2 v = __ldg(src + n);
+            buf0[sk(n)] = v;
+            sumsq += v.x * v.x + v.y * v.y;
+        }
     }
     if (has_noise) {
         const float* nsrc = noise_bank + p.noise_offset;
@@ -761,7 +781,8 @@ static int get_plan(int T, FftPlan* out) {
     plan.tw_t = d_t;
     HB_CUDA_OK(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
-    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     g_plans[{dev, T}] = plan;
     *out = plan;
     return HB_OK;
@@ -794,15 +815,34 @@ extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_b
     const bool aligned = ((reinterpret_cast<uintptr_t>(clips_dev) | reinterpret_cast<uintptr_t>(out_dev) |
                            reinterpret_cast<uintptr_t>(colored_bases_dev)) & 7) == 0;
     if (T == kFastT && aligned) {
-        augment_fast_kernel<<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
-            clips_dev, noise_bank_dev, colored_bases_dev, reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev,
-            out_dev, plan);
+        augment_fast_kernel<false><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+            clips_dev, nullptr, nullptr, nullptr, noise_bank_dev, colored_bases_dev, reinterpret_cast<const float2*>(rir_spec_bank_dev),
+            params_dev, out_dev, plan);
     } else {
         const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
         augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
                                                                          reinterpret_cast<const float2*>(rir_spec_bank_dev),
                                                                          params_dev, out_dev, T, plan);
     }
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+extern "C" int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                                    const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
+                                    const hb_clip_aug* params_dev, float* out_dev, int n, int T, void* stream) {
+    HB_REQUIRE(samples_dev && offsets_dev && pad_before_dev && params_dev && out_dev && n >= 0, "hb_augment_clips_i16: bad argument");
+    if (T != kFastT || ((reinterpret_cast<uintptr_t>(out_dev) | reinterpret_cast<uintptr_t>(colored_bases_dev)) & 7) != 0) {
+        set_error("hb_augment_clips_i16: only T = 23040 with 8-byte aligned buffers is fused; use hb_fix_length_i16 + hb_augment_clips_f32");
+        return HB_ERR_UNSUPPORTED;
+    }
+    if (n == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(T, &plan);
+    if (rc) return rc;
+    augment_fast_kernel<true><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+        nullptr, samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev,
+        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, out_dev, plan);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -7,7 +7,7 @@ This is what ``TrainingFeaturesGenerator.generate`` (reference dataset/features.
 with a python loop per clip, a D2H per clip and one ORT call per 32 items; here a chunk of
 augmentation batches is five kinds of kernel launches on one stream:
 
-    hb_fix_length_i16 -> hb_augment_clips_f32 -> hb_mel_f32 -> hb_embed_clips (trunk + tail)
+    hb_augment_clips_i16 (length fix + augmentation) -> hb_mel_f32 -> hb_embed_clips (trunk + tail)
 
 ``featurize_host`` adds the pinned-memory H2D / D2H copies on a second stream so chunk i+1 uploads
 while chunk i computes (double buffering).
@@ -153,17 +153,20 @@ class FeaturizePipeline:
         with torch.cuda.device(dev):
             st = _native.stream_ptr(dev)
             self._mark("begin")
-            fixed = self._buf("fixed", (n, t), torch.float32)
-            _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
-                                                fixed.data_ptr(), n, t, st), "hb_fix_length_i16")
-            self._mark("fix_length")
             audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
             nb, rb = aug.noise_bank, aug.rir_bank
-            _native.check(lib.hb_augment_clips_f32(
-                fixed.data_ptr(), nb.stream.data_ptr() if nb is not None else None,
-                chunk.bases.data_ptr() if chunk.bases is not None else None,
-                rb.spec.data_ptr() if rb is not None else None,
-                chunk.params.data_ptr(), audio.data_ptr(), n, t, st), "hb_augment_clips_f32")
+            banks = (nb.stream.data_ptr() if nb is not None else None, chunk.bases.data_ptr() if chunk.bases is not None else None,
+                     rb.spec.data_ptr() if rb is not None else None)
+            if t == spec.CLIP_SAMPLES:
+                # length fix fused into the augmentation kernel's load: int16 samples -> shared memory, no f32 intermediate
+                _native.check(lib.hb_augment_clips_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                                                       *banks, chunk.params.data_ptr(), audio.data_ptr(), n, t, st), "hb_augment_clips_i16")
+            else:
+                fixed = self._buf("fixed", (n, t), torch.float32)
+                _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                                                    fixed.data_ptr(), n, t, st), "hb_fix_length_i16")
+                _native.check(lib.hb_augment_clips_f32(fixed.data_ptr(), *banks, chunk.params.data_ptr(), audio.data_ptr(), n, t, st),
+                              "hb_augment_clips_f32")
             self._mark("augment")
             mel = self._buf("mel", (n, spec.mel_frames(t), spec.N_MELS), torch.float32)
             self.speech.spectrogram.run_device(audio, scale=spec.AUDIO_SCALE, out=mel)

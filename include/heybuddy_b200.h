@@ -132,6 +132,13 @@ int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-f
 int hb_fix_length_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
                       float* out_dev, int n, int T, void* stream);
 
+/* a1 + K1-K4 in one kernel (T = 23040 only): the clip goes from the ragged int16 samples through the length fix into the
+ * augmentation kernel's shared memory; the f32 [n][T] intermediate of hb_fix_length_i16 never reaches HBM.  Same arithmetic
+ * as hb_fix_length_i16 followed by hb_augment_clips_f32 (bit-identical).  Other T: HB_ERR_UNSUPPORTED (use the two calls). */
+int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                         const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
+                         const hb_clip_aug* params_dev, float* out_dev, int n, int T, void* stream);
+
 /* ---- K8: wake-word classifier ---------------------------------------------------------------
  * Replaces WakeWordMLPModel.forward (src/python/heybuddy/wakeword.py:334-348) and the
  * loss/backward/Adam of WakeWordTrainer.train_epoch (trainer.py:405-462).

@@ -167,3 +167,39 @@ def test_unsupported_transforms_raise():
 
     with pytest.raises(NotImplementedError):
         AugmentedAudioGenerator([], pitch_shift_prob=0.25)
+
+
+def test_fused_length_fix_is_bit_identical(cuda_device):
+    """hb_augment_clips_i16 (length fix fused into the kernel's load) == hb_fix_length_i16 -> hb_augment_clips_f32."""
+    from heybuddy_b200 import _native
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+    from heybuddy_b200.pipeline import FeaturizePipeline, RaggedClips
+
+    rng = np.random.default_rng(77)
+    clips = _sources(rng, 40) + [np.zeros(0, np.int16), (rng.standard_normal(30000) * 3000).astype(np.int16),
+                                 (rng.standard_normal(23040) * 3000).astype(np.int16), (rng.standard_normal(23039) * 3000).astype(np.int16)]
+    gen = _generator(rng, [], 8)
+    pipe = FeaturizePipeline(gen, SpeechEmbeddings(device_id=0, precision="fp32", load=False), device_id=0)
+    ragged = RaggedClips.from_list(clips)
+    table = gen.next_table(ragged.lengths)
+    chunk = pipe.upload(ragged, table)
+    lib = _native.load()
+    n, t = len(clips), spec.CLIP_SAMPLES
+    st = _native.stream_ptr(pipe.device)
+    nb, rb = gen.noise_bank, gen.rir_bank
+    banks = (nb.stream.data_ptr(), chunk.bases.data_ptr() if chunk.bases is not None else None, rb.spec.data_ptr())
+    fixed = torch.empty((n, t), dtype=torch.float32, device="cuda")
+    two = torch.empty_like(fixed)
+    one = torch.empty_like(fixed)
+    _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                                        fixed.data_ptr(), n, t, st), "fix")
+    _native.check(lib.hb_augment_clips_f32(fixed.data_ptr(), *banks, chunk.params.data_ptr(), two.data_ptr(), n, t, st), "f32")
+    _native.check(lib.hb_augment_clips_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(), *banks,
+                                           chunk.params.data_ptr(), one.data_ptr(), n, t, st), "i16")
+    torch.cuda.synchronize()
+    a, b = one.cpu().numpy(), two.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+    # other lengths are not fused: the entry point says so instead of falling back silently
+    assert lib.hb_augment_clips_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(), *banks,
+                                    chunk.params.data_ptr(), one.data_ptr(), n, 16000, st) < 0
