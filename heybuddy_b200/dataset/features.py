@@ -315,16 +315,27 @@ class TrainingFeaturesGenerator:
     @classmethod
     def _features(cls, name: str, want: int, directory: str, use_cache: bool, keep_in_memory: bool, make: Callable[[], "TrainingFeaturesGenerator"],
                   **call_kwargs: Any) -> PrecalculatedDatasetIterator:
-        """Reuse ``<name>.npy`` when it has enough rows, otherwise generate the missing rows and rewrite it (features.py:686-760)."""
+        """
+        Reuse ``<name>.npy`` when it has enough rows, otherwise generate the missing rows (features.py:686-760).  The
+        reference concatenates old + new in memory and rewrites the whole file; here the new rows are appended in place
+        (``util/npy_append.py``: the header gets spare digits once, then only the row count changes) -- same file contents.
+        """
         existing, have = cls._cached(name, directory, use_cache)
         if existing is not None and have >= want:
             return existing
         gen = make()
         if have > 0:
-            gen._generated = (have // max(gen.augment_batch_size, 1)) * 0 + have
-            feats = np.concatenate([np.asarray(existing.precalculated), gen(want - have, **call_kwargs)])
-        else:
-            feats = gen(want, **call_kwargs)
+            from heybuddy_b200.util.npy_append import AppendableNumpyArrayFile, AppendableNumpyHeaderInfo
+
+            gen._generated = have
+            new_rows = gen(want - have, **call_kwargs)
+            path = os.path.join(directory, f"{name}.npy")
+            del existing                       # drop the read-only memmap before the file changes under it
+            AppendableNumpyHeaderInfo.ensure_appendable(path, in_place=True)
+            with AppendableNumpyArrayFile(path) as out:
+                out.append(new_rows)
+            return PrecalculatedDatasetIterator(name, directory=directory)
+        feats = gen(want, **call_kwargs)
         return PrecalculatedDatasetIterator.from_array(feats, name=name, directory=directory, keep_in_memory=keep_in_memory)
 
     @classmethod
