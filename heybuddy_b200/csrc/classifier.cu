@@ -161,10 +161,11 @@ __global__ void head_select_kernel(const float* __restrict__ z, const int64_t* _
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&stats[1], (float)__popc(m));
 }
 
+// n_total: rows selected over the whole (possibly multi-rank) batch = the normaliser of the mean loss
 __global__ void head_grad_kernel(const float* __restrict__ p, const int64_t* __restrict__ y, float* __restrict__ dz,
-                                 float* __restrict__ stats, int B, float thr, float neg_w) {
+                                 float* __restrict__ stats, const float* __restrict__ n_total, int B, float thr, float neg_w) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float n_sel = stats[1];
+    const float n_sel = *n_total;
     float l = 0.f;
     if (i < B) {
         const float pr = p[i];
@@ -184,8 +185,8 @@ __global__ void head_grad_kernel(const float* __restrict__ p, const int64_t* __r
     if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(&stats[0], l);
 }
 
-__global__ void head_finish_kernel(float* __restrict__ stats, int B, int min_selected) {
-    stats[2] = stats[1] >= (float)min_selected ? 1.f : 0.f;
+__global__ void head_finish_kernel(float* __restrict__ stats, const float* __restrict__ n_total, int B, int min_selected) {
+    stats[2] = *n_total >= (float)min_selected ? 1.f : 0.f;
     stats[3] = stats[1] / (float)B;
 }
 
@@ -434,26 +435,28 @@ extern "C" int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const fl
     return HB_OK;
 }
 
-extern "C" int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float lr,
-                                 float negative_weight, float high_loss_threshold, int min_selected, float* prob_dev,
-                                 float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
-    HB_REQUIRE(m && x_dev && y_dev && prob_dev && stats_dev && workspace_dev, "hb_mlp_train_step: null pointer");
-    HB_REQUIRE(B > 0, "hb_mlp_train_step: empty batch");
-    HB_REQUIRE(workspace_bytes >= hb_mlp_workspace_bytes(B, 1), "hb_mlp_train_step: workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    Ws w;
-    carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
+namespace hb {
+
+// forward + sigmoid + high-loss selection: prob, stats[1] = rows selected in THIS batch (stats[0,2,3] zeroed)
+static int select_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float thr, float* prob_dev, float* stats_dev,
+                       const Ws& w, cudaStream_t st) {
     int rc = forward_impl(m, x_dev, B, w, st);
     if (rc) return rc;
     HB_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 4 * sizeof(float), st));
-    head_select_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.o[3], y_dev, prob_dev, stats_dev, B, high_loss_threshold);
+    head_select_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.o[3], y_dev, prob_dev, stats_dev, B, thr);
     HB_LAUNCHED();
-    head_grad_kernel<<<ceil_div(B, 256), 256, 0, st>>>(prob_dev, y_dev, w.dz, stats_dev, B, high_loss_threshold, negative_weight);
-    HB_LAUNCHED();
-    head_finish_kernel<<<1, 1, 0, st>>>(stats_dev, B, min_selected);
-    HB_LAUNCHED();
+    return HB_OK;
+}
 
-    // ---- backward -----------------------------------------------------------------------------------------
+// weighted BCE over the selected rows divided by *n_total, and its gradient with respect to every parameter -> m->g
+static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float negative_weight, float thr,
+                         const float* n_total_dev, int min_selected, const float* prob_dev, float* stats_dev, const Ws& w,
+                         cudaStream_t st) {
+    int rc;
+    head_grad_kernel<<<ceil_div(B, 256), 256, 0, st>>>(prob_dev, y_dev, w.dz, stats_dev, n_total_dev, B, thr, negative_weight);
+    HB_LAUNCHED();
+    head_finish_kernel<<<1, 1, 0, st>>>(stats_dev, n_total_dev, B, min_selected);
+    HB_LAUNCHED();
     const float* d_out = w.dz;   // gradient wrt the stage's output o[s]
     for (int s = kStages - 1; s >= 0; --s) {
         const StageOff& L = kLayout.s[s];
@@ -487,9 +490,65 @@ extern "C" int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int6
             d_out = w.d_o;
         }
     }
+    return HB_OK;
+}
+
+static int adam_impl(hb_mlp_model* m, float lr, const float* stats_dev, cudaStream_t st) {
     adam_kernel<<<148, 256, 0, st>>>(m->p, m->g, m->m, m->v, m->step, stats_dev, lr, kLayout.total);
     HB_LAUNCHED();
     adam_step_inc_kernel<<<1, 1, 0, st>>>(m->step, stats_dev);
     HB_LAUNCHED();
     return HB_OK;
+}
+
+}  // namespace hb
+
+extern "C" int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float lr,
+                                 float negative_weight, float high_loss_threshold, int min_selected, float* prob_dev,
+                                 float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+    HB_REQUIRE(m && x_dev && y_dev && prob_dev && stats_dev && workspace_dev, "hb_mlp_train_step: null pointer");
+    HB_REQUIRE(B > 0, "hb_mlp_train_step: empty batch");
+    HB_REQUIRE(workspace_bytes >= hb_mlp_workspace_bytes(B, 1), "hb_mlp_train_step: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w;
+    carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
+    int rc;
+    if ((rc = select_impl(m, x_dev, y_dev, B, high_loss_threshold, prob_dev, stats_dev, w, st))) return rc;
+    // single device: the batch's own selection count is the normaliser
+    if ((rc = backward_impl(m, x_dev, y_dev, B, negative_weight, high_loss_threshold, stats_dev + 1, min_selected, prob_dev, stats_dev, w, st)))
+        return rc;
+    return adam_impl(m, lr, stats_dev, st);
+}
+
+// ---- data-parallel form of the same step: select -> (all-reduce n) -> backward -> (all-reduce grads) -> adam ----
+extern "C" int hb_mlp_select(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float high_loss_threshold,
+                             float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+    HB_REQUIRE(m && x_dev && y_dev && prob_dev && stats_dev && workspace_dev && B > 0, "hb_mlp_select: bad argument");
+    HB_REQUIRE(workspace_bytes >= hb_mlp_workspace_bytes(B, 1), "hb_mlp_select: workspace too small");
+    Ws w;
+    carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
+    return select_impl(m, x_dev, y_dev, B, high_loss_threshold, prob_dev, stats_dev, w, (cudaStream_t)stream);
+}
+
+extern "C" int hb_mlp_backward(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float negative_weight,
+                               float high_loss_threshold, const float* n_selected_total_dev, int min_selected,
+                               const float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+    HB_REQUIRE(m && x_dev && y_dev && prob_dev && stats_dev && workspace_dev && n_selected_total_dev && B > 0, "hb_mlp_backward: bad argument");
+    HB_REQUIRE(workspace_bytes >= hb_mlp_workspace_bytes(B, 1), "hb_mlp_backward: workspace too small");
+    Ws w;
+    carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
+    return backward_impl(m, x_dev, y_dev, B, negative_weight, high_loss_threshold, n_selected_total_dev, min_selected, prob_dev,
+                         stats_dev, w, (cudaStream_t)stream);
+}
+
+extern "C" int hb_mlp_grads_copy(hb_mlp_model* m, float* buf_dev, int64_t n_floats, int to_model, void* stream) {
+    HB_REQUIRE(m && buf_dev && n_floats == kLayout.total, "hb_mlp_grads_copy: expected %d floats", kLayout.total);
+    HB_CUDA_OK(cudaMemcpyAsync(to_model ? m->g : buf_dev, to_model ? buf_dev : m->g, (size_t)n_floats * sizeof(float),
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+extern "C" int hb_mlp_adam(hb_mlp_model* m, float lr, const float* stats_dev, void* stream) {
+    HB_REQUIRE(m && stats_dev, "hb_mlp_adam: null pointer");
+    return adam_impl(m, lr, stats_dev, (cudaStream_t)stream);
 }

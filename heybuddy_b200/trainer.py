@@ -34,8 +34,13 @@ def get_learning_rate(step: int, warmup_steps: int = 0, hold_steps: int = 0, tot
 
 class WakeWordTrainer:
     def __init__(self, model: Optional[WakeWordMLPModel] = None, learning_rate: float = DEFAULT_LEARNING_RATE,
-                 checkpoint_dir: Optional[str] = None, device_id: Optional[int] = None) -> None:
+                 checkpoint_dir: Optional[str] = None, device_id: Optional[int] = None, distributed: Optional[bool] = None) -> None:
         self.model = model or WakeWordMLPModel(device_id=device_id)
+        if distributed is None:     # data-parallel when launched under torchrun with more than one rank
+            import torch.distributed as dist
+
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.distributed = bool(distributed)
         self.learning_rate = learning_rate
         self.checkpoint_dir = checkpoint_dir
         self.history: Dict[str, List[float]] = {"loss": [], "learning_rate": [], "high_loss_rate": [], "negative_weight": [], "stepped": []}
@@ -96,7 +101,14 @@ class WakeWordTrainer:
             x = x.to(self.device, dtype=torch.float32, non_blocking=True)
             y = y.to(self.device, dtype=torch.int64, non_blocking=True)
             # reference: no backward/step until >= 128 selected rows have accumulated over consecutive steps (:441-458)
-            _, stats = self.model.train_step(x, y, lr, negative_weight, high_loss_threshold, min_selected=max(1, 128 - accumulated))
+            if self.distributed:
+                # every rank feeds its shard of the global batch; selection count, loss and gradients are reduced over the ranks
+                from heybuddy_b200.dp import distributed_train_step
+
+                _, stats = distributed_train_step(self.model, x, y, lr, negative_weight, high_loss_threshold,
+                                                  min_selected=max(1, 128 - accumulated))
+            else:
+                _, stats = self.model.train_step(x, y, lr, negative_weight, high_loss_threshold, min_selected=max(1, 128 - accumulated))
             loss, n_sel, stepped, rate = stats.tolist()
             accumulated = 0 if stepped else accumulated + int(n_sel)
             for k, v in (("loss", loss), ("learning_rate", lr), ("high_loss_rate", rate), ("negative_weight", negative_weight), ("stepped", stepped)):

@@ -234,6 +234,59 @@ class WakeWordMLPModel:
                                                 ws.data_ptr(), ws.numel(), _native.stream_ptr(x.device)), "hb_mlp_train_step")
         return prob, stats
 
+    # -- the same step split for data-parallel training (heybuddy_b200/dp.py drives these) ----------------------------
+    def dp_select(self, x, y, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD):
+        """Forward + high-loss selection of this rank's shard -> (prob cuda [b,1], stats cuda f32[4]; stats[1] = rows selected)."""
+        import torch
+
+        x = x.reshape(x.shape[0], -1).contiguous()
+        assert x.is_cuda and x.dtype == torch.float32 and y.is_cuda and y.dtype == torch.int64
+        b = x.shape[0]
+        prob = torch.empty((b, 1), dtype=torch.float32, device=x.device)
+        stats = torch.empty(4, dtype=torch.float32, device=x.device)
+        lib = _native.load()
+        with torch.cuda.device(x.device):
+            ws = self._ws(lib.hb_mlp_workspace_bytes(b, 1))
+            _native.check(lib.hb_mlp_select(self._ensure(), x.data_ptr(), y.data_ptr(), b, float(high_loss_threshold), prob.data_ptr(),
+                                            stats.data_ptr(), ws.data_ptr(), ws.numel(), _native.stream_ptr(x.device)), "hb_mlp_select")
+        self._dp = (x, y, prob, stats, ws)     # the workspace holds the forward activations until dp_backward
+        return prob, stats
+
+    def dp_backward(self, n_selected_total, negative_weight: float = 1.0, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD,
+                    min_selected: int = 128):
+        """Gradients of (weighted BCE of this shard's selected rows) / n_selected_total -> the model's gradient buffer."""
+        import torch
+
+        x, y, prob, stats, ws = self._dp
+        assert n_selected_total.is_cuda and n_selected_total.dtype == torch.float32 and n_selected_total.numel() == 1
+        lib = _native.load()
+        with torch.cuda.device(x.device):
+            _native.check(lib.hb_mlp_backward(self._ensure(), x.data_ptr(), y.data_ptr(), x.shape[0], float(negative_weight),
+                                              float(high_loss_threshold), n_selected_total.data_ptr(), int(min_selected), prob.data_ptr(),
+                                              stats.data_ptr(), ws.data_ptr(), ws.numel(), _native.stream_ptr(x.device)), "hb_mlp_backward")
+        return stats
+
+    def dp_grads(self, buf=None, to_model: bool = False):
+        """Copy the packed gradients model -> ``buf`` (a cuda f32 [n_params] tensor, allocated when None) or back."""
+        import torch
+
+        lib = _native.load()
+        n = int(lib.hb_mlp_num_params())
+        if buf is None:
+            buf = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(lib.hb_mlp_grads_copy(self._ensure(), buf.data_ptr(), n, int(to_model), _native.stream_ptr(self.device)),
+                          "hb_mlp_grads_copy")
+        return buf
+
+    def dp_adam(self, lr: float, stats):
+        """Adam on the (all-reduced) gradient buffer; skipped on the device when stats[2] == 0."""
+        import torch
+
+        lib = _native.load()
+        with torch.cuda.device(self.device):
+            _native.check(lib.hb_mlp_adam(self._ensure(), float(lr), stats.data_ptr(), _native.stream_ptr(self.device)), "hb_mlp_adam")
+
     # -- inference mixin (wakeword.py:129-169) ---------------------------------------------------------------
     @property
     def speech_embeddings(self):

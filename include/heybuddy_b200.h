@@ -159,7 +159,23 @@ int hb_mlp_forward(const hb_mlp_model* m, const float* x_dev, float* prob_dev, i
 int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B,
                       float lr, float negative_weight, float high_loss_threshold, int min_selected,
                       float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
-/* Gradients of the last hb_mlp_train_step (packed like params), for parity tests. */
+/* The same step in data-parallel form (the reference trains on one device).  Every rank holds a replica
+ * and a shard of the batch:
+ *   hb_mlp_select    forward + selection; stats_dev[1] = rows selected in this shard
+ *   (all-reduce SUM of stats_dev[1] over the ranks -> n_selected_total_dev)
+ *   hb_mlp_backward  BCE / n_total and its gradients for this shard -> the model's gradient buffer; stats_dev[0] = this
+ *                    shard's part of the mean loss, stats_dev[2] = 1 when n_total >= min_selected
+ *   hb_mlp_grads_copy(to_model=0) -> all-reduce SUM -> hb_mlp_grads_copy(to_model=1)
+ *   hb_mlp_adam      the Adam update (skipped when stats_dev[2] == 0), identical on every rank
+ * With one rank and n_selected_total_dev = stats_dev + 1 this is exactly hb_mlp_train_step. */
+int hb_mlp_select(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float high_loss_threshold,
+                  float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+int hb_mlp_backward(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float negative_weight,
+                    float high_loss_threshold, const float* n_selected_total_dev, int min_selected,
+                    const float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+int hb_mlp_grads_copy(hb_mlp_model* m, float* buf_dev, int64_t n_floats, int to_model, void* stream);
+int hb_mlp_adam(hb_mlp_model* m, float lr, const float* stats_dev, void* stream);
+/* Gradients of the last hb_mlp_train_step / hb_mlp_backward (packed like params), for parity tests. */
 int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats);
 
 /* config 5: M models evaluated on the same inputs.  x_dev [B][1536] -> prob_dev [M][B]. */
