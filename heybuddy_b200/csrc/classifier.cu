@@ -79,13 +79,20 @@ constexpr int kTile = 64, kTk = 16;
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                    const float* __restrict__ Bm, int64_t sbk, int64_t sbn,
                                                    float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-                                                   int M, int N, int K, int accumulate) {
+                                                   int M, int N, int K, int accumulate, int k_per_split) {
+    // split-K (gridDim.z > 1): slice z of K goes to the partial buffer C + z * M * ldc (ldc = N), summed in a fixed order by
+    // splitk_reduce_kernel -- deterministic, unlike atomics
     __shared__ float As[kTk][kTile + 1];
     __shared__ float Bs[kTk][kTile + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+    const int k_begin = blockIdx.z * k_per_split;
+    if (gridDim.z > 1) {
+        C += (int64_t)blockIdx.z * M * ldc;
+        K = min(K, k_begin + k_per_split);
+    }
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += kTk) {
+    for (int k0 = k_begin; k0 < K; k0 += kTk) {
         for (int i = threadIdx.x; i < kTile * kTk; i += 256) {
             int m, k;
             if (sak == 1) { k = i % kTk; m = i / kTk; } else { m = i % kTile; k = i / kTile; }
@@ -289,16 +296,49 @@ struct hb_mlp_model {
 
 namespace hb {
 
+// C[m, n] (+)= bias[n] + sum over the S partial results, in slice order
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+                                     int M, int N, int S, int accumulate) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
+        float v = bias ? bias[n] : 0.f;
+        for (int z = 0; z < S; ++z) v += part[(int64_t)z * total + i];
+        float* c = C + (int64_t)m * ldc + n;
+        *c = accumulate ? *c + v : v;
+    }
+}
+
+constexpr int64_t kPartFloats = 16ll * 64 * 1536;     // split-K partial buffer: up to 16 slices of the largest weight gradient
+
+// part != nullptr: GEMMs with few output tiles and a long K (the weight gradients: K = batch) are split over K so they fill
+// the GPU; partial sums go through `part` and are reduced in a fixed order.
 static int gemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
-                const float* bias, int M, int N, int K, int accumulate, cudaStream_t st) {
+                const float* bias, int M, int N, int K, int accumulate, cudaStream_t st, float* part = nullptr) {
     dim3 grid(ceil_div(N, kTile), ceil_div(M, kTile));
-    gemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, C, ldc, bias, M, N, K, accumulate);
+    const int tiles = (int)(grid.x * grid.y);
+    int S = 1;
+    if (part != nullptr && tiles < 148 && K >= 512) {
+        S = std::min(std::min(K / 128, 32), ceil_div(2 * 148, tiles));
+        while (S > 1 && (int64_t)S * M * N > kPartFloats) --S;
+    }
+    if (S <= 1) {
+        gemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, C, ldc, bias, M, N, K, accumulate, K);
+        HB_LAUNCHED();
+        return HB_OK;
+    }
+    const int k_per = ceil_div(ceil_div(K, S), kTk) * kTk;
+    grid.z = ceil_div(K, k_per);
+    gemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, part, N, nullptr, M, N, K, 0, k_per);
+    HB_LAUNCHED();
+    const int64_t total = (int64_t)M * N;
+    splitk_reduce_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, st>>>(part, C, ldc, bias, M, N, (int)grid.z, accumulate);
     HB_LAUNCHED();
     return HB_OK;
 }
 // y[B,N] = x[B,K] W[N,K]^T + b
-static int linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int N, int K, cudaStream_t st) {
-    return gemm(x, K, 1, W, 1, K, y, N, b, B, N, K, 0, st);
+static int linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int N, int K, cudaStream_t st, float* part = nullptr) {
+    return gemm(x, K, 1, W, 1, K, y, N, b, B, N, K, 0, st, part);
 }
 
 // workspace carve-up (floats)
@@ -308,6 +348,7 @@ struct Ws {
     float *h[kStages], *g[kStages], *a[kStages], *o[kStages];
     float *dz, *d_o, *d_a, *d_h, *d_g, *d_u, *d_x;
     float* stats_tmp;
+    float* part;             // split-K partial sums
 };
 static int64_t carve(Ws* w, float* base, int B, int training) {
     int64_t off = 0;
@@ -332,6 +373,7 @@ static int64_t carve(Ws* w, float* base, int B, int training) {
         w->d_u = take((int64_t)B * kIn);
         w->d_x = take((int64_t)B * kDim);
     }
+    w->part = take(kPartFloats);
     return off;
 }
 
@@ -342,8 +384,8 @@ static int forward_impl(const hb_mlp_model* m, const float* x, int B, const Ws& 
         ln_fwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(cur, m->p + L.ln_w, m->p + L.ln_b, w.u[s], w.mean[s], w.rstd[s], B, L.in_dim);
         HB_LAUNCHED();
         int rc;
-        if ((rc = linear_fwd(w.u[s], m->p + L.hw, m->p + L.hb, w.h[s], B, kHid, L.in_dim, st))) return rc;
-        if ((rc = linear_fwd(w.u[s], m->p + L.gw, m->p + L.gb, w.g[s], B, kHid, L.in_dim, st))) return rc;
+        if ((rc = linear_fwd(w.u[s], m->p + L.hw, m->p + L.hb, w.h[s], B, kHid, L.in_dim, st, w.part))) return rc;
+        if ((rc = linear_fwd(w.u[s], m->p + L.gw, m->p + L.gb, w.g[s], B, kHid, L.in_dim, st, w.part))) return rc;
         const int64_t n = (int64_t)B * kHid;
         gate_fwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.h[s], w.g[s], w.a[s], n);
         HB_LAUNCHED();
@@ -462,7 +504,7 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
         const StageOff& L = kLayout.s[s];
         const int in_dim = L.in_dim, out_dim = L.out_dim;
         // output linear: dW_o = d_out^T a, db_o = colsum(d_out), d_a = d_out W_o
-        if ((rc = gemm(d_out, 1, out_dim, w.a[s], kHid, 1, m->g + L.ow, kHid, nullptr, out_dim, kHid, B, 0, st))) return rc;
+        if ((rc = gemm(d_out, 1, out_dim, w.a[s], kHid, 1, m->g + L.ow, kHid, nullptr, out_dim, kHid, B, 0, st, w.part))) return rc;
         colsum_kernel<<<ceil_div(out_dim, 32), 256, 0, st>>>(d_out, m->g + L.ob, B, out_dim, 0);
         HB_LAUNCHED();
         if ((rc = gemm(d_out, out_dim, 1, m->p + L.ow, kHid, 1, w.d_a, kHid, nullptr, B, kHid, out_dim, 0, st))) return rc;
@@ -470,8 +512,8 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
         gate_bwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.h[s], w.g[s], w.d_a, w.d_h, w.d_g, n);
         HB_LAUNCHED();
         // hidden / gate linears: dW = d^T u, db = colsum(d), d_u = d_h W_h + d_g W_g
-        if ((rc = gemm(w.d_h, 1, kHid, w.u[s], in_dim, 1, m->g + L.hw, in_dim, nullptr, kHid, in_dim, B, 0, st))) return rc;
-        if ((rc = gemm(w.d_g, 1, kHid, w.u[s], in_dim, 1, m->g + L.gw, in_dim, nullptr, kHid, in_dim, B, 0, st))) return rc;
+        if ((rc = gemm(w.d_h, 1, kHid, w.u[s], in_dim, 1, m->g + L.hw, in_dim, nullptr, kHid, in_dim, B, 0, st, w.part))) return rc;
+        if ((rc = gemm(w.d_g, 1, kHid, w.u[s], in_dim, 1, m->g + L.gw, in_dim, nullptr, kHid, in_dim, B, 0, st, w.part))) return rc;
         colsum_kernel<<<ceil_div(kHid, 32), 256, 0, st>>>(w.d_h, m->g + L.hb, B, kHid, 0);
         HB_LAUNCHED();
         colsum_kernel<<<ceil_div(kHid, 32), 256, 0, st>>>(w.d_g, m->g + L.gb, B, kHid, 0);
