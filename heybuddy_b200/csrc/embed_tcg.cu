@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&hdr.tmem_full, 1);
-        mbar_init(&hdr.tmem_empty, kGEpiWarps);
+        mbar_init(&hdr.tmem_empty, kGEpiWarps + 1);   // the 8 epilogue warps + warp 1 (padding zeroing)
         mbar_init(&hdr.wbar, 1);
         fence_barrier_init();
     }
@@ -345,8 +345,10 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
                     *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
                 }
             }
+            // stores above -> visible to the tensor core's async-proxy reads, then release the buffer to the MMA issuer
             fence_proxy_async();
             __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr.tmem_empty);
         } else {
             const int e = warp - 2, quad = warp & 3, part = e >> 2;   // TMEM lane quadrant, column half
             const uint16_t* tab = hdr.tab[l];
@@ -381,15 +383,20 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
                 if (h == 0) g_epilogue<true>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
                 else g_epilogue<false>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
             }
+            fence_proxy_async();          // this warp's stmatrix stores -> visible to the async proxy before the buffer is released
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr.tmem_empty);
-            fence_proxy_async();
             if (warp == 2) TCG_FINE(13); else if (warp == 9) TCG_FINE(14);
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
+        // No CTA-wide barrier between layers: the MMA issuer waits on tmem_empty (9 arrivals: every epilogue warp and warp 1 have
+        // stored and fenced), the epilogue warps and warp 1 wait on tmem_full.  Only the block's last layer (the store below reads
+        // the buffer with all threads) and the parity hook need everyone.
+        if (last || a.dbg != nullptr) {
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+        }
         if (first_tile) TC_STAMP(3 + l);
         if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
