@@ -192,3 +192,19 @@ def test_nan_repair(cuda_device):
     assert any(np.array_equal(fixed[1], raw[k]) for k in (0, 2))
     allnan = np.full((2, spec.CLIP_SAMPLES), np.nan, dtype=np.float32)
     assert np.array_equal(se(list(allnan)), np.zeros((2, 16, 96), np.float32))
+
+
+def test_repeated_runs_are_bit_identical(cuda_device):
+    """The tcgen05 path has no atomics and no data-dependent scheduling: a hand-off race would show up as run-to-run noise."""
+    import torch
+
+    from heybuddy_b200.embeddings import SpeechEmbeddingModel
+
+    model = SpeechEmbeddingModel(device_id=0, precision="f16", load=True)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    mel = (torch.randn((296 * 3 + 5, 141, 32), generator=g) * 0.6 + 1.0).cuda()
+    offs = spec.embedding_frame_offsets(spec.CLIP_SAMPLES)
+    first = model.run_clips_device(mel, offs).clone()
+    assert torch.isfinite(first).all()
+    for _ in range(12):
+        assert torch.equal(model.run_clips_device(mel, offs), first)
