@@ -599,14 +599,39 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         const int len = (int)(offsets[blockIdx.x + 1] - s0);
         const int pad = len >= T ? 0 : pad_before[blockIdx.x];
         const int16_t* s = samples + s0 - pad;
-#pragma unroll 5
-        for (int n = tid; n < M; n += NT) {
-            const int j = 2 * n - pad;
-            float2 v;
-            v.x = (j >= 0 && j < len) ? (float)__ldg(s + 2 * n) * (1.0f / 32768.0f) : 0.f;
-            v.y = (j + 1 >= 0 && j + 1 < len) ? (float)__ldg(s + 2 * n + 1) * (1.0f / 32768.0f) : 0.f;
-            buf0[sk(n)] = v;
-            sumsq += v.x * v.x + v.y * v.y;
+        // all 15 loads of a thread in flight at once; sample pairs as one 32-bit load when the clip starts on an even sample
+        if ((reinterpret_cast<uintptr_t>(s) & 3) == 0) {
+            const uint32_t* s2 = reinterpret_cast<const uint32_t*>(s);
+            uint32_t raw[M / NT];
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) {
+                const int n = tid + i * NT, j = 2 * n - pad;
+                const bool lo_ok = j >= 0 && j < len, hi_ok = j + 1 >= 0 && j + 1 < len;
+                raw[i] = (lo_ok && hi_ok) ? __ldg(s2 + n)
+                                          : ((lo_ok ? (uint32_t)(uint16_t)__ldg(s + 2 * n) : 0u) | (hi_ok ? ((uint32_t)(uint16_t)__ldg(s + 2 * n + 1) << 16) : 0u));
+            }
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) {
+                const int n = tid + i * NT;
+                const float2 v = make_float2((float)(int16_t)(raw[i] & 0xffffu) * (1.0f / 32768.0f), (float)(int16_t)(raw[i] >> 16) * (1.0f / 32768.0f));
+                buf0[sk(n)] = v;
+                sumsq += v.x * v.x + v.y * v.y;
+            }
+        } else {
+            int16_t r0[M / NT], r1[M / NT];
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) {
+                const int n = tid + i * NT, j = 2 * n - pad;
+                r0[i] = (j >= 0 && j < len) ? __ldg(s + 2 * n) : (int16_t)0;
+                r1[i] = (j + 1 >= 0 && j + 1 < len) ? __ldg(s + 2 * n + 1) : (int16_t)0;
+            }
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) {
+                const int n = tid + i * NT;
+                const float2 v = make_float2((float)r0[i] * (1.0f / 32768.0f), (float)r1[i] * (1.0f / 32768.0f));
+                buf0[sk(n)] = v;
+                sumsq += v.x * v.x + v.y * v.y;
+            }
         }
     } else {
 #pragma unroll 5
@@ -620,11 +645,13 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         const float* nsrc = noise_bank + p.noise_offset;
         if ((reinterpret_cast<uintptr_t>(nsrc) & 7) == 0) {
             const float2* n2 = reinterpret_cast<const float2*>(nsrc);
-#pragma unroll 5
-            for (int n = tid; n < M; n += NT) {
-                const float2 v = __ldg(n2 + n);
-                buf1[n] = v;
-                nsq += v.x * v.x + v.y * v.y;
+            float2 nv[M / NT];
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) nv[i] = __ldg(n2 + tid + i * NT);     // 15 loads in flight
+#pragma unroll
+            for (int i = 0; i < M / NT; ++i) {
+                buf1[tid + i * NT] = nv[i];
+                nsq += nv[i].x * nv[i].x + nv[i].y * nv[i].y;
             }
         } else {
             for (int n = tid; n < M; n += NT) {

@@ -113,6 +113,16 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
         const int f0 = (int)(p - (int64_t)clip * pairs_per_clip) * 2;
         const int f = min(f0 + h, F - 1);            // an odd F repeats the last frame in the idle half-warp
         const float* x = audio + (int64_t)clip * row_stride + (int64_t)f * kHop;
+        {
+            // pull the NEXT pair's 672 samples (21 lines of 128 B) into L1 while this pair is transformed: with 8 warps per CTA
+            // there is not enough parallelism to hide the L2 latency of the sample loads otherwise
+            const int64_t pn = p + warp_stride;
+            if (pn < n_pairs && lane < 22) {
+                const int cn = (int)(pn / pairs_per_clip);
+                const float* xn = audio + (int64_t)cn * row_stride + (int64_t)((int)(pn - (int64_t)cn * pairs_per_clip) * 2) * kHop;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(xn + lane * 32));
+            }
+        }
 
         // z[i] = point n = l + 16 i; the window is zero outside samples [56, 456) = points [28, 228)
         float2 v[16];
