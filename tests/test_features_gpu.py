@@ -140,3 +140,58 @@ def test_cache_reuse_and_extend(cuda_device, tmp_path):
             break
     tr.stop()
     assert seen > 12
+
+
+def test_full_size_chunk_invariance_and_determinism(cuda_device):
+    """
+    BASELINE configs[1] at bench size (8192 ragged clips, augmentation batch 128): properties that need no oracle --
+    (1) the result of clip i does not depend on how the stream is cut into device passes (one 8192-clip pass == eight
+    1024-clip passes through the host pipeline, bit for bit), (2) two runs are bit-identical, (3) a clip that is not reverbed
+    or noised is a pure gain of its length-fixed source (linearity of the augmentation path), (4) outputs are finite.
+    """
+    import bench
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+    from heybuddy_b200.dataset.draws import DrawTable
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+    from heybuddy_b200.pipeline import FeaturizePipeline
+
+    dev = torch.device("cuda:0")
+    n = 8192
+    old = bench.NOISE_CLIPS
+    bench.NOISE_CLIPS = 256                       # a smaller bank than the bench's 1.3 GB keeps the test light
+    try:
+        noise, rir = bench.make_banks(dev)
+    finally:
+        bench.NOISE_CLIPS = old
+    speech = SpeechEmbeddings(device_id=0, precision="f16")
+    aug = AugmentedAudioGenerator([], device_id=0, augmentation_dataset=noise, impulse_response_dataset=rir, batch_size=128,
+                                  colored_noise_min_f_decay=0.0, colored_noise_max_f_decay=0.0, seed=2004)
+    pipe = FeaturizePipeline(aug, speech, device_id=0)
+    clips = bench.make_sources(n, 2001, dev)
+    table = aug.next_table(clips.lengths)
+
+    def parts(sub):
+        out, bps = [], sub // 128
+        for lo in range(0, len(table.batches), bps):
+            d = DrawTable(cfg=table.cfg, seed=table.seed)
+            d.batches, d.noise_clip_cursor, d.rir_index = table.batches[lo:lo + bps], table.noise_clip_cursor[lo:lo + bps], table.rir_index[lo:lo + bps]
+            out.append(d)
+        return out
+
+    whole, _, _ = pipe.featurize_host(clips, parts(n), n)
+    again, _, _ = pipe.featurize_host(clips, parts(n), n)
+    pieces, _, _ = pipe.featurize_host(clips, parts(1024), 1024)
+    assert whole.shape == (n, 16, 96) and np.isfinite(whole).all()
+    assert np.array_equal(whole, again)
+    assert np.array_equal(whole, pieces)
+    # linearity: batches that drew neither coloured noise, background nor reverb are gain * fixed-length source
+    plain = [g for g, d in enumerate(table.batches) if not (d.colored_apply or d.background_apply or d.reverb_apply)]
+    if plain:
+        g = plain[0]
+        d = table.batches[g]
+        sub = clips.slice(g * 128, (g + 1) * 128)
+        one = DrawTable(cfg=table.cfg, seed=table.seed)
+        one.batches, one.noise_clip_cursor, one.rir_index = [d], [table.noise_clip_cursor[g]], [table.rir_index[g]]
+        _, audio = pipe.run_device(pipe.upload(sub, one), keep_audio=True)
+        fixed = aug.fix_length_device([sub.samples[sub.offsets[i]:sub.offsets[i + 1]] for i in range(len(sub))], d.pad_before)
+        assert torch.allclose(audio, fixed * d.gain_linear, rtol=1e-6, atol=1e-7)
