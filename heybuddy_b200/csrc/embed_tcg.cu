@@ -69,6 +69,8 @@ struct GCfg {
     __host__ __device__ static constexpr int w_bytes(int l) { return kchunks(l) * 2048; }
     __host__ __device__ static constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
     __host__ __device__ static constexpr int pi(int f) { return (f % G) * 8 + f / G; }
+    // accumulator columns a layer really has (a multiple of 16): an MMA costs N / 2 cycles, so N is not rounded up to 256
+    __host__ __device__ static constexpr int ncols(int l) { return ((is_freq(l) ? TT * 9 : (TT / G) * F) + 15) & ~15; }
     // K chunk kk = c * (G + 2) + ord (channel chunk major).  ord -> input offset d within the group: time d = dt = ord;
     // freq d = df: 0 .. G, -1 (G >= 2) or -1, 0, 1 (G = 1) -- orders that keep every K-step pair address-ordered.
     __host__ __device__ static constexpr int kd(int l, int kk) {
@@ -141,11 +143,12 @@ __device__ __forceinline__ void g_epilogue(const uint32_t (&r)[32], const uint16
 template <class Cfg, int L, int J>
 __device__ __forceinline__ void issue_steps(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t idesc) {
     if constexpr (J < Cfg::kchunks(L) / 2) {
+        constexpr uint32_t idesc_l = make_idesc(128, Cfg::ncols(L));
         constexpr uint32_t o0 = Cfg::koff(L, 2 * J), o1 = Cfg::koff(L, 2 * J + 1);
         static_assert(o1 > o0 && ((o1 - o0) >> 4) < 0x4000, "K chunk pair must be address-ordered");
         constexpr uint64_t a_inc = (uint64_t)((2 * J * 2048) >> 4);
         constexpr uint64_t b_inc = (uint64_t)(o0 >> 4) | ((uint64_t)((o1 - o0) >> 4) << 16);
-        umma_f16(d_tmem, a_base + a_inc, b_base + b_inc, idesc, J > 0 ? 1u : 0u);
+        umma_f16(d_tmem, a_base + a_inc, b_base + b_inc, idesc_l, J > 0 ? 1u : 0u);
         issue_steps<Cfg, L, J + 1>(d_tmem, a_base, b_base, idesc);
     }
 }
@@ -363,16 +366,18 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             // four fragments per warp: (16-lane half h, 64-column sub); the TMEM load of fragment k + 1 is in flight while
             // fragment k is converted and stored
             uint32_t frag[2][32];
+            const int n_half = (3 * quad + 2 < Cfg::RC) ? 2 : ((3 * quad < Cfg::RC) ? 1 : 0);   // rows of half 1 / half 0 exist?
+            const int n_sub = (part * 128 + 64 < Cfg::ncols(l)) ? 2 : 1;                         // columns past ncols were never written
+            const int n_frag = n_half * n_sub;
             auto frag_addr = [&](int k) {
-                const int h = k >> 1, sub = k & 1;
+                const int h = k / n_sub, sub = k - h * n_sub;
                 return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(part * 128 + sub * 64);
             };
-            const int n_frag = (3 * quad + 2 < Cfg::RC) ? 4 : ((3 * quad < Cfg::RC) ? 2 : 0);   // rows of half 1 / half 0 exist?
             if (n_frag > 0) tmem_ld_16x256b_64cols_issue(frag_addr(0), frag[0]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (k >= n_frag) break;
-                const int h = k >> 1, sub = k & 1;
+                const int h = k / n_sub, sub = k - h * n_sub;
                 tmem_ld_wait_32(frag[k & 1]);
                 if (k + 1 < n_frag) tmem_ld_16x256b_64cols_issue(frag_addr(k + 1), frag[(k + 1) & 1]);
                 const int rc0 = 3 * quad + 2 * h;                                // row chunk of octet 0 of this 16-lane half
