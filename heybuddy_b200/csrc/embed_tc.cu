@@ -286,7 +286,6 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
             // One elected lane issues the whole layer (a lean loop: the issue path must not be slower than the MMAs it feeds:
             // an N = 256 MMA takes 128 cycles, scripts/micro/umma_swizzle.cu).
             if (elect_one()) {
-                const uint32_t idesc = make_idesc(128, kTileN);
                 const int ksteps = L.cin_chunks / 2;
                 const uint32_t w_region16 = (uint32_t)L.w_rows;                // (bytes of one (tap, k chunk) region = LBO of A) >> 4
                 const uint64_t a_hi = make_desc(0, w_region16 * 16u, 128), b_hi = make_desc(0, chunk_stride, 128);
@@ -301,6 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                     tc_fence_after();
                     TC_FINE(0, 2 + 2 * nt);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(slot * kTileN);
+                    // N = the tile's real positions rounded up to 16 (an MMA costs N / 2 cycles): the last tile is usually short
+                    const uint32_t idesc = make_idesc(128, min(kTileN, (P - nt * kTileN + 15) & ~15));
                     uint32_t acc = 0;
 #pragma unroll
                     for (int tap = 0; tap < 3; ++tap) {
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                     if (c0[h] < 0) continue;   // octets are filled in order: c1 >= 0 implies c0 >= 0
                     for (int sub = 0; sub < kColsPerWarp / 64; ++sub) {
                         const int col = part * kColsPerWarp + sub * 64;
+                        if (nt * kTileN + col >= P) continue;   // columns past the tile's positions were never written by the MMAs
                         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(slot * kTileN + col);
                         const int pos0 = nt * kTileN + col;
                         if (!last_f32) {
