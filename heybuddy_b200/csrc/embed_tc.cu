@@ -328,6 +328,17 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                 mbar_expect_tx(&hdr.wbar[(l + 1) & 1], (uint32_t)Ln.w_bytes);
                 bulk_g2s(wn, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[(l + 1) & 1]);
             }
+            if (!a.w_double && l + 1 < a.n_layers) {
+                // single weight buffer: refill it for the next layer as soon as this layer's last MMAs have completed, i.e.
+                // under this layer's last epilogue instead of after the layer barrier
+                const int it = tile_counter + a.n_nt - 1;
+                mbar_wait(&hdr.tmem_full[it % kSlots], (uint32_t)((it / kSlots) & 1));
+                if (lane == 0) {
+                    const TcLayer& Ln = a.layers[l + 1];
+                    mbar_expect_tx(&hdr.wbar[0], (uint32_t)Ln.w_bytes);
+                    bulk_g2s(wbuf0, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[0]);
+                }
+            }
             __syncwarp();
         } else {
             const int e = warp - 2;            // 0..kEpiWarps-1
@@ -414,12 +425,6 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
         __syncthreads();
         tc_fence_after();
         TC_STAMP(3 + 2 * l);
-        if (!a.w_double && warp == 1 && lane == 0 && l + 1 < a.n_layers) {
-            // single weight buffer: this layer's MMAs are complete (barrier above), refill it for the next layer
-            const TcLayer& Ln = a.layers[l + 1];
-            mbar_expect_tx(&hdr.wbar[0], (uint32_t)Ln.w_bytes);
-            bulk_g2s(wbuf0, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[0]);
-        }
         unsigned char* t = cur; cur = nxt; nxt = t;
         // The epilogue does not mask the pad column (and position 0): their values only ever feed pad outputs, except
         // through a conv with column taps (freq SAME padding) -- zero them right before such a layer.
