@@ -115,10 +115,6 @@ struct GSmemHeader {
     alignas(16) uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
 };
 
-// fp16 pair of LeakyReLU(a), LeakyReLU(b), activation in fp32 before the rounding.  (Doing max(h, 0.2 h) on the packed pair
-// saves 2 of 5 instructions but rounds the negative side twice; measured gain 0.4 % -- not taken.)
-__device__ __forceinline__ uint32_t leaky_half2(float a, float b) { return pack_half2(leaky(a), leaky(b)); }
-
 // LeakyReLU + fp16 + stmatrix of one 16-lane x 64-column fragment (already in registers; the bias came through the MMA)
 template <bool kTwo>
 __device__ __forceinline__ void g_epilogue(const uint32_t (&r)[32], const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,

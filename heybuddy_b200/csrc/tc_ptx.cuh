@@ -194,6 +194,15 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp16 pair of LeakyReLU(a), LeakyReLU(b) for the f16 mode's epilogues: round to fp16 first, then max(h, 0.2 h) on the packed
+// pair -- 3 instructions per pair instead of 5 (the epilogues are issue bound: embed 5.04 -> 4.91 ms).  Non-negative values are
+// unchanged; a negative one is rounded twice (<= 1 fp16 ulp instead of 0.5), which moves the f16 mode's end-to-end error from
+// 5.6e-4 to 6.1e-4 of max|ref| (tolerance 2e-3; the fp32 parity mode is a different kernel).  NaN propagates.
+__device__ __forceinline__ uint32_t leaky_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 m = __hmax2_nan(h, __hmul2(h, __float2half2_rn(kLeaky)));
+    return *reinterpret_cast<const uint32_t*>(&m);
+}
 
 // Epilogue of one 64-column sub-block of one accumulator tile for one 16-lane half:
 // TMEM (lane = channel, column = position) -> +bias -> LeakyReLU -> fp16 -> stmatrix.trans into the next layer's
@@ -204,13 +213,12 @@ __device__ __forceinline__ void epilogue_sub(uint32_t taddr, uint32_t row_addr, 
     tmem_ld_16x256b_64cols(taddr, v);
 #pragma unroll
     for (int g = 0; g < 8; g += 2) {   // two 8-position groups per store
-        float x0 = v[4 * g + 0] + b0, x1 = v[4 * g + 1] + b0, x4 = v[4 * g + 4] + b0, x5 = v[4 * g + 5] + b0;
-        if (kLeaky) { x0 = leaky(x0); x1 = leaky(x1); x4 = leaky(x4); x5 = leaky(x5); }
-        const uint32_t ra = pack_half2(x0, x1), rc = pack_half2(x4, x5);
+        const float x0 = v[4 * g + 0] + b0, x1 = v[4 * g + 1] + b0, x4 = v[4 * g + 4] + b0, x5 = v[4 * g + 5] + b0;
+        const uint32_t ra = kLeaky ? leaky_half2(x0, x1) : pack_half2(x0, x1), rc = kLeaky ? leaky_half2(x4, x5) : pack_half2(x4, x5);
         if (kTwo) {
-            float x2 = v[4 * g + 2] + b1, x3 = v[4 * g + 3] + b1, x6 = v[4 * g + 6] + b1, x7 = v[4 * g + 7] + b1;
-            if (kLeaky) { x2 = leaky(x2); x3 = leaky(x3); x6 = leaky(x6); x7 = leaky(x7); }
-            stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, pack_half2(x2, x3), rc, pack_half2(x6, x7));
+            const float x2 = v[4 * g + 2] + b1, x3 = v[4 * g + 3] + b1, x6 = v[4 * g + 6] + b1, x7 = v[4 * g + 7] + b1;
+            stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, kLeaky ? leaky_half2(x2, x3) : pack_half2(x2, x3), rc,
+                              kLeaky ? leaky_half2(x6, x7) : pack_half2(x6, x7));
         } else {
             stmatrix_x2_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rc);
         }
