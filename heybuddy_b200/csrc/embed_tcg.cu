@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
                     for (int j = 0; j < 8; ++j) {
                         float acc = fmaf(m0, w0[j], bb[j]);
                         acc = fmaf(m1, w1[j], acc);
-                        v[j] = leaky(fmaf(m2, w2[j], acc));
+                        v[j] = fmaf(m2, w2[j], acc);
                     }
                     *reinterpret_cast<uint4*>(dst + Cfg::pi(f) * 16) =
-                        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+                        make_uint4(leaky_half2(v[0], v[1]), leaky_half2(v[2], v[3]), leaky_half2(v[4], v[5]), leaky_half2(v[6], v[7]));
                 }
             }
         }
