@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CHUNK = int(os.environ.get("HB_BENCH_CHUNK", "8192"))       # clips per GPU per step
-E2E_SUB = int(os.environ.get("HB_BENCH_E2E_SUB", "2048"))   # e2e: sub-chunk pipelined H2D / compute / D2H inside a step
+E2E_SUB = int(os.environ.get("HB_BENCH_E2E_SUB", "4096"))   # e2e: sub-chunk pipelined H2D / compute / D2H inside a step
 POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cycled through
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
