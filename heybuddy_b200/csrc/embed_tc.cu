@@ -12,9 +12,10 @@
 //  * Orientation: D^T[cout, position] = sum_tap W_tap^T[cout, cin] X^T[cin, position + shift].
 //    A = weights (M = 128 rows, cout zero padded / aliased), B = activations with N = 256 positions
 //    per tcgen05.mma (kind::f16, fp16 operands, fp32 accumulation in TMEM).  Measured on B200
-//    (scripts/micro/umma_bench.cu): an SS tcgen05.mma costs max(141, N/2 + 43) cycles whatever M is,
-//    so the small dimension (cout = 24..96) must sit in M and the long one (positions) in N: N = 256
-//    keeps the tensor pipe busy 128 of every 171 cycles, N = cout <= 96 at most 48 of 141.
+//    (scripts/micro/umma_swizzle.cu): an SS tcgen05.mma with K = 16 costs N / 2 cycles whatever M is,
+//    so the small dimension (cout = 24..96) sits in M and the long one (positions) in N, and N is the
+//    tile's real position count rounded up to 16.  Blocks 1-3 go further (embed_tcg.cu: several
+//    positions per column); this file runs block 4 and the tail.
 //  * One CTA owns a tile (a time slice of one clip, or 6 whole clips for the tail) and runs the block's
 //    convs back to back, activations ping-ponging between two shared-memory buffers, the next layer's
 //    pre-packed weights arriving by cp.async.bulk (mbarrier tx-count) while the current layer computes.
