@@ -152,9 +152,27 @@ class FeaturizePipeline:
         aug = self.augment
         with torch.cuda.device(dev):
             st = _native.stream_ptr(dev)
+            nb, rb = aug.noise_bank, aug.rir_bank
+            if t == spec.CLIP_SAMPLES and not keep_audio and not self.profile:
+                # one C-ABI call for the whole path (hb_featurize_i16 = augment_i16 -> mel -> embed on one workspace)
+                emb_model = self.speech.embeddings
+                if not emb_model.loaded:
+                    emb_model.load()
+                _native.ensure_tables(dev)
+                offs = np.ascontiguousarray(self.slot_offsets, dtype=np.int32)
+                if out is None:
+                    out = torch.empty((n, offs.size, spec.EMB_DIM), dtype=torch.float32, device=dev)
+                nbytes = lib.hb_featurize_workspace_bytes(n, t, emb_model.mode)
+                _native.check(nbytes, "hb_featurize_workspace_bytes")
+                ws = self._buf("featurize_ws", (int(nbytes),), torch.uint8)
+                _native.check(lib.hb_featurize_i16(
+                    emb_model._handle, emb_model.mode, chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                    nb.stream.data_ptr() if nb is not None else None, chunk.bases.data_ptr() if chunk.bases is not None else None,
+                    rb.spec.data_ptr() if rb is not None else None, chunk.params.data_ptr(), offs.ctypes.data, offs.size,
+                    out.data_ptr(), n, t, ws.data_ptr(), int(nbytes), st), "hb_featurize_i16")
+                return out
             self._mark("begin")
             audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
-            nb, rb = aug.noise_bank, aug.rir_bank
             banks = (nb.stream.data_ptr() if nb is not None else None, chunk.bases.data_ptr() if chunk.bases is not None else None,
                      rb.spec.data_ptr() if rb is not None else None)
             if t == spec.CLIP_SAMPLES:

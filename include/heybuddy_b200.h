@@ -139,6 +139,15 @@ int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* offsets_dev,
                          const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
                          const hb_clip_aug* params_dev, float* out_dev, int n, int T, void* stream);
 
+/* The whole featurization path of one chunk in one call (the fused entry SURVEY.md 8b ring 3 proposes): ragged int16 clips
+ * -> length fix + augmentation -> log-mel (audio x 32767) -> embeddings f32 [n][n_slots][96].  Equivalent to
+ * hb_augment_clips_i16, hb_mel_f32(scale = 32767) and hb_embed_clips run back to back on `stream` (bit-identical); T = 23040. */
+int64_t hb_featurize_workspace_bytes(int n, int T, int mode);
+int hb_featurize_i16(const hb_embed_model* m, int mode, const int16_t* samples_dev, const int64_t* offsets_dev,
+                     const int32_t* pad_before_dev, const float* noise_bank_dev, const float* colored_bases_dev,
+                     const float* rir_spec_bank_dev, const hb_clip_aug* params_dev, const int32_t* slot_offsets_host,
+                     int n_slots, float* out_dev, int n, int T, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* ---- K8: wake-word classifier ---------------------------------------------------------------
  * Replaces WakeWordMLPModel.forward (src/python/heybuddy/wakeword.py:334-348) and the
  * loss/backward/Adam of WakeWordTrainer.train_epoch (trainer.py:405-462).

@@ -195,3 +195,22 @@ def test_full_size_chunk_invariance_and_determinism(cuda_device):
         _, audio = pipe.run_device(pipe.upload(sub, one), keep_audio=True)
         fixed = aug.fix_length_device([sub.samples[sub.offsets[i]:sub.offsets[i + 1]] for i in range(len(sub))], d.pad_before)
         assert torch.allclose(audio, fixed * d.gain_linear, rtol=1e-6, atol=1e-7)
+
+
+def test_fused_entry_point_equals_staged_calls(cuda_device):
+    """hb_featurize_i16 (one C-ABI call) == hb_augment_clips_i16 -> hb_mel_f32 -> hb_embed_clips, bit for bit."""
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+    from heybuddy_b200.pipeline import FeaturizePipeline, RaggedClips
+
+    rng = np.random.default_rng(12)
+    noise, rirs = _banks(rng)
+    aug = AugmentedAudioGenerator([], device_id=0, augmentation_dataset=noise, impulse_response_dataset=rirs, batch_size=8, seed=2004)
+    pipe = FeaturizePipeline(aug, SpeechEmbeddings(device_id=0, precision="f16"), device_id=0)
+    clips = RaggedClips.from_list([(rng.standard_normal(int(rng.integers(6400, 22400))) * 4000).astype(np.int16) for _ in range(40)])
+    chunk = pipe.upload(clips, aug.next_table(clips.lengths))
+    fused = pipe.run_device(chunk).clone()
+    pipe.profile = True                      # stage marks on -> the three separate calls
+    staged = pipe.run_device(chunk).clone()
+    pipe.profile = False
+    assert torch.equal(fused, staged) and torch.isfinite(fused).all()
