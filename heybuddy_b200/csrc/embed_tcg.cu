@@ -35,18 +35,27 @@ namespace hb {
 
 namespace {
 
-constexpr int kGThreads = 320;
-constexpr int kGEpiWarps = 8;
+#ifndef HB_TCG_THREADS23
+#define HB_TCG_THREADS23 320   // launch shape of blocks 2 and 3 (320 = 8 epilogue warps, 576 = 16)
+#endif
 constexpr int kGPlane = 4096 + 32;  // bytes per plane: 256 columns + a 32-byte skew so that chunk planes start in different banks
 constexpr int kGPlanes = 12;        // planes allocated (G * channel chunks <= 12)
 constexpr int kGActBytes = kGPlanes * kGPlane;
 constexpr int kGTmemCols = 256;
 constexpr int kGMaxLayers = 4;
+// Epilogue scatter table of a layer: entry (n & 15) * kGTabRow + (n >> 4) = byte offset >> 4 of accumulator column n in the layer's
+// target layout.  The four columns n, n + 16, n + 32, n + 48 one lane stores from a 64-column fragment are one 8-byte load; a row
+// pitch of 20 entries (40 B) keeps the 16 rows a warp reads in different banks.
+constexpr int kGTabRow = 20;
 
 // G positions per column, CC 8-channel chunks (G * CC = 12 row chunks = 96 M rows), F freq bins (F / G = 8), TT input rows
 // per tile (multiple of G), NL tensor-core layers alternating freq / time, CIN0 input chunks of the first layer.
-template <int G_, int CC_, int F_, int TT_, int NL_, bool FIRST_FREQ_, int CIN0_, int POOL_T_, bool MEL_IN_, int OUT_CH_, int CONV0_>
+template <int G_, int CC_, int F_, int TT_, int NL_, bool FIRST_FREQ_, int CIN0_, int POOL_T_, bool MEL_IN_, int OUT_CH_, int CONV0_, int THREADS_>
 struct GCfg {
+    // launch shape: warp 0 MMA issuer, warp 1 weight loader, then 8 or 16 epilogue warps (2 or 4 per TMEM lane quadrant, each
+    // owning 128 or 64 accumulator columns = two fragments of SUBC columns per 16-lane half)
+    static constexpr int THREADS = THREADS_, EPI_WARPS = THREADS_ / 32 - 2, PARTS = EPI_WARPS / 4, SUBC = 128 / PARTS;
+    static_assert(THREADS_ % 32 == 0 && (EPI_WARPS == 8 || EPI_WARPS == 16), "launch shape");
     static constexpr int G = G_, CC = CC_, F = F_, TT = TT_, NL = NL_, CIN0 = CIN0_, POOL_T = POOL_T_, OUT_CH = OUT_CH_;
     static constexpr bool FIRST_FREQ = FIRST_FREQ_, MEL_IN = MEL_IN_;
     static constexpr int CONV0 = CONV0_;                       // conv index (layer table) of the first tensor-core layer
@@ -89,9 +98,9 @@ struct GCfg {
         return (uint32_t)(((d % G) * ci + c) * kGPlane + (d / G) * F * 16);
     }
 };
-using Cfg1 = GCfg<4, 3, 32, 28, 3, false, 3, 2, true, 4, 1>;    // conv2d (CUDA cores) + conv2d_1..3, pool 2x2
-using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4>;    // conv2d_4..7, pool 1x2
-using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
+using Cfg1 = GCfg<4, 3, 32, 28, 3, false, 3, 2, true, 4, 1, 320>;    // conv2d (CUDA cores) + conv2d_1..3, pool 2x2
+using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4, HB_TCG_THREADS23>;    // conv2d_4..7, pool 1x2
+using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8, HB_TCG_THREADS23>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
 
 struct GArgs {
     const void* in;               // MEL_IN: mel f32 [clips][in_T][32]; else fp16 chunk-major [clips][in_chunks][in_T][F][8]
@@ -99,7 +108,7 @@ struct GArgs {
     const unsigned char* w;       // packed A operands of the NL layers
     const float* bias;            // NL x C
     const float* l0_w;            // MEL_IN: conv2d kernel f32 [3][24] + bias [24]
-    const uint16_t* tab;          // [NL][256] column -> ((byte offset >> 4) << 1) | invalid of every layer's epilogue
+    const uint16_t* tab;          // [NL][16 * kGTabRow] epilogue scatter tables (tcg_tables)
     float* dbg;                   // optional f32 NHWC [clips][dbg_T][F][C] activation dump
     int dbg_layer;                // -1 none, 100 = staged input (MEL_IN: conv2d output), l = output of tensor-core layer l
     int dbg_T;
@@ -112,22 +121,25 @@ struct GSmemHeader {
     uint32_t tmem_base;
     uint32_t pad[1];
     float l0[3 * 24 + 24 + 8];
-    alignas(16) uint16_t tab[kGMaxLayers][256];   // column -> ((byte offset >> 4) << 1) | invalid, per layer
+    alignas(16) uint16_t tab[kGMaxLayers][kGTabRow * 16];   // epilogue scatter tables (tcg_tables), per layer
 };
 
-// LeakyReLU + fp16 + stmatrix of one 16-lane x 64-column fragment (already in registers; the bias came through the MMA)
-template <bool kTwo>
-__device__ __forceinline__ void g_epilogue(const uint32_t (&r)[32], const uint16_t* __restrict__ tab, int n_lane, uint32_t base_lane,
-                                           uint32_t dump_lane) {
+// LeakyReLU + fp16 + stmatrix of one 16-lane x (8 NR)-column fragment (already in registers; the bias came through the MMA).
+// tb = the lane's scatter-table entries (columns n, n + 16, ..; 16 bits each); 16-column groups at or past n_valid
+// (warp-uniform) were never written by the layer's MMAs and are skipped.
+template <bool kTwo, int NR>
+__device__ __forceinline__ void g_epilogue(const uint32_t (&r)[NR], uint2 tb, uint32_t base_lane, int col0, int n_valid) {
 #pragma unroll
-    for (int g = 0; g < 8; g += 2) {
-        const uint32_t e = tab[n_lane + 8 * g];
-        const uint32_t addr = (e & 1u) ? dump_lane : base_lane + ((e >> 1) << 4);
-        const uint32_t ra = leaky_half2(__uint_as_float(r[4 * g + 0]), __uint_as_float(r[4 * g + 1]));
-        const uint32_t rc = leaky_half2(__uint_as_float(r[4 * g + 4]), __uint_as_float(r[4 * g + 5]));
+    for (int gg = 0; gg < NR / 8; ++gg) {
+        if (col0 + 16 * gg >= n_valid) break;
+        const uint32_t w = gg < 2 ? tb.x : tb.y;
+        const uint32_t e = (gg & 1) ? (w >> 16) : (w & 0xffffu);
+        const uint32_t addr = base_lane + (e << 4);
+        const uint32_t ra = leaky_half2(__uint_as_float(r[8 * gg + 0]), __uint_as_float(r[8 * gg + 1]));
+        const uint32_t rc = leaky_half2(__uint_as_float(r[8 * gg + 4]), __uint_as_float(r[8 * gg + 5]));
         if (kTwo) {
-            const uint32_t rb = leaky_half2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
-            const uint32_t rd = leaky_half2(__uint_as_float(r[4 * g + 6]), __uint_as_float(r[4 * g + 7]));
+            const uint32_t rb = leaky_half2(__uint_as_float(r[8 * gg + 2]), __uint_as_float(r[8 * gg + 3]));
+            const uint32_t rd = leaky_half2(__uint_as_float(r[8 * gg + 6]), __uint_as_float(r[8 * gg + 7]));
             stmatrix_x4_trans(addr, ra, rb, rc, rd);
         } else {
             stmatrix_x2_trans(addr, ra, rc);
@@ -157,7 +169,8 @@ __device__ __forceinline__ void issue_layer(int l, uint32_t d_tmem, uint64_t a_b
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) {
+__global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs a) {
+    constexpr int kGThreads = Cfg::THREADS, kGEpiWarps = Cfg::EPI_WARPS;
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C;
     extern __shared__ __align__(128) unsigned char smem[];
     GSmemHeader<Cfg>& hdr = *reinterpret_cast<GSmemHeader<Cfg>*>(smem);
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kGTmemCols);
     if (Cfg::MEL_IN)
         for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
-    for (int i = tid; i < NL * 256 / 8; i += kGThreads)       // epilogue scatter tables, precomputed on the host (tcg_tables)
+    for (int i = tid; i < NL * kGTabRow * 16 / 8; i += kGThreads)   // epilogue scatter tables, precomputed on the host (tcg_tables)
         reinterpret_cast<uint4*>(&hdr.tab[0][0])[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
     // everything the MMAs may read must be finite: clear the activation buffer and its guard
     for (int i = tid; i < (kGActBytes + 512) / 16; i += kGThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
@@ -227,6 +240,10 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
 #pragma unroll
         for (int k = 0; k < kMelPerThread; ++k)
             if (tid + k * kGThreads < TT * kMels) mel_tile[tid + k * kGThreads] = mel_reg[k];
+        // the records the freq layer's padding columns were dumped to (tcg_tables) are rows >= TT of layout T, which this tile's
+        // first (time) conv reads into dropped outputs: clear them so that a non-finite clip cannot reach the next clip's tile
+        if (tid < G * CC)
+            *reinterpret_cast<uint4*>(act + (tid % CC) * kGPlane + ((TT / G) * F + 8 * (tid / CC)) * 16) = make_uint4(0, 0, 0, 0);
         __syncthreads();
         prefetch_mel(tile_id + (int)gridDim.x);
         const int ch = lane & 3;
@@ -349,46 +366,60 @@ __global__ void __launch_bounds__(kGThreads, 2) tcg_block_kernel(const GArgs a) 
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr.tmem_empty);
         } else {
-            const int e = warp - 2, quad = warp & 3, part = e >> 2;   // TMEM lane quadrant, column half
-            const uint16_t* tab = hdr.tab[l];
+            constexpr int SUBC = Cfg::SUBC, PARTC = 2 * Cfg::SUBC;      // columns per fragment / per warp
+            const int e = warp - 2, quad = warp & 3, part = e >> 2;     // TMEM lane quadrant, column part
             const int m = lane >> 3;
             // (sub-position i, chunk cc) -> byte offset in the layer's target layout
             const uint32_t i_unit = freq ? 128u : (last ? (uint32_t)(F * 16) : 9u * 16u);
             const uint32_t cc_unit = last ? (uint32_t)Cfg::PLAIN : (uint32_t)kGPlane;
-            const uint32_t dump_lane = smem_u32(dump) + (uint32_t)((lane & 7) * 16);
-            mbar_wait(&hdr.tmem_full, ph & 1u);
-            tc_fence_after();
-            if (warp == 2) TCG_FINE(12);
-            // four fragments per warp: (16-lane half h, 64-column sub); the TMEM load of fragment k + 1 is in flight while
-            // fragment k is converted and stored
-            uint32_t frag[2][32];
+            // four fragments per warp: (16-lane half h, SUBC-column sub).  Half 0 holds row chunks 3 quad, 3 quad + 1 (stmatrix.x4:
+            // matrix m = row chunk m & 1, column group m >> 1), half 1 row chunk 3 quad + 2 (stmatrix.x2: column group m & 1).
+            const int rc_a = 3 * quad + (m & 1), rc_b = 3 * quad + 2;
+            const uint32_t base_a = act_u32 + (uint32_t)(rc_a / CC) * i_unit + (uint32_t)(rc_a % CC) * cc_unit;
+            const uint32_t base_b = act_u32 + (uint32_t)(rc_b / CC) * i_unit + (uint32_t)(rc_b % CC) * cc_unit;
+            const uint16_t* tab_a = hdr.tab[l] + (8 * (m >> 1) + (lane & 7)) * kGTabRow + part * (PARTC / 16);
+            const uint16_t* tab_b = hdr.tab[l] + (8 * (m & 1) + (lane & 7)) * kGTabRow + part * (PARTC / 16);
+            uint32_t frag[2][SUBC / 2];
             const int n_half = (3 * quad + 2 < Cfg::RC) ? 2 : ((3 * quad < Cfg::RC) ? 1 : 0);   // rows of half 1 / half 0 exist?
-            const int n_sub = (part * 128 + 64 < Cfg::ncols(l)) ? 2 : 1;                         // columns past ncols were never written
+            // columns at or past ncols were never written
+            const int n_sub = (part * PARTC >= Cfg::ncols(l)) ? 0 : ((part * PARTC + SUBC < Cfg::ncols(l)) ? 2 : 1);
             const int n_frag = n_half * n_sub;
             auto frag_addr = [&](int k) {
                 const int h = k / n_sub, sub = k - h * n_sub;
-                return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(part * 128 + sub * 64);
+                return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(part * PARTC + sub * SUBC);
             };
-            if (n_frag > 0) tmem_ld_16x256b_64cols_issue(frag_addr(0), frag[0]);
+            auto frag_tab = [&](int k) {
+                const int h = k / n_sub, sub = k - h * n_sub;
+                const uint16_t* t = (h == 0 ? tab_a : tab_b) + sub * (SUBC / 16);
+                if constexpr (SUBC == 64) return *reinterpret_cast<const uint2*>(t);
+                else return make_uint2(*reinterpret_cast<const uint32_t*>(t), 0u);
+            };
+            // the table entries do not depend on the MMAs: they are in registers before the accumulator is ready
+            uint2 tb = n_frag > 0 ? frag_tab(0) : make_uint2(0, 0);
+            mbar_wait(&hdr.tmem_full, ph & 1u);
+            tc_fence_after();
+            if (warp == 2) TCG_FINE(12);
+            // the TMEM load and the table entries of fragment k + 1 are in flight while fragment k is converted and stored
+            if (n_frag > 0) tmem_ld_frag_issue(frag_addr(0), frag[0]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (k >= n_frag) break;
                 const int h = k / n_sub, sub = k - h * n_sub;
-                tmem_ld_wait_32(frag[k & 1]);
-                if (k + 1 < n_frag) tmem_ld_16x256b_64cols_issue(frag_addr(k + 1), frag[(k + 1) & 1]);
-                const int rc0 = 3 * quad + 2 * h;                                // row chunk of octet 0 of this 16-lane half
-                const int rc_lane = h == 0 ? rc0 + (m & 1) : rc0;               // row chunk this lane's stmatrix rows belong to
-                const int pg = h == 0 ? (m >> 1) : (m & 1);                     // +8 column group of this lane's matrix
-                const uint32_t base_lane = act_u32 + (uint32_t)(rc_lane / CC) * i_unit + (uint32_t)(rc_lane % CC) * cc_unit;
-                const int n_lane = part * 128 + sub * 64 + 8 * pg + (lane & 7);
-                if (h == 0) g_epilogue<true>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
-                else g_epilogue<false>(frag[k & 1], tab, n_lane, base_lane, dump_lane);
+                const uint2 tb_k = tb;
+                tmem_ld_frag_wait(frag[k & 1]);
+                if (k + 1 < n_frag) {
+                    tmem_ld_frag_issue(frag_addr(k + 1), frag[(k + 1) & 1]);
+                    tb = frag_tab(k + 1);
+                }
+                const int col0 = part * PARTC + sub * SUBC;
+                if (h == 0) g_epilogue<true, SUBC / 2>(frag[k & 1], tb_k, base_a, col0, Cfg::ncols(l));
+                else g_epilogue<false, SUBC / 2>(frag[k & 1], tb_k, base_b, col0, Cfg::ncols(l));
             }
             fence_proxy_async();          // this warp's stmatrix stores -> visible to the async proxy before the buffer is released
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr.tmem_empty);
-            if (warp == 2) TCG_FINE(13); else if (warp == 9) TCG_FINE(14);
+            if (warp == 2) TCG_FINE(13); else if (warp == kGThreads / 32 - 1) TCG_FINE(14);
         }
         // No CTA-wide barrier between layers: the MMA issuer waits on tmem_empty (9 arrivals: every epilogue warp and warp 1 have
         // stored and fenced), the epilogue warps and warp 1 wait on tmem_full.  Only the block's last layer (the store below reads
@@ -455,27 +486,31 @@ size_t tcg_smem_bytes() {
            (Cfg::MEL_IN ? Cfg::TT * kMels * sizeof(float) : 0) + 128;
 }
 
-// Epilogue scatter table of layer l: accumulator column n -> byte offset of its first output record in the layer's target
-// layout (the per-row-chunk part is added by the epilogue), or "invalid" for columns that are padding.
+// Epilogue scatter table of layer l: accumulator column n -> byte offset >> 4 of its first output record in the layer's target
+// layout (the per-row-chunk part is added by the epilogue), stored at (n & 15) * kGTabRow + (n >> 4).  Padding columns of a freq
+// layer (group 8 of every row, rows >= TT) go to columns (TT / G) * F + 8 i of their own plane: layout T does not use them, and
+// the time conv that follows reads them only as rows >= TT, i.e. into output rows that are dropped anyway (finite garbage instead
+// of zeros).  A time layer has no padding columns below ncols(l); the epilogue skips the 16-column groups at or past it.
 template <class Cfg>
 void tcg_tables(std::vector<uint16_t>& tab) {
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL;
-    tab.assign((size_t)NL * 256, 1);
+    static_assert((TT / G) * F + 8 * G <= 256, "no free columns for the freq layers' padding outputs");
+    tab.assign((size_t)NL * kGTabRow * 16, 0);
     for (int l = 0; l < NL; ++l)
         for (int n = 0; n < 256; ++n) {
-            int off, valid;
+            int off;
             if (Cfg::is_freq(l)) {
                 // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
                 const int t = n / 9, fg = n - t * 9;
-                valid = fg < 8 && t < TT;
-                off = (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16;
+                const bool valid = fg < 8 && t < TT;
+                off = valid ? (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16 : (TT / G) * F * 16;
             } else {
                 const int tq = n / F, pf = n - tq * F;
-                valid = tq < TT / G;
+                if (tq >= TT / G) continue;                                                           // >= ncols(l): skipped
                 if (l < NL - 1) off = (pf >> 3) * CC * kGPlane + (1 + 9 * G * tq + (pf & 7)) * 16;   // -> layout F
                 else off = (G * tq * F + pf) * 16;                                                    // -> layout P
             }
-            if (valid) tab[(size_t)l * 256 + n] = (uint16_t)((off >> 4) << 1);
+            tab[(size_t)l * kGTabRow * 16 + (size_t)(n & 15) * kGTabRow + (n >> 4)] = (uint16_t)(off >> 4);
         }
 }
 
@@ -573,7 +608,7 @@ int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __h
     }
     const int64_t n_tiles = (int64_t)B * a.tiles_per_clip;
     const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)n_sm);     // persistent: two CTAs per SM stride over the tiles
-    tcg_block_kernel<Cfg><<<grid, kGThreads, tcg_smem_bytes<Cfg>(), st>>>(a);
+    tcg_block_kernel<Cfg><<<grid, Cfg::THREADS, tcg_smem_bytes<Cfg>(), st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -44,10 +44,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up instead of hanging the box
+    // every failed try_wait has slept in hardware (suspend-time hint): a plain retry counter bounds the wait (seconds) with two
+    // instructions per retry -- the waiting warps share issue slots with the co-resident CTA's epilogue
+    for (uint32_t tries = 0; !mbar_try_wait(bar, parity); ++tries) {
+        if (tries > (1u << 24)) {   // give up instead of hanging the box
             atomicExch(&g_tc_timeout, 1u);
             return;
         }
@@ -177,6 +177,26 @@ __device__ __forceinline__ void tmem_ld_wait_32(uint32_t (&r)[32]) {
         :
         : "memory");
 }
+// 16 lanes x 32 columns (one 16x256b.x4): the half-size fragment of the 16-epilogue-warp launch shape
+__device__ __forceinline__ void tmem_ld_16x256b_32cols_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+          "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_frag_issue(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_16x256b_64cols_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_frag_issue(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_16x256b_32cols_issue(taddr, r); }
+__device__ __forceinline__ void tmem_ld_frag_wait(uint32_t (&r)[32]) { tmem_ld_wait_32(r); }
+__device__ __forceinline__ void tmem_ld_frag_wait(uint32_t (&r)[16]) { tmem_ld_wait_16(r); }
 __device__ __forceinline__ void stmatrix_x2_trans(uint32_t row_addr, uint32_t a, uint32_t b) {
     asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(row_addr), "r"(a), "r"(b) : "memory");
 }
