@@ -98,7 +98,7 @@ struct GCfg {
         return (uint32_t)(((d % G) * ci + c) * kGPlane + (d / G) * F * 16);
     }
 };
-using Cfg1 = GCfg<4, 3, 32, 28, 3, false, 3, 2, true, 4, 1, 320>;    // conv2d (CUDA cores) + conv2d_1..3, pool 2x2
+using Cfg1 = GCfg<4, 3, 32, 28, 4, true, 1, 2, true, 4, 0, 320>;     // conv2d (mel as an fp16 hi + lo pair) .. conv2d_3, pool 2x2
 using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4, HB_TCG_THREADS23>;    // conv2d_4..7, pool 1x2
 using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8, HB_TCG_THREADS23>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
 
@@ -120,7 +120,6 @@ struct GSmemHeader {
     uint64_t tmem_full, tmem_empty, wbar;
     uint32_t tmem_base;
     uint32_t pad[1];
-    float l0[3 * 24 + 24 + 8];
     alignas(16) uint16_t tab[kGMaxLayers][kGTabRow * 16];   // epilogue scatter tables (tcg_tables), per layer
 };
 
@@ -178,7 +177,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
     unsigned char* wbuf = smem + ((sizeof(GSmemHeader<Cfg>) + 127) & ~127);
     unsigned char* act = wbuf + Cfg::W_MAX;
     unsigned char* dump = act + kGActBytes + 512;             // 512 B finite guard for reads past the last plane
-    float* mel_tile = reinterpret_cast<float*>(dump + 128 + Cfg::EXTRA_SMEM);   // MEL_IN only
 
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... -- TMEM, barriers, tables and the ones plane are set up
     // once; mbarrier phases simply keep counting across tiles.
@@ -207,8 +205,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&hdr.tmem_base, kGTmemCols);
-    if (Cfg::MEL_IN)
-        for (int i = tid; i < 3 * 24 + 24; i += kGThreads) hdr.l0[i] = a.l0_w[i];
     for (int i = tid; i < NL * kGTabRow * 16 / 8; i += kGThreads)   // epilogue scatter tables, precomputed on the host (tcg_tables)
         reinterpret_cast<uint4*>(&hdr.tab[0][0])[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
     // everything the MMAs may read must be finite: clear the activation buffer and its guard
@@ -235,63 +231,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
     const int row0 = tile * Cfg::ROWS_OUT;
 
     // ---- stage the input tile -----------------------------------------------------------------------------
-    if (Cfg::MEL_IN) {
-        // mel rows -> conv2d (Cin = 1, CUDA cores) -> layout T
-#pragma unroll
-        for (int k = 0; k < kMelPerThread; ++k)
-            if (tid + k * kGThreads < TT * kMels) mel_tile[tid + k * kGThreads] = mel_reg[k];
-        // the records the freq layer's padding columns were dumped to (tcg_tables) are rows >= TT of layout T, which this tile's
-        // first (time) conv reads into dropped outputs: clear them so that a non-finite clip cannot reach the next clip's tile
-        if (tid < G * CC)
-            *reinterpret_cast<uint4*>(act + (tid % CC) * kGPlane + ((TT / G) * F + 8 * (tid / CC)) * 16) = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        prefetch_mel(tile_id + (int)gridDim.x);
-        const int ch = lane & 3;
-        float w0[8], w1[8], w2[8], bb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = ch * 8 + j;
-            w0[j] = ch < 3 ? hdr.l0[c] : 0.f;
-            w1[j] = ch < 3 ? hdr.l0[24 + c] : 0.f;
-            w2[j] = ch < 3 ? hdr.l0[48 + c] : 0.f;
-            bb[j] = ch < 3 ? hdr.l0[72 + c] : 0.f;
+    static_assert(Cfg::FIRST_FREQ, "blocks start with a freq conv");
+    if (!first_tile) {
+        // the buffer holds the previous tile's layout P: restore layout F's zero padding (column 0, group 8 of every row)
+        for (int i = tid; i < G * Cfg::CIN0 * (TT + 1); i += kGThreads) {
+            const int pl = i / (TT + 1), k = i - pl * (TT + 1);
+            const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
+            *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
         }
-        if (ch < 3) {
-            for (int r = warp; r < TT; r += kGThreads / 32) {
-                const float* mrow = mel_tile + r * kMels;
-                unsigned char* dst = act + ((r % G) * Cfg::CIN0 + ch) * kGPlane + (r / G) * F * 16;
+    }
+    if (Cfg::MEL_IN) {
+        // mel rows -> layout F with ONE input chunk whose channels 0 / 1 are the fp16 hi / lo halves of the f32 mel value (exact to
+        // 2^-22; the A operand carries conv2d's weight in both rows): conv2d (Cin = 1) runs on the tensor core like every other layer
+        static_assert(!Cfg::MEL_IN || Cfg::CIN0 == 1, "mel input = one chunk");
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    // a quarter-warp's 8 stores = 3 chunk planes (32-byte skew) x the records pi(f), pi(f + 4) = pi(f) + 1:
-                    // six different 16-byte bank groups
-                    const int f = (lane >> 3) + 4 * ((lane >> 2) & 1) + 8 * j4;
-                    const float m1 = mrow[f];
-                    const float m0 = f > 0 ? mrow[f - 1] : 0.f;
-                    const float m2 = f < kMels - 1 ? mrow[f + 1] : 0.f;
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float acc = fmaf(m0, w0[j], bb[j]);
-                        acc = fmaf(m1, w1[j], acc);
-                        v[j] = fmaf(m2, w2[j], acc);
-                    }
-                    *reinterpret_cast<uint4*>(dst + Cfg::pi(f) * 16) =
-                        make_uint4(leaky_half2(v[0], v[1]), leaky_half2(v[2], v[3]), leaky_half2(v[4], v[5]), leaky_half2(v[6], v[7]));
-                }
+        for (int k = 0; k < kMelPerThread; ++k) {
+            const int i = tid + k * kGThreads;
+            if (i < TT * kMels) {
+                const int t = i / kMels, f = i - t * kMels;
+                const __half hi = __float2half_rn(mel_reg[k]);
+                const __half lo = __float2half_rn(mel_reg[k] - __half2float(hi));
+                *reinterpret_cast<uint4*>(act + (f % G) * kGPlane + (1 + 9 * t + f / G) * 16) =
+                    make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0, 0, 0);
             }
         }
+        prefetch_mel(tile_id + (int)gridDim.x);
     } else {
         // fp16 chunk-major rows [row0, row0 + TT) -> layout F (the first layer is a freq conv), 16-byte cp.async records
-        static_assert(Cfg::MEL_IN || Cfg::FIRST_FREQ, "global-input blocks start with a freq conv");
         const uint4* in = reinterpret_cast<const uint4*>(a.in) + (int64_t)clip * a.in_chunks * a.in_T * F;
-        if (!first_tile) {
-            // the buffer holds the previous tile's layout P: restore layout F's zero padding (column 0, group 8 of every row)
-            for (int i = tid; i < G * Cfg::CIN0 * (TT + 1); i += kGThreads) {
-                const int pl = i / (TT + 1), k = i - pl * (TT + 1);
-                const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
-                *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
-            }
-        }
         for (int i = tid; i < Cfg::CIN0 * TT * F; i += kGThreads) {
             const int c = i / (TT * F), rem = i - c * (TT * F);
             const int t = rem / F, f = rem - t * F;
@@ -482,8 +449,7 @@ struct GWeights {
 
 template <class Cfg>
 size_t tcg_smem_bytes() {
-    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 + Cfg::EXTRA_SMEM +
-           (Cfg::MEL_IN ? Cfg::TT * kMels * sizeof(float) : 0) + 128;
+    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 + Cfg::EXTRA_SMEM + 128;
 }
 
 // Epilogue scatter table of layer l: accumulator column n -> byte offset >> 4 of its first output record in the layer's target
@@ -526,7 +492,9 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
         const int li = Cfg::CONV0 + l;
         const ConvLayer& L = kLayers[li];
         const bool freq = Cfg::is_freq(l);
-        HB_REQUIRE(L.cin == Cfg::cin(l) * 8 && L.cout == Cfg::C && L.kh * L.kw == 3 && L.leaky && (L.kw == 3) == freq,
+        const bool mel_layer = Cfg::MEL_IN && l == 0;         // conv2d: Cin = 1, fed as the (hi, lo) fp16 pair of the mel value
+        HB_REQUIRE((mel_layer ? L.cin == 1 && Cfg::cin(l) == 1 : L.cin == Cfg::cin(l) * 8) && L.cout == Cfg::C && L.kh * L.kw == 3 &&
+                       L.leaky && (L.kw == 3) == freq,
                    "tcg: unexpected layer table entry for conv2d_%d", li);
         const float* w = weights_host + w_off[li];            // [tap][cin][cout]
         for (int kk = 0; kk < Cfg::kchunks(l); ++kk) {
@@ -553,9 +521,9 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
                 if (o >= 3 || rc >= Cfg::RC) continue;
                 const int tap = freq ? d - i + 1 : d - i;
                 if (tap < 0 || tap > 2) continue;
-                for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < (mel_layer ? 2 : 8); ++e)
                     packed[(size_t)Cfg::w_off(l) / 2 + ((size_t)kk * 128 + row) * 8 + e] =
-                        __float2half_rn(w[((int64_t)tap * L.cin + c * 8 + e) * L.cout + cc * 8 + r]);
+                        __float2half_rn(w[((int64_t)tap * L.cin + (mel_layer ? 0 : c * 8 + e)) * L.cout + cc * 8 + r]);
             }
         }
         for (int n = 0; n < Cfg::C; ++n) bias[(size_t)l * Cfg::C + n] = weights_host[b_off[li] + n];
@@ -654,7 +622,8 @@ int tcg_block1(const hb_embed_model* m, const float* mel, __half* out, int B, in
                cudaStream_t st) {
     const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
     HB_REQUIRE(gw != nullptr, "tcg weights missing");
-    return tcg_launch<Cfg1>(gw, 0, mel, 0, out, B, in_T, dbg, dbg_layer, st);
+    // conv2d is tensor-core layer 0 of the block: the caller's 100 (conv2d) / 0 / 1 are layers 0 / 1 / 2
+    return tcg_launch<Cfg1>(gw, 0, mel, 0, out, B, in_T, dbg, dbg_layer == 100 ? 0 : dbg_layer + 1, st);
 }
 
 // block 1 output fp16 [B][4][in_T][16][8] -> conv2d_7 output after its 1x2 pool, fp16 chunk-major [B][6][in_T - 4][8][8].
