@@ -64,6 +64,9 @@ int tcg_block2(const hb_embed_model* m, const __half* in_dev, __half* out_dev, i
                cudaStream_t st);
 int tcg_block3(const hb_embed_model* m, const __half* in_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
                cudaStream_t st);
+int tcg_block4(const hb_embed_model* m, const __half* in_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st);
+int tcg_block4_max_rows();
 int tcg_check_timeout();
 int tcg_debug_times(long long* out_host);
 }  // namespace hb

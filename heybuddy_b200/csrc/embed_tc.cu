@@ -28,6 +28,11 @@
 //  * conv2d (Cin = 1) is CUDA-core work fused into block 1's prologue; the last 2x2 max-pool (both
 //    phases) is fused into the tail block's loader; block 5 runs on the same kernel, 6 clips per CTA.
 #include "tc_ptx.cuh"
+#ifdef HB_EXP_NO_WEIGHTS   // timing experiment only (wrong results): weight refills shrink to 16 bytes
+#define HB_EXP_WB(x) 16u
+#else
+#define HB_EXP_WB(x) (x)
+#endif
 
 #include <cstdlib>
 #include <vector>
@@ -336,8 +341,8 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                 mbar_wait(&hdr.tmem_full[it % kSlots], (uint32_t)((it / kSlots) & 1));
                 if (lane == 0) {
                     const TcLayer& Ln = a.layers[l + 1];
-                    mbar_expect_tx(&hdr.wbar[0], (uint32_t)Ln.w_bytes);
-                    bulk_g2s(wbuf0, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[0]);
+                    mbar_expect_tx(&hdr.wbar[0], HB_EXP_WB((uint32_t)Ln.w_bytes));
+                    bulk_g2s(wbuf0, a.w_packed + Ln.w_off, HB_EXP_WB((uint32_t)Ln.w_bytes), &hdr.wbar[0]);
                 }
             }
             __syncwarp();
@@ -845,7 +850,9 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     static const bool b3_old = getenv("HB_B3_OLD") != nullptr;   // A/B switch while tuning
     if (b3_old) { if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc; }
     else if ((rc = tcg_block3(m, hB, hA, B, g[2].T_in, nullptr, -1, st))) return rc;
-    if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc;
+    static const bool b4_old = getenv("HB_B4_OLD") != nullptr;   // A/B switch while tuning
+    if (b4_old) { if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc; }
+    else if ((rc = tcg_block4(m, hA, hB, B, g[3].T_in, nullptr, -1, st))) return rc;
     for (int p = 0; p < 2; ++p)
         if (need_phase[p] && (rc = launch_block(m, 4, gt, hB, tmp[p], B, 12, 4, p, nullptr, -1, st))) return rc;
     return fp32_gather_slots(tmp[0], tmp[1], gt.T_out, gt.T_out, slot_m_dev, n_slots, out, B, st);
@@ -879,8 +886,8 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         const int last_layer_of_block = p.first_layer + p.n_layers - 1;
         int dbg_layer = -1;
         if (last && layer != last_layer_of_block) dbg_layer = (layer == 0) ? 100 : layer - p.first_layer;
-        if (b <= 2) {
-            // blocks 1-3 run on the grouped kernels (embed_tcg.cu), which dump f32 NHWC directly
+        if (b <= 3) {
+            // blocks 1-4 run on the grouped kernels (embed_tcg.cu), which dump f32 NHWC directly
             const __half* in_h = reinterpret_cast<const __half*>(in);
             if (dbg_layer >= 0) {
                 int t_convs = 0;
@@ -890,7 +897,8 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
                 if (n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
                 int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, out, dbg_layer, st)
                        : b == 1 ? tcg_block2(m, in_h, bufs[which], B, g[1].T_in, out, dbg_layer, st)
-                                : tcg_block3(m, in_h, bufs[which], B, g[2].T_in, out, dbg_layer, st);
+                       : b == 2 ? tcg_block3(m, in_h, bufs[which], B, g[2].T_in, out, dbg_layer, st)
+                                : tcg_block4(m, in_h, bufs[which], B, g[3].T_in, out, dbg_layer, st);
                 if (rc) return rc;
                 if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("hb_embed_activation: kernel failed"); return HB_ERR_CUDA; }
                 if (check_timeout() != HB_OK) return HB_ERR_CUDA;
@@ -898,13 +906,14 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
             }
             int rc = b == 0 ? tcg_block1(m, mel, bufs[which], B, F, nullptr, -1, st)
                    : b == 1 ? tcg_block2(m, in_h, bufs[which], B, g[1].T_in, nullptr, -1, st)
-                            : tcg_block3(m, in_h, bufs[which], B, g[2].T_in, nullptr, -1, st);
+                   : b == 2 ? tcg_block3(m, in_h, bufs[which], B, g[2].T_in, nullptr, -1, st)
+                            : tcg_block4(m, in_h, bufs[which], B, g[3].T_in, nullptr, -1, st);
             if (rc) return rc;
         } else if (dbg_layer >= 0) {
             const int64_t need = (int64_t)g[b].grid * g[b].ch_alloc * g[b].P_alloc * 16;
             if (cudaMalloc(&dbg_mem, need) != cudaSuccess) { set_error("hb_embed_activation: debug allocation failed"); return HB_ERR_CUDA; }
         }
-        if (b > 2) {
+        if (b > 3) {
             int rc = launch_block(m, b, g[b], in, bufs[which], B, in_chunks[b], in_F[b], 0, reinterpret_cast<__half*>(dbg_mem), dbg_layer, st);
             if (rc) { if (dbg_mem) cudaFree(dbg_mem); return rc; }
         }

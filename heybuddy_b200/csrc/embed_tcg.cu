@@ -28,6 +28,11 @@
 // NaN note: the zero Toeplitz entries multiply neighbouring positions of the same tile, so a non-finite activation
 // reaches up to 3 more positions of its own clip than in the reference arithmetic (0 * inf); finite data is unaffected.
 #include "tc_ptx.cuh"
+#ifdef HB_EXP_NO_WEIGHTS   // timing experiment only (wrong results): weight refills shrink to 16 bytes
+#define HB_EXP_WB(x) 16u
+#else
+#define HB_EXP_WB(x) (x)
+#endif
 
 #include <vector>
 
@@ -38,9 +43,7 @@ namespace {
 #ifndef HB_TCG_THREADS23
 #define HB_TCG_THREADS23 320   // launch shape of blocks 2 and 3 (320 = 8 epilogue warps, 576 = 16)
 #endif
-constexpr int kGPlane = 4096 + 32;  // bytes per plane: 256 columns + a 32-byte skew so that chunk planes start in different banks
 constexpr int kGPlanes = 12;        // planes allocated (G * channel chunks <= 12)
-constexpr int kGActBytes = kGPlanes * kGPlane;
 constexpr int kGTmemCols = 256;
 constexpr int kGMaxLayers = 4;
 // Epilogue scatter table of a layer: entry (n & 15) * kGTabRow + (n >> 4) = byte offset >> 4 of accumulator column n in the layer's
@@ -50,13 +53,20 @@ constexpr int kGTabRow = 20;
 
 // G positions per column, CC 8-channel chunks (G * CC = 12 row chunks = 96 M rows), F freq bins (F / G = 8), TT input rows
 // per tile (multiple of G), NL tensor-core layers alternating freq / time, CIN0 input chunks of the first layer.
-template <int G_, int CC_, int F_, int TT_, int NL_, bool FIRST_FREQ_, int CIN0_, int POOL_T_, bool MEL_IN_, int OUT_CH_, int CONV0_, int THREADS_>
+template <int G_, int CC_, int F_, int TT_, int NL_, bool FIRST_FREQ_, int CIN0_, int POOL_T_, bool MEL_IN_, int OUT_CH_, int CONV0_, int THREADS_,
+          int POOL_F_ = 2, int PCOLS_ = 256>
 struct GCfg {
     // launch shape: warp 0 MMA issuer, warp 1 weight loader, then 8 or 16 epilogue warps (2 or 4 per TMEM lane quadrant, each
     // owning 128 or 64 accumulator columns = two fragments of SUBC columns per 16-lane half)
     static constexpr int THREADS = THREADS_, EPI_WARPS = THREADS_ / 32 - 2, PARTS = EPI_WARPS / 4, SUBC = 128 / PARTS;
     static_assert(THREADS_ % 32 == 0 && (EPI_WARPS == 8 || EPI_WARPS == 16), "launch shape");
     static constexpr int G = G_, CC = CC_, F = F_, TT = TT_, NL = NL_, CIN0 = CIN0_, POOL_T = POOL_T_, OUT_CH = OUT_CH_;
+    static constexpr int POOL_F = POOL_F_, PCOLS = PCOLS_;
+    static constexpr int FG = F_ / G_;                         // column groups per row (a freq conv's row has FG + 1 columns: + the zero pad)
+    // bytes per plane: PCOLS columns; a plane pitch that is a multiple of 128 B gets a 32-byte skew so that chunk planes start in
+    // different banks
+    static constexpr int PLANE = PCOLS_ * 16 + ((PCOLS_ * 16) % 128 == 0 ? 32 : 0);
+    static constexpr int ACT_BYTES = kGPlanes * PLANE;
     static constexpr bool FIRST_FREQ = FIRST_FREQ_, MEL_IN = MEL_IN_;
     static constexpr int CONV0 = CONV0_;                       // conv index (layer table) of the first tensor-core layer
     static constexpr int C = CC * 8;
@@ -65,21 +75,22 @@ struct GCfg {
     static constexpr int W_MAX = (((G + 2) * CC + 2) & ~1) * 2048;   // largest A operand: [K chunk][row 128][8]
     static constexpr int PLAIN = TT * F * 16;                  // layout P bytes per chunk
     static constexpr int RC = G * CC;                          // row chunks (sub-position, channel chunk); rows = 8 RC <= 96
-    static_assert(RC <= kGPlanes && F / G == 8 && TT % G == 0 && (TT / G) * F <= 256 && TT * 9 <= 256, "tile shape");
-    static_assert(CC * PLAIN <= kGActBytes && ROWS_OUT % POOL_T == 0, "tile shape");
+    static_assert(RC <= kGPlanes && F % G == 0 && TT % G == 0 && (TT / G) * F <= 256 && TT * (FG + 1) <= 256, "tile shape");
+    static_assert(TT * (FG + 1) + 2 <= PCOLS_ && (TT / G) * F + (G > 1 ? F : 2 * F) <= PCOLS_, "plane too small for the MMAs' reads");
+    static_assert(CC * PLAIN <= ACT_BYTES && ROWS_OUT % POOL_T == 0, "tile shape");
     __host__ __device__ static constexpr bool is_freq(int l) { return ((l & 1) == 0) == FIRST_FREQ; }
     __host__ __device__ static constexpr int cin(int l) { return l == 0 ? CIN0 : CC; }
     __host__ __device__ static constexpr int kreal(int l) { return (G + 2) * cin(l); }            // K chunks of the conv itself
     // + one "ones" chunk that carries the bias (A row = [bias_hi, bias_lo, 0..], B record = [1, 1, 0..]), padded to whole K = 16 steps
     __host__ __device__ static constexpr int kchunks(int l) { return (kreal(l) + 2) & ~1; }
     // the constant ones plane: a spare plane when the block uses fewer than 12, else right after the buffer's guard + dump slots
-    static constexpr int ONES_OFF = RC < kGPlanes ? RC * kGPlane : kGActBytes + 512 + 128;
-    static constexpr int EXTRA_SMEM = RC < kGPlanes ? 0 : kGPlane + 64;
+    static constexpr int ONES_OFF = RC < kGPlanes ? RC * PLANE : ACT_BYTES + 512 + 128;
+    static constexpr int EXTRA_SMEM = RC < kGPlanes ? 0 : PLANE + 64;
     __host__ __device__ static constexpr int w_bytes(int l) { return kchunks(l) * 2048; }
     __host__ __device__ static constexpr int w_off(int l) { return l == 0 ? 0 : w_off(l - 1) + w_bytes(l - 1); }
-    __host__ __device__ static constexpr int pi(int f) { return (f % G) * 8 + f / G; }
+    __host__ __device__ static constexpr int pi(int f) { return (f % G) * FG + f / G; }
     // accumulator columns a layer really has (a multiple of 16): an MMA costs N / 2 cycles, so N is not rounded up to 256
-    __host__ __device__ static constexpr int ncols(int l) { return ((is_freq(l) ? TT * 9 : (TT / G) * F) + 15) & ~15; }
+    __host__ __device__ static constexpr int ncols(int l) { return ((is_freq(l) ? TT * (FG + 1) : (TT / G) * F) + 15) & ~15; }
     // K chunk kk = c * (G + 2) + ord (channel chunk major).  ord -> input offset d within the group: time d = dt = ord;
     // freq d = df: 0 .. G, -1 (G >= 2) or -1, 0, 1 (G = 1) -- orders that keep every K-step pair address-ordered.
     __host__ __device__ static constexpr int kd(int l, int kk) {
@@ -93,14 +104,16 @@ struct GCfg {
         if (is_freq(l)) {
             const int fm = ((d % G) + G) % G;
             const int sh = d < 0 ? 0 : (d >= G ? 2 : 1);        // 1 + column shift (column 0 is the guard)
-            return (uint32_t)((fm * ci + c) * kGPlane + sh * 16);
+            return (uint32_t)((fm * ci + c) * PLANE + sh * 16);
         }
-        return (uint32_t)(((d % G) * ci + c) * kGPlane + (d / G) * F * 16);
+        return (uint32_t)(((d % G) * ci + c) * PLANE + (d / G) * F * 16);
     }
 };
 using Cfg1 = GCfg<4, 3, 32, 28, 4, true, 1, 2, true, 4, 0, 320>;     // conv2d (mel as an fp16 hi + lo pair) .. conv2d_3, pool 2x2
 using Cfg2 = GCfg<2, 6, 16, 26, 4, true, 3, 1, false, 6, 4, HB_TCG_THREADS23>;    // conv2d_4..7, pool 1x2
-using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8, HB_TCG_THREADS23>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
+using Cfg3 = GCfg<1, 9, 8, 24, 4, true, 6, 2, false, 10, 8, HB_TCG_THREADS23>;
+// conv2d_12..15, no pool (the tail pools with a time phase): the whole clip (<= 32 rows) is one tile; 162-column planes keep two CTAs per SM
+using Cfg4 = GCfg<1, 12, 4, 32, 4, true, 9, 1, false, 12, 12, 320, 1, 162>;    // conv2d_8..11, pool 2x2 (one position per column, N = 256)
 
 struct GArgs {
     const void* in;               // MEL_IN: mel f32 [clips][in_T][32]; else fp16 chunk-major [clips][in_chunks][in_T][F][8]
@@ -170,7 +183,8 @@ __device__ __forceinline__ void issue_layer(int l, uint32_t d_tmem, uint64_t a_b
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs a) {
     constexpr int kGThreads = Cfg::THREADS, kGEpiWarps = Cfg::EPI_WARPS;
-    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C;
+    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C, FG = Cfg::FG;
+    constexpr int kGPlane = Cfg::PLANE, kGActBytes = Cfg::ACT_BYTES;
     extern __shared__ __align__(128) unsigned char smem[];
     GSmemHeader<Cfg>& hdr = *reinterpret_cast<GSmemHeader<Cfg>*>(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
     // everything the MMAs may read must be finite: clear the activation buffer and its guard
     for (int i = tid; i < (kGActBytes + 512) / 16; i += kGThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
     if (Cfg::RC < kGPlanes) __syncthreads();                  // the ones plane is one of the planes just cleared
-    for (int i = tid; i < 256 + 2; i += kGThreads)            // [1, 1, 0, 0, 0, 0, 0, 0] per column: the bias K chunk's B operand
+    for (int i = tid; i < Cfg::PCOLS + 2; i += kGThreads)     // [1, 1, 0, 0, 0, 0, 0, 0] per column: the bias K chunk's B operand
         *reinterpret_cast<uint4*>(act + Cfg::ONES_OFF + i * 16) = make_uint4(0x3c003c00u, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
         // the buffer holds the previous tile's layout P: restore layout F's zero padding (column 0, group 8 of every row)
         for (int i = tid; i < G * Cfg::CIN0 * (TT + 1); i += kGThreads) {
             const int pl = i / (TT + 1), k = i - pl * (TT + 1);
-            const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
+            const int col = k == 0 ? 0 : 1 + (FG + 1) * (k - 1) + FG;
             *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
         }
     }
@@ -251,7 +265,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
                 const int t = i / kMels, f = i - t * kMels;
                 const __half hi = __float2half_rn(mel_reg[k]);
                 const __half lo = __float2half_rn(mel_reg[k] - __half2float(hi));
-                *reinterpret_cast<uint4*>(act + (f % G) * kGPlane + (1 + 9 * t + f / G) * 16) =
+                *reinterpret_cast<uint4*>(act + (f % G) * kGPlane + (1 + (FG + 1) * t + f / G) * 16) =
                     make_uint4((uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16), 0, 0, 0);
             }
         }
@@ -264,7 +278,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
             const int t = rem / F, f = rem - t * F;
             // rows past the clip are zero-filled (src-size 0): they only feed outputs that are dropped, but must be finite
             const bool real = row0 + t < a.in_T;
-            cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + 9 * t + f / G) * 16,
+            cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + (FG + 1) * t + f / G) * 16,
                        real ? in + ((int64_t)c * a.in_T + row0 + t) * F + f : in, real ? 16u : 0u);
         }
         cp_async_wait_all();
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
         for (int i = tid; i < Cfg::ROWS_OUT * F * C; i += kGThreads) {
             const int c = i % C, f = (i / C) % F, t = i / (C * F);
             if (row0 + t >= a.dbg_T || (c >> 3) >= cc_planes) continue;
-            const unsigned char* p = layout_f ? act + ((f % G) * cc_planes + (c >> 3)) * kGPlane + (1 + 9 * t + f / G) * 16
+            const unsigned char* p = layout_f ? act + ((f % G) * cc_planes + (c >> 3)) * kGPlane + (1 + (FG + 1) * t + f / G) * 16
                                               : act + ((t % G) * cc_planes + (c >> 3)) * kGPlane + ((t / G) * F + Cfg::pi(f)) * 16;
             a.dbg[(((int64_t)clip * a.dbg_T + row0 + t) * F + f) * C + c] = __half2float(reinterpret_cast<const __half*>(p)[c & 7]);
         }
@@ -313,18 +327,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
             mbar_wait(&hdr.tmem_full, ph & 1u);
             if (lane == 0 && !last) {
-                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(l + 1));
-                bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), (uint32_t)Cfg::w_bytes(l + 1), &hdr.wbar);
+                mbar_expect_tx(&hdr.wbar, HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)));
+                bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)), &hdr.wbar);
             } else if (lane == 0 && tile_id + (int)gridDim.x < n_tiles) {
                 // the next tile's first layer: its weights arrive under this tile's last epilogue, store and next staging
-                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
-                bulk_g2s(wbuf, a.w, (uint32_t)Cfg::w_bytes(0), &hdr.wbar);
+                mbar_expect_tx(&hdr.wbar, HB_EXP_WB((uint32_t)Cfg::w_bytes(0)));
+                bulk_g2s(wbuf, a.w, HB_EXP_WB((uint32_t)Cfg::w_bytes(0)), &hdr.wbar);
             }
             if (!freq && !last) {
                 // the epilogue is writing layout F: zero its SAME padding (column 0 and group 8 of every row, all planes)
                 for (int i = lane; i < Cfg::RC * (TT + 1); i += 32) {
                     const int pl = i / (TT + 1), k = i - pl * (TT + 1);
-                    const int col = k == 0 ? 0 : 1 + 9 * (k - 1) + 8;
+                    const int col = k == 0 ? 0 : 1 + (FG + 1) * (k - 1) + FG;
                     *reinterpret_cast<uint4*>(act + pl * kGPlane + col * 16) = make_uint4(0, 0, 0, 0);
                 }
             }
@@ -333,31 +347,33 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr.tmem_empty);
         } else {
-            constexpr int SUBC = Cfg::SUBC, PARTC = 2 * Cfg::SUBC;      // columns per fragment / per warp
-            const int e = warp - 2, quad = warp & 3, part = e >> 2;     // TMEM lane quadrant, column part
+            // columns per fragment; a warp's two fragments are SUBC-column blocks 2 part, 2 part + 1 -- or part, part + PARTS
+            // (interleaved) in the narrow-plane configuration, so that its 128 / 160-column layers spread over all the warps
+            constexpr int SUBC = Cfg::SUBC, S_PART = Cfg::PCOLS < 256 ? 1 : 2, S_SUB = Cfg::PCOLS < 256 ? Cfg::PARTS : 1;
+            const int e = warp - 2, quad = warp & 3, part = e >> 2;
             const int m = lane >> 3;
             // (sub-position i, chunk cc) -> byte offset in the layer's target layout
-            const uint32_t i_unit = freq ? 128u : (last ? (uint32_t)(F * 16) : 9u * 16u);
+            const uint32_t i_unit = freq ? (uint32_t)(FG * 16) : (last ? (uint32_t)(F * 16) : (uint32_t)((FG + 1) * 16));
             const uint32_t cc_unit = last ? (uint32_t)Cfg::PLAIN : (uint32_t)kGPlane;
             // four fragments per warp: (16-lane half h, SUBC-column sub).  Half 0 holds row chunks 3 quad, 3 quad + 1 (stmatrix.x4:
             // matrix m = row chunk m & 1, column group m >> 1), half 1 row chunk 3 quad + 2 (stmatrix.x2: column group m & 1).
             const int rc_a = 3 * quad + (m & 1), rc_b = 3 * quad + 2;
             const uint32_t base_a = act_u32 + (uint32_t)(rc_a / CC) * i_unit + (uint32_t)(rc_a % CC) * cc_unit;
             const uint32_t base_b = act_u32 + (uint32_t)(rc_b / CC) * i_unit + (uint32_t)(rc_b % CC) * cc_unit;
-            const uint16_t* tab_a = hdr.tab[l] + (8 * (m >> 1) + (lane & 7)) * kGTabRow + part * (PARTC / 16);
-            const uint16_t* tab_b = hdr.tab[l] + (8 * (m & 1) + (lane & 7)) * kGTabRow + part * (PARTC / 16);
+            const uint16_t* tab_a = hdr.tab[l] + (8 * (m >> 1) + (lane & 7)) * kGTabRow + part * (S_PART * SUBC / 16);
+            const uint16_t* tab_b = hdr.tab[l] + (8 * (m & 1) + (lane & 7)) * kGTabRow + part * (S_PART * SUBC / 16);
             uint32_t frag[2][SUBC / 2];
             const int n_half = (3 * quad + 2 < Cfg::RC) ? 2 : ((3 * quad < Cfg::RC) ? 1 : 0);   // rows of half 1 / half 0 exist?
             // columns at or past ncols were never written
-            const int n_sub = (part * PARTC >= Cfg::ncols(l)) ? 0 : ((part * PARTC + SUBC < Cfg::ncols(l)) ? 2 : 1);
+            const int n_sub = (part * S_PART * SUBC >= Cfg::ncols(l)) ? 0 : (((part * S_PART + S_SUB) * SUBC < Cfg::ncols(l)) ? 2 : 1);
             const int n_frag = n_half * n_sub;
             auto frag_addr = [&](int k) {
                 const int h = k / n_sub, sub = k - h * n_sub;
-                return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)(part * PARTC + sub * SUBC);
+                return tmem_base + ((uint32_t)(quad * 32 + h * 16) << 16) + (uint32_t)((part * S_PART + sub * S_SUB) * SUBC);
             };
             auto frag_tab = [&](int k) {
                 const int h = k / n_sub, sub = k - h * n_sub;
-                const uint16_t* t = (h == 0 ? tab_a : tab_b) + sub * (SUBC / 16);
+                const uint16_t* t = (h == 0 ? tab_a : tab_b) + sub * (S_SUB * SUBC / 16);
                 if constexpr (SUBC == 64) return *reinterpret_cast<const uint2*>(t);
                 else return make_uint2(*reinterpret_cast<const uint32_t*>(t), 0u);
             };
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
                     tmem_ld_frag_issue(frag_addr(k + 1), frag[(k + 1) & 1]);
                     tb = frag_tab(k + 1);
                 }
-                const int col0 = part * PARTC + sub * SUBC;
+                const int col0 = (part * S_PART + sub * S_SUB) * SUBC;
                 if (h == 0) g_epilogue<true, SUBC / 2>(frag[k & 1], tb_k, base_a, col0, Cfg::ncols(l));
                 else g_epilogue<false, SUBC / 2>(frag[k & 1], tb_k, base_b, col0, Cfg::ncols(l));
             }
@@ -402,8 +418,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
 
     // ---- max-pool + store (fp16 chunk-major [clip][OUT_CH][T_out][F / 2][8]) -----------------------------------
     {
-        constexpr int PT = Cfg::POOL_T, Fo = F / 2;
+        constexpr int PT = Cfg::POOL_T, PF = Cfg::POOL_F, Fo = F / PF;
         constexpr int rows_p = Cfg::ROWS_OUT / PT;
+        static_assert(PT == 1 || PF == 2, "a time pool comes with a freq pool");
         const int rowp0 = tile * rows_p;
         uint4* out = reinterpret_cast<uint4*>(a.out);
         for (int i = tid; i < Cfg::OUT_CH * rows_p * Fo; i += kGThreads) {
@@ -414,13 +431,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
             uint4 o = make_uint4(0, 0, 0, 0);
             if (ch < CC) {
                 constexpr int dpi = (Cfg::pi(1) - Cfg::pi(0)) * 16;   // pi(2 fo + 1) - pi(2 fo), in bytes
-                const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(2 * fo) * 16;
-                const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + dpi);
+                const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(PF * fo) * 16;
+                const uint4 x0 = *reinterpret_cast<const uint4*>(base);
                 const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
                 __half2 mx[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(h0[j], h1[j]);
+                for (int j = 0; j < 4; ++j) mx[j] = h0[j];
+                if (PF == 2) {
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(base + dpi);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(mx[j], h1[j]);
+                }
                 if (PT == 2) {
                     const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + dpi);
                     const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
@@ -441,15 +463,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
 }
 
 struct GWeights {
-    unsigned char* w[3] = {nullptr, nullptr, nullptr};
-    float* bias[3] = {nullptr, nullptr, nullptr};
-    uint16_t* tab[3] = {nullptr, nullptr, nullptr};
+    unsigned char* w[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* bias[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint16_t* tab[4] = {nullptr, nullptr, nullptr, nullptr};
     float* l0 = nullptr;
 };
 
 template <class Cfg>
 size_t tcg_smem_bytes() {
-    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + kGActBytes + 512 + 128 + Cfg::EXTRA_SMEM + 128;
+    return ((sizeof(GSmemHeader<Cfg>) + 127) & ~(size_t)127) + Cfg::W_MAX + Cfg::ACT_BYTES + 512 + 128 + Cfg::EXTRA_SMEM + 128;
 }
 
 // Epilogue scatter table of layer l: accumulator column n -> byte offset >> 4 of its first output record in the layer's target
@@ -459,21 +481,21 @@ size_t tcg_smem_bytes() {
 // of zeros).  A time layer has no padding columns below ncols(l); the epilogue skips the 16-column groups at or past it.
 template <class Cfg>
 void tcg_tables(std::vector<uint16_t>& tab) {
-    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL;
-    static_assert((TT / G) * F + 8 * G <= 256, "no free columns for the freq layers' padding outputs");
+    constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, FG = Cfg::FG, kGPlane = Cfg::PLANE;
+    static_assert((TT / G) * F + FG * G <= 256 && (TT / G) * F % 16 == 0, "no free columns for the freq layers' padding outputs");
     tab.assign((size_t)NL * kGTabRow * 16, 0);
     for (int l = 0; l < NL; ++l)
         for (int n = 0; n < 256; ++n) {
             int off;
             if (Cfg::is_freq(l)) {
                 // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
-                const int t = n / 9, fg = n - t * 9;
-                const bool valid = fg < 8 && t < TT;
+                const int t = n / (FG + 1), fg = n - t * (FG + 1);
+                const bool valid = fg < FG && t < TT;
                 off = valid ? (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16 : (TT / G) * F * 16;
             } else {
                 const int tq = n / F, pf = n - tq * F;
                 if (tq >= TT / G) continue;                                                           // >= ncols(l): skipped
-                if (l < NL - 1) off = (pf >> 3) * CC * kGPlane + (1 + 9 * G * tq + (pf & 7)) * 16;   // -> layout F
+                if (l < NL - 1) off = (pf / FG) * CC * kGPlane + (1 + (FG + 1) * G * tq + (pf % FG)) * 16;   // -> layout F
                 else off = (G * tq * F + pf) * 16;                                                    // -> layout P
             }
             tab[(size_t)l * kGTabRow * 16 + (size_t)(n & 15) * kGTabRow + (n >> 4)] = (uint16_t)(off >> 4);
@@ -598,6 +620,7 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
     if ((rc = tcg_pack<Cfg1>(weights_host, w_off, b_off, &gw->w[0], &gw->bias[0], &gw->tab[0]))) return rc;
     if ((rc = tcg_pack<Cfg2>(weights_host, w_off, b_off, &gw->w[1], &gw->bias[1], &gw->tab[1]))) return rc;
     if ((rc = tcg_pack<Cfg3>(weights_host, w_off, b_off, &gw->w[2], &gw->bias[2], &gw->tab[2]))) return rc;
+    if ((rc = tcg_pack<Cfg4>(weights_host, w_off, b_off, &gw->w[3], &gw->bias[3], &gw->tab[3]))) return rc;
     HB_CUDA_OK(cudaMalloc(&gw->l0, (3 * 24 + 24) * sizeof(float)));
     HB_CUDA_OK(cudaMemcpy(gw->l0, weights_host + w_off[0], (3 * 24 + 24) * sizeof(float), cudaMemcpyHostToDevice));
     return HB_OK;
@@ -606,7 +629,7 @@ int tcg_prepare(hb_embed_model* m, const float* weights_host) {
 void tcg_release(hb_embed_model* m) {
     GWeights* gw = reinterpret_cast<GWeights*>(m->tcg);
     if (!gw) return;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         cudaFree(gw->w[i]);
         cudaFree(gw->bias[i]);
         cudaFree(gw->tab[i]);
@@ -643,6 +666,16 @@ int tcg_block3(const hb_embed_model* m, const __half* in, __half* out, int B, in
     HB_REQUIRE(gw != nullptr, "tcg weights missing");
     return tcg_launch<Cfg3>(gw, 2, in, 6, out, B, in_T, dbg, dbg_layer, st);
 }
+
+// block 3 output fp16 [B][10][in_T][4][8] (chunk 9 = padding, not read) -> conv2d_15 output before its pool, fp16 chunk-major
+// [B][12][in_T - 4][4][8] (a 1.44 s clip has in_T = 30: one tile).  dbg: activation after conv2d_12 / 13 / 14, f32 NHWC [B][rows][4][96].
+int tcg_block4(const hb_embed_model* m, const __half* in, __half* out, int B, int in_T, float* dbg, int dbg_layer,
+               cudaStream_t st) {
+    const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
+    HB_REQUIRE(gw != nullptr, "tcg weights missing");
+    return tcg_launch<Cfg4>(gw, 3, in, 10, out, B, in_T, dbg, dbg_layer, st);
+}
+int tcg_block4_max_rows() { return Cfg4::TT; }
 
 // profiling aid: phase timestamps (start, setup, staged, layers.., stored, dealloc) of the first 8 CTAs of the last launch
 int tcg_debug_times(long long* out_host) {
