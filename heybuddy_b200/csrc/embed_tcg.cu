@@ -273,6 +273,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
     } else {
         // fp16 chunk-major rows [row0, row0 + TT) -> layout F (the first layer is a freq conv), 16-byte cp.async records
         const uint4* in = reinterpret_cast<const uint4*>(a.in) + (int64_t)clip * a.in_chunks * a.in_T * F;
+#ifndef HB_TCG_NO_PREFETCH
+        // the next tile's rows (written to HBM by the previous block's kernel) start their trip to L2 now: its staging then pays an
+        // L2 latency instead of an HBM one
+        if (tid < Cfg::CIN0 && tile_id + (int)gridDim.x < n_tiles) {
+            const int nt = tile_id + (int)gridDim.x, nc = nt / a.tiles_per_clip, nr0 = (nt - nc * a.tiles_per_clip) * Cfg::ROWS_OUT;
+            const int rows = min(TT, a.in_T - nr0);
+            if (rows > 0)
+                bulk_prefetch_l2(reinterpret_cast<const uint4*>(a.in) + (((int64_t)nc * a.in_chunks + tid) * a.in_T + nr0) * F,
+                                 (uint32_t)(rows * F * 16));
+        }
+#endif
         for (int i = tid; i < Cfg::CIN0 * TT * F; i += kGThreads) {
             const int c = i / (TT * F), rem = i - c * (TT * F);
             const int t = rem / F, f = rem - t * F;
