@@ -566,6 +566,13 @@ __device__ __forceinline__ float block_sum_n(float v, float* scratch, int n_warp
     return scratch[32];
 }
 
+// bulk L2 prefetch of the byte range [p, p + bytes) widened to 16-byte boundaries
+__device__ __forceinline__ void prefetch_range_l2(const void* p, int64_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
+    const uint32_t n = (uint32_t)(((reinterpret_cast<uintptr_t>(p) + (uintptr_t)bytes + 15) & ~(uintptr_t)15) - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+}
+
 // kI16: the length fix (a1: /32768, front-truncate or left-pad by pad_before) is fused into the load -- the clip comes
 // straight from the ragged int16 samples and the f32 [n][T] intermediate never exists in HBM.
 template <bool kI16>
@@ -573,7 +580,7 @@ __global__ void __launch_bounds__(kFastThreads, 1)
 augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
                     const int32_t* __restrict__ pad_before, const float* __restrict__ noise_bank,
                     const float* __restrict__ colored_bases, const float2* __restrict__ rir_specs,
-                    const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan) {
+                    const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan, int prefetch_ahead) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float scratch[40];
     __shared__ TwTables tw;
@@ -662,6 +669,22 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         }
     }
 
+#ifndef HB_AUG_NO_PREFETCH
+    // One CTA per SM and one clip per CTA: the load phase above cannot overlap this CTA's own FFT.  CTAs are dispatched in
+    // order, so the clip that will follow on this SM is about one wave (gridDim-independent: prefetch_ahead CTAs) ahead: start
+    // its source samples and noise row on their way to L2 now.
+    if (tid == 0 && prefetch_ahead > 0 && (int)blockIdx.x + prefetch_ahead < (int)gridDim.x) {
+        const int nb = (int)blockIdx.x + prefetch_ahead;
+        if (kI16) {
+            const int64_t q0 = offsets[nb], q1 = offsets[nb + 1];
+            if (q1 > q0) prefetch_range_l2(samples + q0, (q1 - q0) * 2);
+        } else {
+            prefetch_range_l2(clips + (int64_t)nb * T, (int64_t)T * 4);
+        }
+        const int64_t noff = params[nb].noise_offset;
+        if (noff >= 0 && noise_bank != nullptr) prefetch_range_l2(noise_bank + noff, (int64_t)T * 4);
+    }
+#endif
     // every thread only ever touches its own points n = tid + i NT until the FFT: no barriers needed in between
     // ---- K1 coloured noise + K2 gain ---------------------------------------------------------------
     if (has_colored) {
@@ -831,6 +854,22 @@ extern "C" int hb_rir_spectrum(const float* kernels_dev, float* spec_dev, int n,
     return HB_OK;
 }
 
+// CTAs ahead whose inputs a CTA prefetches into L2 = one wave (one CTA per SM); HB_AUG_PREFETCH overrides (0 = off)
+static int prefetch_distance() {
+    static int d = -1;
+    if (d < 0) {
+        const char* e = getenv("HB_AUG_PREFETCH");
+        if (e) d = atoi(e);
+        else {
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            d = n_sm;
+        }
+    }
+    return d;
+}
+
 extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_bank_dev, const float* colored_bases_dev,
                                     const float* rir_spec_bank_dev, const hb_clip_aug* params_dev, float* out_dev, int n,
                                     int T, void* stream) {
@@ -844,7 +883,7 @@ extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_b
     if (T == kFastT && aligned) {
         augment_fast_kernel<false><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
             clips_dev, nullptr, nullptr, nullptr, noise_bank_dev, colored_bases_dev, reinterpret_cast<const float2*>(rir_spec_bank_dev),
-            params_dev, out_dev, plan);
+            params_dev, out_dev, plan, prefetch_distance());
     } else {
         const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
         augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
@@ -869,7 +908,7 @@ extern "C" int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* o
     if (rc) return rc;
     augment_fast_kernel<true><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
         nullptr, samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev,
-        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, out_dev, plan);
+        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, out_dev, plan, prefetch_distance());
     HB_LAUNCHED();
     return HB_OK;
 }
