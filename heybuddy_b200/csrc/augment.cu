@@ -686,45 +686,54 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
     }
 #endif
     // every thread only ever touches its own points n = tid + i NT until the FFT: no barriers needed in between
-    // ---- K1 coloured noise + K2 gain ---------------------------------------------------------------
+    // ---- K1 coloured noise + K2 gain + K3 background noise: at most two passes over the clip --------------------
+    // A gain that is not followed by coloured noise is not applied on its own: the energy K3 needs is gain^2 * sum(x^2) and
+    // the factor rides the mixing pass.  The mean |x| the reverb rescaling needs is accumulated by whichever pass is last.
+    float e = 0.f, a = 0.f, pending = 1.0f;
+    bool have_abs = false;
     if (has_colored) {
         const float rms = sqrtf(block_sum_n(sumsq, scratch, NW) / (float)T);
-        const float a = rms / exp10f(p.colored_snr_db * 0.05f);
+        const float ac = rms / exp10f(p.colored_snr_db * 0.05f);
         const float* base = colored_bases + (int64_t)p.colored_index * kColoredBase;
         for (int n = tid; n < M; n += NT) {
             const float2 c = __ldg(reinterpret_cast<const float2*>(base + ((2 * n) % kColoredBase)));
             float2 v = buf0[sk(n)];
-            v.x = (v.x + a * c.x) * p.gain;
-            v.y = (v.y + a * c.y) * p.gain;
+            v.x = (v.x + ac * c.x) * p.gain;
+            v.y = (v.y + ac * c.y) * p.gain;
             buf0[sk(n)] = v;
+            e += v.x * v.x + v.y * v.y;
+            a += fabsf(v.x) + fabsf(v.y);
         }
-    } else if (p.gain != 1.0f) {
-        for (int n = tid; n < M; n += NT) {
-            float2 v = buf0[sk(n)];
-            v.x *= p.gain;
-            v.y *= p.gain;
-            buf0[sk(n)] = v;
-        }
+        have_abs = true;
+    } else {
+        pending = p.gain;
     }
 
-    // ---- K3 background noise at the per-clip SNR -------------------------------------------------------
     if (has_noise) {
-        float e = 0.f;
-        for (int n = tid; n < M; n += NT) {
-            const float2 v = buf0[sk(n)];
-            e += v.x * v.x + v.y * v.y;
-        }
-        const float e_s = block_sum_n(e, scratch, NW);
+        const float e_s = has_colored ? block_sum_n(e, scratch, NW) : p.gain * p.gain * block_sum_n(sumsq, scratch, NW);
         const float e_n = block_sum_n(nsq, scratch, NW);
         const float orig = 10.0f * (log10f(e_s) - log10f(e_n));
         const float scale = exp10f((orig - p.noise_snr_db) * 0.05f);
+        a = 0.f;
         for (int n = tid; n < M; n += NT) {
             float2 v = buf0[sk(n)];
             const float2 z = buf1[n];
-            v.x = fmaf(scale, z.x, v.x);
-            v.y = fmaf(scale, z.y, v.y);
+            v.x = fmaf(scale, z.x, v.x * pending);
+            v.y = fmaf(scale, z.y, v.y * pending);
             buf0[sk(n)] = v;
+            a += fabsf(v.x) + fabsf(v.y);
         }
+        have_abs = true;
+    } else if (pending != 1.0f) {
+        a = 0.f;
+        for (int n = tid; n < M; n += NT) {
+            float2 v = buf0[sk(n)];
+            v.x *= pending;
+            v.y *= pending;
+            buf0[sk(n)] = v;
+            a += fabsf(v.x) + fabsf(v.y);
+        }
+        have_abs = true;
     }
 
     if (!has_rir) {
@@ -733,10 +742,11 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
     }
 
     // ---- K4 reverb -------------------------------------------------------------------------------------
-    float a = 0.f;
-    for (int n = tid; n < M; n += NT) {
-        const float2 v = buf0[sk(n)];
-        a += fabsf(v.x) + fabsf(v.y);
+    if (!have_abs) {
+        for (int n = tid; n < M; n += NT) {
+            const float2 v = buf0[sk(n)];
+            a += fabsf(v.x) + fabsf(v.y);
+        }
     }
     const float amp_x = block_sum_n(a, scratch, NW) / (float)T;   // its barriers also publish buf0 and tw
 

@@ -40,6 +40,9 @@ namespace hb {
 
 namespace {
 
+#ifndef HB_TCG_INTERLEAVE
+#define HB_TCG_INTERLEAVE 1   // narrow-plane configuration (block 4): interleave the epilogue warps' column blocks
+#endif
 #ifndef HB_TCG_THREADS23
 #define HB_TCG_THREADS23 320   // launch shape of blocks 2 and 3 (320 = 8 epilogue warps, 576 = 16)
 #endif
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs 
         } else {
             // columns per fragment; a warp's two fragments are SUBC-column blocks 2 part, 2 part + 1 -- or part, part + PARTS
             // (interleaved) in the narrow-plane configuration, so that its 128 / 160-column layers spread over all the warps
-            constexpr int SUBC = Cfg::SUBC, S_PART = Cfg::PCOLS < 256 ? 1 : 2, S_SUB = Cfg::PCOLS < 256 ? Cfg::PARTS : 1;
+            constexpr int SUBC = Cfg::SUBC, S_PART = (Cfg::PCOLS < 256 && HB_TCG_INTERLEAVE) ? 1 : 2, S_SUB = (Cfg::PCOLS < 256 && HB_TCG_INTERLEAVE) ? Cfg::PARTS : 1;
             const int e = warp - 2, quad = warp & 3, part = e >> 2;
             const int m = lane >> 3;
             // (sub-position i, chunk cc) -> byte offset in the layer's target layout
