@@ -166,12 +166,15 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
         __syncwarp();
 
         // banded projection: lane = mel bin, both frames of the pair
+        float fw[kMelTaps];                           // this lane's filterbank taps: loaded once for both frames of the pair
+#pragma unroll
+        for (int j = 0; j < kMelTaps; ++j) fw[j] = s.fbw[j * kMels + lane];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const float* q = s.power[warp][hh] + my_lo;
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < kMelTaps; ++j) acc = fmaf(q[j], s.fbw[j * kMels + lane], acc);
+            for (int j = 0; j < kMelTaps; ++j) acc = fmaf(q[j], fw[j], acc);
             const int fo = f0 + hh;
             if (fo < F)   // NaN-propagating clamp, like np.maximum / torch.clamp
                 mel[((int64_t)clip * F + fo) * kMels + lane] = log10f(acc < 1e-10f ? 1e-10f : acc) + 2.0f;
