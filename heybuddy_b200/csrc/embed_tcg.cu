@@ -1,32 +1,34 @@
-// K7, blocks 1 and 2 (conv2d .. conv2d_3 + 2x2 pool; conv2d_4 .. conv2d_7 + 1x2 pool): tcgen05 implicit GEMMs with
-// G = 4 (24 channels) or G = 2 (48 channels) output positions per accumulator column.
+// K7, blocks 1-4 of the speech-embedding conv stack (conv2d .. conv2d_15, reference embeddings.py:32-42 = one ONNX session
+// run): tcgen05 implicit GEMMs with G output positions per accumulator column.
 //
-// Why a second kernel: an SS tcgen05.mma costs max(141, N/2 + 43) cycles whatever M is (scripts/micro/umma_bench.cu),
-// and block 1 has only 24 channels, so the one-position-per-column form of embed_tc.cu fills 24 of the 128 M rows
-// and pays 6 MMAs (3 taps x K = 32) per 256 positions.  Here M carries (sub-position i = 0..G-1, cout) = 96
-// rows: a column is a group of G adjacent positions ALONG THE CONV AXIS, K runs over the G + 2 input positions the
-// group touches (block 1: 6 x 24 = 144 = nine K = 16 steps) and the A operand is the banded Toeplitz matrix of the
-// 3-tap kernel (zeros where a tap does not connect).  Block 1: 9 MMAs per 1024 positions instead of 24, 162 MMAs
-// per 1.44 s clip instead of 504, and a third of the epilogue calls; block 2 (G = 2): 12 per 512 instead of 18.
+// An SS tcgen05.mma with K = 16 costs N / 2 cycles whatever M is (scripts/micro/umma_swizzle.cu), so the short dimension
+// (24 .. 96 output channels) sits in M and positions in N.  With one position per column a 24-channel layer would fill 24 of
+// the 128 M rows; here M carries (sub-position i = 0..G-1, cout) = up to 96 rows: a column is a group of G adjacent positions
+// ALONG THE CONV AXIS, K runs over the G + 2 input positions the group touches (block 1: 6 x 24 = 144 = nine K = 16 steps)
+// and the A operand is the banded Toeplitz matrix of the 3-tap kernel (zeros where a tap does not connect).  Block 1: 9 MMAs
+// per 1024 positions instead of 24; block 2 (G = 2): 12 per 512 instead of 18; blocks 3 and 4 have G = 1.
 //
-// Layouts (all [plane][column][8 x fp16], 16-byte records, one plane per (phase, 8-channel chunk), 4096 B planes):
-//   T (input of a time conv):  plane (t mod G, chunk), column (t div G) * F + pi(f),  pi(f) = (f mod G) * 8 + f div G
-//   F (input of a freq conv):  plane (f mod G, chunk), column 1 + 9 t + f div G  (group 8 of every row and column 0
-//                              are the zero SAME padding; F / G = 8 in both blocks)
+// Layouts (all [plane][column][8 x fp16], 16-byte records, one plane per (phase, 8-channel chunk); FG = F / G):
+//   T (input of a time conv):  plane (t mod G, chunk), column (t div G) * F + pi(f),  pi(f) = (f mod G) * FG + f div G
+//   F (input of a freq conv):  plane (f mod G, chunk), column 1 + (FG + 1) t + f div G  (group FG of every row and column 0
+//                              are the zero SAME padding)
 //   P (pre-pool output):       [chunk][t * F + pi(f)]
-// A K step is two K chunks = two plane addresses: the UMMA descriptor's (start, LBO) pair expresses any of them, so
-// there is still no im2col.  The permutation pi makes every stmatrix of the epilogue (8 consecutive columns x 8
-// channels) land on 128 contiguous bytes in either target layout.  The tile's single activation buffer is rewritten
-// in place: a layer has one accumulator tile (N = 256 columns), so all of its MMAs have completed (tcgen05.commit)
-// before the first epilogue store.
+// A K step is two K chunks = two plane addresses: the UMMA descriptor's (start, LBO) pair expresses any of them, so there is
+// no im2col.  The tile's single activation buffer is rewritten in place: a layer has one accumulator tile (N <= 256 columns),
+// so all of its MMAs have completed (tcgen05.commit) before the first epilogue store.
 //
-// Tile = 28 (block 1) / 26 (block 2) input rows of one clip -> 24 / 22 output rows; twin launch shape (320 threads,
-// 2 CTAs/SM, 256 TMEM columns each) like embed_tc.cu.  Warp 0 issues MMAs, warp 1 streams the next layer's weights as soon as
-// the current MMAs have completed and zeroes the SAME padding, warps 2-9 run the epilogue (TMEM lane quadrant q holds
-// row chunks 3 q .. 3 q + 2 of the 12 (sub-position, 8-channel chunk) row chunks).
+// conv2d (Cin = 1) is layer 0 of block 1: the f32 mel value enters as one input chunk whose channels 0 / 1 are its fp16
+// hi / lo halves, the A operand carries conv2d's weight in both rows.  The bias of every layer rides the MMA as an extra
+// "ones" K chunk (fp16 hi + lo pair).
 //
-// NaN note: the zero Toeplitz entries multiply neighbouring positions of the same tile, so a non-finite activation
-// reaches up to 3 more positions of its own clip than in the reference arithmetic (0 * inf); finite data is unaffected.
+// Tile = 28 / 26 / 24 / 32 input rows of one clip (blocks 1-4); 320 threads, 2 persistent CTAs per SM, 256 TMEM columns each.
+// Warp 0 issues MMAs, warp 1 streams the next layer's weights as soon as the current MMAs have completed and zeroes the SAME
+// padding, warps 2-9 run the epilogue (TMEM lane quadrant q holds row chunks 3 q .. 3 q + 2 of the 12 (sub-position,
+// 8-channel chunk) row chunks): tcgen05.ld -> LeakyReLU on the packed fp16 pair -> stmatrix.trans through a host-built
+// scatter table straight into the next layer's operand layout.
+//
+// NaN note: the zero Toeplitz entries multiply neighbouring positions of the same tile, so a non-finite activation reaches
+// up to G + 1 more positions of its own clip than in the reference arithmetic (0 * inf); finite data is unaffected.
 #include "tc_ptx.cuh"
 #ifdef HB_EXP_NO_WEIGHTS   // timing experiment only (wrong results): weight refills shrink to 16 bytes
 #define HB_EXP_WB(x) 16u
