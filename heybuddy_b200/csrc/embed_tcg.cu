@@ -45,6 +45,9 @@ namespace {
 #ifndef HB_TCG_INTERLEAVE
 #define HB_TCG_INTERLEAVE 1   // narrow-plane configuration (block 4): interleave the epilogue warps' column blocks
 #endif
+#ifndef HB_TCG_WIDE_CTAS
+#define HB_TCG_WIDE_CTAS 2      // CTAs per SM of the 16-epilogue-warp shape (1 lifts its 56-register cap; experiments only)
+#endif
 #ifndef HB_TCG_THREADS23
 #define HB_TCG_THREADS23 320   // launch shape of blocks 2 and 3 (320 = 8 epilogue warps, 576 = 16)
 #endif
@@ -186,7 +189,7 @@ __device__ __forceinline__ void issue_layer(int l, uint32_t d_tmem, uint64_t a_b
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 2) tcg_block_kernel(const GArgs a) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE_CTAS : 2) tcg_block_kernel(const GArgs a) {
     constexpr int kGThreads = Cfg::THREADS, kGEpiWarps = Cfg::EPI_WARPS;
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, C = Cfg::C, FG = Cfg::FG;
     constexpr int kGPlane = Cfg::PLANE, kGActBytes = Cfg::ACT_BYTES;
@@ -613,7 +616,7 @@ int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __h
         HB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     const int64_t n_tiles = (int64_t)B * a.tiles_per_clip;
-    const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)n_sm);     // persistent: two CTAs per SM stride over the tiles
+    const int grid = (int)std::min<int64_t>(n_tiles, (Cfg::THREADS > 320 ? HB_TCG_WIDE_CTAS : 2) * (int64_t)n_sm);   // persistent: two CTAs per SM stride over the tiles
     tcg_block_kernel<Cfg><<<grid, Cfg::THREADS, tcg_smem_bytes<Cfg>(), st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
