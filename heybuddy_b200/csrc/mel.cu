@@ -30,8 +30,9 @@ struct MelTables {
     float2 win2[256];                // (w[2n], w[2n+1]) of the 512-sample padded Hann window
     float2 w256[256];                // exp(-2 pi i k / 256)
     float2 w512[128];                // exp(-2 pi i k / 512), k = 0..127
-    float fbw[kMelTaps * kMels];     // banded filterbank: fbw[j][m] = fb[lo[m] + j][m]
+    float fbw[kMelTaps * kMels];     // banded filterbank, taps rotated per mel bin: fbw[j][m] = fb[lo[m] + (j + rot[m]) % 16][m]
     int lo[kMels];                   // first FFT bin of mel bin m
+    int rot[kMels];                  // tap rotation of mel bin m: lane m reads power[lo[m] + (j + rot[m]) % 16] at step j
 };
 
 __device__ MelTables g_mel_tables;
@@ -39,15 +40,17 @@ static bool g_tables_ready[64] = {false};
 
 constexpr int kMelThreads = 256;
 constexpr int kMelWarps = kMelThreads / 32;
+constexpr int kPowerRow = 128 + 16;
 constexpr int kTrStride = 17;        // float2 row stride of the transpose tile: conflict-free both ways
 
 struct MelSmem {
-    float2 win2[256];
+    float2 win2[kWinLength / 2];     // the non-zero part of the window: points [kWinPad / 2, (kWinPad + kWinLength) / 2)
     float2 w512[128];
     float fbw[kMelTaps * kMels];
     int lo[kMels];
+    int rot[kMels];
     float2 tr[kMelWarps][2][16 * kTrStride];
-    float power[kMelWarps][2][128];  // bins [0,128); hb_init_tables checks lo + kMelTaps <= 128
+    float power[kMelWarps][2][kPowerRow];  // bins [0,128) (+16: the two frames of a pair start 16 banks apart); lo + kMelTaps <= 128
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -92,16 +95,17 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
     __shared__ MelSmem s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = lane >> 4, l = lane & 15;
-    for (int i = tid; i < 256; i += kMelThreads) s.win2[i] = g_mel_tables.win2[i];
+    for (int i = tid; i < kWinLength / 2; i += kMelThreads) s.win2[i] = g_mel_tables.win2[i + kWinPad / 2];
     for (int i = tid; i < 128; i += kMelThreads) s.w512[i] = g_mel_tables.w512[i];
     for (int i = tid; i < kMelTaps * kMels; i += kMelThreads) s.fbw[i] = g_mel_tables.fbw[i];
     if (tid < kMels) s.lo[tid] = g_mel_tables.lo[tid];
-    for (int i = tid; i < kMelWarps * 2 * 128; i += kMelThreads) (&s.power[0][0][0])[i] = 0.f;
+    if (tid < kMels) s.rot[tid] = g_mel_tables.rot[tid];
+    for (int i = tid; i < kMelWarps * 2 * kPowerRow; i += kMelThreads) (&s.power[0][0][0])[i] = 0.f;
     float2 tw[16];                                   // W256^(l k1)
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) tw[k1] = g_mel_tables.w256[(l * k1) & 255];
     __syncthreads();
-    const int my_lo = s.lo[lane];
+    const int my_lo = s.lo[lane], my_rot = s.rot[lane];
     float2* tr = s.tr[warp][h];
     float* pw = s.power[warp][h];
     const bool vec_ok = ((row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(audio) & 7) == 0);
@@ -134,7 +138,7 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
                 float2 xv;
                 if (vec_ok) xv = __ldg(reinterpret_cast<const float2*>(x) + n);
                 else xv = make_float2(__ldg(x + 2 * n), __ldg(x + 2 * n + 1));
-                const float2 w = s.win2[n];
+                const float2 w = s.win2[n - kWinPad / 2];
                 v[i] = make_float2(xv.x * scale * w.x, xv.y * scale * w.y);
             }
         }
@@ -174,7 +178,7 @@ mel_kernel(const float* __restrict__ audio, int64_t row_stride, float scale, flo
             const float* q = s.power[warp][hh] + my_lo;
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < kMelTaps; ++j) acc = fmaf(q[j], fw[j], acc);
+            for (int j = 0; j < kMelTaps; ++j) acc = fmaf(q[(j + my_rot) & (kMelTaps - 1)], fw[j], acc);   // rotated: no bank conflicts
             const int fo = f0 + hh;
             if (fo < F)   // NaN-propagating clamp, like np.maximum / torch.clamp
                 mel[((int64_t)clip * F + fo) * kMels + lane] = log10f(acc < 1e-10f ? 1e-10f : acc) + 2.0f;
@@ -219,7 +223,56 @@ extern "C" int hb_init_tables(const float* hann_host, const float* melfb_host) {
                    last - first + 1, kMelTaps);
         if (first + kMelTaps > 128) first = 128 - kMelTaps;   // keep the tap window inside the power row
         t.lo[m] = first;
+        t.rot[m] = 0;
         for (int j = 0; j < kMelTaps; ++j) t.fbw[j * kMels + m] = (first + j <= last) ? melfb_host[(first + j) * kMels + m] : 0.f;
+    }
+    // Lane m reads power[lo[m] + j] at step j of the projection: mel bins whose bands start a multiple of 32 bins apart collide
+    // in a shared-memory bank (32 excess wavefronts per frame with the 60..3800 Hz bank, a third of the kernel's shared-memory
+    // traffic).  The order of a lane's taps is free, so rotate it per lane -- step j reads tap (j + rot[m]) % 16 -- and search the
+    // rotations (deterministic local search) for the assignment with the fewest same-bank, different-address reads.
+    {
+        static_assert(kMelTaps == 16, "tap rotation assumes 16 taps");
+        auto cost = [&](const int* rot) {
+            int c = 0;
+            for (int j = 0; j < kMelTaps; ++j) {
+                int worst = 1;
+                for (int b = 0; b < 32; ++b) {
+                    int addrs[kMels], n = 0;
+                    for (int m = 0; m < kMels; ++m) {
+                        const int a = t.lo[m] + ((j + rot[m]) & (kMelTaps - 1));
+                        if ((a & 31) != b) continue;
+                        bool seen = false;
+                        for (int i = 0; i < n; ++i) seen |= (addrs[i] == a);
+                        if (!seen) addrs[n++] = a;
+                    }
+                    if (n > worst) worst = n;
+                }
+                c += worst - 1;
+            }
+            return c;
+        };
+        int best[kMels] = {0};
+        int best_cost = cost(best);
+        uint32_t lcg = 12345u;
+        for (int it = 0; it < 200000 && best_cost > 0; ++it) {
+            int trial[kMels];
+            for (int m = 0; m < kMels; ++m) trial[m] = best[m];
+            lcg = lcg * 1664525u + 1013904223u;
+            const int m = (int)((lcg >> 8) % kMels);
+            lcg = lcg * 1664525u + 1013904223u;
+            trial[m] = (int)((lcg >> 8) % kMelTaps);
+            const int c = cost(trial);
+            if (c <= best_cost) {
+                best_cost = c;
+                for (int i = 0; i < kMels; ++i) best[i] = trial[i];
+            }
+        }
+        float rotated[kMelTaps * kMels];
+        for (int m = 0; m < kMels; ++m) {
+            t.rot[m] = best[m];
+            for (int j = 0; j < kMelTaps; ++j) rotated[j * kMels + m] = t.fbw[((j + best[m]) & (kMelTaps - 1)) * kMels + m];
+        }
+        for (int i = 0; i < kMelTaps * kMels; ++i) t.fbw[i] = rotated[i];
     }
     HB_CUDA_OK(cudaMemcpyToSymbol(g_mel_tables, &t, sizeof(MelTables)));
     int dev = 0;
