@@ -42,6 +42,9 @@ namespace hb {
 
 namespace {
 
+#ifndef HB_TCG_PLANE_SKEW
+#define HB_TCG_PLANE_SKEW 0    // experiments: 32 = the old bank skew between planes
+#endif
 #ifndef HB_TCG_INTERLEAVE
 #define HB_TCG_INTERLEAVE 1   // narrow-plane configuration (block 4): interleave the epilogue warps' column blocks
 #endif
@@ -71,9 +74,9 @@ struct GCfg {
     static constexpr int G = G_, CC = CC_, F = F_, TT = TT_, NL = NL_, CIN0 = CIN0_, POOL_T = POOL_T_, OUT_CH = OUT_CH_;
     static constexpr int POOL_F = POOL_F_, PCOLS = PCOLS_;
     static constexpr int FG = F_ / G_;                         // column groups per row (a freq conv's row has FG + 1 columns: + the zero pad)
-    // bytes per plane: PCOLS columns; a plane pitch that is a multiple of 128 B gets a 32-byte skew so that chunk planes start in
-    // different banks
-    static constexpr int PLANE = PCOLS_ * 16 + ((PCOLS_ * 16) % 128 == 0 ? 32 : 0);
+    // bytes per plane: PCOLS columns.  With FG = 8 the pitch is a multiple of 128 B: consecutive rows of layout T then start in
+    // the same bank, which is what makes the freq layers' row-straddling stmatrix stores conflict-free (tcg_tables).
+    static constexpr int PLANE = PCOLS_ * 16 + HB_TCG_PLANE_SKEW;
     static constexpr int ACT_BYTES = kGPlanes * PLANE;
     static constexpr bool FIRST_FREQ = FIRST_FREQ_, MEL_IN = MEL_IN_;
     static constexpr int CONV0 = CONV0_;                       // conv index (layer table) of the first tensor-core layer
@@ -208,14 +211,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
     // MEL_IN: a tile's mel rows start their trip from global memory one tile ahead and wait in registers
     constexpr int kMelPerThread = (TT * kMels + kGThreads - 1) / kGThreads;
     float mel_reg[Cfg::MEL_IN ? kMelPerThread : 1];
+    auto mel_bin = [](int i) { return ((i & 7) << 2) | ((i >> 3) & 3); };
     auto prefetch_mel = [&](int tile_id) {
         if (!Cfg::MEL_IN || tile_id >= n_tiles) return;
         const int pc = tile_id / a.tiles_per_clip, pr0 = (tile_id - pc * a.tiles_per_clip) * Cfg::ROWS_OUT;
         const float* mel = reinterpret_cast<const float*>(a.in) + (int64_t)pc * a.in_T * kMels;
 #pragma unroll
         for (int k = 0; k < kMelPerThread; ++k) {
+            // element (row r, bin mel_bin(i)): a warp still reads one 128-byte row, but its 8-lane groups hold bins 4 j + const,
+            // i.e. ONE plane of layout F and 8 consecutive columns -- conflict-free 16-byte staging stores
             const int i = tid + k * kGThreads, r = i / kMels;
-            mel_reg[k] = (i < TT * kMels && pr0 + r < a.in_T) ? __ldg(mel + (int64_t)pr0 * kMels + i) : 0.f;
+            mel_reg[k] = (i < TT * kMels && pr0 + r < a.in_T) ? __ldg(mel + (int64_t)(pr0 + r) * kMels + mel_bin(i)) : 0.f;
         }
     };
     prefetch_mel(blockIdx.x);
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         for (int k = 0; k < kMelPerThread; ++k) {
             const int i = tid + k * kGThreads;
             if (i < TT * kMels) {
-                const int t = i / kMels, f = i - t * kMels;
+                const int t = i / kMels, f = mel_bin(i);
                 const __half hi = __float2half_rn(mel_reg[k]);
                 const __half lo = __float2half_rn(mel_reg[k] - __half2float(hi));
                 *reinterpret_cast<uint4*>(act + (f % G) * kGPlane + (1 + (FG + 1) * t + f / G) * 16) =
@@ -503,22 +509,49 @@ void tcg_tables(std::vector<uint16_t>& tab) {
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, FG = Cfg::FG, kGPlane = Cfg::PLANE;
     static_assert((TT / G) * F + FG * G <= 256 && (TT / G) * F % 16 == 0, "no free columns for the freq layers' padding outputs");
     tab.assign((size_t)NL * kGTabRow * 16, 0);
-    for (int l = 0; l < NL; ++l)
+    for (int l = 0; l < NL; ++l) {
+        int off_of[256];
+        bool valid_of[256];
         for (int n = 0; n < 256; ++n) {
-            int off;
+            int off = 0;
+            bool valid = true;
             if (Cfg::is_freq(l)) {
-                // column n = 9 t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * 8 +) fg
+                // column n = (FG + 1) t + fg -> layout T: plane (t mod G, .), column (t div G) * F + (i * FG +) fg
                 const int t = n / (FG + 1), fg = n - t * (FG + 1);
-                const bool valid = fg < FG && t < TT;
+                valid = fg < FG && t < TT;
                 off = valid ? (t % G) * CC * kGPlane + ((t / G) * F + fg) * 16 : (TT / G) * F * 16;
             } else {
                 const int tq = n / F, pf = n - tq * F;
-                if (tq >= TT / G) continue;                                                           // >= ncols(l): skipped
-                if (l < NL - 1) off = (pf / FG) * CC * kGPlane + (1 + (FG + 1) * G * tq + (pf % FG)) * 16;   // -> layout F
+                valid = tq < TT / G;                                                                  // >= ncols(l): skipped
+                if (!valid) off = 0;
+                else if (l < NL - 1) off = (pf / FG) * CC * kGPlane + (1 + (FG + 1) * G * tq + (pf % FG)) * 16;   // -> layout F
                 else off = (G * tq * F + pf) * 16;                                                    // -> layout P
             }
-            tab[(size_t)l * kGTabRow * 16 + (size_t)(n & 15) * kGTabRow + (n >> 4)] = (uint16_t)(off >> 4);
+            off_of[n] = off;
+            valid_of[n] = valid;
         }
+        // One stmatrix matrix = 8 consecutive columns = 8 row addresses.  A freq layer's matrix straddles a row boundary (FG + 1 = 9
+        // columns per row): with a plane pitch that is a multiple of 128 B the records of the two rows use different 16-byte bank
+        // groups, and the padding column(s) in between are dumped to the group(s) the matrix leaves free -- one wavefront per matrix.
+        if (Cfg::is_freq(l) && FG == 8 && kGPlane % 128 == 0)
+            for (int n0 = 0; n0 < 256; n0 += 8) {
+                bool used[8] = {false, false, false, false, false, false, false, false};
+                for (int n = n0; n < n0 + 8; ++n)
+                    if (valid_of[n]) used[(off_of[n] >> 4) & 7] = true;
+                int u = 0;
+                for (int n = n0; n < n0 + 8; ++n) {
+                    if (valid_of[n]) continue;
+                    while (u < 8 && used[u]) ++u;
+                    if (u < 8) {
+                        off_of[n] = (TT / G) * F * 16 + u * 16;
+                        used[u] = true;
+                    }
+                }
+            }
+        for (int n = 0; n < 256; ++n)
+            if (valid_of[n] || Cfg::is_freq(l))
+                tab[(size_t)l * kGTabRow * 16 + (size_t)(n & 15) * kGTabRow + (n >> 4)] = (uint16_t)(off_of[n] >> 4);
+    }
 }
 
 // Banded Toeplitz A operands of the block's layers: [layer][K chunk][row 128][8 cin]; row = 32 q + 8 o + channel holds row
