@@ -451,25 +451,33 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         for (int i = tid; i < Cfg::OUT_CH * rows_p * Fo; i += kGThreads) {
             const int ch = i / (rows_p * Fo);
             const int rem = i - ch * rows_p * Fo;
-            const int rp = rem / Fo, fo = rem - rp * Fo;
+            const int rp = rem / Fo;
+            int fo = rem - rp * Fo;
+            // G = 4: pi(2 fo) = 16 (fo % 2) + fo / 2, so consecutive fo pairs share a 16-byte bank group: an 8-lane group takes the
+            // even fo (groups 0..7), the next one the odd fo
+            if constexpr (G == 4 && Fo == 16) fo = ((fo & 7) << 1) | (fo >> 3);
             if (rowp0 + rp >= a.T_out) continue;
             uint4 o = make_uint4(0, 0, 0, 0);
             if (ch < CC) {
                 constexpr int dpi = (Cfg::pi(1) - Cfg::pi(0)) * 16;   // pi(2 fo + 1) - pi(2 fo), in bytes
                 const unsigned char* base = act + ch * Cfg::PLAIN + (PT * rp) * F * 16 + Cfg::pi(PF * fo) * 16;
+                // G = 1 with a freq pool: the four fo of a row sit in groups 0, 2, 4, 6 and the next pooled row starts in group 0
+                // again: odd rows read their two columns in the other order (max is commutative)
+                if constexpr (G == 1 && PF == 2) base += (rp & 1) * dpi;
+                const int dpi_l = (G == 1 && PF == 2 && (rp & 1)) ? -dpi : dpi;
                 const uint4 x0 = *reinterpret_cast<const uint4*>(base);
                 const __half2* h0 = reinterpret_cast<const __half2*>(&x0);
                 __half2 mx[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mx[j] = h0[j];
                 if (PF == 2) {
-                    const uint4 x1 = *reinterpret_cast<const uint4*>(base + dpi);
+                    const uint4 x1 = *reinterpret_cast<const uint4*>(base + dpi_l);
                     const __half2* h1 = reinterpret_cast<const __half2*>(&x1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(mx[j], h1[j]);
                 }
                 if (PT == 2) {
-                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + dpi);
+                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + dpi_l);
                     const __half2* h2 = reinterpret_cast<const __half2*>(&x2);
                     const __half2* h3 = reinterpret_cast<const __half2*>(&x3);
 #pragma unroll
