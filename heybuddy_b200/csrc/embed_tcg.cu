@@ -515,7 +515,7 @@ size_t tcg_smem_bytes() {
 template <class Cfg>
 void tcg_tables(std::vector<uint16_t>& tab) {
     constexpr int G = Cfg::G, CC = Cfg::CC, F = Cfg::F, TT = Cfg::TT, NL = Cfg::NL, FG = Cfg::FG, kGPlane = Cfg::PLANE;
-    static_assert((TT / G) * F + FG * G <= 256 && (TT / G) * F % 16 == 0, "no free columns for the freq layers' padding outputs");
+    static_assert((TT / G) * F + (FG > 8 ? FG : 8) * G <= Cfg::PCOLS && (TT / G) * F % 16 == 0, "no free columns for the freq layers' padding outputs");
     tab.assign((size_t)NL * kGTabRow * 16, 0);
     for (int l = 0; l < NL; ++l) {
         int off_of[256];
@@ -541,7 +541,7 @@ void tcg_tables(std::vector<uint16_t>& tab) {
         // One stmatrix matrix = 8 consecutive columns = 8 row addresses.  A freq layer's matrix straddles a row boundary (FG + 1 = 9
         // columns per row): with a plane pitch that is a multiple of 128 B the records of the two rows use different 16-byte bank
         // groups, and the padding column(s) in between are dumped to the group(s) the matrix leaves free -- one wavefront per matrix.
-        if (Cfg::is_freq(l) && FG == 8 && kGPlane % 128 == 0)
+        if (Cfg::is_freq(l) && (G == 1 || kGPlane % 128 == 0))
             for (int n0 = 0; n0 < 256; n0 += 8) {
                 bool used[8] = {false, false, false, false, false, false, false, false};
                 for (int n = n0; n < n0 + 8; ++n)
