@@ -351,6 +351,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         } else if (warp == 1) {
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
             mbar_wait(&hdr.tmem_full, ph & 1u);
+#ifndef HB_TCG_POLL_ALL
+            // this warp is the only one that polls the mbarrier: the eight epilogue warps wait at a hardware barrier it releases
+            named_bar_sync(1, 32 * (kGEpiWarps + 1));
+#endif
             if (lane == 0 && !last) {
                 mbar_expect_tx(&hdr.wbar, HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)));
                 bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)), &hdr.wbar);
@@ -404,7 +408,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
             };
             // the table entries do not depend on the MMAs: they are in registers before the accumulator is ready
             uint2 tb = n_frag > 0 ? frag_tab(0) : make_uint2(0, 0);
+#ifndef HB_TCG_POLL_ALL
+            named_bar_sync(1, 32 * (kGEpiWarps + 1));   // released by warp 1 once tmem_full has completed
+#else
             mbar_wait(&hdr.tmem_full, ph & 1u);
+#endif
             tc_fence_after();
             if (warp == 2) TCG_FINE(12);
             // the TMEM load and the table entries of fragment k + 1 are in flight while fragment k is converted and stored

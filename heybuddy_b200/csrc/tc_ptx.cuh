@@ -53,6 +53,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// named hardware barrier over `threads` threads (a multiple of 32) of the CTA: waiting costs no instructions and no shared-memory polls
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
