@@ -28,11 +28,6 @@
 //  * conv2d (Cin = 1) is CUDA-core work fused into block 1's prologue; the last 2x2 max-pool (both
 //    phases) is fused into the tail block's loader; block 5 runs on the same kernel, 6 clips per CTA.
 #include "tc_ptx.cuh"
-#ifdef HB_EXP_NO_WEIGHTS   // timing experiment only (wrong results): weight refills shrink to 16 bytes
-#define HB_EXP_WB(x) 16u
-#else
-#define HB_EXP_WB(x) (x)
-#endif
 
 #include <cstdlib>
 #include <vector>
@@ -341,8 +336,8 @@ __global__ void __launch_bounds__(kTcThreads, kMinBlocks) tc_block_kernel(const 
                 mbar_wait(&hdr.tmem_full[it % kSlots], (uint32_t)((it / kSlots) & 1));
                 if (lane == 0) {
                     const TcLayer& Ln = a.layers[l + 1];
-                    mbar_expect_tx(&hdr.wbar[0], HB_EXP_WB((uint32_t)Ln.w_bytes));
-                    bulk_g2s(wbuf0, a.w_packed + Ln.w_off, HB_EXP_WB((uint32_t)Ln.w_bytes), &hdr.wbar[0]);
+                    mbar_expect_tx(&hdr.wbar[0], (uint32_t)Ln.w_bytes);
+                    bulk_g2s(wbuf0, a.w_packed + Ln.w_off, (uint32_t)Ln.w_bytes, &hdr.wbar[0]);
                 }
             }
             __syncwarp();
@@ -847,12 +842,8 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     int rc;
     if ((rc = tcg_block1(m, mel, hA, B, F, nullptr, -1, st))) return rc;
     if ((rc = tcg_block2(m, hA, hB, B, g[1].T_in, nullptr, -1, st))) return rc;
-    static const bool b3_old = getenv("HB_B3_OLD") != nullptr;   // A/B switch while tuning
-    if (b3_old) { if ((rc = launch_block(m, 2, g[2], hB, hA, B, 6, 8, 0, nullptr, -1, st))) return rc; }
-    else if ((rc = tcg_block3(m, hB, hA, B, g[2].T_in, nullptr, -1, st))) return rc;
-    static const bool b4_old = getenv("HB_B4_OLD") != nullptr;   // A/B switch while tuning
-    if (b4_old) { if ((rc = launch_block(m, 3, g[3], hA, hB, B, 10, 4, 0, nullptr, -1, st))) return rc; }
-    else if ((rc = tcg_block4(m, hA, hB, B, g[3].T_in, nullptr, -1, st))) return rc;
+    if ((rc = tcg_block3(m, hB, hA, B, g[2].T_in, nullptr, -1, st))) return rc;
+    if ((rc = tcg_block4(m, hA, hB, B, g[3].T_in, nullptr, -1, st))) return rc;
     for (int p = 0; p < 2; ++p)
         if (need_phase[p] && (rc = launch_block(m, 4, gt, hB, tmp[p], B, 12, 4, p, nullptr, -1, st))) return rc;
     return fp32_gather_slots(tmp[0], tmp[1], gt.T_out, gt.T_out, slot_m_dev, n_slots, out, B, st);

@@ -30,11 +30,6 @@
 // NaN note: the zero Toeplitz entries multiply neighbouring positions of the same tile, so a non-finite activation reaches
 // up to G + 1 more positions of its own clip than in the reference arithmetic (0 * inf); finite data is unaffected.
 #include "tc_ptx.cuh"
-#ifdef HB_EXP_NO_WEIGHTS   // timing experiment only (wrong results): weight refills shrink to 16 bytes
-#define HB_EXP_WB(x) 16u
-#else
-#define HB_EXP_WB(x) (x)
-#endif
 
 #include <vector>
 
@@ -356,12 +351,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
             named_bar_sync(1, 32 * (kGEpiWarps + 1));
 #endif
             if (lane == 0 && !last) {
-                mbar_expect_tx(&hdr.wbar, HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)));
-                bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), HB_EXP_WB((uint32_t)Cfg::w_bytes(l + 1)), &hdr.wbar);
+                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(l + 1));
+                bulk_g2s(wbuf, a.w + Cfg::w_off(l + 1), (uint32_t)Cfg::w_bytes(l + 1), &hdr.wbar);
             } else if (lane == 0 && tile_id + (int)gridDim.x < n_tiles) {
                 // the next tile's first layer: its weights arrive under this tile's last epilogue, store and next staging
-                mbar_expect_tx(&hdr.wbar, HB_EXP_WB((uint32_t)Cfg::w_bytes(0)));
-                bulk_g2s(wbuf, a.w, HB_EXP_WB((uint32_t)Cfg::w_bytes(0)), &hdr.wbar);
+                mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
+                bulk_g2s(wbuf, a.w, (uint32_t)Cfg::w_bytes(0), &hdr.wbar);
             }
             if (!freq && !last) {
                 // the epilogue is writing layout F: zero its SAME padding (column 0 and group 8 of every row, all planes)
