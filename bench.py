@@ -358,6 +358,7 @@ def main():
     h2d, d2h = pipe.featurize_stream(items, sub)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_host_busy = max(0.0, 1.0 - pipe.last_stream_wait_s / max(e2e_s, 1e-9))   # share of the e2e time the host thread was NOT waiting on the GPU
     clocks = sampler.stop()
 
     times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
@@ -399,6 +400,7 @@ def main():
             "dtype": "f16 operands / f32 accumulate (embed), f32 (augment, mel)" if precision == "f16" else "f32",
             "data": "synthetic", "config": workload_config(precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                    "host_busy_frac": e2e_host_busy,
                     "api": f"FeaturizePipeline.featurize_stream over the K steps' host chunks (pinned int16 clips in, pinned f32 [n,16,96] out, "
                            f"{sub}-clip sub-chunks, H2D / compute / D2H on three streams)"},
             "gpu_launches": int(launches),

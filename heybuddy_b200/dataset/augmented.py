@@ -257,24 +257,34 @@ class AugmentedAudioGenerator:
                     colored_slot_of_batch: Sequence[int]) -> np.ndarray:
         """Per-clip ``hb_clip_aug`` records for consecutive batches (numpy structured array)."""
         t = self.target_num_samples
-        recs = []
-        for d, ncur, ridx, cslot in zip(draws, noise_cursors, rir_indices, colored_slot_of_batch):
-            b = len(d.pad_before)
-            r = np.zeros(b, dtype=_native.CLIP_AUG_DTYPE)
-            r["gain"] = d.gain_linear
-            r["colored_index"] = cslot if d.colored_apply else -1
-            r["colored_snr_db"] = d.colored_snr_db
-            r["rir_index"] = ridx if d.reverb_apply else -1
-            if d.background_apply and ncur >= 0:
-                base = self.noise_bank.offset_of_clip(ncur)
-                if base + b * t > self.noise_bank.stream.numel():
-                    raise ValueError("noise bank wrap margin too small for this batch size")
-                r["noise_offset"] = base + np.arange(b, dtype=np.int64) * t
-                r["noise_snr_db"] = d.noise_snr_db
-            else:
-                r["noise_offset"] = -1
-            recs.append(r)
-        return np.concatenate(recs) if recs else np.zeros(0, dtype=_native.CLIP_AUG_DTYPE)
+        n_b = len(draws)
+        if n_b == 0:
+            return np.zeros(0, dtype=_native.CLIP_AUG_DTYPE)
+        # one structured array for the whole table, filled field by field from per-batch vectors (this runs on the host once per
+        # chunk inside the streaming path: a per-batch loop of structured-field assignments was most of its host time)
+        sizes = np.fromiter((len(d.pad_before) for d in draws), dtype=np.int64, count=n_b)
+        starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+        n = int(sizes.sum())
+        rep = lambda values, dtype: np.repeat(np.asarray(values, dtype=dtype), sizes)
+        r = np.zeros(n, dtype=_native.CLIP_AUG_DTYPE)
+        r["gain"] = rep([d.gain_linear for d in draws], np.float32)
+        r["colored_index"] = rep([cs if d.colored_apply else -1 for d, cs in zip(draws, colored_slot_of_batch)], np.int32)
+        r["colored_snr_db"] = rep([d.colored_snr_db for d in draws], np.float32)
+        r["rir_index"] = rep([ri if d.reverb_apply else -1 for d, ri in zip(draws, rir_indices)], np.int32)
+        has_bg = np.fromiter((bool(d.background_apply and nc >= 0) for d, nc in zip(draws, noise_cursors)), dtype=bool, count=n_b)
+        noise_offset = np.full(n, -1, dtype=np.int64)
+        if has_bg.any():
+            base = np.array([self.noise_bank.offset_of_clip(nc) if hb else 0 for nc, hb in zip(noise_cursors, has_bg)], dtype=np.int64)
+            if np.any(has_bg & (base + sizes * t > self.noise_bank.stream.numel())):
+                raise ValueError("noise bank wrap margin too small for this batch size")
+            within = np.arange(n, dtype=np.int64) - np.repeat(starts, sizes)
+            noise_offset = np.where(np.repeat(has_bg, sizes), np.repeat(base, sizes) + within * t, -1)
+            snr = np.zeros(n, dtype=np.float32)
+            for g in np.nonzero(has_bg)[0]:
+                snr[starts[g]:starts[g] + sizes[g]] = draws[g].noise_snr_db
+            r["noise_snr_db"] = snr
+        r["noise_offset"] = noise_offset
+        return r
 
     def augment_device(self, fixed, table: DrawTable, out=None):
         """

@@ -14,6 +14,8 @@ while chunk i computes (double buffering).
 """
 from __future__ import annotations
 
+import time
+from collections import deque
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -228,7 +230,13 @@ class FeaturizePipeline:
         d2h_stream = self._bufs[("d2h_stream", 0)]     # results drain on their own stream, off the compute stream's critical path
         compute = torch.cuda.current_stream(dev)
         h2d = d2h = 0
-        stage_events = [None, None]
+        # The host stages up to DEPTH chunks ahead of the chunk whose kernels it is enqueueing (small draw-table arrays go through
+        # N_SLOTS pinned staging buffers; the samples come straight from the caller's pinned memory), so a host hiccup of a few
+        # milliseconds does not starve the GPU.  At most MAX_INFLIGHT chunks are uploaded-but-not-finished at any time (bounds the
+        # device memory of a long run: uploads are faster than the kernels and would otherwise run ahead without limit).
+        DEPTH, N_SLOTS, MAX_INFLIGHT = 3, 4, 5
+        stage_events = [None] * N_SLOTS
+        wait_s = 0.0    # host time spent blocked on the device (the rest of the call is host work)
 
         work = []   # (item index, chunk index, lo, hi)
         sinks = []  # per item: (numpy view, pinned torch tensor or None)
@@ -244,6 +252,14 @@ class FeaturizePipeline:
             assert len(tables) >= n_chunks, "one draw table per chunk"
             for ci in range(n_chunks):
                 work.append((ii, ci, ci * chunk_clips, min(n, (ci + 1) * chunk_clips)))
+        done_events = [None] * len(work)   # compute of chunk k finished
+
+        def blocked(ev):
+            nonlocal wait_s
+            if ev is not None and not ev.query():
+                t0 = time.perf_counter()
+                ev.synchronize()
+                wait_s += time.perf_counter() - t0
 
         def stage(k: int):
             nonlocal h2d
@@ -251,10 +267,10 @@ class FeaturizePipeline:
             clips, tables, _ = items[ii]
             part = clips.slice(lo, hi)
             pads, params, bases = self.pack_params(tables[ci])
-            slot = k % 2
-            prev = stage_events[slot]
-            if prev is not None:
-                prev.synchronize()   # the H2D that last read this slot's pinned staging buffers must have finished
+            slot = k % N_SLOTS
+            blocked(stage_events[slot])          # the H2D that last read this slot's pinned staging buffers must have finished
+            if k >= MAX_INFLIGHT:
+                blocked(done_events[k - MAX_INFLIGHT])
             host = {}
             for name, arr in (("samples", part.samples), ("offsets", part.offsets), ("pads", pads),
                               ("params", params.view(np.uint8).reshape(hi - lo, -1)), ("bases", bases)):
@@ -294,15 +310,23 @@ class FeaturizePipeline:
             nonlocal pending
             if pending is not None:
                 p_pin, p_sink, p_lo, p_hi, p_ev = pending
-                p_ev.synchronize()
+                blocked(p_ev)
                 p_sink[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
                 pending = None
 
-        nxt = stage(0) if work else None
+        staged = deque()
+        next_stage = 0
+
+        def fill():
+            nonlocal next_stage
+            while next_stage < len(work) and len(staged) < DEPTH:
+                staged.append(stage(next_stage))
+                next_stage += 1
+
+        fill()
         for k in range(len(work)):
-            chunk, ev = nxt
+            chunk, ev = staged.popleft()
             ii, ci, lo, hi = work[k]
-            nxt = stage(k + 1) if k + 1 < len(work) else None
             compute.wait_event(ev)
             for v in (chunk.samples, chunk.offsets, chunk.pad_before, chunk.params, chunk.bases):
                 if v is not None:
@@ -310,6 +334,9 @@ class FeaturizePipeline:
             emb = self.run_device(chunk)
             ready = torch.cuda.Event()
             ready.record(compute)
+            done_events[k] = ready
+            if k >= MAX_INFLIGHT + 1:
+                done_events[k - MAX_INFLIGHT - 1] = None
             d2h_stream.wait_event(ready)
             emb.record_stream(d2h_stream)
             sink, out_t = sinks[ii]
@@ -317,6 +344,8 @@ class FeaturizePipeline:
             if out_t is not None:
                 with torch.cuda.stream(d2h_stream):
                     out_t[lo:hi].copy_(emb, non_blocking=True)
+                del chunk, emb
+                fill()
                 continue
             key = (f"pin_out_{k % 2}", 0)
             pin = self._bufs.get(key)
@@ -329,6 +358,11 @@ class FeaturizePipeline:
                 done = torch.cuda.Event()
                 done.record(d2h_stream)
             pending = (pin, sink, lo, hi, done)
+            del chunk, emb
+            fill()
         drain()
+        t0 = time.perf_counter()
         d2h_stream.synchronize()
+        wait_s += time.perf_counter() - t0
+        self.last_stream_wait_s = wait_s   # host time spent blocked on the device during the call (diagnostic)
         return h2d, d2h
