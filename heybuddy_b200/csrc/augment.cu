@@ -360,14 +360,15 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
 //     inverse  transposed R9 -> R16 -> R16 (the FFT matrix is symmetric: running the transposed passes in
 //              reverse order on conjugated data is the inverse transform, natural order in and out)
 // 768 threads: 720 radix-16 butterflies per pass (94 % of the threads busy), 1280 radix-9, 1153 middle tasks.
-// Shared-memory index i lives at i + i / 32 (float2 units) so the stride-16 stores of the first pass (and the
-// stride-16 loads of the last) are conflict-free.
+// Shared-memory index i lives at i + i / 16 (float2 units): a 64-bit access is served one half-warp at a time, and with this
+// skew the 16 lanes of a half-warp hit 16 different bank pairs in the stride-16 stores of the first pass and the stride-16
+// loads of the last (i + i / 32 left them two-way conflicted: 1440 instead of 720 wavefronts per pass).
 constexpr int kFastT = 23040;
 constexpr int kFastM = kFastT / 2;
 constexpr int kFastThreads = 768;
-constexpr int kFastBuf = kFastM + kFastM / 32;     // skewed float2 slots per buffer
+constexpr int kFastBuf = kFastM + kFastM / 16;     // skewed float2 slots per buffer
 
-__device__ __forceinline__ int sk(int i) { return i + (i >> 5); }
+__device__ __forceinline__ int sk(int i) { return i + (i >> 4); }
 
 template <int R> __host__ __device__ constexpr int out_idx(int k) { return k; }                 // where dftr<R> leaves X[k]
 template <> __host__ __device__ constexpr int out_idx<16>(int k) { return 4 * (k & 3) + (k >> 2); }
