@@ -293,15 +293,33 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
                                  (uint32_t)(rows * F * 16));
         }
 #endif
-        for (int i = tid; i < Cfg::CIN0 * TT * F; i += kGThreads) {
-            const int c = i / (TT * F), rem = i - c * (TT * F);
-            const int t = rem / F, f = rem - t * F;
-            // rows past the clip are zero-filled (src-size 0): they only feed outputs that are dropped, but must be finite
-            const bool real = row0 + t < a.in_T;
-            cp_async16(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + (FG + 1) * t + f / G) * 16,
-                       real ? in + ((int64_t)c * a.in_T + row0 + t) * F + f : in, real ? 16u : 0u);
+        // Through registers, not cp.async: a 16-byte LDGSTS is one shared-memory wavefront per THREAD (1248 per tile in block 2,
+        // a quarter of the kernel's LSU wavefronts), a 16-byte STS is one per 8 lanes.  All loads of a thread are in flight before
+        // its first store; with G = 2 an 8-lane group takes the even (or odd) bins of a row = 8 consecutive columns of one plane.
+        constexpr int kRec = Cfg::CIN0 * TT * F, kPer = (kRec + kGThreads - 1) / kGThreads;
+        uint4 rec[kPer];
+        auto place = [&](int i, int& c, int& t, int& f) {
+            c = i / (TT * F);
+            const int rem = i - c * (TT * F);
+            t = rem / F;
+            const int fi = rem - t * F;
+            f = (G == 2 && F == 16) ? (((fi & 7) << 1) | (fi >> 3)) : fi;
+        };
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kGThreads;
+            int c, t, f;
+            place(i, c, t, f);
+            // rows past the clip are zero-filled: they only feed outputs that are dropped, but must be finite
+            rec[k] = (i < kRec && row0 + t < a.in_T) ? __ldg(in + ((int64_t)c * a.in_T + row0 + t) * F + f) : make_uint4(0, 0, 0, 0);
         }
-        cp_async_wait_all();
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = tid + k * kGThreads;
+            int c, t, f;
+            place(i, c, t, f);
+            if (i < kRec) *reinterpret_cast<uint4*>(act + ((f % G) * Cfg::CIN0 + c) * kGPlane + (1 + (FG + 1) * t + f / G) * 16) = rec[k];
+        }
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
