@@ -53,3 +53,60 @@ def test_colored_base_matches_oracle_restatement():
         np.testing.assert_allclose(colored_noise_base(g, f_decay), oaug.colored_noise_base(g, f_decay), atol=1e-6)
     # white noise: f_decay = 0 leaves the pattern unchanged up to the RMS normalisation
     np.testing.assert_allclose(colored_noise_base(g, 0.0), g / np.sqrt(np.mean(g * g)), atol=1e-5)
+
+
+def test_clip_params_vectorised_matches_per_batch_records():
+    """
+    AugmentedAudioGenerator.clip_params builds the per-clip hb_clip_aug records of a whole draw table in one vectorised
+    pass (it runs on the host once per chunk of the streaming path): byte-identical to the per-batch construction it
+    replaced, including a ragged last batch and batches without background noise / reverb / coloured noise.
+    """
+    import types
+
+    from heybuddy_b200 import _native
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+
+    cfg = AugmentConfig(batch_size=128, colored_noise_min_f_decay=0.0, colored_noise_max_f_decay=0.0)
+    rng = np.random.default_rng(7)
+    lengths = rng.integers(6400, 22400, size=128 * 9 + 37)
+    table = DrawTable.build(lengths, cfg, 2004, noise_clip_lengths=np.full(64, 160000), num_rirs=271,
+                            first_batch=3, noise_cursor=5, rir_cursor=2)
+    t = spec.CLIP_SAMPLES
+
+    class Bank:
+        class _Stream:
+            @staticmethod
+            def numel():
+                return 64 * 160000 + 128 * t
+
+        stream = _Stream()
+
+        @staticmethod
+        def offset_of_clip(c):
+            return int(c) * 160000
+
+    fake = types.SimpleNamespace(target_num_samples=t, noise_bank=Bank())
+    slots, k = [], 0
+    for d in table.batches:
+        slots.append(k if d.colored_apply else -1)
+        k += int(d.colored_apply)
+    got = AugmentedAudioGenerator.clip_params(fake, table.batches, table.noise_clip_cursor, table.rir_index, slots)
+
+    recs = []
+    for d, ncur, ridx, cslot in zip(table.batches, table.noise_clip_cursor, table.rir_index, slots):
+        b = len(d.pad_before)
+        r = np.zeros(b, dtype=_native.CLIP_AUG_DTYPE)
+        r["gain"] = d.gain_linear
+        r["colored_index"] = cslot if d.colored_apply else -1
+        r["colored_snr_db"] = d.colored_snr_db
+        r["rir_index"] = ridx if d.reverb_apply else -1
+        if d.background_apply and ncur >= 0:
+            r["noise_offset"] = Bank.offset_of_clip(ncur) + np.arange(b, dtype=np.int64) * t
+            r["noise_snr_db"] = d.noise_snr_db
+        else:
+            r["noise_offset"] = -1
+        recs.append(r)
+    want = np.concatenate(recs)
+    assert got.dtype == want.dtype and got.shape == want.shape == (len(lengths),)
+    assert got.tobytes() == want.tobytes()
+    assert any(d.background_apply for d in table.batches) and not all(d.background_apply for d in table.batches)
