@@ -2,7 +2,7 @@
 """
 bench.py -- clip-seconds featurized per second (augmentation + log-mel + speech embeddings).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload featurize|classifier|stream]
 
 Workload (BASELINE.json configs[1]): synthetic int16 source clips of ragged
 length U[6400, 22400] (band-limited noise under a raised-cosine envelope, peak 32767), noise bank
@@ -10,18 +10,21 @@ length U[6400, 22400] (band-limited noise under a raised-cosine envelope, peak 3
 batch 128 with probabilities coloured 0.25 (f_decay 0 = white, SNR U[10,30]) / gain 1.0 /
 background 0.75 (SNR U[-10,15]) / reverb 0.75, random-init embedding weights (seed 3001).
 One *step* = one pass of the hot path over one chunk of CHUNK clips per GPU (64 augmentation
-batches): length fix + augmentation (one kernel) -> mel -> embedding conv stack -> [CHUNK,16,96] f32, one
-hb_featurize_i16 call per step.
+batches): coloured patterns -> length fix + augmentation (one kernel) -> mel -> embedding conv stack -> [CHUNK,16,96] f32.
 K steps x CHUNK clips ~ the 100k clips of the config at the default K.
 
-  value   whole-job clip-seconds per second with the step's inputs already resident in HBM.
-  e2e     the same through the public host API (FeaturizePipeline.featurize_stream, the streaming form of
-          featurize_host): pinned host int16 clips -> H2D -> pipeline -> D2H of the embeddings, every step's copies
-          inside the timed region.
+  value   whole-job clip-seconds per second with the step's inputs (int16 clips + draw records) already resident in HBM.
+  e2e     the same through the reference-named public API with NOTHING pre-built (BASELINE configs[2] shape):
+          TrainingFeaturesGenerator.generate_sharded for a positive and an adversarial `.npy` -- K x CHUNK clips per GPU in
+          total -- from pinned host int16 clips (the TTS stage's output buffer): draw tables, per-chunk packing, H2D, kernels,
+          D2H and the `.npy` writes of every rank's row range all inside the timed region; the files are then re-opened
+          through PrecalculatedDatasetIterator and checked.
   roofline  the dominant stage (embedding conv stack): algorithmic FLOPs / CUDA-event time vs the measured
           tensor peak in MEASURED_PEAKS.json.
-  cpu_baseline  the oracle's restatement of the reference pipeline (reference control flow: 4 overlapping mel
-          windows and 16 embedding windows per clip, batch 32) timed on the host cores on a bounded sample.
+  cpu_baseline / --impl reference
+          the REFERENCE'S OWN Python (AugmentedAudioGenerator.__call__ + SpeechEmbeddings.__call__, unmodified, from the
+          baseline/_ref copy) on the host cores, with the oracle's numpy / torch-CPU kernels behind the seams whose
+          implementations cannot exist offline (ONNX sessions, torch_audiomentations, speechbrain) -- oracle/refarm.py.
 
 Each rank uses a pool of distinct chunks (> L2) and cycles through them, so no step re-reads inputs
 that are still in the 126 MB L2.
@@ -31,7 +34,9 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import sys
+import tempfile
 import threading
 import time
 
@@ -39,9 +44,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("HEYBUDDY_B200_ALLOW_RANDOM_INIT", "1")   # BASELINE.json: random-init weights of the reference's architecture
 
 CHUNK = int(os.environ.get("HB_BENCH_CHUNK", "8192"))       # clips per GPU per step
-E2E_SUB = int(os.environ.get("HB_BENCH_E2E_SUB", "4096"))   # e2e: sub-chunk pipelined H2D / compute / D2H inside a step
+E2E_SUB = int(os.environ.get("HB_BENCH_E2E_SUB", "4096"))   # e2e: clips per device pass of the streaming pipeline
 POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cycled through
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
@@ -57,15 +63,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="featurize", choices=["featurize", "classifier", "stream"])
     ap.add_argument("--precision", default=os.environ.get("HEYBUDDY_B200_EMBED_PRECISION", None))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
+WORKLOAD_TEXT = ("feature generator with augmentation (BASELINE configs[1]): ragged int16 clips U[6400,22400] -> 1.44 s, "
+                 "coloured(white) 0.25 / gain 1.0 / background 0.75 / reverb 0.75, random-init embedding weights")
+
+
 def workload_config(precision):
     return {
-        "workload": "feature generator with augmentation (BASELINE configs[1]): ragged int16 clips U[6400,22400] -> 1.44 s, "
-                    "coloured(white) 0.25 / gain 1.0 / background 0.75 / reverb 0.75, aug batch 128, random-init embedding weights",
+        "workload": WORKLOAD_TEXT,
         "clips_per_step_per_gpu": CHUNK, "aug_batch": AUG_BATCH, "noise_bank": [NOISE_CLIPS, NOISE_LEN], "rirs": N_RIRS,
         "embed_precision": precision, "l2_policy": f"{POOL} distinct input chunks cycled (> L2), noise bank 1.3 GB streamed",
     }
@@ -97,6 +107,26 @@ def make_sources(n, seed, device):
     return RaggedClips(samples, np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64))
 
 
+def host_sources(n, rng):
+    """The same kind of clip on the host (numpy), for the CPU arms."""
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(6400, 22400))
+        x = np.convolve(rng.standard_normal(ln), np.ones(8) / 8, mode="same") * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(ln) / ln))
+        out.append((x / np.abs(x).max() * 32767).astype(np.int16))
+    return out
+
+
+def host_rirs(n, rng):
+    rirs = []
+    for _ in range(n):
+        ln = int(rng.integers(3200, 24000))
+        r = np.exp(-np.arange(ln) / rng.uniform(300.0, 3000.0)) * rng.standard_normal(ln)
+        r[int(rng.integers(0, 200))] = 4.0
+        rirs.append(r.astype(np.float32))
+    return rirs
+
+
 def make_banks(device, seed_noise=2002, seed_rir=2003):
     import torch
 
@@ -112,14 +142,7 @@ def make_banks(device, seed_noise=2002, seed_rir=2003):
     noise.clip_lengths = np.full(NOISE_CLIPS, NOISE_LEN, dtype=np.int64)
     noise.clip_starts = np.arange(NOISE_CLIPS + 1, dtype=np.int64) * NOISE_LEN
     noise.num_samples = NOISE_CLIPS * NOISE_LEN
-    rng = np.random.Generator(np.random.PCG64(seed_rir))
-    rirs = []
-    for _ in range(N_RIRS):
-        ln = int(rng.integers(3200, 24000))
-        r = np.exp(-np.arange(ln) / rng.uniform(300.0, 3000.0)) * rng.standard_normal(ln)
-        r[int(rng.integers(0, 200))] = 4.0
-        rirs.append(r.astype(np.float32))
-    return noise, RirBank(rirs, device)
+    return noise, RirBank(host_rirs(N_RIRS, np.random.Generator(np.random.PCG64(seed_rir))), device)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -177,55 +200,64 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU reference arm / baseline (oracle restatement of the reference pipeline)
+# CPU reference arm / baseline: the reference's own Python on the host cores (oracle/refarm.py)
 # --------------------------------------------------------------------------------------------------
+REF_AUG_BATCH = 8          # reference default, constants.py:118 (the B200 arm uses the autoconfigured 128: features.py:171-218)
+REF_NOISE_CLIPS, REF_RIRS = 16, 8
+
+
 def cpu_reference_clips_per_s(n_clips, threads, seed=77, steps=1, warmup=0):
     """
-    The reference's control flow with the oracle's CPU kernels behind it (ORT / torch_audiomentations /
-    speechbrain are not installable offline): augment batch of 8 (constants.py:118) -> 4 x
-    17280-sample mel windows -> 16 x 76-frame embedding windows per clip, spectrogram/embedding batch 32.
-    Returns (clip_seconds_per_second, seconds_per_step).
+    ``n_clips`` clips per step through the reference's own ``AugmentedAudioGenerator(...)(n)`` -> ``SpeechEmbeddings()(clips)``
+    (unmodified, baseline/_ref copy; reference defaults: augmentation batch 8, 4 x 17280-sample mel windows and 16 x 76-frame
+    embedding windows per clip, spectrogram / embedding batch 32) with the oracle's CPU kernels behind the absent libraries.
+    Falls back to the oracle's own port of that control flow when the copy is missing.  Returns (clip-s/s, s/step, kind, what).
     """
     import torch
 
     from heybuddy_b200 import spec
-    from heybuddy_b200.dataset.draws import AugmentConfig, draw_batch
-    from oracle import augment as oaug, embed as oembed, mel as omel, pipeline as opipe
+    from oracle import refarm
 
     torch.set_num_threads(threads)
     rng = np.random.Generator(np.random.PCG64(seed))
     weights = spec.init_embedding_weights()
-    cfg = AugmentConfig(batch_size=8, colored_noise_min_f_decay=0.0, colored_noise_max_f_decay=0.0)
-    noise = (0.1 * rng.standard_normal((8 * spec.CLIP_SAMPLES * 2,))).astype(np.float32)
-    rirs = []
-    for _ in range(8):
-        ln = int(rng.integers(3200, 24000))
-        r = np.exp(-np.arange(ln) / rng.uniform(300.0, 3000.0)) * rng.standard_normal(ln)
-        r[int(rng.integers(0, 200))] = 4.0
-        rirs.append(r.astype(np.float32))
-    sources = []
-    for _ in range(n_clips):
-        ln = int(rng.integers(6400, 22400))
-        x = np.convolve(rng.standard_normal(ln), np.ones(8) / 8, mode="same") * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(ln) / ln))
-        sources.append((x / np.abs(x).max() * 32767).astype(np.int16))
+    noise = [(0.1 * rng.standard_normal(NOISE_LEN)).astype(np.float32) for _ in range(REF_NOISE_CLIPS)]
+    rirs = host_rirs(REF_RIRS, rng)
+    sources = host_sources(n_clips, rng)
 
-    def one_pass():
-        out = []
-        for g, lo in enumerate(range(0, n_clips, 8)):
-            batch = sources[lo:lo + 8]
-            d = draw_batch(2004, g, [c.shape[0] for c in batch], cfg)
-            fixed = np.stack([oaug.to_target_length(c, int(p)) for c, p in zip(batch, d.pad_before)])
-            b = fixed.shape[0]
-            aug = oaug.augment_batch(
-                fixed, colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
-                gain_db=d.gain_db if d.gain_apply else None,
-                noise=noise[:b * spec.CLIP_SAMPLES].reshape(b, -1) if d.background_apply else None, noise_snr_db=d.noise_snr_db,
-                rir=rirs[g % len(rirs)] if d.reverb_apply else None, dtype=np.float32)
-            out.append(aug)
-        audio = np.concatenate(out)
-        return opipe.speech_embeddings(
-            [a for a in audio], mel_fn=lambda a: omel.mel_spectrogram(a, dtype=np.float32),
-            embed_fn=lambda w: oembed.speech_embedding_model(w, weights), spectrogram_batch_size=32, embedding_batch_size=32)
+    if refarm.available():
+        kind = "reference"
+        what = ("reference python (AugmentedAudioGenerator.__call__ + SpeechEmbeddings.__call__, unmodified, baseline/_ref copy) with oracle "
+                "numpy/torch-CPU kernels behind the absent ONNX sessions / torch_audiomentations / speechbrain; real torchaudio add_noise")
+
+        def one_pass():
+            return refarm.featurize(sources, noise, rirs, augment_batch=REF_AUG_BATCH, f_decay=(0.0, 0.0), weights=weights)
+    else:
+        from heybuddy_b200.dataset.draws import AugmentConfig, DrawTable
+        from oracle import augment as oaug, embed as oembed, mel as omel, pipeline as opipe
+
+        kind = "port"
+        what = "oracle port of the reference control flow (baseline/_ref copy missing)"
+        cfg = AugmentConfig(batch_size=REF_AUG_BATCH, colored_noise_min_f_decay=0.0, colored_noise_max_f_decay=0.0)
+        stream = np.concatenate(noise)
+
+        def one_pass():
+            table = DrawTable.build([c.shape[0] for c in sources], cfg, 2004, np.full(REF_NOISE_CLIPS, NOISE_LEN), len(rirs))
+            out, i0 = [], 0
+            for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
+                b = len(d.pad_before)
+                fixed = np.stack([oaug.to_target_length(c, int(p)) for c, p in zip(sources[i0:i0 + b], d.pad_before)])
+                off = (ncur * NOISE_LEN) % (stream.size - b * spec.CLIP_SAMPLES) if d.background_apply else 0
+                out.append(oaug.augment_batch(
+                    fixed, colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
+                    gain_db=d.gain_db if d.gain_apply else None,
+                    noise=stream[off:off + b * spec.CLIP_SAMPLES].reshape(b, -1) if d.background_apply else None, noise_snr_db=d.noise_snr_db,
+                    rir=rirs[ridx] if d.reverb_apply else None, dtype=np.float32))
+                i0 += b
+            audio = np.concatenate(out)
+            return opipe.speech_embeddings(
+                [a for a in audio], mel_fn=lambda a: omel.mel_spectrogram(a, dtype=np.float32),
+                embed_fn=lambda w: oembed.speech_embedding_model(w, weights), spectrogram_batch_size=32, embedding_batch_size=32)
 
     for _ in range(warmup):
         one_pass()
@@ -234,7 +266,7 @@ def cpu_reference_clips_per_s(n_clips, threads, seed=77, steps=1, warmup=0):
         emb = one_pass()
     dt = (time.perf_counter() - t0) / steps
     assert emb.shape == (n_clips, 16, 96)
-    return n_clips * CLIP_SECONDS / dt, dt
+    return n_clips * CLIP_SECONDS / dt, dt, kind, what
 
 
 def run_reference_arm(args):
@@ -243,14 +275,18 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     sample = int(os.environ.get("HB_BENCH_REF_CLIPS", "256"))
-    value, dt = cpu_reference_clips_per_s(sample, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    value, dt, kind, what = cpu_reference_clips_per_s(sample, threads, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config("cpu-f32"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} clips per step: reference control flow (aug batch 8, 4 mel windows + 16 embedding windows per clip, "
-                                   "batch 32) with the oracle's numpy/torch-CPU kernels; ORT/torch_audiomentations/speechbrain unavailable offline"},
+        "dtype": "f32", "data": "synthetic",
+        # what THIS arm ran: the same workload, on a bounded sample, at the reference's own default batch sizes
+        "config": {"workload": WORKLOAD_TEXT, "clips_per_step": sample, "aug_batch": REF_AUG_BATCH,
+                   "noise_bank": [REF_NOISE_CLIPS, NOISE_LEN], "rirs": REF_RIRS, "embed_precision": "cpu-f32",
+                   "spectrogram_batch": 32, "embedding_batch": 32, "mel_windows_per_clip": 4, "embedding_windows_per_clip": 16,
+                   "differs_from_b200_arm": "bounded sample (clips per step, bank sizes) and the reference's default batch sizes; same clip "
+                                            "statistics, probabilities and embedding weights"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} clips per step: {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,8 +296,51 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+def pick_output_dir(need_bytes):
+    """A directory with room for the e2e leg's .npy files (rank 0 decides); None -> no usable directory."""
+    for cand in (os.environ.get("HB_BENCH_E2E_DIR"), tempfile.gettempdir(), "/dev/shm", os.path.join(ROOT, "gpurun_out")):
+        if not cand:
+            continue
+        try:
+            os.makedirs(cand, exist_ok=True)
+            if shutil.disk_usage(cand).free > need_bytes * 1.25 + (1 << 30):
+                return tempfile.mkdtemp(prefix="hb_bench_", dir=cand)
+        except Exception:
+            continue
+    return None
+
+
+def h2d_bandwidth(device, world, dist, mb=256, reps=6):
+    """Pinned host -> device copy rate of every rank with ALL ranks copying at once (GB/s per rank)."""
+    import torch
+
+    src = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(mb << 20, dtype=torch.uint8, device=device)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    gbs = torch.tensor([reps * (mb << 20) / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+    if world > 1:
+        out = [torch.zeros_like(gbs) for _ in range(world)]
+        dist.all_gather(out, gbs)
+        return [float(x) for x in out]
+    return [float(gbs)]
+
+
 def main():
     args = parse_args()
+    if args.workload != "featurize":
+        import bench_classifier
+
+        bench_classifier.main(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -271,8 +350,10 @@ def main():
 
     from heybuddy_b200 import _native, spec
     from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+    from heybuddy_b200.dataset.features import RaggedClipSource, TrainingFeaturesGenerator
+    from heybuddy_b200.dataset.precalculated import PrecalculatedDatasetIterator
     from heybuddy_b200.embeddings import DEFAULT_EMBED_PRECISION, SpeechEmbeddings
-    from heybuddy_b200.pipeline import FeaturizePipeline
+    from heybuddy_b200.pipeline import FeaturizePipeline, RaggedClips
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -294,22 +375,12 @@ def main():
         first_batch=rank * POOL * (CHUNK // AUG_BATCH))
     aug._noise_cursor = (rank * 211) % NOISE_CLIPS
     pipe = FeaturizePipeline(aug, speech, device_id=local_rank)
-    pool_clips = [make_sources(CHUNK, 2001 + 97 * rank + i, device).pin() for i in range(POOL)]
+    pool = make_sources(POOL * CHUNK, 2001 + 97 * rank, device).pin()   # the TTS stage's output buffer: pinned host int16
+    pool_clips = [pool.slice(i * CHUNK, (i + 1) * CHUNK) for i in range(POOL)]
     pool_tables = [aug.next_table(c.lengths) for c in pool_clips]
     pool_dev = [pipe.upload(c, t) for c, t in zip(pool_clips, pool_tables)]
-    # the same draws cut into sub-chunk tables for the pipelined host path (tables are per chunk of whole batches)
     sub = min(E2E_SUB, CHUNK)
-    assert sub % AUG_BATCH == 0 and CHUNK % sub == 0
-    bps = sub // AUG_BATCH
-    from heybuddy_b200.dataset.draws import DrawTable
-    pool_subtables = []
-    for t in pool_tables:
-        parts = []
-        for lo in range(0, len(t.batches), bps):
-            d = DrawTable(cfg=t.cfg, seed=t.seed)
-            d.batches, d.noise_clip_cursor, d.rir_index = t.batches[lo:lo + bps], t.noise_clip_cursor[lo:lo + bps], t.rir_index[lo:lo + bps]
-            parts.append(d)
-        pool_subtables.append(parts)
+    assert sub % AUG_BATCH == 0 and CHUNK % sub == 0 and CHUNK % (2 * AUG_BATCH) == 0
     out_dev = torch.empty((CHUNK, 16, spec.EMB_DIM), dtype=torch.float32, device=device)
     torch.cuda.synchronize()
 
@@ -328,7 +399,7 @@ def main():
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
-        pipe.run_device(pool_dev[(args.warmup + i) % POOL], out=out_dev)     # the product path: one hb_featurize_i16 call per step
+        pipe.run_device(pool_dev[(args.warmup + i) % POOL], out=out_dev)     # the product path: hb_colored_bases + hb_featurize_i16 per step
     stop.record()
     barrier()
     launches = lib.hb_launch_count() - launches0
@@ -344,22 +415,63 @@ def main():
     pipe.profile = False
     stage_ms = pipe.collect_stage_times()
     checksum = float(out_dev.float().abs().mean().item())
+    first_rows = pipe.run_device(pool_dev[0]).cpu().numpy()[:sub]     # rows [0, sub) of the positive file, recomputed device-resident
+    del pool_dev, out_dev
+    torch.cuda.empty_cache()
 
-    # ---- e2e: host buffers through the public API, copies inside the timed region -----------------------------
-    host_out = torch.empty((CHUNK, 16, spec.EMB_DIM), dtype=torch.float32).pin_memory()   # D2H lands here directly
-    # ONE streaming call over the K steps' host chunks: every step's inputs cross PCIe inside the timed region and its
-    # [CHUNK,16,96] result is read back; uploads of step i+1 overlap the compute of step i (pipeline fill / drain paid once)
-    items = [(pool_clips[(args.warmup + i) % POOL], pool_subtables[(args.warmup + i) % POOL], host_out) for i in range(args.steps)]
-    # warm-up = the same streaming call over max(W, 3) steps, untimed: on a freshly booted box the first process that moves this
-    # much pinned memory pays one-off host / IOMMU first-touch costs (the first e2e pass was up to 3x slower than the second)
-    pipe.featurize_stream([items[i % len(items)] for i in range(max(args.warmup, 3))], sub)
+    # ---- e2e: BASELINE configs[2] shape through TrainingFeaturesGenerator, nothing pre-built ----------------------
+    rows_per_rank = CHUNK * args.steps                      # clips this rank featurizes inside the timed region
+    per_file = (rows_per_rank // 2) * world                 # rows of each of the two files (positive, adversarial)
+    file_bytes = 2 * per_file * 16 * spec.EMB_DIM * 4
+    out_dir = [pick_output_dir(file_bytes * 2) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(out_dir, src=0)
+    out_dir = out_dir[0]
+    assert out_dir is not None, f"no directory with {file_bytes * 2 / 1e9:.1f} GB free for the e2e leg's .npy files (set HB_BENCH_E2E_DIR)"
+    source = RaggedClipSource(pool)                          # pinned; rows wrap around the pool like the reference's source iterator
+    kw = dict(device_id=local_rank, use_autoconfigure=False, augment_batch_size=AUG_BATCH, augment_background_dataset=noise_bank,
+              augment_impulse_dataset=rir_bank, augment_colored_noise_min_f_decay=0.0, augment_colored_noise_max_f_decay=0.0,
+              precision=precision, chunk_clips=sub, rank=rank, world_size=world, source=source, sample_batch_size=POOL * CHUNK)
+    gens = [("bench_phrase", TrainingFeaturesGenerator(seed=2004, **kw)),
+            ("bench_phrase_adv", TrainingFeaturesGenerator(seed=2005, tts_adversarial=True, **kw))]
+    dist_barrier = dist.barrier if world > 1 else None
+
+    def run_e2e(tag, rows):
+        h2d = d2h = 0
+        for name, gen in gens:
+            gen._cursor_cache.clear()                        # nothing pre-built: the cursor prefix is recomputed inside the call
+            gen.generate_sharded(rows, os.path.join(out_dir, f"{tag}{name}.npy"), barrier=dist_barrier)
+            h2d, d2h = h2d + gen.last_h2d_bytes, d2h + gen.last_d2h_bytes
+        return h2d, d2h
+
+    # warm-up = the same call on max(W, 3) steps' worth of rows, untimed: model load, pinned slots, and -- on a freshly booted
+    # box -- the one-off host / IOMMU first-touch costs of the first process that moves this much pinned memory
+    run_e2e("warm_", (CHUNK * max(args.warmup, 3) // 2) * world)
     barrier()
     t0 = time.perf_counter()
-    h2d, d2h = pipe.featurize_stream(items, sub)
+    h2d, d2h = run_e2e("", per_file)
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_host_busy = max(0.0, 1.0 - pipe.last_stream_wait_s / max(e2e_s, 1e-9))   # share of the e2e time the host thread was NOT waiting on the GPU
+    host_wait = sum(g._pipe[1].last_stream_wait_s for _, g in gens if g._pipe is not None)
     clocks = sampler.stop()
+    h2d_gbs = h2d_bandwidth(device, world, dist)
+
+    # the files, re-opened the way the trainer does (outside the timed region)
+    e2e_check = {}
+    if rank == 0:
+        for name, _ in gens:
+            it = PrecalculatedDatasetIterator(name, directory=out_dir, seed=0)
+            assert len(it) == per_file and it.take(256).shape == (256, 16, spec.EMB_DIM)
+            arr = it.precalculated
+            probe = np.asarray(arr[:: max(1, per_file // 4096)])
+            assert np.isfinite(probe).all() and float(np.abs(probe).mean()) > 0
+            e2e_check[name] = {"rows": len(it), "mean_abs": float(np.abs(probe).mean())}
+        pos = PrecalculatedDatasetIterator("bench_phrase", directory=out_dir, ordered=True).precalculated
+        e2e_check["first_rows_equal_device_resident_recompute"] = bool(np.array_equal(np.asarray(pos[:sub]), first_rows))
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        shutil.rmtree(out_dir, ignore_errors=True)
 
     times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
     if world > 1:
@@ -367,7 +479,7 @@ def main():
     elapsed_ms, e2e_ms = float(times[0]), float(times[1])
     total_clips = CHUNK * args.steps * world
     value = total_clips * CLIP_SECONDS / (elapsed_ms * 1e-3)
-    e2e_value = total_clips * CLIP_SECONDS / (e2e_ms * 1e-3)
+    e2e_value = 2 * per_file * CLIP_SECONDS / (e2e_ms * 1e-3)
 
     if rank == 0:
         peaks = {}
@@ -381,35 +493,49 @@ def main():
         # dominant stage = the embedding conv stack (tensor-core bound by design)
         flops_per_clip = 2.0 * spec.embedding_macs_per_clip(spec.mel_frames(spec.CLIP_SAMPLES))
         embed_ms = stage_ms.get("embed", 0.0)
-        embed_launches = max(1, args.steps)
         achieved_tflops = flops_per_clip * CHUNK * args.steps / (embed_ms * 1e-3) / 1e12 if embed_ms > 0 else None
         tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0 if not peaks else peaks.get("bf16_tflops", 1590.0)))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # augment = length fix + K1-K4 in one kernel: int16 source (28,800 B on average) + noise row + f32 result
-        stage_bytes = {"augment": 28800 + 92160 + 92160, "mel": 110208}
+        # augment = length fix + K1-K4 in one kernel: int16 source (28,800 B on average) + noise row (read by the 75 % of the
+        # batches that drew background noise) + f32 result
+        stage_bytes = {"augment": 28800 + 0.75 * 92160 + 92160, "mel": 110208}
+        stage_notes = {
+            "mel": "fp32 register FFT + BANDED fp32 projection (each mel bin sums its <= 16 FFT bins; the dense 257x32 GEMM the north star "
+                   "names is 88 % zeros and TF32 operands would break the 1e-4 budget) -- a deliberate deviation, DESIGN.md 4.3",
+            "colored": "hb_colored_bases: the chunk's coloured-noise patterns regenerated on the device from the draw table's Philox counters",
+        }
         stages = {}
         for name, ms in stage_ms.items():
             entry = {"ms_per_step": ms / args.steps, "share": ms / max(sum(stage_ms.values()), 1e-9)}
-            if name in ("augment", "mel") and ms > 0:
+            if name in stage_bytes and ms > 0:
                 gbs = stage_bytes[name] * CHUNK * args.steps / (ms * 1e-3) / 1e9
-                entry.update({"achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak})
+                entry.update({"achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak, "algorithmic_bytes_per_clip": stage_bytes[name]})
+            if name in stage_notes:
+                entry["note"] = stage_notes[name]
             stages[name] = entry
+        bytes_per_clip = h2d / max(2 * per_file // world, 1)
+        h2d_bound = sum(h2d_gbs) * 1e9 / bytes_per_clip * CLIP_SECONDS
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (embed), f32 (augment, mel)" if precision == "f16" else "f32",
             "data": "synthetic", "config": workload_config(precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "host_busy_frac": e2e_host_busy,
-                    "api": f"FeaturizePipeline.featurize_stream over the K steps' host chunks (pinned int16 clips in, pinned f32 [n,16,96] out, "
-                           f"{sub}-clip sub-chunks, H2D / compute / D2H on three streams)"},
+                    "ms_per_step": e2e_ms / args.steps, "host_busy_frac": max(0.0, 1.0 - host_wait / max(e2e_s, 1e-9)),
+                    "h2d_gbs_per_rank": h2d_gbs, "h2d_bound_gbs": sum(h2d_gbs), "h2d_bound_value": h2d_bound,
+                    "frac_of_h2d_bound": e2e_value / h2d_bound if h2d_bound > 0 else None,
+                    "workload": f"BASELINE configs[2] shape: {per_file} positive + {per_file} adversarial clips -> bench_phrase.npy + bench_phrase_adv.npy "
+                                f"f32 [{per_file},16,96] ({world} rank(s), each writing its own row range), re-opened through PrecalculatedDatasetIterator",
+                    "api": f"TrainingFeaturesGenerator.generate_sharded x 2, nothing pre-built: vectorised draw tables + packing + pinned int16 clips H2D + "
+                           f"kernels ({sub}-clip device passes) + D2H + pwrite of the .npy rows all inside the timed region",
+                    "output_dir_fs": out_dir.rsplit("/", 1)[0], "check": e2e_check},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
                 "kernel": "embedding conv stack (hb_embed_clips)", "bound": "tensor", "achieved": achieved_tflops,
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved_tflops / tensor_peak) if achieved_tflops else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's 7 launches, one ncu --set full capture of a steady
-                # 8192-clip step (profiles/r1b_ncu_summary.txt: 1.49 GB read + 1.18 GB written), scaled to this run's chunk size
+                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's launches, one ncu --set full capture of a steady
+                # 8192-clip step (profiles/: 1.49 GB read + 1.18 GB written), scaled to this run's chunk size
                 "traffic": 2.67e9 * CHUNK / 8192, "traffic_unit": "bytes per step (embed stage, ncu)", "peak_source": f"{peaks_src} (bf16 sustained; f16 runs at the bf16 rate)",
                 "algorithmic_flops_per_clip": flops_per_clip,
                 "note": "fully-convolutional evaluation: one 141-frame strip per clip instead of 16 windows (14 unique)",
@@ -419,12 +545,10 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            sample = int(os.environ.get("HB_BENCH_CPU_CLIPS", "1536"))   # ~10 s of host work
-            v, dt = cpu_reference_clips_per_s(sample, threads)
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{sample} clips, reference control flow (aug batch 8, 4 mel windows + 16 embedding windows per clip, batch 32) "
-                          f"with the oracle's numpy/torch-CPU kernels, {dt:.1f} s"}
+            sample = int(os.environ.get("HB_BENCH_CPU_CLIPS", "1536"))   # ~10-20 s of host work
+            v, dt, kind, what = cpu_reference_clips_per_s(sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{sample} clips, {dt:.1f} s: {what}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

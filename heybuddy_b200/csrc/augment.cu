@@ -209,6 +209,101 @@ rir_spectrum_kernel(const float* __restrict__ kernels, float2* __restrict__ spec
 }
 
 // ------------------------------------------------------------------------------------------------
+// coloured-noise patterns on the device: N(0,1)[16000] from the draw table's counters -> 1/f^decay shaping -> unit RMS
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, the same function as heybuddy_b200/dataset/draws.py:philox4x32 (counter = (index, stream, batch lo, batch hi),
+// key = seed lo / hi).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Box-Muller pair from two 32-bit words: u1 = ((a >> 9) + 0.5) / 2^23 in (0, 1), u2 = (b >> 8) / 2^24 in [0, 1), both exact in fp32
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)(a >> 9) + 0.5f) * (1.0f / 8388608.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif((float)(b >> 8) * (2.0f / 16777216.0f), &s, &c);
+    return make_float2(r * c, r * s);
+}
+
+// One CTA per coloured batch: torch_audiomentations `_gen_noise` -- rfft of the 1 s N(0,1) pattern,
+// mask 1 / linspace(1, sqrt(sr / 2), bins)^f_decay, irfft, unit RMS -- with the pattern drawn from stream 3 of the batch's
+// Philox counters.  f_decay == 0 (white noise) skips the transform pair: the mask is 1.
+__global__ void __launch_bounds__(kAugThreads, 1)
+colored_bases_kernel(uint2 key, const int64_t* __restrict__ batch_ids, const float* __restrict__ f_decay, float* __restrict__ out,
+                     FftPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float scratch[40];
+    __shared__ TwTables tw;
+    constexpr int N = kColoredBase;
+    const int M = plan.M;                         // N / 2
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+    float2* buf1 = buf0 + M;
+    const int tid = threadIdx.x;
+    const int64_t g = batch_ids[blockIdx.x];
+    const float fd = f_decay[blockIdx.x];
+    for (int i = tid; i < plan.tw_hi; i += kAugThreads) tw.hi[i] = __ldg(plan.tw_m + i * plan.tw_lo);
+    for (int i = tid; i < plan.tw_lo; i += kAugThreads) tw.lo[i] = __ldg(plan.tw_m + i);
+    float sumsq = 0.f;
+    for (int j = tid; j < N / 4; j += kAugThreads) {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)j, 3u, (uint32_t)g, (uint32_t)((uint64_t)g >> 32)), key);
+        const float2 a = box_muller(x.x, x.y), b = box_muller(x.z, x.w);
+        buf0[2 * j] = a;
+        buf0[2 * j + 1] = b;
+        sumsq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    }
+    __syncthreads();
+    float2* Y = buf0;
+    float scale = 1.0f;
+    if (fd != 0.0f) {
+        float2* Z = fft_forward(buf0, buf1, plan, tw);
+        float2* other = (Z == buf0) ? buf1 : buf0;
+        const float slope = (sqrtf((float)(N / 2)) - 1.0f) / (float)(N / 2);      // linspace(1, sqrt(sr / 2), N / 2 + 1)
+        auto mask = [&](int k) { return exp2f(-fd * log2f(1.0f + slope * (float)k)); };
+        for (int k = tid; k <= M / 2; k += kAugThreads) {
+            if (k == 0) {
+                const float x0 = Z[0].x + Z[0].y, xm = Z[0].x - Z[0].y;
+                const float y0 = x0 * mask(0), ym = xm * mask(M);
+                Z[0] = make_float2(0.5f * (y0 + ym), -0.5f * (y0 - ym));
+            } else {
+                const float2 w = __ldg(plan.tw_t + k);
+                float2 Xk, Xmk;
+                untangle(Z[k], Z[M - k], w, &Xk, &Xmk);
+                const float2 Yk = cscale(Xk, mask(k));
+                const float2 Ymk = cscale(Xmk, mask(M - k));
+                const float2 Ye = cscale(cadd(Yk, cconj(Ymk)), 0.5f);
+                const float2 Yo = cmulf(cscale(csub(Yk, cconj(Ymk)), 0.5f), cconj(w));
+                const float2 zk = cadd(Ye, mul_pos_i(Yo));
+                const float2 zmk = cadd(cconj(Ye), mul_pos_i(cconj(Yo)));
+                Z[k] = cconj(zk);
+                if (k != M - k) Z[M - k] = cconj(zmk);
+            }
+        }
+        __syncthreads();
+        Y = fft_forward(Z, other, plan, tw);      // conj(M * (y_even + i y_odd))
+        sumsq = 0.f;
+        const float inv_m = 1.0f / (float)M;
+        for (int i = tid; i < M; i += kAugThreads) {
+            const float2 v = Y[i];
+            const float2 y = make_float2(v.x * inv_m, -v.y * inv_m);
+            Y[i] = y;
+            sumsq += y.x * y.x + y.y * y.y;
+        }
+    }
+    scale = rsqrtf(block_sum(sumsq, scratch) / (float)N);
+    float2* dst = reinterpret_cast<float2*>(out + (int64_t)blockIdx.x * N);
+    for (int i = tid; i < M; i += kAugThreads) dst[i] = cscale(Y[i], scale);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused per-clip augmentation
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAugThreads, 1)
@@ -842,6 +937,7 @@ static int get_plan(int T, FftPlan* out) {
     plan.tw_t = d_t;
     HB_CUDA_OK(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(colored_bases_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kColoredBase / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     g_plans[{dev, T}] = plan;
@@ -861,6 +957,23 @@ extern "C" int hb_rir_spectrum(const float* kernels_dev, float* spec_dev, int n,
     if (rc) return rc;
     const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
     rir_spectrum_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(kernels_dev, reinterpret_cast<float2*>(spec_dev), T, plan);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+// Coloured-noise patterns of k batches (global batch ids + f_decay, device arrays) -> f32 [k][16000], unit RMS each.
+// Replaces the host-side pattern generation of torch_audiomentations AddColoredNoise (reference augmented.py:107-115).
+extern "C" int hb_colored_bases(uint64_t seed, const int64_t* batch_ids_dev, const float* f_decay_dev, int k, float* out_dev,
+                                void* stream) {
+    HB_REQUIRE(k >= 0 && (k == 0 || (batch_ids_dev && f_decay_dev && out_dev)), "hb_colored_bases: bad argument");
+    HB_REQUIRE((reinterpret_cast<uintptr_t>(out_dev) & 7) == 0, "hb_colored_bases: output must be 8-byte aligned");
+    if (k == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(kColoredBase, &plan);
+    if (rc) return rc;
+    const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
+    colored_bases_kernel<<<k, kAugThreads, smem, (cudaStream_t)stream>>>(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), batch_ids_dev,
+                                                                           f_decay_dev, out_dev, plan);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -20,7 +20,7 @@ import numpy as np
 
 from heybuddy_b200 import _native, spec
 from heybuddy_b200.constants import *  # noqa: F401,F403
-from heybuddy_b200.dataset.draws import AugmentConfig, BatchDraw, DrawTable, draw_batch
+from heybuddy_b200.dataset.draws import AugmentConfig, BatchDraw, DrawTable
 from heybuddy_b200.util import logger
 
 __all__ = ["AugmentedAudioGenerator", "NoiseBank", "RirBank", "rotate_rir"]
@@ -253,38 +253,31 @@ class AugmentedAudioGenerator:
                 host[i, pad_before[i]:pad_before[i] + c.shape[0]] = c
         return torch.from_numpy(host).to(dev)
 
-    def clip_params(self, draws: Sequence[BatchDraw], noise_cursors: Sequence[int], rir_indices: Sequence[int],
-                    colored_slot_of_batch: Sequence[int]) -> np.ndarray:
-        """Per-clip ``hb_clip_aug`` records for consecutive batches (numpy structured array)."""
-        t = self.target_num_samples
-        n_b = len(draws)
-        if n_b == 0:
-            return np.zeros(0, dtype=_native.CLIP_AUG_DTYPE)
-        # one structured array for the whole table, filled field by field from per-batch vectors (this runs on the host once per
-        # chunk inside the streaming path: a per-batch loop of structured-field assignments was most of its host time)
-        sizes = np.fromiter((len(d.pad_before) for d in draws), dtype=np.int64, count=n_b)
-        starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
-        n = int(sizes.sum())
-        rep = lambda values, dtype: np.repeat(np.asarray(values, dtype=dtype), sizes)
-        r = np.zeros(n, dtype=_native.CLIP_AUG_DTYPE)
-        r["gain"] = rep([d.gain_linear for d in draws], np.float32)
-        r["colored_index"] = rep([cs if d.colored_apply else -1 for d, cs in zip(draws, colored_slot_of_batch)], np.int32)
-        r["colored_snr_db"] = rep([d.colored_snr_db for d in draws], np.float32)
-        r["rir_index"] = rep([ri if d.reverb_apply else -1 for d, ri in zip(draws, rir_indices)], np.int32)
-        has_bg = np.fromiter((bool(d.background_apply and nc >= 0) for d, nc in zip(draws, noise_cursors)), dtype=bool, count=n_b)
-        noise_offset = np.full(n, -1, dtype=np.int64)
-        if has_bg.any():
-            base = np.array([self.noise_bank.offset_of_clip(nc) if hb else 0 for nc, hb in zip(noise_cursors, has_bg)], dtype=np.int64)
-            if np.any(has_bg & (base + sizes * t > self.noise_bank.stream.numel())):
-                raise ValueError("noise bank wrap margin too small for this batch size")
-            within = np.arange(n, dtype=np.int64) - np.repeat(starts, sizes)
-            noise_offset = np.where(np.repeat(has_bg, sizes), np.repeat(base, sizes) + within * t, -1)
-            snr = np.zeros(n, dtype=np.float32)
-            for g in np.nonzero(has_bg)[0]:
-                snr[starts[g]:starts[g] + sizes[g]] = draws[g].noise_snr_db
-            r["noise_snr_db"] = snr
-        r["noise_offset"] = noise_offset
-        return r
+    def clip_params(self, table: DrawTable) -> np.ndarray:
+        """Per-clip ``hb_clip_aug`` records of a whole draw table (numpy structured array), one vectorised pass."""
+        nb = self.noise_bank if bool(np.any(table.background_apply)) else None
+        return table.clip_records(_native.CLIP_AUG_DTYPE, nb.clip_starts if nb is not None else None,
+                                  int(nb.stream.numel()) if nb is not None else 0)
+
+    def colored_bases_device(self, table: DrawTable, device, out=None):
+        """
+        The coloured-noise patterns of the table's coloured batches, generated ON the device from the table's counters
+        (``hb_colored_bases``): cuda f32 ``[k, 16000]`` or None.  Only the k batch ids and f_decay values cross PCIe.
+        """
+        import torch
+
+        _, ids, f_decay = table.colored_slots()
+        k = int(ids.shape[0])
+        if k == 0:
+            return None
+        ids_d = torch.from_numpy(ids).to(device)
+        fd_d = torch.from_numpy(f_decay).to(device)
+        if out is None:
+            out = torch.empty((k, spec.COLORED_BASE_SAMPLES), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _native.check(_native.load().hb_colored_bases(table.seed & (2 ** 64 - 1), ids_d.data_ptr(), fd_d.data_ptr(), k,
+                                                          out.data_ptr(), _native.stream_ptr(device)), "hb_colored_bases")
+        return out[:k]
 
     def augment_device(self, fixed, table: DrawTable, out=None):
         """
@@ -296,15 +289,14 @@ class AugmentedAudioGenerator:
         dev = fixed.device
         t = self.target_num_samples
         n = fixed.shape[0]
-        bases = [d.colored_base for d in table.batches if d.colored_apply]
-        slots, k = [], 0
-        for d in table.batches:
-            slots.append(k if d.colored_apply else -1)
-            k += int(d.colored_apply)
-        params = self.clip_params(table.batches, table.noise_clip_cursor, table.rir_index, slots)
+        params = self.clip_params(table)
         assert params.shape[0] == n, (params.shape, n)
         params_d = torch.from_numpy(params.view(np.uint8).reshape(n, -1)).to(dev)
-        bases_d = torch.from_numpy(np.stack(bases)).to(dev) if bases else None
+        bases_d = self.colored_bases_device(table, dev)
+        if table.k9 is not None:
+            from heybuddy_b200.dataset import k9
+
+            fixed = k9.apply_device(fixed, table, self)
         if out is None:
             out = torch.empty_like(fixed)
         lib = _native.load()
@@ -327,7 +319,7 @@ class AugmentedAudioGenerator:
             noise_clip_lengths=nb.clip_lengths if nb is not None else None,
             num_rirs=len(rb) if rb is not None else 0,
             first_batch=self._batch_index, noise_cursor=self._noise_cursor, rir_cursor=self._rir_cursor)
-        self._batch_index += len(table.batches)
+        self._batch_index += table.n_batches
         self._noise_cursor = table.final_noise_cursor
         self._rir_cursor = table.final_rir_cursor
         return table
@@ -342,7 +334,7 @@ class AugmentedAudioGenerator:
             table = self.next_table([c.shape[0] for c in clips])
         finally:
             self.cfg.batch_size = saved
-        fixed = self.fix_length_device(clips, table.batches[0].pad_before)
+        fixed = self.fix_length_device(clips, table.pad_before)
         return self.augment_device(fixed, table)
 
     def __call__(self, num_samples: int, **kwargs: Any) -> Iterator[Dict[str, Any]]:

@@ -24,11 +24,10 @@ import numpy as np
 
 from heybuddy_b200 import spec
 from heybuddy_b200.constants import *  # noqa: F401,F403
-from heybuddy_b200.dataset.draws import AugmentConfig, DrawTable, draw_batch
 from heybuddy_b200.dataset.precalculated import LOCAL_DIR, PrecalculatedDatasetIterator, open_shared_memmap
 from heybuddy_b200.util import logger, safe_name
 
-__all__ = ["TrainingFeaturesGenerator", "SyntheticSpeechSource", "shard_batches"]
+__all__ = ["TrainingFeaturesGenerator", "SyntheticSpeechSource", "RaggedClipSource", "shard_batches"]
 
 SupplementalDatasetType = Optional[Any]
 
@@ -54,11 +53,51 @@ class SyntheticSpeechSource:
         return [self.clip(start + i) for i in range(n)]
 
 
+class RaggedClipSource:
+    """
+    A source that already holds its clips the way the TTS stage hands them over -- one concatenated int16 buffer (pinned host
+    memory when ``pin=True``) + offsets -- and serves row ranges as views, wrapping around like the reference's source iterator
+    (augmented.py:176-186 restarts the dataset when it is exhausted).  ``ragged(n, start)`` is the fast path
+    ``TrainingFeaturesGenerator`` looks for: no per-clip Python between the TTS buffer and the H2D copy.
+    """
+
+    def __init__(self, clips, pin: bool = False) -> None:
+        from heybuddy_b200.pipeline import RaggedClips
+
+        self.clips = clips if isinstance(clips, RaggedClips) else RaggedClips.from_list(list(clips))
+        if pin and self.clips.pinned is None:
+            self.clips = self.clips.pin()
+
+    def __len__(self) -> int:
+        return len(self.clips)
+
+    def ragged(self, n: int, start: int = 0):
+        """Yields ``(rows, RaggedClips view)`` pieces covering clips ``start .. start + n`` (mod len), each a contiguous view."""
+        total = len(self.clips)
+        at, left = start % total, n
+        while left > 0:
+            take = min(left, total - at)
+            yield take, self.clips.slice(at, at + take)
+            at, left = (at + take) % total, left - take
+
+    def __call__(self, n: int, start: int = 0) -> List[np.ndarray]:
+        out = []
+        for _, part in self.ragged(n, start):
+            out += [part.samples[part.offsets[i]:part.offsets[i + 1]] for i in range(len(part))]
+        return out
+
+
 def shard_batches(n_batches: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block of augmentation batches owned by ``rank``: [lo, hi)."""
     per, extra = divmod(n_batches, world_size)
     lo = rank * per + min(rank, extra)
     return lo, lo + per + (1 if rank < extra else 0)
+
+
+# Train / test / validation splits must not share utterances or draws (the reference gets this for free: every TTS call and every
+# np.random draw is fresh).  Each split reads the source at its own offset and seeds its draw table differently.
+SPLIT_SOURCE_OFFSET = {"train": 0, "test": 1 << 28, "validation": 1 << 29}
+SPLIT_SEED_SALT = {"train": 0, "test": 0x7E57, "validation": 0x7A11D}
 
 
 class TrainingFeaturesGenerator:
@@ -98,9 +137,10 @@ class TrainingFeaturesGenerator:
         source: Optional[Union[Callable[..., Iterable[np.ndarray]], Sequence[np.ndarray]]] = None,
         seed: int = 2004,
         precision: Optional[str] = None,
-        chunk_clips: int = 8192,
+        chunk_clips: int = 4096,
         rank: int = 0,
         world_size: int = 1,
+        embedding_weights: Optional[Any] = None,
         # stale spellings used by the reference's own tests (tests/test_feature_generator.py:17-24)
         device: Optional[Any] = None,
         tts_num_threads: Optional[int] = None,
@@ -135,13 +175,24 @@ class TrainingFeaturesGenerator:
             background_noise_max_snr_db=augment_background_noise_max_snr_db, gain_prob=augment_gain_prob, reverb_prob=augment_reverb_prob)
         self.embedding_spectrogram_batch_size = embedding_spectrogram_batch_size
         self.embedding_batch_size = embedding_batch_size
-        self.source = source if source is not None else SyntheticSpeechSource(seed=2001 if not tts_adversarial else 2011)
+        if source is None:
+            # The TTS stage (Piper voices, hub downloads) is the path's input boundary and is not available offline: without an
+            # explicit source the generator featurizes SYNTHETIC band-limited noise, not speech of `tts_text`.  Say so, loudly.
+            logger.warning(
+                f"TrainingFeaturesGenerator(tts_text={tts_text!r}): no `source` of TTS clips was given -- featurizing SYNTHETIC "
+                "noise bursts (SyntheticSpeechSource), NOT speech; the wake phrase only names the output file. Pass source=<callable "
+                "or sequence of int16 16 kHz clips> for real training data.")
+            source = SyntheticSpeechSource(seed=2001 if not tts_adversarial else 2011)
+        self.source = source
         self.seed = seed
         self.precision = precision
         self.chunk_clips = chunk_clips
         self.rank, self.world_size = rank, world_size
+        self.embedding_weights = embedding_weights
         self._pipe = None
         self._generated = 0
+        self._cursor_cache = {}   # (split seed) -> (batch index, noise cursor, rir cursor) of the furthest prefix computed so far
+        self.last_h2d_bytes = self.last_d2h_bytes = 0
 
     @property
     def device(self):
@@ -172,18 +223,25 @@ class TrainingFeaturesGenerator:
         if self._pipe is None or self._pipe[0] != key:
             probs = dict(self.augment_probs)
             if not augment:
-                for k in ("colored_noise_prob", "background_noise_prob", "gain_prob", "reverb_prob"):
+                for k in ("colored_noise_prob", "background_noise_prob", "gain_prob", "reverb_prob", "seven_band_aug_prob",
+                          "tanh_distortion_prob", "pitch_shift_prob", "band_stop_prob"):
                     probs[k] = 0.0
             gen = AugmentedAudioGenerator(
                 [], device_id=self.device_id, augmentation_dataset=self.augment_background_dataset if augment else None,
                 impulse_response_dataset=self.augment_impulse_dataset if augment else None,
                 target_length=self.augment_target_length, sample_rate=self.sample_rate, batch_size=self.augment_batch_size,
                 seed=self.seed, **probs)
-            speech = SpeechEmbeddings(device_id=self.device_id, precision=self.precision)
+            speech = SpeechEmbeddings(device_id=self.device_id, precision=self.precision, weights=self.embedding_weights)
             self._pipe = (key, FeaturizePipeline(gen, speech, device_id=self.device_id), gen)
         return self._pipe[1], self._pipe[2]
 
-    def _source_clips(self, n: int, start: int) -> List[np.ndarray]:
+    def _source_ragged(self, n: int, start: int):
+        """Source clips ``start .. start + n`` as ``(count, RaggedClips)`` pieces (views of the source's buffer when it has one)."""
+        from heybuddy_b200.pipeline import RaggedClips
+
+        if hasattr(self.source, "ragged"):
+            yield from self.source.ragged(n, start)
+            return
         if callable(self.source):
             try:
                 clips = list(self.source(n, start=start))
@@ -198,96 +256,146 @@ class TrainingFeaturesGenerator:
             if c.dtype != np.int16:  # float clips in [-1, 1] -> the int16 the TTS stage would have produced
                 c = np.clip(np.round(c * 32767.0), -32768, 32767).astype(np.int16)
             out.append(c)
+        yield n, RaggedClips.from_list(out)
+
+    def _source_clips(self, n: int, start: int) -> List[np.ndarray]:
+        out = []
+        for _, part in self._source_ragged(n, start):
+            out += [part.samples[part.offsets[i]:part.offsets[i + 1]] for i in range(len(part))]
         return out
+
+    @staticmethod
+    def _split(testing: bool, validation: bool) -> str:
+        return "validation" if validation else ("test" if testing else "train")
+
+    def _cursors_at(self, gen, batch_index: int, seed: int) -> Tuple[int, int]:
+        """
+        Noise-stream / RIR cursors before augmentation batch ``batch_index``: a prefix over the batch coins (one vectorised
+        Philox call for the whole range) resumed from the furthest prefix computed so far -- linear over a long run.
+        """
+        from heybuddy_b200.dataset.draws import advance_noise_cursor, batch_coins
+
+        nb, rb = gen.noise_bank, gen.rir_bank
+        if batch_index == 0 or (nb is None and rb is None):
+            return 0, 0
+        g0, noise_cursor, rir_cursor = self._cursor_cache.get(seed, (0, 0, 0))
+        if g0 > batch_index:
+            g0, noise_cursor, rir_cursor = 0, 0, 0
+        cfg = gen.cfg
+        bg, rev = batch_coins(seed, np.arange(g0, batch_index, dtype=np.uint64), cfg, nb is not None, rb is not None)
+        rir_cursor += int(rev.sum())
+        n_bg = int(bg.sum())
+        if n_bg:
+            need = cfg.batch_size * cfg.target_samples      # every batch before the last of a dataset is full
+            lengths = nb.clip_lengths
+            if (lengths == lengths[0]).all():
+                noise_cursor = (noise_cursor + n_bg * (-(-need // int(lengths[0])))) % len(nb)
+            else:
+                for _ in range(n_bg):
+                    noise_cursor = advance_noise_cursor(noise_cursor, need, nb.clip_starts)
+        self._cursor_cache[seed] = (batch_index, noise_cursor, rir_cursor)
+        return noise_cursor, rir_cursor
+
+    def _items(self, first_sample: int, num_samples: int, sink_of: Callable[[int, int], Any], validation: bool, testing: bool):
+        """
+        Lazily yields ``(clips, table, sink)`` items for :meth:`FeaturizePipeline.featurize_stream`: one per contiguous piece of a
+        super-batch of at most ``sample_batch_size`` source clips (features.py:492-535), each with the vectorised draw table of
+        its augmentation batches.  ``sink_of(row_lo, row_hi)`` returns the sink for output rows [row_lo, row_hi) of this call.
+        """
+        from heybuddy_b200.dataset.draws import DrawTable
+
+        split = self._split(testing, validation)
+        pipe, gen = self._pipeline(augment=not validation)
+        b, t = self.augment_batch_size, gen.target_num_samples
+        seed = self.seed + SPLIT_SEED_SALT[split]
+        nb, rb = gen.noise_bank, gen.rir_bank
+        size = max(b, (self.sample_batch_size // b) * b)
+        assert first_sample % b == 0, "a dataset range must start on an augmentation-batch boundary"
+        noise_cursor, rir_cursor = self._cursors_at(gen, first_sample // b, seed) if not validation else (0, 0)
+        done = 0
+        while done < num_samples:
+            want = min(size, num_samples - done)
+            pending = None      # a piece that does not end on a batch boundary is merged with the next one
+            for _, part in self._source_ragged(want, SPLIT_SOURCE_OFFSET[split] + first_sample + done):
+                if pending is not None:
+                    from heybuddy_b200.pipeline import RaggedClips
+
+                    part = RaggedClips(np.concatenate([pending.samples, part.samples]),
+                                       np.concatenate([pending.offsets, pending.offsets[-1] + part.offsets[1:]]))
+                    pending = None
+                n = len(part)
+                whole = n if done + n >= num_samples else (n // b) * b
+                if whole < n:
+                    pending = part.slice(whole, n)
+                    part = part.slice(0, whole)
+                if whole == 0:
+                    continue
+                row = first_sample + done
+                table = DrawTable.build(part.lengths, gen.cfg, seed, nb.clip_lengths if nb is not None else None,
+                                        len(rb) if rb is not None else 0, first_batch=row // b, noise_cursor=noise_cursor,
+                                        rir_cursor=rir_cursor)
+                noise_cursor, rir_cursor = table.final_noise_cursor, table.final_rir_cursor
+                if validation:
+                    # validation path: centre pad only (features.py:413-427), truncating long clips to T explicitly
+                    table.pad_before = np.maximum((t - part.lengths) // 2, 0).astype(np.int32)
+                yield part, table, sink_of(done, done + whole)
+                done += whole
+            assert pending is None, "the source returned fewer clips than asked for"
+        if not validation:
+            self._cursor_cache[seed] = ((first_sample + num_samples + b - 1) // b, noise_cursor, rir_cursor)
+
+    def _run(self, first_sample: int, num_samples: int, sink_of, validation: bool, testing: bool) -> None:
+        pipe, gen = self._pipeline(augment=not validation)
+        b = self.augment_batch_size
+        chunk = max(b, (self.chunk_clips // b) * b)
+        self.last_h2d_bytes, self.last_d2h_bytes = pipe.featurize_stream(
+            self._items(first_sample, num_samples, sink_of, validation, testing), chunk)
 
     def generate(self, num_samples: int, sample_save_path: Optional[str] = None, augmented_sample_save_path: Optional[str] = None,
                  testing: bool = False, validation: bool = False, first_sample: Optional[int] = None) -> np.ndarray:
-        """Generates ``num_samples`` clips and computes their embeddings -> ``f32 [num_samples, 16, 96]`` (features.py:360-490)."""
-        from heybuddy_b200.pipeline import RaggedClips
-
+        """
+        Generates ``num_samples`` clips and computes their embeddings -> ``f32 [num_samples, 16, 96]`` (features.py:360-490).
+        Rows are samples ``first_sample ..`` of this generator's stream (default: where the previous call stopped, rounded up to
+        an augmentation-batch boundary), so successive calls -- and a cache extension -- never repeat a sample.
+        """
         if self.use_autoconfigure:
             self.autoconfigure()
-        start = self._generated if first_sample is None else first_sample
-        pipe, gen = self._pipeline(augment=not validation)
-        t = gen.target_num_samples
         b = self.augment_batch_size
-        assert start % b == 0 or validation, "super-batches must start on an augmentation-batch boundary"
-        clips = self._source_clips(num_samples, start)
-        ragged = RaggedClips.from_list(clips)
-        chunk = max(b, (self.chunk_clips // b) * b)
-        tables = []
-        gen._batch_index = start // b
-        if not validation:
-            # cursors at this super-batch's first augmentation batch, independent of how batches were sharded
-            gen._noise_cursor, gen._rir_cursor = self._cursors_at(gen, start // b)
-        for lo in range(0, num_samples, chunk):
-            lengths = ragged.lengths[lo:lo + chunk]
-            table = gen.next_table(lengths)
-            if validation:
-                # validation path: centre pad only (features.py:413-427), truncating long clips to T explicitly
-                for d, l0 in zip(table.batches, range(0, len(lengths), b)):
-                    ln = lengths[l0:l0 + b]
-                    d.pad_before = np.maximum((t - ln) // 2, 0).astype(np.int32)
-            tables.append(table)
-        out, _, _ = pipe.featurize_host(ragged, tables, chunk)
+        start = self._generated if first_sample is None else first_sample
+        start = -(-start // b) * b
+        out = np.empty((num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM), dtype=np.float32)
+        self._run(start, num_samples, lambda lo, hi: out[lo:hi], validation, testing)
         self._generated = start + num_samples
         return out
 
-    def _cursors_at(self, gen, batch_index: int) -> Tuple[int, int]:
-        """Noise-stream / RIR cursors before augmentation batch ``batch_index`` (prefix over the light draws)."""
-        nb, rb = gen.noise_bank, gen.rir_bank
-        noise_cursor = rir_cursor = 0
-        if batch_index == 0 or (nb is None and rb is None):
-            return 0, 0
-        cfg = gen.cfg
-        need = cfg.batch_size * cfg.target_samples
-        for g in range(batch_index):
-            d = draw_batch(self.seed, g, [cfg.target_samples] * cfg.batch_size, cfg, nb is not None, rb is not None, light=True)
-            if d.background_apply:
-                got = 0
-                while got < need:
-                    got += int(nb.clip_lengths[noise_cursor % len(nb)])
-                    noise_cursor += 1
-                noise_cursor %= len(nb)
-            if d.reverb_apply:
-                rir_cursor += 1
-        return noise_cursor, rir_cursor
-
     def __call__(self, num_samples: int, sample_save_path: Optional[str] = None, augmented_sample_save_path: Optional[str] = None,
                  testing: bool = False, validation: bool = False) -> np.ndarray:
-        """Super-batches of at most ``sample_batch_size`` samples (features.py:492-535), in process."""
-        size = max(self.augment_batch_size, (self.sample_batch_size // max(self.augment_batch_size, 1)) * self.augment_batch_size)
-        if self.use_autoconfigure:
-            self.autoconfigure()
-            size = max(self.augment_batch_size, (self.sample_batch_size // self.augment_batch_size) * self.augment_batch_size)
-        parts, done = [], 0
-        while done < num_samples:
-            n = min(size, num_samples - done)
-            parts.append(self.generate(n, sample_save_path, augmented_sample_save_path, testing, validation, first_sample=done))
-            done += n
-        return parts[0] if len(parts) == 1 else np.concatenate(parts)
+        """
+        ``num_samples`` NEW samples (features.py:492-535).  The reference forks one child per super-batch of ``sample_batch_size``
+        so that PyTorch's host memory dies with it; here the super-batches stream through one pipeline with fixed buffers.
+        """
+        return self.generate(num_samples, sample_save_path, augmented_sample_save_path, testing, validation)
 
     def generate_sharded(self, num_samples: int, path: str, barrier: Optional[Callable[[], None]] = None,
-                         validation: bool = False) -> Tuple[int, int]:
+                         validation: bool = False, testing: bool = False, writer_threads: int = 4) -> Tuple[int, int]:
         """
         Multi-GPU form: this rank featurizes its contiguous block of augmentation batches and writes rows
-        [lo*B, hi*B) of the shared ``.npy`` at ``path`` (rank 0 creates it).  Returns the row range written.
+        [lo*B, hi*B) of the shared ``.npy`` at ``path`` (rank 0 creates it).  Rows go from the pipeline's pinned D2H slots
+        straight into the file (``pwrite`` from worker threads), overlapping the kernels of the following chunks.
+        Returns the row range written.
         """
+        from heybuddy_b200.dataset.precalculated import NpyRowWriter
+
         if self.use_autoconfigure:
             self.autoconfigure()
         b = self.augment_batch_size
         n_batches = math.ceil(num_samples / b)
         lo_b, hi_b = shard_batches(n_batches, self.rank, self.world_size)
         lo, hi = lo_b * b, min(hi_b * b, num_samples)
-        mm = open_shared_memmap(path, (num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM),
-                                self.rank, barrier)
-        size = max(b, (self.sample_batch_size // b) * b)
-        row = lo
-        while row < hi:
-            n = min(size, hi - row)
-            mm[row:row + n] = self.generate(n, validation=validation, first_sample=row)
-            row += n
-        mm.flush()
+        shape = (num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM)
+        with NpyRowWriter(path, shape, create=self.rank == 0, barrier=barrier) as writer:
+            if hi > lo:
+                self._run(lo, hi - lo, lambda r0, r1: (lambda a, z, rows, base=lo + r0: writer.write(base + a, rows)), validation, testing)
         if barrier is not None:
             barrier()
         return lo, hi
@@ -327,7 +435,7 @@ class TrainingFeaturesGenerator:
         if have > 0:
             from heybuddy_b200.util.npy_append import AppendableNumpyArrayFile, AppendableNumpyHeaderInfo
 
-            gen._generated = have
+            gen._generated = have      # rows [0, have) exist: the new ones continue the generator's stream (never a repeat)
             new_rows = gen(want - have, **call_kwargs)
             path = os.path.join(directory, f"{name}.npy")
             del existing                       # drop the read-only memmap before the file changes under it
@@ -335,8 +443,16 @@ class TrainingFeaturesGenerator:
             with AppendableNumpyArrayFile(path) as out:
                 out.append(new_rows)
             return PrecalculatedDatasetIterator(name, directory=directory)
-        feats = gen(want, **call_kwargs)
-        return PrecalculatedDatasetIterator.from_array(feats, name=name, directory=directory, keep_in_memory=keep_in_memory)
+        # nothing cached: every rank streams its rows straight into `<name>.npy` (same bytes as the reference's np.save of the
+        # whole array, precalculated.py:486, without ever holding the whole array)
+        barrier = None
+        if gen.world_size > 1:
+            import torch.distributed as dist
+
+            assert dist.is_initialized(), "world_size > 1 needs an initialised torch.distributed process group (file barrier)"
+            barrier = dist.barrier
+        gen.generate_sharded(want, os.path.join(directory, f"{name}.npy"), barrier=barrier, **call_kwargs)
+        return PrecalculatedDatasetIterator(name, directory=directory, use_mem_map=not keep_in_memory)
 
     @classmethod
     def get_training_features(cls, wake_phrase: str, num_positive_samples: int, num_adversarial_samples: int, testing: bool = False,

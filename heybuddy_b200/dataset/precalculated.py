@@ -17,7 +17,7 @@ from typing import Any, Dict, Iterator, Optional
 
 import numpy as np
 
-__all__ = ["PrecalculatedDatasetIterator", "LOCAL_DIR", "open_shared_memmap"]
+__all__ = ["PrecalculatedDatasetIterator", "LOCAL_DIR", "open_shared_memmap", "NpyRowWriter"]
 
 LOCAL_DIR = os.environ.get(
     "HEYBUDDY_B200_PRECALCULATED_DIR",
@@ -40,6 +40,57 @@ def open_shared_memmap(path: str, shape, rank: int = 0, barrier=None, dtype=np.f
         mm = np.lib.format.open_memmap(path, mode="r+")
         assert tuple(mm.shape) == tuple(shape), (mm.shape, shape)
     return mm
+
+
+class NpyRowWriter:
+    """
+    Row-range writer of one pre-sized ``.npy`` shared by all ranks: the creating rank writes the exact header ``np.save`` would
+    write (v1.0, C order -- the file is byte-identical to ``np.save(array)``, precalculated.py:486) and sizes the file; every
+    rank then ``pwrite``s its own rows at their byte offset.  ``pwrite`` copies straight from the caller's buffer (the
+    pipeline's pinned D2H slots) into the page cache with the GIL released, so several worker threads write in parallel and no
+    page of the file is ever faulted into this process the way a memmap store would.
+    """
+
+    def __init__(self, path: str, shape, create: bool = True, barrier=None, dtype=np.float32) -> None:
+        self.path, self.shape, self.dtype = path, tuple(int(x) for x in shape), np.dtype(dtype)
+        self.row_bytes = int(np.prod(self.shape[1:])) * self.dtype.itemsize
+        if create:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            tmp = path + ".partial"
+            with open(tmp, "wb") as fh:
+                np.lib.format.write_array_header_1_0(fh, {"descr": np.lib.format.dtype_to_descr(self.dtype), "fortran_order": False,
+                                                          "shape": self.shape})
+                header = fh.tell()
+                fh.truncate(header + self.shape[0] * self.row_bytes)
+            os.replace(tmp, path)
+        if barrier is not None:
+            barrier()
+        self.fd = os.open(path, os.O_RDWR)
+        with open(path, "rb") as fh:
+            version = np.lib.format.read_magic(fh)
+            got_shape, fortran, got_dtype = np.lib.format.read_array_header_1_0(fh) if version == (1, 0) else np.lib.format.read_array_header_2_0(fh)
+            self.data_offset = fh.tell()
+        assert tuple(got_shape) == self.shape and not fortran and got_dtype == self.dtype, (got_shape, self.shape, got_dtype)
+
+    def write(self, row: int, rows: np.ndarray) -> None:
+        """Rows ``[row, row + len(rows))`` <- ``rows`` (C-contiguous, the file's dtype).  Thread-safe (positional writes)."""
+        assert rows.dtype == self.dtype and rows.flags.c_contiguous and rows.shape[1:] == self.shape[1:]
+        assert 0 <= row and row + rows.shape[0] <= self.shape[0]
+        buf = memoryview(rows).cast("B")
+        at, off = 0, self.data_offset + row * self.row_bytes
+        while at < len(buf):
+            at += os.pwrite(self.fd, buf[at:], off + at)
+
+    def close(self) -> None:
+        if self.fd is not None:
+            os.close(self.fd)
+            self.fd = None
+
+    def __enter__(self) -> "NpyRowWriter":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
 
 
 class PrecalculatedDatasetIterator:

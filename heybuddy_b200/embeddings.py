@@ -33,6 +33,21 @@ DEFAULT_EMBED_PRECISION = os.environ.get("HEYBUDDY_B200_EMBED_PRECISION", "f16")
 DEFAULT_CLIP_CHUNK = int(os.environ.get("HEYBUDDY_B200_CLIP_CHUNK", "1024"))
 
 
+RANDOM_INIT = "random-init"
+_warned_random_init = False
+
+
+def _warn_random_init() -> None:
+    global _warned_random_init
+    if not _warned_random_init:
+        _warned_random_init = True
+        logger.warning(
+            "SpeechEmbeddingModel: NO pretrained weights given -- using the seeded RANDOM init of the embedding CNN. Embeddings from "
+            "an untrained network are not interchangeable with the reference's speech-embedding.onnx features: classifiers trained "
+            "on them, and reference .pt checkpoints scored with them, are meaningless. Pass weights=<dict | .npz path>, set "
+            "HEYBUDDY_B200_EMBED_WEIGHTS, or opt in with weights='random-init' / HEYBUDDY_B200_ALLOW_RANDOM_INIT=1.")
+
+
 def pack_embedding_weights(weights: Dict[str, np.ndarray]) -> np.ndarray:
     """Layer-table order, each kernel ``[kh, kw, cin, cout]`` then its bias (``hb_embed_create`` layout)."""
     parts = []
@@ -52,15 +67,21 @@ class SpeechEmbeddingModel(PretrainedNativeModel):
 
     ``precision``: ``"f16"`` = tcgen05 implicit GEMM, fp16 operands / fp32 TMEM accumulation
     (TF32-class mantissa; tolerance stated in tests/test_embed_gpu.py), ``"fp32"`` = CUDA-core
-    parity mode.  Weights: the speech-embedding.onnx artefact is not available offline, so the
-    default is the seeded random init of ``spec.init_embedding_weights``; ``from_file`` takes an
-    ``.npz`` with ``<layer>.weight`` (HWIO) / ``<layer>.bias`` arrays.
+    parity mode.
+
+    Weights: ``weights`` = a dict of ``<layer>.weight`` (HWIO) / ``<layer>.bias`` arrays or the path of an ``.npz`` holding
+    them (``from_file(path)`` and the environment variable ``HEYBUDDY_B200_EMBED_WEIGHTS`` do the same);
+    ``python -m heybuddy_b200.util.onnx_wire speech-embedding.onnx out.npz`` converts the reference's artefact
+    (embeddings.py:29-30) once it is at hand.  The artefact cannot be downloaded offline, so with NO weights given the model
+    falls back to the seeded RANDOM init of ``spec.init_embedding_weights`` -- an untrained CNN whose features are not
+    interchangeable with the reference's -- and says so with a warning unless the caller opted in
+    (``weights="random-init"`` or ``HEYBUDDY_B200_ALLOW_RANDOM_INIT=1``; tests and the bench do).
     """
 
     input_name = "input_1"
 
     def __init__(self, device_id: Optional[int] = None, load: bool = False, precision: Optional[str] = None,
-                 weights: Optional[Dict[str, np.ndarray]] = None) -> None:
+                 weights: Optional[Union[Dict[str, np.ndarray], str]] = None) -> None:
         self.precision = precision or DEFAULT_EMBED_PRECISION
         if self.precision not in _native.EMBED_MODES:
             raise ValueError(f"precision must be one of {sorted(_native.EMBED_MODES)}, got {self.precision!r}")
@@ -79,12 +100,15 @@ class SpeechEmbeddingModel(PretrainedNativeModel):
         import torch
 
         weights = self._weights
-        if weights is None:
-            if self.pretrained_model_path:
-                with np.load(self.pretrained_model_path) as z:
-                    weights = {k: z[k] for k in z.files}
-            else:
-                weights = spec.init_embedding_weights()
+        path = weights if isinstance(weights, str) and weights != RANDOM_INIT else None
+        path = path or self.pretrained_model_path or (os.environ.get("HEYBUDDY_B200_EMBED_WEIGHTS") if weights is None else None)
+        if path:
+            with np.load(path) as z:
+                weights = {k: z[k] for k in z.files}
+        elif weights is None or isinstance(weights, str):
+            if weights != RANDOM_INIT and os.environ.get("HEYBUDDY_B200_ALLOW_RANDOM_INIT", "") not in ("1", "true", "yes"):
+                _warn_random_init()
+            weights = spec.init_embedding_weights()
         packed = pack_embedding_weights(weights)
         lib = _native.load()
         handle = ctypes.c_void_p()
@@ -179,9 +203,10 @@ class SpeechEmbeddings:
     """A class to compute embeddings from audio (reference embeddings.py:44-234)."""
 
     def __init__(self, device_id: Optional[int] = None, load: bool = False, precision: Optional[str] = None,
-                 clip_chunk: int = DEFAULT_CLIP_CHUNK, seed: Optional[int] = None) -> None:
+                 clip_chunk: int = DEFAULT_CLIP_CHUNK, seed: Optional[int] = None,
+                 weights: Optional[Union[Dict[str, np.ndarray], str]] = None) -> None:
         self.spectrogram = MelSpectrogramModel(device_id=device_id, load=load)
-        self.embeddings = SpeechEmbeddingModel(device_id=device_id, load=load, precision=precision)
+        self.embeddings = SpeechEmbeddingModel(device_id=device_id, load=load, precision=precision, weights=weights)
         self.clip_chunk = clip_chunk
         self._rng = np.random.default_rng(seed)
 
@@ -354,8 +379,11 @@ class SpeechEmbeddings:
 GLOBAL_EMBEDDINGS: Dict[Optional[int], SpeechEmbeddings] = {}
 
 
-def get_speech_embeddings(device_id: Optional[int] = None) -> SpeechEmbeddings:
-    """Get a SpeechEmbeddings instance for a given device_id (embeddings.py:236-243)."""
+def get_speech_embeddings(device_id: Optional[int] = None, weights: Optional[Union[Dict[str, np.ndarray], str]] = None) -> SpeechEmbeddings:
+    """
+    Get a SpeechEmbeddings instance for a given device_id (embeddings.py:236-243).  ``weights`` (dict, ``.npz`` path or
+    ``"random-init"``) applies when the instance is first created.
+    """
     if device_id not in GLOBAL_EMBEDDINGS:
-        GLOBAL_EMBEDDINGS[device_id] = SpeechEmbeddings(device_id=device_id)
+        GLOBAL_EMBEDDINGS[device_id] = SpeechEmbeddings(device_id=device_id, weights=weights)
     return GLOBAL_EMBEDDINGS[device_id]

@@ -5,19 +5,23 @@ the ``[n, 16, 96]`` embeddings.
 
 This is what ``TrainingFeaturesGenerator.generate`` (reference dataset/features.py:360-490) does
 with a python loop per clip, a D2H per clip and one ORT call per 32 items; here a chunk of
-augmentation batches is five kinds of kernel launches on one stream:
+augmentation batches is a handful of kernel launches on one stream:
 
-    hb_augment_clips_i16 (length fix + augmentation) -> hb_mel_f32 -> hb_embed_clips (trunk + tail)
+    hb_colored_bases (the chunk's coloured-noise patterns, from the draw table's counters)
+    hb_featurize_i16 = hb_augment_clips_i16 (length fix + augmentation) -> hb_mel_f32 -> hb_embed_clips
 
-``featurize_host`` adds the pinned-memory H2D / D2H copies on a second stream so chunk i+1 uploads
-while chunk i computes (double buffering).
+``featurize_stream`` is the host side: per chunk ONE pinned metadata blob (offsets, pad offsets, per-clip draw
+records, coloured batch ids) and the int16 samples go up on a copy stream, results come back on a third stream
+into pinned slots, and a small thread pool hands them to the caller's sink (a numpy array, a pinned tensor, or a
+``.npy`` row writer) -- so uploads, kernels, downloads and file writes of different chunks all overlap.
 """
 from __future__ import annotations
 
 import time
 from collections import deque
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
@@ -72,45 +76,83 @@ class DeviceChunk:
     offsets: "object"       # cuda int64 [n + 1]
     pad_before: "object"    # cuda int32 [n]
     params: "object"        # cuda uint8 [n, 32]  (hb_clip_aug records)
-    bases: Optional["object"]  # cuda f32 [k, 16000] coloured patterns or None
+    colored_ids: Optional["object"]     # cuda int64 [k] global batch ids of the coloured batches, or None
+    colored_f_decay: Optional["object"]  # cuda f32 [k]
     n: int
+    seed: int = 0
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
 
 
 class FeaturizePipeline:
-    def __init__(self, augment: Optional[AugmentedAudioGenerator], speech: SpeechEmbeddings, device_id: Optional[int] = None):
+    def __init__(self, augment: AugmentedAudioGenerator, speech: SpeechEmbeddings, device_id: Optional[int] = None):
+        if augment is None:
+            raise ValueError("FeaturizePipeline needs an AugmentedAudioGenerator (set every probability to 0 for a plain length fix)")
         self.augment = augment
         self.speech = speech
         self.device = _native.require_cuda(device_id if device_id is not None else speech.spectrogram.device_id)
-        self.t = spec.CLIP_SAMPLES if augment is None else augment.target_num_samples
+        self.t = augment.target_num_samples
         self.slot_offsets = np.asarray(spec.embedding_frame_offsets(self.t), dtype=np.int32)
         self._bufs: Dict[Tuple[str, int], "object"] = {}
         self.stage_ms: Dict[str, float] = {}
         self._events: List[Tuple[str, object, object]] = []
         self.profile = False
+        self.last_stream_wait_s = 0.0
+        self._writers: Optional[ThreadPoolExecutor] = None
 
     # -- host-side packing -------------------------------------------------------------------------
-    def pack_params(self, table: DrawTable) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
-        """Draw table -> (pad_before i32[n], hb_clip_aug records, coloured bases f32[k,16000] | None)."""
-        aug = self.augment
-        bases = [d.colored_base for d in table.batches if d.colored_apply]
-        slots, k = [], 0
-        for d in table.batches:
-            slots.append(k if d.colored_apply else -1)
-            k += int(d.colored_apply)
-        params = aug.clip_params(table.batches, table.noise_clip_cursor, table.rir_index, slots)
-        pads = np.concatenate([d.pad_before for d in table.batches]).astype(np.int32)
-        return pads, params, (np.stack(bases) if bases else None)
+    def pack_params(self, table: DrawTable) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Draw table -> (pad_before i32[n], hb_clip_aug records [n], coloured batch ids i64[k], their f_decay f32[k])."""
+        params = self.augment.clip_params(table)
+        _, ids, f_decay = table.colored_slots()
+        return np.ascontiguousarray(table.pad_before, dtype=np.int32), params, ids, f_decay
 
-    def upload(self, clips: RaggedClips, table: DrawTable) -> DeviceChunk:
+    def _meta_layout(self, n: int, k: int) -> Tuple[Dict[str, Tuple[int, int]], int]:
+        """Byte ranges of the per-chunk metadata blob: offsets i64[n+1], pads i32[n], params [n][32], ids i64[k], f_decay f32[k]."""
+        lay, at = {}, 0
+        for name, nbytes in (("offsets", 8 * (n + 1)), ("pads", 4 * n), ("params", 32 * n), ("ids", 8 * k), ("fd", 4 * k)):
+            lay[name] = (at, nbytes)
+            at = _align(at + nbytes)
+        return lay, max(at, 256)
+
+    def _fill_meta(self, blob: np.ndarray, clips: RaggedClips, table: DrawTable) -> Tuple[Dict[str, Tuple[int, int]], int, int]:
+        pads, params, ids, fd = self.pack_params(table)
+        n, k = len(clips), int(ids.shape[0])
+        assert params.shape[0] == n == pads.shape[0], (params.shape, pads.shape, n)
+        lay, total = self._meta_layout(n, k)
+        assert blob.nbytes >= total
+        for name, arr in (("offsets", clips.offsets), ("pads", pads), ("params", params), ("ids", ids), ("fd", fd)):
+            at, nbytes = lay[name]
+            if nbytes:
+                blob[at:at + nbytes] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        return lay, total, k
+
+    @staticmethod
+    def _chunk_from_meta(samples_dev, meta_dev, lay, n: int, k: int, seed: int) -> DeviceChunk:
         import torch
 
-        pads, params, bases = self.pack_params(table)
-        dev = self.device
+        def view(name, dtype, shape):
+            at, nbytes = lay[name]
+            return meta_dev[at:at + nbytes].view(dtype).view(shape)
+
         return DeviceChunk(
-            samples=torch.from_numpy(clips.samples).to(dev), offsets=torch.from_numpy(clips.offsets).to(dev),
-            pad_before=torch.from_numpy(pads).to(dev),
-            params=torch.from_numpy(params.view(np.uint8).reshape(len(clips), -1)).to(dev),
-            bases=torch.from_numpy(bases).to(dev) if bases is not None else None, n=len(clips))
+            samples=samples_dev, offsets=view("offsets", torch.int64, (n + 1,)), pad_before=view("pads", torch.int32, (n,)),
+            params=view("params", torch.uint8, (n, 32)), colored_ids=view("ids", torch.int64, (k,)) if k else None,
+            colored_f_decay=view("fd", torch.float32, (k,)) if k else None, n=n, seed=seed)
+
+    def upload(self, clips: RaggedClips, table: DrawTable) -> DeviceChunk:
+        """Synchronous upload of one chunk (tests, the bench's device-resident leg)."""
+        import torch
+
+        n = len(clips)
+        _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)))
+        blob = np.zeros(total, dtype=np.uint8)
+        lay, total, k = self._fill_meta(blob, clips, table)
+        dev = self.device
+        return self._chunk_from_meta(torch.from_numpy(np.ascontiguousarray(clips.samples)).to(dev), torch.from_numpy(blob).to(dev),
+                                     lay, n, k, table.seed)
 
     # -- device path -----------------------------------------------------------------------------------
     def _buf(self, name: str, shape, dtype):
@@ -124,6 +166,16 @@ class FeaturizePipeline:
             buf = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[key] = buf
         return buf.view(shape)
+
+    def _grow(self, name: str, numel: int, dtype):
+        """A device buffer of at least ``numel`` elements that only ever grows (sizes that change per chunk)."""
+        import torch
+
+        buf = self._bufs.get((name, -1))
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = torch.empty(max(int(numel * 1.25), 1), dtype=dtype, device=self.device)
+            self._bufs[(name, -1)] = buf
+        return buf
 
     def _mark(self, name: str):
         import torch
@@ -155,6 +207,16 @@ class FeaturizePipeline:
         with torch.cuda.device(dev):
             st = _native.stream_ptr(dev)
             nb, rb = aug.noise_bank, aug.rir_bank
+            self._mark("begin")
+            bases_ptr = None
+            if chunk.colored_ids is not None:
+                k = int(chunk.colored_ids.numel())
+                bases = self._grow("bases", k * spec.COLORED_BASE_SAMPLES, torch.float32)
+                _native.check(lib.hb_colored_bases(chunk.seed & (2 ** 64 - 1), chunk.colored_ids.data_ptr(), chunk.colored_f_decay.data_ptr(),
+                                                   k, bases.data_ptr(), st), "hb_colored_bases")
+                bases_ptr = bases.data_ptr()
+            self._mark("colored")
+            banks = (nb.stream.data_ptr() if nb is not None else None, bases_ptr, rb.spec.data_ptr() if rb is not None else None)
             if t == spec.CLIP_SAMPLES and not keep_audio and not self.profile:
                 # one C-ABI call for the whole path (hb_featurize_i16 = augment_i16 -> mel -> embed on one workspace)
                 emb_model = self.speech.embeddings
@@ -166,17 +228,13 @@ class FeaturizePipeline:
                     out = torch.empty((n, offs.size, spec.EMB_DIM), dtype=torch.float32, device=dev)
                 nbytes = lib.hb_featurize_workspace_bytes(n, t, emb_model.mode)
                 _native.check(nbytes, "hb_featurize_workspace_bytes")
-                ws = self._buf("featurize_ws", (int(nbytes),), torch.uint8)
+                ws = self._grow("featurize_ws", int(nbytes), torch.uint8)
                 _native.check(lib.hb_featurize_i16(
                     emb_model._handle, emb_model.mode, chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
-                    nb.stream.data_ptr() if nb is not None else None, chunk.bases.data_ptr() if chunk.bases is not None else None,
-                    rb.spec.data_ptr() if rb is not None else None, chunk.params.data_ptr(), offs.ctypes.data, offs.size,
-                    out.data_ptr(), n, t, ws.data_ptr(), int(nbytes), st), "hb_featurize_i16")
+                    *banks, chunk.params.data_ptr(), offs.ctypes.data, offs.size,
+                    out.data_ptr(), n, t, ws.data_ptr(), int(ws.numel()), st), "hb_featurize_i16")
                 return out
-            self._mark("begin")
             audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
-            banks = (nb.stream.data_ptr() if nb is not None else None, chunk.bases.data_ptr() if chunk.bases is not None else None,
-                     rb.spec.data_ptr() if rb is not None else None)
             if t == spec.CLIP_SAMPLES:
                 # length fix fused into the augmentation kernel's load: int16 samples -> shared memory, no f32 intermediate
                 _native.check(lib.hb_augment_clips_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
@@ -198,13 +256,12 @@ class FeaturizePipeline:
         return (out, audio) if keep_audio else out
 
     # -- host path (the call a user makes) -----------------------------------------------------------------
-    def featurize_host(self, clips: RaggedClips, tables: Sequence[DrawTable], chunk_clips: int, out: Optional[np.ndarray] = None):
+    def featurize_host(self, clips: RaggedClips, tables: Union[DrawTable, Sequence[DrawTable]], chunk_clips: int,
+                       out: Optional[np.ndarray] = None):
         """
-        Host int16 clips -> host f32 ``[n, 16, 96]``.  ``tables[i]`` holds the draws of chunk i
-        (``chunk_clips`` clips each, a multiple of the augmentation batch size).  Uploads run on a side
-        stream from pinned staging buffers, double-buffered against the compute stream; results drain on a
-        third stream.  ``out`` may be a numpy array or a pinned CPU torch tensor (the D2H then lands in it
-        directly).  Returns (embeddings, h2d_bytes, d2h_bytes).
+        Host int16 clips -> host f32 ``[n, 16, 96]``.  ``tables``: the draw table of all the clips (or one table per chunk of
+        ``chunk_clips`` clips, a multiple of the augmentation batch size).  ``out`` may be a numpy array, a pinned CPU torch
+        tensor (the D2H then lands in it directly) or a callable ``(lo, hi, rows)``.  Returns (embeddings, h2d_bytes, d2h_bytes).
         """
         n_slots = self.slot_offsets.size
         if out is None:
@@ -212,47 +269,64 @@ class FeaturizePipeline:
         h2d, d2h = self.featurize_stream([(clips, tables, out)], chunk_clips)
         return (out.numpy() if hasattr(out, "is_pinned") else out), h2d, d2h
 
-    def featurize_stream(self, items, chunk_clips: int):
+    def featurize_stream(self, items, chunk_clips: int, writer_threads: int = 4):
         """
-        Streaming form of :meth:`featurize_host`: ``items`` is a sequence of ``(clips, tables, out)`` host datasets
-        (``out``: numpy array or pinned CPU torch tensor ``[len(clips), 16, 96]``).  The upload of the next chunk --
-        of the same or of the next item -- always overlaps the compute of the current one, so a long run pays the
-        pipeline fill (first H2D) and drain (last D2H) once, not once per item.  Returns (h2d_bytes, d2h_bytes).
+        Streaming form of :meth:`featurize_host`: ``items`` is an iterable (pulled lazily, e.g. a generator that fetches one
+        super-batch of source clips at a time) of ``(clips, table, sink)`` host datasets.
+        ``table``: a :class:`DrawTable` covering the item's clips (sliced per chunk here) or a list of per-chunk tables.
+        ``sink``: numpy array / pinned CPU torch tensor ``[len(clips), 16, 96]``, or a callable ``sink(lo, hi, rows)`` that is
+        handed every finished row range (``rows``: f32 numpy view of a pinned slot, valid until the call returns; called from
+        worker threads, possibly out of order).  The upload of the next chunk -- of the same or of the next item -- always
+        overlaps the compute of the current one, so a long run pays the pipeline fill (first H2D) and drain (last D2H) once,
+        not once per item.  Returns (h2d_bytes, d2h_bytes).
         """
         import torch
 
         dev = self.device
         n_slots = self.slot_offsets.size
+        b = self.augment.batch_size
+        assert chunk_clips % b == 0, "chunks are whole augmentation batches"
         for key in ("copy_stream", "d2h_stream"):
             if (key, 0) not in self._bufs:
                 self._bufs[(key, 0)] = torch.cuda.Stream(device=dev)
         copy_stream = self._bufs[("copy_stream", 0)]
         d2h_stream = self._bufs[("d2h_stream", 0)]     # results drain on their own stream, off the compute stream's critical path
         compute = torch.cuda.current_stream(dev)
+        if self._writers is None or getattr(self._writers, "_max_workers", 0) != writer_threads:
+            self._writers = ThreadPoolExecutor(max_workers=writer_threads, thread_name_prefix="hb-sink")
         h2d = d2h = 0
-        # The host stages up to DEPTH chunks ahead of the chunk whose kernels it is enqueueing (small draw-table arrays go through
-        # N_SLOTS pinned staging buffers; the samples come straight from the caller's pinned memory), so a host hiccup of a few
-        # milliseconds does not starve the GPU.  At most MAX_INFLIGHT chunks are uploaded-but-not-finished at any time (bounds the
-        # device memory of a long run: uploads are faster than the kernels and would otherwise run ahead without limit).
-        DEPTH, N_SLOTS, MAX_INFLIGHT = 3, 4, 5
+        # The host stages up to DEPTH chunks ahead of the chunk whose kernels it is enqueueing (the metadata goes through N_SLOTS
+        # pinned staging blobs; the samples come straight from the caller's pinned memory when they are pinned), so a host hiccup
+        # of a few milliseconds does not starve the GPU.  At most MAX_INFLIGHT chunks are uploaded-but-not-finished at any time
+        # (bounds the device memory of a long run: uploads are faster than the kernels and would otherwise run ahead without limit).
+        DEPTH, N_SLOTS, MAX_INFLIGHT, OUT_SLOTS = 3, 4, 5, 4
         stage_events = [None] * N_SLOTS
+        out_tasks = [None] * OUT_SLOTS
         wait_s = 0.0    # host time spent blocked on the device (the rest of the call is host work)
 
-        work = []   # (item index, chunk index, lo, hi)
-        sinks = []  # per item: (numpy view, pinned torch tensor or None)
-        for ii, (clips, tables, out) in enumerate(items):
-            n = len(clips)
-            out_t = out if hasattr(out, "is_pinned") else None
-            if out_t is not None:
-                assert out_t.is_pinned() and tuple(out_t.shape) == (n, n_slots, spec.EMB_DIM) and out_t.dtype == torch.float32
-            else:
-                assert tuple(out.shape) == (n, n_slots, spec.EMB_DIM) and out.dtype == np.float32
-            sinks.append((out if out_t is None else out_t.numpy(), out_t))
-            n_chunks = (n + chunk_clips - 1) // chunk_clips
-            assert len(tables) >= n_chunks, "one draw table per chunk"
-            for ci in range(n_chunks):
-                work.append((ii, ci, ci * chunk_clips, min(n, (ci + 1) * chunk_clips)))
-        done_events = [None] * len(work)   # compute of chunk k finished
+        def work_units():
+            """(sink, clips of the item, lo, hi, table of the chunk) for every chunk of every item, items pulled lazily."""
+            for clips, tables, out in items:
+                n = len(clips)
+                if hasattr(out, "is_pinned"):
+                    assert out.is_pinned() and tuple(out.shape) == (n, n_slots, spec.EMB_DIM) and out.dtype == torch.float32
+                elif isinstance(out, np.ndarray):
+                    assert tuple(out.shape) == (n, n_slots, spec.EMB_DIM) and out.dtype == np.float32
+                else:
+                    assert callable(out), "sink: numpy array, pinned tensor or callable(lo, hi, rows)"
+                n_chunks = (n + chunk_clips - 1) // chunk_clips
+                per_chunk = isinstance(tables, (list, tuple))
+                if per_chunk:
+                    assert len(tables) >= n_chunks, "one draw table per chunk"
+                else:
+                    assert tables.n_clips == n, (tables.n_clips, n)
+                for ci in range(n_chunks):
+                    lo, hi = ci * chunk_clips, min(n, (ci + 1) * chunk_clips)
+                    yield out, clips, lo, hi, (tables[ci] if per_chunk else tables.slice(lo // b, (hi + b - 1) // b))
+
+        units = work_units()
+        done_events = deque()   # compute-finished events of the chunks enqueued so far (bounded)
+        n_staged = 0
 
         def blocked(ev):
             nonlocal wait_s
@@ -261,108 +335,101 @@ class FeaturizePipeline:
                 ev.synchronize()
                 wait_s += time.perf_counter() - t0
 
-        def stage(k: int):
-            nonlocal h2d
-            ii, ci, lo, hi = work[k]
-            clips, tables, _ = items[ii]
+        def pinned(name: str, slot: int, numel: int, dtype):
+            key = (f"pin_{name}_{slot}", 0)
+            pin = self._bufs.get(key)
+            if pin is None or pin.numel() < numel or pin.dtype != dtype:
+                pin = torch.empty(max(int(numel * 1.25), 1), dtype=dtype).pin_memory()
+                self._bufs[key] = pin
+            return pin
+
+        def stage(unit):
+            nonlocal h2d, n_staged
+            sink, clips, lo, hi, table = unit
             part = clips.slice(lo, hi)
-            pads, params, bases = self.pack_params(tables[ci])
+            n = hi - lo
+            k = n_staged
+            n_staged += 1
             slot = k % N_SLOTS
             blocked(stage_events[slot])          # the H2D that last read this slot's pinned staging buffers must have finished
-            if k >= MAX_INFLIGHT:
-                blocked(done_events[k - MAX_INFLIGHT])
-            host = {}
-            for name, arr in (("samples", part.samples), ("offsets", part.offsets), ("pads", pads),
-                              ("params", params.view(np.uint8).reshape(hi - lo, -1)), ("bases", bases)):
-                if arr is None:
-                    host[name] = None
-                    continue
-                if name == "samples" and part.pinned is not None:
-                    host[name] = (part.pinned, arr.shape)  # already pinned: DMA straight from the caller's buffer
-                    continue
-                key = (f"pin_{name}_{slot}", 0)
-                pin = self._bufs.get(key)
-                if pin is None or pin.numel() < arr.size or pin.dtype != torch.from_numpy(arr[:0]).dtype:
-                    pin = torch.empty(max(arr.size, 1), dtype=torch.from_numpy(arr[:0]).dtype).pin_memory()
-                    self._bufs[key] = pin
-                pin[:arr.size].copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(-1)))
-                host[name] = (pin, arr.shape)
+            while len(done_events) > 0 and k - done_events[0][0] >= MAX_INFLIGHT:
+                blocked(done_events.popleft()[1])
+            _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)))
+            meta_pin = pinned("meta", slot, total, torch.uint8)
+            lay, total, kc = self._fill_meta(meta_pin.numpy(), part, table)
+            if part.pinned is not None:
+                samples_pin = part.pinned        # already pinned: DMA straight from the caller's buffer
+            else:
+                samples_pin = pinned("samples", slot, part.samples.size, torch.int16)[:part.samples.size]
+                np.copyto(samples_pin.numpy(), part.samples)
             with torch.cuda.stream(copy_stream):
-                devs = {}
-                for name, v in host.items():
-                    if v is None:
-                        devs[name] = None
-                        continue
-                    pin, shape = v
-                    cnt = int(np.prod(shape))
-                    d = torch.empty(cnt, dtype=pin.dtype, device=dev)
-                    d.copy_(pin[:cnt], non_blocking=True)
-                    h2d += cnt * pin.element_size()
-                    devs[name] = d.view(shape)
+                samples_dev = torch.empty(part.samples.size, dtype=torch.int16, device=dev)
+                samples_dev.copy_(samples_pin, non_blocking=True)
+                meta_dev = torch.empty(total, dtype=torch.uint8, device=dev)
+                meta_dev.copy_(meta_pin[:total], non_blocking=True)
+                h2d += part.samples.size * 2 + total
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             stage_events[slot] = ev
-            return DeviceChunk(devs["samples"], devs["offsets"], devs["pads"], devs["params"], devs["bases"], hi - lo), ev
+            return self._chunk_from_meta(samples_dev, meta_dev, lay, n, kc, table.seed), meta_dev, ev, sink, lo, hi
 
-        pending = None  # staged path: (pinned buffer, numpy sink, lo, hi, event)
-
-        def drain():
-            nonlocal pending
-            if pending is not None:
-                p_pin, p_sink, p_lo, p_hi, p_ev = pending
-                blocked(p_ev)
-                p_sink[p_lo:p_hi] = p_pin[:(p_hi - p_lo) * n_slots * spec.EMB_DIM].numpy().reshape(p_hi - p_lo, n_slots, spec.EMB_DIM)
-                pending = None
+        def deliver(sink, lo, hi, pin, done_ev):
+            done_ev.synchronize()
+            rows = pin[:(hi - lo) * n_slots * spec.EMB_DIM].numpy().reshape(hi - lo, n_slots, spec.EMB_DIM)
+            if isinstance(sink, np.ndarray):
+                np.copyto(sink[lo:hi], rows)
+            else:
+                sink(lo, hi, rows)
 
         staged = deque()
-        next_stage = 0
+        exhausted = False
 
         def fill():
-            nonlocal next_stage
-            while next_stage < len(work) and len(staged) < DEPTH:
-                staged.append(stage(next_stage))
-                next_stage += 1
+            nonlocal exhausted
+            while not exhausted and len(staged) < DEPTH:
+                unit = next(units, None)
+                if unit is None:
+                    exhausted = True
+                    break
+                staged.append(stage(unit))
 
         fill()
-        for k in range(len(work)):
-            chunk, ev = staged.popleft()
-            ii, ci, lo, hi = work[k]
+        k = -1
+        while staged:
+            k += 1
+            chunk, meta_dev, ev, sink, lo, hi = staged.popleft()
             compute.wait_event(ev)
-            for v in (chunk.samples, chunk.offsets, chunk.pad_before, chunk.params, chunk.bases):
-                if v is not None:
-                    v.record_stream(compute)
+            chunk.samples.record_stream(compute)
+            meta_dev.record_stream(compute)
             emb = self.run_device(chunk)
             ready = torch.cuda.Event()
             ready.record(compute)
-            done_events[k] = ready
-            if k >= MAX_INFLIGHT + 1:
-                done_events[k - MAX_INFLIGHT - 1] = None
+            done_events.append((k, ready))
             d2h_stream.wait_event(ready)
             emb.record_stream(d2h_stream)
-            sink, out_t = sinks[ii]
             d2h += emb.numel() * 4
-            if out_t is not None:
+            if hasattr(sink, "is_pinned"):
                 with torch.cuda.stream(d2h_stream):
-                    out_t[lo:hi].copy_(emb, non_blocking=True)
-                del chunk, emb
-                fill()
-                continue
-            key = (f"pin_out_{k % 2}", 0)
-            pin = self._bufs.get(key)
-            if pin is None or pin.numel() < emb.numel():
-                pin = torch.empty(emb.numel(), dtype=torch.float32).pin_memory()
-                self._bufs[key] = pin
-            drain()   # the previous chunk's pinned buffer (the other slot) -> its numpy sink
-            with torch.cuda.stream(d2h_stream):
-                pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(d2h_stream)
-            pending = (pin, sink, lo, hi, done)
-            del chunk, emb
+                    sink[lo:hi].copy_(emb, non_blocking=True)
+            else:
+                oslot = k % OUT_SLOTS
+                if out_tasks[oslot] is not None:   # the task that last read this pinned slot must have handed its rows over
+                    t0 = time.perf_counter()
+                    out_tasks[oslot].result()
+                    wait_s += time.perf_counter() - t0
+                pin = pinned("out", oslot, emb.numel(), torch.float32)
+                with torch.cuda.stream(d2h_stream):
+                    pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(d2h_stream)
+                out_tasks[oslot] = self._writers.submit(deliver, sink, lo, hi, pin, done)
+            del chunk, emb, meta_dev
             fill()
-        drain()
         t0 = time.perf_counter()
+        for task in out_tasks:
+            if task is not None:
+                task.result()
         d2h_stream.synchronize()
         wait_s += time.perf_counter() - t0
-        self.last_stream_wait_s = wait_s   # host time spent blocked on the device during the call (diagnostic)
+        self.last_stream_wait_s = wait_s   # host time spent blocked on the device / the sinks during the call (diagnostic)
         return h2d, d2h

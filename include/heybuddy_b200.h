@@ -119,6 +119,12 @@ typedef struct hb_clip_aug {
  * kernels_dev f32 [n][T] (rotated so the peak is at lag 0, zero padded; augment host code)
  * -> spec_dev f32 [n][T/2+1][2].  T must be even with T/2 = 2^a 3^b 5^c and T <= 23040. */
 int hb_rir_spectrum(const float* kernels_dev, float* spec_dev, int n, int T, void* stream);
+/* Coloured-noise patterns of k augmentation batches, generated on the device (torch_audiomentations AddColoredNoise
+ * `_gen_noise`, call site augmented.py:107-115): for batch ids batch_ids_dev[i] the 16000-sample N(0,1) pattern comes from
+ * stream 3 of the draw table's Philox4x32-10 counters (heybuddy_b200/dataset/draws.py: same seed, same counters, so the
+ * host restatement and the device agree), is shaped by 1 / linspace(1, sqrt(8000), 8001)^f_decay between an rfft / irfft
+ * pair and scaled to unit RMS -> out_dev f32 [k][16000].  Nothing but two k-entry arrays crosses PCIe. */
+int hb_colored_bases(uint64_t seed, const int64_t* batch_ids_dev, const float* f_decay_dev, int k, float* out_dev, void* stream);
 int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-fixed clips            */
                          const float* noise_bank_dev,     /* f32 noise stream or NULL                  */
                          const float* colored_bases_dev,  /* f32 [..][16000] or NULL                   */

@@ -118,3 +118,43 @@ def speech_embeddings(
         t = s.shape[1]
         return e, s[:, : t - ((t - spec.EMB_WINDOW) % spec.EMB_STRIDE)]
     return e
+
+
+def augment_table(clips, table, noise_stream: Optional[np.ndarray], noise_clip_starts: Optional[np.ndarray], rir_kernels, dtype=np.float64):
+    """
+    The oracle's augmentation of ``clips`` (ragged int16 / float arrays) under a draw table
+    (``heybuddy_b200.dataset.draws.DrawTable``): per augmentation batch, length fix with the table's pad offsets, then
+    ``oracle.augment.augment_batch`` with the batch's draws -- the noise rows are consecutive slices of the contiguous noise
+    stream starting at the batch's first noise clip (augmented.py:246-267), the RIR is the batch's (augmented.py:389-392).
+    Returns ``f32 [n, T]``.
+    """
+    from oracle import augment as oaug
+
+    t = table.cfg.target_samples
+    out, i0 = [], 0
+    for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
+        b = len(d.pad_before)
+        fixed = np.stack([oaug.to_target_length(c, int(p), t) for c, p in zip(clips[i0:i0 + b], d.pad_before)])
+        noise = None
+        if d.background_apply:
+            off = int(noise_clip_starts[ncur])
+            noise = noise_stream[off:off + b * t].reshape(b, t)
+        out.append(oaug.augment_batch(
+            fixed, colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
+            gain_db=d.gain_db if d.gain_apply else None, noise=noise, noise_snr_db=d.noise_snr_db,
+            rir=rir_kernels[ridx] if d.reverb_apply else None, dtype=dtype))
+        i0 += b
+    return np.concatenate(out)
+
+
+def well_conditioned_slots(mel_true: np.ndarray, floor_db: float = 80.0) -> np.ndarray:
+    """
+    ``[n, F, 32]`` reference-scale log-mel (``log10(P) + 2``, floor -8) -> bool ``[n, slots]``: True where the slot's 76-frame
+    window holds no (frame, mel bin) within ``floor_db`` of the 1e-10 power floor.  log10 of digital silence / of reverb tails that
+    decayed below fp32 round-off is implementation noise, and an embedding window that contains such frames inherits it.
+    """
+    thr = np.log10(spec.MEL_FLOOR) + floor_db / 10.0 + spec.MEL_POST_ADD
+    frame_min = mel_true.min(axis=2)
+    n_samples = (mel_true.shape[1] - 1) * spec.HOP + spec.N_FFT
+    offs = spec.embedding_frame_offsets(n_samples)
+    return np.stack([frame_min[:, o:o + spec.EMB_WINDOW].min(axis=1) > thr for o in offs], axis=1)

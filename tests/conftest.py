@@ -37,3 +37,6 @@ def cuda_device():
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
     return torch.device("cuda:0")
+
+# The speech-embedding artefact cannot be downloaded offline: tests run on the seeded random init on purpose.
+os.environ.setdefault("HEYBUDDY_B200_ALLOW_RANDOM_INIT", "1")

@@ -155,11 +155,34 @@ def test_zero_clip_gives_nan_like_dependency(cuda_device):
     src = [np.zeros(8000, np.int16), _sources(rng, 1)[0]]
     gen = _generator(rng, src, 2, colored_noise_prob=0.0, gain_prob=0.0, background_noise_prob=1.0, reverb_prob=0.0)
     table = gen.next_table([c.shape[0] for c in src])
-    got = gen.augment_device(gen.fix_length_device(src, table.batches[0].pad_before), table).cpu().numpy()
+    got = gen.augment_device(gen.fix_length_device(src, table.pad_before), table).cpu().numpy()
     want = _oracle_batches(gen, src, table)
     assert not np.isfinite(got[0]).all() or np.abs(got[0]).max() == 0 or True
     assert np.isfinite(want[0]).all() == np.isfinite(got[0]).all()
     _assert_wave_close(got[1:], want[1:])
+
+
+def test_colored_bases_device_matches_host_restatement(cuda_device):
+    """
+    hb_colored_bases regenerates a coloured batch's N(0,1) pattern on the device from the draw table's Philox counters and shapes
+    it there (fp32 Box-Muller, fp32 16000-point real FFT pair): against the float64 host restatement of the same counters
+    (draws.gaussian_pattern + colored_noise_base == oracle.augment.colored_noise_base), white and coloured.
+    """
+    from heybuddy_b200 import _native
+    from heybuddy_b200.dataset.draws import colored_noise_base, gaussian_pattern
+
+    ids = np.array([0, 1, 7, 123456, (1 << 33) + 5], dtype=np.int64)
+    f_decay = np.array([0.0, -1.0, 2.0, 0.37, 1.5], dtype=np.float32)
+    seed = 0x1234_5678_9ABC_DEF0
+    out = torch.empty((len(ids), 16000), dtype=torch.float32, device="cuda")
+    _native.check(_native.load().hb_colored_bases(seed, torch.from_numpy(ids).cuda().data_ptr(), torch.from_numpy(f_decay).cuda().data_ptr(),
+                                                  len(ids), out.data_ptr(), _native.stream_ptr(out.device)), "hb_colored_bases")
+    got = out.cpu().numpy()
+    for i, (g, fd) in enumerate(zip(ids, f_decay)):
+        want = colored_noise_base(gaussian_pattern(seed, int(g)), float(fd))
+        np.testing.assert_allclose(want, oaug.colored_noise_base(gaussian_pattern(seed, int(g)), float(fd)), atol=1e-6)
+        assert abs(np.sqrt(np.mean(got[i].astype(np.float64) ** 2)) - 1.0) < 1e-5
+        assert np.abs(got[i] - want).max() < 2e-5 * np.abs(want).max(), (i, np.abs(got[i] - want).max())
 
 
 def test_unsupported_transforms_raise():
@@ -187,7 +210,9 @@ def test_fused_length_fix_is_bit_identical(cuda_device):
     n, t = len(clips), spec.CLIP_SAMPLES
     st = _native.stream_ptr(pipe.device)
     nb, rb = gen.noise_bank, gen.rir_bank
-    banks = (nb.stream.data_ptr(), chunk.bases.data_ptr() if chunk.bases is not None else None, rb.spec.data_ptr())
+    bases = gen.colored_bases_device(table, pipe.device)
+    assert bases is not None and bases.shape[0] == int(np.count_nonzero(table.colored_apply))
+    banks = (nb.stream.data_ptr(), bases.data_ptr(), rb.spec.data_ptr())
     fixed = torch.empty((n, t), dtype=torch.float32, device="cuda")
     two = torch.empty_like(fixed)
     one = torch.empty_like(fixed)

@@ -33,49 +33,50 @@ def test_reference_shape_contract(cuda_device):
     assert samples.shape == (1, 16, 96) and samples.dtype == np.float32 and np.isfinite(samples).all()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("f16", 4e-3)])
-def test_generator_matches_oracle_pipeline(cuda_device, precision, tol):
-    """Augment -> mel -> embed through the public generator vs the oracle run with the same draw table."""
+# End-to-end tolerance (north star: embeddings within 1e-3 relative; a stated tolerance for the reduced-precision mode):
+# max |got - want| / max |want| over every WELL-CONDITIONED embedding slot of every clip.
+E2E_TOL = {"fp32": 1e-3, "f16": 2e-3}
+# A slot is ill-conditioned when its 76-frame window holds a (frame, mel bin) within FLOOR_DB of the 1e-10 power floor of the
+# log (digital silence, reverb tails decayed below fp32 round-off): log10 of round-off noise differs by O(1) between ANY two
+# correct fp32 implementations (cuFFT vs pocketfft would too) and the embedding inherits it.  Such slots are masked and counted.
+FLOOR_DB = 80.0
+
+
+_slot_mask = lambda mel_true: opipe.well_conditioned_slots(mel_true, FLOOR_DB)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_generator_matches_oracle_pipeline(cuda_device, precision):
+    """Augment -> mel -> embed through the public generator vs the oracle run with the same draw table, ALL clips."""
     from heybuddy_b200.dataset.draws import DrawTable
     from heybuddy_b200.dataset.features import SyntheticSpeechSource, TrainingFeaturesGenerator
 
+    tol = E2E_TOL[precision]
     rng = np.random.default_rng(3)
     noise, rirs = _banks(rng)
+    n = 64
     gen = TrainingFeaturesGenerator(device_id=0, use_autoconfigure=False, augment_batch_size=8, augment_background_dataset=noise,
                                     augment_impulse_dataset=rirs, precision=precision, seed=2004, source=SyntheticSpeechSource(9))
-    got = gen(40)
-    assert got.shape == (40, 16, 96)
+    got = gen(n)
+    assert got.shape == (n, 16, 96)
     # oracle: same clips, same table
     pipe, aug = gen._pipeline(True)
-    clips = SyntheticSpeechSource(9)(40)
+    clips = SyntheticSpeechSource(9)(n)
     table = DrawTable.build([c.shape[0] for c in clips], aug.cfg, 2004, aug.noise_bank.clip_lengths, len(aug.rir_bank))
-    stream = aug.noise_bank.stream.cpu().numpy()
-    audio, i0 = [], 0
-    for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
-        b = len(d.pad_before)
-        fixed = np.stack([oaug.to_target_length(c, int(p)) for c, p in zip(clips[i0:i0 + b], d.pad_before)])
-        off = aug.noise_bank.offset_of_clip(ncur) if d.background_apply else 0
-        audio.append(oaug.augment_batch(
-            fixed, colored_base=d.colored_base if d.colored_apply else None, colored_snr_db=d.colored_snr_db,
-            gain_db=d.gain_db if d.gain_apply else None,
-            noise=stream[off:off + b * spec.CLIP_SAMPLES].reshape(b, -1) if d.background_apply else None, noise_snr_db=d.noise_snr_db,
-            rir=aug.rir_bank.kernels_host[ridx] if d.reverb_apply else None))
-        i0 += b
+    audio = opipe.augment_table(clips, table, aug.noise_bank.stream.cpu().numpy(), aug.noise_bank.clip_starts, aug.rir_bank.kernels_host)
     weights = spec.init_embedding_weights()
-    audio = np.concatenate(audio)
     embed = lambda a: opipe.speech_embeddings([x for x in a], omel.mel_spectrogram,
                                               lambda w: oembed.speech_embedding_model(w, weights, dtype=torch.float64))
     want = embed(audio)
-    # (1) end to end on the well-conditioned clips.  A zero-padded clip with no background noise has frames of digital
-    #     silence whose log-mel is log10 of FFT round-off (1e-7 relative): ANY two correct implementations disagree there
-    #     by O(1) in the log domain (cuFFT vs pocketfft would too), and the embedding inherits it -- so the composition is
-    #     only asserted where no frame sits near the 1e-10 floor.
-    mel_min = omel.mel_spectrogram(audio * np.float32(spec.AUDIO_SCALE)).reshape(40, -1).min(axis=1)
-    good = mel_min > 0.0
-    assert good.sum() >= 24
-    err = np.abs(got[good] - want[good]).max() / np.abs(want).max()
-    assert err < tol, err
-    # (2) stage-wise on ALL clips: the device's own augmented audio (within 1e-4 of the oracle's) pushed through the
+    # (1) end to end, every clip, every well-conditioned slot
+    good = _slot_mask(omel.mel_spectrogram(audio * np.float32(spec.AUDIO_SCALE)))
+    masked = 1.0 - good.mean()
+    err = np.abs(got - want).max(axis=2) / np.abs(want).max()
+    print(f"[e2e {precision}] masked slots {masked:.1%} (clips with a masked slot: {(~good).any(axis=1).mean():.1%}); "
+          f"max err good {err[good].max():.2e}, max err masked {err[~good].max() if (~good).any() else 0.0:.2e}")
+    assert good.any(axis=1).sum() >= n // 2 and masked < 0.6, masked
+    assert err[good].max() < tol, err[good].max()
+    # (2) stage-wise on ALL clips and slots: the device's own augmented audio (within 1e-4 of the oracle's) pushed through the
     #     oracle's mel + embedding must reproduce the device's embeddings.
     from heybuddy_b200.pipeline import RaggedClips
     chunk = pipe.upload(RaggedClips.from_list(clips), table)
@@ -124,7 +125,15 @@ def test_cache_reuse_and_extend(cuda_device, tmp_path):
     assert len(pos2) == 24 and os.path.getmtime(tmp_path / "hello_world.npy") == mtime
     pos3, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 40, 16, **kw)
     assert len(pos3) == 40
-    np.testing.assert_array_equal(np.asarray(pos3.precalculated)[:24], first)
+    ext = np.asarray(pos3.precalculated).copy()
+    np.testing.assert_array_equal(ext[:24], first)
+    # the appended rows are NEW samples (not a replay of rows 0..15) and the extended file equals a single-shot 40-row generation
+    assert not np.array_equal(ext[24:40], first[:16])
+    single = TrainingFeaturesGenerator.default("Hello World", device_id=0, use_autoconfigure=False, augment_batch_size=8)(40)
+    np.testing.assert_array_equal(ext, single)
+    # train / test / validation splits do not share utterances or draws
+    tst_p, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 8, 8, testing=True, **kw)
+    assert not np.array_equal(np.asarray(tst_p.precalculated), first[:8])
     val = TrainingFeaturesGenerator.get_validation_features("Hello World", 8, **kw)
     assert len(val) == 8 and os.path.exists(tmp_path / "hello_world_val.npy")
     tst, _ = TrainingFeaturesGenerator.get_training_features("Hello World", 8, 8, testing=True, **kw)
@@ -171,15 +180,11 @@ def test_full_size_chunk_invariance_and_determinism(cuda_device):
     table = aug.next_table(clips.lengths)
 
     def parts(sub):
-        out, bps = [], sub // 128
-        for lo in range(0, len(table.batches), bps):
-            d = DrawTable(cfg=table.cfg, seed=table.seed)
-            d.batches, d.noise_clip_cursor, d.rir_index = table.batches[lo:lo + bps], table.noise_clip_cursor[lo:lo + bps], table.rir_index[lo:lo + bps]
-            out.append(d)
-        return out
+        bps = sub // 128
+        return [table.slice(lo, min(lo + bps, table.n_batches)) for lo in range(0, table.n_batches, bps)]
 
     whole, _, _ = pipe.featurize_host(clips, parts(n), n)
-    again, _, _ = pipe.featurize_host(clips, parts(n), n)
+    again, _, _ = pipe.featurize_host(clips, table, n)              # the whole table, sliced per chunk by the pipeline
     pieces, _, _ = pipe.featurize_host(clips, parts(1024), 1024)
     assert whole.shape == (n, 16, 96) and np.isfinite(whole).all()
     assert np.array_equal(whole, again)
@@ -190,9 +195,7 @@ def test_full_size_chunk_invariance_and_determinism(cuda_device):
         g = plain[0]
         d = table.batches[g]
         sub = clips.slice(g * 128, (g + 1) * 128)
-        one = DrawTable(cfg=table.cfg, seed=table.seed)
-        one.batches, one.noise_clip_cursor, one.rir_index = [d], [table.noise_clip_cursor[g]], [table.rir_index[g]]
-        _, audio = pipe.run_device(pipe.upload(sub, one), keep_audio=True)
+        _, audio = pipe.run_device(pipe.upload(sub, table.slice(g, g + 1)), keep_audio=True)
         fixed = aug.fix_length_device([sub.samples[sub.offsets[i]:sub.offsets[i + 1]] for i in range(len(sub))], d.pad_before)
         assert torch.allclose(audio, fixed * d.gain_linear, rtol=1e-6, atol=1e-7)
 
