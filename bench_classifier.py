@@ -1,0 +1,388 @@
+"""
+bench.py --workload classifier | stream  (BASELINE.json configs[3] and configs[4]; the default workload is bench.py's own).
+
+classifier  "wake-word classifier three-stage training on precomputed synthetic embeddings (16x96 windows), batch 4096"
+            (SURVEY.md 8d config 4): embeddings f32 [N,16,96], positives randn + 0.5 u, negatives randn, batch 4096 =
+            186 positive + 186 adversarial + 3724 negative rows (the 50:50:1000 ratio of constants.py:99-103), the reference's
+            schedule (trainer.py:918-926: lr x0.5, steps x2, batch x0.5 per stage).  One step = one fused training step
+            (forward, high-loss selection, weighted BCE, backward, Adam: WakeWordMLPModel.train_step = hb_mlp_train_step) at the
+            stage-1 batch of 4096.  value = steps/s with the batches resident in HBM; e2e = WakeWordTrainer.train_epoch fed host
+            batches (pinned H2D of x and y and a D2H of the step's loss inside the timed region); the line also carries ms/step at
+            the three stage batch sizes and the projected wall time of the full 5000/10000/20000-step schedule.
+            cpu_baseline = the reference's own WakeWordMLPModel (baseline/_ref copy) + the trainer's own selection / loss lines +
+            torch.optim.Adam on the host cores.
+
+stream      "streaming sliding-window inference: 64 wake-word models evaluated concurrently over a 1 h synthetic audio stream"
+            (config 5): 57.6 M samples f32, step 1920, window 17280 -> 29 992 steps, browser semantics
+            (src/ts/src/hey-buddy.ts:382-469).  One step = one 5-minute segment of the stream through stream_predict (one mel +
+            fully-convolutional embedding pass, FIFO gather, hb_mlp_forward_multi = ONE stacked first-layer GEMM for all models).
+            value = stream-seconds per second with the audio resident in HBM; e2e = the same from pinned host audio with the
+            [64, steps] probabilities read back.  cpu_baseline = per-step oracle featurization + 64 oracle classifiers on a
+            bounded piece of the stream.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "MEASURED_PEAKS.json"
+    except Exception:
+        return {}, "fallback (B200_PROFILING.md): 6650 GB/s, 1590 TFLOP/s"
+
+
+def _dist():
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    return world, rank, local_rank, device, barrier, dist
+
+
+def _max_over_ranks(values, world, dist, device):
+    import torch
+
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+# --------------------------------------------------------------------------------------------------
+# classifier training (config 4)
+# --------------------------------------------------------------------------------------------------
+POS, ADV, NEG = 186, 186, 3724
+BATCH = POS + ADV + NEG          # 4096
+CLS_POOL = 8                     # distinct batches cycled (8 x 25 MB > L2)
+
+
+def make_batch(rng, scale=1.0):
+    """(x f32 [B,16,96], y i64 [B]) with the config's composition; positives share a fixed direction."""
+    b = max(8, int(BATCH * scale))
+    pos = max(1, int(POS * scale))
+    u = np.random.Generator(np.random.PCG64(4001)).standard_normal((1, 16, 96)).astype(np.float32)
+    x = rng.standard_normal((b, 16, 96)).astype(np.float32)
+    x[:pos] += 0.5 * u
+    y = np.zeros(b, dtype=np.int64)
+    y[:pos] = 1
+    return x, y
+
+
+def cpu_classifier_steps_per_s(threads, steps=12):
+    """The reference's WakeWordMLPModel + the trainer's own step lines (trainer.py:405-462) on the host cores."""
+    import torch
+
+    torch.set_num_threads(threads)
+    kind = "port"
+    model = None
+    try:
+        from oracle import refarm
+
+        refarm.load()
+        from heybuddy.wakeword import WakeWordMLPModel as RefModel  # reference
+
+        model = RefModel()
+        kind = "reference"
+    except Exception:
+        from oracle import classifier as ocls  # noqa: F401
+
+    rng = np.random.Generator(np.random.PCG64(1))
+    x, y = make_batch(rng)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    if model is None:
+        return None, kind
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad()
+        y_pred = model(xt)
+        thr, neg_w = 1e-4, 1.0
+        neg = (yt == 0) & (y_pred.squeeze() >= thr)
+        pos = (yt == 1) & (y_pred.squeeze() < 1 - thr)
+        ysel = torch.cat([yt[neg], yt[pos]]).to(torch.float32)
+        psel = torch.cat([y_pred[neg], y_pred[pos]])
+        w = torch.ones(ysel.shape[0]) * neg_w
+        w[ysel == 1] = 1.0
+        loss = torch.nn.functional.binary_cross_entropy(psel, ysel.unsqueeze(1), w.unsqueeze(1))
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return steps / (time.perf_counter() - t0), kind
+
+
+def run_classifier(args):
+    import torch
+
+    import bench
+    from heybuddy_b200 import _native
+    from heybuddy_b200.trainer import WakeWordTrainer
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        threads = os.cpu_count() or 1
+        v, kind = cpu_classifier_steps_per_s(threads, steps=max(args.steps, 4))
+        print(json.dumps({
+            "impl": "reference", "metric": "classifier training steps/sec (batch 4096)", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v if v else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "classifier training (BASELINE configs[3])", "batch": BATCH},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": kind,
+                             "sample": "reference WakeWordMLPModel + the trainer's selection / weighted-BCE lines + torch.optim.Adam, batch 4096"},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+
+    world, rank, local_rank, device, barrier, dist = _dist()
+    lib = _native.load()
+    rng = np.random.Generator(np.random.PCG64(4001 + rank))
+    model = WakeWordMLPModel(device_id=local_rank, seed=5002)
+    steps = max(args.steps, 1)
+
+    def timed(scale, k, warm):
+        pool = [make_batch(rng, scale) for _ in range(CLS_POOL)]
+        dev = [(torch.from_numpy(x).to(device), torch.from_numpy(y).to(device)) for x, y in pool]
+        for i in range(warm):
+            model.train_step(*dev[i % CLS_POOL], 1e-3, 1.0, 1e-4)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.hb_launch_count()
+        a.record()
+        for i in range(k):
+            model.train_step(*dev[(warm + i) % CLS_POOL], 1e-3, 1.0, 1e-4)
+        b.record()
+        barrier()
+        return a.elapsed_time(b) / k, (lib.hb_launch_count() - l0), pool
+
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
+    ms, launches, pool = timed(1.0, steps, max(args.warmup, 3))
+    stage_ms = {"4096": ms, "2048": timed(0.5, steps, 3)[0], "1024": timed(0.25, steps, 3)[0]}
+    # e2e: the trainer's own loop over host batches (pinned H2D of x / y per step, the loss read back every step)
+    pinned = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()) for x, y in pool]
+
+    def batches(n):
+        for i in range(n):
+            yield pinned[i % CLS_POOL]
+
+    trainer = WakeWordTrainer(model=model, learning_rate=1e-3, distributed=False)
+    trainer.train_epoch(batches(max(args.warmup, 3)), num_steps=max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    trainer.train_epoch(batches(steps), num_steps=steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms, e2e_ms = _max_over_ranks([ms, e2e_s * 1e3 / steps], world, dist, device)
+    if rank == 0:
+        peaks, src = _peaks()
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        x_bytes = BATCH * 1536 * 4
+        alg_bytes = x_bytes + 4 * 256417 * 4          # input + parameters, gradients, two Adam moments
+        flops = 3 * 2 * BATCH * (1536 * 128 + 64 * 96 + 2 * (96 * 128 + 64 * 96) + 96 * 128 + 64)   # fwd + 2 x bwd
+        line = {
+            "metric": "classifier training steps/sec (batch 4096)", "value": world * 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "wake-word classifier three-stage training on precomputed synthetic embeddings (BASELINE configs[3])",
+                       "batch": BATCH, "composition": [POS, ADV, NEG], "l2_policy": f"{CLS_POOL} distinct batches cycled (> L2)",
+                       "replicas": "independent replicas per GPU (data-parallel training with gradient all-reduce: heybuddy_b200/dp.py)"},
+            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": x_bytes + BATCH * 8, "d2h_bytes_per_step": 16,
+                    "api": "WakeWordTrainer.train_epoch over host batches (pinned x / y H2D every step, loss / n_selected / stepped read back every step)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "hb_mlp_train_step (whole step)", "bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
+                         "algorithmic_bytes_per_step": alg_bytes, "flops_per_step": flops, "achieved_tflops_fp32": flops / (ms * 1e-3) / 1e12,
+                         "note": "fp32 CUDA-core step (logits must stay within 1e-3 of the reference): FLOP-bound on the fp32 pipes long before the 29 MB of "
+                                 "algorithmic traffic matters; nominal fp32 FMA peak 74 TFLOP/s"},
+            "stages": {"ms_per_step_by_batch": stage_ms,
+                       "schedule_projection_s": (5000 * stage_ms["4096"] + 10000 * stage_ms["2048"] + 20000 * stage_ms["1024"]) * 1e-3,
+                       "schedule": "steps 5000 / 10000 / 20000, batch 4096 / 2048 / 1024, lr 1e-3 x {1, 1/2, 1/4} (trainer.py:918-926)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v, kind = cpu_classifier_steps_per_s(threads)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": kind,
+                                    "sample": "12 steps at batch 4096: reference WakeWordMLPModel (baseline/_ref copy) + the trainer's own selection / "
+                                              "weighted-BCE lines + torch.optim.Adam on the host cores"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# streaming inference (config 5)
+# --------------------------------------------------------------------------------------------------
+N_MODELS = 64
+SEGMENT_S = 300           # one step = five minutes of stream
+
+
+def run_stream(args):
+    import torch
+
+    import bench
+    from heybuddy_b200 import _native, spec
+    from heybuddy_b200.embeddings import DEFAULT_EMBED_PRECISION, SpeechEmbeddings
+    from heybuddy_b200.streaming import num_stream_steps, stream_predict
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    metric, unit = f"stream-seconds/sec, {N_MODELS} wake-word models", "stream-s/s"
+    seg = SEGMENT_S * 16000
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        v, cores, what = cpu_stream_rate()
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": SEGMENT_S / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "streaming inference (BASELINE configs[4])", "models": N_MODELS},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": what},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+
+    world, rank, local_rank, device, barrier, dist = _dist()
+    lib = _native.load()
+    precision = args.precision or DEFAULT_EMBED_PRECISION
+    speech = SpeechEmbeddings(device_id=local_rank, precision=precision)
+    models = [WakeWordMLPModel(device_id=local_rank, seed=5002 + i) for i in range(N_MODELS)]
+    golden = os.path.join(ROOT, "tests", "golden", "classifier_hey_buddy.npz")
+    if os.path.exists(golden):      # model 0 = the reference's trained hey-buddy weights (src/ts/models/hey-buddy.onnx)
+        with np.load(golden) as z:
+            models[0].load_state_dict({k[7:]: z[k] for k in z.files if k.startswith("param::")})
+    steps = max(args.steps, 1)
+    g = torch.Generator().manual_seed(5001 + rank)
+    pool = [(0.1 * torch.randn(seg + spec.AUDIO_WINDOW, generator=g)).clamp(-1, 1).pin_memory() for _ in range(3)]   # > L2 each (19 MB ... x3)
+    pool_dev = [p.to(device) for p in pool]
+
+    def run(audio):
+        return stream_predict(models, audio, speech=speech)
+
+    for i in range(max(args.warmup, 3)):
+        run(pool_dev[i % 3])
+    barrier()
+    sampler = bench.ClockSampler(local_rank)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.hb_launch_count()
+    a.record()
+    for i in range(steps):
+        probs = run(pool_dev[i % 3])
+    b.record()
+    barrier()
+    launches = lib.hb_launch_count() - l0
+    ms = a.elapsed_time(b) / steps
+    # stage split of one segment
+    t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    from heybuddy_b200.streaming import stream_step_embeddings
+    from heybuddy_b200.wakeword import MultiWakeWordModel
+    t[0].record()
+    emb = stream_step_embeddings(speech, pool_dev[0])
+    t[1].record()
+    n = emb.shape[0]
+    idx = torch.arange(n - 3, device=device)[:, None] + torch.arange(4, device=device)[None, :]
+    MultiWakeWordModel(models)(emb[idx].reshape(n - 3, 16, spec.EMB_DIM).contiguous())
+    t[2].record()
+    barrier()
+    feat_ms, cls_ms = t[0].elapsed_time(t[1]), t[1].elapsed_time(t[2])
+    # e2e: pinned host audio in, probabilities out
+    run(pool[0]).cpu()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        out = run(pool[i % 3]).cpu()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    clocks = sampler.stop()
+    ms, e2e_ms = _max_over_ranks([ms, e2e_ms], world, dist, device)
+    n_steps = num_stream_steps(pool[0].numel())
+    if rank == 0:
+        peaks, src = _peaks()
+        flops = 2.0 * (n_steps - 3) * N_MODELS * (1536 * 128 + 64 * 96 + 2 * (96 * 128 + 64 * 96) + 96 * 128 + 64)
+        seg_seconds = pool[0].numel() / 16000.0
+        line = {
+            "metric": metric, "value": world * seg_seconds / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (embed), f32 (mel, classifiers)" if precision == "f16" else "f32", "data": "synthetic",
+            "config": {"workload": "streaming sliding-window inference: 64 wake-word models over a synthetic stream (BASELINE configs[4]); one step = one "
+                                   f"{SEGMENT_S} s segment ({n_steps} window steps of 1920 samples); a 1 h stream = 12 steps",
+                       "models": N_MODELS, "embed_precision": precision, "l2_policy": "3 distinct segments cycled"},
+            "e2e": {"value": world * seg_seconds / (e2e_ms * 1e-3), "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": pool[0].numel() * 4,
+                    "d2h_bytes_per_step": int(out.numel()) * 4, "api": "stream_predict(models, pinned host audio) -> probabilities [64, steps] on the host"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "hb_mlp_forward_multi (stacked first-layer GEMM + batched remainder)", "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
+                         "unit": "GB/s", "frac": None, "traffic": None, "peak_source": src, "classifier_flops_per_step": flops,
+                         "classifier_tflops_fp32": flops / (cls_ms * 1e-3) / 1e12,
+                         "note": "fp32 CUDA-core GEMMs: FLOP-bound (nominal fp32 FMA peak 74 TFLOP/s), not HBM-bound"},
+            "stages": {"featurize_ms": feat_ms, "classifiers_ms": cls_ms, "one_hour_projection_s": 3600.0 / (seg_seconds / (ms * 1e-3))},
+            "output_checksum": float(probs.mean().item()),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, what = cpu_stream_rate()
+            line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": what}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_stream_rate(seconds=20.0):
+    """Browser semantics on the host cores: per 1920-sample step, mel + 4 embeddings of the last 17280 samples, then 64 classifiers."""
+    import torch
+
+    from heybuddy_b200 import spec
+    from oracle import classifier as ocls, embed as oembed, mel as omel
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rng = np.random.Generator(np.random.PCG64(5001))
+    n = int(seconds * 16000)
+    stream = (0.1 * rng.standard_normal(n)).clip(-1, 1).astype(np.float32)
+    weights = spec.init_embedding_weights()
+    params = [spec.init_classifier_weights(5002 + i) for i in range(N_MODELS)]
+    t0 = time.perf_counter()
+    fifo = []
+    for start in spec.audio_window_starts(n):
+        m = omel.mel_spectrogram(stream[None, start:start + spec.AUDIO_WINDOW] * np.float32(spec.AUDIO_SCALE), dtype=np.float32)[0]
+        wins = np.stack([m[o:o + 76] for o in (0, 8, 16, 24)])[..., None]
+        fifo.append(oembed.speech_embedding_model(wins, weights))
+        if len(fifo) >= 4:
+            x = np.concatenate(fifo[-4:])[None]
+            for p in params:
+                ocls.forward(x, p, dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return seconds / dt, threads, (f"{seconds:.0f} s of stream: per-step oracle mel + 4 embedding windows (torch-CPU convs) + {N_MODELS} oracle classifiers "
+                                  "(numpy), browser semantics hey-buddy.ts:382-469")
+
+
+def main(args):
+    os.environ.setdefault("HEYBUDDY_B200_ALLOW_RANDOM_INIT", "1")
+    if args.workload == "classifier":
+        run_classifier(args)
+    else:
+        run_stream(args)

@@ -92,6 +92,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_mlp_grads_copy": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
         "hb_mlp_adam": (c_int, [c_vp, c_f, c_vp, c_vp]),
         "hb_mlp_get_grads": (c_int, [c_vp, c_vp, c_i64]),
+        "hb_mlp_multi_workspace_bytes": (c_i64, [c_int, c_int]),
         "hb_mlp_forward_multi": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     }
     for name, (res, args) in sig.items():

@@ -467,12 +467,217 @@ extern "C" int hb_mlp_forward(const hb_mlp_model* m, const float* x_dev, float* 
     return HB_OK;
 }
 
+// ---- config 5: M models on the same inputs, one launch chain --------------------------------------------------------------
+// The models differ in every parameter, including norm_in's affine -- but LN(x) = xhat * gamma + beta with xhat = (x - mu) * rstd
+// shared by all of them, so gamma folds into the first-layer weights and beta into their bias:
+//     W'_m[n][k] = W_m[n][k] * gamma_m[k],   b'_m[n] = b_m[n] + sum_k W_m[n][k] * beta_m[k]
+// and the 2 M first-layer products (hidden and gate of every model; 97 % of a forward pass's FLOPs) become ONE stacked GEMM
+// xhat[B,1536] x W'[M*128,1536]^T that reads the input once.  The 96-wide remainder of every model runs as GEMMs batched over the
+// models (blockIdx.z = model).  The fold is redone on every call (it reads the models' live parameters; 1 MB per model).
+namespace hb {
+
+constexpr int kMaxPack = 64;
+struct PtrPack { const float* p[kMaxPack]; };
+
+// xhat = (x - mean) * rstd, one warp per row (LayerNorm without the affine)
+__global__ void xhat_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float* xr = x + (int64_t)row * D;
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) s += xr[i];
+    const float mu = warp_sum(s) / D;
+    float v = 0.f;
+    for (int i = lane; i < D; i += 32) { const float d = xr[i] - mu; v += d * d; }
+    const float rs = rsqrtf(warp_sum(v) / D + kLnEps);
+    float* yr = y + (int64_t)row * D;
+    for (int i = lane; i < D; i += 32) yr[i] = (xr[i] - mu) * rs;
+}
+
+// one warp per stacked row (model m, n in [0,128): n < 64 hidden, else gate): W' row and b'
+__global__ void fold_first_layer_kernel(PtrPack pk, int m0, int M, StageOff L, float* __restrict__ Wst, float* __restrict__ bst) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M * 2 * kHid) return;
+    const int m = row / (2 * kHid), n = row - m * 2 * kHid;
+    const float* p = pk.p[m];
+    const float* W = p + (n < kHid ? L.hw + n * kIn : L.gw + (n - kHid) * kIn);
+    const float* gamma = p + L.ln_w;
+    const float* beta = p + L.ln_b;
+    float* out = Wst + ((int64_t)(m0 + m) * 2 * kHid + n) * kIn;
+    float acc = 0.f;
+    for (int k = lane; k < kIn; k += 32) {
+        const float w = W[k];
+        out[k] = w * gamma[k];
+        acc = fmaf(w, beta[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) bst[(int64_t)(m0 + m) * 2 * kHid + n] = acc + p[(n < kHid ? L.hb + n : L.gb + n - kHid)];
+}
+
+// HG [B][Mtot*128] -> A [Mtot][B][64] = silu(h) * g
+__global__ void gate_stacked_kernel(const float* __restrict__ hg, float* __restrict__ a, int B, int M) {
+    const int64_t n = (int64_t)B * M * kHid;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % kHid);
+        const int64_t r = i / kHid;
+        const int m = (int)(r % M);
+        const int64_t b = r / M;
+        const float hv = hg[(b * M + m) * 2 * kHid + j], gv = hg[(b * M + m) * 2 * kHid + kHid + j];
+        a[((int64_t)m * B + b) * kHid + j] = hv / (1.f + expf(-hv)) * gv;
+    }
+}
+
+// LayerNorm with per-model affine: x, y [M][B][D]; blockIdx.y = model
+__global__ void ln_fwd_batched_kernel(const float* __restrict__ x, PtrPack pk, int w_off, int b_off, float* __restrict__ y, int B, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, m = blockIdx.y;
+    if (row >= B) return;
+    const float* w = pk.p[m] + w_off;
+    const float* b = pk.p[m] + b_off;
+    const float* xr = x + ((int64_t)m * B + row) * D;
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) s += xr[i];
+    const float mu = warp_sum(s) / D;
+    float v = 0.f;
+    for (int i = lane; i < D; i += 32) { const float d = xr[i] - mu; v += d * d; }
+    const float rs = rsqrtf(warp_sum(v) / D + kLnEps);
+    float* yr = y + ((int64_t)m * B + row) * D;
+    for (int i = lane; i < D; i += 32) yr[i] = (xr[i] - mu) * rs * w[i] + b[i];
+}
+
+// y[m] [B][N] = x[m] [B][K] W_m[N][K]^T + b_m, batched over the models (blockIdx.z = model); same tile loop as gemm_kernel
+__global__ void __launch_bounds__(256) linear_batched_kernel(const float* __restrict__ X, PtrPack pk, int w_off, int b_off,
+                                                             float* __restrict__ Y, int B, int N, int K) {
+    __shared__ float As[kTk][kTile + 1];
+    __shared__ float Bs[kTk][kTile + 1];
+    const int m = blockIdx.z;
+    const float* A = X + (int64_t)m * B * K;
+    const float* W = pk.p[m] + w_off;
+    const float* bias = pk.p[m] + b_off;
+    float* C = Y + (int64_t)m * B * N;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += kTk) {
+        for (int i = threadIdx.x; i < kTile * kTk; i += 256) {
+            const int k = i % kTk, r = i / kTk;
+            As[k][r] = (m0 + r < B && k0 + k < K) ? A[(int64_t)(m0 + r) * K + k0 + k] : 0.f;
+            Bs[k][r] = (n0 + r < N && k0 + k < K) ? W[(int64_t)(n0 + r) * K + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTk; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gm = m0 + ty + 16 * i, gn = n0 + tx + 16 * j;
+            if (gm < B && gn < N) C[(int64_t)gm * N + gn] = acc[i][j] + bias[gn];
+        }
+}
+
+struct MultiWs {
+    float *xhat, *Wst, *bst, *hg, *a, *o, *u, *h, *g;
+    float* part;
+};
+static int64_t carve_multi(MultiWs* w, float* base, int M, int B) {
+    int64_t off = 0;
+    auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += (n + 63) & ~63ll; return p; };
+    w->xhat = take((int64_t)B * kIn);
+    w->Wst = take((int64_t)M * 2 * kHid * kIn);
+    w->bst = take((int64_t)M * 2 * kHid);
+    w->hg = take((int64_t)B * M * 2 * kHid);
+    w->a = take((int64_t)M * B * kHid);
+    w->o = take((int64_t)M * B * kDim);
+    w->u = take((int64_t)M * B * kDim);
+    w->h = take((int64_t)M * B * kHid);
+    w->g = take((int64_t)M * B * kHid);
+    w->part = take(kPartFloats);
+    return off;
+}
+
+}  // namespace hb
+
+extern "C" int64_t hb_mlp_multi_workspace_bytes(int M, int B) {
+    if (M < 0 || B < 0) return HB_ERR_INVALID;
+    MultiWs w;
+    return carve_multi(&w, nullptr, M, B) * (int64_t)sizeof(float) + 256;
+}
+
 extern "C" int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const float* x_dev, float* prob_dev, int B,
                                     void* workspace_dev, int64_t workspace_bytes, void* stream) {
-    HB_REQUIRE(models && M >= 0, "hb_mlp_forward_multi: bad argument");
-    for (int i = 0; i < M; ++i) {
-        int rc = hb_mlp_forward(models[i], x_dev, prob_dev + (int64_t)i * B, B, workspace_dev, workspace_bytes, stream);
-        if (rc) return rc;
+    HB_REQUIRE(models && M >= 0 && B >= 0, "hb_mlp_forward_multi: bad argument");
+    if (M == 0 || B == 0) return HB_OK;
+    HB_REQUIRE(x_dev && prob_dev && workspace_dev, "hb_mlp_forward_multi: null pointer");
+    HB_REQUIRE(workspace_bytes >= hb_mlp_multi_workspace_bytes(M, B), "hb_mlp_forward_multi: workspace too small (hb_mlp_multi_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MultiWs w;
+    carve_multi(&w, reinterpret_cast<float*>(workspace_dev), M, B);
+    int rc;
+    // 1. shared normalised input
+    xhat_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x_dev, w.xhat, B, kIn);
+    HB_LAUNCHED();
+    // 2. fold norm_in into the stacked first layer (packs of up to 64 models per launch: the pointers travel as kernel arguments)
+    for (int m0 = 0; m0 < M; m0 += kMaxPack) {
+        PtrPack pk;
+        const int n = std::min(kMaxPack, M - m0);
+        for (int i = 0; i < n; ++i) {
+            HB_REQUIRE(models[m0 + i] != nullptr, "hb_mlp_forward_multi: null model %d", m0 + i);
+            pk.p[i] = models[m0 + i]->p;
+        }
+        fold_first_layer_kernel<<<ceil_div(n * 2 * kHid, 8), 256, 0, st>>>(pk, m0, n, kLayout.s[0], w.Wst, w.bst);
+        HB_LAUNCHED();
+    }
+    // 3. ONE stacked GEMM: hidden and gate pre-activations of every model
+    if ((rc = linear_fwd(w.xhat, w.Wst, w.bst, w.hg, B, M * 2 * kHid, kIn, st, w.part))) return rc;
+    const int64_t n_gate = (int64_t)B * M * kHid;
+    const int gate_grid = (int)std::min<int64_t>(ceil_div64(n_gate, 256), 2368);
+    gate_stacked_kernel<<<gate_grid, 256, 0, st>>>(w.hg, w.a, B, M);
+    HB_LAUNCHED();
+    // 4. the 96-wide remainder, batched over the models
+    for (int m0 = 0; m0 < M; m0 += kMaxPack) {
+        PtrPack pk;
+        const int n = std::min(kMaxPack, M - m0);
+        for (int i = 0; i < n; ++i) pk.p[i] = models[m0 + i]->p;
+        float* a = w.a + (int64_t)m0 * B * kHid;
+        float* o = w.o + (int64_t)m0 * B * kDim;
+        float* u = w.u + (int64_t)m0 * B * kDim;
+        float* h = w.h + (int64_t)m0 * B * kHid;
+        float* g = w.g + (int64_t)m0 * B * kHid;
+        const dim3 grid_o(ceil_div(kDim, kTile), ceil_div(B, kTile), n), grid_h(1, ceil_div(B, kTile), n);
+        linear_batched_kernel<<<grid_o, 256, 0, st>>>(a, pk, kLayout.s[0].ow, kLayout.s[0].ob, o, B, kDim, kHid);
+        HB_LAUNCHED();
+        for (int s = 1; s < kStages; ++s) {
+            const StageOff& L = kLayout.s[s];
+            ln_fwd_batched_kernel<<<dim3(ceil_div(B, 8), n), 256, 0, st>>>(o, pk, L.ln_w, L.ln_b, u, B, kDim);
+            HB_LAUNCHED();
+            linear_batched_kernel<<<grid_h, 256, 0, st>>>(u, pk, L.hw, L.hb, h, B, kHid, kDim);
+            HB_LAUNCHED();
+            linear_batched_kernel<<<grid_h, 256, 0, st>>>(u, pk, L.gw, L.gb, g, B, kHid, kDim);
+            HB_LAUNCHED();
+            const int64_t ng = (int64_t)n * B * kHid;
+            gate_fwd_kernel<<<(int)std::min<int64_t>(ceil_div64(ng, 256), 2368), 256, 0, st>>>(h, g, a, ng);
+            HB_LAUNCHED();
+            // stage 3's output is one logit per row: o is reused as [n][B][1]
+            const dim3 grid_out(ceil_div(L.out_dim, kTile), ceil_div(B, kTile), n);
+            linear_batched_kernel<<<grid_out, 256, 0, st>>>(a, pk, L.ow, L.ob, o, B, L.out_dim, kHid);
+            HB_LAUNCHED();
+        }
+        const int total = n * B;   // logits [n][B] contiguous
+        sigmoid_kernel<<<ceil_div(total, 256), 256, 0, st>>>(o, prob_dev + (int64_t)m0 * B, total);
+        HB_LAUNCHED();
     }
     return HB_OK;
 }

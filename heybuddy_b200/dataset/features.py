@@ -193,6 +193,7 @@ class TrainingFeaturesGenerator:
         self._generated = 0
         self._cursor_cache = {}   # (split seed) -> (batch index, noise cursor, rir cursor) of the furthest prefix computed so far
         self.last_h2d_bytes = self.last_d2h_bytes = 0
+        self.last_sink = ""
 
     @property
     def device(self):
@@ -344,12 +345,13 @@ class TrainingFeaturesGenerator:
         if not validation:
             self._cursor_cache[seed] = ((first_sample + num_samples + b - 1) // b, noise_cursor, rir_cursor)
 
-    def _run(self, first_sample: int, num_samples: int, sink_of, validation: bool, testing: bool) -> None:
+    def _run(self, first_sample: int, num_samples: int, sink_of, validation: bool, testing: bool, writer_threads: int = 4,
+             wait: bool = True) -> None:
         pipe, gen = self._pipeline(augment=not validation)
         b = self.augment_batch_size
         chunk = max(b, (self.chunk_clips // b) * b)
         self.last_h2d_bytes, self.last_d2h_bytes = pipe.featurize_stream(
-            self._items(first_sample, num_samples, sink_of, validation, testing), chunk)
+            self._items(first_sample, num_samples, sink_of, validation, testing), chunk, writer_threads=writer_threads, wait=wait)
 
     def generate(self, num_samples: int, sample_save_path: Optional[str] = None, augmented_sample_save_path: Optional[str] = None,
                  testing: bool = False, validation: bool = False, first_sample: Optional[int] = None) -> np.ndarray:
@@ -377,12 +379,14 @@ class TrainingFeaturesGenerator:
         return self.generate(num_samples, sample_save_path, augmented_sample_save_path, testing, validation)
 
     def generate_sharded(self, num_samples: int, path: str, barrier: Optional[Callable[[], None]] = None,
-                         validation: bool = False, testing: bool = False, writer_threads: int = 4) -> Tuple[int, int]:
+                         validation: bool = False, testing: bool = False, writer_threads: int = 4, defer: bool = False):
         """
         Multi-GPU form: this rank featurizes its contiguous block of augmentation batches and writes rows
         [lo*B, hi*B) of the shared ``.npy`` at ``path`` (rank 0 creates it).  Rows go from the pipeline's pinned D2H slots
         straight into the file (``pwrite`` from worker threads), overlapping the kernels of the following chunks.
-        Returns the row range written.
+        Returns the row range written -- or, with ``defer=True``, a ``finish()`` callable that waits for the last rows to reach
+        the file, closes it, runs the final barrier and returns the row range (lets the caller start the next file's kernels while
+        this one's tail is still being written: ``get_training_features`` does so for the positive / adversarial pair).
         """
         from heybuddy_b200.dataset.precalculated import NpyRowWriter
 
@@ -393,12 +397,36 @@ class TrainingFeaturesGenerator:
         lo_b, hi_b = shard_batches(n_batches, self.rank, self.world_size)
         lo, hi = lo_b * b, min(hi_b * b, num_samples)
         shape = (num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM)
-        with NpyRowWriter(path, shape, create=self.rank == 0, barrier=barrier) as writer:
+        writer = NpyRowWriter(path, shape, create=self.rank == 0, barrier=barrier)
+        mapped = None
+        try:
             if hi > lo:
-                self._run(lo, hi - lo, lambda r0, r1: (lambda a, z, rows, base=lo + r0: writer.write(base + a, rows)), validation, testing)
-        if barrier is not None:
-            barrier()
-        return lo, hi
+                # opt-in on memory-backed file systems: the D2H copies land in the file's own (registered) pages; otherwise rows go
+                # from the pipeline's pinned slots into the file with pwrite
+                mapped = writer.map_pinned(lo, hi, populate_threads=writer_threads)
+                self.last_sink = "pinned file mapping (D2H straight into the page cache)" if mapped is not None else "pwrite from pinned slots"
+                if mapped is not None:
+                    sink_of = lambda r0, r1: mapped[r0:r1]
+                else:
+                    sink_of = lambda r0, r1: (lambda a, z, rows, base=lo + r0: writer.write(base + a, rows))
+                self._run(lo, hi - lo, sink_of, validation, testing, writer_threads=writer_threads, wait=False)
+        except BaseException:
+            writer.close()
+            raise
+
+        def finish() -> Tuple[int, int]:
+            nonlocal mapped
+            try:
+                if self._pipe is not None:
+                    self._pipe[1].finish_stream()
+                mapped = None
+            finally:
+                writer.close()
+            if barrier is not None:
+                barrier()
+            return lo, hi
+
+        return finish if defer else finish()
 
     # -- reference classmethods ----------------------------------------------------------------------------------
     @classmethod
@@ -422,7 +450,7 @@ class TrainingFeaturesGenerator:
 
     @classmethod
     def _features(cls, name: str, want: int, directory: str, use_cache: bool, keep_in_memory: bool, make: Callable[[], "TrainingFeaturesGenerator"],
-                  **call_kwargs: Any) -> PrecalculatedDatasetIterator:
+                  defer: bool = False, **call_kwargs: Any):
         """
         Reuse ``<name>.npy`` when it has enough rows, otherwise generate the missing rows (features.py:686-760).  The
         reference concatenates old + new in memory and rewrites the whole file; here the new rows are appended in place
@@ -430,7 +458,7 @@ class TrainingFeaturesGenerator:
         """
         existing, have = cls._cached(name, directory, use_cache)
         if existing is not None and have >= want:
-            return existing
+            return (lambda: existing) if defer else existing
         gen = make()
         if have > 0:
             from heybuddy_b200.util.npy_append import AppendableNumpyArrayFile, AppendableNumpyHeaderInfo
@@ -442,7 +470,8 @@ class TrainingFeaturesGenerator:
             AppendableNumpyHeaderInfo.ensure_appendable(path, in_place=True)
             with AppendableNumpyArrayFile(path) as out:
                 out.append(new_rows)
-            return PrecalculatedDatasetIterator(name, directory=directory)
+            it = PrecalculatedDatasetIterator(name, directory=directory)
+            return (lambda: it) if defer else it
         # nothing cached: every rank streams its rows straight into `<name>.npy` (same bytes as the reference's np.save of the
         # whole array, precalculated.py:486, without ever holding the whole array)
         barrier = None
@@ -451,8 +480,13 @@ class TrainingFeaturesGenerator:
 
             assert dist.is_initialized(), "world_size > 1 needs an initialised torch.distributed process group (file barrier)"
             barrier = dist.barrier
-        gen.generate_sharded(want, os.path.join(directory, f"{name}.npy"), barrier=barrier, **call_kwargs)
-        return PrecalculatedDatasetIterator(name, directory=directory, use_mem_map=not keep_in_memory)
+        finish = gen.generate_sharded(want, os.path.join(directory, f"{name}.npy"), barrier=barrier, defer=True, **call_kwargs)
+
+        def open_it() -> PrecalculatedDatasetIterator:
+            finish()
+            return PrecalculatedDatasetIterator(name, directory=directory, use_mem_map=not keep_in_memory)
+
+        return open_it if defer else open_it()
 
     @classmethod
     def get_training_features(cls, wake_phrase: str, num_positive_samples: int, num_adversarial_samples: int, testing: bool = False,
@@ -461,11 +495,12 @@ class TrainingFeaturesGenerator:
         """(positive, adversarial) iterators over ``<name>.npy`` / ``<name>_adv.npy`` (features.py:628-838)."""
         directory = directory or LOCAL_DIR
         name = cls.get_wake_phrase_file_name(wake_phrase, testing=testing)
+        # the adversarial file's kernels start while the tail of the positive file is still on its way to the page cache
         positive = cls._features(name, num_positive_samples, directory, use_cache, keep_in_memory,
-                                 lambda: cls.default(wake_phrase, **kwargs), testing=testing)
+                                 lambda: cls.default(wake_phrase, **kwargs), defer=True, testing=testing)
         adversarial = cls._features(f"{name}_adv", num_adversarial_samples, directory, use_cache, keep_in_memory,
-                                    lambda: cls.default(wake_phrase, adversarial=True, **kwargs), testing=testing)
-        return positive, adversarial
+                                    lambda: cls.default(wake_phrase, adversarial=True, **kwargs), defer=True, testing=testing)
+        return positive(), adversarial()
 
     @classmethod
     def get_validation_features(cls, wake_phrase: str, num_positive_samples: int, use_cache: bool = True, save_samples: bool = False,

@@ -269,7 +269,7 @@ class FeaturizePipeline:
         h2d, d2h = self.featurize_stream([(clips, tables, out)], chunk_clips)
         return (out.numpy() if hasattr(out, "is_pinned") else out), h2d, d2h
 
-    def featurize_stream(self, items, chunk_clips: int, writer_threads: int = 4):
+    def featurize_stream(self, items, chunk_clips: int, writer_threads: int = 4, wait: bool = True):
         """
         Streaming form of :meth:`featurize_host`: ``items`` is an iterable (pulled lazily, e.g. a generator that fetches one
         super-batch of source clips at a time) of ``(clips, table, sink)`` host datasets.
@@ -278,13 +278,16 @@ class FeaturizePipeline:
         handed every finished row range (``rows``: f32 numpy view of a pinned slot, valid until the call returns; called from
         worker threads, possibly out of order).  The upload of the next chunk -- of the same or of the next item -- always
         overlaps the compute of the current one, so a long run pays the pipeline fill (first H2D) and drain (last D2H) once,
-        not once per item.  Returns (h2d_bytes, d2h_bytes).
+        not once per item.  Returns (h2d_bytes, d2h_bytes); with ``wait=False`` the call returns as soon as the last chunk is
+        enqueued and ``self.finish_stream()`` waits for the downloads and the sinks (lets the caller start the next dataset's
+        kernels while this one's rows are still being written).
         """
         import torch
 
         dev = self.device
         n_slots = self.slot_offsets.size
         b = self.augment.batch_size
+        self.finish_stream()          # a previous deferred call must have drained: it owns the pinned output slots
         assert chunk_clips % b == 0, "chunks are whole augmentation batches"
         for key in ("copy_stream", "d2h_stream"):
             if (key, 0) not in self._bufs:
@@ -303,6 +306,7 @@ class FeaturizePipeline:
         stage_events = [None] * N_SLOTS
         out_tasks = [None] * OUT_SLOTS
         wait_s = 0.0    # host time spent blocked on the device (the rest of the call is host work)
+        stats = {"items_s": 0.0, "stage_s": 0.0, "enqueue_s": 0.0, "wait_slot_s": 0.0, "wait_sink_s": 0.0, "sink_s": 0.0, "chunks": 0}
 
         def work_units():
             """(sink, clips of the item, lo, hi, table of the chunk) for every chunk of every item, items pulled lazily."""
@@ -375,11 +379,13 @@ class FeaturizePipeline:
 
         def deliver(sink, lo, hi, pin, done_ev):
             done_ev.synchronize()
+            t0 = time.perf_counter()
             rows = pin[:(hi - lo) * n_slots * spec.EMB_DIM].numpy().reshape(hi - lo, n_slots, spec.EMB_DIM)
             if isinstance(sink, np.ndarray):
                 np.copyto(sink[lo:hi], rows)
             else:
                 sink(lo, hi, rows)
+            stats["sink_s"] += time.perf_counter() - t0     # summed over the worker threads
 
         staged = deque()
         exhausted = False
@@ -387,17 +393,22 @@ class FeaturizePipeline:
         def fill():
             nonlocal exhausted
             while not exhausted and len(staged) < DEPTH:
+                t0 = time.perf_counter()
                 unit = next(units, None)
+                t1 = time.perf_counter()
+                stats["items_s"] += t1 - t0
                 if unit is None:
                     exhausted = True
                     break
                 staged.append(stage(unit))
+                stats["stage_s"] += time.perf_counter() - t1
 
         fill()
         k = -1
         while staged:
             k += 1
             chunk, meta_dev, ev, sink, lo, hi = staged.popleft()
+            t_enq = time.perf_counter()
             compute.wait_event(ev)
             chunk.samples.record_stream(compute)
             meta_dev.record_stream(compute)
@@ -417,6 +428,8 @@ class FeaturizePipeline:
                     t0 = time.perf_counter()
                     out_tasks[oslot].result()
                     wait_s += time.perf_counter() - t0
+                    stats["wait_sink_s"] += time.perf_counter() - t0
+                    t_enq += time.perf_counter() - t0
                 pin = pinned("out", oslot, emb.numel(), torch.float32)
                 with torch.cuda.stream(d2h_stream):
                     pin[:emb.numel()].copy_(emb.reshape(-1), non_blocking=True)
@@ -424,12 +437,26 @@ class FeaturizePipeline:
                     done.record(d2h_stream)
                 out_tasks[oslot] = self._writers.submit(deliver, sink, lo, hi, pin, done)
             del chunk, emb, meta_dev
+            stats["enqueue_s"] += time.perf_counter() - t_enq
+            stats["chunks"] += 1
             fill()
-        t0 = time.perf_counter()
-        for task in out_tasks:
-            if task is not None:
-                task.result()
-        d2h_stream.synchronize()
-        wait_s += time.perf_counter() - t0
-        self.last_stream_wait_s = wait_s   # host time spent blocked on the device / the sinks during the call (diagnostic)
+        def finish():
+            t0 = time.perf_counter()
+            for task in out_tasks:
+                if task is not None:
+                    task.result()
+            d2h_stream.synchronize()
+            stats["wait_s"] = wait_s + time.perf_counter() - t0
+            self.last_stream_wait_s = stats["wait_s"]   # host time spent blocked on the device / the sinks (diagnostic)
+
+        self.last_stats = stats            # host-side time breakdown of the call (diagnostic; bench.py prints it)
+        self._pending_finish = finish
+        if wait:
+            self.finish_stream()
         return h2d, d2h
+
+    def finish_stream(self) -> None:
+        """Waits for the downloads and sink tasks of the last ``featurize_stream(..., wait=False)``."""
+        fin, self._pending_finish = getattr(self, "_pending_finish", None), None
+        if fin is not None:
+            fin()

@@ -52,7 +52,7 @@ def stream_step_embeddings(speech: SpeechEmbeddings, audio, strips_per_call: int
     # pad the tail so the last (partial) strip is addressable; its extra steps are dropped below
     need = (n_strips - 1) * k * spec.AUDIO_STRIDE + strip_samples
     if need > audio.numel():
-        audio = torch.cat([audio, torch.zeros(need - audio.numel(), dtype=torch.float32)])
+        audio = torch.cat([audio, torch.zeros(need - audio.numel(), dtype=torch.float32, device=audio.device)])
     for lo in range(0, n_strips, strips_per_call):
         hi = min(n_strips, lo + strips_per_call)
         # overlapping strips as a strided view of the stream (no copy on the host), one H2D per call

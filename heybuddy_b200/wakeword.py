@@ -318,7 +318,9 @@ class MultiWakeWordModel:
     """
     BASELINE config 5: N wake-word models evaluated on the same rolling ``[16, 96]`` embedding buffer
     (browser semantics, src/ts/src/hey-buddy.ts:350-413; the Python reference runs one thread per model and
-    re-featurizes per model, util/model_util.py:62-93).  Featurize once, then ``hb_mlp_forward_multi``.
+    re-featurizes per model, util/model_util.py:62-93).  Featurize once, then ``hb_mlp_forward_multi``: ONE stacked
+    ``[M*128, 1536]`` first-layer GEMM for all the models (norm_in folded into the weights) + the 96-wide remainder batched over
+    the models -- a launch chain whose length does not depend on M.
     """
 
     def __init__(self, models: List[WakeWordMLPModel]):
@@ -336,7 +338,7 @@ class MultiWakeWordModel:
         lib = _native.load()
         handles = (ctypes.c_void_p * m)(*[mod._ensure() for mod in self.models])
         with torch.cuda.device(x.device):
-            nbytes = lib.hb_mlp_workspace_bytes(b, 0)
+            nbytes = lib.hb_mlp_multi_workspace_bytes(m, b)
             if self._ws is None or self._ws.numel() < nbytes:
                 self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
             _native.check(lib.hb_mlp_forward_multi(handles, m, x.data_ptr(), out.data_ptr(), b, self._ws.data_ptr(), self._ws.numel(),

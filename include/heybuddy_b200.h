@@ -193,7 +193,11 @@ int hb_mlp_adam(hb_mlp_model* m, float lr, const float* stats_dev, void* stream)
 /* Gradients of the last hb_mlp_train_step / hb_mlp_backward (packed like params), for parity tests. */
 int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats);
 
-/* config 5: M models evaluated on the same inputs.  x_dev [B][1536] -> prob_dev [M][B]. */
+/* config 5 (src/ts/src/hey-buddy.ts:350-413: every wake-word model runs on the SAME [16, 96] buffer): M models evaluated on
+ * the same inputs in one launch chain whose length does not depend on M -- the shared (x - mean) * rstd, norm_in's affine folded
+ * into ONE stacked [M*128, 1536] first-layer GEMM (hidden + gate of every model), then the 96-wide remainder batched over the
+ * models.  x_dev [B][1536] -> prob_dev [M][B].  The models' live parameters are read on every call. */
+int64_t hb_mlp_multi_workspace_bytes(int M, int B);
 int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const float* x_dev, float* prob_dev, int B,
                          void* workspace_dev, int64_t workspace_bytes, void* stream);
 

@@ -147,7 +147,7 @@ def augment_table(clips, table, noise_stream: Optional[np.ndarray], noise_clip_s
     return np.concatenate(out)
 
 
-def well_conditioned_slots(mel_true: np.ndarray, floor_db: float = 80.0) -> np.ndarray:
+def well_conditioned_slots(mel_true: np.ndarray, floor_db: float = 80.0, num_samples: int = spec.CLIP_SAMPLES) -> np.ndarray:
     """
     ``[n, F, 32]`` reference-scale log-mel (``log10(P) + 2``, floor -8) -> bool ``[n, slots]``: True where the slot's 76-frame
     window holds no (frame, mel bin) within ``floor_db`` of the 1e-10 power floor.  log10 of digital silence / of reverb tails that
@@ -155,6 +155,6 @@ def well_conditioned_slots(mel_true: np.ndarray, floor_db: float = 80.0) -> np.n
     """
     thr = np.log10(spec.MEL_FLOOR) + floor_db / 10.0 + spec.MEL_POST_ADD
     frame_min = mel_true.min(axis=2)
-    n_samples = (mel_true.shape[1] - 1) * spec.HOP + spec.N_FFT
-    offs = spec.embedding_frame_offsets(n_samples)
+    assert mel_true.shape[1] == spec.mel_frames(num_samples), (mel_true.shape, num_samples)
+    offs = spec.embedding_frame_offsets(num_samples)
     return np.stack([frame_min[:, o:o + spec.EMB_WINDOW].min(axis=1) > thr for o in offs], axis=1)

@@ -175,14 +175,15 @@ def test_colored_bases_device_matches_host_restatement(cuda_device):
     f_decay = np.array([0.0, -1.0, 2.0, 0.37, 1.5], dtype=np.float32)
     seed = 0x1234_5678_9ABC_DEF0
     out = torch.empty((len(ids), 16000), dtype=torch.float32, device="cuda")
-    _native.check(_native.load().hb_colored_bases(seed, torch.from_numpy(ids).cuda().data_ptr(), torch.from_numpy(f_decay).cuda().data_ptr(),
-                                                  len(ids), out.data_ptr(), _native.stream_ptr(out.device)), "hb_colored_bases")
+    ids_d, fd_d = torch.from_numpy(ids).cuda(), torch.from_numpy(f_decay).cuda()      # keep the device copies alive across the call
+    _native.check(_native.load().hb_colored_bases(seed, ids_d.data_ptr(), fd_d.data_ptr(), len(ids), out.data_ptr(),
+                                                  _native.stream_ptr(out.device)), "hb_colored_bases")
     got = out.cpu().numpy()
     for i, (g, fd) in enumerate(zip(ids, f_decay)):
         want = colored_noise_base(gaussian_pattern(seed, int(g)), float(fd))
         np.testing.assert_allclose(want, oaug.colored_noise_base(gaussian_pattern(seed, int(g)), float(fd)), atol=1e-6)
         assert abs(np.sqrt(np.mean(got[i].astype(np.float64) ** 2)) - 1.0) < 1e-5
-        assert np.abs(got[i] - want).max() < 2e-5 * np.abs(want).max(), (i, np.abs(got[i] - want).max())
+        assert np.abs(got[i] - want).max() < 5e-6 * np.abs(want).max(), (i, np.abs(got[i] - want).max())
 
 
 def test_unsupported_transforms_raise():

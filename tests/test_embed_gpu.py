@@ -15,18 +15,23 @@ pytestmark = pytest.mark.gpu
 # Tolerances (north star: embeddings within 1e-3 relative; a stated tolerance for reduced-precision operands).
 #   fp32  CUDA-core parity mode: max|err| <= 1e-4 * max|ref|   (observed ~1e-6)
 #   f16   tcgen05, fp16 operands (11-bit mantissa = TF32-class) with fp32 accumulation:
-#         ||err||_2 <= 1e-3 * ||ref||_2  and  max|err| <= 2e-3 * max|ref|
-#         (CPU emulation of the operand rounding gives 3.2e-4 / 6.2e-4 on white-noise clips)
-TOL = {"fp32": dict(max=1e-4, l2=1e-4), "f16": dict(max=2e-3, l2=1e-3)}
+#         ||err||_2 <= 5e-4 * ||ref||_2  and  max|err| <= 1e-3 * max|ref|   -- the north star's embedding tolerance itself
+#         (measured on 256 clips, scripts/f16_error.py: 2.9e-4 / 5.7e-4 .. 7.1e-4; CPU emulation of the operand rounding 3.2e-4 / 6.2e-4)
+TOL = {"fp32": dict(max=1e-4, l2=1e-4), "f16": dict(max=1e-3, l2=5e-4)}
+#   intermediate activations of the f16 mode (per-layer parity hook): the relative error peaks in the early, narrow layers
+#   (measured 1.0e-3 max / 7.0e-4 l2 after conv2d_3) and is averaged down by the wider layers that follow; only the model's output
+#   (conv2d_19) carries the north-star bound above.
+TOL_LAYER = {"fp32": dict(max=1e-4, l2=1e-4), "f16": dict(max=2e-3, l2=1e-3)}
 PRECISIONS = ["fp32", "f16"]
 
 
-def _assert_close(got, want, precision):
+def _assert_close(got, want, precision, tol=None):
+    tol = tol or TOL
     assert got.shape == want.shape
     err = got.astype(np.float64) - want.astype(np.float64)
     emax = np.abs(err).max() / np.abs(want).max()
     el2 = np.linalg.norm(err) / np.linalg.norm(want)
-    assert emax <= TOL[precision]["max"] and el2 <= TOL[precision]["l2"], f"{precision}: max {emax:.3e} l2 {el2:.3e}"
+    assert emax <= tol[precision]["max"] and el2 <= tol[precision]["l2"], f"{precision}: max {emax:.3e} l2 {el2:.3e}"
 
 
 def _mel(seed, n, frames):
@@ -86,8 +91,6 @@ def test_zero_input_shape_contract(model, weights):
 @pytest.mark.parametrize("layer", [0, 1, 3, 4, 7, 8, 11, 12, 15, 16, 17, 18, 19])
 def test_layer_activations(model, weights, layer):
     """Per-layer parity over a 141-frame strip (fully convolutional evaluation)."""
-    if model.precision == "f16" and layer > 15:
-        pytest.skip("conv2d_16..19 run on the fp32 CUDA-core tail in f16 mode; covered by the fp32 case and the end-to-end tests")
     m = _mel(2, 3, 141)
     got = model.activation_device(torch.from_numpy(m).cuda(), layer).cpu().numpy()
     # oracle activation after `layer`
@@ -101,7 +104,7 @@ def test_layer_activations(model, weights, layer):
         if pool:
             x = F.max_pool2d(x, pool, pool)
     want = x.permute(0, 2, 3, 1).numpy()
-    _assert_close(got, want, model.precision)
+    _assert_close(got, want, model.precision, TOL if layer == 19 else TOL_LAYER)
 
 
 def test_clip_slots_match_windows(model, weights):
@@ -175,6 +178,39 @@ def test_speech_embeddings_batch_list_int16_and_golden(cuda_device, golden_dir, 
     assert e.shape == (2, 32, 96) and s.shape == (2, 836, 32)
     with pytest.raises(ValueError):
         se(np.zeros(1000, dtype=np.float32))  # shorter than one audio window
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_config1_values_at_size(cuda_device, weights, precision):
+    """
+    BASELINE configs[0] (the reference's tests/test_embeddings.py geometry at size): 1000 synthetic 2 s clips, seed 1001, no
+    augmentation -> mel [1000, 836, 32] + embeddings [1000, 32, 96] through SpeechEmbeddings.__call__.  Values: every clip's mel
+    and embeddings against the oracle evaluated FULLY CONVOLUTIONALLY over the same clips (one 197-frame mel per clip; slot k
+    of a 2 s clip is the 76-frame window at global frame offset 12 (k // 4) + 8 (k % 4), SURVEY.md A.5) -- the oracle's windowed
+    evaluation, which is what the reference executes, is pinned to it on a 24-clip subset.
+    """
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+
+    se = SpeechEmbeddings(device_id=0, precision=precision)
+    torch.manual_seed(1001)
+    clips = (0.1 * torch.randn((1000, 32000))).clamp(-1, 1)
+    emb, spectro = se(list(clips), return_spectrograms=True)
+    assert emb.shape == (1000, 32, 96) and spectro.shape == (1000, 836, 32)          # 8 windows x 105 frames = 840, truncated (embeddings.py:229-232)
+    offs = spec.embedding_frame_offsets(32000)
+    assert len(offs) == 32 and offs[:5] == [0, 8, 16, 24, 12]
+    mel = omel.mel_spectrogram(clips.numpy() * np.float32(spec.AUDIO_SCALE))             # [1000, 197, 32]
+    # concatenated per-window layout of return_spectrograms: window w = global frames 12 w .. 12 w + 104
+    frame_index = np.array([12 * w + f for w in range(8) for f in range(105)])[:836]
+    assert np.abs(spectro - mel[:, frame_index]).max() <= 1e-4 * np.abs(mel).max()
+    chunks = range(0, 1000, 125)
+    strip = np.concatenate([oembed.embed_strip(mel[i:i + 125], weights, dtype=torch.float64) for i in chunks])        # [1000, 16, 96]: offsets 0, 8, ..
+    half = np.concatenate([oembed.embed_strip(mel[i:i + 125, 4:], weights, dtype=torch.float64) for i in chunks])     # offsets 4, 12, ..
+    want = np.stack([strip[:, o // 8] if o % 8 == 0 else half[:, (o - 4) // 8] for o in offs], axis=1)
+    _assert_close(emb, want, precision)
+    # the windowed evaluation the reference executes == the strip evaluation (float64), on a subset
+    sub = opipe.speech_embeddings([c for c in clips[:24].numpy()], omel.mel_spectrogram,
+                                  lambda w: oembed.speech_embedding_model(w, weights, dtype=torch.float64))
+    np.testing.assert_allclose(sub, want[:24], atol=1e-6 * np.abs(want).max())
 
 
 def test_nan_repair(cuda_device):

@@ -89,25 +89,50 @@ def test_generator_matches_oracle_pipeline(cuda_device, precision):
     assert err2 < tol, err2
 
 
-def test_sharding_is_world_size_independent(cuda_device, tmp_path):
-    """Two ranks writing their row ranges of one .npy give bit-identical rows to a single-rank run."""
+@pytest.mark.parametrize("where", ["disk", "shm"])
+def test_sharding_is_world_size_independent(cuda_device, tmp_path, where, monkeypatch):
+    """
+    Two ranks writing their row ranges of one .npy give bit-identical rows to a single-rank run -- through both
+    sinks: pwrite from the pipeline's pinned slots (disk-backed directory) and D2H straight into the registered file mapping
+    (memory-backed directory); the file is byte-identical to np.save of the single-rank array.
+    """
+    import shutil
+    import tempfile
+
     from heybuddy_b200.dataset.features import TrainingFeaturesGenerator
     from heybuddy_b200.dataset.precalculated import PrecalculatedDatasetIterator
 
-    rng = np.random.default_rng(4)
-    noise, rirs = _banks(rng)
-    kw = dict(device_id=0, use_autoconfigure=False, augment_batch_size=16, augment_background_dataset=noise,
-              augment_impulse_dataset=rirs, seed=77, sample_batch_size=32)
-    single = TrainingFeaturesGenerator(**kw)(100)
-    path = str(tmp_path / "hello_world.npy")
-    ranges = []
-    for rank in (0, 1):  # rank 0 creates the file; ranks run one after the other here, concurrently under torchrun
-        ranges.append(TrainingFeaturesGenerator(rank=rank, world_size=2, **kw).generate_sharded(100, path))
-    assert ranges == [(0, 64), (64, 100)]
-    sharded = np.load(path, mmap_mode="r")
-    np.testing.assert_array_equal(np.asarray(sharded), single)
-    it = PrecalculatedDatasetIterator("hello_world", directory=str(tmp_path))
-    assert it.take(3).shape == (3, 16, 96)
+    if where == "shm":
+        if not os.path.isdir("/dev/shm"):
+            pytest.skip("no /dev/shm")
+        monkeypatch.setenv("HEYBUDDY_B200_PINNED_FILE", "1")      # the registered-mapping sink is opt-in
+        directory = tempfile.mkdtemp(prefix="hb_test_", dir="/dev/shm")
+    else:
+        directory = str(tmp_path)
+    try:
+        rng = np.random.default_rng(4)
+        noise, rirs = _banks(rng)
+        kw = dict(device_id=0, use_autoconfigure=False, augment_batch_size=16, augment_background_dataset=noise,
+                  augment_impulse_dataset=rirs, seed=77, sample_batch_size=32, chunk_clips=32)
+        single = TrainingFeaturesGenerator(**kw)(100)
+        path = os.path.join(directory, "hello_world.npy")
+        ranges, sinks = [], []
+        for rank in (0, 1):  # rank 0 creates the file; ranks run one after the other here, concurrently under torchrun
+            gen = TrainingFeaturesGenerator(rank=rank, world_size=2, **kw)
+            ranges.append(gen.generate_sharded(100, path))
+            sinks.append(gen.last_sink)
+        assert ranges == [(0, 64), (64, 100)]
+        assert all(("pinned file mapping" in s_) == (where == "shm") for s_ in sinks), sinks
+        sharded = np.load(path, mmap_mode="r")
+        np.testing.assert_array_equal(np.asarray(sharded), single)
+        np.save(os.path.join(directory, "single.npy"), single)
+        with open(path, "rb") as a, open(os.path.join(directory, "single.npy"), "rb") as b:
+            assert a.read() == b.read()
+        it = PrecalculatedDatasetIterator("hello_world", directory=directory)
+        assert it.take(3).shape == (3, 16, 96)
+    finally:
+        if where == "shm":
+            shutil.rmtree(directory, ignore_errors=True)
 
 
 def test_cache_reuse_and_extend(cuda_device, tmp_path):

@@ -140,3 +140,40 @@ def test_to_target_length():
     assert out[:7].sum() == 0 and out[107:].sum() == 0
     long = np.ones(300, dtype=np.float32)
     assert oaug.to_target_length(long, 0, target=128).shape == (128,)
+
+
+def test_reverb_independent_cross_check():
+    """
+    `oracle.augment.reverberate` restates speechbrain's reverberate (absent offline).  Independent routes to the same definition
+    (SURVEY.md A.3 item 5), none of which touches rotate_rir / numpy's rfft:
+      (a) scipy.signal.convolve (direct, time domain) of the clip with the RIR, wrapped modulo T, then rolled left by the peak
+          delay d = argmax|rir| -- circular convolution with [rir[d:], 0.., rir[:d]] is the un-rotated circular convolution delayed by -d;
+      (b) torch.fft on the whole batch.
+    Both followed by the avg-amplitude rescale written out directly.
+    """
+    torch = pytest.importorskip("torch")
+    signal = pytest.importorskip("scipy.signal")
+    rng = np.random.Generator(np.random.PCG64(17))
+    t = spec.CLIP_SAMPLES
+    x = (rng.standard_normal((3, t)) * 0.1).astype(np.float32)
+    for ln, peak in ((4000, 37), (24000, 150), (30000, 0)):            # shorter than, about, and longer than the clip (truncated to T)
+        rir = (np.exp(-np.arange(ln) / 900.0) * rng.standard_normal(ln)).astype(np.float32)
+        rir[peak] = 3.5
+        want = oaug.reverberate(x, rir)
+        r = rir[:t].astype(np.float64)
+        d = int(np.argmax(np.abs(rir)))
+        # (a) direct convolution, wrapped, rolled
+        full = np.stack([signal.convolve(xi.astype(np.float64), r, mode="full", method="direct") for xi in x[:1]])
+        wrapped = full[:, :t].copy()
+        wrapped[:, :full.shape[1] - t] += full[:, t:]
+        ya = np.roll(wrapped, -d, axis=1)
+        ya = ya * np.abs(x[:1].astype(np.float64)).mean(axis=1, keepdims=True) / (np.abs(ya).mean(axis=1, keepdims=True) + 1e-14)
+        np.testing.assert_allclose(want[:1], ya, atol=2e-7 * np.abs(ya).max())
+        # (b) torch.fft, whole batch
+        k = torch.zeros(t, dtype=torch.float64)
+        k[:r.shape[0]] = torch.from_numpy(r)
+        k = torch.roll(k, -d)
+        xb = torch.from_numpy(x).double()
+        yb = torch.fft.irfft(torch.fft.rfft(xb) * torch.fft.rfft(k), n=t)
+        yb = yb * xb.abs().mean(dim=1, keepdim=True) / (yb.abs().mean(dim=1, keepdim=True) + 1e-14)
+        np.testing.assert_allclose(want, yb.numpy(), atol=2e-7 * float(yb.abs().max()))

@@ -34,7 +34,7 @@ def test_stream_matches_per_step_oracle(cuda_device, seconds):
     assert steps == (n - 17280) // 1920 + 1
     weights = spec.init_embedding_weights()
     want = _oracle_steps(stream, weights)
-    for precision, tol in (("fp32", 1e-4), ("f16", 2e-3)):
+    for precision, tol in (("fp32", 1e-4), ("f16", 1e-3)):
         speech = SpeechEmbeddings(device_id=0, precision=precision)
         got = stream_step_embeddings(speech, stream).cpu().numpy()
         assert got.shape == (steps, 4, 96)
@@ -59,7 +59,7 @@ def test_long_strip_geometry(cuda_device):
     offs = [12 * s + 8 * j for s in range(32) for j in range(4)]
     w = spec.init_embedding_weights()
     want = np.stack([oembed.speech_embedding_model(m[:, o:o + 76, :, None], w, dtype=torch.float64) for o in offs], axis=1)
-    for precision, tol in (("fp32", 1e-4), ("f16", 2e-3)):
+    for precision, tol in (("fp32", 1e-4), ("f16", 1e-3)):
         model = SpeechEmbeddingModel(device_id=0, precision=precision, load=True)
         got = model.run_clips_device(torch.from_numpy(m).cuda(), offs).cpu().numpy()
         assert np.abs(got - want).max() / np.abs(want).max() < tol, precision
