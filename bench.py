@@ -496,6 +496,17 @@ def main():
     h2d, d2h = run_e2e("", per_file)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the same API with the rows left in (pinned) host memory instead of a file: what the host pipeline sustains when the box's
+    # page-cache write rate is out of the picture
+    mem_rows = min(rows_per_rank, 6 * CHUNK)
+    host_out = torch.empty((mem_rows, 16, spec.EMB_DIM), dtype=torch.float32).pin_memory()
+    gens[0][1].generate(mem_rows, first_sample=0, out=host_out)
+    barrier()
+    t1 = time.perf_counter()
+    gens[0][1].generate(mem_rows, first_sample=0, out=host_out)
+    barrier()
+    mem_s = time.perf_counter() - t1
+    del host_out
     host_wait = sum(g._pipe[1].last_stream_wait_s for _, g in gens if g._pipe is not None)
     host_stats = {name: {k: round(float(v), 4) for k, v in g._pipe[1].last_stats.items()} for name, g in gens if g._pipe is not None}
     clocks = sampler.stop()
@@ -519,10 +530,10 @@ def main():
     if rank == 0:
         shutil.rmtree(out_dir, ignore_errors=True)
 
-    times = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    times = torch.tensor([elapsed_ms, e2e_s * 1e3, mem_s * 1e3], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms = float(times[0]), float(times[1])
+    elapsed_ms, e2e_ms, mem_ms = float(times[0]), float(times[1]), float(times[2])
     total_clips = CHUNK * args.steps * world
     value = total_clips * CLIP_SECONDS / (elapsed_ms * 1e-3)
     e2e_value = 2 * per_file * CLIP_SECONDS / (e2e_ms * 1e-3)
@@ -572,6 +583,8 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "host_busy_frac": max(0.0, 1.0 - host_wait / max(e2e_s, 1e-9)),
                     "h2d_gbs_per_rank": h2d_gbs, "h2d_bound_gbs": sum(h2d_gbs), "h2d_bound_value": h2d_bound,
                     "sink_gbs_per_rank": sink_gbs, "sink_bound_value": sink_bound,
+                    "to_host_memory": {"value": mem_rows * world * CLIP_SECONDS / (mem_ms * 1e-3), "unit": UNIT, "clips_per_rank": mem_rows,
+                                       "api": "TrainingFeaturesGenerator.generate(n, out=<pinned tensor>): the same path with the rows left in host memory"},
                     "frac_of_host_bound": e2e_value / host_bound if host_bound > 0 else None,
                     "bounds_note": "measured in this run with all ranks active: pinned H2D copy rate (input: ragged int16, the smallest lossless form) and the rate "
                                    "at which the box turns downloaded f32 rows into .npy page-cache pages (pwrite, 4 threads per rank); the e2e leg cannot beat the "

@@ -677,7 +677,7 @@ static TcGeom tc_geometry(int b, int T_in, int B, const TcWeights* tw) {
 }
 
 // tail block: pooled rows per clip = T15 / 2; several whole clips per CTA when they fit one tile, else time tiles
-static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
+static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw, bool one_clip_per_cta = false) {
     const TcBlockPlan& p = kPlans[4];
     TcGeom g;
     g.T_in = T15;
@@ -691,7 +691,7 @@ static TcGeom tc_tail_geometry(int T15, int B, const TcWeights* tw) {
         g.tiles_per_clip = 1;
         g.rows_out = g.T_out;
         g.Tt = rows;
-        g.segs = std::max(1, (g.tile_n - 1) / (g.Tt * S));
+        g.segs = one_clip_per_cta ? 1 : std::max(1, (g.tile_n - 1) / (g.Tt * S));   // the parity hook dumps one clip per CTA
         g.grid = ceil_div(B, g.segs);
     } else {
         g.segs = 1;
@@ -856,15 +856,47 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
         set_error("hb_embed_activation(f16): bad workspace");
         return HB_ERR_INVALID;
     }
-    if (layer > 15) {
-        set_error("hb_embed_activation(f16): conv2d_16..19 are fused with the slot gather; compare the final embeddings instead");
-        return HB_ERR_UNSUPPORTED;
-    }
     TcGeom g[4];
     tc_chain(F, B, tw, g);
     const int64_t act_bytes = tc_act_bytes(B, g);
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     __half* bufs[2] = {reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + act_bytes)};
+    if (layer > 15) {
+        // conv2d_16..19 = the tail block on pool phase 0 of conv2d_15's output (what spec.embedding_layer_shapes describes), one clip per
+        // CTA so that the block's own activation dump maps back to [clip][row][96]
+        int rc;
+        if ((rc = tcg_block1(m, mel, bufs[0], B, F, nullptr, -1, st))) return rc;
+        if ((rc = tcg_block2(m, bufs[0], bufs[1], B, g[1].T_in, nullptr, -1, st))) return rc;
+        if ((rc = tcg_block3(m, bufs[1], bufs[0], B, g[2].T_in, nullptr, -1, st))) return rc;
+        if ((rc = tcg_block4(m, bufs[0], bufs[1], B, g[3].T_in, nullptr, -1, st))) return rc;
+        const int T15 = g[3].T_out;
+        const TcGeom gt = tc_tail_geometry(T15, B, tw, true);
+        if (gt.tiles_per_clip != 1) { set_error("hb_embed_activation(f16): conv2d_16..19 need a strip whose pooled rows fit one tile"); return HB_ERR_UNSUPPORTED; }
+        float* tail_out = reinterpret_cast<float*>(base + 2 * act_bytes);
+        const int rows = T15 / 2;
+        const int T = layer == 16 ? rows : (layer == 19 ? rows - 4 : rows - 2);
+        const int64_t n = (int64_t)B * T * kEmbDim;
+        if (T <= 0 || n > cap) { set_error("hb_embed_activation: output capacity too small"); return HB_ERR_INVALID; }
+        void* dbg_mem = nullptr;
+        if (layer < 19) {
+            const int64_t need = (int64_t)gt.grid * gt.ch_alloc * gt.P_alloc * 16;
+            if (cudaMalloc(&dbg_mem, need) != cudaSuccess) { set_error("hb_embed_activation: debug allocation failed"); return HB_ERR_CUDA; }
+        }
+        rc = launch_block(m, 4, gt, bufs[1], tail_out, B, 12, 4, 0, reinterpret_cast<__half*>(dbg_mem), layer < 19 ? layer - 16 : -1, st);
+        if (rc) { if (dbg_mem) cudaFree(dbg_mem); return rc; }
+        if (layer < 19) {
+            const int blocks = (int)std::min<int64_t>(ceil_div64(n, 256), 148 * 8);
+            dump_to_nhwc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<__half*>(dbg_mem), out, B, 1, gt.ch_alloc, gt.P_alloc, kPlans[4].F + 1, 1, gt.Tt, T, kEmbDim);
+        } else if (cudaMemcpyAsync(out, tail_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("hb_embed_activation: copy failed");
+            return HB_ERR_CUDA;
+        }
+        const bool ok = cudaGetLastError() == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+        if (dbg_mem) cudaFree(dbg_mem);
+        if (!ok) { set_error("hb_embed_activation: kernel failed"); return HB_ERR_CUDA; }
+        if (check_timeout() != HB_OK) return HB_ERR_CUDA;
+        return n;
+    }
     const int target_block = layer < 4 ? 0 : (layer < 8 ? 1 : (layer < 12 ? 2 : 3));
     static const int in_chunks[4] = {0, 4, 6, 10}, in_F[4] = {kMels, 16, 8, 4};
     const void* in = mel;

@@ -354,21 +354,25 @@ class TrainingFeaturesGenerator:
             self._items(first_sample, num_samples, sink_of, validation, testing), chunk, writer_threads=writer_threads, wait=wait)
 
     def generate(self, num_samples: int, sample_save_path: Optional[str] = None, augmented_sample_save_path: Optional[str] = None,
-                 testing: bool = False, validation: bool = False, first_sample: Optional[int] = None) -> np.ndarray:
+                 testing: bool = False, validation: bool = False, first_sample: Optional[int] = None, out: Optional[Any] = None) -> np.ndarray:
         """
         Generates ``num_samples`` clips and computes their embeddings -> ``f32 [num_samples, 16, 96]`` (features.py:360-490).
         Rows are samples ``first_sample ..`` of this generator's stream (default: where the previous call stopped, rounded up to
         an augmentation-batch boundary), so successive calls -- and a cache extension -- never repeat a sample.
+        ``out``: optional destination, a numpy array or a pinned CPU torch tensor ``[num_samples, 16, 96]`` f32 (the device -> host
+        copies then land in it directly).
         """
         if self.use_autoconfigure:
             self.autoconfigure()
         b = self.augment_batch_size
         start = self._generated if first_sample is None else first_sample
         start = -(-start // b) * b
-        out = np.empty((num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM), dtype=np.float32)
+        if out is None:
+            out = np.empty((num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM), dtype=np.float32)
+        assert tuple(out.shape) == (num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM)
         self._run(start, num_samples, lambda lo, hi: out[lo:hi], validation, testing)
         self._generated = start + num_samples
-        return out
+        return out.numpy() if hasattr(out, "is_pinned") else out
 
     def __call__(self, num_samples: int, sample_save_path: Optional[str] = None, augmented_sample_save_path: Optional[str] = None,
                  testing: bool = False, validation: bool = False) -> np.ndarray:
