@@ -91,6 +91,10 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_mlp_backward": (c_int, [c_vp, c_vp, c_vp, c_int, c_f, c_f, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
         "hb_mlp_grads_copy": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
         "hb_mlp_adam": (c_int, [c_vp, c_f, c_vp, c_vp]),
+        "hb_mlp_set_loss_scale": (c_int, [c_vp, c_f]),
+        "hb_mlp_get_adam": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64]),
+        "hb_mlp_set_adam": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64]),
+        "hb_mlp_dropout": (c_int, [c_vp, c_vp, c_i64, c_f, ctypes.c_uint64, ctypes.c_uint64, c_vp]),
         "hb_mlp_get_grads": (c_int, [c_vp, c_vp, c_i64]),
         "hb_mlp_multi_workspace_bytes": (c_i64, [c_int, c_int]),
         "hb_mlp_forward_multi": (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),

@@ -170,9 +170,9 @@ __global__ void head_select_kernel(const float* __restrict__ z, const int64_t* _
 
 // n_total: rows selected over the whole (possibly multi-rank) batch = the normaliser of the mean loss
 __global__ void head_grad_kernel(const float* __restrict__ p, const int64_t* __restrict__ y, float* __restrict__ dz,
-                                 float* __restrict__ stats, const float* __restrict__ n_total, int B, float thr, float neg_w) {
+                                 float* __restrict__ stats, const float* __restrict__ n_total, int B, float thr, float neg_w, float loss_scale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float n_sel = *n_total;
+    const float n_sel = *n_total / loss_scale;     // loss_scale = 1 / accumulation_steps of the reference's loop
     float l = 0.f;
     if (i < B) {
         const float pr = p[i];
@@ -287,6 +287,7 @@ __global__ void adam_step_inc_kernel(int* step, const float* stats) {
 }  // namespace hb
 
 struct hb_mlp_model {
+    float loss_scale = 1.0f;   // multiplies the loss and its gradients (the reference divides by its accumulation counter, trainer.py:441)
     float* p = nullptr;   // parameters
     float* g = nullptr;   // gradients of the last training step
     float* m = nullptr;   // Adam first moment
@@ -443,6 +444,66 @@ extern "C" int hb_mlp_set_params(hb_mlp_model* m, const float* params_host, int6
 extern "C" int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats) {
     HB_REQUIRE(m && grads_host && n_floats == kLayout.total, "hb_mlp_get_grads: bad argument");
     HB_CUDA_OK(cudaMemcpy(grads_host, m->g, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+extern "C" int hb_mlp_set_loss_scale(hb_mlp_model* m, float scale) {
+    HB_REQUIRE(m && scale > 0.f, "hb_mlp_set_loss_scale: bad argument");
+    m->loss_scale = scale;
+    return HB_OK;
+}
+
+// Adam state (torch.optim.Adam's exp_avg / exp_avg_sq / step) <-> host, packed like the parameters: checkpoint + resume
+extern "C" int hb_mlp_get_adam(const hb_mlp_model* m, float* exp_avg_host, float* exp_avg_sq_host, int* step_host, int64_t n_floats) {
+    HB_REQUIRE(m && exp_avg_host && exp_avg_sq_host && step_host && n_floats == kLayout.total, "hb_mlp_get_adam: bad argument");
+    HB_CUDA_OK(cudaMemcpy(exp_avg_host, m->m, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    HB_CUDA_OK(cudaMemcpy(exp_avg_sq_host, m->v, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    HB_CUDA_OK(cudaMemcpy(step_host, m->step, sizeof(int), cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+extern "C" int hb_mlp_set_adam(hb_mlp_model* m, const float* exp_avg_host, const float* exp_avg_sq_host, int step, int64_t n_floats) {
+    HB_REQUIRE(m && exp_avg_host && exp_avg_sq_host && step >= 0 && n_floats == kLayout.total, "hb_mlp_set_adam: bad argument");
+    HB_CUDA_OK(cudaMemcpy(m->m, exp_avg_host, (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    HB_CUDA_OK(cudaMemcpy(m->v, exp_avg_sq_host, (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    HB_CUDA_OK(cudaMemcpy(m->step, &step, sizeof(int), cudaMemcpyHostToDevice));
+    return HB_OK;
+}
+
+namespace hb {
+// one Philox4x32-10 block per four elements: counter = (index / 4, 7, call lo, call hi), key = seed (same generator as the draw table)
+__device__ __forceinline__ uint4 philox_cls(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// nn.Dropout(p) on the classifier input (wakeword.py:197,338): y = x * keep / (1 - p), keep ~ Bernoulli(1 - p) per element
+__global__ void dropout_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, float p, uint2 key, uint64_t call) {
+    const float scale = 1.0f / (1.0f - p);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox_cls(make_uint4((uint32_t)i, 7u ^ ((uint32_t)(i >> 32) << 8), (uint32_t)call, (uint32_t)(call >> 32)), key);
+        const float4 v = x[i];
+        const float t = p * 16777216.0f;     // keep when the 24-bit uniform >= p
+        y[i] = make_float4((float)(r.x >> 8) >= t ? v.x * scale : 0.f, (float)(r.y >> 8) >= t ? v.y * scale : 0.f,
+                           (float)(r.z >> 8) >= t ? v.z * scale : 0.f, (float)(r.w >> 8) >= t ? v.w * scale : 0.f);
+    }
+}
+}  // namespace hb
+
+extern "C" int hb_mlp_dropout(const float* x_dev, float* y_dev, int64_t n, float p, uint64_t seed, uint64_t call, void* stream) {
+    HB_REQUIRE(x_dev && y_dev && n >= 0 && n % 4 == 0 && p >= 0.f && p < 1.f, "hb_mlp_dropout: bad argument (n must be a multiple of 4)");
+    HB_REQUIRE(((reinterpret_cast<uintptr_t>(x_dev) | reinterpret_cast<uintptr_t>(y_dev)) & 15) == 0, "hb_mlp_dropout: 16-byte aligned buffers");
+    if (n == 0) return HB_OK;
+    const int64_t n4 = n / 4;
+    dropout_kernel<<<(int)std::min<int64_t>(ceil_div64(n4, 256), 2368), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x_dev), reinterpret_cast<float4*>(y_dev), n4, p, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), call);
+    HB_LAUNCHED();
     return HB_OK;
 }
 
@@ -700,7 +761,7 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
                          const float* n_total_dev, int min_selected, const float* prob_dev, float* stats_dev, const Ws& w,
                          cudaStream_t st) {
     int rc;
-    head_grad_kernel<<<ceil_div(B, 256), 256, 0, st>>>(prob_dev, y_dev, w.dz, stats_dev, n_total_dev, B, thr, negative_weight);
+    head_grad_kernel<<<ceil_div(B, 256), 256, 0, st>>>(prob_dev, y_dev, w.dz, stats_dev, n_total_dev, B, thr, negative_weight, m->loss_scale);
     HB_LAUNCHED();
     head_finish_kernel<<<1, 1, 0, st>>>(stats_dev, n_total_dev, B, min_selected);
     HB_LAUNCHED();

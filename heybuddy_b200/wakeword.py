@@ -9,8 +9,8 @@ in the hand-written kernels of ``csrc/classifier.cu`` through ``hb_mlp_*``; ther
 
 Only the default architecture (layer_dim 96, 2 layers, gating, no half layers) is built: the
 transformer classifier and the half-layer variant are outside the north-star path.
-Dropout(0.1) on the input is train-only in the reference; the fused training step runs without it
-(parity configuration).
+Dropout(0.1) on the input is train-only in the reference (wakeword.py:197,338): ``train_step(dropout=p)`` / ``apply_dropout`` draw
+it on the device and ``WakeWordTrainer`` uses it by default; ``dropout=0`` is the parity configuration.
 """
 from __future__ import annotations
 
@@ -211,15 +211,82 @@ class WakeWordMLPModel:
 
     forward = __call__
 
-    def train_step(self, x, y, lr: float, negative_weight: float = 1.0, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD,
-                   min_selected: int = 128):
+    def set_loss_scale(self, scale: float) -> None:
+        """Loss / gradient multiplier of the following training steps (the reference's ``1 / accumulation_steps``, trainer.py:441)."""
+        if getattr(self, "_loss_scale", 1.0) != float(scale):
+            import torch
+
+            with torch.cuda.device(self.device):
+                _native.check(_native.load().hb_mlp_set_loss_scale(self._ensure(), float(scale)), "hb_mlp_set_loss_scale")
+            self._loss_scale = float(scale)
+
+    def apply_dropout(self, x, p: float, seed: int = 0):
         """
-        One reference training step (trainer.py:405-462) fused on the device: forward, high-loss selection,
-        weighted BCE (mean over the selected rows), backward and -- when at least ``min_selected`` rows were
-        selected -- Adam.  Returns (probabilities cuda [B,1], stats cuda f32[4] = loss, n_selected, stepped, high_loss_rate).
+        Train-mode ``nn.Dropout(p)`` on the classifier input (wakeword.py:197,338): a dropped copy of ``x`` drawn on the device
+        (``hb_mlp_dropout``: Philox4x32-10, key = seed, one counter block per four elements, call index = number of calls so far).
+        ``p == 0`` returns ``x`` itself.
         """
         import torch
 
+        if not p:
+            return x
+        x = x.reshape(x.shape[0], -1).contiguous()
+        out = torch.empty_like(x)
+        call = getattr(self, "_dropout_calls", 0)
+        self._dropout_calls = call + 1
+        with torch.cuda.device(x.device):
+            _native.check(_native.load().hb_mlp_dropout(x.data_ptr(), out.data_ptr(), x.numel(), float(p), int(seed) & (2 ** 64 - 1), call,
+                                                        _native.stream_ptr(x.device)), "hb_mlp_dropout")
+        return out
+
+    def optimizer_state_dict(self, lr: float = DEFAULT_LEARNING_RATE) -> Dict[str, Any]:
+        """The fused step's Adam state as a ``torch.optim.Adam(model.parameters()).state_dict()`` (what trainer.py:197-198 saves)."""
+        import torch
+
+        n = self._host_params.size
+        m, v, step = np.empty(n, np.float32), np.empty(n, np.float32), ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            _native.check(_native.load().hb_mlp_get_adam(self._ensure(), m.ctypes.data, v.ctypes.data, ctypes.byref(step), n), "hb_mlp_get_adam")
+        ms, vs = unpack_classifier_params(m), unpack_classifier_params(v)
+        names = [name for name, _ in spec.classifier_param_shapes()]
+        state = {} if step.value == 0 else {
+            i: {"step": torch.tensor(float(step.value)), "exp_avg": torch.from_numpy(ms[k]), "exp_avg_sq": torch.from_numpy(vs[k])}
+            for i, k in enumerate(names)}
+        group = {"lr": float(lr), "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: Dict[str, Any]) -> None:
+        """Inverse of :meth:`optimizer_state_dict`; accepts the reference's ``<name>_optimizer.pt`` (parameters in registration order)."""
+        import torch
+
+        names = [name for name, _ in spec.classifier_param_shapes()]
+        state = sd.get("state", {})
+        zeros = unpack_classifier_params(np.zeros_like(self._host_params))
+        ms, vs, step = dict(zeros), {k: a.copy() for k, a in zeros.items()}, 0
+        for i, k in enumerate(names):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            ms[k] = st["exp_avg"].detach().cpu().numpy().astype(np.float32)
+            vs[k] = st["exp_avg_sq"].detach().cpu().numpy().astype(np.float32)
+            step = max(step, int(float(st["step"])))
+        m, v = pack_classifier_params(ms), pack_classifier_params(vs)
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().hb_mlp_set_adam(self._ensure(), m.ctypes.data, v.ctypes.data, step, m.size), "hb_mlp_set_adam")
+
+    def train_step(self, x, y, lr: float, negative_weight: float = 1.0, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD,
+                   min_selected: int = 128, dropout: float = 0.0, dropout_seed: int = 0):
+        """
+        One reference training step (trainer.py:405-462) fused on the device: forward, high-loss selection,
+        weighted BCE (mean over the selected rows), backward and -- when at least ``min_selected`` rows were
+        selected -- Adam.  ``dropout`` > 0 applies the train-mode input dropout first (the trainer does; parity tests do not).
+        Returns (probabilities cuda [B,1], stats cuda f32[4] = loss, n_selected, stepped, high_loss_rate).
+        """
+        import torch
+
+        x = self.apply_dropout(x, dropout, dropout_seed)
         x = x.reshape(x.shape[0], -1).contiguous()
         assert x.is_cuda and x.dtype == torch.float32 and y.is_cuda and y.dtype == torch.int64
         b = x.shape[0]

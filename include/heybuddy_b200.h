@@ -190,6 +190,17 @@ int hb_mlp_backward(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, i
                     const float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 int hb_mlp_grads_copy(hb_mlp_model* m, float* buf_dev, int64_t n_floats, int to_model, void* stream);
 int hb_mlp_adam(hb_mlp_model* m, float lr, const float* stats_dev, void* stream);
+/* The reference divides the loss of the step that finally fires by its accumulation counter (1 + the number of preceding steps
+ * that selected fewer than 128 rows and were skipped, trainer.py:441-458): scale = 1 / accumulation_steps, applied to the loss
+ * and its gradients of the following hb_mlp_train_step / hb_mlp_backward calls (default 1). */
+int hb_mlp_set_loss_scale(hb_mlp_model* m, float scale);
+/* Adam state = torch.optim.Adam's exp_avg / exp_avg_sq (packed like params) and step: `<name>_optimizer.pt` checkpoints and
+ * Trainer.resume (trainer.py:54-118, 186-198). */
+int hb_mlp_get_adam(const hb_mlp_model* m, float* exp_avg_host, float* exp_avg_sq_host, int* step_host, int64_t n_floats);
+int hb_mlp_set_adam(hb_mlp_model* m, const float* exp_avg_host, const float* exp_avg_sq_host, int step, int64_t n_floats);
+/* nn.Dropout(p) on the classifier input, train mode only (wakeword.py:197,338): y = x * keep / (1 - p) with keep drawn per
+ * element from Philox4x32-10 (key = seed, counter = (element / 4, 7, call)); n a multiple of 4, 16-byte aligned buffers. */
+int hb_mlp_dropout(const float* x_dev, float* y_dev, int64_t n, float p, uint64_t seed, uint64_t call, void* stream);
 /* Gradients of the last hb_mlp_train_step / hb_mlp_backward (packed like params), for parity tests. */
 int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats);
 

@@ -148,3 +148,67 @@ def test_training_reduces_loss_and_lr_schedule(cuda_device):
     assert np.mean(loss[-10:]) < 0.6 * np.mean(loss[:5])
     metrics = trainer.evaluate(batches(), max_batches=2)
     assert metrics["recall"] > 0.9 and metrics["false_positive_rate"] < 0.1
+
+
+def test_loss_scale_dropout_and_optimizer_checkpoint(cuda_device, tmp_path):
+    """
+    The trainer's remaining reference behaviours: (1) the loss / gradients of a firing step divided by the
+    accumulation counter (trainer.py:441); (2) train-mode input dropout (wakeword.py:197,338) -- the device mask is the draw
+    table's Philox generator, reproduced here in numpy; (3) `<name>_optimizer.pt` is a torch.optim.Adam state dict: a torch
+    optimiser resumed from it takes the same next step as the fused kernel, and `resume()` restores model + Adam state.
+    """
+    from heybuddy_b200.dataset.draws import philox4x32
+    from heybuddy_b200.trainer import WakeWordTrainer
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    rng = np.random.Generator(np.random.PCG64(11))
+    x = rng.standard_normal((512, 16, 96)).astype(np.float32)
+    y = (rng.random(512) < 0.2).astype(np.int64)
+    x[y == 1] += 0.3
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+
+    # (1) loss scale
+    a, b = WakeWordMLPModel(device_id=0, seed=3), WakeWordMLPModel(device_id=0, seed=3)
+    b.set_loss_scale(1.0 / 3.0)
+    _, sa = a.train_step(xt, yt, lr=0.0, min_selected=1)
+    _, sb = b.train_step(xt, yt, lr=0.0, min_selected=1)
+    np.testing.assert_allclose(sb[0].item(), sa[0].item() / 3.0, rtol=1e-6)
+    ga, gb = a.gradients(), b.gradients()
+    for k in ga:
+        np.testing.assert_allclose(gb[k], ga[k] / 3.0, rtol=1e-5, atol=1e-10)
+
+    # (2) dropout mask == numpy Philox (key = seed, counter = (i / 4, 7, call), keep when the 24-bit uniform >= p)
+    p, seed = 0.1, 1234
+    m = WakeWordMLPModel(device_id=0, seed=3)
+    for call in range(2):
+        d = m.apply_dropout(xt, p, seed).cpu().numpy().reshape(-1)
+        r = np.stack(philox4x32(np.arange(x.size // 4), 7, call, 0, seed), axis=1).reshape(-1)
+        keep = (r >> np.uint64(8)).astype(np.float32) >= np.float32(p * 16777216.0)
+        np.testing.assert_array_equal(d, np.where(keep, x.reshape(-1) * np.float32(1.0 / (1.0 - p)), 0).astype(np.float32))
+    assert abs(keep.mean() - 0.9) < 0.01
+
+    # (3) optimizer checkpoint interchange
+    tr = WakeWordTrainer(model=WakeWordMLPModel(device_id=0, seed=3), checkpoint_dir=str(tmp_path), dropout=0.0)
+    for _ in range(3):
+        tr.model.train_step(xt, yt, lr=1e-3, min_selected=1)
+    tr.save_checkpoint("ck")
+    assert sorted(os.listdir(tmp_path)) == ["ck.pt", "ck_optimizer.pt"]
+    before = {k: v.clone() for k, v in tr.model.state_dict().items()}
+    tr.model.train_step(xt, yt, lr=1e-3, min_selected=1)
+    grads = tr.model.gradients()
+    after = tr.model.state_dict()
+    # a torch.optim.Adam resumed from the checkpoint + the same gradients -> the same parameters
+    params = [torch.nn.Parameter(before[k].clone()) for k, _ in spec.classifier_param_shapes()]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    opt.load_state_dict(torch.load(tmp_path / "ck_optimizer.pt", weights_only=True))
+    for prm, (k, _) in zip(params, spec.classifier_param_shapes()):
+        prm.grad = torch.from_numpy(grads[k])
+    opt.step()
+    for prm, (k, _) in zip(params, spec.classifier_param_shapes()):
+        np.testing.assert_allclose(prm.detach().numpy(), after[k].numpy(), rtol=2e-5, atol=2e-7, err_msg=k)
+    # resume(): a fresh trainer continues bit-identically
+    tr2 = WakeWordTrainer(model=WakeWordMLPModel(device_id=0, seed=99), checkpoint_dir=str(tmp_path), dropout=0.0)
+    tr2.resume("ck")
+    tr2.model.train_step(xt, yt, lr=1e-3, min_selected=1)
+    for k, v in tr2.model.state_dict().items():
+        assert torch.equal(v, after[k]), k
