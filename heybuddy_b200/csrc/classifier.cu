@@ -74,61 +74,189 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
     if (lane == 0 && mean) { mean[row] = mu; rstd[row] = rs; }
 }
 
-// Generic tiled fp32 GEMM: C[m,n] (+)= sum_k A(m,k) * Bm(k,n) (+ bias[n]); element strides make NT / NN / TN.
-constexpr int kTile = 64, kTk = 16;
-__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
-                                                   const float* __restrict__ Bm, int64_t sbk, int64_t sbn,
-                                                   float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-                                                   int M, int N, int K, int accumulate, int k_per_split) {
-    // split-K (gridDim.z > 1): slice z of K goes to the partial buffer C + z * M * ldc (ldc = N), summed in a fixed order by
-    // splitk_reduce_kernel -- deterministic, unlike atomics
-    __shared__ float As[kTk][kTile + 1];
-    __shared__ float Bs[kTk][kTile + 1];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * kTile, n0 = blockIdx.x * kTile;
-    const int k_begin = blockIdx.z * k_per_split;
-    if (gridDim.z > 1) {
-        C += (int64_t)blockIdx.z * M * ldc;
-        K = min(K, k_begin + k_per_split);
-    }
-    float acc[4][4] = {};
-    for (int k0 = k_begin; k0 < K; k0 += kTk) {
-        for (int i = threadIdx.x; i < kTile * kTk; i += 256) {
-            int m, k;
-            if (sak == 1) { k = i % kTk; m = i / kTk; } else { m = i % kTile; k = i / kTile; }
-            const int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+constexpr int kTile = 64, kTk = 16;   // tile of the model-batched linear kernel (config 5)
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Register-blocked fp32 SGEMM for the step's large products: C[m,n] = sum_k A(m,k) B(k,n) (+ bias[n]).
+//   * BM x BN x BK tiles (128 x 128 x 8 or 64 x 64 x 16), (BM/TM) x (BN/TN) threads, every thread a TM x TN micro-tile made of 4 x 4 blocks BM/2 (BN/2) apart, so
+//     that each shared-memory read is a conflict-free LDS.128; double-buffered shared memory, the next k-tile's global loads in
+//     flight (registers) while the current one is multiplied.
+//   * either operand may be k-contiguous or m/n-contiguous (A_K / B_K): NT (activations x weights^T), TN (weight gradients:
+//     d^T u) and NN (input gradients: d W) are the same kernel.
+//   * the B operand (and the bias, and the output rows) may come from TWO parameter blocks -- the hidden and the gate linears of a
+//     gated MLP share their input, so [W_h; W_g] is one stacked 128-row operand and the A tile is read once for both.
+//   * gridDim.z > 1 = split-K: slice z writes its partial tile to part + z * M * N; sgemm_reduce_kernel adds the slices in a fixed
+//     order (deterministic, unlike atomics) and applies bias / destinations.
+struct SgemmArgs {
+    const float* A; int lda;
+    const float* B0; const float* B1; int bsplit; int ldb;     // B row r (r = n when B_K, else k): r < bsplit ? B0 + r ldb : B1 + (r - bsplit) ldb
+    float* C0; float* C1; int csplit; int ldc;                   // C row m: m < csplit ? C0 + m ldc : C1 + (m - csplit) ldc
+    const float* bias0; const float* bias1; int biassplit;       // bias[n]: n < biassplit ? bias0[n] : bias1[n - biassplit]; bias0 == nullptr: none
+    float* part;                                                 // split-K partial buffer
+    int M, N, K, k_per_split;
+};
+
+template <int BM, int BN, int BK, int TM, int TN, bool A_K, bool B_K>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) sgemm_kernel(const SgemmArgs a) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int A_LOADS = BM * BK / 4 / NT, B_LOADS = BN * BK / 4 / NT;   // float4 slots per thread per k-tile
+    static_assert(TM % 4 == 0 && TN % 4 == 0 && A_LOADS >= 1 && B_LOADS >= 1, "tile shape");
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * a.k_per_split, k_end = min(a.K, k_begin + a.k_per_split);
+
+    float4 ra[A_LOADS], rb[B_LOADS];
+    // slot -> (row along the non-contiguous dim, 4 elements along the contiguous dim)
+    auto load_a = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_LOADS; ++i) {
+            const int slot = tid + i * NT;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (A_K) {
+                const int m = m0 + slot / (BK / 4), k = k0 + (slot % (BK / 4)) * 4;
+                if (m < a.M) {
+                    const float* p = a.A + (int64_t)m * a.lda + k;
+                    if (k + 3 < k_end && (reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (k + j < k_end) v[j] = __ldg(p + j);
+                }
+            } else {
+                const int k = k0 + slot / (BM / 4), m = m0 + (slot % (BM / 4)) * 4;
+                if (k < k_end) {
+                    const float* p = a.A + (int64_t)k * a.lda + m;
+                    if (m + 3 < a.M && (reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (m + j < a.M) v[j] = __ldg(p + j);
+                }
+            }
+            ra[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        for (int i = threadIdx.x; i < kTile * kTk; i += 256) {
-            int n, k;
-            if (sbk == 1) { k = i % kTk; n = i / kTk; } else { n = i % kTile; k = i / kTile; }
-            const int gn = n0 + n, gk = k0 + k;
-            Bs[k][n] = (gn < N && gk < K) ? Bm[gk * sbk + gn * sbn] : 0.f;
+    };
+    auto load_b = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            const int slot = tid + i * NT;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (B_K) {
+                const int n = n0 + slot / (BK / 4), k = k0 + (slot % (BK / 4)) * 4;
+                if (n < a.N) {
+                    const float* p = (n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb) + k;
+                    if (k + 3 < k_end && (reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (k + j < k_end) v[j] = __ldg(p + j);
+                }
+            } else {
+                const int k = k0 + slot / (BN / 4), n = n0 + (slot % (BN / 4)) * 4;
+                if (k < k_end) {
+                    const float* p = (k < a.bsplit ? a.B0 + (int64_t)k * a.ldb : a.B1 + (int64_t)(k - a.bsplit) * a.ldb) + n;
+                    if (n + 3 < a.N && (reinterpret_cast<uintptr_t>(p) & 15) == 0) *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p));
+                    else
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (n + j < a.N) v[j] = __ldg(p + j);
+                }
+            }
+            rb[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        __syncthreads();
+    };
+    auto store_tiles = [&](int buf) {
 #pragma unroll
-        for (int k = 0; k < kTk; ++k) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gm = m0 + ty + 16 * i, gn = n0 + tx + 16 * j;
-            if (gm < M && gn < N) {
-                float v = acc[i][j] + (bias ? bias[gn] : 0.f);
-                float* c = C + gm * ldc + gn;
-                *c = accumulate ? *c + v : v;
+        for (int i = 0; i < A_LOADS; ++i) {
+            const int slot = tid + i * NT;
+            if (A_K) {
+                const int m = slot / (BK / 4), k = (slot % (BK / 4)) * 4;
+                As[buf][k][m] = ra[i].x; As[buf][k + 1][m] = ra[i].y; As[buf][k + 2][m] = ra[i].z; As[buf][k + 3][m] = ra[i].w;
+            } else {
+                const int k = slot / (BM / 4), m = (slot % (BM / 4)) * 4;
+                *reinterpret_cast<float4*>(&As[buf][k][m]) = ra[i];
             }
         }
+#pragma unroll
+        for (int i = 0; i < B_LOADS; ++i) {
+            const int slot = tid + i * NT;
+            if (B_K) {
+                const int n = slot / (BK / 4), k = (slot % (BK / 4)) * 4;
+                Bs[buf][k][n] = rb[i].x; Bs[buf][k + 1][n] = rb[i].y; Bs[buf][k + 2][n] = rb[i].z; Bs[buf][k + 3][n] = rb[i].w;
+            } else {
+                const int k = slot / (BN / 4), n = (slot % (BN / 4)) * 4;
+                *reinterpret_cast<float4*>(&Bs[buf][k][n]) = rb[i];
+            }
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    int buf = 0;
+    if (k_begin < k_end) {
+        load_a(k_begin);
+        load_b(k_begin);
+        store_tiles(0);
+    }
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) {
+            load_a(k0 + BK);
+            load_b(k0 + BK);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[TM], bv[TN];
+#pragma unroll
+            for (int i = 0; i < TM / 4; ++i)
+                *reinterpret_cast<float4*>(&av[4 * i]) = *reinterpret_cast<const float4*>(&As[buf][k][i * (BM / (TM / 4)) + ty * 4]);
+#pragma unroll
+            for (int j = 0; j < TN / 4; ++j)
+                *reinterpret_cast<float4*>(&bv[4 * j]) = *reinterpret_cast<const float4*>(&Bs[buf][k][j * (BN / (TN / 4)) + tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    // epilogue: micro-tile row i -> m0 + (i / 4) * (BM / (TM / 4)) + ty * 4 + i % 4, same for columns
+    const bool split = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + (i / 4) * (BM / (TM / 4)) + ty * 4 + (i % 4);
+        if (m >= a.M) continue;
+        float* crow = split ? a.part + ((int64_t)blockIdx.z * a.M + m) * a.N
+                            : (m < a.csplit ? a.C0 + (int64_t)m * a.ldc : a.C1 + (int64_t)(m - a.csplit) * a.ldc);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + (j / 4) * (BN / (TN / 4)) + tx * 4 + (j % 4);
+            if (n >= a.N) continue;
+            float v = acc[i][j];
+            if (!split && a.bias0 != nullptr) v += (n < a.biassplit ? a.bias0[n] : a.bias1[n - a.biassplit]);
+            crow[n] = v;
+        }
+    }
+}
+
+__global__ void sgemm_reduce_kernel(const SgemmArgs a, int S) {
+    const int64_t total = (int64_t)a.M * a.N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / a.N), n = (int)(i - (int64_t)m * a.N);
+        float v = a.bias0 != nullptr ? (n < a.biassplit ? a.bias0[n] : a.bias1[n - a.biassplit]) : 0.f;
+        for (int z = 0; z < S; ++z) v += a.part[(int64_t)z * total + i];
+        float* crow = m < a.csplit ? a.C0 + (int64_t)m * a.ldc : a.C1 + (int64_t)(m - a.csplit) * a.ldc;
+        crow[n] = v;
+    }
 }
 
 __global__ void gate_fwd_kernel(const float* __restrict__ h, const float* __restrict__ g, float* __restrict__ a, int64_t n) {
@@ -146,6 +274,27 @@ __global__ void gate_bwd_kernel(const float* __restrict__ h, const float* __rest
         const float d = da[i];
         dg[i] = d * silu;
         dh[i] = d * g[i] * (sg * (1.f + hv * (1.f - sg)));
+    }
+}
+
+// stacked layout: hg [B][128] = [hidden | gate] pre-activations of a gated MLP; a [B][64] = silu(h) * g
+__global__ void gate_hg_fwd_kernel(const float* __restrict__ hg, float* __restrict__ a, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / kHid;
+        const int j = (int)(i - r * kHid);
+        const float hv = hg[r * 2 * kHid + j], gv = hg[r * 2 * kHid + kHid + j];
+        a[i] = hv / (1.f + expf(-hv)) * gv;
+    }
+}
+__global__ void gate_hg_bwd_kernel(const float* __restrict__ hg, const float* __restrict__ da, float* __restrict__ dhg, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / kHid;
+        const int j = (int)(i - r * kHid);
+        const float hv = hg[r * 2 * kHid + j], gv = hg[r * 2 * kHid + kHid + j];
+        const float sg = 1.f / (1.f + expf(-hv));
+        const float d = da[i];
+        dhg[r * 2 * kHid + kHid + j] = d * hv * sg;                                   // d gate
+        dhg[r * 2 * kHid + j] = d * gv * (sg * (1.f + hv * (1.f - sg)));              // d hidden
     }
 }
 
@@ -195,6 +344,45 @@ __global__ void head_grad_kernel(const float* __restrict__ p, const int64_t* __r
 __global__ void head_finish_kernel(float* __restrict__ stats, const float* __restrict__ n_total, int B, int min_selected) {
     stats[2] = *n_total >= (float)min_selected ? 1.f : 0.f;
     stats[3] = stats[1] / (float)B;
+}
+
+// Column reductions over the batch, two deterministic passes: blockIdx.y owns a slice of the rows and writes its partial sums to
+// scratch [gridDim.y][2][N]; colred_finish_kernel adds the slices in order.  MODE 0: sum_m X[m,n] (bias gradients);
+// MODE 1: LayerNorm parameter gradients, first = sum_m dy * xhat (gamma), second = sum_m dy (beta).
+constexpr int kColSlices = 16;
+template <int MODE>
+__global__ void colred_kernel(const float* __restrict__ X, const float* __restrict__ x_in, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, float* __restrict__ scratch, int M, int N) {
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int part = threadIdx.x >> 5;  // 8 row partitions per slice
+    const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
+    __shared__ float r_a[8][33], r_b[8][33];
+    float a = 0.f, b = 0.f;
+    if (n < N)
+        for (int m = r0 + part; m < r1; m += 8) {
+            const float d = X[(int64_t)m * N + n];
+            if (MODE == 1) { a += d * (x_in[(int64_t)m * N + n] - mean[m]) * rstd[m]; b += d; }
+            else a += d;
+        }
+    r_a[part][threadIdx.x & 31] = a;
+    r_b[part][threadIdx.x & 31] = b;
+    __syncthreads();
+    if (part == 0 && n < N) {
+        float ta = 0.f, tb = 0.f;
+        for (int i = 0; i < 8; ++i) { ta += r_a[i][threadIdx.x & 31]; tb += r_b[i][threadIdx.x & 31]; }
+        scratch[((int64_t)blockIdx.y * 2 + 0) * N + n] = ta;
+        scratch[((int64_t)blockIdx.y * 2 + 1) * N + n] = tb;
+    }
+}
+// first sums: column n < split -> out0[n], else out1[n - split]; second sums (MODE 1 only) -> out_b[n]
+__global__ void colred_finish_kernel(const float* __restrict__ scratch, float* __restrict__ out0, float* __restrict__ out1, int split,
+                                     float* __restrict__ out_b, int slices, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float ta = 0.f, tb = 0.f;
+    for (int s = 0; s < slices; ++s) { ta += scratch[((int64_t)s * 2 + 0) * N + n]; tb += scratch[((int64_t)s * 2 + 1) * N + n]; }
+    if (n < split) out0[n] = ta; else out1[n - split] = ta;
+    if (out_b != nullptr) out_b[n] = tb;
 }
 
 // column sums: out[n] (+)= sum_m X[m, n]
@@ -297,59 +485,106 @@ struct hb_mlp_model {
 
 namespace hb {
 
-// C[m, n] (+)= bias[n] + sum over the S partial results, in slice order
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-                                     int M, int N, int S, int accumulate) {
-    const int64_t total = (int64_t)M * N;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
-        float v = bias ? bias[n] : 0.f;
-        for (int z = 0; z < S; ++z) v += part[(int64_t)z * total + i];
-        float* c = C + (int64_t)m * ldc + n;
-        *c = accumulate ? *c + v : v;
+constexpr int64_t kPartFloats = 32ll * 128 * 1536;    // split-K partial buffer: up to 32 slices of the largest (stacked) weight gradient
+
+// ---- SGEMM driver ------------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
     }
+    return g_sm_count;
 }
 
-constexpr int64_t kPartFloats = 16ll * 64 * 1536;     // split-K partial buffer: up to 16 slices of the largest weight gradient
+template <int BM, int BN, int BK, int TM, int TN>
+static void sgemm_launch(const SgemmArgs& a, bool a_k, bool b_k, dim3 grid, cudaStream_t st) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    if (a_k && b_k) sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, NT, 0, st>>>(a);
+    else if (a_k) sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, NT, 0, st>>>(a);
+    else if (b_k) sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, NT, 0, st>>>(a);
+    else sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, NT, 0, st>>>(a);
+}
 
-// part != nullptr: GEMMs with few output tiles and a long K (the weight gradients: K = batch) are split over K so they fill
-// the GPU; partial sums go through `part` and are reduced in a fixed order.
-static int gemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
-                const float* bias, int M, int N, int K, int accumulate, cudaStream_t st, float* part = nullptr) {
-    dim3 grid(ceil_div(N, kTile), ceil_div(M, kTile));
+// part / part_floats: split-K scratch (nullptr: never split).  Large outputs get 128 x 128 tiles, small ones 64 x 64; products
+// whose tiles do not fill the GPU and whose K is long (the weight gradients: K = batch; the first layer: K = 1536) are split over K.
+static int sgemm(SgemmArgs a, bool a_k, bool b_k, cudaStream_t st, float* part, int64_t part_floats) {
+    if (a.M <= 0 || a.N <= 0) return HB_OK;
+    if (a.C1 == nullptr) { a.C1 = a.C0; a.csplit = a.M; }
+    if (a.B1 == nullptr) { a.B1 = a.B0; a.bsplit = 1 << 30; }
+    if (a.bias1 == nullptr) { a.bias1 = a.bias0; a.biassplit = 1 << 30; }
+    // 128 x 128 tiles when they (times the K slices a long K allows) fill the GPU; otherwise 64 x 64 tiles for more CTAs
+    const int tiles128 = ceil_div(a.M, 128) * ceil_div(a.N, 128);
+    const bool big = a.M >= 128 && a.N >= 128 && (tiles128 >= sm_count() * 3 / 4 || (part != nullptr && a.K >= 1024));
+    const int bm = big ? 128 : 64, bn = big ? 128 : 64;
+    dim3 grid(ceil_div(a.N, bn), ceil_div(a.M, bm), 1);
     const int tiles = (int)(grid.x * grid.y);
     int S = 1;
-    if (part != nullptr && tiles < 148 && K >= 512) {
-        S = std::min(std::min(K / 128, 32), ceil_div(2 * 148, tiles));
-        while (S > 1 && (int64_t)S * M * N > kPartFloats) --S;
+    if (part != nullptr && tiles < sm_count() && a.K >= 512) {
+        S = std::min(std::min(a.K / 256, 32), ceil_div(2 * sm_count(), tiles));     // slices of at least 256 k
+        while (S > 1 && (int64_t)S * a.M * a.N > part_floats) --S;
     }
-    if (S <= 1) {
-        gemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, C, ldc, bias, M, N, K, accumulate, K);
-        HB_LAUNCHED();
-        return HB_OK;
-    }
-    const int k_per = ceil_div(ceil_div(K, S), kTk) * kTk;
-    grid.z = ceil_div(K, k_per);
-    gemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, part, N, nullptr, M, N, K, 0, k_per);
+    a.k_per_split = S > 1 ? ceil_div(ceil_div(a.K, S), 16) * 16 : a.K;
+    a.part = part;
+    grid.z = S > 1 ? ceil_div(a.K, a.k_per_split) : 1;
+    if (big) sgemm_launch<128, 128, 8, 8, 8>(a, a_k, b_k, grid, st);
+    else sgemm_launch<64, 64, 16, 4, 4>(a, a_k, b_k, grid, st);
     HB_LAUNCHED();
-    const int64_t total = (int64_t)M * N;
-    splitk_reduce_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 1184), 256, 0, st>>>(part, C, ldc, bias, M, N, (int)grid.z, accumulate);
+    if (grid.z > 1) {
+        const int64_t total = (int64_t)a.M * a.N;
+        sgemm_reduce_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 8 * sm_count()), 256, 0, st>>>(a, (int)grid.z);
+        HB_LAUNCHED();
+    }
+    return HB_OK;
+}
+
+static SgemmArgs sgemm_args(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int M, int N, int K) {
+    SgemmArgs a;
+    a.A = A; a.lda = lda;
+    a.B0 = B; a.B1 = nullptr; a.bsplit = 0; a.ldb = ldb;
+    a.C0 = C; a.C1 = nullptr; a.csplit = 0; a.ldc = ldc;
+    a.bias0 = bias; a.bias1 = nullptr; a.biassplit = 0;
+    a.part = nullptr;
+    a.M = M; a.N = N; a.K = K; a.k_per_split = K;
+    return a;
+}
+
+// bias gradients: column sums of X [M][N] -> out0 (columns < split) / out1
+static int colsum(const float* X, int M, int N, float* out0, float* out1, int split, float* scratch, cudaStream_t st) {
+    const int slices = std::max(1, std::min(kColSlices, M / 64));
+    colred_kernel<0><<<dim3(ceil_div(N, 32), slices), 256, 0, st>>>(X, nullptr, nullptr, nullptr, scratch, M, N);
+    HB_LAUNCHED();
+    colred_finish_kernel<<<ceil_div(N, 256), 256, 0, st>>>(scratch, out0, out1 ? out1 : out0, out1 ? split : N, nullptr, slices, N);
     HB_LAUNCHED();
     return HB_OK;
 }
-// y[B,N] = x[B,K] W[N,K]^T + b
+// LayerNorm parameter gradients: dgamma[n] = sum_m dy * xhat, dbeta[n] = sum_m dy
+static int ln_param_grads(const float* dy, const float* x, const float* mean, const float* rstd, float* dgamma, float* dbeta, int M, int N,
+                          float* scratch, cudaStream_t st) {
+    const int slices = std::max(1, std::min(kColSlices, M / 64));
+    colred_kernel<1><<<dim3(ceil_div(N, 32), slices), 256, 0, st>>>(dy, x, mean, rstd, scratch, M, N);
+    HB_LAUNCHED();
+    colred_finish_kernel<<<ceil_div(N, 256), 256, 0, st>>>(scratch, dgamma, dgamma, N, dbeta, slices, N);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+// y[B,N] = x[B,K] W[N,K]^T + b  (kept for the stacked multi-model forward)
 static int linear_fwd(const float* x, const float* W, const float* b, float* y, int B, int N, int K, cudaStream_t st, float* part = nullptr) {
-    return gemm(x, K, 1, W, 1, K, y, N, b, B, N, K, 0, st, part);
+    return sgemm(sgemm_args(x, K, W, K, y, N, b, B, N, K), true, true, st, part, kPartFloats);
 }
 
 // workspace carve-up (floats)
 struct Ws {
     float *xn, *mean[kStages], *rstd[kStages];
     float *u[kStages];       // LN output = stage input (u[0] = xn)
-    float *h[kStages], *g[kStages], *a[kStages], *o[kStages];
-    float *dz, *d_o, *d_a, *d_h, *d_g, *d_u, *d_x;
-    float* stats_tmp;
+    float *hg[kStages];      // [B][128]: hidden | gate pre-activations (one stacked product)
+    float *a[kStages], *o[kStages];
+    float *dz, *d_o[2], *d_a, *d_hg, *d_u;
     float* part;             // split-K partial sums
+    float* colred;           // column-reduction partials [kColSlices][2][1536]
 };
 static int64_t carve(Ws* w, float* base, int B, int training) {
     int64_t off = 0;
@@ -359,22 +594,21 @@ static int64_t carve(Ws* w, float* base, int B, int training) {
         w->u[s] = take((int64_t)B * in_dim);
         w->mean[s] = take(B);
         w->rstd[s] = take(B);
-        w->h[s] = take((int64_t)B * kHid);
-        w->g[s] = take((int64_t)B * kHid);
+        w->hg[s] = take((int64_t)B * 2 * kHid);
         w->a[s] = take((int64_t)B * kHid);
         w->o[s] = take((int64_t)B * out_dim);
     }
     w->xn = w->u[0];
     if (training) {
         w->dz = take(B);
-        w->d_o = take((int64_t)B * kDim);
+        w->d_o[0] = take((int64_t)B * kDim);
+        w->d_o[1] = take((int64_t)B * kDim);
         w->d_a = take((int64_t)B * kHid);
-        w->d_h = take((int64_t)B * kHid);
-        w->d_g = take((int64_t)B * kHid);
+        w->d_hg = take((int64_t)B * 2 * kHid);
         w->d_u = take((int64_t)B * kIn);
-        w->d_x = take((int64_t)B * kDim);
     }
     w->part = take(kPartFloats);
+    w->colred = take((int64_t)kColSlices * 2 * kIn);
     return off;
 }
 
@@ -385,12 +619,15 @@ static int forward_impl(const hb_mlp_model* m, const float* x, int B, const Ws& 
         ln_fwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(cur, m->p + L.ln_w, m->p + L.ln_b, w.u[s], w.mean[s], w.rstd[s], B, L.in_dim);
         HB_LAUNCHED();
         int rc;
-        if ((rc = linear_fwd(w.u[s], m->p + L.hw, m->p + L.hb, w.h[s], B, kHid, L.in_dim, st, w.part))) return rc;
-        if ((rc = linear_fwd(w.u[s], m->p + L.gw, m->p + L.gb, w.g[s], B, kHid, L.in_dim, st, w.part))) return rc;
+        // hidden and gate linears share their input: ONE product against the stacked [W_h; W_g]
+        SgemmArgs hg = sgemm_args(w.u[s], L.in_dim, m->p + L.hw, L.in_dim, w.hg[s], 2 * kHid, m->p + L.hb, B, 2 * kHid, L.in_dim);
+        hg.B1 = m->p + L.gw; hg.bsplit = kHid;
+        hg.bias1 = m->p + L.gb; hg.biassplit = kHid;
+        if ((rc = sgemm(hg, true, true, st, w.part, kPartFloats))) return rc;
         const int64_t n = (int64_t)B * kHid;
-        gate_fwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.h[s], w.g[s], w.a[s], n);
+        gate_hg_fwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.hg[s], w.a[s], n);
         HB_LAUNCHED();
-        if ((rc = linear_fwd(w.a[s], m->p + L.ow, m->p + L.ob, w.o[s], B, L.out_dim, kHid, st))) return rc;
+        if ((rc = sgemm(sgemm_args(w.a[s], kHid, m->p + L.ow, kHid, w.o[s], L.out_dim, m->p + L.ob, B, L.out_dim, kHid), true, true, st, nullptr, 0))) return rc;
         cur = w.o[s];
     }
     return HB_OK;
@@ -766,36 +1003,33 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
     head_finish_kernel<<<1, 1, 0, st>>>(stats_dev, n_total_dev, B, min_selected);
     HB_LAUNCHED();
     const float* d_out = w.dz;   // gradient wrt the stage's output o[s]
+    int flip = 0;
     for (int s = kStages - 1; s >= 0; --s) {
         const StageOff& L = kLayout.s[s];
         const int in_dim = L.in_dim, out_dim = L.out_dim;
-        // output linear: dW_o = d_out^T a, db_o = colsum(d_out), d_a = d_out W_o
-        if ((rc = gemm(d_out, 1, out_dim, w.a[s], kHid, 1, m->g + L.ow, kHid, nullptr, out_dim, kHid, B, 0, st, w.part))) return rc;
-        colsum_kernel<<<ceil_div(out_dim, 32), 256, 0, st>>>(d_out, m->g + L.ob, B, out_dim, 0);
-        HB_LAUNCHED();
-        if ((rc = gemm(d_out, out_dim, 1, m->p + L.ow, kHid, 1, w.d_a, kHid, nullptr, B, kHid, out_dim, 0, st))) return rc;
+        // output linear: dW_o [out,64] = d_out^T a, db_o = colsum(d_out), d_a [B,64] = d_out W_o
+        if ((rc = sgemm(sgemm_args(d_out, out_dim, w.a[s], kHid, m->g + L.ow, kHid, nullptr, out_dim, kHid, B), false, false, st, w.part, kPartFloats))) return rc;
+        if ((rc = colsum(d_out, B, out_dim, m->g + L.ob, nullptr, 0, w.colred, st))) return rc;
+        if ((rc = sgemm(sgemm_args(d_out, out_dim, m->p + L.ow, kHid, w.d_a, kHid, nullptr, B, kHid, out_dim), true, false, st, nullptr, 0))) return rc;
         const int64_t n = (int64_t)B * kHid;
-        gate_bwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.h[s], w.g[s], w.d_a, w.d_h, w.d_g, n);
+        gate_hg_bwd_kernel<<<(int)std::min<int64_t>(ceil_div64(n, 256), 1184), 256, 0, st>>>(w.hg[s], w.d_a, w.d_hg, n);
         HB_LAUNCHED();
-        // hidden / gate linears: dW = d^T u, db = colsum(d), d_u = d_h W_h + d_g W_g
-        if ((rc = gemm(w.d_h, 1, kHid, w.u[s], in_dim, 1, m->g + L.hw, in_dim, nullptr, kHid, in_dim, B, 0, st, w.part))) return rc;
-        if ((rc = gemm(w.d_g, 1, kHid, w.u[s], in_dim, 1, m->g + L.gw, in_dim, nullptr, kHid, in_dim, B, 0, st, w.part))) return rc;
-        colsum_kernel<<<ceil_div(kHid, 32), 256, 0, st>>>(w.d_h, m->g + L.hb, B, kHid, 0);
-        HB_LAUNCHED();
-        colsum_kernel<<<ceil_div(kHid, 32), 256, 0, st>>>(w.d_g, m->g + L.gb, B, kHid, 0);
-        HB_LAUNCHED();
-        if ((rc = gemm(w.d_h, kHid, 1, m->p + L.hw, in_dim, 1, w.d_u, in_dim, nullptr, B, in_dim, kHid, 0, st))) return rc;
-        if ((rc = gemm(w.d_g, kHid, 1, m->p + L.gw, in_dim, 1, w.d_u, in_dim, nullptr, B, in_dim, kHid, 1, st))) return rc;
+        // hidden / gate linears, stacked: dW [128,in] = d_hg^T u (rows < 64 -> hidden, else gate), db = colsum(d_hg), d_u = d_hg [W_h; W_g]
+        SgemmArgs dw = sgemm_args(w.d_hg, 2 * kHid, w.u[s], in_dim, m->g + L.hw, in_dim, nullptr, 2 * kHid, in_dim, B);
+        dw.C1 = m->g + L.gw; dw.csplit = kHid;
+        if ((rc = sgemm(dw, false, false, st, w.part, kPartFloats))) return rc;
+        if ((rc = colsum(w.d_hg, B, 2 * kHid, m->g + L.hb, m->g + L.gb, kHid, w.colred, st))) return rc;
+        SgemmArgs du = sgemm_args(w.d_hg, 2 * kHid, m->p + L.hw, in_dim, w.d_u, in_dim, nullptr, B, in_dim, 2 * kHid);
+        du.B1 = m->p + L.gw; du.bsplit = kHid;
+        if ((rc = sgemm(du, true, false, st, nullptr, 0))) return rc;
         // LayerNorm: parameter grads always, input grad unless the input is the data
         const float* ln_in = (s == 0) ? x_dev : w.o[s - 1];
-        ln_bwd_params_kernel<<<ceil_div(in_dim, 32), 256, 0, st>>>(w.d_u, ln_in, w.mean[s], w.rstd[s], m->g + L.ln_w, m->g + L.ln_b, B, in_dim);
-        HB_LAUNCHED();
+        if ((rc = ln_param_grads(w.d_u, ln_in, w.mean[s], w.rstd[s], m->g + L.ln_w, m->g + L.ln_b, B, in_dim, w.colred, st))) return rc;
         if (s > 0) {
-            ln_bwd_input_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.d_u, ln_in, m->p + L.ln_w, w.mean[s], w.rstd[s], w.d_x, B, in_dim);
+            ln_bwd_input_kernel<<<ceil_div(B, 8), 256, 0, st>>>(w.d_u, ln_in, m->p + L.ln_w, w.mean[s], w.rstd[s], w.d_o[flip], B, in_dim);
             HB_LAUNCHED();
-            // d_x becomes the next d_out; keep it in d_o so d_x can be rewritten
-            HB_CUDA_OK(cudaMemcpyAsync(w.d_o, w.d_x, (size_t)B * in_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            d_out = w.d_o;
+            d_out = w.d_o[flip];
+            flip ^= 1;
         }
     }
     return HB_OK;

@@ -175,7 +175,7 @@ def test_loss_scale_dropout_and_optimizer_checkpoint(cuda_device, tmp_path):
     np.testing.assert_allclose(sb[0].item(), sa[0].item() / 3.0, rtol=1e-6)
     ga, gb = a.gradients(), b.gradients()
     for k in ga:
-        np.testing.assert_allclose(gb[k], ga[k] / 3.0, rtol=1e-5, atol=1e-10)
+        np.testing.assert_allclose(gb[k], ga[k] / 3.0, rtol=1e-5, atol=1e-6 * np.abs(ga[k]).max())
 
     # (2) dropout mask == numpy Philox (key = seed, counter = (i / 4, 7, call), keep when the 24-bit uniform >= p)
     p, seed = 0.1, 1234
