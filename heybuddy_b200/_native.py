@@ -75,6 +75,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_rir_spectrum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_colored_bases": (c_int, [ctypes.c_uint64, c_vp, c_vp, c_int, c_vp, c_vp]),
         "hb_augment_clips_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_k9_eq_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_k9_tanh_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_fix_length_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_featurize_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
         "hb_featurize_i16": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),

@@ -1,0 +1,165 @@
+// K9: the reference's per-clip numpy augmentations on the device -- SevenBandParametricEQ and TanhDistortion
+// (audiomentations.Compose at reference src/python/heybuddy/dataset/augmented.py:79-90, applied to every length-fixed clip at
+// :325-328).  audiomentations is absent offline: both are restated from the library's published behaviour (parity unpinned; the
+// arithmetic spec and every constant live in heybuddy_b200/dataset/k9.py, the CPU restatement in oracle/k9.py).
+//
+// Both kernels work in place on the f32 [n][T] length-fixed clips and touch only the clips whose coin came up (index lists from
+// the draw table), so a chunk with the reference's default probabilities (0.25 each) pays for a quarter of its clips.
+#include "hb_common.cuh"
+
+#include <math.h>
+
+namespace hb {
+
+constexpr int kEqBands = 7;
+
+// ---- SevenBandParametricEQ: seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt) ----------------------------
+// An IIR cascade is a serial recurrence in time; the parallelism is ACROSS clips: one thread per equalised clip runs the whole
+// cascade in float64 (what sosfilt computes in; direct form II transposed).  Within a thread the seven sections of one sample and
+// the state updates of the previous one overlap in the FP64 pipe, so the latency-bound chain is ~2 dependent FMAs per sample.
+__global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, const int32_t* __restrict__ clip_index,
+                                                   const double* __restrict__ sos, int k, int T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    double b0[kEqBands], b1[kEqBands], b2[kEqBands], a1[kEqBands], a2[kEqBands], z1[kEqBands], z2[kEqBands];
+#pragma unroll
+    for (int s = 0; s < kEqBands; ++s) {
+        const double* c = sos + ((int64_t)i * kEqBands + s) * 5;
+        b0[s] = c[0]; b1[s] = c[1]; b2[s] = c[2]; a1[s] = c[3]; a2[s] = c[4];
+        z1[s] = 0.0; z2[s] = 0.0;
+    }
+    float* x = clips + (int64_t)clip_index[i] * T;
+    auto step = [&](float v) {
+        double y = (double)v;
+#pragma unroll
+        for (int s = 0; s < kEqBands; ++s) {
+            const double in = y;
+            y = fma(b0[s], in, z1[s]);
+            z1[s] = fma(b1[s], in, fma(-a1[s], y, z2[s]));
+            z2[s] = fma(b2[s], in, -a2[s] * y);
+        }
+        return (float)y;
+    };
+    int t = 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        for (; t + 3 < T; t += 4) {
+            float4 v = *reinterpret_cast<const float4*>(x + t);
+            v.x = step(v.x); v.y = step(v.y); v.z = step(v.z); v.w = step(v.w);
+            *reinterpret_cast<float4*>(x + t) = v;
+        }
+    for (; t < T; ++t) x[t] = step(x[t]);
+}
+
+// ---- TanhDistortion ------------------------------------------------------------------------------------------------------------------
+// threshold = np.percentile(|x|, 100 - 99 * amount) (linear interpolation between the two neighbouring order statistics); the order
+// statistics come from an exact radix select over the bit patterns of |x| (non-negative floats order like their bits): four 8-bit
+// passes per rank over the clip's magnitudes in shared memory.
+constexpr int kTanhThreads = 512;
+
+__device__ __forceinline__ uint32_t radix_select(const uint32_t* __restrict__ bits, int n, int rank, uint32_t* hist, uint32_t* bcast) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = rank;                 // rank among the elements that match the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += kTanhThreads) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kTanhThreads) {
+            const uint32_t v = bits[i];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0, b = 0;
+            for (; b < 256; ++b) {
+                const int c = (int)hist[b];
+                if (remaining < acc + c) break;
+                acc += c;
+            }
+            bcast[0] = (uint32_t)b;
+            bcast[1] = (uint32_t)(remaining - acc);
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= 255u << shift;
+        remaining = (int)bcast[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__device__ __forceinline__ float block_sum_512(float v, float* scratch) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < kTanhThreads / 32 ? scratch[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__global__ void __launch_bounds__(kTanhThreads) k9_tanh_kernel(float* __restrict__ clips, const int32_t* __restrict__ clip_index,
+                                                               const float* __restrict__ amount, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t bcast[2];
+    __shared__ float scratch[40];
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_raw);
+    float* x = clips + (int64_t)clip_index[blockIdx.x] * T;
+    for (int i = threadIdx.x; i < T; i += kTanhThreads) bits[i] = __float_as_uint(fabsf(x[i]));
+    __syncthreads();
+    // np.percentile(..., q) with q = 100 - 99 * amount: virtual index q / 100 * (n - 1), linear interpolation
+    const double q = 100.0 - 99.0 * (double)amount[blockIdx.x];
+    const double pos = q / 100.0 * (double)(T - 1);
+    int lo = (int)floor(pos);
+    lo = max(0, min(lo, T - 1));
+    const int hi = min(lo + 1, T - 1);
+    const float frac = (float)(pos - (double)lo);
+    const float v_lo = __uint_as_float(radix_select(bits, T, lo, hist, bcast));
+    const float v_hi = hi == lo ? v_lo : __uint_as_float(radix_select(bits, T, hi, hist, bcast));
+    const float threshold = v_lo + frac * (v_hi - v_lo);
+    const float gain = 0.5f / (threshold + 1e-6f);
+    float* y = reinterpret_cast<float*>(smem_raw);      // the magnitudes are not needed any more
+    float sx = 0.f, sy = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += kTanhThreads) {
+        const float v = x[i];
+        const float d = tanhf(gain * v);
+        y[i] = d;
+        sx = fmaf(v, v, sx);
+        sy = fmaf(d, d, sy);
+    }
+    const float rms_before = sqrtf(block_sum_512(sx, scratch) / (float)T);
+    const float rms_after = sqrtf(block_sum_512(sy, scratch) / (float)T);
+    const float post = rms_before > 1e-9f ? rms_before / rms_after : 1.0f;
+    for (int i = threadIdx.x; i < T; i += kTanhThreads) x[i] = y[i] * post;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream) {
+    HB_REQUIRE(k >= 0 && T > 0 && (k == 0 || (clips_dev && clip_index_dev && sos_dev)), "hb_k9_eq_f32: bad argument");
+    if (k == 0) return HB_OK;
+    // 16 threads per block: the kernel is latency bound per clip, so spread the clips over as many SMs as possible
+    k9_eq_kernel<<<ceil_div(k, 16), 16, 0, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, sos_dev, k, T);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+extern "C" int hb_k9_tanh_f32(float* clips_dev, const int32_t* clip_index_dev, const float* amount_dev, int k, int T, void* stream) {
+    HB_REQUIRE(k >= 0 && T > 0 && T <= 24576 && (k == 0 || (clips_dev && clip_index_dev && amount_dev)), "hb_k9_tanh_f32: bad argument (T <= 24576)");
+    if (k == 0) return HB_OK;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(k9_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24576 * 4));
+        configured = true;
+    }
+    k9_tanh_kernel<<<k, kTanhThreads, (size_t)T * 4, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, amount_dev, T);
+    HB_LAUNCHED();
+    return HB_OK;
+}

@@ -80,6 +80,7 @@ class DeviceChunk:
     colored_f_decay: Optional["object"]  # cuda f32 [k]
     n: int
     seed: int = 0
+    k9: Optional[tuple] = None          # (eq idx i32[ke], eq sos f64[ke,7,5], tanh idx i32[kt], tanh amount f32[kt]) on the device
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -109,10 +110,19 @@ class FeaturizePipeline:
         _, ids, f_decay = table.colored_slots()
         return np.ascontiguousarray(table.pad_before, dtype=np.int32), params, ids, f_decay
 
-    def _meta_layout(self, n: int, k: int) -> Tuple[Dict[str, Tuple[int, int]], int]:
-        """Byte ranges of the per-chunk metadata blob: offsets i64[n+1], pads i32[n], params [n][32], ids i64[k], f_decay f32[k]."""
+    @staticmethod
+    def _k9_counts(table: DrawTable) -> Tuple[int, int]:
+        return (0, 0) if table.k9 is None else (int(np.count_nonzero(table.k9.eq_apply)), int(np.count_nonzero(table.k9.tanh_apply)))
+
+    def _meta_layout(self, n: int, k: int, k9: Tuple[int, int] = (0, 0)) -> Tuple[Dict[str, Tuple[int, int]], int]:
+        """
+        Byte ranges of the per-chunk metadata blob: offsets i64[n+1], pads i32[n], params [n][32], ids i64[k], f_decay f32[k] and,
+        when K9 transforms were drawn, eq clip indices i32[ke] + sos f64[ke][7][5] and tanh clip indices i32[kt] + amounts f32[kt].
+        """
+        ke, kt = k9
         lay, at = {}, 0
-        for name, nbytes in (("offsets", 8 * (n + 1)), ("pads", 4 * n), ("params", 32 * n), ("ids", 8 * k), ("fd", 4 * k)):
+        for name, nbytes in (("offsets", 8 * (n + 1)), ("pads", 4 * n), ("params", 32 * n), ("ids", 8 * k), ("fd", 4 * k),
+                             ("eq_idx", 4 * ke), ("eq_sos", 8 * 35 * ke), ("th_idx", 4 * kt), ("th_amt", 4 * kt)):
             lay[name] = (at, nbytes)
             at = _align(at + nbytes)
         return lay, max(at, 256)
@@ -121,9 +131,12 @@ class FeaturizePipeline:
         pads, params, ids, fd = self.pack_params(table)
         n, k = len(clips), int(ids.shape[0])
         assert params.shape[0] == n == pads.shape[0], (params.shape, pads.shape, n)
-        lay, total = self._meta_layout(n, k)
+        lay, total = self._meta_layout(n, k, self._k9_counts(table))
         assert blob.nbytes >= total
-        for name, arr in (("offsets", clips.offsets), ("pads", pads), ("params", params), ("ids", ids), ("fd", fd)):
+        arrays = [("offsets", clips.offsets), ("pads", pads), ("params", params), ("ids", ids), ("fd", fd)]
+        if table.k9 is not None:
+            arrays += list(zip(("eq_idx", "eq_sos", "th_idx", "th_amt"), table.k9.pack()))
+        for name, arr in arrays:
             at, nbytes = lay[name]
             if nbytes:
                 blob[at:at + nbytes] = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
@@ -137,17 +150,22 @@ class FeaturizePipeline:
             at, nbytes = lay[name]
             return meta_dev[at:at + nbytes].view(dtype).view(shape)
 
+        ke, kt = lay["eq_idx"][1] // 4, lay["th_idx"][1] // 4
+        k9 = None
+        if ke or kt:
+            k9 = (view("eq_idx", torch.int32, (ke,)), view("eq_sos", torch.float64, (ke, 7, 5)), view("th_idx", torch.int32, (kt,)),
+                  view("th_amt", torch.float32, (kt,)))
         return DeviceChunk(
             samples=samples_dev, offsets=view("offsets", torch.int64, (n + 1,)), pad_before=view("pads", torch.int32, (n,)),
             params=view("params", torch.uint8, (n, 32)), colored_ids=view("ids", torch.int64, (k,)) if k else None,
-            colored_f_decay=view("fd", torch.float32, (k,)) if k else None, n=n, seed=seed)
+            colored_f_decay=view("fd", torch.float32, (k,)) if k else None, n=n, seed=seed, k9=k9)
 
     def upload(self, clips: RaggedClips, table: DrawTable) -> DeviceChunk:
         """Synchronous upload of one chunk (tests, the bench's device-resident leg)."""
         import torch
 
         n = len(clips)
-        _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)))
+        _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_counts(table))
         blob = np.zeros(total, dtype=np.uint8)
         lay, total, k = self._fill_meta(blob, clips, table)
         dev = self.device
@@ -217,7 +235,7 @@ class FeaturizePipeline:
                 bases_ptr = bases.data_ptr()
             self._mark("colored")
             banks = (nb.stream.data_ptr() if nb is not None else None, bases_ptr, rb.spec.data_ptr() if rb is not None else None)
-            if t == spec.CLIP_SAMPLES and not keep_audio and not self.profile:
+            if t == spec.CLIP_SAMPLES and not keep_audio and not self.profile and chunk.k9 is None:
                 # one C-ABI call for the whole path (hb_featurize_i16 = augment_i16 -> mel -> embed on one workspace)
                 emb_model = self.speech.embeddings
                 if not emb_model.loaded:
@@ -235,7 +253,7 @@ class FeaturizePipeline:
                     out.data_ptr(), n, t, ws.data_ptr(), int(ws.numel()), st), "hb_featurize_i16")
                 return out
             audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
-            if t == spec.CLIP_SAMPLES:
+            if t == spec.CLIP_SAMPLES and chunk.k9 is None:
                 # length fix fused into the augmentation kernel's load: int16 samples -> shared memory, no f32 intermediate
                 _native.check(lib.hb_augment_clips_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
                                                        *banks, chunk.params.data_ptr(), audio.data_ptr(), n, t, st), "hb_augment_clips_i16")
@@ -243,6 +261,15 @@ class FeaturizePipeline:
                 fixed = self._buf("fixed", (n, t), torch.float32)
                 _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
                                                     fixed.data_ptr(), n, t, st), "hb_fix_length_i16")
+                if chunk.k9 is not None:
+                    # K9: the reference's per-clip numpy transforms sit between the length fix and the batch transforms
+                    # (augmented.py:325-328): SevenBandParametricEQ, then TanhDistortion, in place on the selected clips
+                    eq_idx, eq_sos, th_idx, th_amt = chunk.k9
+                    if eq_idx.numel():
+                        _native.check(lib.hb_k9_eq_f32(fixed.data_ptr(), eq_idx.data_ptr(), eq_sos.data_ptr(), int(eq_idx.numel()), t, st), "hb_k9_eq_f32")
+                    if th_idx.numel():
+                        _native.check(lib.hb_k9_tanh_f32(fixed.data_ptr(), th_idx.data_ptr(), th_amt.data_ptr(), int(th_idx.numel()), t, st), "hb_k9_tanh_f32")
+                    self._mark("k9")
                 _native.check(lib.hb_augment_clips_f32(fixed.data_ptr(), *banks, chunk.params.data_ptr(), audio.data_ptr(), n, t, st),
                               "hb_augment_clips_f32")
             self._mark("augment")
@@ -358,7 +385,7 @@ class FeaturizePipeline:
             blocked(stage_events[slot])          # the H2D that last read this slot's pinned staging buffers must have finished
             while len(done_events) > 0 and k - done_events[0][0] >= MAX_INFLIGHT:
                 blocked(done_events.popleft()[1])
-            _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)))
+            _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_counts(table))
             meta_pin = pinned("meta", slot, total, torch.uint8)
             lay, total, kc = self._fill_meta(meta_pin.numpy(), part, table)
             if part.pinned is not None:

@@ -132,6 +132,14 @@ int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-f
                          const hb_clip_aug* params_dev,   /* [n] device array                          */
                          float* out_dev, int n, int T, void* stream);
 
+/* ---- K9: the reference's per-clip numpy augmentations (audiomentations.Compose, augmented.py:79-90, applied at :325-328) ----
+ * In place on the f32 [n][T] length-fixed clips, only on the clips listed in clip_index_dev (the ones whose coin came up).
+ * hb_k9_eq_f32:   SevenBandParametricEQ = seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt), float64
+ *                 arithmetic; sos_dev f64 [k][7][5] = (b0, b1, b2, a1, a2) / a0 per section (computed on the host from the draws).
+ * hb_k9_tanh_f32: TanhDistortion = tanh(x * 0.5 / (percentile(|x|, 100 - 99 amount) + 1e-6)), RMS-matched to the input. */
+int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream);
+int hb_k9_tanh_f32(float* clips_dev, const int32_t* clip_index_dev, const float* amount_dev, int k, int T, void* stream);
+
 /* a1: int16 ragged clips -> length-fixed f32 [n][T] (to_target_length, augmented.py:200-232):
  * /32768, front-truncate when longer than T, otherwise zero-pad with pad_before[b] zeros on
  * the left.  samples_dev: concatenated int16 samples; offsets_dev i64[n+1]; pad_before_dev i32[n]. */

@@ -130,11 +130,15 @@ def augment_table(clips, table, noise_stream: Optional[np.ndarray], noise_clip_s
     """
     from oracle import augment as oaug
 
+    from oracle import k9 as ok9
+
     t = table.cfg.target_samples
     out, i0 = [], 0
-    for d, ncur, ridx in zip(table.batches, table.noise_clip_cursor, table.rir_index):
+    for k, (d, ncur, ridx) in enumerate(zip(table.batches, table.noise_clip_cursor, table.rir_index)):
         b = len(d.pad_before)
         fixed = np.stack([oaug.to_target_length(c, int(p), t) for c, p in zip(clips[i0:i0 + b], d.pad_before)])
+        if table.k9 is not None:      # the per-clip numpy transforms come first (augmented.py:325-328)
+            fixed = ok9.apply_table(fixed, table.slice(k, k + 1))
         noise = None
         if d.background_apply:
             off = int(noise_clip_starts[ncur])

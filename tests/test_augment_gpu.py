@@ -187,6 +187,7 @@ def test_colored_bases_device_matches_host_restatement(cuda_device):
 
 
 def test_unsupported_transforms_raise():
+    """PitchShift and BandStopFilter are not built (heybuddy_b200/dataset/k9.py): a non-zero probability raises."""
     from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
 
     with pytest.raises(NotImplementedError):
