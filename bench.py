@@ -334,6 +334,20 @@ def h2d_bandwidth(device, world, dist, mb=256, reps=6):
     return [float(gbs)]
 
 
+class stdout_to_stderr:
+    """Temporarily points file descriptor 1 at stderr (library banners printed from C must not precede the JSON line)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def sink_bandwidth(out_dir, world, dist, device, mb=24, blocks=24, threads=4):
     """
     Rate at which this box turns freshly downloaded rows into `.npy` pages, every rank at once (GB/s per rank): `threads` workers
@@ -346,16 +360,25 @@ def sink_bandwidth(out_dir, world, dist, device, mb=24, blocks=24, threads=4):
     src = torch.empty((blocks, mb << 20), dtype=torch.uint8).pin_memory()
     src.copy_(torch.randint(0, 255, (blocks, mb << 20), dtype=torch.uint8, device=device))     # written by DMA: cold in the CPU caches
     torch.cuda.synchronize()
-    path = os.path.join(out_dir, f"sink_probe_{rank}.bin")
-    with open(path, "wb") as fh:
-        fh.truncate(blocks * (mb << 20))
+    # ONE file shared by all ranks, every rank its own range -- the way generate_sharded's .npy is written
+    path = os.path.join(out_dir, "sink_probe.bin")
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.truncate(world * blocks * (mb << 20))
+    if world > 1:
+        dist.barrier()
+    mode = os.environ.get("HEYBUDDY_B200_SINK") or ("mmap" if world > 1 else "pwrite")      # NpyRowWriter's choice
     fd = os.open(path, os.O_RDWR)
     arr = src.numpy()
+    mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(world * blocks, mb << 20)) if mode == "mmap" else None
 
     def w(i):
+        if mm is not None:
+            np.copyto(mm[rank * blocks + i], arr[i])
+            return
         buf, at = memoryview(arr[i]).cast("B"), 0
         while at < len(buf):
-            at += os.pwrite(fd, buf[at:], i * (mb << 20) + at)
+            at += os.pwrite(fd, buf[at:], (rank * blocks + i) * (mb << 20) + at)
 
     if world > 1:
         dist.barrier()
@@ -363,8 +386,12 @@ def sink_bandwidth(out_dir, world, dist, device, mb=24, blocks=24, threads=4):
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(w, range(blocks)))
     dt = time.perf_counter() - t0
+    del mm
     os.close(fd)
-    os.remove(path)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        os.remove(path)
     gbs = torch.tensor([blocks * (mb << 20) / dt / 1e9], dtype=torch.float64, device=device)
     if world > 1:
         out = [torch.zeros_like(gbs) for _ in range(world)]
@@ -401,7 +428,9 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        with stdout_to_stderr():     # NCCL prints its version banner on stdout; the contract is ONE JSON line there
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
     precision = args.precision or DEFAULT_EMBED_PRECISION
     lib = _native.load()
 
@@ -587,7 +616,7 @@ def main():
                                        "api": "TrainingFeaturesGenerator.generate(n, out=<pinned tensor>): the same path with the rows left in host memory"},
                     "frac_of_host_bound": e2e_value / host_bound if host_bound > 0 else None,
                     "bounds_note": "measured in this run with all ranks active: pinned H2D copy rate (input: ragged int16, the smallest lossless form) and the rate "
-                                   "at which the box turns downloaded f32 rows into .npy page-cache pages (pwrite, 4 threads per rank); the e2e leg cannot beat the "
+                                   "at which the box turns downloaded f32 rows into page-cache pages of ONE shared file (4 threads per rank, the writer's mode); the e2e leg cannot beat the "
                                    "smaller of the two whatever the kernels do",
                     "workload": f"BASELINE configs[2] shape: {per_file} positive + {per_file} adversarial clips -> bench_phrase.npy + bench_phrase_adv.npy "
                                 f"f32 [{per_file},16,96] ({world} rank(s), each writing its own row range), re-opened through PrecalculatedDatasetIterator",

@@ -51,7 +51,11 @@ def _dist():
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import bench
+
+        with bench.stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
 
     def barrier():
         if world > 1:

@@ -401,14 +401,14 @@ class TrainingFeaturesGenerator:
         lo_b, hi_b = shard_batches(n_batches, self.rank, self.world_size)
         lo, hi = lo_b * b, min(hi_b * b, num_samples)
         shape = (num_samples, len(spec.embedding_frame_offsets(spec.CLIP_SAMPLES)), spec.EMB_DIM)
-        writer = NpyRowWriter(path, shape, create=self.rank == 0, barrier=barrier)
+        writer = NpyRowWriter(path, shape, create=self.rank == 0, barrier=barrier, shared=self.world_size > 1)
         mapped = None
         try:
             if hi > lo:
                 # opt-in on memory-backed file systems: the D2H copies land in the file's own (registered) pages; otherwise rows go
                 # from the pipeline's pinned slots into the file with pwrite
                 mapped = writer.map_pinned(lo, hi, populate_threads=writer_threads)
-                self.last_sink = "pinned file mapping (D2H straight into the page cache)" if mapped is not None else "pwrite from pinned slots"
+                self.last_sink = "pinned file mapping (D2H straight into the page cache)" if mapped is not None else f"{writer.mode} from pinned slots"
                 if mapped is not None:
                     sink_of = lambda r0, r1: mapped[r0:r1]
                 else:

@@ -66,7 +66,7 @@ class NpyRowWriter:
     page of the file is ever faulted into this process the way a memmap store would.
     """
 
-    def __init__(self, path: str, shape, create: bool = True, barrier=None, dtype=np.float32) -> None:
+    def __init__(self, path: str, shape, create: bool = True, barrier=None, dtype=np.float32, shared: bool = False) -> None:
         self.path, self.shape, self.dtype = path, tuple(int(x) for x in shape), np.dtype(dtype)
         self.row_bytes = int(np.prod(self.shape[1:])) * self.dtype.itemsize
         if create:
@@ -87,15 +87,37 @@ class NpyRowWriter:
             self.data_offset = fh.tell()
         assert tuple(got_shape) == self.shape and not fortran and got_dtype == self.dtype, (got_shape, self.shape, got_dtype)
         self._mapped = []
+        # one writer process: positional writes were the faster way into the page cache (10.8 vs 16.0 ms per 8192-clip step);
+        # several ranks sharing the file: pwrite serialises on the inode lock (27.8 ms at two ranks), stores through a shared
+        # mapping do not (21.2 ms) -- measured on the round-2 bench boxes, profiles/README.md "e2e sink"
+        self.mode = os.environ.get("HEYBUDDY_B200_SINK") or ("mmap" if shared else "pwrite")
+        assert self.mode in ("mmap", "pwrite"), self.mode
+        self._mm = None
+        self._mm_lock = Lock()
 
     def write(self, row: int, rows: np.ndarray) -> None:
-        """Rows ``[row, row + len(rows))`` <- ``rows`` (C-contiguous, the file's dtype).  Thread-safe (positional writes)."""
+        """
+        Rows ``[row, row + len(rows))`` <- ``rows`` (C-contiguous, the file's dtype).  Thread-safe.  Two ways into the page cache
+        (``HEYBUDDY_B200_SINK`` overrides the choice made in ``__init__``): ``pwrite`` issues positional writes, which Linux file
+        systems serialise on the inode's write lock; ``mmap`` stores through a shared mapping -- a page fault per new page, no
+        per-file lock, so the writer threads of several ranks fill one file side by side.
+        """
         assert rows.dtype == self.dtype and rows.flags.c_contiguous and rows.shape[1:] == self.shape[1:]
         assert 0 <= row and row + rows.shape[0] <= self.shape[0]
+        if self.mode == "mmap":
+            np.copyto(self._memmap()[row:row + rows.shape[0]], rows)
+            return
         buf = memoryview(rows).cast("B")
         at, off = 0, self.data_offset + row * self.row_bytes
         while at < len(buf):
             at += os.pwrite(self.fd, buf[at:], off + at)
+
+    def _memmap(self) -> np.ndarray:
+        if self._mm is None:
+            with self._mm_lock:
+                if self._mm is None:
+                    self._mm = np.memmap(self.path, dtype=self.dtype, mode="r+", offset=self.data_offset, shape=self.shape)
+        return self._mm
 
     def map_pinned(self, row_lo: int, row_hi: int, populate_threads: int = 4):
         """
@@ -177,6 +199,9 @@ class NpyRowWriter:
             except BufferError:
                 pass          # a tensor view is still alive: the mapping goes away with it
         self._mapped = []
+        if self._mm is not None:
+            del self._mm           # dirty pages stay in the page cache like after a write(); no msync, np.save does none either
+            self._mm = None
         if self.fd is not None:
             os.close(self.fd)
             self.fd = None
