@@ -6,7 +6,8 @@ classifier  "wake-word classifier three-stage training on precomputed synthetic 
             186 positive + 186 adversarial + 3724 negative rows (the 50:50:1000 ratio of constants.py:99-103), the reference's
             schedule (trainer.py:918-926: lr x0.5, steps x2, batch x0.5 per stage).  One step = one fused training step
             (forward, high-loss selection, weighted BCE, backward, Adam: WakeWordMLPModel.train_step = hb_mlp_train_step) at the
-            stage-1 batch of 4096.  value = steps/s with the batches resident in HBM; e2e = WakeWordTrainer.train_epoch fed host
+            stage-1 batch of 4096.  value = training rows/s with the batches resident in HBM (N > 1: data-parallel, every rank a
+            4096-row shard of the global batch, gradients all-reduced over NCCL); e2e = WakeWordTrainer.train_epoch fed host
             batches (pinned H2D of x and y and a D2H of the step's loss inside the timed region); the line also carries ms/step at
             the three stage batch sizes and the projected wall time of the full 5000/10000/20000-step schedule.
             cpu_baseline = the reference's own WakeWordMLPModel (baseline/_ref copy) + the trainer's own selection / loss lines +
@@ -156,12 +157,12 @@ def run_classifier(args):
         threads = os.cpu_count() or 1
         v, kind = cpu_classifier_steps_per_s(threads, steps=max(args.steps, 4))
         print(json.dumps({
-            "impl": "reference", "metric": "classifier training steps/sec (batch 4096)", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": "classifier training rows/sec (batch 4096 per GPU)", "value": v * BATCH, "unit": "rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v if v else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "classifier training (BASELINE configs[3])", "batch": BATCH},
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": kind,
+            "cpu_baseline": {"value": v * BATCH, "unit": "rows/s", "cores": threads, "kind": kind,
                              "sample": "reference WakeWordMLPModel + the trainer's selection / weighted-BCE lines + torch.optim.Adam, batch 4096"},
-            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+            "e2e": {"value": v * BATCH, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
 
     world, rank, local_rank, device, barrier, dist = _dist()
@@ -170,17 +171,26 @@ def run_classifier(args):
     model = WakeWordMLPModel(device_id=local_rank, seed=5002)
     steps = max(args.steps, 1)
 
+    from heybuddy_b200.dp import distributed_train_step
+
+    def one_step(x, y):
+        # N > 1: data-parallel training (heybuddy_b200/dp.py) -- every rank a 4096-row shard of the global batch, two NCCL
+        # all-reduces per step (selection count, then the 1 MB of gradients + loss), identical Adam on every replica
+        if world > 1:
+            return distributed_train_step(model, x.reshape(x.shape[0], -1), y, 1e-3, 1.0, 1e-4)
+        return model.train_step(x, y, 1e-3, 1.0, 1e-4)
+
     def timed(scale, k, warm):
         pool = [make_batch(rng, scale) for _ in range(CLS_POOL)]
         dev = [(torch.from_numpy(x).to(device), torch.from_numpy(y).to(device)) for x, y in pool]
         for i in range(warm):
-            model.train_step(*dev[i % CLS_POOL], 1e-3, 1.0, 1e-4)
+            one_step(*dev[i % CLS_POOL])
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.hb_launch_count()
         a.record()
         for i in range(k):
-            model.train_step(*dev[(warm + i) % CLS_POOL], 1e-3, 1.0, 1e-4)
+            one_step(*dev[(warm + i) % CLS_POOL])
         b.record()
         barrier()
         return a.elapsed_time(b) / k, (lib.hb_launch_count() - l0), pool
@@ -196,7 +206,7 @@ def run_classifier(args):
         for i in range(n):
             yield pinned[i % CLS_POOL]
 
-    trainer = WakeWordTrainer(model=model, learning_rate=1e-3, distributed=False)
+    trainer = WakeWordTrainer(model=model, learning_rate=1e-3, distributed=world > 1, dropout=0.0)
     trainer.train_epoch(batches(max(args.warmup, 3)), num_steps=max(args.warmup, 3))
     barrier()
     t0 = time.perf_counter()
@@ -212,13 +222,14 @@ def run_classifier(args):
         alg_bytes = x_bytes + 4 * 256417 * 4          # input + parameters, gradients, two Adam moments
         flops = 3 * 2 * BATCH * (1536 * 128 + 64 * 96 + 2 * (96 * 128 + 64 * 96) + 96 * 128 + 64)   # fwd + 2 x bwd
         line = {
-            "metric": "classifier training steps/sec (batch 4096)", "value": world * 1e3 / ms, "unit": "steps/s", "n_gpus": world, "steps": steps,
+            "metric": "classifier training rows/sec (batch 4096 per GPU)", "value": world * BATCH * 1e3 / ms, "unit": "rows/s", "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "wake-word classifier three-stage training on precomputed synthetic embeddings (BASELINE configs[3])",
                        "batch": BATCH, "composition": [POS, ADV, NEG], "l2_policy": f"{CLS_POOL} distinct batches cycled (> L2)",
-                       "replicas": "independent replicas per GPU (data-parallel training with gradient all-reduce: heybuddy_b200/dp.py)"},
-            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": x_bytes + BATCH * 8, "d2h_bytes_per_step": 16,
+                       "parallelism": "single GPU" if world == 1 else f"data parallel x{world}: global batch {world * BATCH}, all-reduce of the selection count "
+                                      "and of gradients + loss (1 MB) per step over NCCL (heybuddy_b200/dp.py)"},
+            "e2e": {"value": world * BATCH * 1e3 / e2e_ms, "unit": "rows/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": x_bytes + BATCH * 8, "d2h_bytes_per_step": 16,
                     "api": "WakeWordTrainer.train_epoch over host batches (pinned x / y H2D every step, loss / n_selected / stepped read back every step)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"kernel": "hb_mlp_train_step (whole step)", "bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
@@ -233,7 +244,7 @@ def run_classifier(args):
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             v, kind = cpu_classifier_steps_per_s(threads)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": kind,
+            line["cpu_baseline"] = {"value": v * BATCH, "unit": "rows/s", "cores": threads, "kind": kind,
                                     "sample": "12 steps at batch 4096: reference WakeWordMLPModel (baseline/_ref copy) + the trainer's own selection / "
                                               "weighted-BCE lines + torch.optim.Adam on the host cores"}
         print(json.dumps(line), flush=True)

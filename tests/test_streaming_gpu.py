@@ -63,3 +63,33 @@ def test_long_strip_geometry(cuda_device):
         model = SpeechEmbeddingModel(device_id=0, precision=precision, load=True)
         got = model.run_clips_device(torch.from_numpy(m).cuda(), offs).cpu().numpy()
         assert np.abs(got - want).max() / np.abs(want).max() < tol, precision
+
+
+def test_stream_service_matches_offline(cuda_device):
+    """
+    The batched multi-stream service (browser loop semantics, hey-buddy.ts:382-469): three streams pushed in uneven chunks give,
+    step for step, what the offline strip evaluation of each whole stream gives; the first three steps report 0 / not valid
+    while the 16-frame buffer fills.
+    """
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+    from heybuddy_b200.streaming import WakeWordStreamService, num_stream_steps, stream_predict
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    rng = np.random.Generator(np.random.PCG64(77))
+    n = 1920 * 60
+    streams = (0.1 * rng.standard_normal((3, n))).clip(-1, 1).astype(np.float32)
+    speech = SpeechEmbeddings(device_id=0, precision="f16")
+    models = [WakeWordMLPModel(device_id=0, seed=5002 + i) for i in range(4)]
+    want = np.stack([stream_predict(models, s, speech=speech).cpu().numpy() for s in streams], axis=1)     # [M, S, steps - 3]
+    steps = num_stream_steps(n)
+    service = WakeWordStreamService(models, num_streams=3, speech=speech)
+    got, valid, at = [], [], 0
+    for chunk in (1920 * 5, 1920 * 4, 1920, 1920 * 37, 1920 * 2, 1920 * 11):
+        p, v = service.push(streams[:, at:at + chunk])
+        at += chunk
+        got.append(p.cpu().numpy())
+        valid += v
+    got = np.concatenate(got, axis=2)
+    assert at == n and got.shape == (4, 3, steps) and service.steps_emitted == steps
+    assert valid == [False] * 3 + [True] * (steps - 3) and not got[:, :, :3].any()
+    np.testing.assert_allclose(got[:, :, 3:], want, rtol=0, atol=2e-6)
