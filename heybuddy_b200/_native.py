@@ -81,6 +81,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_featurize_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
         "hb_featurize_i16": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),
         "hb_augment_clips_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_augment_mel_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_vp, c_int, c_int, c_vp]),
         "hb_mlp_num_params": (c_i64, []),
         "hb_mlp_create": (c_int, [ctypes.POINTER(c_vp), c_vp, c_i64]),
         "hb_mlp_destroy": (c_int, [c_vp]),

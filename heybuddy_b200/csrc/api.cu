@@ -2,6 +2,7 @@
 #include "hb_common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -22,7 +23,7 @@ extern "C" const char* hb_last_error(void) { return hb::g_error; }
 extern "C" int64_t hb_launch_count(void) { return hb::g_launches.load(); }
 
 // ---- fused featurization: ragged int16 clips -> embeddings, one call -----------------------------------------------
-// a1 + K1-K4 (hb_augment_clips_i16) -> K6 (hb_mel_f32, audio x 32767) -> K7 (hb_embed_clips) through one workspace.
+// a1 + K1-K4 + K6 (hb_augment_mel_i16: one kernel, audio x 32767) -> K7 (hb_embed_clips) through one workspace.
 static int64_t featurize_align(int64_t n) { return (n + 255) & ~255ll; }
 
 extern "C" int64_t hb_featurize_workspace_bytes(int n, int T, int mode) {
@@ -45,10 +46,19 @@ extern "C" int hb_featurize_i16(const hb_embed_model* m, int mode, const int16_t
     float* audio = reinterpret_cast<float*>(base);
     float* mel = reinterpret_cast<float*>(base + featurize_align((int64_t)n * T * 4));
     void* ews = base + featurize_align((int64_t)n * T * 4) + featurize_align((int64_t)n * F * hb::kMels * 4);
-    int rc = hb_augment_clips_i16(samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev, rir_spec_bank_dev,
+    // production mode: augmentation and mel in ONE kernel (the augmented clip stays in shared memory); HB_FEATURIZE_STAGED=1 runs the
+    // bit-identical parity pair hb_augment_clips_i16 -> hb_mel_f32 through the f32 [n][T] intermediate instead
+    static const bool staged = getenv("HB_FEATURIZE_STAGED") != nullptr && atoi(getenv("HB_FEATURIZE_STAGED")) != 0;
+    int rc;
+    if (staged) {
+        rc = hb_augment_clips_i16(samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev, rir_spec_bank_dev,
                                   params_dev, audio, n, T, stream);
-    if (rc) return rc;
-    if ((rc = hb_mel_f32(audio, T, 32767.0f, mel, n, T, stream))) return rc;
+        if (rc) return rc;
+        if ((rc = hb_mel_f32(audio, T, 32767.0f, mel, n, T, stream))) return rc;
+    } else if ((rc = hb_augment_mel_i16(samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev, rir_spec_bank_dev,
+                                        params_dev, 32767.0f, mel, n, T, stream))) {
+        return rc;
+    }
     return hb_embed_clips(m, mode, mel, n, F, slot_offsets_host, n_slots, out_dev, ews,
                           hb_embed_clips_workspace_bytes(n, F, mode), stream);
 }

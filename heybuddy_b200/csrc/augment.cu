@@ -16,7 +16,7 @@
 //
 // HBM traffic per clip: read clip (4T) + read noise row (4T, when drawn) + read coloured base
 // (64 KB, L2-resident per batch) + RIR spectrum (4T+8, L2-resident per batch) + write 4T.
-#include "hb_common.cuh"
+#include "mel_core.cuh"
 
 #include <math.h>
 
@@ -671,15 +671,32 @@ __device__ __forceinline__ void prefetch_range_l2(const void* p, int64_t bytes) 
 
 // kI16: the length fix (a1: /32768, front-truncate or left-pad by pad_before) is fused into the load -- the clip comes
 // straight from the ragged int16 samples and the f32 [n][T] intermediate never exists in HBM.
-template <bool kI16>
+// kMel (production mode): the augmented clip never leaves the SM either -- it is left in shared memory
+// (natural order, in the buffer the FFT no longer needs) and 16 of the CTA's 24 warps turn it into the clip's 141 log-mel frames
+// with the same frame-pair routine as the stand-alone mel kernel (mel_core.cuh: bit-identical frames); `out` receives
+// [n][141][32] mel instead of [n][T] audio.  HBM traffic per clip: source + noise row + 18 KB of mel.
+constexpr int kFusedFrames = 1 + (kFastT - kNFFT) / kHop;   // 141 frames = 71 pairs = 3 rounds of the CTA's 24 warps
+constexpr int kFusedTr = 2 * 16 * kTrStride;          // float2 per warp: two transpose tiles (the power rows alias them)
+constexpr int kFusedWarpsInBuf = (kFastBuf / kFusedTr) < (kFastThreads / 32) ? (kFastBuf / kFusedTr) : (kFastThreads / 32);   // 22 in the freed FFT buffer
+static_assert(2 * kPowerRow * sizeof(float) <= kFusedTr * sizeof(float2), "the power rows alias the transpose tiles");
+
+template <bool kI16, bool kMel>
 __global__ void __launch_bounds__(kFastThreads, 1)
 augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
                     const int32_t* __restrict__ pad_before, const float* __restrict__ noise_bank,
                     const float* __restrict__ colored_bases, const float2* __restrict__ rir_specs,
-                    const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan, int prefetch_ahead) {
+                    const hb_clip_aug* __restrict__ params, float* __restrict__ out, FftPlan plan, int prefetch_ahead,
+                    const MelTables* __restrict__ mel_tables, float mel_scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float scratch[40];
     __shared__ TwTables tw;
+    __shared__ MelShared mel_s;                 // kMel only (4.9 KB)
+    __shared__ float2 mel_w256[kMel ? 256 : 1];  // W256^k: the fused kernel has no registers to spare for a lane's 16 twiddles
+    __shared__ float2 mel_extra[kMel ? (kFastThreads / 32 - kFusedWarpsInBuf) * kFusedTr : 1];   // scratch of the warps that do not fit the FFT buffer
+    if (kMel) {
+        mel_load_shared(mel_s, *mel_tables, threadIdx.x, kFastThreads);
+        for (int i = threadIdx.x; i < 256; i += kFastThreads) mel_w256[i] = mel_tables->w256[i];
+    }
     constexpr int T = kFastT, M = kFastM, NT = kFastThreads, NW = kFastThreads / 32;
     float2* buf0 = reinterpret_cast<float2*>(smem_raw);   // skewed: point n at sk(n)
     float2* buf1 = buf0 + kFastBuf;
@@ -832,11 +849,15 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         have_abs = true;
     }
 
+    float2* fin = buf1;          // kMel: the finished clip, natural order (buf1 is free once the noise row has been mixed in)
     if (!has_rir) {
-        for (int n = tid; n < M; n += NT) dst[n] = buf0[sk(n)];
-        return;
-    }
-
+        if (kMel) {
+            for (int n = tid; n < M; n += NT) fin[n] = buf0[sk(n)];     // a thread re-uses only the points it read the noise from
+        } else {
+            for (int n = tid; n < M; n += NT) dst[n] = buf0[sk(n)];
+            return;
+        }
+    } else {
     // ---- K4 reverb -------------------------------------------------------------------------------------
     if (!have_abs) {
         for (int n = tid; n < M; n += NT) {
@@ -868,7 +889,24 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
     const float amp_y = block_sum_n(ay, scratch, NW) / (float)T;
     const float g = amp_x / (amp_y + 1e-14f);
 #pragma unroll
-    for (int i = 0; i < M / NT; ++i) dst[tid + i * NT] = make_float2(y[i].x * g, y[i].y * g);
+    for (int i = 0; i < M / NT; ++i) (kMel ? fin : dst)[tid + i * NT] = make_float2(y[i].x * g, y[i].y * g);
+    }   // has_rir
+    if (!kMel) return;
+
+    // ---- K6 in place: the clip's 141 log-mel frames from shared memory -------------------------------------------
+    __syncthreads();                                   // fin complete, buf0 free, mel tables loaded
+    const int warp = tid >> 5, lane = tid & 31;
+    float2* tr_pair = warp < kFusedWarpsInBuf ? buf0 + warp * kFusedTr : mel_extra + (warp - kFusedWarpsInBuf) * kFusedTr;
+    const int l = lane & 15;
+    const int my_lo = mel_s.lo[lane], my_rot = mel_s.rot[lane];
+    float* mel_clip = out + (int64_t)blockIdx.x * kFusedFrames * kMels;
+    constexpr int kPairs = (kFusedFrames + 1) / 2;
+    for (int pr = warp; pr < kPairs; pr += NW) {
+        const int f0 = 2 * pr;
+        auto load = [&](int h, int n) { return fin[(kHop / 2) * min(f0 + h, kFusedFrames - 1) + n]; };
+        mel_frame_pair(mel_s, tr_pair, reinterpret_cast<float*>(tr_pair), [&](int k1) { return mel_w256[(l * k1) & 255]; }, my_lo, my_rot, load,
+                       mel_scale, f0, kFusedFrames, mel_clip);
+    }
 }
 
 __global__ void fix_length_kernel(const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
@@ -938,8 +976,9 @@ static int get_plan(int T, FftPlan* out) {
     HB_CUDA_OK(cudaFuncSetAttribute(augment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(colored_bases_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kColoredBase / 2) * (int)sizeof(float2)));
-    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
-    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     g_plans[{dev, T}] = plan;
     *out = plan;
     return HB_OK;
@@ -1005,9 +1044,9 @@ extern "C" int hb_augment_clips_f32(const float* clips_dev, const float* noise_b
     const bool aligned = ((reinterpret_cast<uintptr_t>(clips_dev) | reinterpret_cast<uintptr_t>(out_dev) |
                            reinterpret_cast<uintptr_t>(colored_bases_dev)) & 7) == 0;
     if (T == kFastT && aligned) {
-        augment_fast_kernel<false><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+        augment_fast_kernel<false, false><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
             clips_dev, nullptr, nullptr, nullptr, noise_bank_dev, colored_bases_dev, reinterpret_cast<const float2*>(rir_spec_bank_dev),
-            params_dev, out_dev, plan, prefetch_distance());
+            params_dev, out_dev, plan, prefetch_distance(), nullptr, 1.0f);
     } else {
         const size_t smem = 2 * (size_t)plan.M * sizeof(float2);
         augment_kernel<<<n, kAugThreads, smem, (cudaStream_t)stream>>>(clips_dev, noise_bank_dev, colored_bases_dev,
@@ -1030,9 +1069,33 @@ extern "C" int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* o
     FftPlan plan;
     int rc = get_plan(T, &plan);
     if (rc) return rc;
-    augment_fast_kernel<true><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+    augment_fast_kernel<true, false><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
         nullptr, samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev,
-        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, out_dev, plan, prefetch_distance());
+        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, out_dev, plan, prefetch_distance(), nullptr, 1.0f);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+// Production mode: a1 + K1-K4 + K6 in ONE kernel -- ragged int16 clips -> augmented clip (shared memory only) -> log-mel
+// mel_dev f32 [n][141][32] (T = 23040).  Bit-identical to hb_augment_clips_i16 followed by hb_mel_f32(scale).
+extern "C" int hb_augment_mel_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                                  const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
+                                  const hb_clip_aug* params_dev, float scale, float* mel_dev, int n, int T, void* stream) {
+    HB_REQUIRE(samples_dev && offsets_dev && pad_before_dev && params_dev && mel_dev && n >= 0, "hb_augment_mel_i16: bad argument");
+    if (T != kFastT || (reinterpret_cast<uintptr_t>(colored_bases_dev) & 7) != 0) {
+        set_error("hb_augment_mel_i16: only T = 23040 with 8-byte aligned buffers is fused; use hb_augment_clips_* + hb_mel_f32");
+        return HB_ERR_UNSUPPORTED;
+    }
+    HB_REQUIRE(mel_tables_ready(), "hb_augment_mel_i16: hb_init_tables has not been called on this device");
+    if (n == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(T, &plan);
+    if (rc) return rc;
+    const MelTables* tables = mel_tables_device();
+    HB_REQUIRE(tables != nullptr, "hb_augment_mel_i16: mel tables unavailable");
+    augment_fast_kernel<true, true><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+        nullptr, samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev,
+        reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, mel_dev, plan, prefetch_distance(), tables, scale);
     HB_LAUNCHED();
     return HB_OK;
 }

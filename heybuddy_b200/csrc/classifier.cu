@@ -266,17 +266,6 @@ __global__ void gate_fwd_kernel(const float* __restrict__ h, const float* __rest
     }
 }
 
-__global__ void gate_bwd_kernel(const float* __restrict__ h, const float* __restrict__ g, const float* __restrict__ da,
-                                float* __restrict__ dh, float* __restrict__ dg, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float hv = h[i], sg = 1.f / (1.f + expf(-hv));
-        const float silu = hv * sg;
-        const float d = da[i];
-        dg[i] = d * silu;
-        dh[i] = d * g[i] * (sg * (1.f + hv * (1.f - sg)));
-    }
-}
-
 // stacked layout: hg [B][128] = [hidden | gate] pre-activations of a gated MLP; a [B][64] = silu(h) * g
 __global__ void gate_hg_fwd_kernel(const float* __restrict__ hg, float* __restrict__ a, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -383,49 +372,6 @@ __global__ void colred_finish_kernel(const float* __restrict__ scratch, float* _
     for (int s = 0; s < slices; ++s) { ta += scratch[((int64_t)s * 2 + 0) * N + n]; tb += scratch[((int64_t)s * 2 + 1) * N + n]; }
     if (n < split) out0[n] = ta; else out1[n - split] = ta;
     if (out_b != nullptr) out_b[n] = tb;
-}
-
-// column sums: out[n] (+)= sum_m X[m, n]
-__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int accumulate) {
-    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int part = threadIdx.x >> 5;  // 8 row partitions
-    __shared__ float red[8][33];
-    float s = 0.f;
-    if (n < N)
-        for (int m = part; m < M; m += 8) s += X[(int64_t)m * N + n];
-    red[part][threadIdx.x & 31] = s;
-    __syncthreads();
-    if (part == 0 && n < N) {
-        float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        out[n] = accumulate ? out[n] + t : t;
-    }
-}
-
-// LayerNorm backward: dgamma[n] = sum_m dy*xhat, dbeta[n] = sum_m dy; optionally dx.
-// xhat is recomputed from the LN output: xhat = (y - beta) / gamma is unsafe for gamma = 0, so the caller passes x, mean, rstd.
-__global__ void ln_bwd_params_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     int M, int N) {
-    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int part = threadIdx.x >> 5;
-    __shared__ float r1[8][33], r2[8][33];
-    float a = 0.f, b = 0.f;
-    if (n < N)
-        for (int m = part; m < M; m += 8) {
-            const float d = dy[(int64_t)m * N + n];
-            a += d * (x[(int64_t)m * N + n] - mean[m]) * rstd[m];
-            b += d;
-        }
-    r1[part][threadIdx.x & 31] = a;
-    r2[part][threadIdx.x & 31] = b;
-    __syncthreads();
-    if (part == 0 && n < N) {
-        float ta = 0.f, tb = 0.f;
-        for (int i = 0; i < 8; ++i) { ta += r1[i][threadIdx.x & 31]; tb += r2[i][threadIdx.x & 31]; }
-        dgamma[n] = ta;
-        dbeta[n] = tb;
-    }
 }
 
 // dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat)), dyg = dy * gamma; one warp per row

@@ -282,6 +282,33 @@ class FeaturizePipeline:
             self._mark("embed")
         return (out, audio) if keep_audio else out
 
+    def run_fused_front(self, chunk: DeviceChunk, mel_out=None):
+        """Only the production-mode front end: ``hb_colored_bases`` + ``hb_augment_mel_i16`` (length fix + augmentation + mel in ONE
+        kernel) -> cuda f32 ``[n, 141, 32]``.  Used by the parity test against the staged pair and by bench.py's stage timing."""
+        import torch
+
+        lib = _native.load()
+        n, t, dev = chunk.n, self.t, self.device
+        aug = self.augment
+        _native.ensure_tables(dev)
+        with torch.cuda.device(dev):
+            st = _native.stream_ptr(dev)
+            nb, rb = aug.noise_bank, aug.rir_bank
+            bases_ptr = None
+            if chunk.colored_ids is not None:
+                k = int(chunk.colored_ids.numel())
+                bases = self._grow("bases", k * spec.COLORED_BASE_SAMPLES, torch.float32)
+                _native.check(lib.hb_colored_bases(chunk.seed & (2 ** 64 - 1), chunk.colored_ids.data_ptr(), chunk.colored_f_decay.data_ptr(),
+                                                   k, bases.data_ptr(), st), "hb_colored_bases")
+                bases_ptr = bases.data_ptr()
+            if mel_out is None:
+                mel_out = torch.empty((n, spec.mel_frames(t), spec.N_MELS), dtype=torch.float32, device=dev)
+            _native.check(lib.hb_augment_mel_i16(
+                chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(), nb.stream.data_ptr() if nb is not None else None,
+                bases_ptr, rb.spec.data_ptr() if rb is not None else None, chunk.params.data_ptr(), float(spec.AUDIO_SCALE), mel_out.data_ptr(),
+                n, t, st), "hb_augment_mel_i16")
+        return mel_out
+
     # -- host path (the call a user makes) -----------------------------------------------------------------
     def featurize_host(self, clips: RaggedClips, tables: Union[DrawTable, Sequence[DrawTable]], chunk_clips: int,
                        out: Optional[np.ndarray] = None):

@@ -153,8 +153,17 @@ int hb_augment_clips_i16(const int16_t* samples_dev, const int64_t* offsets_dev,
                          const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
                          const hb_clip_aug* params_dev, float* out_dev, int n, int T, void* stream);
 
+/* Production mode of the front end: a1 + K1-K4 + K6 in ONE kernel (T = 23040 only).  The augmented clip
+ * never reaches HBM -- it goes from the augmentation's shared memory straight into the 141 log-mel frames (audio x scale,
+ * MelSpectrogramModel's x/10 + 2 folded in) -> mel_dev f32 [n][141][32].  Bit-identical to hb_augment_clips_i16 followed by
+ * hb_mel_f32(scale) (the parity-mode pair, which crosses the f32 [n][T] intermediate the reference crosses through the host:
+ * augmented.py:416-421 -> embeddings.py:178-190).  Needs hb_init_tables.  Other T: HB_ERR_UNSUPPORTED. */
+int hb_augment_mel_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
+                       const float* noise_bank_dev, const float* colored_bases_dev, const float* rir_spec_bank_dev,
+                       const hb_clip_aug* params_dev, float scale, float* mel_dev, int n, int T, void* stream);
+
 /* The whole featurization path of one chunk in one call (the fused entry SURVEY.md 8b ring 3 proposes): ragged int16 clips
- * -> length fix + augmentation -> log-mel (audio x 32767) -> embeddings f32 [n][n_slots][96].  Equivalent to
+ * -> length fix + augmentation + log-mel (hb_augment_mel_i16, audio x 32767) -> embeddings f32 [n][n_slots][96].  Equivalent to
  * hb_augment_clips_i16, hb_mel_f32(scale = 32767) and hb_embed_clips run back to back on `stream` (bit-identical); T = 23040. */
 int64_t hb_featurize_workspace_bytes(int n, int T, int mode);
 int hb_featurize_i16(const hb_embed_model* m, int mode, const int16_t* samples_dev, const int64_t* offsets_dev,

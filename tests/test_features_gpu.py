@@ -242,3 +242,33 @@ def test_fused_entry_point_equals_staged_calls(cuda_device):
     staged = pipe.run_device(chunk).clone()
     pipe.profile = False
     assert torch.equal(fused, staged) and torch.isfinite(fused).all()
+
+
+def test_fused_augment_mel_equals_staged_pair(cuda_device):
+    """
+    Production mode (hb_augment_mel_i16: length fix + augmentation + mel in ONE kernel, the augmented clip never leaves shared
+    memory) == the parity pair hb_augment_clips_i16 -> hb_mel_f32 through the f32 [n][T] intermediate, bit for bit -- clips with and
+    without reverb / noise / coloured noise, empty, short, exact-length and over-long clips, non-finite results included.
+    """
+    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
+    from heybuddy_b200.embeddings import SpeechEmbeddings
+    from heybuddy_b200.pipeline import FeaturizePipeline, RaggedClips
+
+    rng = np.random.default_rng(31)
+    noise, rirs = _banks(rng)
+    aug = AugmentedAudioGenerator([], device_id=0, augmentation_dataset=noise, impulse_response_dataset=rirs, batch_size=8, seed=5)
+    pipe = FeaturizePipeline(aug, SpeechEmbeddings(device_id=0, precision="f16"), device_id=0)
+    clips = [(rng.standard_normal(int(rng.integers(6400, 22400))) * 4000).astype(np.int16) for _ in range(156)]
+    clips += [np.zeros(0, np.int16), np.zeros(9000, np.int16), (rng.standard_normal(30000) * 3000).astype(np.int16),
+              (rng.standard_normal(23040) * 3000).astype(np.int16)]
+    ragged = RaggedClips.from_list(clips)
+    table = aug.next_table(ragged.lengths)
+    kinds = {(bool(c), bool(b), bool(r)) for c, b, r in zip(table.colored_apply, table.background_apply, table.reverb_apply)}
+    assert len(kinds) >= 4
+    chunk = pipe.upload(ragged, table)
+    fused = pipe.run_fused_front(chunk).clone()
+    _, audio = pipe.run_device(chunk, keep_audio=True)                     # staged: hb_augment_clips_i16 (+ hb_mel_f32 + embed)
+    staged = pipe.speech.spectrogram.run_device(audio, scale=spec.AUDIO_SCALE)
+    a, b = fused.cpu().numpy(), staged.cpu().numpy()
+    assert a.shape == b.shape == (len(clips), 141, 32)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a, posinf=1e30, neginf=-1e30), np.nan_to_num(b, posinf=1e30, neginf=-1e30))
