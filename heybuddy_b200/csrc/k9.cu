@@ -14,40 +14,61 @@ namespace hb {
 constexpr int kEqBands = 7;
 
 // ---- SevenBandParametricEQ: seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt) ----------------------------
-// An IIR cascade is a serial recurrence in time; the parallelism is ACROSS clips: one thread per equalised clip runs the whole
-// cascade in float64 (what sosfilt computes in; direct form II transposed).  Within a thread the seven sections of one sample and
-// the state updates of the previous one overlap in the FP64 pipe, so the latency-bound chain is ~2 dependent FMAs per sample.
+// An IIR cascade is a serial recurrence in time, computed in float64 (what sosfilt computes in; a float32 direct form loses up to
+// 1e-2 on the low-Q shelves).  An FP64 FMA has ~50 cycles of latency here, so the cost of a clip is (dependent FMAs per sample)
+// x 50 cycles x 23040 samples, whatever else the GPU could be doing -- 2.6 ms when one thread runs the seven sections one after
+// the other.  Two things shorten the chain to ONE FMA per sample:
+//   * a SYSTOLIC ARRAY across lanes -- eight lanes per clip (four clips per warp), lane s owns section s (lane 7 is a pure delay);
+//     at tick tau lane s works on sample tau - 3 s, its input arriving by shuffle from lane s - 1's output of three ticks ago, so
+//     the shuffle and the feed-forward part are off the critical path;
+//   * direct form I inside a lane: y[n] = f[n] - a1 y[n-1] - a2 y[n-2] with f = b0 v[n] + b1 v[n-1] + b2 v[n-2]; only
+//     fma(-a1, y[n-1], .) waits for the previous tick.
+// Lane 7's output lags the input by 24 samples, so loads and stores are whole, aligned float4s (in place: the store trails the
+// load by six groups).
+constexpr int kEqLanes = 8, kEqDelay = 3, kEqLagGroups = kEqLanes * kEqDelay / 4;      // 24 samples = 6 float4 groups
+
 __global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, const int32_t* __restrict__ clip_index,
                                                    const double* __restrict__ sos, int k, int T) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k) return;
-    double b0[kEqBands], b1[kEqBands], b2[kEqBands], a1[kEqBands], a2[kEqBands], z1[kEqBands], z2[kEqBands];
-#pragma unroll
-    for (int s = 0; s < kEqBands; ++s) {
-        const double* c = sos + ((int64_t)i * kEqBands + s) * 5;
-        b0[s] = c[0]; b1[s] = c[1]; b2[s] = c[2]; a1[s] = c[3]; a2[s] = c[4];
-        z1[s] = 0.0; z2[s] = 0.0;
+    static_assert(kEqDelay == 3 && (kEqLanes * kEqDelay) % 4 == 0, "the delay registers below are written out for a delay of 3");
+    const int lane = threadIdx.x & 31, sec = lane & (kEqLanes - 1);
+    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / kEqLanes) + lane / kEqLanes;   // clip of this 8-lane group
+    const bool live = i < k;
+    double b0 = 1.0, b1 = 0.0, b2 = 0.0, a1 = 0.0, a2 = 0.0;        // lane 7 (and idle groups): identity
+    if (live && sec < kEqBands) {
+        const double* c = sos + ((int64_t)i * kEqBands + sec) * 5;
+        b0 = c[0]; b1 = c[1]; b2 = c[2]; a1 = c[3]; a2 = c[4];
     }
-    float* x = clips + (int64_t)clip_index[i] * T;
-    auto step = [&](float v) {
-        double y = (double)v;
+    float* x = clips + (int64_t)(live ? clip_index[i] : 0) * T;
+    const bool vec = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    double d1 = 0.0, d2 = 0.0, d3 = 0.0, v1 = 0.0, v2 = 0.0;      // this lane's last three outputs and last two inputs
+    const int groups = (T + 3) / 4;
+    for (int g = 0; g < groups + kEqLagGroups; ++g) {
+        float xin[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live && sec == 0 && g < groups) {
+            if (vec) *reinterpret_cast<float4*>(xin) = *reinterpret_cast<const float4*>(x + 4 * g);
+            else
 #pragma unroll
-        for (int s = 0; s < kEqBands; ++s) {
-            const double in = y;
-            y = fma(b0[s], in, z1[s]);
-            z1[s] = fma(b1[s], in, fma(-a1[s], y, z2[s]));
-            z2[s] = fma(b2[s], in, -a2[s] * y);
+                for (int j = 0; j < 4; ++j) if (4 * g + j < T) xin[j] = x[4 * g + j];
         }
-        return (float)y;
-    };
-    int t = 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
-        for (; t + 3 < T; t += 4) {
-            float4 v = *reinterpret_cast<const float4*>(x + t);
-            v.x = step(v.x); v.y = step(v.y); v.z = step(v.z); v.w = step(v.w);
-            *reinterpret_cast<float4*>(x + t) = v;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double up = __shfl_up_sync(0xffffffffu, d3, 1, kEqLanes);
+            const double v = sec == 0 ? (double)xin[j] : up;
+            o[j] = (float)d3;                         // lane 7: sample tau - 24 = 4 (g - 6) + j
+            const double f = fma(b0, v, fma(b1, v1, b2 * v2));
+            const double y = fma(-a1, d1, fma(-a2, d2, f));
+            d3 = d2; d2 = d1; d1 = y;
+            v2 = v1; v1 = v;
         }
-    for (; t < T; ++t) x[t] = step(x[t]);
+        if (live && sec == kEqLanes - 1 && g >= kEqLagGroups) {
+            float* dst = x + 4 * (g - kEqLagGroups);
+            if (vec) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            else
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (4 * (g - kEqLagGroups) + j < T) dst[j] = o[j];
+        }
+    }
 }
 
 // ---- TanhDistortion ------------------------------------------------------------------------------------------------------------------
@@ -145,8 +166,8 @@ using namespace hb;
 extern "C" int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream) {
     HB_REQUIRE(k >= 0 && T > 0 && (k == 0 || (clips_dev && clip_index_dev && sos_dev)), "hb_k9_eq_f32: bad argument");
     if (k == 0) return HB_OK;
-    // 16 threads per block: the kernel is latency bound per clip, so spread the clips over as many SMs as possible
-    k9_eq_kernel<<<ceil_div(k, 16), 16, 0, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, sos_dev, k, T);
+    // one warp (four clips) per block: the kernel is FP64-issue bound per warp, so spread the warps over every SM sub-partition
+    k9_eq_kernel<<<ceil_div(k, 32 / kEqLanes), 32, 0, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, sos_dev, k, T);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -87,6 +87,23 @@ def _align(n: int, a: int = 256) -> int:
     return (n + a - 1) // a * a
 
 
+class _nvtx:
+    """NVTX range around a pipeline stage (tracing) -- shows up in nsys / `ncu --nvtx`; a no-op without a profiler."""
+
+    def __init__(self, name: str) -> None:
+        self.name = name
+
+    def __enter__(self):
+        import torch
+
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        import torch
+
+        torch.cuda.nvtx.range_pop()
+
+
 class FeaturizePipeline:
     def __init__(self, augment: AugmentedAudioGenerator, speech: SpeechEmbeddings, device_id: Optional[int] = None):
         if augment is None:
@@ -230,8 +247,9 @@ class FeaturizePipeline:
             if chunk.colored_ids is not None:
                 k = int(chunk.colored_ids.numel())
                 bases = self._grow("bases", k * spec.COLORED_BASE_SAMPLES, torch.float32)
-                _native.check(lib.hb_colored_bases(chunk.seed & (2 ** 64 - 1), chunk.colored_ids.data_ptr(), chunk.colored_f_decay.data_ptr(),
-                                                   k, bases.data_ptr(), st), "hb_colored_bases")
+                with _nvtx("hb/colored_bases"):
+                    _native.check(lib.hb_colored_bases(chunk.seed & (2 ** 64 - 1), chunk.colored_ids.data_ptr(), chunk.colored_f_decay.data_ptr(),
+                                                       k, bases.data_ptr(), st), "hb_colored_bases")
                 bases_ptr = bases.data_ptr()
             self._mark("colored")
             banks = (nb.stream.data_ptr() if nb is not None else None, bases_ptr, rb.spec.data_ptr() if rb is not None else None)
@@ -247,10 +265,11 @@ class FeaturizePipeline:
                 nbytes = lib.hb_featurize_workspace_bytes(n, t, emb_model.mode)
                 _native.check(nbytes, "hb_featurize_workspace_bytes")
                 ws = self._grow("featurize_ws", int(nbytes), torch.uint8)
-                _native.check(lib.hb_featurize_i16(
-                    emb_model._handle, emb_model.mode, chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
-                    *banks, chunk.params.data_ptr(), offs.ctypes.data, offs.size,
-                    out.data_ptr(), n, t, ws.data_ptr(), int(ws.numel()), st), "hb_featurize_i16")
+                with _nvtx(f"hb/featurize_i16[{n}]"):
+                    _native.check(lib.hb_featurize_i16(
+                        emb_model._handle, emb_model.mode, chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
+                        *banks, chunk.params.data_ptr(), offs.ctypes.data, offs.size,
+                        out.data_ptr(), n, t, ws.data_ptr(), int(ws.numel()), st), "hb_featurize_i16")
                 return out
             audio = self._buf("audio", (n, t), torch.float32) if not keep_audio else torch.empty((n, t), dtype=torch.float32, device=dev)
             if t == spec.CLIP_SAMPLES and chunk.k9 is None:
@@ -274,11 +293,13 @@ class FeaturizePipeline:
                               "hb_augment_clips_f32")
             self._mark("augment")
             mel = self._buf("mel", (n, spec.mel_frames(t), spec.N_MELS), torch.float32)
-            self.speech.spectrogram.run_device(audio, scale=spec.AUDIO_SCALE, out=mel)
+            with _nvtx("hb/mel"):
+                self.speech.spectrogram.run_device(audio, scale=spec.AUDIO_SCALE, out=mel)
             self._mark("mel")
             if out is None:
                 out = torch.empty((n, self.slot_offsets.size, spec.EMB_DIM), dtype=torch.float32, device=dev)
-            self.speech.embeddings.run_clips_device(mel, self.slot_offsets, out=out)
+            with _nvtx("hb/embed"):
+                self.speech.embeddings.run_clips_device(mel, self.slot_offsets, out=out)
             self._mark("embed")
         return (out, audio) if keep_audio else out
 
@@ -412,6 +433,7 @@ class FeaturizePipeline:
             blocked(stage_events[slot])          # the H2D that last read this slot's pinned staging buffers must have finished
             while len(done_events) > 0 and k - done_events[0][0] >= MAX_INFLIGHT:
                 blocked(done_events.popleft()[1])
+            torch.cuda.nvtx.range_push(f"hb/stage_chunk[{n}]")
             _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_counts(table))
             meta_pin = pinned("meta", slot, total, torch.uint8)
             lay, total, kc = self._fill_meta(meta_pin.numpy(), part, table)
@@ -429,6 +451,7 @@ class FeaturizePipeline:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             stage_events[slot] = ev
+            torch.cuda.nvtx.range_pop()
             return self._chunk_from_meta(samples_dev, meta_dev, lay, n, kc, table.seed), meta_dev, ev, sink, lo, hi
 
         def deliver(sink, lo, hi, pin, done_ev):
