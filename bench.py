@@ -602,7 +602,7 @@ def main():
         stage_bytes = {"augment": 28800 + 0.75 * 92160 + 92160, "mel": 110208, "augment_mel_fused": 28800 + 0.75 * 92160 + 18048}
         stage_notes = {
             "mel": "fp32 register FFT + BANDED fp32 projection (each mel bin sums its <= 16 FFT bins; the dense 257x32 GEMM the north star "
-                   "names is 88 % zeros and TF32 operands would break the 1e-4 budget) -- a deliberate deviation, DESIGN.md 4.3",
+                   "names is 88 % zeros and TF32 operands would break the 1e-4 budget) -- a deliberate deviation, DESIGN.md 5.2",
             "colored": "hb_colored_bases: the chunk's coloured-noise patterns regenerated on the device from the draw table's Philox counters",
             "k9": "hb_k9_eq_f32 + hb_k9_tanh_f32 on the clips whose coins came up (HB_BENCH_K9; 0 in BASELINE configs[1])",
             "augment": "parity-mode kernel hb_augment_clips_i16 (writes the f32 [n][T] clip), timed in a separate staged pass",
