@@ -77,6 +77,11 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_augment_clips_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_k9_eq_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_k9_tanh_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_k9_bandstop_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_pitch_plan_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+        "hb_pitch_plan_destroy": (c_int, [c_vp]),
+        "hb_k9_pitch_workspace_bytes": (c_i64, [c_vp, c_int]),
+        "hb_k9_pitch_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
         "hb_fix_length_i16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_featurize_workspace_bytes": (c_i64, [c_int, c_int, c_int]),
         "hb_featurize_i16": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_i64, c_vp]),

@@ -18,6 +18,8 @@
 // (64 KB, L2-resident per batch) + RIR spectrum (4T+8, L2-resident per batch) + write 4T.
 #include "mel_core.cuh"
 
+#include "cplx.cuh"
+
 #include <math.h>
 
 #include <map>
@@ -40,60 +42,6 @@ struct FftPlan {
     int tw_lo;             // two-level twiddle split: exp(-2 pi i m / M) = hi[m / tw_lo] * lo[m % tw_lo]
     int tw_hi;             // number of hi entries (tw_hi * tw_lo >= M)
 };
-
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
-__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // -i a
-__device__ __forceinline__ float2 mul_pos_i(float2 a) { return make_float2(-a.y, a.x); }  // +i a
-
-template <int R>
-__device__ __forceinline__ void dft(float2* v);
-
-template <>
-__device__ __forceinline__ void dft<2>(float2* v) {
-    const float2 a = v[0], b = v[1];
-    v[0] = cadd(a, b);
-    v[1] = csub(a, b);
-}
-template <>
-__device__ __forceinline__ void dft<3>(float2* v) {
-    const float2 t1 = cadd(v[1], v[2]);
-    const float2 m1 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
-    const float2 t2 = cscale(csub(v[1], v[2]), 0.86602540378443864676f);
-    v[0] = cadd(v[0], t1);
-    v[1] = cadd(m1, mul_neg_i(t2));
-    v[2] = cadd(m1, mul_pos_i(t2));
-}
-template <>
-__device__ __forceinline__ void dft<4>(float2* v) {
-    const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
-    const float2 a2 = cadd(v[1], v[3]), a3 = csub(v[1], v[3]);
-    v[0] = cadd(a0, a2);
-    v[2] = csub(a0, a2);
-    v[1] = cadd(a1, mul_neg_i(a3));
-    v[3] = cadd(a1, mul_pos_i(a3));
-}
-template <>
-__device__ __forceinline__ void dft<5>(float2* v) {
-    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    const float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
-    const float2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
-    const float2 p1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
-    const float2 p2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
-    const float2 q1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-    const float2 q2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-    v[0] = cadd(v[0], cadd(a1, a2));
-    v[1] = cadd(p1, mul_neg_i(q1));
-    v[4] = cadd(p1, mul_pos_i(q1));
-    v[2] = cadd(p2, mul_neg_i(q2));
-    v[3] = cadd(p2, mul_pos_i(q2));
-}
 
 constexpr int kTwMax = 128;   // entries per twiddle level kept in shared memory
 
@@ -909,6 +857,95 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
     }
 }
 
+// ---- K9: BandStopFilter ---------------------------------------------------------------------------------------------------------
+// torch_audiomentations.BandStopFilter (reference augmented.py:102-106; restated, parity unpinned: heybuddy_b200/dataset/k9.py):
+// x - (lowpass_high(x) - lowpass_low(x)) with julius' Hann-windowed-sinc low-pass pair, both 2 h + 1 taps, on the clip replicate-padded
+// by h.  With d = f_high - f_low (one FIR per augmentation batch): y[n] = x[n] - sum_k d[k] xp[n + 2 h - k], xp[i] = x[clamp(i - h)].
+// Uniformly partitioned overlap-save on the clip's own exact-length FFT: blocks of T samples, partitions of B = T / 2 taps.  Block
+// (c, p) is u[i] = xp[(c - p - 1) B + 2 h + i], i < T; its circular convolution with partition p (spectrum from hb_rir_spectrum of
+// the zero-padded taps) is exact for i in [B, 2 B) = partition p's share of the outputs [c B, (c + 1) B).  h <= B / 2 (a low cut-off
+// above 11 Hz at 16 kHz, ~98 % of the draws) is one partition: two blocks = two FFT pairs per clip.
+template <bool kFast>
+__global__ void __launch_bounds__(kFast ? kFastThreads : kAugThreads, 1)
+bandstop_kernel(float* __restrict__ clips, const int32_t* __restrict__ clip_index, const int32_t* __restrict__ meta,
+                const float2* __restrict__ specs, const float* __restrict__ scratch, int T, FftPlan plan) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TwTables tw;
+    constexpr int NT = kFast ? kFastThreads : kAugThreads;
+    const int M = plan.M, B = M, tid = threadIdx.x;
+    float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+    float2* buf1 = buf0 + (kFast ? kFastBuf : M);
+    auto at = [](int n) { return kFast ? sk(n) : n; };
+    for (int i = tid; i < plan.tw_hi; i += NT) tw.hi[i] = __ldg(plan.tw_m + i * plan.tw_lo);
+    for (int i = tid; i < plan.tw_lo; i += NT) tw.lo[i] = __ldg(plan.tw_m + i);
+    const float* x = scratch + (int64_t)blockIdx.x * T;                 // the untouched copy of the clip
+    float* dst = clips + (int64_t)clip_index[blockIdx.x] * T;
+    const int row0 = meta[3 * blockIdx.x], n_part = meta[3 * blockIdx.x + 1], h = meta[3 * blockIdx.x + 2];
+    const float inv_m = 1.0f / (float)M;
+    for (int c = 0; c < 2; ++c)
+        for (int p = 0; p < n_part; ++p) {
+            const int a = (c - p - 1) * B + h;                          // u[i] = x[clamp(a + i, 0, T - 1)]
+            for (int n = tid; n < M; n += NT) {
+                const int i0 = min(max(a + 2 * n, 0), T - 1), i1 = min(max(a + 2 * n + 1, 0), T - 1);
+                buf0[at(n)] = make_float2(__ldg(x + i0), __ldg(x + i1));
+            }
+            __syncthreads();
+            const float2* H = specs + (int64_t)(row0 + p) * (M + 1);
+            const float2* res;
+            if constexpr (kFast) {
+                const int lo_n = plan.tw_lo;
+                fast_pass_fwd<16, 1>(buf0, buf1, tw, lo_n);
+                fast_pass_fwd<16, 16>(buf1, buf0, tw, lo_n);
+                fast_pass_fwd<9, 256>(buf0, buf1, tw, lo_n);
+                fast_middle(buf1, H, plan.tw_t, tw, lo_n);
+                fast_pass_bwd<9, 256>(buf1, buf0, tw, lo_n);
+                fast_pass_bwd<16, 16>(buf0, buf1, tw, lo_n);
+                fast_pass_bwd<16, 1>(buf1, buf0, tw, lo_n);             // buf0 = conj(M * (y_even + i y_odd)), natural order
+                res = buf0;
+            } else {
+                float2* Z = fft_forward(buf0, buf1, plan, tw);
+                float2* other = (Z == buf0) ? buf1 : buf0;
+                for (int k = tid; k <= M / 2; k += NT) {
+                    if (k == 0) {
+                        const float x0 = Z[0].x + Z[0].y, xm = Z[0].x - Z[0].y;
+                        const float y0 = x0 * __ldg(&H[0]).x, ym = xm * __ldg(&H[M]).x;
+                        Z[0] = make_float2(0.5f * (y0 + ym), -0.5f * (y0 - ym));
+                    } else {
+                        const float2 w = __ldg(plan.tw_t + k);
+                        float2 Xk, Xmk;
+                        untangle(Z[k], Z[M - k], w, &Xk, &Xmk);
+                        const float2 Yk = cmulf(Xk, __ldg(&H[k]));
+                        const float2 Ymk = cmulf(Xmk, __ldg(&H[M - k]));
+                        const float2 Ye = cscale(cadd(Yk, cconj(Ymk)), 0.5f);
+                        const float2 Yo = cmulf(cscale(csub(Yk, cconj(Ymk)), 0.5f), cconj(w));
+                        const float2 zk = cadd(Ye, mul_pos_i(Yo));
+                        const float2 zmk = cadd(cconj(Ye), mul_pos_i(cconj(Yo)));
+                        Z[k] = cconj(zk);
+                        if (k != M - k) Z[M - k] = cconj(zmk);
+                    }
+                }
+                __syncthreads();
+                res = fft_forward(Z, other, plan, tw);
+            }
+            // v[i], i in [B, 2 B): pair mm = i / 2 in [M / 2, M) -> outputs n = c B + 2 mm - B, n + 1 (the same thread every time)
+            for (int mm = M / 2 + tid; mm < M; mm += NT) {
+                const float2 v = res[at(mm)];
+                const int n = c * B + 2 * mm - B;
+                float2 o = p == 0 ? make_float2(__ldg(x + n), __ldg(x + n + 1)) : *reinterpret_cast<const float2*>(dst + n);
+                o.x -= v.x * inv_m;
+                o.y += v.y * inv_m;
+                *reinterpret_cast<float2*>(dst + n) = o;
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ clips, const int32_t* __restrict__ clip_index, float* __restrict__ out, int T) {
+    const float* src = clips + (int64_t)clip_index[blockIdx.x] * T;
+    float* dst = out + (int64_t)blockIdx.x * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) dst[i] = src[i];
+}
+
 __global__ void fix_length_kernel(const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets,
                                   const int32_t* __restrict__ pad_before, float* __restrict__ out, int T) {
     const int b = blockIdx.x;
@@ -979,6 +1016,8 @@ static int get_plan(int T, FftPlan* out) {
     HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
     HB_CUDA_OK(cudaFuncSetAttribute(augment_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(bandstop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFastBuf * (int)sizeof(float2)));
+    HB_CUDA_OK(cudaFuncSetAttribute(bandstop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (kMaxT / 2) * (int)sizeof(float2)));
     g_plans[{dev, T}] = plan;
     *out = plan;
     return HB_OK;
@@ -1096,6 +1135,29 @@ extern "C" int hb_augment_mel_i16(const int16_t* samples_dev, const int64_t* off
     augment_fast_kernel<true, true><<<n, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
         nullptr, samples_dev, offsets_dev, pad_before_dev, noise_bank_dev, colored_bases_dev,
         reinterpret_cast<const float2*>(rir_spec_bank_dev), params_dev, mel_dev, plan, prefetch_distance(), tables, scale);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+// K9 BandStopFilter, in place on the k clips listed in clip_index (rows of clips_dev f32 [n][T]): meta i32 [k][3] = (first
+// spectrum row, partitions, half size h) per clip, spec_dev = hb_rir_spectrum of the partition rows, scratch_dev f32 [k][T].
+extern "C" int hb_k9_bandstop_f32(float* clips_dev, const int32_t* clip_index_dev, const int32_t* meta_dev, const float* spec_dev,
+                                  float* scratch_dev, int k, int T, void* stream) {
+    HB_REQUIRE(k >= 0 && T > 0 && T % 4 == 0 && (k == 0 || (clips_dev && clip_index_dev && meta_dev && spec_dev && scratch_dev)),
+               "hb_k9_bandstop_f32: bad argument (T must be a multiple of 4)");
+    HB_REQUIRE(((reinterpret_cast<uintptr_t>(clips_dev) | reinterpret_cast<uintptr_t>(spec_dev)) & 7) == 0, "hb_k9_bandstop_f32: buffers must be 8-byte aligned");
+    if (k == 0) return HB_OK;
+    FftPlan plan;
+    int rc = get_plan(T, &plan);
+    if (rc) return rc;
+    gather_rows_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, scratch_dev, T);
+    HB_LAUNCHED();
+    if (T == kFastT)
+        bandstop_kernel<true><<<k, kFastThreads, 2 * kFastBuf * sizeof(float2), (cudaStream_t)stream>>>(
+            clips_dev, clip_index_dev, meta_dev, reinterpret_cast<const float2*>(spec_dev), scratch_dev, T, plan);
+    else
+        bandstop_kernel<false><<<k, kAugThreads, 2 * (size_t)plan.M * sizeof(float2), (cudaStream_t)stream>>>(
+            clips_dev, clip_index_dev, meta_dev, reinterpret_cast<const float2*>(spec_dev), scratch_dev, T, plan);
     HB_LAUNCHED();
     return HB_OK;
 }

@@ -4,11 +4,12 @@
 Same constructor / ``execute_augment_batch`` / ``__call__`` surface (augmented.py:25-52, 297, 396).
 The north-star transforms -- coloured/white noise, gain, background noise at a target SNR, RIR
 reverb -- run in ONE fused CUDA kernel per clip (``hb_augment_clips_f32``) with the noise bank and
-the RIR spectra resident in HBM; the length fix runs in ``hb_fix_length_i16``.  Of the K9 transforms
-(augmented.py:79-106) the two per-clip numpy ones -- SevenBandParametricEQ and
-TanhDistortion -- run on the device between the length fix and the batch transforms
-(``heybuddy_b200/dataset/k9.py``); PitchShift and BandStopFilter are not built: a non-zero
-probability raises.
+the RIR spectra resident in HBM; the length fix runs in ``hb_fix_length_i16``.  The K9 transforms
+(augmented.py:79-106) run on the device between the length fix and that kernel, in the
+reference's order: the per-clip numpy ones (SevenBandParametricEQ, TanhDistortion), then the head of the batch
+Compose (PitchShift, BandStopFilter) -- ``heybuddy_b200/dataset/k9.py``.  Their probabilities default to 0 here
+(BASELINE configs[1] has none of them; the reference's constants are 0.25 each) and all four libraries are absent
+offline, so their arithmetic is restated from published behaviour (parity unpinned).
 
 Randomness comes from the seeded draw table (``heybuddy_b200.dataset.draws``), generated in the
 reference's call order; with ``seed=None`` a fresh seed is drawn (the reference is unseeded).
@@ -151,11 +152,6 @@ class AugmentedAudioGenerator:
         seed: Optional[int] = None,
         first_batch: int = 0,
     ) -> None:
-        for name, p in (("pitch_shift_prob", pitch_shift_prob), ("band_stop_prob", band_stop_prob)):
-            if p:
-                raise NotImplementedError(
-                    f"{name}={p}: PitchShift (torch_pitch_shift phase vocoder + resampler) and BandStopFilter (julius windowed-sinc "
-                    "pair with replicate padding) are not built (heybuddy_b200/dataset/k9.py); set the probability to 0")
         if sample_rate != spec.SAMPLE_RATE:
             raise ValueError("the B200 hot path is 16 kHz only")
         self.device_id = device_id
@@ -181,7 +177,8 @@ class AugmentedAudioGenerator:
             background_noise_prob=background_noise_prob, background_noise_min_snr_db=background_noise_min_snr_db,
             background_noise_max_snr_db=background_noise_max_snr_db, reverb_prob=reverb_prob,
             seven_band_prob=seven_band_aug_prob, seven_band_gain_db=seven_band_aug_gain_db, tanh_distortion_prob=tanh_distortion_prob,
-            tanh_min_distortion=tanh_min_distortion, tanh_max_distortion=tanh_max_distortion)
+            tanh_min_distortion=tanh_min_distortion, tanh_max_distortion=tanh_max_distortion,
+            pitch_shift_prob=pitch_shift_prob, pitch_shift_semitones=pitch_shift_semitones, band_stop_prob=band_stop_prob)
         self.seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if seed is None else int(seed)
         self._augmentation_dataset = augmentation_dataset
         self._impulse_response_dataset = impulse_response_dataset

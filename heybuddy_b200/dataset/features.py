@@ -118,8 +118,12 @@ class TrainingFeaturesGenerator:
         augment_background_dataset: SupplementalDatasetType = None,
         augment_impulse_dataset: SupplementalDatasetType = None,
         augment_seven_band_prob: float = 0.0,
+        augment_seven_band_gain_db: float = DEFAULT_AUGMENT_SEVEN_BAND_GAIN_DB,
         augment_tanh_distortion_prob: float = 0.0,
+        augment_tanh_min_distortion: float = DEFAULT_AUGMENT_TANH_MIN_DISTORTION,
+        augment_tanh_max_distortion: float = DEFAULT_AUGMENT_TANH_MAX_DISTORTION,
         augment_pitch_shift_prob: float = 0.0,
+        augment_pitch_shift_semitones: int = DEFAULT_AUGMENT_PITCH_SHIFT_SEMITONES,
         augment_band_stop_prob: float = 0.0,
         augment_colored_noise_prob: float = DEFAULT_AUGMENT_COLORED_NOISE_PROB,
         augment_colored_noise_min_snr_db: float = DEFAULT_AUGMENT_COLORED_NOISE_MIN_SNR_DB,
@@ -166,8 +170,10 @@ class TrainingFeaturesGenerator:
         self.augment_background_dataset = augment_background_dataset
         self.augment_impulse_dataset = augment_impulse_dataset
         self.augment_probs = dict(
-            seven_band_aug_prob=augment_seven_band_prob, tanh_distortion_prob=augment_tanh_distortion_prob,
-            pitch_shift_prob=augment_pitch_shift_prob, band_stop_prob=augment_band_stop_prob,
+            seven_band_aug_prob=augment_seven_band_prob, seven_band_aug_gain_db=augment_seven_band_gain_db,
+            tanh_distortion_prob=augment_tanh_distortion_prob, tanh_min_distortion=augment_tanh_min_distortion,
+            tanh_max_distortion=augment_tanh_max_distortion, pitch_shift_prob=augment_pitch_shift_prob,
+            pitch_shift_semitones=augment_pitch_shift_semitones, band_stop_prob=augment_band_stop_prob,
             colored_noise_prob=augment_colored_noise_prob, colored_noise_min_snr_db=augment_colored_noise_min_snr_db,
             colored_noise_max_snr_db=augment_colored_noise_max_snr_db, colored_noise_min_f_decay=augment_colored_noise_min_f_decay,
             colored_noise_max_f_decay=augment_colored_noise_max_f_decay, background_noise_prob=augment_background_noise_prob,

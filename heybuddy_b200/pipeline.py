@@ -80,7 +80,7 @@ class DeviceChunk:
     colored_f_decay: Optional["object"]  # cuda f32 [k]
     n: int
     seed: int = 0
-    k9: Optional[tuple] = None          # (eq idx i32[ke], eq sos f64[ke,7,5], tanh idx i32[kt], tanh amount f32[kt]) on the device
+    k9: Optional[dict] = None           # K9Draws.pack(): name -> device tensor (ps_ratios / ps_counts stay host arrays)
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -128,31 +128,44 @@ class FeaturizePipeline:
         return np.ascontiguousarray(table.pad_before, dtype=np.int32), params, ids, f_decay
 
     @staticmethod
-    def _k9_counts(table: DrawTable) -> Tuple[int, int]:
-        return (0, 0) if table.k9 is None else (int(np.count_nonzero(table.k9.eq_apply)), int(np.count_nonzero(table.k9.tanh_apply)))
+    def _k9_pack(table: DrawTable) -> Optional[Dict[str, np.ndarray]]:
+        """The table's packed K9 draws (built once per table: the band-stop FIRs are designed here), or None when nothing was drawn."""
+        if table.k9 is None or not table.k9.any():
+            return None
+        pk = getattr(table, "_k9_packed", None)
+        if pk is None:
+            pk = table.k9.pack()
+            table._k9_packed = pk
+        return pk
 
-    def _meta_layout(self, n: int, k: int, k9: Tuple[int, int] = (0, 0)) -> Tuple[Dict[str, Tuple[int, int]], int]:
+    def _meta_layout(self, n: int, k: int, k9: Optional[Dict[str, np.ndarray]] = None) -> Tuple[Dict[str, Tuple[int, int]], int]:
         """
         Byte ranges of the per-chunk metadata blob: offsets i64[n+1], pads i32[n], params [n][32], ids i64[k], f_decay f32[k] and,
-        when K9 transforms were drawn, eq clip indices i32[ke] + sos f64[ke][7][5] and tanh clip indices i32[kt] + amounts f32[kt].
+        when K9 transforms were drawn, the device-side arrays of ``K9Draws.pack()`` (index lists, biquads, band-stop FIR rows).
         """
-        ke, kt = k9
+        from heybuddy_b200.dataset.k9 import HOST_ONLY
+
+        fields = [("offsets", 8 * (n + 1)), ("pads", 4 * n), ("params", 32 * n), ("ids", 8 * k), ("fd", 4 * k)]
+        if k9 is not None:
+            fields += [(name, int(arr.nbytes)) for name, arr in k9.items() if name not in HOST_ONLY]
         lay, at = {}, 0
-        for name, nbytes in (("offsets", 8 * (n + 1)), ("pads", 4 * n), ("params", 32 * n), ("ids", 8 * k), ("fd", 4 * k),
-                             ("eq_idx", 4 * ke), ("eq_sos", 8 * 35 * ke), ("th_idx", 4 * kt), ("th_amt", 4 * kt)):
+        for name, nbytes in fields:
             lay[name] = (at, nbytes)
             at = _align(at + nbytes)
         return lay, max(at, 256)
 
     def _fill_meta(self, blob: np.ndarray, clips: RaggedClips, table: DrawTable) -> Tuple[Dict[str, Tuple[int, int]], int, int]:
+        from heybuddy_b200.dataset.k9 import HOST_ONLY
+
         pads, params, ids, fd = self.pack_params(table)
         n, k = len(clips), int(ids.shape[0])
         assert params.shape[0] == n == pads.shape[0], (params.shape, pads.shape, n)
-        lay, total = self._meta_layout(n, k, self._k9_counts(table))
+        k9 = self._k9_pack(table)
+        lay, total = self._meta_layout(n, k, k9)
         assert blob.nbytes >= total
         arrays = [("offsets", clips.offsets), ("pads", pads), ("params", params), ("ids", ids), ("fd", fd)]
-        if table.k9 is not None:
-            arrays += list(zip(("eq_idx", "eq_sos", "th_idx", "th_amt"), table.k9.pack()))
+        if k9 is not None:
+            arrays += [(name, arr) for name, arr in k9.items() if name not in HOST_ONLY]
         for name, arr in arrays:
             at, nbytes = lay[name]
             if nbytes:
@@ -160,18 +173,18 @@ class FeaturizePipeline:
         return lay, total, k
 
     @staticmethod
-    def _chunk_from_meta(samples_dev, meta_dev, lay, n: int, k: int, seed: int) -> DeviceChunk:
+    def _chunk_from_meta(samples_dev, meta_dev, lay, n: int, k: int, seed: int, k9_host: Optional[Dict[str, np.ndarray]] = None) -> DeviceChunk:
         import torch
+
+        from heybuddy_b200.dataset.k9 import HOST_ONLY
 
         def view(name, dtype, shape):
             at, nbytes = lay[name]
             return meta_dev[at:at + nbytes].view(dtype).view(shape)
 
-        ke, kt = lay["eq_idx"][1] // 4, lay["th_idx"][1] // 4
         k9 = None
-        if ke or kt:
-            k9 = (view("eq_idx", torch.int32, (ke,)), view("eq_sos", torch.float64, (ke, 7, 5)), view("th_idx", torch.int32, (kt,)),
-                  view("th_amt", torch.float32, (kt,)))
+        if k9_host is not None:
+            k9 = {name: (arr if name in HOST_ONLY else view(name, torch.from_numpy(arr[:0]).dtype, arr.shape)) for name, arr in k9_host.items()}
         return DeviceChunk(
             samples=samples_dev, offsets=view("offsets", torch.int64, (n + 1,)), pad_before=view("pads", torch.int32, (n,)),
             params=view("params", torch.uint8, (n, 32)), colored_ids=view("ids", torch.int64, (k,)) if k else None,
@@ -182,12 +195,12 @@ class FeaturizePipeline:
         import torch
 
         n = len(clips)
-        _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_counts(table))
+        _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_pack(table))
         blob = np.zeros(total, dtype=np.uint8)
         lay, total, k = self._fill_meta(blob, clips, table)
         dev = self.device
         return self._chunk_from_meta(torch.from_numpy(np.ascontiguousarray(clips.samples)).to(dev), torch.from_numpy(blob).to(dev),
-                                     lay, n, k, table.seed)
+                                     lay, n, k, table.seed, self._k9_pack(table))
 
     # -- device path -----------------------------------------------------------------------------------
     def _buf(self, name: str, shape, dtype):
@@ -281,13 +294,12 @@ class FeaturizePipeline:
                 _native.check(lib.hb_fix_length_i16(chunk.samples.data_ptr(), chunk.offsets.data_ptr(), chunk.pad_before.data_ptr(),
                                                     fixed.data_ptr(), n, t, st), "hb_fix_length_i16")
                 if chunk.k9 is not None:
-                    # K9: the reference's per-clip numpy transforms sit between the length fix and the batch transforms
-                    # (augmented.py:325-328): SevenBandParametricEQ, then TanhDistortion, in place on the selected clips
-                    eq_idx, eq_sos, th_idx, th_amt = chunk.k9
-                    if eq_idx.numel():
-                        _native.check(lib.hb_k9_eq_f32(fixed.data_ptr(), eq_idx.data_ptr(), eq_sos.data_ptr(), int(eq_idx.numel()), t, st), "hb_k9_eq_f32")
-                    if th_idx.numel():
-                        _native.check(lib.hb_k9_tanh_f32(fixed.data_ptr(), th_idx.data_ptr(), th_amt.data_ptr(), int(th_idx.numel()), t, st), "hb_k9_tanh_f32")
+                    # K9: the reference's per-clip numpy transforms (augmented.py:325-328: SevenBandParametricEQ, TanhDistortion) and
+                    # the head of its batch Compose (:369-372: PitchShift, BandStopFilter), in place on the selected clips
+                    from heybuddy_b200.dataset.k9 import apply_packed
+
+                    with _nvtx("hb/k9"):
+                        apply_packed(fixed, chunk.k9, lambda name, numel, dtype: self._grow("k9_" + name, numel, dtype))
                     self._mark("k9")
                 _native.check(lib.hb_augment_clips_f32(fixed.data_ptr(), *banks, chunk.params.data_ptr(), audio.data_ptr(), n, t, st),
                               "hb_augment_clips_f32")
@@ -434,7 +446,7 @@ class FeaturizePipeline:
             while len(done_events) > 0 and k - done_events[0][0] >= MAX_INFLIGHT:
                 blocked(done_events.popleft()[1])
             torch.cuda.nvtx.range_push(f"hb/stage_chunk[{n}]")
-            _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_counts(table))
+            _, total = self._meta_layout(n, int(np.count_nonzero(table.colored_apply)), self._k9_pack(table))
             meta_pin = pinned("meta", slot, total, torch.uint8)
             lay, total, kc = self._fill_meta(meta_pin.numpy(), part, table)
             if part.pinned is not None:
@@ -452,7 +464,7 @@ class FeaturizePipeline:
                 ev.record(copy_stream)
             stage_events[slot] = ev
             torch.cuda.nvtx.range_pop()
-            return self._chunk_from_meta(samples_dev, meta_dev, lay, n, kc, table.seed), meta_dev, ev, sink, lo, hi
+            return self._chunk_from_meta(samples_dev, meta_dev, lay, n, kc, table.seed, self._k9_pack(table)), meta_dev, ev, sink, lo, hi
 
         def deliver(sink, lo, hi, pin, done_ev):
             done_ev.synchronize()

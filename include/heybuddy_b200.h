@@ -140,6 +140,27 @@ int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-f
 int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream);
 int hb_k9_tanh_f32(float* clips_dev, const int32_t* clip_index_dev, const float* amount_dev, int k, int T, void* stream);
 
+/* ---- K9: the two batch transforms ahead of AddColoredNoise / Gain (torch_audiomentations.Compose, augmented.py:93-106, applied at
+ * :369-372; mode per_batch).  Both work in place on the clips listed in clip_index_dev.
+ * hb_k9_bandstop_f32: BandStopFilter = x - julius.bandpass_filter(x): one FIR (difference of two Hann-windowed-sinc low-passes of
+ *                 2 h + 1 taps, replicate padding) per batch, run as a partitioned overlap-save convolution on the clip's
+ *                 exact-length FFT.  meta_dev i32 [k][3] = (first spectrum row, partitions, h) per clip; spec_dev = hb_rir_spectrum
+ *                 of the partition rows (T / 2 taps each, zero-padded to T); scratch_dev f32 [k][T].
+ * hb_k9_pitch_f32: PitchShift = torch_pitch_shift.pitch_shift: torch.stft(250, 7, rectangular) -> torchaudio phase vocoder ->
+ *                 torch.istft -> torchaudio sinc resampling -> crop / zero-pad.  A plan holds one ratio's host-computed tables:
+ *                 the vocoder's time steps (idx0 = floor(t), idx1 = floor(t + 1), alpha = t mod 1; float32, as the library
+ *                 computes them), the phase advance per bin, and the resampling kernel f32 [up][2 width + orig]. */
+int hb_k9_bandstop_f32(float* clips_dev, const int32_t* clip_index_dev, const int32_t* meta_dev, const float* spec_dev,
+                       float* scratch_dev, int k, int T, void* stream);
+typedef struct hb_pitch_plan hb_pitch_plan;
+int hb_pitch_plan_create(hb_pitch_plan** out, int T, int n_fft, int hop, int frames_out, const int32_t* idx0_host,
+                         const int32_t* idx1_host, const float* alpha_host, const float* phase_advance_host, int orig, int up,
+                         int width, const float* kernel_host);
+int hb_pitch_plan_destroy(hb_pitch_plan* plan);
+int64_t hb_k9_pitch_workspace_bytes(const hb_pitch_plan* plan, int k);
+int hb_k9_pitch_f32(const hb_pitch_plan* plan, float* clips_dev, const int32_t* clip_index_dev, int k, void* workspace_dev,
+                    int64_t workspace_bytes, void* stream);
+
 /* a1: int16 ragged clips -> length-fixed f32 [n][T] (to_target_length, augmented.py:200-232):
  * /32768, front-truncate when longer than T, otherwise zero-pad with pad_before[b] zeros on
  * the left.  samples_dev: concatenated int16 samples; offsets_dev i64[n+1]; pad_before_dev i32[n]. */
