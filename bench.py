@@ -52,7 +52,7 @@ POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cy
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
 N_RIRS = 271
-K9_PROB = float(os.environ.get("HB_BENCH_K9", "0"))         # SevenBandParametricEQ / TanhDistortion probability (value leg + stages only)
+K9_PROB = float(os.environ.get("HB_BENCH_K9", "0"))         # probability of each of the four K9 transforms (value leg + stages only)
 CLIP_SECONDS = 1.44
 METRIC = "clip-sec featurized/sec (aug+mel+embed)"
 UNIT = "clip-s/s"
@@ -441,7 +441,7 @@ def main():
     aug = AugmentedAudioGenerator(
         [], device_id=local_rank, augmentation_dataset=noise_bank, impulse_response_dataset=rir_bank, batch_size=AUG_BATCH,
         colored_noise_min_f_decay=0.0, colored_noise_max_f_decay=0.0, seed=2004,
-        seven_band_aug_prob=K9_PROB, tanh_distortion_prob=K9_PROB,          # 0 in BASELINE configs[1]; HB_BENCH_K9=0.25 = the reference's defaults
+        seven_band_aug_prob=K9_PROB, tanh_distortion_prob=K9_PROB, pitch_shift_prob=K9_PROB, band_stop_prob=K9_PROB,   # 0 in BASELINE configs[1]; HB_BENCH_K9=0.25 = the reference's defaults
         first_batch=rank * POOL * (CHUNK // AUG_BATCH))
     aug._noise_cursor = (rank * 211) % NOISE_CLIPS
     pipe = FeaturizePipeline(aug, speech, device_id=local_rank)
@@ -604,7 +604,7 @@ def main():
             "mel": "fp32 register FFT + BANDED fp32 projection (each mel bin sums its <= 16 FFT bins; the dense 257x32 GEMM the north star "
                    "names is 88 % zeros and TF32 operands would break the 1e-4 budget) -- a deliberate deviation, DESIGN.md 5.2",
             "colored": "hb_colored_bases: the chunk's coloured-noise patterns regenerated on the device from the draw table's Philox counters",
-            "k9": "hb_k9_eq_f32 + hb_k9_tanh_f32 on the clips whose coins came up (HB_BENCH_K9; 0 in BASELINE configs[1])",
+            "k9": "hb_k9_eq_f32 + hb_k9_tanh_f32 + hb_k9_pitch_f32 + hb_k9_bandstop_f32 on the clips / batches whose coins came up (HB_BENCH_K9; 0 in BASELINE configs[1])",
             "augment": "parity-mode kernel hb_augment_clips_i16 (writes the f32 [n][T] clip), timed in a separate staged pass",
             "augment_mel_fused": "PRODUCTION mode, what `value` runs: hb_colored_bases + hb_augment_mel_i16 (length fix + augmentation + mel in one kernel, the "
                                  "augmented clip stays in shared memory; bit-identical to augment -> mel). Not part of `share` (the staged pass is)",

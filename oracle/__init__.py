@@ -27,4 +27,10 @@ Parity status:
   speech-embedding.onnx, torch_audiomentations>=0.11, speechbrain>=1.0).  The
   oracle restates their published behaviour and anchors
   on the reference's call sites and pinned shapes.
+* K9 (``oracle.k9``): SevenBandParametricEQ, TanhDistortion, BandStopFilter
+  -- **PARITY UNPINNED** (audiomentations, torch_audiomentations, julius absent;
+  scipy ``sosfilt`` / numpy ``percentile`` / torch do the arithmetic the libraries
+  delegate).  PitchShift: the four stages are the library's own calls
+  (``torch.stft``, torchaudio ``TimeStretch`` / ``Resample``, ``torch.istft``: present,
+  PINNED); ``torch_pitch_shift``'s glue around them is restated (UNPINNED).
 """

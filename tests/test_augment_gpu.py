@@ -186,14 +186,6 @@ def test_colored_bases_device_matches_host_restatement(cuda_device):
         assert np.abs(got[i] - want).max() < 5e-6 * np.abs(want).max(), (i, np.abs(got[i] - want).max())
 
 
-def test_unsupported_transforms_raise():
-    """PitchShift and BandStopFilter are not built (heybuddy_b200/dataset/k9.py): a non-zero probability raises."""
-    from heybuddy_b200.dataset.augmented import AugmentedAudioGenerator
-
-    with pytest.raises(NotImplementedError):
-        AugmentedAudioGenerator([], pitch_shift_prob=0.25)
-
-
 def test_fused_length_fix_is_bit_identical(cuda_device):
     """hb_augment_clips_i16 (length fix fused into the kernel's load) == hb_fix_length_i16 -> hb_augment_clips_f32."""
     from heybuddy_b200 import _native

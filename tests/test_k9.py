@@ -75,6 +75,12 @@ def test_batch_k9_draws_and_packing():
     assert part.k9.ps_shift == t.slice(5, 9).k9.ps_shift
 
 
+def test_pitch_shift_without_a_fast_ratio_raises():
+    """torch_audiomentations raises when no fast ratio lies inside the semitone range; so does the draw table."""
+    with pytest.raises(ValueError):
+        DrawTable.build(np.full(16, 9000), AugmentConfig(batch_size=8, pitch_shift_prob=1.0, pitch_shift_semitones=0.2), 1)
+
+
 def test_fast_shifts_and_bandstop_design():
     assert fast_shifts(16000, 3) == [Fraction(125, 128), Fraction(128, 125)]          # torch_pitch_shift.get_fast_shifts at 16 kHz
     assert fast_shifts(16000, 4) == [Fraction(4, 5), Fraction(125, 128), Fraction(128, 125), Fraction(5, 4)]
