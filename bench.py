@@ -52,6 +52,7 @@ POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cy
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
 N_RIRS = 271
+WRITER_THREADS = int(os.environ.get("HB_BENCH_WRITERS", "4"))   # sink threads of the e2e leg (generate_sharded's default is 4)
 K9_PROB = float(os.environ.get("HB_BENCH_K9", "0"))         # probability of each of the four K9 transforms (value leg + stages only)
 CLIP_SECONDS = 1.44
 METRIC = "clip-sec featurized/sec (aug+mel+embed)"
@@ -525,7 +526,8 @@ def main():
         pending = []
         for name, gen in gens:
             gen._cursor_cache.clear()                        # nothing pre-built: the cursor prefix is recomputed inside the call
-            pending.append(gen.generate_sharded(rows, os.path.join(out_dir, f"{tag}{name}.npy"), barrier=dist_barrier, defer=True))
+            pending.append(gen.generate_sharded(rows, os.path.join(out_dir, f"{tag}{name}.npy"), barrier=dist_barrier, defer=True,
+                                                writer_threads=WRITER_THREADS))
             h2d, d2h = h2d + gen.last_h2d_bytes, d2h + gen.last_d2h_bytes
         for finish in pending:
             finish()
