@@ -14,18 +14,24 @@ namespace hb {
 constexpr int kEqBands = 7;
 
 // ---- SevenBandParametricEQ: seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt) ----------------------------
-// An IIR cascade is a serial recurrence in time, computed in float64 (what sosfilt computes in; a float32 direct form loses up to
-// 1e-2 on the low-Q shelves).  An FP64 FMA has ~50 cycles of latency here, so the cost of a clip is (dependent FMAs per sample)
-// x 50 cycles x 23040 samples, whatever else the GPU could be doing -- 2.6 ms when one thread runs the seven sections one after
-// the other.  Two things shorten the chain to ONE FMA per sample:
-//   * a SYSTOLIC ARRAY across lanes -- eight lanes per clip (four clips per warp), lane s owns section s (lane 7 is a pure delay);
-//     at tick tau lane s works on sample tau - 3 s, its input arriving by shuffle from lane s - 1's output of three ticks ago, so
-//     the shuffle and the feed-forward part are off the critical path;
-//   * direct form I inside a lane: y[n] = f[n] - a1 y[n-1] - a2 y[n-2] with f = b0 v[n] + b1 v[n-1] + b2 v[n-2]; only
-//     fma(-a1, y[n-1], .) waits for the previous tick.
-// Lane 7's output lags the input by 24 samples, so loads and stores are whole, aligned float4s (in place: the store trails the
-// load by six groups).
+// scipy filters in float64; a float32 DIRECT form loses up to 1e-2 on the low-Q shelves (poles a few 1e-3 from z = 1: the
+// coefficients cancel).  Round 2 first ran the cascade in FP64 (1.9 ms per 2029 clips: B200 issues non-tensor FP64 at one lane per
+// clock per SM sub-partition).  The same transfer function in the trapezoidal state-variable form (Zavalishin's TPT structure) has no
+// such cancellation: any stable biquad maps exactly onto it --
+//     z^-1 = (1 - s) / (1 + s):  H = (n2 s^2 + n1 s + n0) / (d2 s^2 + d1 s + d0),  n2 = b0 - b1 + b2, n1 = 2 (b0 - b2), n0 = b0 + b1 + b2,
+//                                                                                 d2 = 1 - a1 + a2,  d1 = 2 (1 - a2),  d0 = 1 + a1 + a2
+//     g = sqrt(d0 / d2), k = d1 / (d2 g);  out = m0 v0 + m1 v1 + m2 v2,  m0 = n2 / d2, m1 = n1 / (d2 g) - m0 k, m2 = n0 / (d2 g^2) - m0
+//     v3 = v0 - ic2;  v1 = a1 ic1 + a2 v3;  v2 = ic2 + a2 ic1 + a3 v3;  ic1 = 2 v1 - ic1;  ic2 = 2 v2 - ic2   (a1 = 1 / (1 + g (g + k)), a2 = g a1, a3 = g a2)
+// -- and in FLOAT32 it stays within 4e-6 of float64 sosfilt over the whole parameter range (measured on the CPU, 64 random cascades;
+// 8e-12 in float64).  The per-section constants are derived from the caller's float64 sos once per lane, in float64.
+//
+// The cascade is a SYSTOLIC ARRAY across lanes: eight lanes per clip (four clips per warp), lane s owns section s (lane 7 is a pure
+// delay); at tick tau lane s works on sample tau - 3 s, its input arriving by shuffle from lane s - 1's output of three ticks ago,
+// so the shuffle is off the loop-carried chain (ic1, ic2: four dependent float32 operations per tick).  Lane 7's output lags the
+// input by 24 samples, so loads and stores are whole, aligned float4s (in place: the store trails the load by six groups); lane 0's
+// loads run one 32-sample block ahead of the arithmetic.
 constexpr int kEqLanes = 8, kEqDelay = 3, kEqLagGroups = kEqLanes * kEqDelay / 4;      // 24 samples = 6 float4 groups
+constexpr int kEqBlock = 8;                                                             // float4 groups per prefetched block
 
 __global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, const int32_t* __restrict__ clip_index,
                                                    const double* __restrict__ sos, int k, int T) {
@@ -33,40 +39,71 @@ __global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, co
     const int lane = threadIdx.x & 31, sec = lane & (kEqLanes - 1);
     const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / kEqLanes) + lane / kEqLanes;   // clip of this 8-lane group
     const bool live = i < k;
-    double b0 = 1.0, b1 = 0.0, b2 = 0.0, a1 = 0.0, a2 = 0.0;        // lane 7 (and idle groups): identity
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f, m0 = 1.f, m1 = 0.f, m2 = 0.f;       // lane 7 (and idle groups): identity
     if (live && sec < kEqBands) {
         const double* c = sos + ((int64_t)i * kEqBands + sec) * 5;
-        b0 = c[0]; b1 = c[1]; b2 = c[2]; a1 = c[3]; a2 = c[4];
+        const double b0 = c[0], b1 = c[1], b2 = c[2], p1 = c[3], p2 = c[4];
+        const double n2 = b0 - b1 + b2, n1 = 2.0 * (b0 - b2), n0 = b0 + b1 + b2;
+        const double d2 = 1.0 - p1 + p2, d1 = 2.0 * (1.0 - p2), d0 = 1.0 + p1 + p2;
+        const double g = sqrt(d0 / d2), kk = d1 / (d2 * g);
+        const double hp = n2 / d2;
+        const double e1 = 1.0 / (1.0 + g * (g + kk));
+        a1 = (float)e1; a2 = (float)(g * e1); a3 = (float)(g * g * e1);
+        m0 = (float)hp; m1 = (float)(n1 / (d2 * g) - hp * kk); m2 = (float)(n0 / (d2 * g * g) - hp);
     }
     float* x = clips + (int64_t)(live ? clip_index[i] : 0) * T;
     const bool vec = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    double d1 = 0.0, d2 = 0.0, d3 = 0.0, v1 = 0.0, v2 = 0.0;      // this lane's last three outputs and last two inputs
-    const int groups = (T + 3) / 4;
-    for (int g = 0; g < groups + kEqLagGroups; ++g) {
-        float xin[4] = {0.f, 0.f, 0.f, 0.f};
-        if (live && sec == 0 && g < groups) {
-            if (vec) *reinterpret_cast<float4*>(xin) = *reinterpret_cast<const float4*>(x + 4 * g);
-            else
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (4 * g + j < T) xin[j] = x[4 * g + j];
+    const bool loader = live && sec == 0, storer = live && sec == kEqLanes - 1;
+    float ic1 = 0.f, ic2 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;        // state; this lane's last three outputs
+    const int groups = (T + 3) / 4, total = groups + kEqLagGroups;
+    auto load_group = [&](int g) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (loader && g < groups) {
+            if (vec) v = *reinterpret_cast<const float4*>(x + 4 * g);
+            else {
+                if (4 * g + 0 < T) v.x = x[4 * g + 0];
+                if (4 * g + 1 < T) v.y = x[4 * g + 1];
+                if (4 * g + 2 < T) v.z = x[4 * g + 2];
+                if (4 * g + 3 < T) v.w = x[4 * g + 3];
+            }
         }
-        float o[4];
+        return v;
+    };
+    float4 nxt[kEqBlock];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double up = __shfl_up_sync(0xffffffffu, d3, 1, kEqLanes);
-            const double v = sec == 0 ? (double)xin[j] : up;
-            o[j] = (float)d3;                         // lane 7: sample tau - 24 = 4 (g - 6) + j
-            const double f = fma(b0, v, fma(b1, v1, b2 * v2));
-            const double y = fma(-a1, d1, fma(-a2, d2, f));
-            d3 = d2; d2 = d1; d1 = y;
-            v2 = v1; v1 = v;
-        }
-        if (live && sec == kEqLanes - 1 && g >= kEqLagGroups) {
-            float* dst = x + 4 * (g - kEqLagGroups);
-            if (vec) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            else
+    for (int q = 0; q < kEqBlock; ++q) nxt[q] = load_group(q);
+    for (int g0 = 0; g0 < total; g0 += kEqBlock) {
+        float4 cur[kEqBlock];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (4 * (g - kEqLagGroups) + j < T) dst[j] = o[j];
+        for (int q = 0; q < kEqBlock; ++q) cur[q] = nxt[q];
+#pragma unroll
+        for (int q = 0; q < kEqBlock; ++q) nxt[q] = load_group(g0 + kEqBlock + q);     // in flight during this block's 32 ticks
+#pragma unroll
+        for (int q = 0; q < kEqBlock; ++q) {
+            const int g = g0 + q;
+            if (g >= total) break;
+            const float xin[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float up = __shfl_up_sync(0xffffffffu, d3, 1, kEqLanes);
+                const float v0 = sec == 0 ? xin[j] : up;
+                o[j] = d3;                                // lane 7: sample tau - 24 = 4 (g - 6) + j
+                const float v3 = v0 - ic2;
+                const float v1 = fmaf(a2, v3, a1 * ic1);
+                const float v2 = fmaf(a3, v3, fmaf(a2, ic1, ic2));
+                ic1 = fmaf(2.0f, v1, -ic1);
+                ic2 = fmaf(2.0f, v2, -ic2);
+                const float y = fmaf(m0, v0, fmaf(m1, v1, m2 * v2));
+                d3 = d2; d2 = d1; d1 = y;
+            }
+            if (storer && g >= kEqLagGroups) {
+                float* dst = x + 4 * (g - kEqLagGroups);
+                if (vec) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (4 * (g - kEqLagGroups) + j < T) dst[j] = o[j];
+            }
         }
     }
 }
@@ -166,7 +203,7 @@ using namespace hb;
 extern "C" int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream) {
     HB_REQUIRE(k >= 0 && T > 0 && (k == 0 || (clips_dev && clip_index_dev && sos_dev)), "hb_k9_eq_f32: bad argument");
     if (k == 0) return HB_OK;
-    // one warp (four clips) per block: the kernel is FP64-issue bound per warp, so spread the warps over every SM sub-partition
+    // one warp (four clips) per block: a warp is one latency chain, so spread the warps over every SM sub-partition
     k9_eq_kernel<<<ceil_div(k, 32 / kEqLanes), 32, 0, (cudaStream_t)stream>>>(clips_dev, clip_index_dev, sos_dev, k, T);
     HB_LAUNCHED();
     return HB_OK;

@@ -134,8 +134,9 @@ int hb_augment_clips_f32(const float* clips_dev,          /* f32 [n][T] length-f
 
 /* ---- K9: the reference's per-clip numpy augmentations (audiomentations.Compose, augmented.py:79-90, applied at :325-328) ----
  * In place on the f32 [n][T] length-fixed clips, only on the clips listed in clip_index_dev (the ones whose coin came up).
- * hb_k9_eq_f32:   SevenBandParametricEQ = seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt), float64
- *                 arithmetic; sos_dev f64 [k][7][5] = (b0, b1, b2, a1, a2) / a0 per section (computed on the host from the draws).
+ * hb_k9_eq_f32:   SevenBandParametricEQ = seven cascaded biquads, causal, zero initial state (scipy.signal.sosfilt); sos_dev f64
+ *                 [k][7][5] = (b0, b1, b2, a1, a2) / a0 per section (computed on the host from the draws).  Each biquad runs in the
+ *                 trapezoidal state-variable form (same transfer function, float32, within 4e-6 of float64 sosfilt).
  * hb_k9_tanh_f32: TanhDistortion = tanh(x * 0.5 / (percentile(|x|, 100 - 99 amount) + 1e-6)), RMS-matched to the input. */
 int hb_k9_eq_f32(float* clips_dev, const int32_t* clip_index_dev, const double* sos_dev, int k, int T, void* stream);
 int hb_k9_tanh_f32(float* clips_dev, const int32_t* clip_index_dev, const float* amount_dev, int k, int T, void* stream);
