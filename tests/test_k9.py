@@ -203,6 +203,31 @@ def test_bandstop_kernel_matches_oracle(cuda_device):
 
 
 @pytest.mark.gpu
+def test_batch_k9_transforms_at_another_clip_length(cuda_device):
+    """1 s clips (T = 16000): band-stop on the generic exact-length FFT plan, pitch shift with the tables of that length."""
+    import torch
+
+    from heybuddy_b200.dataset import k9
+
+    t = 16000
+    cfg = AugmentConfig(batch_size=4, target_samples=t, band_stop_prob=0.5, pitch_shift_prob=0.5)
+    rng = np.random.default_rng(21)
+    n = 24
+    table = DrawTable.build(rng.integers(4000, 15000, size=n), cfg, 9)
+    assert table.k9.bs_apply.any() and table.k9.ps_apply.any()
+    fixed = np.zeros((n, t), dtype=np.float32)
+    for i in range(n):
+        ln = int(rng.integers(4000, 12000))
+        fixed[i, 2000:2000 + ln] = (rng.standard_normal(ln) * 0.1).astype(np.float32)
+    want = ok9.apply_table(fixed, table)
+    got = k9.apply_device(torch.from_numpy(fixed.copy()).cuda(), table).cpu().numpy()
+    scale = np.maximum(np.abs(want).max(axis=1, keepdims=True), 1e-12)
+    err = (np.abs(got - want) / scale).max(axis=1)
+    both = np.repeat(table.k9.bs_apply & table.k9.ps_apply, table.k9.sizes)      # pitch then band-stop: the chained case
+    assert err[~both].max() < 1e-4 and err.max() < 2e-3, (err[~both].max(), err.max())
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("ratio", [Fraction(128, 125), Fraction(125, 128)])
 def test_pitch_shift_stages_match_torch(cuda_device, ratio):
     """hb_k9_pitch_f32 stage by stage against the library calls torch_pitch_shift makes: torch.stft, torchaudio's phase vocoder,
