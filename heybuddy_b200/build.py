@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
-] + os.environ.get("HB_NVCC_EXTRA", "").split()      # e.g. -DHB_TC_FINE for the profiling stamps in embed_tc.cu
+] + os.environ.get("HB_NVCC_EXTRA", "").split()      # e.g. -DHB_TCG_PLANE_SKEW=32 for the experiments in embed_tcg.cu
 
 
 def nvcc() -> str:

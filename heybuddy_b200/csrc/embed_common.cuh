@@ -34,8 +34,8 @@ struct hb_embed_model {
     float* w32 = nullptr;              // packed fp32 [layer: kernel HWIO, bias]
     int64_t w_off[hb::kNumConv];       // float offset of each layer's kernel
     int64_t b_off[hb::kNumConv];       // float offset of each layer's bias
-    void* tc = nullptr;                // tensor-core path's repacked weights (embed_tc.cu)
-    void* tcg = nullptr;               // blocks 1-2: Toeplitz-packed weights (embed_tcg.cu)
+    void* tcg = nullptr;               // blocks 1-4: Toeplitz-packed weights (embed_tcg.cu)
+    void* tail = nullptr;              // conv2d_16..19: per-layer B operands (embed_tail.cu)
     int device = 0;
 };
 
@@ -65,8 +65,17 @@ int tcg_block2(const hb_embed_model* m, const __half* in_dev, __half* out_dev, i
 int tcg_block3(const hb_embed_model* m, const __half* in_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
                cudaStream_t st);
 int tcg_block4(const hb_embed_model* m, const __half* in_dev, __half* out_dev, int B, int in_T, float* dbg, int dbg_layer,
-               cudaStream_t st);
+               cudaStream_t st, __half* pool2_out = nullptr);
+int tcg_block4_rows_per_tile();
 int tcg_block4_max_rows();
 int tcg_check_timeout();
+// embed_tail.cu (conv2d_15's pool + conv2d_16 .. 19, one launch per layer over both pool phases)
+int tail_prepare(hb_embed_model* m, const float* weights_host);
+void tail_release(hb_embed_model* m);
+int64_t tail_scratch_bytes(int B, int T15);
+int tail_run(const hb_embed_model* m, const __half* block4_out, bool pooled, int B, int T15, float* out0, float* out1, void* scratch,
+             int64_t scratch_bytes, int upto, float* dbg_out, cudaStream_t st);
+int tail_check_timeout();
+int tail_debug_times(long long* out_host);
 int tcg_debug_times(long long* out_host);
 }  // namespace hb

@@ -128,6 +128,8 @@ struct GArgs {
     const float* bias;            // NL x C
     const float* l0_w;            // MEL_IN: conv2d kernel f32 [3][24] + bias [24]
     const uint16_t* tab;          // [NL][16 * kGTabRow] epilogue scatter tables (tcg_tables)
+    __half* pool2_out;            // block 4 only, optional: the tail's input instead of `out` -- conv2d_15's 2x2 pool for BOTH time
+                                  // phases, fp16 [(clip, phase, row)][bin 0..1][12 chunks][8] (embed_tail.cu); one tile per clip
     float* dbg;                   // optional f32 NHWC [clips][dbg_T][F][C] activation dump
     int dbg_layer;                // -1 none, 100 = staged input (MEL_IN: conv2d output), l = output of tensor-core layer l
     int dbg_T;
@@ -462,8 +464,39 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
 
+    // ---- block 4 feeding the tail: conv2d_15's 2x2 max-pool for both time phases, straight from the tile in shared memory ------
+    bool stored = false;
+    if constexpr (G == 1 && F == 4 && Cfg::POOL_T == 1 && Cfg::POOL_F == 1) {
+        if (a.pool2_out != nullptr) {
+            // item (chunk, phase, pooled row, pooled bin), chunk slowest: rows 2 rp + phase, + 1 and bins 2 fo, 2 fo + 1 of layout P
+            const int R = a.T_out / 2;
+            uint4* o = reinterpret_cast<uint4*>(a.pool2_out) + (int64_t)clip * 2 * R * 2 * CC;
+            for (int i = tid; i < CC * 2 * R * 2; i += kGThreads) {
+                const int fo = i & 1;
+                int r = i >> 1;
+                const int rp = r % R;
+                r /= R;
+                const int ph = r & 1, ch = r >> 1;
+                const int rr = 2 * rp + ph;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (rr + 1 < a.T_out) {
+                    const unsigned char* base = act + ch * Cfg::PLAIN + (rr * F + 2 * fo) * 16;
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + 16);
+                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + 16);
+                    const __half2 *h0 = reinterpret_cast<const __half2*>(&x0), *h1 = reinterpret_cast<const __half2*>(&x1);
+                    const __half2 *h2 = reinterpret_cast<const __half2*>(&x2), *h3 = reinterpret_cast<const __half2*>(&x3);
+                    __half2 mx[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mx[j] = __hmax2_nan(__hmax2_nan(h0[j], h1[j]), __hmax2_nan(h2[j], h3[j]));
+                    v = *reinterpret_cast<uint4*>(mx);
+                }
+                o[((int64_t)(ph * R + rp) * 2 + fo) * CC + ch] = v;
+            }
+            stored = true;
+        }
+    }
     // ---- max-pool + store (fp16 chunk-major [clip][OUT_CH][T_out][F / 2][8]) -----------------------------------
-    {
+    if (!stored) {
         constexpr int PT = Cfg::POOL_T, PF = Cfg::POOL_F, Fo = F / PF;
         constexpr int rows_p = Cfg::ROWS_OUT / PT;
         static_assert(PT == 1 || PF == 2, "a time pool comes with a freq pool");
@@ -644,10 +677,11 @@ int tcg_pack(const float* weights_host, const std::vector<int64_t>& w_off, const
 
 template <class Cfg>
 int tcg_launch(const GWeights* gw, int which, const void* in, int in_chunks, __half* out, int B, int in_T, float* dbg, int dbg_layer,
-               cudaStream_t st) {
+               cudaStream_t st, __half* pool2_out = nullptr) {
     GArgs a;
     a.in = in;
     a.out = out;
+    a.pool2_out = pool2_out;
     a.w = gw->w[which];
     a.bias = gw->bias[which];
     a.l0_w = gw->l0;
@@ -750,12 +784,16 @@ int tcg_block3(const hb_embed_model* m, const __half* in, __half* out, int B, in
 
 // block 3 output fp16 [B][10][in_T][4][8] (chunk 9 = padding, not read) -> conv2d_15 output before its pool, fp16 chunk-major
 // [B][12][in_T - 4][4][8] (a 1.44 s clip has in_T = 30: one tile).  dbg: activation after conv2d_12 / 13 / 14, f32 NHWC [B][rows][4][96].
+// pool2_out != nullptr (and in_T - 4 <= 28 rows: one tile per clip): instead of `out`, write conv2d_15's 2x2 pool for both time phases
+// in the tail's operand format, fp16 [B][2 phases][(in_T - 4) / 2 rows][2 bins][12 chunks][8].
 int tcg_block4(const hb_embed_model* m, const __half* in, __half* out, int B, int in_T, float* dbg, int dbg_layer,
-               cudaStream_t st) {
+               cudaStream_t st, __half* pool2_out) {
     const GWeights* gw = reinterpret_cast<const GWeights*>(m->tcg);
     HB_REQUIRE(gw != nullptr, "tcg weights missing");
-    return tcg_launch<Cfg4>(gw, 3, in, 10, out, B, in_T, dbg, dbg_layer, st);
+    HB_REQUIRE(pool2_out == nullptr || (dbg == nullptr && in_T - 4 <= Cfg4::ROWS_OUT), "tcg_block4: the pooled store needs one tile per clip");
+    return tcg_launch<Cfg4>(gw, 3, in, 10, out, B, in_T, dbg, dbg_layer, st, pool2_out);
 }
+int tcg_block4_rows_per_tile() { return Cfg4::ROWS_OUT; }
 int tcg_block4_max_rows() { return Cfg4::TT; }
 
 // profiling aid: phase timestamps (start, setup, staged, layers.., stored, dealloc) of the first 8 CTAs of the last launch

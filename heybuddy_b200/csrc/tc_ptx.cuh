@@ -1,5 +1,5 @@
-// tcgen05 / TMEM / mbarrier / stmatrix PTX wrappers shared by the tensor-core embedding kernels (embed_tc.cu,
-// embed_tcg.cu).  Device-side globals are per translation unit (static): each .cu checks its own timeout flag.
+// tcgen05 / TMEM / mbarrier / stmatrix PTX wrappers shared by the tensor-core embedding kernels (embed_tcg.cu,
+// embed_tail.cu).  Device-side globals are per translation unit (static): each .cu checks its own timeout flag.
 #pragma once
 #include "embed_common.cuh"
 
@@ -13,13 +13,6 @@ namespace hb {
 static __device__ unsigned int g_tc_timeout = 0;  // set when a barrier wait gave up (never hang the GPU)
 static __device__ long long g_tc_times[8][16];    // phase timestamps of the first 8 CTAs of the last launch (profiling aid)
 #define TC_STAMP(i) do { if (tid == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
-#ifdef HB_TC_FINE
-// finer stamps inside layer 1 (MMA issuer = [0,16), epilogue warp 2 = [16,32), epilogue warp 9 = [32,48)); profiling builds only
-static __device__ long long g_tc_fine[8][48];
-#define TC_FINE(base, i) do { if (l == 1 && lane == 0 && blockIdx.x < 8 && (i) < 16) g_tc_fine[blockIdx.x][(base) + (i)] = clock64(); } while (0)
-#else
-#define TC_FINE(base, i) do { } while (0)
-#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -76,11 +69,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
-// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -133,36 +121,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 
-// 16 TMEM lanes x 16 fp32 columns (16x256b.x2): thread t gets, for each 8-column group g,
-//   v[4g+0], v[4g+1] = lane (t/4),     columns 8g + 2(t%4), +1
-//   v[4g+2], v[4g+3] = lane (t/4) + 8, same columns          (verified by scripts/micro/ldst_layout.cu)
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-// 16 lanes x 64 columns as two 32-column loads in flight under one wait: eight 8-column groups, v[4g..4g+3] as above.
-// Loads and wait live in ONE asm statement so no consumer can be scheduled before the wait.
-__device__ __forceinline__ void tmem_ld_16x256b_64cols(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr), "r"(taddr + 32u)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 // Split form of the load above for software pipelining: issue now, wait later.  The wait lists the destination
 // registers as in/out operands so that no consumer can be scheduled before it.
 __device__ __forceinline__ void tmem_ld_16x256b_64cols_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -211,17 +169,8 @@ __device__ __forceinline__ void stmatrix_x2_trans(uint32_t row_addr, uint32_t a,
 __device__ __forceinline__ void stmatrix_x4_trans(uint32_t row_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void stmatrix_x1_trans(uint32_t row_addr, uint32_t a) {
-    asm volatile("stmatrix.sync.aligned.m8n8.x1.trans.shared.b16 [%0], {%1};" ::"r"(row_addr), "r"(a) : "memory");
-}
 
-// LeakyReLU(0.2) as max(v, 0.2 v) (slope < 1); NaN propagates
-__device__ __forceinline__ float leaky(float v) { return fmaxf(v, kLeaky * v); }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
 // fp16 pair of LeakyReLU(a), LeakyReLU(b) for the f16 mode's epilogues: round to fp16 first, then max(h, 0.2 h) on the packed
 // pair -- 3 instructions per pair instead of 5 (the epilogues are issue bound: embed 5.04 -> 4.91 ms).  Non-negative values are
 // unchanged; a negative one is rounded twice (<= 1 fp16 ulp instead of 0.5), which moves the f16 mode's end-to-end error from
@@ -232,25 +181,5 @@ __device__ __forceinline__ uint32_t leaky_half2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&m);
 }
 
-// Epilogue of one 64-column sub-block of one accumulator tile for one 16-lane half:
-// TMEM (lane = channel, column = position) -> +bias -> LeakyReLU -> fp16 -> stmatrix.trans into the next layer's
-// [chunk][position][8] operand buffer.  kTwo: the half holds two 8-channel chunks (else only octet 0 is real).
-template <bool kTwo, bool kLeaky>
-__device__ __forceinline__ void epilogue_sub(uint32_t taddr, uint32_t row_addr, float b0, float b1) {
-    float v[32];
-    tmem_ld_16x256b_64cols(taddr, v);
-#pragma unroll
-    for (int g = 0; g < 8; g += 2) {   // two 8-position groups per store
-        const float x0 = v[4 * g + 0] + b0, x1 = v[4 * g + 1] + b0, x4 = v[4 * g + 4] + b0, x5 = v[4 * g + 5] + b0;
-        const uint32_t ra = kLeaky ? leaky_half2(x0, x1) : pack_half2(x0, x1), rc = kLeaky ? leaky_half2(x4, x5) : pack_half2(x4, x5);
-        if (kTwo) {
-            const float x2 = v[4 * g + 2] + b1, x3 = v[4 * g + 3] + b1, x6 = v[4 * g + 6] + b1, x7 = v[4 * g + 7] + b1;
-            stmatrix_x4_trans(row_addr + (uint32_t)(g * 8 * 16), ra, kLeaky ? leaky_half2(x2, x3) : pack_half2(x2, x3), rc,
-                              kLeaky ? leaky_half2(x6, x7) : pack_half2(x6, x7));
-        } else {
-            stmatrix_x2_trans(row_addr + (uint32_t)(g * 8 * 16), ra, rc);
-        }
-    }
-}
 
 }  // namespace hb
