@@ -468,21 +468,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
     bool stored = false;
     if constexpr (G == 1 && F == 4 && Cfg::POOL_T == 1 && Cfg::POOL_F == 1) {
         if (a.pool2_out != nullptr) {
-            // item (chunk, phase, pooled row, pooled bin), chunk slowest: rows 2 rp + phase, + 1 and bins 2 fo, 2 fo + 1 of layout P
+            // item (chunk, pooled row, phase, pooled bin), bin fastest: rows 2 rp + phase, + 1 and bins 2 fo, 2 fo + 1 of layout P.
+            // The four (phase, bin) items of a pooled row start in the 16-byte bank groups 0, 2, 4, 6 of layout P's 128-byte window, so the
+            // lanes of odd pooled rows read their two bins in the other order (max is commutative): eight lanes, eight bank groups.
             const int R = a.T_out / 2;
             uint4* o = reinterpret_cast<uint4*>(a.pool2_out) + (int64_t)clip * 2 * R * 2 * CC;
             for (int i = tid; i < CC * 2 * R * 2; i += kGThreads) {
-                const int fo = i & 1;
-                int r = i >> 1;
-                const int rp = r % R;
-                r /= R;
-                const int ph = r & 1, ch = r >> 1;
+                const int fo = i & 1, ph = (i >> 1) & 1;
+                const int r = i >> 2;
+                const int rp = r % R, ch = r / R;
                 const int rr = 2 * rp + ph;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (rr + 1 < a.T_out) {
                     const unsigned char* base = act + ch * Cfg::PLAIN + (rr * F + 2 * fo) * 16;
-                    const uint4 x0 = *reinterpret_cast<const uint4*>(base), x1 = *reinterpret_cast<const uint4*>(base + 16);
-                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + 16);
+                    const int sw = (rp & 1) * 16;
+                    const uint4 x0 = *reinterpret_cast<const uint4*>(base + sw), x1 = *reinterpret_cast<const uint4*>(base + 16 - sw);
+                    const uint4 x2 = *reinterpret_cast<const uint4*>(base + F * 16 + sw), x3 = *reinterpret_cast<const uint4*>(base + F * 16 + 16 - sw);
                     const __half2 *h0 = reinterpret_cast<const __half2*>(&x0), *h1 = reinterpret_cast<const __half2*>(&x1);
                     const __half2 *h2 = reinterpret_cast<const __half2*>(&x2), *h3 = reinterpret_cast<const __half2*>(&x3);
                     __half2 mx[4];

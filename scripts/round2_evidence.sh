@@ -1,10 +1,7 @@
 set -x
-# round-2 evidence run (1 GPU): bench lines, launch list, full ncu capture of one steady step, smem-pipe counters of the embed kernels
-python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"colored_bases|augment_fast|tcg_block|tail_layer|gather_slots" --launch-skip 33 -c 11 -o gpurun_out/r2_step python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
 tail -3 gpurun_out/ncu2.log | cut -c1-200
 ncu -i gpurun_out/r2_step.ncu-rep --page raw --csv > gpurun_out/r2_raw.csv 2>/dev/null
 bash scripts/smem_counters.sh 8192 > gpurun_out/r2_smem_counters.txt 2>&1
-cut -c1-400 gpurun_out/r2_bench_n1.json
+tail -9 gpurun_out/r2_smem_counters.txt | cut -c1-300

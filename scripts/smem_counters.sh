@@ -1,7 +1,7 @@
 #!/bin/bash
 # shared-memory pipe counters of the grouped embed kernels (LSU wavefronts / bank conflicts by op, tensor-core operand wavefronts)
 M=l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum
-ncu --metrics $M --clock-control none -k regex:"tcg_block|tc_block" -c 6 --csv --log-file gpurun_out/smem.csv python scripts/embed_time.py ${1:-8192} > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:"tcg_block|tail_layer" -c 8 --csv --log-file gpurun_out/smem.csv python scripts/embed_time.py ${1:-8192} > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/smem.csv')) if len(r)>8]
