@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr.tmem_base;
-    TC_STAMP(1);
 
     if (warp == 1 && lane == 0) {
         mbar_expect_tx(&hdr.wbar, (uint32_t)Cfg::w_bytes(0));
@@ -252,6 +251,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
     uint32_t ph = 0;   // layers processed so far by this CTA = phase index of tmem_full / wbar (tmem_empty lags by one)
     for (int tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
     const bool first_tile = (tile_id == (int)blockIdx.x);
+    // profiling stamps describe the CTA's SECOND tile (steady state: warm caches, the co-resident CTA out of phase); stamp 1 = its start
+    const bool stamp_tile = (tile_id == (int)blockIdx.x + (int)gridDim.x);
+    if (stamp_tile) TC_STAMP(1);
     const int clip = tile_id / a.tiles_per_clip, tile = tile_id - clip * a.tiles_per_clip;
     const int row0 = tile * Cfg::ROWS_OUT;
 
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
     }
     fence_proxy_async();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
     __syncthreads();
-    if (first_tile) TC_STAMP(2);
+    if (stamp_tile) TC_STAMP(2);
 
     // f32 NHWC dump of the tile's rows from layout T / F (parity hook only)
     auto dump_act = [&](bool layout_f, int cc_planes) {
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         constexpr int kDummy = 0; (void)kDummy;
         const bool freq = Cfg::is_freq(l);
         const bool last = (l == NL - 1);
-#define TCG_FINE(i) do { if (l == 1 && first_tile && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
+#define TCG_FINE(i) do { if (l == 1 && stamp_tile && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
         if (warp == 0) {
             TCG_FINE(9);
             mbar_wait(&hdr.wbar, ph & 1u);
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
             __syncthreads();
             tc_fence_after();
         }
-        if (first_tile) TC_STAMP(3 + l);
+        if (stamp_tile) TC_STAMP(3 + l);
         if (a.dbg != nullptr && a.dbg_layer == l && !last) dump_act(!freq, CC);
     }
 
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
         }
     }
     __syncthreads();   // the store has read the buffer: the next tile may stage into it
-    if (first_tile) TC_STAMP(7);
+    if (stamp_tile) TC_STAMP(7);
     }                  // tile loop
     if (warp == 0) tmem_dealloc(tmem_base, kGTmemCols);
     TC_STAMP(8);
