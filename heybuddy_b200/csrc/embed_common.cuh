@@ -74,7 +74,9 @@ int tail_prepare(hb_embed_model* m, const float* weights_host);
 void tail_release(hb_embed_model* m);
 int64_t tail_scratch_bytes(int B, int T15);
 int tail_run(const hb_embed_model* m, const __half* block4_out, bool pooled, int B, int T15, float* out0, float* out1, void* scratch,
-             int64_t scratch_bytes, int upto, float* dbg_out, cudaStream_t st);
+             int64_t scratch_bytes, int upto, float* dbg_out, cudaStream_t st, const int32_t* slot_map_dev = nullptr,
+             float* out_slots = nullptr, int n_slots = 0);
+int tail_max_dup();
 int tail_check_timeout();
 int tail_debug_times(long long* out_host);
 int tcg_debug_times(long long* out_host);

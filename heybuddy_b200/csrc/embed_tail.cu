@@ -24,6 +24,7 @@ namespace hb {
 namespace {
 
 constexpr int kTailC = 96, kTailChunks = 12, kTailCols = 128, kTailThreads = 256;
+constexpr int kTailMaxDup = 4;                  // slots one (phase, row) may feed when conv2d_19 writes the slots itself
 // bytes per operand plane: 128 columns + 2 taps of overhang + pad.  137 records: consecutive planes start 16 B apart modulo 128 B, so
 // the staging stores of a quarter-warp (one column, eight chunks = eight planes) fall into eight different bank groups
 constexpr int kTailPitch = 137 * 16;
@@ -40,6 +41,11 @@ struct TailArgs {
     float* out1;
     const unsigned char* w;
     const float* bias;
+    // LAST, optional: write the caller's slots directly -- slot_map i32 [2 R][kTailMaxDup] lists the slots fed by (phase, row), -1 = none;
+    // out_slots f32 [B][n_slots][96]
+    const int32_t* slot_map;
+    float* out_slots;
+    int n_slots;
     int B, T15, R, T_out, n_cols, n_tiles;
 };
 
@@ -121,6 +127,8 @@ __global__ void __launch_bounds__(kTailThreads, 2) tail_layer_kernel(const TailA
                 if (POOL_IN) {
                     const int rr = 2 * row + ph;
                     if (rr + 1 < a.T15) off = ((int64_t)clip * kTailChunks * a.T15 + rr) * 4;        // uint4 index of (clip, chunk 0, row rr, bin 0)
+                } else if (a.slot_map != nullptr) {
+                    off = ((int64_t)clip << 32) | (uint32_t)(ph * a.R + row);                         // clip, slot-map row
                 } else if (row < a.T_out) {
                     off = (((int64_t)clip * a.T_out + row) * kTailC) * 2 + ph;                         // float offset * 2 + phase
                 }
@@ -227,7 +235,17 @@ __global__ void __launch_bounds__(kTailThreads, 2) tail_layer_kernel(const TailA
                     const uint4 val = *reinterpret_cast<const uint4*>(act + row * OPITCH + piece * 16);
                     if (LAST) {
                         const int64_t off = row_off[row];
-                        if (off >= 0) *reinterpret_cast<uint4*>(((off & 1) ? a.out1 : a.out0) + (off >> 1) + 32 * q + 4 * piece) = val;
+                        if (off >= 0 && a.slot_map != nullptr) {
+                            const int32_t* slots = a.slot_map + (int64_t)(uint32_t)off * kTailMaxDup;
+                            float* dst = a.out_slots + (off >> 32) * a.n_slots * kTailC + 32 * q + 4 * piece;
+#pragma unroll
+                            for (int d = 0; d < kTailMaxDup; ++d) {
+                                const int sl = __ldg(slots + d);
+                                if (sl >= 0) *reinterpret_cast<uint4*>(dst + (int64_t)sl * kTailC) = val;
+                            }
+                        } else if (off >= 0) {
+                            *reinterpret_cast<uint4*>(((off & 1) ? a.out1 : a.out0) + (off >> 1) + 32 * q + 4 * piece) = val;
+                        }
                     } else {
                         reinterpret_cast<uint4*>(a.out)[(int64_t)col * kTailChunks + 4 * q + piece] = val;
                     }
@@ -329,8 +347,9 @@ int64_t tail_scratch_bytes(int B, int T15) {
 // pooled operand format fp16 [(clip, phase, row)][24][8] (tcg_block4's pool2_out, one tile per clip); else fp16 [B][12][T15][4][8] and
 // conv2d_16's staging pools (long strips, parity hook).
 // upto: 16 .. 19 = stop after that conv (parity hook; dbg_out then receives the phase-0 activation f32 [B][T][96]).
+// slot_map_dev / out_slots / n_slots (optional, upto = 19): conv2d_19 writes out_slots f32 [B][n_slots][96] itself (out0 / out1 unused).
 int tail_run(const hb_embed_model* m, const __half* block4_out, bool pooled, int B, int T15, float* out0, float* out1, void* scratch,
-             int64_t scratch_bytes, int upto, float* dbg_out, cudaStream_t st) {
+             int64_t scratch_bytes, int upto, float* dbg_out, cudaStream_t st, const int32_t* slot_map_dev, float* out_slots, int n_slots) {
     const TailWeights* tw = reinterpret_cast<const TailWeights*>(m->tail);
     HB_REQUIRE(tw != nullptr, "tail weights missing");
     const int R = T15 / 2;
@@ -343,6 +362,9 @@ int tail_run(const hb_embed_model* m, const __half* block4_out, bool pooled, int
     a.n_cols = (int)n_cols64;
     a.n_tiles = ceil_div(a.n_cols, kTailCols);
     a.out0 = out0; a.out1 = out1;
+    a.slot_map = upto == 19 ? slot_map_dev : nullptr;
+    a.out_slots = out_slots;
+    a.n_slots = n_slots;
     __half* x = reinterpret_cast<__half*>(scratch);
     __half* y = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(scratch) + tail_scratch_bytes(B, T15) / 2);
     auto dump = [&](const __half* act, int T) {
@@ -369,6 +391,8 @@ int tail_run(const hb_embed_model* m, const __half* block4_out, bool pooled, int
 int tail_debug_times(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, g_tc_times, sizeof(long long) * 8 * 16) == cudaSuccess ? 0 : -2;
 }
+
+int tail_max_dup() { return kTailMaxDup; }
 
 int tail_check_timeout() {
     unsigned int flag = 0;

@@ -120,13 +120,24 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     std::vector<int> slot_m(n_slots);
     HB_REQUIRE(n_slots <= 1024, "hb_embed_clips: too many slots (%d)", n_slots);
     const int J[2] = {T15 / 2 - 4, (T15 - 1) / 2 - 4};     // outputs of pool phase 0 / 1
+    const int R = T15 / 2, dup = tail_max_dup();
+    // slot map for conv2d_19's epilogue: the slots fed by (phase, row); it replaces the gather pass unless a row feeds more than `dup`
+    // slots or the table does not fit the workspace's 8 KB (long strips)
+    std::vector<int32_t> slot_map((size_t)2 * std::max(R, 1) * dup, -1);
+    bool direct = (int64_t)slot_map.size() * 4 + (int64_t)n_slots * 4 <= 8192;
     for (int s = 0; s < n_slots; ++s) {
         slot_m[s] = slot_offsets_host[s] / 4;
         const int p = slot_m[s] & 1, j = slot_m[s] >> 1;
         HB_REQUIRE(j < J[p], "hb_embed_clips: slot %d (offset %d) beyond the strip (phase %d has %d outputs)", s,
                    slot_offsets_host[s], p, J[p]);
+        int32_t* e = slot_map.data() + ((size_t)p * R + j) * dup;
+        int d = 0;
+        while (d < dup && e[d] >= 0) ++d;
+        if (d < dup) e[d] = s; else direct = false;
     }
+    int32_t* slot_map_dev = reinterpret_cast<int32_t*>(slot_m_dev + n_slots);
     HB_CUDA_OK(cudaMemcpyAsync(slot_m_dev, slot_m.data(), n_slots * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (direct) HB_CUDA_OK(cudaMemcpyAsync(slot_map_dev, slot_map.data(), slot_map.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
 
     int rc;
     if ((rc = run_block(m, 0, mel, hA, B, F, nullptr, -1, st))) return rc;
@@ -137,6 +148,7 @@ int tc_embed_clips(const hb_embed_model* m, const float* mel, int B, int F, cons
     if ((rc = run_block(m, 3, hA, hB, B, c.T_in[3], nullptr, -1, st, pooled ? hB : nullptr))) return rc;
     // the tail (pool phases 0 and 1, conv2d_16 .. 19): one launch per layer over all columns; hA is free once block 4 has read it
     HB_REQUIRE(c.act_bytes >= tail_scratch_bytes(B, T15), "hb_embed: activation buffer smaller than the tail's scratch");
+    if (direct) return tail_run(m, hB, pooled, B, T15, tmp[0], tmp[1], hA, c.act_bytes, 19, nullptr, st, slot_map_dev, out, n_slots);
     if ((rc = tail_run(m, hB, pooled, B, T15, tmp[0], tmp[1], hA, c.act_bytes, 19, nullptr, st))) return rc;
     return fp32_gather_slots(tmp[0], tmp[1], T15 / 2 - 4, T15 / 2 - 4, slot_m_dev, n_slots, out, B, st);
 }
