@@ -654,7 +654,7 @@ def main():
                 "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved_tflops / tensor_peak) if achieved_tflops else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the stage's launches, one ncu --set full capture of a steady
                 # 8192-clip step (profiles/: 1.49 GB read + 1.18 GB written), scaled to this run's chunk size
-                "traffic": 2.67e9 * CHUNK / 8192, "traffic_unit": "bytes per step (embed stage, ncu)", "peak_source": f"{peaks_src} (bf16 sustained; f16 runs at the bf16 rate)",
+                "traffic": 2.41e9 * CHUNK / 8192, "traffic_unit": "bytes per step (embed stage, ncu)", "peak_source": f"{peaks_src} (bf16 sustained; f16 runs at the bf16 rate)",
                 "algorithmic_flops_per_clip": flops_per_clip,
                 "note": "fully-convolutional evaluation: one 141-frame strip per clip instead of 16 windows (14 unique)",
             },
