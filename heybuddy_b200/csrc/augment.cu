@@ -406,6 +406,10 @@ augment_kernel(const float* __restrict__ clips, const float* __restrict__ noise_
 // Shared-memory index i lives at i + i / 16 (float2 units): a 64-bit access is served one half-warp at a time, and with this
 // skew the 16 lanes of a half-warp hit 16 different bank pairs in the stride-16 stores of the first pass and the stride-16
 // loads of the last (i + i / 32 left them two-way conflicted: 1440 instead of 720 wavefronts per pass).
+// profiling aid: cycle stamps of the fused kernel's phases for the CTAs that run on the same SMs as CTAs 0..7 one wave later
+static __device__ long long g_aug_times[8][8];
+#define AUG_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x >= 1184 && blockIdx.x < 1192) g_aug_times[blockIdx.x - 1184][i] = clock64(); } while (0)
+
 constexpr int kFastT = 23040;
 constexpr int kFastM = kFastT / 2;
 constexpr int kFastThreads = 768;
@@ -646,6 +650,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         for (int i = threadIdx.x; i < 256; i += kFastThreads) mel_w256[i] = mel_tables->w256[i];
     }
     constexpr int T = kFastT, M = kFastM, NT = kFastThreads, NW = kFastThreads / 32;
+    AUG_STAMP(0);
     float2* buf0 = reinterpret_cast<float2*>(smem_raw);   // skewed: point n at sk(n)
     float2* buf1 = buf0 + kFastBuf;
     const int tid = threadIdx.x;
@@ -746,6 +751,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         if (noff >= 0 && noise_bank != nullptr) prefetch_range_l2(noise_bank + noff, (int64_t)T * 4);
     }
 #endif
+    AUG_STAMP(1);
     // every thread only ever touches its own points n = tid + i NT until the FFT: no barriers needed in between
     // ---- K1 coloured noise + K2 gain + K3 background noise: at most two passes over the clip --------------------
     // A gain that is not followed by coloured noise is not applied on its own: the energy K3 needs is gain^2 * sum(x^2) and
@@ -797,6 +803,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         have_abs = true;
     }
 
+    AUG_STAMP(2);
     float2* fin = buf1;          // kMel: the finished clip, natural order (buf1 is free once the noise row has been mixed in)
     if (!has_rir) {
         if (kMel) {
@@ -814,6 +821,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         }
     }
     const float amp_x = block_sum_n(a, scratch, NW) / (float)T;   // its barriers also publish buf0 and tw
+    AUG_STAMP(3);
 
     const float2* H = rir_specs + (int64_t)p.rir_index * (M + 1);
     const int lo_n = plan.tw_lo;
@@ -824,6 +832,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
     fast_pass_bwd<9, 256>(buf1, buf0, tw, lo_n);
     fast_pass_bwd<16, 16>(buf0, buf1, tw, lo_n);
     fast_pass_bwd<16, 1>(buf1, buf0, tw, lo_n);      // buf0 = conj(M * (y_even + i y_odd)), natural order
+    AUG_STAMP(4);
 
     const float inv_m = 1.0f / (float)M;
     float ay = 0.f;
@@ -843,6 +852,7 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
 
     // ---- K6 in place: the clip's 141 log-mel frames from shared memory -------------------------------------------
     __syncthreads();                                   // fin complete, buf0 free, mel tables loaded
+    AUG_STAMP(5);
     const int warp = tid >> 5, lane = tid & 31;
     float2* tr_pair = warp < kFusedWarpsInBuf ? buf0 + warp * kFusedTr : mel_extra + (warp - kFusedWarpsInBuf) * kFusedTr;
     const int l = lane & 15;
@@ -855,6 +865,8 @@ augment_fast_kernel(const float* __restrict__ clips, const int16_t* __restrict__
         mel_frame_pair(mel_s, tr_pair, reinterpret_cast<float*>(tr_pair), [&](int k1) { return mel_w256[(l * k1) & 255]; }, my_lo, my_rot, load,
                        mel_scale, f0, kFusedFrames, mel_clip);
     }
+    __syncthreads();
+    AUG_STAMP(6);
 }
 
 // ---- K9: BandStopFilter ---------------------------------------------------------------------------------------------------------
@@ -1160,6 +1172,10 @@ extern "C" int hb_k9_bandstop_f32(float* clips_dev, const int32_t* clip_index_de
             clips_dev, clip_index_dev, meta_dev, reinterpret_cast<const float2*>(spec_dev), scratch_dev, T, plan);
     HB_LAUNCHED();
     return HB_OK;
+}
+
+extern "C" int hb_debug_aug_times(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, g_aug_times, sizeof(long long) * 8 * 8) == cudaSuccess ? 0 : -2;
 }
 
 extern "C" int hb_fix_length_i16(const int16_t* samples_dev, const int64_t* offsets_dev, const int32_t* pad_before_dev,
