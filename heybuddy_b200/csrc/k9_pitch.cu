@@ -96,17 +96,27 @@ ps_stft_polar_kernel(const float* __restrict__ clips, const int32_t* __restrict_
     const float* x = clips + (int64_t)clip_index[blockIdx.y] * T;
     float2* a = buf[warp][0];
     float2* b = buf[warp][1];
+    bool any = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = lane + 32 * i;
         if (m < kPsM) {
             const int j0 = kPsHop * t + 2 * m - kPsM;          // centre = True: the frame starts n_fft / 2 before sample hop * t
-            a[m] = make_float2(__ldg(x + reflect_index(j0, T)), __ldg(x + reflect_index(j0 + 1, T)));
+            const float2 v = make_float2(__ldg(x + reflect_index(j0, T)), __ldg(x + reflect_index(j0 + 1, T)));
+            a[m] = v;
+            any |= v.x != 0.f || v.y != 0.f;
         }
+    }
+    float2* out = S + ((int64_t)blockIdx.y * F + t) * kPsBins;
+    if (!__any_sync(0xffffffffu, any)) {
+        // a frame of exact zeros (the zero padding of a length-fixed clip): its spectrum is exactly zero, |S| = 0 and angle = atan2(0, 0) = 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (lane + 32 * i < kPsBins) out[lane + 32 * i] = make_float2(0.f, 0.f);
+        return;
     }
     __syncwarp();
     const float2* Z = fft125(a, b, w125, lane);
-    float2* out = S + ((int64_t)blockIdx.y * F + t) * kPsBins;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int k = lane + 32 * i;
@@ -189,6 +199,7 @@ ps_istft_resample_kernel(const float2* __restrict__ Y, float* __restrict__ clips
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float2 buf[kPsIstftWarps][2][128];
     __shared__ float2 w125[kPsM], w250[kPsBins];
+    __shared__ bool frame_live[kPsIstftWarps];
     float* ola = reinterpret_cast<float*>(smem_raw);                 // padded coordinates [s_lo, s_hi)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // this CTA's outputs [o_lo, o_hi) read y[(o / up) orig - width + j], j < taps
@@ -211,7 +222,21 @@ ps_istft_resample_kernel(const float2* __restrict__ Y, float* __restrict__ clips
         const int j = j0 + warp;
         float2* a = buf[warp][0];
         float2* b = buf[warp][1];
+        bool live = false;
         if (j <= j_last) {
+            // a frame whose 126 bins are all exactly zero (both source frames were zero padding) adds nothing: skip its transform
+            const float2* Yz = y + (int64_t)j * kPsBins;
+            bool nz = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (lane + 32 * i < kPsBins) {
+                    const float2 v = __ldg(Yz + lane + 32 * i);
+                    nz |= v.x != 0.f || v.y != 0.f;
+                }
+            live = __any_sync(0xffffffffu, nz);
+        }
+        if (lane == 0) frame_live[warp] = live;
+        if (live) {
             // irfft: Z[k] = E[k] + i O[k], E = (X[k] + conj X[M-k]) / 2, O = conj(W^k) (X[k] - conj X[M-k]) / 2; the imaginary parts
             // of the DC and Nyquist bins are ignored (C2R); z = conj(FFT(conj Z)) / M, frame[2 m] = Re z[m], frame[2 m + 1] = Im z[m]
             const float2* Yj = y + (int64_t)j * kPsBins;
@@ -248,7 +273,7 @@ ps_istft_resample_kernel(const float2* __restrict__ Y, float* __restrict__ clips
             for (int f = 0; f < kPsIstftWarps; ++f) {
                 const int off = tid - kPsHop * f;
                 // three passes leave a warp's result in its second buffer
-                if (off >= 0 && off < kPsNfft && j0 + f <= j_last) sum += reinterpret_cast<const float*>(buf[f][1])[off];
+                if (off >= 0 && off < kPsNfft && frame_live[f]) sum += reinterpret_cast<const float*>(buf[f][1])[off];
             }
             ola[sidx - s_lo] = sum;
         }

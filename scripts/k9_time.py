@@ -7,6 +7,10 @@ from heybuddy_b200.dataset import k9
 from heybuddy_b200.dataset.draws import AugmentConfig, DrawTable
 n, T = 8192, 23040
 x = (torch.randn((n, T), device="cuda") * 0.1)
+if len(sys.argv) > 1:      # zero padding like length-fixed clips: the first and the last `pad` samples of every clip
+    pad = int(sys.argv[1])
+    x[:, :pad] = 0
+    x[:, T - pad:] = 0
 bufs = {}
 def scratch(name, numel, dtype):
     if name not in bufs or bufs[name].numel() < numel or bufs[name].dtype != dtype:
