@@ -121,6 +121,16 @@ def test_clip_slots_match_windows(model, weights):
     np.testing.assert_allclose(got, own, rtol=0, atol=1e-5 * np.abs(want).max() if model.precision == "fp32" else 2e-3 * np.abs(want).max())
 
 
+def test_repeated_slots_take_the_gather_path(model):
+    """A row that feeds more slots than conv2d_19's slot map holds (4) falls back to the separate gather pass: same rows either way."""
+    m = torch.from_numpy(_mel(7, 4, 141)).cuda()
+    base = model.run_clips_device(m, [0, 8, 12, 60]).cpu().numpy()
+    many = model.run_clips_device(m, [8, 0, 8, 8, 8, 8, 12, 8, 60]).cpu().numpy()      # offset 8 six times
+    assert many.shape == (4, 9, 96)
+    for j, src in enumerate([1, 0, 1, 1, 1, 1, 2, 1, 3]):
+        np.testing.assert_array_equal(many[:, j], base[:, src])
+
+
 def test_bad_slot_offsets_raise(model):
     from heybuddy_b200 import _native
 
