@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
 #define TCG_FINE(i) do { if (l == 1 && stamp_tile && lane == 0 && blockIdx.x < 8) g_tc_times[blockIdx.x][i] = clock64(); } while (0)
         if (warp == 0) {
             TCG_FINE(9);
-            mbar_wait(&hdr.wbar, ph & 1u);
+            mbar_wait(&hdr.wbar, ph & 1u, 1u);
             TCG_FINE(10);
-            if (ph > 0) mbar_wait(&hdr.tmem_empty, (ph - 1) & 1u);
+            if (ph > 0) mbar_wait(&hdr.tmem_empty, (ph - 1) & 1u, 2u);
             tc_fence_after();
             // One elected lane issues the whole layer; l and j are compile-time, so every descriptor is an immediate
             // (an issue loop that computes offsets at run time is slower than the MMAs it feeds).
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::THREADS > 320 ? HB_TCG_WIDE
             __syncwarp();
         } else if (warp == 1) {
             // all MMAs of the layer have completed: the weight buffer and the activation buffer are free
-            mbar_wait(&hdr.tmem_full, ph & 1u);
+            mbar_wait(&hdr.tmem_full, ph & 1u, 3u);
 #ifndef HB_TCG_POLL_ALL
             // this warp is the only one that polls the mbarrier: the eight epilogue warps wait at a hardware barrier it releases
             named_bar_sync(1, 32 * (kGEpiWarps + 1));
@@ -807,7 +807,7 @@ int tcg_debug_times(long long* out_host) {
 int tcg_check_timeout() {
     unsigned int flag = 0;
     HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
-    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (blocks 1-3): an mbarrier wait timed out (pipeline bug)");
+    HB_REQUIRE(flag == 0, "tcgen05 embed kernel (blocks 1-4): an mbarrier wait timed out (pipeline bug; barrier code %u: 2 = weights, 3 = accumulator free, 4 = accumulator ready)", flag);
     return HB_OK;
 }
 

@@ -36,12 +36,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // every failed try_wait has slept in hardware (suspend-time hint): a plain retry counter bounds the wait (seconds) with two
-    // instructions per retry -- the waiting warps share issue slots with the co-resident CTA's epilogue
-    for (uint32_t tries = 0; !mbar_try_wait(bar, parity); ++tries) {
-        if (tries > (1u << 24)) {   // give up instead of hanging the box
-            atomicExch(&g_tc_timeout, 1u);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t id = 0) {
+    // every failed try_wait has slept in hardware (suspend-time hint).  A wait that has not completed after ~2 s of SM clock is a
+    // pipeline bug: give up instead of hanging the box, and say which barrier it was (g_tc_timeout = 1 + id; the host checks it).
+    // Keep the number of polling warps small: all ten warps of a block CTA waiting on ONE barrier this way never woke up (round-2
+    // experiment); one warp polls and the others meet it at a hardware barrier.
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(&g_tc_timeout, 1u + id);
             return;
         }
     }
