@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, co
     const bool vec = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const bool loader = live && sec == 0, storer = live && sec == kEqLanes - 1;
     float ic1 = 0.f, ic2 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;        // state; this lane's last three outputs
+    float up = 0.f;                                                   // lane s - 1's output of three ticks ago (fetched one tick ahead)
     const int groups = (T + 3) / 4, total = groups + kEqLagGroups;
     auto load_group = [&](int g) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(32) k9_eq_kernel(float* __restrict__ clips, co
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float up = __shfl_up_sync(0xffffffffu, d3, 1, kEqLanes);
                 const float v0 = sec == 0 ? xin[j] : up;
+                up = __shfl_up_sync(0xffffffffu, d2, 1, kEqLanes);     // the neighbour's d3 of the NEXT tick: the shuffle's latency is off the chain
                 o[j] = d3;                                // lane 7: sample tau - 24 = 4 (g - 6) + j
                 const float v3 = v0 - ic2;
                 const float v1 = fmaf(a2, v3, a1 * ic1);
