@@ -73,6 +73,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_embed_clips": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_vp]),
         "hb_embed_activation": (c_i64, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
         "hb_rir_spectrum": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+        "hb_check_kernels": (c_int, []),
+        "hb_linear_tf32x3": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
         "hb_colored_bases": (c_int, [ctypes.c_uint64, c_vp, c_vp, c_int, c_vp, c_vp]),
         "hb_augment_clips_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
         "hb_k9_eq_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),

@@ -456,8 +456,24 @@ static void sgemm_launch(const SgemmArgs& a, bool a_k, bool b_k, dim3 grid, cuda
 
 // part / part_floats: split-K scratch (nullptr: never split).  Large outputs get 128 x 128 tiles, small ones 64 x 64; products
 // whose tiles do not fill the GPU and whose K is long (the weight gradients: K = batch; the first layer: K = 1536) are split over K.
+// HB_MLP_FMA=1: keep every product on the fp32 FMA kernels (parity mode / A-B comparisons)
+static bool tensor_path_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HB_MLP_FMA");
+        on = (e && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 static int sgemm(SgemmArgs a, bool a_k, bool b_k, cudaStream_t st, float* part, int64_t part_floats) {
     if (a.M <= 0 || a.N <= 0) return HB_OK;
+    // The first-layer x W^T products (K = 1536; both operands K-major) go to the tensor cores, three TF32 passes = fp32-level accuracy
+    // (gemm_tf32.cu) -- whatever the batch size, so that a row's result does not depend on how many rows travel with it (the streaming
+    // service and the offline strip evaluation agree).  The 96- and 64-wide products stay here: at K < 512 the FMA kernel is faster.
+    if (a_k && b_k && a.C1 == nullptr && a.K >= 512 && tensor_path_enabled() &&
+        gemm_tf32x3_ok(a.A, a.lda, a.B0, a.B1, a.ldb, a.C0, a.ldc, a.M, a.N, a.K))
+        return gemm_tf32x3_tn(a.A, a.lda, a.B0, a.B1, a.bsplit, a.ldb, a.bias0, a.bias1, a.biassplit, a.C0, a.ldc, a.M, a.N, a.K, st);
     if (a.C1 == nullptr) { a.C1 = a.C0; a.csplit = a.M; }
     if (a.B1 == nullptr) { a.B1 = a.B0; a.bsplit = 1 << 30; }
     if (a.bias1 == nullptr) { a.bias1 = a.bias0; a.biassplit = 1 << 30; }

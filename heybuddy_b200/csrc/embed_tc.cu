@@ -239,6 +239,16 @@ int64_t tc_activation(const hb_embed_model* m, const float* mel, int B, int F, i
 
 }  // namespace hb
 
+// Every tcgen05 kernel bounds its mbarrier waits (~2 s of SM clock) and raises a flag instead of hanging the GPU; this returns an error
+// naming the kernel family if any flag is up.  Synchronises the device.
+extern "C" int hb_check_kernels(void) {
+    HB_CUDA_OK(cudaDeviceSynchronize());
+    int rc = hb::tcg_check_timeout();
+    if (rc == HB_OK) rc = hb::tail_check_timeout();
+    if (rc == HB_OK) rc = hb::gemm_tf32_check_timeout();
+    return rc;
+}
+
 // profiling aids (not part of the public header): phase timestamps of the first 8 CTAs of the last block / tail launch
 extern "C" int hb_debug_tcg_times(long long* out_host) { return hb::tcg_debug_times(out_host); }
 extern "C" int hb_debug_tail_times(long long* out_host) { return hb::tail_debug_times(out_host); }

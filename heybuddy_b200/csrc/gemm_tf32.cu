@@ -1,0 +1,225 @@
+// Classifier (K8): C[M, N] = A[M, K] B[N, K]^T + bias on the tensor cores with fp32 accuracy -- the first-layer products of the gated
+// MLP (reference wakeword.py:334-348: 1536 -> 64 + 64 per model; 97 % of a forward pass) for one model (hidden | gate stacked) and
+// for M models stacked (hb_mlp_forward_multi).
+//
+// tcgen05.mma.kind::tf32 reads fp32 words from shared memory and uses their upper 19 bits.  Classifier logits have to stay within 1e-3
+// of the reference; one TF32 pass rounds each operand to 2^-11, which puts a K = 1536 dot product at a few 1e-4 relative -- on the
+// bound.  Three passes restore fp32: with a = a_hi + a_lo (a_hi = what the hardware sees, a_lo = a - a_hi, exact),
+//     a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo            (the dropped a_lo b_lo term is 2^-22 relative)
+// all three accumulating in the same fp32 TMEM tile.  Measured against float64: see tests/test_classifier_gpu.py.
+//
+// One CTA = one 128 x 128 tile of C.  Per K step of 32: every thread brings its share of the A and B tiles from global memory
+// (registers, loads one step ahead), writes the raw words and the lo words as K-major core-matrix tiles ([k / 4][row][4 floats], chunk
+// pitch 129 rows so that a quarter-warp's eight chunks fall into eight bank groups), thread 0 issues 4 x 3 MMAs (M = 128, N = 128,
+// K = 8) and commits to the stage's mbarrier; three shared-memory stages and loads two steps ahead, so global latency, the split and
+// the MMAs of neighbouring steps overlap.
+// The epilogue goes through shared memory so that C is written in whole 128-byte row segments.
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+
+namespace hb {
+
+namespace {
+
+constexpr int kTfBM = 128, kTfBN = 128, kTfBK = 32, kTfThreads = 256;
+constexpr int kTfChunks = kTfBK / 4;                    // 16-byte K chunks per step
+constexpr int kTfPitch = 129 * 16;                      // bytes between K chunks of a tile (128 rows + one row of skew)
+constexpr int kTfTile = kTfChunks * kTfPitch;           // one operand tile: 16.5 KB
+constexpr int kTfStage = 4 * kTfTile;                   // A, A_lo, B, B_lo
+
+struct TfArgs {
+    const float* A; int lda;
+    const float* B0; const float* B1; int bsplit; int ldb;      // B row n: n < bsplit ? B0 + n ldb : B1 + (n - bsplit) ldb
+    const float* bias0; const float* bias1; int biassplit;      // bias0 == nullptr: none
+    float* C; int ldc;
+    int M, N, K;
+};
+
+constexpr int kTfStages = 3;
+
+struct TfHeader {
+    uint64_t done[kTfStages];
+    uint32_t tmem;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor: c_format F32 (bit 4), a / b format TF32 (2 at [7,10) and [10,13)), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    TfHeader& hdr = *reinterpret_cast<TfHeader*>(smem);
+    unsigned char* stage0 = smem + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kTfBM, n0 = blockIdx.x * kTfBN;
+    if (tid == 0) {
+        for (int i = 0; i < kTfStages; ++i) mbar_init(&hdr.done[i], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&hdr.tmem, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = hdr.tmem;
+    constexpr uint32_t idesc = make_idesc_tf32(kTfBM, kTfBN);
+
+    // thread -> 4 (row, chunk) slots of each operand tile: slot = tid + 256 i, chunk = slot % 8 (a row's 128 bytes are 8 lanes), row = slot / 8
+    constexpr int kSlots = kTfBM * kTfChunks / kTfThreads;      // 4
+    float4 ra[2][kSlots], rb[2][kSlots];                        // two register sets: the loads run TWO steps ahead of their use
+    auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int slot = tid + i * kTfThreads, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
+            const int m = m0 + r, n = n0 + r;
+            xa[i] = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* brow = n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb;
+            xb[i] = n < a.N ? __ldg(reinterpret_cast<const float4*>(brow + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); };       // v - (what kind::tf32 reads of v)
+    auto store = [&](unsigned char* st, const float4 (&xa)[kSlots], const float4 (&xb)[kSlots]) {
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) {
+            const int slot = tid + i * kTfThreads, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
+            const int off = c * kTfPitch + r * 16;
+            *reinterpret_cast<float4*>(st + off) = xa[i];
+            *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(xa[i].x), lo_of(xa[i].y), lo_of(xa[i].z), lo_of(xa[i].w));
+            *reinterpret_cast<float4*>(st + 2 * kTfTile + off) = xb[i];
+            *reinterpret_cast<float4*>(st + 3 * kTfTile + off) = make_float4(lo_of(xb[i].x), lo_of(xb[i].y), lo_of(xb[i].z), lo_of(xb[i].w));
+        }
+    };
+
+    const int steps = a.K / kTfBK;
+    load(0, ra[0], rb[0]);
+    if (steps > 1) load(kTfBK, ra[1], rb[1]);
+    // step s lives in shared-memory stage s % 3 and register set s % 2.  A stage is free once the MMAs of step s - 3 have completed.
+    auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+        const int sg = s % kTfStages;
+        unsigned char* st = stage0 + sg * kTfStage;
+        if (s >= kTfStages && warp == 0) mbar_wait(&hdr.done[sg], ((s - kTfStages) / kTfStages) & 1u, 8u + sg);     // one warp polls
+        __syncthreads();
+        store(st, xa, xb);
+        if (s + 2 < steps) load((s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t base = smem_u32(st);
+#pragma unroll
+            for (int j = 0; j < kTfBK / 8; ++j) {               // K = 8 per MMA = two chunks
+                const uint64_t a_hi = make_desc(base + 2 * j * kTfPitch, kTfPitch, 128u);
+                const uint64_t a_lo = make_desc(base + kTfTile + 2 * j * kTfPitch, kTfPitch, 128u);
+                const uint64_t b_hi = make_desc(base + 2 * kTfTile + 2 * j * kTfPitch, kTfPitch, 128u);
+                const uint64_t b_lo = make_desc(base + 3 * kTfTile + 2 * j * kTfPitch, kTfPitch, 128u);
+                umma_tf32(tmem, a_lo, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);        // small terms first
+                umma_tf32(tmem, a_hi, b_lo, idesc, 1u);
+                umma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit(&hdr.done[sg]);
+        }
+    };
+    for (int s = 0; s < steps; s += 2) {
+        body(s, ra[0], rb[0]);
+        if (s + 1 < steps) body(s + 1, ra[1], rb[1]);
+    }
+    // commits complete in issue order: the last one implies every MMA has completed
+    if (warp == 0) {
+        const int last = steps - 1;
+        mbar_wait(&hdr.done[last % kTfStages], (last / kTfStages) & 1u, 12u);
+    }
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- epilogue: TMEM lane = row of C, 128 columns; 32 columns at a time through shared memory ----------------------------------
+    constexpr int OPITCH = 32 * 4 + 16;                     // 36 words: a quarter-warp's 16-byte stores are conflict-free
+    float* ost = reinterpret_cast<float*>(stage0);
+    const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(16 * half);
+#pragma unroll 1
+    for (int q = 0; q < kTfBN / 32; ++q) {
+        float v[16];
+        tmem_ld16(taddr + 32 * q, v);
+        if (a.bias0 != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = n0 + 32 * q + 16 * half + e;
+                if (n < a.N) v[e] += n < a.biassplit ? __ldg(a.bias0 + n) : __ldg(a.bias1 + (n - a.biassplit));
+            }
+        }
+        unsigned char* mine = reinterpret_cast<unsigned char*>(ost) + row * OPITCH + half * 64;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) reinterpret_cast<float4*>(mine)[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTfBM * 8 / kTfThreads; ++k) {
+            const int idx = tid + k * kTfThreads, r = idx >> 3, piece = idx & 7;
+            const int m = m0 + r, n = n0 + 32 * q + 4 * piece;
+            if (m < a.M && n < a.N)        // N is a multiple of 4 (checked by the caller)
+                *reinterpret_cast<float4*>(a.C + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace
+
+// Whether gemm_tf32x3_tn can run this product (both operands K-major with 16-byte aligned rows, K a multiple of 32, C rows 16-byte aligned).
+bool gemm_tf32x3_ok(const float* A, int lda, const float* B0, const float* B1, int ldb, const float* C, int ldc, int M, int N, int K) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return M >= 1 && N >= 4 && K >= kTfBK && K % kTfBK == 0 && N % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && al(A) && al(B0) &&
+           (B1 == nullptr || al(B1)) && al(C);
+}
+
+// C[M, N] = A[M, K] B[N, K]^T + bias (fp32 in and out, 3 x TF32 on tcgen05).  B rows / bias entries at or past `bsplit` come from B1 / bias1.
+int gemm_tf32x3_tn(const float* A, int lda, const float* B0, const float* B1, int bsplit, int ldb, const float* bias0, const float* bias1,
+                   int biassplit, float* C, int ldc, int M, int N, int K, cudaStream_t st) {
+    HB_REQUIRE(gemm_tf32x3_ok(A, lda, B0, B1, ldb, C, ldc, M, N, K), "gemm_tf32x3_tn: unsupported shape or alignment");
+    TfArgs a;
+    a.A = A; a.lda = lda;
+    a.B0 = B0; a.B1 = B1 ? B1 : B0; a.bsplit = B1 ? bsplit : (1 << 30); a.ldb = ldb;
+    a.bias0 = bias0; a.bias1 = bias1 ? bias1 : bias0; a.biassplit = bias1 ? biassplit : (1 << 30);
+    a.C = C; a.ldc = ldc;
+    a.M = M; a.N = N; a.K = K;
+    const size_t smem = 128 + kTfStages * (size_t)kTfStage + 128;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    gemm_tf32x3_kernel<<<dim3(ceil_div(N, kTfBN), ceil_div(M, kTfBM)), kTfThreads, smem, st>>>(a);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+int gemm_tf32_check_timeout() {
+    unsigned int flag = 0;
+    HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
+    HB_REQUIRE(flag == 0, "tcgen05 classifier GEMM: an mbarrier wait timed out (pipeline bug; barrier code %u)", flag);
+    return HB_OK;
+}
+
+}  // namespace hb
+
+// y = x W^T + b with fp32 accuracy on the tensor cores (three TF32 passes): x f32 [M][K] (row stride lda), W f32 [N][K] (row stride ldb),
+// bias f32 [N] or NULL, y f32 [M][N] (row stride ldc).  K a multiple of 32; N, lda, ldb, ldc multiples of 4; 16-byte aligned pointers.
+// The product behind torch.nn.Linear in the classifier's gated MLPs (reference wakeword.py:334-348).
+extern "C" int hb_linear_tf32x3(const float* x_dev, int lda, const float* w_dev, int ldb, const float* bias_dev, float* y_dev, int ldc, int M,
+                                int N, int K, void* stream) {
+    HB_REQUIRE(x_dev && w_dev && y_dev && M >= 0, "hb_linear_tf32x3: bad argument");
+    if (M == 0) return HB_OK;
+    return hb::gemm_tf32x3_tn(x_dev, lda, w_dev, nullptr, 0, ldb, bias_dev, nullptr, 0, y_dev, ldc, M, N, K, (cudaStream_t)stream);
+}

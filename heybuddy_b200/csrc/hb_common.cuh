@@ -39,6 +39,13 @@ extern std::atomic<long long> g_launches;  // kernels launched by this library (
         }                                        \
     } while (0)
 
+// gemm_tf32.cu: C[M, N] = A[M, K] B[N, K]^T + bias on tcgen05 with three TF32 passes (fp32 accuracy); B rows / bias entries at or past the
+// split come from the second pointer (nullptr: none)
+bool gemm_tf32x3_ok(const float* A, int lda, const float* B0, const float* B1, int ldb, const float* C, int ldc, int M, int N, int K);
+int gemm_tf32x3_tn(const float* A, int lda, const float* B0, const float* B1, int bsplit, int ldb, const float* bias0, const float* bias1,
+                   int biassplit, float* C, int ldc, int M, int N, int K, cudaStream_t st);
+int gemm_tf32_check_timeout();
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -44,6 +44,9 @@ typedef struct hb_mlp_model hb_mlp_model;     /* device-resident classifier   */
 /* ---- library ---------------------------------------------------------------------- */
 int hb_abi_version(void);
 const char* hb_last_error(void);
+/* The tensor-core kernels bound their barrier waits and flag a timeout instead of hanging; this synchronises the device and reports
+ * any such flag (HB_OK otherwise).  For tests and smoke runs. */
+int hb_check_kernels(void);
 /* Number of kernels this library has launched in this process (all streams); bench.py reports the
  * per-step delta as "gpu_launches". */
 int64_t hb_launch_count(void);
@@ -248,6 +251,12 @@ int hb_mlp_get_grads(const hb_mlp_model* m, float* grads_host, int64_t n_floats)
  * into ONE stacked [M*128, 1536] first-layer GEMM (hidden + gate of every model), then the 96-wide remainder batched over the
  * models.  x_dev [B][1536] -> prob_dev [M][B].  The models' live parameters are read on every call. */
 int64_t hb_mlp_multi_workspace_bytes(int M, int B);
+/* y = x W^T + b on tcgen05 with fp32 accuracy (three TF32 passes, csrc/gemm_tf32.cu): the product behind torch.nn.Linear in the gated
+ * MLPs (wakeword.py:334-348).  x f32 [M][K], w f32 [N][K], bias f32 [N] or NULL, y f32 [M][N]; row strides lda / ldb / ldc in floats.
+ * K a multiple of 32; N and the strides multiples of 4; 16-byte aligned pointers.  hb_mlp_forward / _train_step / _forward_multi use it
+ * for their x W^T products (HB_MLP_FMA=1 keeps them on the fp32 FMA kernels). */
+int hb_linear_tf32x3(const float* x_dev, int lda, const float* w_dev, int ldb, const float* bias_dev, float* y_dev, int ldc, int M, int N,
+                     int K, void* stream);
 int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const float* x_dev, float* prob_dev, int B,
                          void* workspace_dev, int64_t workspace_bytes, void* stream);
 

@@ -126,6 +126,32 @@ def test_config4_batch_and_multi_model(cuda_device):
     np.testing.assert_allclose(models[2](xt).cpu().numpy()[:, 0], got[2], rtol=1e-6)
 
 
+def test_tensor_core_products_keep_fp32_accuracy(cuda_device):
+    """hb_linear_tf32x3 (tcgen05, three TF32 passes) against float64.  One pass would be ~3e-4 of the output scale -- on the classifier's
+    1e-3 logit bound; three passes measure <= 1e-5 at K = 1536 (what is left is the tensor core's truncating fp32 accumulation over
+    576 MMAs, not the operands) and ~1e-6 at short K.  Shapes: the stacked first layer, ragged M / N, short K."""
+    from heybuddy_b200 import _native
+
+    lib = _native.load()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    for m, n, k, bias in ((4096, 128, 1536, True), (1000, 8192, 1536, True), (777, 96, 64, False), (130, 260, 96, True)):
+        x = torch.randn((m, k), generator=g)
+        w = torch.randn((n, k), generator=g) * k ** -0.5
+        b = torch.randn(n, generator=g) if bias else None
+        xd, wd = x.to(dev), w.to(dev)
+        bd = b.to(dev) if bias else None
+        y = torch.empty((m, n), device=dev)
+        _native.check(lib.hb_linear_tf32x3(xd.data_ptr(), k, wd.data_ptr(), k, bd.data_ptr() if bias else None, y.data_ptr(), n, m, n, k,
+                                           _native.stream_ptr(dev)), "hb_linear_tf32x3")
+        _native.check(lib.hb_check_kernels(), "hb_check_kernels")
+        want = x.double() @ w.double().T + (b.double() if bias else 0.0)
+        err = (y.cpu().double() - want).abs().max().item() / want.abs().max().item()
+        ref32 = ((x @ w.T + (b if bias else 0.0)).double() - want).abs().max().item() / want.abs().max().item()
+        print(f"hb_linear_tf32x3 [{m}x{k}] x [{n}x{k}]^T: max error {err:.2e} of the output scale (torch fp32 on the CPU: {ref32:.2e})")
+        assert err < (2e-5 if k > 512 else 3e-6), (m, n, k, err)
+
+
 def test_training_reduces_loss_and_lr_schedule(cuda_device):
     from heybuddy_b200.trainer import WakeWordTrainer, get_learning_rate
 
