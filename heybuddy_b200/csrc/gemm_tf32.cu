@@ -8,11 +8,12 @@
 //     a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo            (the dropped a_lo b_lo term is 2^-22 relative)
 // all three accumulating in the same fp32 TMEM tile.  Measured against float64: see tests/test_classifier_gpu.py.
 //
-// One CTA = one 128 x 128 tile of C.  Per K step of 32: every thread brings its share of the A and B tiles from global memory
-// (registers, loads one step ahead), writes the raw words and the lo words as K-major core-matrix tiles ([k / 4][row][4 floats], chunk
-// pitch 129 rows so that a quarter-warp's eight chunks fall into eight bank groups), thread 0 issues 4 x 3 MMAs (M = 128, N = 128,
-// K = 8) and commits to the stage's mbarrier; three shared-memory stages and loads two steps ahead, so global latency, the split and
-// the MMAs of neighbouring steps overlap.
+// One CTA = one 128 x 128 tile of C, K steps of 32 through three shared-memory stages.  Warps 0-7 produce: each thread brings its
+// share of the A and B tiles from global memory (registers, loads two steps ahead) and writes the raw words and the lo words as
+// K-major core-matrix tiles ([k / 4][row][4 floats], chunk pitch 129 rows so that a quarter-warp's eight chunks fall into eight bank
+// groups), then one of them arrives on the stage's `full` barrier.  Warp 8 consumes: one thread waits for `full`, issues 4 x 3 MMAs
+// (M = 128, N = 128, K = 8) and commits to the stage's `empty` barrier, which the producers wait on before they overwrite the stage.
+// No CTA-wide barrier inside the loop (the first version had two per step and ran at a third of this one's rate).
 // The epilogue goes through shared memory so that C is written in whole 128-byte row segments.
 #include "tc_ptx.cuh"
 
@@ -22,7 +23,7 @@ namespace hb {
 
 namespace {
 
-constexpr int kTfBM = 128, kTfBN = 128, kTfBK = 32, kTfThreads = 256;
+constexpr int kTfBM = 128, kTfBN = 128, kTfBK = 32, kTfProducers = 256, kTfThreads = kTfProducers + 32;
 constexpr int kTfChunks = kTfBK / 4;                    // 16-byte K chunks per step
 constexpr int kTfPitch = 129 * 16;                      // bytes between K chunks of a tile (128 rows + one row of skew)
 constexpr int kTfTile = kTfChunks * kTfPitch;           // one operand tile: 16.5 KB
@@ -39,7 +40,7 @@ struct TfArgs {
 constexpr int kTfStages = 3;
 
 struct TfHeader {
-    uint64_t done[kTfStages];
+    uint64_t full[kTfStages], empty[kTfStages];
     uint32_t tmem;
     uint32_t pad;
 };
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * kTfBM, n0 = blockIdx.x * kTfBN;
     if (tid == 0) {
-        for (int i = 0; i < kTfStages; ++i) mbar_init(&hdr.done[i], 1);
+        for (int i = 0; i < kTfStages; ++i) { mbar_init(&hdr.full[i], 1); mbar_init(&hdr.empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&hdr.tmem, 128);
@@ -75,12 +76,12 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     constexpr uint32_t idesc = make_idesc_tf32(kTfBM, kTfBN);
 
     // thread -> 4 (row, chunk) slots of each operand tile: slot = tid + 256 i, chunk = slot % 8 (a row's 128 bytes are 8 lanes), row = slot / 8
-    constexpr int kSlots = kTfBM * kTfChunks / kTfThreads;      // 4
+    constexpr int kSlots = kTfBM * kTfChunks / kTfProducers;    // 4
     float4 ra[2][kSlots], rb[2][kSlots];                        // two register sets: the loads run TWO steps ahead of their use
     auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-            const int slot = tid + i * kTfThreads, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
+            const int slot = tid + i * kTfProducers, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
             const int m = m0 + r, n = n0 + r;
             xa[i] = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float* brow = n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     auto store = [&](unsigned char* st, const float4 (&xa)[kSlots], const float4 (&xb)[kSlots]) {
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-            const int slot = tid + i * kTfThreads, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
+            const int slot = tid + i * kTfProducers, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
             const int off = c * kTfPitch + r * 16;
             *reinterpret_cast<float4*>(st + off) = xa[i];
             *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(xa[i].x), lo_of(xa[i].y), lo_of(xa[i].z), lo_of(xa[i].w));
@@ -101,21 +102,35 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     };
 
     const int steps = a.K / kTfBK;
-    load(0, ra[0], rb[0]);
-    if (steps > 1) load(kTfBK, ra[1], rb[1]);
-    // step s lives in shared-memory stage s % 3 and register set s % 2.  A stage is free once the MMAs of step s - 3 have completed.
-    auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
-        const int sg = s % kTfStages;
-        unsigned char* st = stage0 + sg * kTfStage;
-        if (s >= kTfStages && warp == 0) mbar_wait(&hdr.done[sg], ((s - kTfStages) / kTfStages) & 1u, 8u + sg);     // one warp polls
-        __syncthreads();
-        store(st, xa, xb);
-        if (s + 2 < steps) load((s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
+    if (warp < kTfProducers / 32) {
+        // ---- producers: step s lives in shared-memory stage s % 3 and register set s % 2 ------------------------------------------
+        load(0, ra[0], rb[0]);
+        if (steps > 1) load(kTfBK, ra[1], rb[1]);
+        auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+            const int sg = s % kTfStages;
+            // the stage is free once the MMAs of step s - 3 have completed: warp 0 polls their commit, the producers meet at a barrier
+            if (s >= kTfStages) {
+                if (warp == 0) mbar_wait(&hdr.empty[sg], ((s - kTfStages) / kTfStages) & 1u, 8u + sg);
+                named_bar_sync(1, kTfProducers);
+            }
+            store(stage0 + sg * kTfStage, xa, xb);
+            if (s + 2 < steps) load((s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
+            fence_proxy_async();                                    // generic-proxy stores -> visible to the tensor core
+            named_bar_sync(1, kTfProducers);
+            if (tid == 0) mbar_arrive(&hdr.full[sg]);
+        };
+        for (int s = 0; s < steps; s += 2) {
+            body(s, ra[0], rb[0]);
+            if (s + 1 < steps) body(s + 1, ra[1], rb[1]);
+        }
+    } else {
+      if (lane == 0) {
+        // ---- consumer: one thread issues every MMA -------------------------------------------------------------------------------
+        for (int s = 0; s < steps; ++s) {
+            const int sg = s % kTfStages;
+            mbar_wait(&hdr.full[sg], (s / kTfStages) & 1u, 4u + sg);
             tc_fence_after();
-            const uint32_t base = smem_u32(st);
+            const uint32_t base = smem_u32(stage0 + sg * kTfStage);
 #pragma unroll
             for (int j = 0; j < kTfBK / 8; ++j) {               // K = 8 per MMA = two chunks
                 const uint64_t a_hi = make_desc(base + 2 * j * kTfPitch, kTfPitch, 128u);
@@ -126,17 +141,13 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
                 umma_tf32(tmem, a_hi, b_lo, idesc, 1u);
                 umma_tf32(tmem, a_hi, b_hi, idesc, 1u);
             }
-            umma_commit(&hdr.done[sg]);
+            umma_commit(&hdr.empty[sg]);
         }
-    };
-    for (int s = 0; s < steps; s += 2) {
-        body(s, ra[0], rb[0]);
-        if (s + 1 < steps) body(s + 1, ra[1], rb[1]);
-    }
-    // commits complete in issue order: the last one implies every MMA has completed
-    if (warp == 0) {
+        // commits complete in issue order: the last one implies every MMA has completed
         const int last = steps - 1;
-        mbar_wait(&hdr.done[last % kTfStages], (last / kTfStages) & 1u, 12u);
+        mbar_wait(&hdr.empty[last % kTfStages], (last / kTfStages) & 1u, 12u);
+      }
+      __syncwarp();
     }
     __syncthreads();
     tc_fence_after();
@@ -144,10 +155,10 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     // ---- epilogue: TMEM lane = row of C, 128 columns; 32 columns at a time through shared memory ----------------------------------
     constexpr int OPITCH = 32 * 4 + 16;                     // 36 words: a quarter-warp's 16-byte stores are conflict-free
     float* ost = reinterpret_cast<float*>(stage0);
-    const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+    const int quad = warp & 3, half = (warp >> 2) & 1, row = quad * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(16 * half);
 #pragma unroll 1
-    for (int q = 0; q < kTfBN / 32; ++q) {
+    for (int q = 0; q < kTfBN / 32 && warp < kTfProducers / 32; ++q) {
         float v[16];
         tmem_ld16(taddr + 32 * q, v);
         if (a.bias0 != nullptr) {
@@ -160,15 +171,15 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
         unsigned char* mine = reinterpret_cast<unsigned char*>(ost) + row * OPITCH + half * 64;
 #pragma unroll
         for (int e = 0; e < 4; ++e) reinterpret_cast<float4*>(mine)[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        __syncthreads();
+        named_bar_sync(1, kTfProducers);
 #pragma unroll
-        for (int k = 0; k < kTfBM * 8 / kTfThreads; ++k) {
-            const int idx = tid + k * kTfThreads, r = idx >> 3, piece = idx & 7;
+        for (int k = 0; k < kTfBM * 8 / kTfProducers; ++k) {
+            const int idx = tid + k * kTfProducers, r = idx >> 3, piece = idx & 7;
             const int m = m0 + r, n = n0 + 32 * q + 4 * piece;
             if (m < a.M && n < a.N)        // N is a multiple of 4 (checked by the caller)
                 *reinterpret_cast<float4*>(a.C + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
         }
-        __syncthreads();
+        named_bar_sync(1, kTfProducers);
     }
     tc_fence_before();
     __syncthreads();
