@@ -52,6 +52,7 @@ POOL = int(os.environ.get("HB_BENCH_POOL", "3"))            # distinct chunks cy
 AUG_BATCH = 128
 NOISE_CLIPS, NOISE_LEN = int(os.environ.get("HB_BENCH_NOISE_CLIPS", "2048")), 160000
 N_RIRS = 271
+E2E_PASSES = int(os.environ.get("HB_BENCH_E2E_PASSES", "3"))    # timed passes of the e2e leg (median reported)
 WRITER_THREADS = int(os.environ.get("HB_BENCH_WRITERS", "4"))   # sink threads of the e2e leg (generate_sharded's default is 4)
 K9_PROB = float(os.environ.get("HB_BENCH_K9", "0"))         # probability of each of the four K9 transforms (value leg + stages only)
 CLIP_SECONDS = 1.44
@@ -536,11 +537,16 @@ def main():
     # warm-up = the same call on max(W, 3) steps' worth of rows, untimed: model load, pinned slots, and -- on a freshly booted
     # box -- the one-off host / IOMMU first-touch costs of the first process that moves this much pinned memory
     run_e2e("warm_", (CHUNK * max(args.warmup, 3) // 2) * world)
-    barrier()
-    t0 = time.perf_counter()
-    h2d, d2h = run_e2e("", per_file)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    # The timed pass is ~0.1-0.3 s of host + device work on a shared 16-vCPU VM: one descheduled host thread shows up as a 2x
+    # outlier.  Three passes (each K steps through the API into NEW files), the median is reported and all three are listed.
+    e2e_passes = []
+    for rep in range(E2E_PASSES):
+        barrier()
+        t0 = time.perf_counter()
+        h2d, d2h = run_e2e("", per_file)
+        barrier()
+        e2e_passes.append(time.perf_counter() - t0)
+    e2e_s = sorted(e2e_passes)[len(e2e_passes) // 2]
     # the same API with the rows left in (pinned) host memory instead of a file: what the host pipeline sustains when the box's
     # page-cache write rate is out of the picture
     mem_rows = min(rows_per_rank, 6 * CHUNK)
@@ -633,7 +639,9 @@ def main():
             "dtype": "f16 operands / f32 accumulate (embed), f32 (augment, mel)" if precision == "f16" else "f32",
             "data": "synthetic", "config": workload_config(precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": e2e_ms / args.steps, "host_busy_frac": max(0.0, 1.0 - host_wait / max(e2e_s, 1e-9)),
+                    "ms_per_step": e2e_ms / args.steps, "passes_ms_per_step": [round(t * 1e3 / args.steps, 3) for t in e2e_passes],
+                    "passes_note": "median of the listed passes (rank 0's clock; value uses the max over ranks of each rank's median)",
+                    "host_busy_frac": max(0.0, 1.0 - host_wait / max(e2e_passes[-1], 1e-9)),
                     "h2d_gbs_per_rank": h2d_gbs, "h2d_bound_gbs": sum(h2d_gbs), "h2d_bound_value": h2d_bound,
                     "sink_gbs_per_rank": sink_gbs, "sink_bound_value": sink_bound,
                     "to_host_memory": {"value": mem_rows * world * CLIP_SECONDS / (mem_ms * 1e-3), "unit": UNIT, "clips_per_rank": mem_rows,
