@@ -12,48 +12,13 @@
 // checkpoints and the in-repo ONNX initializers interchange.  The step is launch-latency / HBM
 // bound (25 MB of input per 4096-row batch, 1 MB of parameters); fp32 FMA keeps logits within 1e-3
 // of the reference.
-#include "hb_common.cuh"
+#include "mlp_common.cuh"
 
 #include <math.h>
 
 namespace hb {
 
-constexpr int kIn = 1536, kDim = 96, kHid = 64, kStages = 4;  // stages: mlp_in, layers.0, layers.1, mlp_out
-constexpr float kLnEps = 1e-5f;
-
-struct StageOff {     // float offsets into the packed parameter vector
-    int ln_w, ln_b, in_dim, out_dim;
-    int hw, hb, ow, ob, gw, gb;
-};
-
-struct MlpLayout {
-    StageOff s[kStages];
-    int total;
-};
-
-static MlpLayout make_layout() {
-    MlpLayout L;
-    int o = 0;
-    auto stage = [&](int i, int in_dim, int out_dim) {
-        StageOff& s = L.s[i];
-        s.in_dim = in_dim; s.out_dim = out_dim;
-        s.ln_w = o; o += in_dim;
-        s.ln_b = o; o += in_dim;
-        s.hw = o; o += kHid * in_dim;
-        s.hb = o; o += kHid;
-        s.ow = o; o += out_dim * kHid;
-        s.ob = o; o += out_dim;
-        s.gw = o; o += kHid * in_dim;
-        s.gb = o; o += kHid;
-    };
-    stage(0, kIn, kDim);
-    stage(1, kDim, kDim);
-    stage(2, kDim, kDim);
-    stage(3, kDim, 1);
-    L.total = o;
-    return L;
-}
-static const MlpLayout kLayout = make_layout();
+static const MlpLayout kLayout = make_mlp_layout();
 
 // ---- kernels -------------------------------------------------------------------------------------------
 // LayerNorm forward: one warp per row.
@@ -420,14 +385,6 @@ __global__ void adam_step_inc_kernel(int* step, const float* stats) {
 
 }  // namespace hb
 
-struct hb_mlp_model {
-    float loss_scale = 1.0f;   // multiplies the loss and its gradients (the reference divides by its accumulation counter, trainer.py:441)
-    float* p = nullptr;   // parameters
-    float* g = nullptr;   // gradients of the last training step
-    float* m = nullptr;   // Adam first moment
-    float* v = nullptr;   // Adam second moment
-    int* step = nullptr;
-};
 
 namespace hb {
 
@@ -547,6 +504,8 @@ struct Ws {
     float *dz, *d_o[2], *d_a, *d_hg, *d_u;
     float* part;             // split-K partial sums
     float* colred;           // column-reduction partials [kColSlices][2][1536]
+    float* fused;            // workspace of the fused step (mlp_fused.cu), behind the staged path's buffers
+    int training;
 };
 static int64_t carve(Ws* w, float* base, int B, int training) {
     int64_t off = 0;
@@ -571,10 +530,26 @@ static int64_t carve(Ws* w, float* base, int B, int training) {
     }
     w->part = take(kPartFloats);
     w->colred = take((int64_t)kColSlices * 2 * kIn);
+    w->fused = base ? base + off : nullptr;
+    w->training = training;
+    off += mlp_fused_ws_floats(B, training);
     return off;
 }
 
-static int forward_impl(const hb_mlp_model* m, const float* x, int B, const Ws& w, cudaStream_t st) {
+// HB_MLP_STAGED=1 (or HB_MLP_FMA=1): the one-kernel-per-operation path below instead of the fused step of mlp_fused.cu (parity mode)
+static bool fused_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HB_MLP_STAGED");
+        on = ((e && e[0] == '1') || !tensor_path_enabled()) ? 0 : 1;
+    }
+    return on == 1;
+}
+
+// logits of the batch -> *logits (a workspace buffer)
+static int forward_impl(const hb_mlp_model* m, const float* x, int B, const Ws& w, cudaStream_t st, const float** logits) {
+    if (fused_enabled()) return mlp_fused_forward(m, x, B, w.fused, w.training, logits, st);
+    *logits = w.o[kStages - 1];
     const float* cur = x;
     for (int s = 0; s < kStages; ++s) {
         const StageOff& L = kLayout.s[s];
@@ -720,9 +695,10 @@ extern "C" int hb_mlp_forward(const hb_mlp_model* m, const float* x_dev, float* 
     cudaStream_t st = (cudaStream_t)stream;
     Ws w;
     carve(&w, reinterpret_cast<float*>(workspace_dev), B, 0);
-    int rc = forward_impl(m, x_dev, B, w, st);
+    const float* logits = nullptr;
+    int rc = forward_impl(m, x_dev, B, w, st, &logits);
     if (rc) return rc;
-    sigmoid_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.o[kStages - 1], prob_dev, B);
+    sigmoid_kernel<<<ceil_div(B, 256), 256, 0, st>>>(logits, prob_dev, B);
     HB_LAUNCHED();
     return HB_OK;
 }
@@ -947,10 +923,11 @@ namespace hb {
 // forward + sigmoid + high-loss selection: prob, stats[1] = rows selected in THIS batch (stats[0,2,3] zeroed)
 static int select_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float thr, float* prob_dev, float* stats_dev,
                        const Ws& w, cudaStream_t st) {
-    int rc = forward_impl(m, x_dev, B, w, st);
+    const float* logits = nullptr;
+    int rc = forward_impl(m, x_dev, B, w, st, &logits);
     if (rc) return rc;
     HB_CUDA_OK(cudaMemsetAsync(stats_dev, 0, 4 * sizeof(float), st));
-    head_select_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.o[3], y_dev, prob_dev, stats_dev, B, thr);
+    head_select_kernel<<<ceil_div(B, 256), 256, 0, st>>>(logits, y_dev, prob_dev, stats_dev, B, thr);
     HB_LAUNCHED();
     return HB_OK;
 }
@@ -964,6 +941,7 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
     HB_LAUNCHED();
     head_finish_kernel<<<1, 1, 0, st>>>(stats_dev, n_total_dev, B, min_selected);
     HB_LAUNCHED();
+    if (fused_enabled()) return mlp_fused_backward(m, x_dev, B, w.fused, w.dz, st);
     const float* d_out = w.dz;   // gradient wrt the stage's output o[s]
     int flip = 0;
     for (int s = kStages - 1; s >= 0; --s) {

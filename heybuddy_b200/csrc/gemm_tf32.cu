@@ -15,6 +15,7 @@
 // (M = 128, N = 128, K = 8) and commits to the stage's `empty` barrier, which the producers wait on before they overwrite the stage.
 // No CTA-wide barrier inside the loop (the first version had two per step and ran at a third of this one's rate).
 // The epilogue goes through shared memory so that C is written in whole 128-byte row segments.
+#include "mlp_common.cuh"
 #include "tc_ptx.cuh"
 
 #include <algorithm>
@@ -29,13 +30,6 @@ constexpr int kTfPitch = 129 * 16;                      // bytes between K chunk
 constexpr int kTfTile = kTfChunks * kTfPitch;           // one operand tile: 16.5 KB
 constexpr int kTfStage = 4 * kTfTile;                   // A, A_lo, B, B_lo
 
-struct TfArgs {
-    const float* A; int lda;
-    const float* B0; const float* B1; int bsplit; int ldb;      // B row n: n < bsplit ? B0 + n ldb : B1 + (n - bsplit) ldb
-    const float* bias0; const float* bias1; int biassplit;      // bias0 == nullptr: none
-    float* C; int ldc;
-    int M, N, K;
-};
 
 constexpr int kTfStages = 3;
 
@@ -58,6 +52,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kMode 0: both operands K-major (A [M][K], B [N][K]).  kMode 1: both batch-major (A [K][M], B [K][N]): the producers transpose 4 x 4
+// blocks in registers on the way to the same K-major shared-memory tiles.
+template <int kMode>
 __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     TfHeader& hdr = *reinterpret_cast<TfHeader*>(smem);
@@ -75,25 +72,63 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     const uint32_t tmem = hdr.tmem;
     constexpr uint32_t idesc = make_idesc_tf32(kTfBM, kTfBN);
 
-    // thread -> 4 (row, chunk) slots of each operand tile: slot = tid + 256 i, chunk = slot % 8 (a row's 128 bytes are 8 lanes), row = slot / 8
+    // K slice of this CTA (blockIdx.z): steps [s_begin, s_end) of 32
+    const int steps_total = (a.K + kTfBK - 1) / kTfBK;
+    const int s_begin = (int)((int64_t)blockIdx.z * steps_total / a.splits), s_end = (int)((int64_t)(blockIdx.z + 1) * steps_total / a.splits);
+    const int steps = s_end - s_begin;
+    const int kbase = s_begin * kTfBK;
+
+    // thread -> 4 (row, chunk) slots of each operand tile.  kMode 0: slot = tid + 256 i, chunk = slot % 8 (a row's 128 bytes are 8 lanes),
+    // row = slot / 8.  kMode 1: chunk = warp, row = lane + 32 i (a warp reads 128 consecutive floats of four k rows).
     constexpr int kSlots = kTfBM * kTfChunks / kTfProducers;    // 4
     float4 ra[2][kSlots], rb[2][kSlots];                        // two register sets: the loads run TWO steps ahead of their use
-    auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+    auto slot_c = [&](int i) { return kMode == 0 ? ((tid + i * kTfProducers) & (kTfChunks - 1)) : warp; };
+    auto slot_r = [&](int i) { return kMode == 0 ? ((tid + i * kTfProducers) / kTfChunks) : (lane + 32 * i); };
+    float mu[kSlots], rs[kSlots];
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i) {
-            const int slot = tid + i * kTfProducers, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
-            const int m = m0 + r, n = n0 + r;
-            xa[i] = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* brow = n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb;
-            xb[i] = n < a.N ? __ldg(reinterpret_cast<const float4*>(brow + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kSlots; ++i) {
+        const int m = m0 + slot_r(i);
+        const bool on = kMode == 0 && a.mean != nullptr && m < a.M;
+        mu[i] = on ? __ldg(a.mean + m) : 0.f;
+        rs[i] = on ? __ldg(a.rstd + m) : 1.f;
+    }
+    auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+        if (kMode == 0) {
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                const int c = slot_c(i), r = slot_r(i);
+                const int m = m0 + r, n = n0 + r;
+                float4 v = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xa[i] = make_float4((v.x - mu[i]) * rs[i], (v.y - mu[i]) * rs[i], (v.z - mu[i]) * rs[i], (v.w - mu[i]) * rs[i]);
+                const float* brow = n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb;
+                xb[i] = n < a.N ? __ldg(reinterpret_cast<const float4*>(brow + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            float ta[kSlots][4], tb[kSlots][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + 4 * warp + j;
+                const bool kv = k < a.K;
+                const float kmu = (kv && a.mean != nullptr) ? __ldg(a.mean + k) : 0.f, krs = (kv && a.rstd != nullptr) ? __ldg(a.rstd + k) : 1.f;
+#pragma unroll
+                for (int i = 0; i < kSlots; ++i) {
+                    const int m = m0 + lane + 32 * i, n = n0 + lane + 32 * i;
+                    ta[i][j] = (kv && m < a.M) ? __ldg(a.A + (int64_t)k * a.lda + m) : 0.f;
+                    tb[i][j] = (kv && n < a.N) ? (__ldg(a.B0 + (int64_t)k * a.ldb + n) - kmu) * krs : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                xa[i] = make_float4(ta[i][0], ta[i][1], ta[i][2], ta[i][3]);
+                xb[i] = make_float4(tb[i][0], tb[i][1], tb[i][2], tb[i][3]);
+            }
         }
     };
     auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); };       // v - (what kind::tf32 reads of v)
     auto store = [&](unsigned char* st, const float4 (&xa)[kSlots], const float4 (&xb)[kSlots]) {
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
-            const int slot = tid + i * kTfProducers, c = slot & (kTfChunks - 1), r = slot / kTfChunks;
-            const int off = c * kTfPitch + r * 16;
+            const int off = slot_c(i) * kTfPitch + slot_r(i) * 16;
             *reinterpret_cast<float4*>(st + off) = xa[i];
             *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(xa[i].x), lo_of(xa[i].y), lo_of(xa[i].z), lo_of(xa[i].w));
             *reinterpret_cast<float4*>(st + 2 * kTfTile + off) = xb[i];
@@ -101,11 +136,10 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
         }
     };
 
-    const int steps = a.K / kTfBK;
     if (warp < kTfProducers / 32) {
         // ---- producers: step s lives in shared-memory stage s % 3 and register set s % 2 ------------------------------------------
-        load(0, ra[0], rb[0]);
-        if (steps > 1) load(kTfBK, ra[1], rb[1]);
+        load(kbase, ra[0], rb[0]);
+        if (steps > 1) load(kbase + kTfBK, ra[1], rb[1]);
         auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
             const int sg = s % kTfStages;
             // the stage is free once the MMAs of step s - 3 have completed: warp 0 polls their commit, the producers meet at a barrier
@@ -114,7 +148,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
                 named_bar_sync(1, kTfProducers);
             }
             store(stage0 + sg * kTfStage, xa, xb);
-            if (s + 2 < steps) load((s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
+            if (s + 2 < steps) load(kbase + (s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
             fence_proxy_async();                                    // generic-proxy stores -> visible to the tensor core
             named_bar_sync(1, kTfProducers);
             if (tid == 0) mbar_arrive(&hdr.full[sg]);
@@ -177,7 +211,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
             const int idx = tid + k * kTfProducers, r = idx >> 3, piece = idx & 7;
             const int m = m0 + r, n = n0 + 32 * q + 4 * piece;
             if (m < a.M && n < a.N)        // N is a multiple of 4 (checked by the caller)
-                *reinterpret_cast<float4*>(a.C + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
+                *reinterpret_cast<float4*>(a.C + (int64_t)blockIdx.z * a.split_stride + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
         }
         named_bar_sync(1, kTfProducers);
     }
@@ -195,25 +229,47 @@ bool gemm_tf32x3_ok(const float* A, int lda, const float* B0, const float* B1, i
            (B1 == nullptr || al(B1)) && al(C);
 }
 
+template <int kMode>
+static int tf_launch(const TfArgs& a, cudaStream_t st) {
+    const size_t smem = 128 + kTfStages * (size_t)kTfStage + 128;
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    gemm_tf32x3_kernel<kMode><<<dim3(ceil_div(a.N, kTfBN), ceil_div(a.M, kTfBM), a.splits), kTfThreads, smem, st>>>(a);
+    HB_LAUNCHED();
+    return HB_OK;
+}
+
+static bool tf_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int gemm_tf32x3_launch(const TfArgs& a, cudaStream_t st) {
+    HB_REQUIRE(gemm_tf32x3_ok(a.A, a.lda, a.B0, a.B1, a.ldb, a.C, a.ldc, a.M, a.N, a.K), "gemm_tf32x3: unsupported shape or alignment");
+    HB_REQUIRE(a.splits >= 1 && a.splits <= a.K / kTfBK && (a.splits == 1 || (a.bias0 == nullptr && a.split_stride % 4 == 0)),
+               "gemm_tf32x3: bad K split");
+    return tf_launch<0>(a, st);
+}
+
+int gemm_tf32x3_launch_batch_major(const TfArgs& a, cudaStream_t st) {
+    HB_REQUIRE(a.M >= 1 && a.N >= 4 && a.K >= 1 && a.N % 4 == 0 && a.ldc % 4 == 0 && tf_aligned(a.C) && a.B1 == nullptr && a.bias0 == nullptr,
+               "gemm_tf32x3 (batch-major): unsupported shape or alignment");
+    HB_REQUIRE(a.splits >= 1 && a.splits <= ceil_div(a.K, kTfBK) && a.split_stride % 4 == 0, "gemm_tf32x3 (batch-major): bad K split");
+    return tf_launch<1>(a, st);
+}
+
 // C[M, N] = A[M, K] B[N, K]^T + bias (fp32 in and out, 3 x TF32 on tcgen05).  B rows / bias entries at or past `bsplit` come from B1 / bias1.
 int gemm_tf32x3_tn(const float* A, int lda, const float* B0, const float* B1, int bsplit, int ldb, const float* bias0, const float* bias1,
                    int biassplit, float* C, int ldc, int M, int N, int K, cudaStream_t st) {
-    HB_REQUIRE(gemm_tf32x3_ok(A, lda, B0, B1, ldb, C, ldc, M, N, K), "gemm_tf32x3_tn: unsupported shape or alignment");
     TfArgs a;
     a.A = A; a.lda = lda;
     a.B0 = B0; a.B1 = B1 ? B1 : B0; a.bsplit = B1 ? bsplit : (1 << 30); a.ldb = ldb;
     a.bias0 = bias0; a.bias1 = bias1 ? bias1 : bias0; a.biassplit = bias1 ? biassplit : (1 << 30);
     a.C = C; a.ldc = ldc;
     a.M = M; a.N = N; a.K = K;
-    const size_t smem = 128 + kTfStages * (size_t)kTfStage + 128;
-    static bool configured = false;
-    if (!configured) {
-        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    gemm_tf32x3_kernel<<<dim3(ceil_div(N, kTfBN), ceil_div(M, kTfBM)), kTfThreads, smem, st>>>(a);
-    HB_LAUNCHED();
-    return HB_OK;
+    a.mean = nullptr; a.rstd = nullptr;
+    a.splits = 1; a.split_stride = 0;
+    return gemm_tf32x3_launch(a, st);
 }
 
 int gemm_tf32_check_timeout() {

@@ -123,7 +123,8 @@ def test_config4_batch_and_multi_model(cuda_device):
     for i in (0, 3, 6):
         want = ocls.forward(x[:512], spec.init_classifier_weights(5002 + i))[:, 0]
         np.testing.assert_allclose(got[i, :512], want, rtol=1e-3, atol=1e-6)
-    np.testing.assert_allclose(models[2](xt).cpu().numpy()[:, 0], got[2], rtol=1e-6)
+    # single-model and stacked paths fold the input LayerNorm the same way but add their K slices up in a different order
+    np.testing.assert_allclose(models[2](xt).cpu().numpy()[:, 0], got[2], rtol=2e-5)
 
 
 def test_tensor_core_products_keep_fp32_accuracy(cuda_device):
