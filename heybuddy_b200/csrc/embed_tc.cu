@@ -246,6 +246,7 @@ extern "C" int hb_check_kernels(void) {
     int rc = hb::tcg_check_timeout();
     if (rc == HB_OK) rc = hb::tail_check_timeout();
     if (rc == HB_OK) rc = hb::gemm_tf32_check_timeout();
+    if (rc == HB_OK) rc = hb::mlp_fused_check_timeout();
     return rc;
 }
 

@@ -92,29 +92,30 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
         mu[i] = on ? __ldg(a.mean + m) : 0.f;
         rs[i] = on ? __ldg(a.rstd + m) : 1.f;
     }
-    auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+    // loads leave the words as they came (nothing may depend on them until `store`, two steps later); the row statistics are applied there
+    auto load = [&](int k0, float4 (&xa)[kSlots], float4 (&xb)[kSlots], float4& km, float4& kr) {
         if (kMode == 0) {
 #pragma unroll
             for (int i = 0; i < kSlots; ++i) {
                 const int c = slot_c(i), r = slot_r(i);
                 const int m = m0 + r, n = n0 + r;
-                float4 v = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xa[i] = make_float4((v.x - mu[i]) * rs[i], (v.y - mu[i]) * rs[i], (v.z - mu[i]) * rs[i], (v.w - mu[i]) * rs[i]);
+                xa[i] = m < a.M ? __ldg(reinterpret_cast<const float4*>(a.A + (int64_t)m * a.lda + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* brow = n < a.bsplit ? a.B0 + (int64_t)n * a.ldb : a.B1 + (int64_t)(n - a.bsplit) * a.ldb;
                 xb[i] = n < a.N ? __ldg(reinterpret_cast<const float4*>(brow + k0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
-            float ta[kSlots][4], tb[kSlots][4];
+            float ta[kSlots][4], tb[kSlots][4], tm[4], tr[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = k0 + 4 * warp + j;
                 const bool kv = k < a.K;
-                const float kmu = (kv && a.mean != nullptr) ? __ldg(a.mean + k) : 0.f, krs = (kv && a.rstd != nullptr) ? __ldg(a.rstd + k) : 1.f;
+                tm[j] = (kv && a.mean != nullptr) ? __ldg(a.mean + k) : 0.f;
+                tr[j] = (kv && a.rstd != nullptr) ? __ldg(a.rstd + k) : 1.f;
 #pragma unroll
                 for (int i = 0; i < kSlots; ++i) {
                     const int m = m0 + lane + 32 * i, n = n0 + lane + 32 * i;
                     ta[i][j] = (kv && m < a.M) ? __ldg(a.A + (int64_t)k * a.lda + m) : 0.f;
-                    tb[i][j] = (kv && n < a.N) ? (__ldg(a.B0 + (int64_t)k * a.ldb + n) - kmu) * krs : 0.f;
+                    tb[i][j] = (kv && n < a.N) ? __ldg(a.B0 + (int64_t)k * a.ldb + n) : 0.f;
                 }
             }
 #pragma unroll
@@ -122,40 +123,46 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
                 xa[i] = make_float4(ta[i][0], ta[i][1], ta[i][2], ta[i][3]);
                 xb[i] = make_float4(tb[i][0], tb[i][1], tb[i][2], tb[i][3]);
             }
+            km = make_float4(tm[0], tm[1], tm[2], tm[3]);
+            kr = make_float4(tr[0], tr[1], tr[2], tr[3]);
         }
     };
     auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); };       // v - (what kind::tf32 reads of v)
-    auto store = [&](unsigned char* st, const float4 (&xa)[kSlots], const float4 (&xb)[kSlots]) {
+    auto store = [&](unsigned char* st, const float4 (&xa)[kSlots], const float4 (&xb)[kSlots], const float4& km, const float4& kr) {
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) {
             const int off = slot_c(i) * kTfPitch + slot_r(i) * 16;
-            *reinterpret_cast<float4*>(st + off) = xa[i];
-            *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(xa[i].x), lo_of(xa[i].y), lo_of(xa[i].z), lo_of(xa[i].w));
-            *reinterpret_cast<float4*>(st + 2 * kTfTile + off) = xb[i];
-            *reinterpret_cast<float4*>(st + 3 * kTfTile + off) = make_float4(lo_of(xb[i].x), lo_of(xb[i].y), lo_of(xb[i].z), lo_of(xb[i].w));
+            float4 va = xa[i], vb = xb[i];
+            if (kMode == 0) va = make_float4((va.x - mu[i]) * rs[i], (va.y - mu[i]) * rs[i], (va.z - mu[i]) * rs[i], (va.w - mu[i]) * rs[i]);
+            else vb = make_float4((vb.x - km.x) * kr.x, (vb.y - km.y) * kr.y, (vb.z - km.z) * kr.z, (vb.w - km.w) * kr.w);
+            *reinterpret_cast<float4*>(st + off) = va;
+            *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(va.x), lo_of(va.y), lo_of(va.z), lo_of(va.w));
+            *reinterpret_cast<float4*>(st + 2 * kTfTile + off) = vb;
+            *reinterpret_cast<float4*>(st + 3 * kTfTile + off) = make_float4(lo_of(vb.x), lo_of(vb.y), lo_of(vb.z), lo_of(vb.w));
         }
     };
 
     if (warp < kTfProducers / 32) {
         // ---- producers: step s lives in shared-memory stage s % 3 and register set s % 2 ------------------------------------------
-        load(kbase, ra[0], rb[0]);
-        if (steps > 1) load(kbase + kTfBK, ra[1], rb[1]);
-        auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots]) {
+        float4 km[2], kr[2];
+        load(kbase, ra[0], rb[0], km[0], kr[0]);
+        if (steps > 1) load(kbase + kTfBK, ra[1], rb[1], km[1], kr[1]);
+        auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots], float4& xm, float4& xr) {
             const int sg = s % kTfStages;
             // the stage is free once the MMAs of step s - 3 have completed: warp 0 polls their commit, the producers meet at a barrier
             if (s >= kTfStages) {
                 if (warp == 0) mbar_wait(&hdr.empty[sg], ((s - kTfStages) / kTfStages) & 1u, 8u + sg);
                 named_bar_sync(1, kTfProducers);
             }
-            store(stage0 + sg * kTfStage, xa, xb);
-            if (s + 2 < steps) load(kbase + (s + 2) * kTfBK, xa, xb);      // two steps ahead, in flight across the next iteration
+            store(stage0 + sg * kTfStage, xa, xb, xm, xr);
+            if (s + 2 < steps) load(kbase + (s + 2) * kTfBK, xa, xb, xm, xr);      // two steps ahead, in flight across the next iteration
             fence_proxy_async();                                    // generic-proxy stores -> visible to the tensor core
             named_bar_sync(1, kTfProducers);
             if (tid == 0) mbar_arrive(&hdr.full[sg]);
         };
         for (int s = 0; s < steps; s += 2) {
-            body(s, ra[0], rb[0]);
-            if (s + 1 < steps) body(s + 1, ra[1], rb[1]);
+            body(s, ra[0], rb[0], km[0], kr[0]);
+            if (s + 1 < steps) body(s + 1, ra[1], rb[1], km[1], kr[1]);
         }
     } else {
       if (lane == 0) {

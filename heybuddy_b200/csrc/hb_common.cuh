@@ -45,6 +45,7 @@ bool gemm_tf32x3_ok(const float* A, int lda, const float* B0, const float* B1, i
 int gemm_tf32x3_tn(const float* A, int lda, const float* B0, const float* B1, int bsplit, int ldb, const float* bias0, const float* bias1,
                    int biassplit, float* C, int ldc, int M, int N, int K, cudaStream_t st);
 int gemm_tf32_check_timeout();
+int mlp_fused_check_timeout();
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -20,6 +20,7 @@
 // output-linear gradients share one grouped FMA launch (`grads_kernel`); `finish_kernel` adds the K slices up in a fixed order and
 // applies the formulas above.  Every sum has a fixed order: the step is deterministic.
 #include "mlp_common.cuh"
+#include "tc_ptx.cuh"
 
 #include <algorithm>
 #include <math.h>
@@ -32,7 +33,8 @@ const MlpLayout kL = make_mlp_layout();
 
 constexpr int kRows = 32;                 // rows per CTA of the tail kernels
 constexpr int kHg = 2 * kHid;             // 128 interleaved hidden / gate columns
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 128;
+constexpr int kNjHg = kHg / 16, kNjA = kHid / 16, kNjO = kDim / 16;     // columns per thread: 8 pre-activations (4 gates), 4, 6
 
 // transposed copies of the small weights for the forward tail (written by prep_kernel)
 constexpr int kWoT0 = 0;                                  // stage s: [64][out_dim]  (stage 3: [64])
@@ -58,7 +60,7 @@ constexpr int kRsHg0 = kOOff3 + kHid;                     // column sums of d_hg
 constexpr int kRsO0 = kRsHg0 + 4 * kHg;                   // column sums of d_o, stages 0..2: [96] each; stage 3 (dz): [1]
 constexpr int kPartFloatsPerSlice = ((kRsO0 + 3 * kDim + 1 + 63) / 64) * 64;
 
-constexpr int kGradSlicesMax = 16;
+constexpr int kGradSlicesMax = 32;
 constexpr int kG0SlicesMax = 16;
 constexpr int kFwdSlicesMax = 8;
 
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ p, 
         const float* gamma = p + S.ln_w;
         const float* beta = p + S.ln_b;
         float acc = 0.f;
+#pragma unroll 8
         for (int k = lane; k < kIn; k += 32) {
             const float w = W[k];
             w0f[n * kIn + k] = w * gamma[k];
@@ -174,54 +177,107 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
 
-// ---- tail kernels: shared helpers ------------------------------------------------------------------------------------------------------
-// acc[j] += sum_k act[k][lane] W[k][col0 + j]      (act: [K][32] plane, W: [K][pitch] in shared memory, 16-byte broadcast reads)
+// ---- tail kernels ----------------------------------------------------------------------------------------------------------------------
+// One CTA = 32 rows; 128 threads, thread (rq, cg) = rows 4 rq .. 4 rq + 3 x one of 16 column groups: a 4 x NJ register tile per product
+// (NJ = 8 pre-activations = 4 gates, 6 outputs, 4 gated activations), so each 16-byte shared-memory read feeds 16 - 32 FMAs (a 1 x NJ tile
+// per thread ran at a quarter of this: one weight word per FMA is all the shared-memory return path delivers).  Activations are
+// [feature][row] planes; the weight matrices arrive by cp.async.bulk into two buffers, matrix i + 1 in flight while matrix i is used.
+constexpr int kMatFloats = kDim * kHg + kHg;              // the largest staged matrix: [96][128] + its bias
+constexpr int kRed = 16 * kRows;
+constexpr int kTailSmemFloats = 2 * kMatFloats + kHg * kRows + kDim * kRows + 2 * kRed;
+constexpr int kTailSmemBytes = 128 + kTailSmemFloats * 4;
+
+struct MatList { const float* src[6]; int floats[6]; };
+
+struct WeightPipe {
+    uint64_t* bar;      // [2]
+    float* buf;         // [2][kMatFloats]
+    __device__ __forceinline__ void issue(const MatList& ml, int i) {
+        mbar_expect_tx(&bar[i & 1], (uint32_t)ml.floats[i] * 4u);
+        bulk_g2s(buf + (i & 1) * kMatFloats, ml.src[i], (uint32_t)ml.floats[i] * 4u, &bar[i & 1]);
+    }
+    // matrix i is in its buffer and everything every thread wrote to shared memory before this call is visible; matrix i - 1 is no longer
+    // needed by anyone, so its buffer takes matrix i + 1
+    __device__ __forceinline__ const float* acquire(const MatList& ml, int i, int n) {
+        if (threadIdx.x < 32) mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u, 16u + i);
+        __syncthreads();
+        if (threadIdx.x == 0 && i >= 1 && i + 1 < n) issue(ml, i + 1);
+        return buf + (i & 1) * kMatFloats;
+    }
+};
+
+// acc[i][j] += sum_k act[k][r0 + i] W[k][col0 + j]
 template <int K, int NJ>
-__device__ __forceinline__ void plane_fma(const float* __restrict__ act, const float* __restrict__ W, int pitch, int col0, int lane, float (&acc)[NJ]) {
+__device__ __forceinline__ void plane_fma4(const float* __restrict__ act, const float* __restrict__ W, int pitch, int col0, int r0, float (&acc)[4][NJ]) {
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const float a = act[k * kRows + lane];
-        const float4* w4 = reinterpret_cast<const float4*>(W + k * pitch + col0);
+        const float4 a4 = *reinterpret_cast<const float4*>(act + k * kRows + r0);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        float w[NJ];
+        if (NJ % 4 == 0) {
 #pragma unroll
-        for (int q = 0; q < NJ / 4; ++q) {
-            const float4 w = w4[q];
-            acc[4 * q] = fmaf(a, w.x, acc[4 * q]);
-            acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+            for (int q = 0; q < NJ / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(W + k * pitch + col0 + 4 * q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NJ / 2; ++q) {
+                const float2 t = *reinterpret_cast<const float2*>(W + k * pitch + col0 + 2 * q);
+                w[2 * q] = t.x; w[2 * q + 1] = t.y;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
     }
-}
-
-__device__ __forceinline__ void stage_copy(float* __restrict__ dst, const float* __restrict__ src, int n_floats, int tid) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < n_floats / 4; i += kTailThreads) d4[i] = __ldg(s4 + i);
 }
 
 template <int N>
 __device__ __forceinline__ void load_row(float (&v)[N], const float* __restrict__ src, bool ok) {
+    if (N % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-        const float4 t = ok ? *reinterpret_cast<const float4*>(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        for (int q = 0; q < N / 4; ++q) {
+            const float4 t = ok ? *reinterpret_cast<const float4*>(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < N / 2; ++q) {
+            const float2 t = ok ? *reinterpret_cast<const float2*>(src + 2 * q) : make_float2(0.f, 0.f);
+            v[2 * q] = t.x; v[2 * q + 1] = t.y;
+        }
     }
 }
 template <int N>
 __device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&v)[N], bool ok) {
     if (!ok) return;
+    if (N % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < N / 2; ++q) *reinterpret_cast<float2*>(dst + 2 * q) = make_float2(v[2 * q], v[2 * q + 1]);
+    }
 }
-
-// sum over the 8 warps of a per-(warp, lane) value: red is [8][32]; the caller separates uses of the same array by a barrier
-__device__ __forceinline__ float cross_warp_sum(float* red, float v, int warp, int lane) {
-    red[warp * kRows + lane] = v;
-    __syncthreads();
-    float s = 0.f;
+// a thread's 4 x NJ tile -> the plane [col0 + j][r0 .. r0 + 3]
+template <int NJ>
+__device__ __forceinline__ void store_plane(float* __restrict__ plane, int col0, int r0, const float (&v)[4][NJ]) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w * kRows + lane];
-    return s;
+    for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(plane + (col0 + j) * kRows + r0) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+}
+// per-row sums over the 16 column groups: every thread deposits its four rows' partial sums, and after the caller's barrier reads the totals
+__device__ __forceinline__ void red_put(float* red, int cg, int r0, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(red + cg * kRows + r0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void red_get(const float* red, int r0, float (&v)[4]) {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const float4 t = *reinterpret_cast<const float4*>(red + w * kRows + r0);
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+    }
 }
 
 struct FwdArgs {
@@ -231,80 +287,130 @@ struct FwdArgs {
     Stages L;
 };
 
-constexpr int kTailSmemFloats = kHg * kDim + kHg * kRows + kDim * kRows + 4 * 8 * kRows;     // weights | wide plane | narrow plane | reductions
-
 // first-layer pre-activations (K slices) -> logits
-__global__ void __launch_bounds__(kTailThreads) fwd_tail_kernel(const FwdArgs f) {
-    extern __shared__ __align__(16) float sm[];
-    float* wbuf = sm;                              // one weight matrix at a time (up to [96][128])
-    float* abuf = wbuf + kHg * kDim;               // gated activations [64][32]
+__global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs f) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw);
+    float* sm = reinterpret_cast<float*>(smraw + 128);
+    float* abuf = sm + 2 * kMatFloats;             // gated activations [64][32]
     float* ubuf = abuf + kHg * kRows;              // stage input [96][32]
-    float* red = ubuf + kDim * kRows;              // [4][8][32]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = blockIdx.x * kRows + lane;
-    const bool ok = row < f.B;
-    const bool save = ok && f.save;
+    float* red = ubuf + kDim * kRows;              // [2][16][32]
+    const int tid = threadIdx.x, rq = tid & 7, cg = tid >> 3, r0 = 4 * rq;
+    const int row0 = blockIdx.x * kRows + r0;
+    bool ok[4], save[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ok[i] = row0 + i < f.B; save[i] = ok[i] && f.save; }
+
+    MatList ml;
+    for (int s = 0; s < 3; ++s) {
+        ml.src[2 * s] = f.wt + wot_off(s); ml.floats[2 * s] = kHid * kDim;
+        ml.src[2 * s + 1] = f.wt + whgt_off(s + 1); ml.floats[2 * s + 1] = kMatFloats;
+    }
+    WeightPipe wp{bars, sm};
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+        wp.issue(ml, 0);
+        wp.issue(ml, 1);
+    }
+    __syncthreads();
 
     for (int s = 0; s < kStages; ++s) {
         const StageOff& S = f.L.s[s];
-        float hgv[16];
+        float hgv[4][kNjHg];
         if (s == 0) {
-            load_row(hgv, f.b0f + warp * 16, true);
-            for (int z = 0; z < f.splits; ++z) {
-                float t[16];
-                load_row(t, f.hgpart + z * f.split_stride + (int64_t)row * kHg + warp * 16, ok);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) hgv[e] += t[e];
+            for (int i = 0; i < 4; ++i) {
+                load_row(hgv[i], f.b0f + cg * kNjHg, true);
+                for (int z = 0; z < f.splits; ++z) {
+                    float t[kNjHg];
+                    load_row(t, f.hgpart + z * f.split_stride + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
+#pragma unroll
+                    for (int e = 0; e < kNjHg; ++e) hgv[i][e] += t[e];
+                }
             }
         } else {
-            __syncthreads();                       // every warp is done with the previous matrix; ubuf is complete
-            stage_copy(wbuf, f.wt + whgt_off(s), kDim * kHg, tid);
-            __syncthreads();
-            load_row(hgv, f.wt + whgt_off(s) + kDim * kHg + warp * 16, true);
-            plane_fma<kDim, 16>(ubuf, wbuf, kHg, warp * 16, lane, hgv);
-        }
-        if (save) store_row(f.hg[s] + (int64_t)row * kHg + warp * 16, hgv, true);
-        float av[8];
+            const float* W = wp.acquire(ml, 2 * s - 1, 6);        // ubuf is complete
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float h = hgv[2 * j], g = hgv[2 * j + 1];
-            av[j] = h / (1.f + expf(-h)) * g;
-            abuf[(warp * 8 + j) * kRows + lane] = av[j];
+            for (int i = 0; i < 4; ++i) load_row(hgv[i], W + kDim * kHg + cg * kNjHg, true);
+            plane_fma4<kDim, kNjHg>(ubuf, W, kHg, cg * kNjHg, r0, hgv);
         }
-        if (save) store_row(f.a[s] + (int64_t)row * kHid + warp * 8, av, true);
-        __syncthreads();                           // abuf complete; wbuf free
+        float av[4][kNjA];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (save[i]) store_row(f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, hgv[i], true);
+#pragma unroll
+            for (int j = 0; j < kNjA; ++j) {
+                const float h = hgv[i][2 * j], g = hgv[i][2 * j + 1];
+                av[i][j] = h / (1.f + expf(-h)) * g;
+            }
+            if (save[i]) store_row(f.a[s] + (int64_t)(row0 + i) * kHid + cg * kNjA, av[i], true);
+        }
         if (s < kStages - 1) {
-            stage_copy(wbuf, f.wt + wot_off(s), kHid * kDim, tid);
-            __syncthreads();
-            float ov[12];
-            load_row(ov, f.p + S.ob + warp * 12, true);
-            plane_fma<kHid, 12>(abuf, wbuf, kDim, warp * 12, lane, ov);
-            // LayerNorm of the next stage over the row's 96 features (12 per warp)
+            store_plane(abuf, cg * kNjA, r0, av);
+            const float* W = wp.acquire(ml, 2 * s, 6);            // abuf is complete
+            float ov[4][kNjO];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) load_row(ov[i], f.p + S.ob + cg * kNjO, true);
+            plane_fma4<kHid, kNjO>(abuf, W, kDim, cg * kNjO, r0, ov);
+            // LayerNorm of the next stage over each row's 96 features (6 per column group)
             const StageOff& N = f.L.s[s + 1];
-            float ps = 0.f;
+            float ps[4], mu[4], rs[4];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) ps += ov[j];
-            const float mu = cross_warp_sum(red + (s & 1) * 2 * 8 * kRows, ps, warp, lane) * (1.f / kDim);
-            float pq = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                ps[i] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 12; ++j) { const float d = ov[j] - mu; pq = fmaf(d, d, pq); }
-            const float rs = rsqrtf(cross_warp_sum(red + (s & 1) * 2 * 8 * kRows + 8 * kRows, pq, warp, lane) * (1.f / kDim) + kLnEps);
-            float xh[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                xh[j] = (ov[j] - mu) * rs;
-                ubuf[(warp * 12 + j) * kRows + lane] = fmaf(xh[j], __ldg(f.p + N.ln_w + warp * 12 + j), __ldg(f.p + N.ln_b + warp * 12 + j));
+                for (int j = 0; j < kNjO; ++j) ps[i] += ov[i][j];
             }
-            if (save) {
-                store_row(f.xh[s + 1] + (int64_t)row * kDim + warp * 12, xh, true);
-                if (warp == 0) f.rstd[s + 1][row] = rs;
+            red_put(red, cg, r0, ps);
+            __syncthreads();
+            red_get(red, r0, mu);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mu[i] *= (1.f / kDim);
+                ps[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < kNjO; ++j) { const float d = ov[i][j] - mu[i]; ps[i] = fmaf(d, d, ps[i]); }
             }
+            red_put(red + kRed, cg, r0, ps);
+            __syncthreads();
+            red_get(red + kRed, r0, rs);
+            float gam[kNjO], bet[kNjO];
+            load_row(gam, f.p + N.ln_w + cg * kNjO, true);
+            load_row(bet, f.p + N.ln_b + cg * kNjO, true);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                rs[i] = rsqrtf(rs[i] * (1.f / kDim) + kLnEps);
+                float xh[kNjO];
+#pragma unroll
+                for (int j = 0; j < kNjO; ++j) {
+                    xh[j] = (ov[i][j] - mu[i]) * rs[i];
+                    ov[i][j] = fmaf(xh[j], gam[j], bet[j]);
+                }
+                if (save[i]) {
+                    store_row(f.xh[s + 1] + (int64_t)(row0 + i) * kDim + cg * kNjO, xh, true);
+                    if (cg == 0) f.rstd[s + 1][row0 + i] = rs[i];
+                }
+            }
+            store_plane(ubuf, cg * kNjO, r0, ov);
         } else {
-            float ps = 0.f;
+            float ps[4], z[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ps = fmaf(av[j], __ldg(f.p + S.ow + warp * 8 + j), ps);
-            const float z = cross_warp_sum(red + (s & 1) * 2 * 8 * kRows, ps, warp, lane) + __ldg(f.p + S.ob);
-            if (ok && warp == 0) f.logit[row] = z;
+            for (int i = 0; i < 4; ++i) {
+                ps[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < kNjA; ++j) ps[i] = fmaf(av[i][j], __ldg(f.p + S.ow + cg * kNjA + j), ps[i]);
+            }
+            __syncthreads();                       // the previous stage's reads of `red` are over
+            red_put(red, cg, r0, ps);
+            __syncthreads();
+            red_get(red, r0, z);
+            if (cg == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (ok[i]) f.logit[row0 + i] = z[i] + __ldg(f.p + S.ob);
+            }
         }
     }
 }
@@ -318,71 +424,107 @@ struct BwdArgs {
 };
 
 // d loss / d logit -> d_hg of every stage and d_o of stages 0..2 (what the weight-gradient products read)
-__global__ void __launch_bounds__(kTailThreads) bwd_tail_kernel(const BwdArgs f) {
-    extern __shared__ __align__(16) float sm[];
-    float* wbuf = sm;                              // [128][96] interleaved hidden / gate rows, or W_o [96][64]
-    float* dbuf = wbuf + kHg * kDim;               // d_hg plane [128][32]
+__global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs f) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw);
+    float* sm = reinterpret_cast<float*>(smraw + 128);
+    float* dbuf = sm + 2 * kMatFloats;             // d_hg plane [128][32]
     float* dobuf = dbuf + kHg * kRows;             // d_o plane [96][32]
     float* red = dobuf + kDim * kRows;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = blockIdx.x * kRows + lane;
-    const bool ok = row < f.B;
+    const int tid = threadIdx.x, rq = tid & 7, cg = tid >> 3, r0 = 4 * rq;
+    const int row0 = blockIdx.x * kRows + r0;
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ok[i] = row0 + i < f.B;
 
+    // in the order of use: W_I of stage 3, then (W_o, W_I) of stages 2 and 1, then W_o of stage 0
+    MatList ml;
+    ml.src[0] = f.wt + wi_off(3); ml.floats[0] = kHg * kDim;
+    ml.src[1] = f.p + f.L.s[2].ow; ml.floats[1] = kDim * kHid;
+    ml.src[2] = f.wt + wi_off(2); ml.floats[2] = kHg * kDim;
+    ml.src[3] = f.p + f.L.s[1].ow; ml.floats[3] = kDim * kHid;
+    ml.src[4] = f.wt + wi_off(1); ml.floats[4] = kHg * kDim;
+    ml.src[5] = f.p + f.L.s[0].ow; ml.floats[5] = kDim * kHid;
+    WeightPipe wp{bars, sm};
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+        wp.issue(ml, 0);
+        wp.issue(ml, 1);
+    }
+    __syncthreads();
+
+    int mat = 0;
     for (int s = kStages - 1; s >= 0; --s) {
         const StageOff& S = f.L.s[s];
-        float dav[8];
+        float dav[4][kNjA];
         if (s == kStages - 1) {
-            const float dzr = ok ? f.dz[row] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dav[j] = dzr * __ldg(f.p + S.ow + warp * 8 + j);
+            for (int i = 0; i < 4; ++i) {
+                const float dzr = ok[i] ? f.dz[row0 + i] : 0.f;
+#pragma unroll
+                for (int j = 0; j < kNjA; ++j) dav[i][j] = dzr * __ldg(f.p + S.ow + cg * kNjA + j);
+            }
         } else {
-            __syncthreads();                       // dobuf complete; every warp is done with the previous matrix
-            stage_copy(wbuf, f.p + S.ow, kDim * kHid, tid);
-            __syncthreads();
+            const float* W = wp.acquire(ml, mat++, 6);            // dobuf is complete
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dav[j] = 0.f;
-            plane_fma<kDim, 8>(dobuf, wbuf, kHid, warp * 8, lane, dav);
-        }
-        float hgv[16], dhv[16];
-        load_row(hgv, f.hg[s] + (int64_t)row * kHg + warp * 16, ok);
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float h = hgv[2 * j], g = hgv[2 * j + 1];
-            const float sg = 1.f / (1.f + expf(-h));
-            dhv[2 * j] = dav[j] * g * (sg * (1.f + h * (1.f - sg)));      // d hidden
-            dhv[2 * j + 1] = dav[j] * h * sg;                             // d gate
+                for (int j = 0; j < kNjA; ++j) dav[i][j] = 0.f;
+            plane_fma4<kDim, kNjA>(dobuf, W, kHid, cg * kNjA, r0, dav);
         }
-        store_row(f.dhg[s] + (int64_t)row * kHg + warp * 16, dhv, ok);
+        float dhv[4][kNjHg];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float hgv[kNjHg];
+            load_row(hgv, f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
+#pragma unroll
+            for (int j = 0; j < kNjA; ++j) {
+                const float h = hgv[2 * j], g = hgv[2 * j + 1];
+                const float sg = 1.f / (1.f + expf(-h));
+                dhv[i][2 * j] = dav[i][j] * g * (sg * (1.f + h * (1.f - sg)));      // d hidden
+                dhv[i][2 * j + 1] = dav[i][j] * h * sg;                             // d gate
+            }
+            store_row(f.dhg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, dhv[i], ok[i]);
+        }
         if (s == 0) break;
+        store_plane(dbuf, cg * kNjHg, r0, dhv);
+        const float* W = wp.acquire(ml, mat++, 6);                // dbuf is complete
+        float duv[4][kNjO];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dbuf[(warp * 16 + e) * kRows + lane] = dhv[e];
-        __syncthreads();                           // dbuf complete; wbuf free
-        stage_copy(wbuf, f.wt + wi_off(s), kHg * kDim, tid);
-        __syncthreads();
-        float duv[12];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 12; ++j) duv[j] = 0.f;
-        plane_fma<kHg, 12>(dbuf, wbuf, kDim, warp * 12, lane, duv);
+            for (int j = 0; j < kNjO; ++j) duv[i][j] = 0.f;
+        plane_fma4<kHg, kNjO>(dbuf, W, kDim, cg * kNjO, r0, duv);
         // LayerNorm backward (input of stage s = output of stage s - 1)
-        float xh[12];
-        load_row(xh, f.xh[s] + (int64_t)row * kDim + warp * 12, ok);
-        float p1 = 0.f, p2 = 0.f;
+        float gam[kNjO], xh[4][kNjO], p1[4], p2[4], m1[4], m2[4];
+        load_row(gam, f.p + S.ln_w + cg * kNjO, true);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            duv[j] *= __ldg(f.p + S.ln_w + warp * 12 + j);
-            p1 += duv[j];
-            p2 = fmaf(duv[j], xh[j], p2);
-        }
-        const float m1 = cross_warp_sum(red + (s & 1) * 2 * 8 * kRows, p1, warp, lane) * (1.f / kDim);
-        const float m2 = cross_warp_sum(red + (s & 1) * 2 * 8 * kRows + 8 * kRows, p2, warp, lane) * (1.f / kDim);
-        const float rs = ok ? f.rstd[s][row] : 0.f;
-        float dov[12];
+        for (int i = 0; i < 4; ++i) {
+            load_row(xh[i], f.xh[s] + (int64_t)(row0 + i) * kDim + cg * kNjO, ok[i]);
+            p1[i] = 0.f; p2[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            dov[j] = rs * (duv[j] - m1 - xh[j] * m2);
-            dobuf[(warp * 12 + j) * kRows + lane] = dov[j];
+            for (int j = 0; j < kNjO; ++j) {
+                duv[i][j] *= gam[j];
+                p1[i] += duv[i][j];
+                p2[i] = fmaf(duv[i][j], xh[i][j], p2[i]);
+            }
         }
-        store_row(f.dout[s - 1] + (int64_t)row * kDim + warp * 12, dov, ok);
+        red_put(red, cg, r0, p1);
+        red_put(red + kRed, cg, r0, p2);
+        __syncthreads();
+        red_get(red, r0, m1);
+        red_get(red + kRed, r0, m2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float rs = ok[i] ? f.rstd[s][row0 + i] : 0.f;
+            const float a1 = m1[i] * (1.f / kDim), a2 = m2[i] * (1.f / kDim);
+#pragma unroll
+            for (int j = 0; j < kNjO; ++j) duv[i][j] = rs * (duv[i][j] - a1 - xh[i][j] * a2);
+            store_row(f.dout[s - 1] + (int64_t)(row0 + i) * kDim + cg * kNjO, duv[i], ok[i]);
+        }
+        store_plane(dobuf, cg * kNjO, r0, duv);
     }
 }
 
@@ -400,9 +542,10 @@ struct GradArgs {
     float* part;
 };
 
+constexpr int kGradBK = 32;
 __global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
-    __shared__ __align__(16) float As[2][16][64];
-    __shared__ __align__(16) float Bs[2][16][64];
+    __shared__ __align__(16) float As[2][kGradBK][64];
+    __shared__ __align__(16) float Bs[2][kGradBK][64];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     int pi = 0;
     while (pi + 1 < g.nprob && (int)blockIdx.x >= g.pr[pi + 1].tile0) ++pi;
@@ -410,7 +553,7 @@ __global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
     const int t = blockIdx.x - P.tile0, tm = t / P.tiles_n, tn = t - tm * P.tiles_n;
     const int m0 = tm * 64, n0 = tn * 64;
     const int k_begin = blockIdx.y * g.k_per_slice, k_end = min(g.K, k_begin + g.k_per_slice);
-    const int lk = tid >> 4, lc = (tid & 15) * 4;          // this thread's load slot: row lk of the 16-row chunk, 4 columns from lc
+    const int lk = tid >> 4, lc = (tid & 15) * 4;          // this thread's load slots: rows lk and lk + 16 of the 32-row chunk, 4 columns from lc
     auto fetch = [&](const float* X, int ld, int dim, int c0, int k) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (X == nullptr || k >= k_end) return v;
@@ -426,15 +569,26 @@ __global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
     float acc[4][4] = {};
     float rsum[4] = {0.f, 0.f, 0.f, 0.f};
     const bool do_rs = tn == 0 && tx == 0;
-    float4 va = fetch(P.A, P.lda, P.M, m0, k_begin + lk), vb = fetch(P.B, P.ldb, P.N, n0, k_begin + lk);
-    int buf = 0;
-    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-        *reinterpret_cast<float4*>(&As[buf][lk][lc]) = va;
-        *reinterpret_cast<float4*>(&Bs[buf][lk][lc]) = vb;
-        __syncthreads();
-        if (k0 + 16 < k_end) { va = fetch(P.A, P.lda, P.M, m0, k0 + 16 + lk); vb = fetch(P.B, P.ldb, P.N, n0, k0 + 16 + lk); }
+    float4 va[2], vb[2];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
+    for (int q = 0; q < 2; ++q) { va[q] = fetch(P.A, P.lda, P.M, m0, k_begin + lk + 16 * q); vb[q] = fetch(P.B, P.ldb, P.N, n0, k_begin + lk + 16 * q); }
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += kGradBK) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            *reinterpret_cast<float4*>(&As[buf][lk + 16 * q][lc]) = va[q];
+            *reinterpret_cast<float4*>(&Bs[buf][lk + 16 * q][lc]) = vb[q];
+        }
+        __syncthreads();
+        if (k0 + kGradBK < k_end) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                va[q] = fetch(P.A, P.lda, P.M, m0, k0 + kGradBK + lk + 16 * q);
+                vb[q] = fetch(P.B, P.ldb, P.N, n0, k0 + kGradBK + lk + 16 * q);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < kGradBK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
             const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -469,15 +623,16 @@ struct FinArgs {
     Stages L;
 };
 constexpr int kFinColBlocks = kIn / 32 + 3 * (kDim / 32);    // 32 input columns of one stage per block
-constexpr int kFinOutBlocks = 8;
+constexpr int kFinOutBlocks = 4;
 
-__global__ void __launch_bounds__(256) finish_kernel(const FinArgs f) {
+constexpr int kFinThreads = 1024, kFinGroups = kFinThreads / 32;
+__global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     __shared__ float db[kHg];
-    __shared__ float red[2][8][32];
+    __shared__ float red[2][kFinGroups][32];
     const int tid = threadIdx.x;
     if (blockIdx.x >= kFinColBlocks) {
         // output linears: dW_o = O, db_o = column sums of d_o
-        const int t0 = (blockIdx.x - kFinColBlocks) * 256 + tid, stride = kFinOutBlocks * 256;
+        const int t0 = (blockIdx.x - kFinColBlocks) * kFinThreads + tid, stride = kFinOutBlocks * kFinThreads;
         for (int s = 0; s < kStages; ++s) {
             const StageOff& S = f.L.s[s];
             const int off = s < 3 ? kOOff0 + s * kOStride : kOOff3, rs_off = kRsO0 + s * kDim;
@@ -512,8 +667,9 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinArgs f) {
     const int nz = s == 0 ? f.g0_slices : f.slices;
     const int64_t zstride = s == 0 ? (int64_t)kHg * kIn : kPartFloatsPerSlice;
     float dgam = 0.f, dbet = 0.f;
-    for (int n = ny; n < kHg; n += 8) {
+    for (int n = ny; n < kHg; n += kFinGroups) {
         float Gv = 0.f;
+#pragma unroll 4
         for (int z = 0; z < nz; ++z) Gv += G[z * zstride + (int64_t)n * in + k];
         const int widx = ((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k;
         f.g[widx] = fmaf(gamma, Gv, beta * db[n]);
@@ -527,7 +683,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinArgs f) {
     if (ny == 0) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { a += red[0][w][kx]; b += red[1][w][kx]; }
+        for (int w = 0; w < kFinGroups; ++w) { a += red[0][w][kx]; b += red[1][w][kx]; }
         f.g[S.ln_w + k] = a;
         f.g[S.ln_b + k] = b;
     }
@@ -536,15 +692,21 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinArgs f) {
 int configure_tail_smem() {
     static bool done = false;
     if (!done) {
-        const int bytes = kTailSmemFloats * (int)sizeof(float);
-        HB_CUDA_OK(cudaFuncSetAttribute(fwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        HB_CUDA_OK(cudaFuncSetAttribute(bwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HB_CUDA_OK(cudaFuncSetAttribute(fwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        HB_CUDA_OK(cudaFuncSetAttribute(bwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
         done = true;
     }
     return HB_OK;
 }
 
 }  // namespace
+
+int mlp_fused_check_timeout() {
+    unsigned int flag = 0;
+    HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
+    HB_REQUIRE(flag == 0, "classifier tail kernels: an mbarrier wait timed out (pipeline bug; barrier code %u)", flag);
+    return HB_OK;
+}
 
 int64_t mlp_fused_ws_floats(int B, int training) {
     FusedWs w;
@@ -558,7 +720,7 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     FusedWs w;
     carve(&w, ws, B, training);
     const Stages L = stages();
-    prep_kernel<<<kPrepFoldBlocks + 32, 256, 0, st>>>(m->p, L, w.w0f, w.b0f, w.wt);
+    prep_kernel<<<kPrepFoldBlocks + 96, 256, 0, st>>>(m->p, L, w.w0f, w.b0f, w.wt);
     HB_LAUNCHED();
     rowstats_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x, w.mean0, w.rstd0, B);
     HB_LAUNCHED();
@@ -577,7 +739,7 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     f.logit = w.logit;
     f.B = B; f.save = training;
     f.L = L;
-    fwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemFloats * sizeof(float), st>>>(f);
+    fwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(f);
     HB_LAUNCHED();
     *logits = w.logit;
     return HB_OK;
@@ -595,7 +757,7 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     for (int s = 0; s < kStages - 1; ++s) b.dout[s] = w.dout[s];
     b.B = B;
     b.L = L;
-    bwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemFloats * sizeof(float), st>>>(b);
+    bwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(b);
     HB_LAUNCHED();
 
     // first layer: G_0 = d_hg0^T xhat_0 on the tensor cores, xhat formed from x and the row statistics in the operand load
@@ -624,7 +786,7 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     g.nprob = np;
     g.K = B;
     const int slices = grad_slices(B);
-    g.k_per_slice = ceil_div(ceil_div(B, slices), 16) * 16;
+    g.k_per_slice = ceil_div(ceil_div(B, slices), kGradBK) * kGradBK;
     g.part = w.part;
     const int used = ceil_div(B, g.k_per_slice);
     grads_kernel<<<dim3(tile, used), 256, 0, st>>>(g);
@@ -635,7 +797,7 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     fin.part = w.part; fin.slices = used;
     fin.g0part = w.g0part; fin.g0_slices = t.splits;
     fin.L = L;
-    finish_kernel<<<kFinColBlocks + kFinOutBlocks, 256, 0, st>>>(fin);
+    finish_kernel<<<kFinColBlocks + kFinOutBlocks, kFinThreads, 0, st>>>(fin);
     HB_LAUNCHED();
     return HB_OK;
 }
