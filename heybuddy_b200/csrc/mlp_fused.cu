@@ -321,14 +321,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
         float hgv[4][kNjHg];
         if (s == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                load_row(hgv[i], f.b0f + cg * kNjHg, true);
-                for (int z = 0; z < f.splits; ++z) {
-                    float t[kNjHg];
-                    load_row(t, f.hgpart + z * f.split_stride + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
+            for (int i = 0; i < 4; ++i) load_row(hgv[i], f.b0f + cg * kNjHg, true);
+            // all four rows of a K slice in flight together; the slices add up in a fixed order
+#pragma unroll 2
+            for (int z = 0; z < f.splits; ++z) {
+                float t[4][kNjHg];
 #pragma unroll
-                    for (int e = 0; e < kNjHg; ++e) hgv[i][e] += t[e];
-                }
+                for (int i = 0; i < 4; ++i) load_row(t[i], f.hgpart + z * f.split_stride + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < kNjHg; ++e) hgv[i][e] += t[i][e];
             }
         } else {
             const float* W = wp.acquire(ml, 2 * s - 1, 6);        // ubuf is complete
@@ -339,23 +342,28 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
         float av[4][kNjA];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (save[i]) store_row(f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, hgv[i], true);
 #pragma unroll
             for (int j = 0; j < kNjA; ++j) {
                 const float h = hgv[i][2 * j], g = hgv[i][2 * j + 1];
                 av[i][j] = h / (1.f + expf(-h)) * g;
             }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (save[i]) store_row(f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, hgv[i], true);
             if (save[i]) store_row(f.a[s] + (int64_t)(row0 + i) * kHid + cg * kNjA, av[i], true);
         }
         if (s < kStages - 1) {
             store_plane(abuf, cg * kNjA, r0, av);
             const float* W = wp.acquire(ml, 2 * s, 6);            // abuf is complete
-            float ov[4][kNjO];
+            const StageOff& N = f.L.s[s + 1];
+            float ov[4][kNjO], gam[kNjO], bet[kNjO];
+            load_row(gam, f.p + N.ln_w + cg * kNjO, true);
+            load_row(bet, f.p + N.ln_b + cg * kNjO, true);
 #pragma unroll
             for (int i = 0; i < 4; ++i) load_row(ov[i], f.p + S.ob + cg * kNjO, true);
             plane_fma4<kHid, kNjO>(abuf, W, kDim, cg * kNjO, r0, ov);
             // LayerNorm of the next stage over each row's 96 features (6 per column group)
-            const StageOff& N = f.L.s[s + 1];
             float ps[4], mu[4], rs[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -376,9 +384,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             red_put(red + kRed, cg, r0, ps);
             __syncthreads();
             red_get(red + kRed, r0, rs);
-            float gam[kNjO], bet[kNjO];
-            load_row(gam, f.p + N.ln_w + cg * kNjO, true);
-            load_row(bet, f.p + N.ln_b + cg * kNjO, true);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 rs[i] = rsqrtf(rs[i] * (1.f / kDim) + kLnEps);
@@ -458,6 +463,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
     int mat = 0;
     for (int s = kStages - 1; s >= 0; --s) {
         const StageOff& S = f.L.s[s];
+        // this stage's saved pre-activations: requested before the product that precedes their use
+        float hgv[4][kNjHg];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) load_row(hgv[i], f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
         float dav[4][kNjA];
         if (s == kStages - 1) {
 #pragma unroll
@@ -477,19 +486,25 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
         float dhv[4][kNjHg];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float hgv[kNjHg];
-            load_row(hgv, f.hg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, ok[i]);
 #pragma unroll
             for (int j = 0; j < kNjA; ++j) {
-                const float h = hgv[2 * j], g = hgv[2 * j + 1];
+                const float h = hgv[i][2 * j], g = hgv[i][2 * j + 1];
                 const float sg = 1.f / (1.f + expf(-h));
                 dhv[i][2 * j] = dav[i][j] * g * (sg * (1.f + h * (1.f - sg)));      // d hidden
                 dhv[i][2 * j + 1] = dav[i][j] * h * sg;                             // d gate
             }
-            store_row(f.dhg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, dhv[i], ok[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_row(f.dhg[s] + (int64_t)(row0 + i) * kHg + cg * kNjHg, dhv[i], ok[i]);
         if (s == 0) break;
         store_plane(dbuf, cg * kNjHg, r0, dhv);
+        float gam[kNjO], xh[4][kNjO], rsv[4], p1[4], p2[4], m1[4], m2[4];
+        load_row(gam, f.p + S.ln_w + cg * kNjO, true);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            load_row(xh[i], f.xh[s] + (int64_t)(row0 + i) * kDim + cg * kNjO, ok[i]);
+            rsv[i] = ok[i] ? f.rstd[s][row0 + i] : 0.f;
+        }
         const float* W = wp.acquire(ml, mat++, 6);                // dbuf is complete
         float duv[4][kNjO];
 #pragma unroll
@@ -498,11 +513,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
             for (int j = 0; j < kNjO; ++j) duv[i][j] = 0.f;
         plane_fma4<kHg, kNjO>(dbuf, W, kDim, cg * kNjO, r0, duv);
         // LayerNorm backward (input of stage s = output of stage s - 1)
-        float gam[kNjO], xh[4][kNjO], p1[4], p2[4], m1[4], m2[4];
-        load_row(gam, f.p + S.ln_w + cg * kNjO, true);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            load_row(xh[i], f.xh[s] + (int64_t)(row0 + i) * kDim + cg * kNjO, ok[i]);
             p1[i] = 0.f; p2[i] = 0.f;
 #pragma unroll
             for (int j = 0; j < kNjO; ++j) {
@@ -518,12 +530,13 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
         red_get(red + kRed, r0, m2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float rs = ok[i] ? f.rstd[s][row0 + i] : 0.f;
+            const float rs = rsv[i];
             const float a1 = m1[i] * (1.f / kDim), a2 = m2[i] * (1.f / kDim);
 #pragma unroll
             for (int j = 0; j < kNjO; ++j) duv[i][j] = rs * (duv[i][j] - a1 - xh[i][j] * a2);
-            store_row(f.dout[s - 1] + (int64_t)(row0 + i) * kDim + cg * kNjO, duv[i], ok[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_row(f.dout[s - 1] + (int64_t)(row0 + i) * kDim + cg * kNjO, duv[i], ok[i]);
         store_plane(dobuf, cg * kNjO, r0, duv);
     }
 }
@@ -542,23 +555,24 @@ struct GradArgs {
     float* part;
 };
 
-constexpr int kGradBK = 32;
-__global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
-    __shared__ __align__(16) float As[2][kGradBK][64];
-    __shared__ __align__(16) float Bs[2][kGradBK][64];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+// 128 x 64 tile, 128 threads, 8 x 8 outputs per thread as four 4 x 4 blocks half a tile apart (conflict-free 16-byte reads; a 4 x 4
+// micro-tile ran at half the rate: the shared-memory return path delivers one word per two FMAs there, one per four here)
+constexpr int kGradBK = 16, kGradTM = 128, kGradTN = 64, kGradThreads = 128;
+__global__ void __launch_bounds__(kGradThreads) grads_kernel(const GradArgs g) {
+    __shared__ __align__(16) float As[2][kGradBK][kGradTM];
+    __shared__ __align__(16) float Bs[2][kGradBK][kGradTN];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
     int pi = 0;
     while (pi + 1 < g.nprob && (int)blockIdx.x >= g.pr[pi + 1].tile0) ++pi;
     const GradProb& P = g.pr[pi];
     const int t = blockIdx.x - P.tile0, tm = t / P.tiles_n, tn = t - tm * P.tiles_n;
-    const int m0 = tm * 64, n0 = tn * 64;
+    const int m0 = tm * kGradTM, n0 = tn * kGradTN;
     const int k_begin = blockIdx.y * g.k_per_slice, k_end = min(g.K, k_begin + g.k_per_slice);
-    const int lk = tid >> 4, lc = (tid & 15) * 4;          // this thread's load slots: rows lk and lk + 16 of the 32-row chunk, 4 columns from lc
-    auto fetch = [&](const float* X, int ld, int dim, int c0, int k) {
+    auto fetch = [&](const float* X, int ld, int dim, int c, int k) {        // 4 words from column c of row k
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (X == nullptr || k >= k_end) return v;
-        const float* src = X + (int64_t)k * ld + c0 + lc;
-        const int left = dim - (c0 + lc);
+        const float* src = X + (int64_t)k * ld + c;
+        const int left = dim - c;
         if (left >= 4 && (ld & 3) == 0) return __ldg(reinterpret_cast<const float4*>(src));
         if (left > 0) v.x = __ldg(src);
         if (left > 1) v.y = __ldg(src + 1);
@@ -566,36 +580,37 @@ __global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
         if (left > 3) v.w = __ldg(src + 3);
         return v;
     };
-    float acc[4][4] = {};
-    float rsum[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool do_rs = tn == 0 && tx == 0;
-    float4 va[2], vb[2];
+    // load slots: A chunk = 16 rows x 32 float4 (4 per thread), B chunk = 16 rows x 16 float4 (2 per thread)
+    float4 va[4], vb[2];
+    auto fetch_chunk = [&](int k0) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) { va[q] = fetch(P.A, P.lda, P.M, m0, k_begin + lk + 16 * q); vb[q] = fetch(P.B, P.ldb, P.N, n0, k_begin + lk + 16 * q); }
+        for (int q = 0; q < 4; ++q) { const int slot = tid + q * kGradThreads; va[q] = fetch(P.A, P.lda, P.M, m0 + (slot & 31) * 4, k0 + (slot >> 5)); }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const int slot = tid + q * kGradThreads; vb[q] = fetch(P.B, P.ldb, P.N, n0 + (slot & 15) * 4, k0 + (slot >> 4)); }
+    };
+    float acc[8][8] = {};
+    float rsum[8] = {};
+    const bool do_rs = tn == 0 && tx == 0;
+    fetch_chunk(k_begin);
     int buf = 0;
     for (int k0 = k_begin; k0 < k_end; k0 += kGradBK) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            *reinterpret_cast<float4*>(&As[buf][lk + 16 * q][lc]) = va[q];
-            *reinterpret_cast<float4*>(&Bs[buf][lk + 16 * q][lc]) = vb[q];
-        }
-        __syncthreads();
-        if (k0 + kGradBK < k_end) {
+        for (int q = 0; q < 4; ++q) { const int slot = tid + q * kGradThreads; *reinterpret_cast<float4*>(&As[buf][slot >> 5][(slot & 31) * 4]) = va[q]; }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                va[q] = fetch(P.A, P.lda, P.M, m0, k0 + kGradBK + lk + 16 * q);
-                vb[q] = fetch(P.B, P.ldb, P.N, n0, k0 + kGradBK + lk + 16 * q);
-            }
-        }
+        for (int q = 0; q < 2; ++q) { const int slot = tid + q * kGradThreads; *reinterpret_cast<float4*>(&Bs[buf][slot >> 4][(slot & 15) * 4]) = vb[q]; }
+        __syncthreads();
+        if (k0 + kGradBK < k_end) fetch_chunk(k0 + kGradBK);
 #pragma unroll
         for (int kk = 0; kk < kGradBK; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][kGradTM / 2 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][kGradTN / 2 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
                 if (do_rs) rsum[i] += av[i];
             }
         }
@@ -603,49 +618,61 @@ __global__ void __launch_bounds__(256) grads_kernel(const GradArgs g) {
     }
     float* out = g.part + (int64_t)blockIdx.y * kPartFloatsPerSlice;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i >> 2) * (kGradTM / 2) + ty * 4 + (i & 3);
         if (m >= P.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j >> 2) * (kGradTN / 2) + tx * 4 + (j & 3);
             if (n < P.N) out[P.part_off + m * P.N + n] = acc[i][j];
         }
         if (do_rs) out[P.rs_off + m] = rsum[i];
     }
 }
 
-// ---- finish: add the K slices up and turn G, db into the parameter gradients ---------------------------------------------------------------
+// ---- finish: add the K slices up (in slice order, into slice 0), then turn G and db into the parameter gradients -----------------------------
+__global__ void __launch_bounds__(256) slice_sum_kernel(float* __restrict__ part, int n, int slices, int64_t stride, float* __restrict__ part2, int n2,
+                                                        int slices2, int64_t stride2) {
+    const int n4 = n / 4, m4 = n2 / 4;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4 + m4; i += gridDim.x * 256) {
+        float* base = i < n4 ? part + 4 * (int64_t)i : part2 + 4 * (int64_t)(i - n4);
+        const int nz = i < n4 ? slices : slices2;
+        const int64_t st = i < n4 ? stride : stride2;
+        float4 acc = *reinterpret_cast<const float4*>(base);
+#pragma unroll 8
+        for (int z = 1; z < nz; ++z) {
+            const float4 t = *reinterpret_cast<const float4*>(base + z * st);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        *reinterpret_cast<float4*>(base) = acc;
+    }
+}
+
 struct FinArgs {
     const float* p; float* g;
-    const float* part; int slices;
-    const float* g0part; int g0_slices;
+    const float* part;          // slice 0 of the grouped launch's buffer, summed
+    const float* g0;            // slice 0 of the first-layer G, summed
     Stages L;
 };
 constexpr int kFinColBlocks = kIn / 32 + 3 * (kDim / 32);    // 32 input columns of one stage per block
 constexpr int kFinOutBlocks = 4;
-
 constexpr int kFinThreads = 1024, kFinGroups = kFinThreads / 32;
+
 __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     __shared__ float db[kHg];
     __shared__ float red[2][kFinGroups][32];
     const int tid = threadIdx.x;
+    const float* __restrict__ part = f.part;
+    const float* __restrict__ p = f.p;
+    float* __restrict__ g = f.g;
     if (blockIdx.x >= kFinColBlocks) {
         // output linears: dW_o = O, db_o = column sums of d_o
         const int t0 = (blockIdx.x - kFinColBlocks) * kFinThreads + tid, stride = kFinOutBlocks * kFinThreads;
         for (int s = 0; s < kStages; ++s) {
             const StageOff& S = f.L.s[s];
             const int off = s < 3 ? kOOff0 + s * kOStride : kOOff3, rs_off = kRsO0 + s * kDim;
-            for (int i = t0; i < S.out_dim * kHid; i += stride) {
-                float v = 0.f;
-                for (int z = 0; z < f.slices; ++z) v += f.part[(int64_t)z * kPartFloatsPerSlice + off + i];
-                f.g[S.ow + i] = v;
-            }
-            for (int n = t0; n < S.out_dim; n += stride) {
-                float v = 0.f;
-                for (int z = 0; z < f.slices; ++z) v += f.part[(int64_t)z * kPartFloatsPerSlice + rs_off + n];
-                f.g[S.ob + n] = v;
-            }
+            for (int i = t0; i < S.out_dim * kHid; i += stride) g[S.ow + i] = part[off + i];
+            for (int n = t0; n < S.out_dim; n += stride) g[S.ob + n] = part[rs_off + n];
         }
         return;
     }
@@ -655,27 +682,28 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     const StageOff& S = f.L.s[s];
     const int in = S.in_dim;
     if (tid < kHg) {
-        float v = 0.f;
-        for (int z = 0; z < f.slices; ++z) v += f.part[(int64_t)z * kPartFloatsPerSlice + kRsHg0 + s * kHg + tid];
+        const float v = part[kRsHg0 + s * kHg + tid];
         db[tid] = v;
-        if (kb == 0) f.g[((tid & 1) ? S.gb : S.hb) + (tid >> 1)] = v;
+        if (kb == 0) g[((tid & 1) ? S.gb : S.hb) + (tid >> 1)] = v;
     }
     __syncthreads();
     const int kx = tid & 31, ny = tid >> 5, k = kb * 32 + kx;
-    const float gamma = f.p[S.ln_w + k], beta = f.p[S.ln_b + k];
-    const float* G = s == 0 ? f.g0part : f.part + kGOff1 + (s - 1) * kGStride;
-    const int nz = s == 0 ? f.g0_slices : f.slices;
-    const int64_t zstride = s == 0 ? (int64_t)kHg * kIn : kPartFloatsPerSlice;
+    const float gamma = p[S.ln_w + k], beta = p[S.ln_b + k];
+    const float* __restrict__ G = s == 0 ? f.g0 : part + kGOff1 + (s - 1) * kGStride;
+    float Gv[kHg / kFinGroups], Wv[kHg / kFinGroups];
+#pragma unroll
+    for (int i = 0; i < kHg / kFinGroups; ++i) {
+        const int n = ny + kFinGroups * i;
+        Gv[i] = G[(int64_t)n * in + k];
+        Wv[i] = p[((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k];
+    }
     float dgam = 0.f, dbet = 0.f;
-    for (int n = ny; n < kHg; n += kFinGroups) {
-        float Gv = 0.f;
-#pragma unroll 4
-        for (int z = 0; z < nz; ++z) Gv += G[z * zstride + (int64_t)n * in + k];
-        const int widx = ((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k;
-        f.g[widx] = fmaf(gamma, Gv, beta * db[n]);
-        const float w = f.p[widx];
-        dgam = fmaf(w, Gv, dgam);
-        dbet = fmaf(w, db[n], dbet);
+#pragma unroll
+    for (int i = 0; i < kHg / kFinGroups; ++i) {
+        const int n = ny + kFinGroups * i;
+        g[((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k] = fmaf(gamma, Gv[i], beta * db[n]);
+        dgam = fmaf(Wv[i], Gv[i], dgam);
+        dbet = fmaf(Wv[i], db[n], dbet);
     }
     red[0][ny][kx] = dgam;
     red[1][ny][kx] = dbet;
@@ -684,8 +712,8 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int w = 0; w < kFinGroups; ++w) { a += red[0][w][kx]; b += red[1][w][kx]; }
-        f.g[S.ln_w + k] = a;
-        f.g[S.ln_b + k] = b;
+        g[S.ln_w + k] = a;
+        g[S.ln_b + k] = b;
     }
 }
 
@@ -776,8 +804,8 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     auto add = [&](const float* A, int lda, int M, const float* Bm, int ldb, int N, int part_off, int rs_off) {
         GradProb& P = g.pr[np++];
         P.A = A; P.B = Bm; P.M = M; P.N = N; P.lda = lda; P.ldb = ldb; P.part_off = part_off; P.rs_off = rs_off;
-        P.tile0 = tile; P.tiles_n = std::max(1, ceil_div(N, 64));
-        tile += ceil_div(M, 64) * P.tiles_n;
+        P.tile0 = tile; P.tiles_n = std::max(1, ceil_div(N, kGradTN));
+        tile += ceil_div(M, kGradTM) * P.tiles_n;
     };
     add(w.dhg[0], kHg, kHg, nullptr, 0, 0, 0, kRsHg0);                                                  // column sums only
     for (int s = 1; s < kStages; ++s) add(w.dhg[s], kHg, kHg, w.xh[s], kDim, kDim, kGOff1 + (s - 1) * kGStride, kRsHg0 + s * kHg);
@@ -789,13 +817,15 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     g.k_per_slice = ceil_div(ceil_div(B, slices), kGradBK) * kGradBK;
     g.part = w.part;
     const int used = ceil_div(B, g.k_per_slice);
-    grads_kernel<<<dim3(tile, used), 256, 0, st>>>(g);
+    grads_kernel<<<dim3(tile, used), kGradThreads, 0, st>>>(g);
     HB_LAUNCHED();
 
+    slice_sum_kernel<<<296, 256, 0, st>>>(w.part, kPartFloatsPerSlice, used, kPartFloatsPerSlice, w.g0part, kHg * kIn, t.splits, (int64_t)kHg * kIn);
+    HB_LAUNCHED();
     FinArgs fin;
     fin.p = m->p; fin.g = m->g;
-    fin.part = w.part; fin.slices = used;
-    fin.g0part = w.g0part; fin.g0_slices = t.splits;
+    fin.part = w.part;
+    fin.g0 = w.g0part;
     fin.L = L;
     finish_kernel<<<kFinColBlocks + kFinOutBlocks, kFinThreads, 0, st>>>(fin);
     HB_LAUNCHED();
