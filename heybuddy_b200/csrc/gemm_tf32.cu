@@ -55,12 +55,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // kMode 0: both operands K-major (A [M][K], B [N][K]).  kMode 1: both batch-major (A [K][M], B [K][N]): the producers transpose 4 x 4
 // blocks in registers on the way to the same K-major shared-memory tiles.
 template <int kMode>
-__global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs a) {
+__device__ __forceinline__ void gemm_tf32x3_tile(const TfArgs& a, const int tile_n, const int tile_m, const int slice) {
     extern __shared__ __align__(128) unsigned char smem[];
     TfHeader& hdr = *reinterpret_cast<TfHeader*>(smem);
     unsigned char* stage0 = smem + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * kTfBM, n0 = blockIdx.x * kTfBN;
+    const int m0 = tile_m * kTfBM, n0 = tile_n * kTfBN;
     if (tid == 0) {
         for (int i = 0; i < kTfStages; ++i) { mbar_init(&hdr.full[i], 1); mbar_init(&hdr.empty[i], 1); }
         fence_barrier_init();
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
     const uint32_t tmem = hdr.tmem;
     constexpr uint32_t idesc = make_idesc_tf32(kTfBM, kTfBN);
 
-    // K slice of this CTA (blockIdx.z): steps [s_begin, s_end) of 32
+    // K slice of this CTA: steps [s_begin, s_end) of 32
     const int steps_total = (a.K + kTfBK - 1) / kTfBK;
-    const int s_begin = (int)((int64_t)blockIdx.z * steps_total / a.splits), s_end = (int)((int64_t)(blockIdx.z + 1) * steps_total / a.splits);
+    const int s_begin = (int)((int64_t)slice * steps_total / a.splits), s_end = (int)((int64_t)(slice + 1) * steps_total / a.splits);
     const int steps = s_end - s_begin;
     const int kbase = s_begin * kTfBK;
 
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
                 for (int i = 0; i < kSlots; ++i) {
                     const int m = m0 + lane + 32 * i, n = n0 + lane + 32 * i;
                     ta[i][j] = (kv && m < a.M) ? __ldg(a.A + (int64_t)k * a.lda + m) : 0.f;
-                    tb[i][j] = (kv && n < a.N) ? __ldg(a.B0 + (int64_t)k * a.ldb + n) : 0.f;
+                    tb[i][j] = (kv && n < a.N) ? __ldg(a.B0 + (int64_t)k * a.ldb + n) : ((kv && n == a.ones_col) ? 1.f : 0.f);
                 }
             }
 #pragma unroll
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
             const int off = slot_c(i) * kTfPitch + slot_r(i) * 16;
             float4 va = xa[i], vb = xb[i];
             if (kMode == 0) va = make_float4((va.x - mu[i]) * rs[i], (va.y - mu[i]) * rs[i], (va.z - mu[i]) * rs[i], (va.w - mu[i]) * rs[i]);
-            else vb = make_float4((vb.x - km.x) * kr.x, (vb.y - km.y) * kr.y, (vb.z - km.z) * kr.z, (vb.w - km.w) * kr.w);
+            else if (a.mean != nullptr) vb = make_float4((vb.x - km.x) * kr.x, (vb.y - km.y) * kr.y, (vb.z - km.z) * kr.z, (vb.w - km.w) * kr.w);
             *reinterpret_cast<float4*>(st + off) = va;
             *reinterpret_cast<float4*>(st + kTfTile + off) = make_float4(lo_of(va.x), lo_of(va.y), lo_of(va.z), lo_of(va.w));
             *reinterpret_cast<float4*>(st + 2 * kTfTile + off) = vb;
@@ -217,14 +217,33 @@ __global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs
         for (int k = 0; k < kTfBM * 8 / kTfProducers; ++k) {
             const int idx = tid + k * kTfProducers, r = idx >> 3, piece = idx & 7;
             const int m = m0 + r, n = n0 + 32 * q + 4 * piece;
-            if (m < a.M && n < a.N)        // N is a multiple of 4 (checked by the caller)
-                *reinterpret_cast<float4*>(a.C + (int64_t)blockIdx.z * a.split_stride + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
+            if (m < a.M && n < a.store_n)        // a multiple of 4 (checked by the caller)
+                *reinterpret_cast<float4*>(a.C + (int64_t)slice * a.split_stride + (int64_t)m * a.ldc + n) = *reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(ost) + r * OPITCH + piece * 16);
         }
         named_bar_sync(1, kTfProducers);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+__global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_kernel(const TfArgs a) { gemm_tf32x3_tile<0>(a, blockIdx.x, blockIdx.y, blockIdx.z); }
+
+// batch-major form, a group of products in one launch: blockIdx.x = a 128-column tile of one of them, blockIdx.z = K slice
+__global__ void __launch_bounds__(kTfThreads, 1) gemm_tf32x3_group_kernel(const TfGroup g) {
+    int pi = 0;
+    while (pi + 1 < g.nprob && (int)blockIdx.x >= g.tile0[pi + 1]) ++pi;
+    // the chosen entry goes to registers: a dynamically indexed kernel parameter would be re-read from the constant bank after every barrier
+    TfArgs a;
+    a.A = g.pr[pi].A; a.lda = g.pr[pi].lda;
+    a.B0 = g.pr[pi].B0; a.B1 = nullptr; a.bsplit = 1 << 30; a.ldb = g.pr[pi].ldb;
+    a.bias0 = nullptr; a.bias1 = nullptr; a.biassplit = 1 << 30;
+    a.C = g.pr[pi].C; a.ldc = g.pr[pi].ldc;
+    a.M = g.pr[pi].M; a.N = g.pr[pi].N; a.K = g.pr[pi].K;
+    a.mean = g.pr[pi].mean; a.rstd = g.pr[pi].rstd;
+    a.splits = g.pr[pi].splits; a.split_stride = g.pr[pi].split_stride;
+    a.ones_col = g.pr[pi].ones_col; a.store_n = g.pr[pi].store_n;
+    gemm_tf32x3_tile<1>(a, blockIdx.x - g.tile0[pi], 0, blockIdx.z);
 }
 
 }  // namespace
@@ -236,33 +255,45 @@ bool gemm_tf32x3_ok(const float* A, int lda, const float* B0, const float* B1, i
            (B1 == nullptr || al(B1)) && al(C);
 }
 
-template <int kMode>
-static int tf_launch(const TfArgs& a, cudaStream_t st) {
-    const size_t smem = 128 + kTfStages * (size_t)kTfStage + 128;
+constexpr size_t kTfSmem = 128 + kTfStages * (size_t)kTfStage + 128;
+static bool tf_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int gemm_tf32x3_launch(const TfArgs& a0, cudaStream_t st) {
+    TfArgs a = a0;
+    a.ones_col = -1; a.store_n = a.N;
+    HB_REQUIRE(gemm_tf32x3_ok(a.A, a.lda, a.B0, a.B1, a.ldb, a.C, a.ldc, a.M, a.N, a.K), "gemm_tf32x3: unsupported shape or alignment");
+    HB_REQUIRE(a.splits >= 1 && a.splits <= a.K / kTfBK && (a.splits == 1 || (a.bias0 == nullptr && a.split_stride % 4 == 0)),
+               "gemm_tf32x3: bad K split");
     static bool configured = false;
     if (!configured) {
-        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem));
         configured = true;
     }
-    gemm_tf32x3_kernel<kMode><<<dim3(ceil_div(a.N, kTfBN), ceil_div(a.M, kTfBM), a.splits), kTfThreads, smem, st>>>(a);
+    gemm_tf32x3_kernel<<<dim3(ceil_div(a.N, kTfBN), ceil_div(a.M, kTfBM), a.splits), kTfThreads, kTfSmem, st>>>(a);
     HB_LAUNCHED();
     return HB_OK;
 }
 
-static bool tf_aligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-int gemm_tf32x3_launch(const TfArgs& a, cudaStream_t st) {
-    HB_REQUIRE(gemm_tf32x3_ok(a.A, a.lda, a.B0, a.B1, a.ldb, a.C, a.ldc, a.M, a.N, a.K), "gemm_tf32x3: unsupported shape or alignment");
-    HB_REQUIRE(a.splits >= 1 && a.splits <= a.K / kTfBK && (a.splits == 1 || (a.bias0 == nullptr && a.split_stride % 4 == 0)),
-               "gemm_tf32x3: bad K split");
-    return tf_launch<0>(a, st);
-}
-
-int gemm_tf32x3_launch_batch_major(const TfArgs& a, cudaStream_t st) {
-    HB_REQUIRE(a.M >= 1 && a.N >= 4 && a.K >= 1 && a.N % 4 == 0 && a.ldc % 4 == 0 && tf_aligned(a.C) && a.B1 == nullptr && a.bias0 == nullptr,
-               "gemm_tf32x3 (batch-major): unsupported shape or alignment");
-    HB_REQUIRE(a.splits >= 1 && a.splits <= ceil_div(a.K, kTfBK) && a.split_stride % 4 == 0, "gemm_tf32x3 (batch-major): bad K split");
-    return tf_launch<1>(a, st);
+int gemm_tf32x3_launch_group(TfGroup& g, cudaStream_t st) {
+    HB_REQUIRE(g.nprob >= 1 && g.nprob <= kTfGroupMax, "gemm_tf32x3 (group): bad problem count");
+    int tiles = 0;
+    for (int i = 0; i < g.nprob; ++i) {
+        TfArgs& a = g.pr[i];
+        HB_REQUIRE(a.M >= 1 && a.M <= kTfBM && a.N >= 0 && (a.N >= 1 || a.ones_col >= 0) && (a.ones_col < 0 || a.mean == nullptr) && a.K >= 1 && a.K == g.pr[0].K && a.splits == g.pr[0].splits && a.ldc % 4 == 0 &&
+                       a.store_n % 4 == 0 && tf_aligned(a.C) && a.bias0 == nullptr && a.split_stride % 4 == 0 && a.splits >= 1 &&
+                       a.splits <= ceil_div(a.K, kTfBK),
+                   "gemm_tf32x3 (group): unsupported shape, alignment or K split");
+        g.tile0[i] = tiles;
+        tiles += ceil_div(std::max(a.N, a.ones_col + 1), kTfBN);
+    }
+    static bool configured = false;
+    if (!configured) {
+        HB_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTfSmem));
+        configured = true;
+    }
+    gemm_tf32x3_group_kernel<<<dim3(tiles, 1, g.pr[0].splits), kTfThreads, kTfSmem, st>>>(g);
+    HB_LAUNCHED();
+    return HB_OK;
 }
 
 // C[M, N] = A[M, K] B[N, K]^T + bias (fp32 in and out, 3 x TF32 on tcgen05).  B rows / bias entries at or past `bsplit` come from B1 / bias1.
@@ -276,6 +307,7 @@ int gemm_tf32x3_tn(const float* A, int lda, const float* B0, const float* B1, in
     a.M = M; a.N = N; a.K = K;
     a.mean = nullptr; a.rstd = nullptr;
     a.splits = 1; a.split_stride = 0;
+    a.ones_col = -1; a.store_n = N;
     return gemm_tf32x3_launch(a, st);
 }
 

@@ -51,11 +51,16 @@ struct TfArgs {
     // row statistics folded into the load: K-major form: A(m, k) <- (A(m, k) - mean[m]) rstd[m];  batch-major form: B(k, n) <- (B(k, n) - mean[k]) rstd[k]
     const float* mean; const float* rstd;
     int splits; int64_t split_stride;                           // K slices (blockIdx.z); slice z writes C + z split_stride (no bias when > 1)
+    int ones_col;                                               // batch-major form: B(k, ones_col) = 1 (a column of A's column sums); -1: none
+    int store_n;                                                // columns of C written (>= N to include the ones column; a multiple of 4)
 };
+constexpr int kTfGroupMax = 9;
+struct TfGroup { TfArgs pr[kTfGroupMax]; int tile0[kTfGroupMax]; int nprob; };
 // K-major form:      C[M, N] = A[M][K] B[N][K]^T (+ bias)
 int gemm_tf32x3_launch(const TfArgs& a, cudaStream_t st);
-// batch-major form:  C[M, N] = sum_k A[k][M] B[k][N]   (the weight-gradient shape: both operands stored with the reduction index outermost)
-int gemm_tf32x3_launch_batch_major(const TfArgs& a, cudaStream_t st);
+// batch-major form:  C_p[M, N] = sum_k A_p[k][M] B_p[k][N]   (the weight-gradient shape: both operands stored with the reduction index
+// outermost), a group of products (M <= 128 each, same K and K split) in one launch
+int gemm_tf32x3_launch_group(TfGroup& g, cudaStream_t st);
 
 }  // namespace hb
 

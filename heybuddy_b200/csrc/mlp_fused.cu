@@ -50,26 +50,19 @@ __host__ __device__ constexpr int wot_off(int s) { return s < 3 ? kWoT0 + s * kW
 __host__ __device__ constexpr int whgt_off(int s) { return kWhgT1 + (s - 1) * kWhgTStride; }
 __host__ __device__ constexpr int wi_off(int s) { return kWI1 + (s - 1) * kWIStride; }
 
-// gradient partial sums of the grouped launch: per K slice, [G_1 | G_2 | G_3 | O_0 | O_1 | O_2 | O_3 | row sums]
-constexpr int kGOff1 = 0;                                 // G_s (s = 1..3): [128][96]
-constexpr int kGStride = kHg * kDim;
-constexpr int kOOff0 = 3 * kGStride;                      // O_s (s = 0..2): [96][64];  O_3: [1][64]
-constexpr int kOStride = kDim * kHid;
-constexpr int kOOff3 = kOOff0 + 3 * kOStride;
-constexpr int kRsHg0 = kOOff3 + kHid;                     // column sums of d_hg, stages 0..3: [128] each
-constexpr int kRsO0 = kRsHg0 + 4 * kHg;                   // column sums of d_o, stages 0..2: [96] each; stage 3 (dz): [1]
-constexpr int kPartFloatsPerSlice = ((kRsO0 + 3 * kDim + 1 + 63) / 64) * 64;
-
-constexpr int kGradSlicesMax = 32;
-constexpr int kG0SlicesMax = 16;
+// gradient partial sums of the grouped launch's small products: per K slice, 8 slots of [128][128]
+//   slot 0: column 0 = column sums of d_hg0;  slots 1..3: G_s [128][96] and, in column 96, the column sums of d_hg_s;
+//   slots 4..6: O_s [96][64] (stages 0..2) and, in column 64, the column sums of d_o_s;  slot 7: O_3 [1][64], column 64 = sum of dz
+constexpr int kSlot = 128 * 128;
+constexpr int kSmallFloatsPerSlice = 8 * kSlot;
+constexpr int kGradSlicesMax = 7;
 constexpr int kFwdSlicesMax = 8;
 
 int fwd_slices(int B) {
     const int tiles = ceil_div(B, 128);
     return std::max(1, std::min(kFwdSlicesMax, 148 / tiles));
 }
-int grad_slices(int B) { return std::max(1, std::min(kGradSlicesMax, B / 64)); }
-int g0_slices(int B) { return std::max(1, std::min(std::min(kG0SlicesMax, 12), ceil_div(B, 32) / 4)); }
+int grad_slices(int B) { return std::max(1, std::min(kGradSlicesMax, ceil_div(B, 32) / 4)); }     // 20 tiles x 7 slices = 140 CTAs
 
 struct FusedWs {
     float *w0f, *b0f, *wt, *mean0, *rstd0, *hgpart;
@@ -97,8 +90,8 @@ int64_t carve(FusedWs* w, float* base, int B, int training) {
     if (training) {
         for (int s = 0; s < kStages; ++s) w->dhg[s] = take((int64_t)B * kHg);
         for (int s = 0; s < kStages - 1; ++s) w->dout[s] = take((int64_t)B * kDim);
-        w->part = take((int64_t)grad_slices(B) * kPartFloatsPerSlice);
-        w->g0part = take((int64_t)g0_slices(B) * kHg * kIn);
+        w->part = take((int64_t)grad_slices(B) * kSmallFloatsPerSlice);
+        w->g0part = take((int64_t)grad_slices(B) * kHg * kIn);
     }
     return off;
 }
@@ -541,95 +534,6 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
     }
 }
 
-// ---- grouped weight-gradient products: C_p[M, N] = sum_k A_p[k][m] B_p[k][n], plus the column sums of A_p -----------------------------
-constexpr int kGradProbs = 8;
-struct GradProb {
-    const float* A; const float* B;
-    int M, N, lda, ldb;
-    int part_off, rs_off;       // into a slice of the partial buffer
-    int tile0, tiles_n;
-};
-struct GradArgs {
-    GradProb pr[kGradProbs];
-    int nprob, K, k_per_slice;
-    float* part;
-};
-
-// 128 x 64 tile, 128 threads, 8 x 8 outputs per thread as four 4 x 4 blocks half a tile apart (conflict-free 16-byte reads; a 4 x 4
-// micro-tile ran at half the rate: the shared-memory return path delivers one word per two FMAs there, one per four here)
-constexpr int kGradBK = 16, kGradTM = 128, kGradTN = 64, kGradThreads = 128;
-__global__ void __launch_bounds__(kGradThreads) grads_kernel(const GradArgs g) {
-    __shared__ __align__(16) float As[2][kGradBK][kGradTM];
-    __shared__ __align__(16) float Bs[2][kGradBK][kGradTN];
-    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-    int pi = 0;
-    while (pi + 1 < g.nprob && (int)blockIdx.x >= g.pr[pi + 1].tile0) ++pi;
-    const GradProb& P = g.pr[pi];
-    const int t = blockIdx.x - P.tile0, tm = t / P.tiles_n, tn = t - tm * P.tiles_n;
-    const int m0 = tm * kGradTM, n0 = tn * kGradTN;
-    const int k_begin = blockIdx.y * g.k_per_slice, k_end = min(g.K, k_begin + g.k_per_slice);
-    auto fetch = [&](const float* X, int ld, int dim, int c, int k) {        // 4 words from column c of row k
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (X == nullptr || k >= k_end) return v;
-        const float* src = X + (int64_t)k * ld + c;
-        const int left = dim - c;
-        if (left >= 4 && (ld & 3) == 0) return __ldg(reinterpret_cast<const float4*>(src));
-        if (left > 0) v.x = __ldg(src);
-        if (left > 1) v.y = __ldg(src + 1);
-        if (left > 2) v.z = __ldg(src + 2);
-        if (left > 3) v.w = __ldg(src + 3);
-        return v;
-    };
-    // load slots: A chunk = 16 rows x 32 float4 (4 per thread), B chunk = 16 rows x 16 float4 (2 per thread)
-    float4 va[4], vb[2];
-    auto fetch_chunk = [&](int k0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int slot = tid + q * kGradThreads; va[q] = fetch(P.A, P.lda, P.M, m0 + (slot & 31) * 4, k0 + (slot >> 5)); }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int slot = tid + q * kGradThreads; vb[q] = fetch(P.B, P.ldb, P.N, n0 + (slot & 15) * 4, k0 + (slot >> 4)); }
-    };
-    float acc[8][8] = {};
-    float rsum[8] = {};
-    const bool do_rs = tn == 0 && tx == 0;
-    fetch_chunk(k_begin);
-    int buf = 0;
-    for (int k0 = k_begin; k0 < k_end; k0 += kGradBK) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int slot = tid + q * kGradThreads; *reinterpret_cast<float4*>(&As[buf][slot >> 5][(slot & 31) * 4]) = va[q]; }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int slot = tid + q * kGradThreads; *reinterpret_cast<float4*>(&Bs[buf][slot >> 4][(slot & 15) * 4]) = vb[q]; }
-        __syncthreads();
-        if (k0 + kGradBK < k_end) fetch_chunk(k0 + kGradBK);
-#pragma unroll
-        for (int kk = 0; kk < kGradBK; ++kk) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][kGradTM / 2 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][kGradTN / 2 + tx * 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-                if (do_rs) rsum[i] += av[i];
-            }
-        }
-        buf ^= 1;       // the next chunk goes to the other buffer: one barrier per chunk is enough
-    }
-    float* out = g.part + (int64_t)blockIdx.y * kPartFloatsPerSlice;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i >> 2) * (kGradTM / 2) + ty * 4 + (i & 3);
-        if (m >= P.M) continue;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = n0 + (j >> 2) * (kGradTN / 2) + tx * 4 + (j & 3);
-            if (n < P.N) out[P.part_off + m * P.N + n] = acc[i][j];
-        }
-        if (do_rs) out[P.rs_off + m] = rsum[i];
-    }
-}
-
 // ---- finish: add the K slices up (in slice order, into slice 0), then turn G and db into the parameter gradients -----------------------------
 __global__ void __launch_bounds__(256) slice_sum_kernel(float* __restrict__ part, int n, int slices, int64_t stride, float* __restrict__ part2, int n2,
                                                         int slices2, int64_t stride2) {
@@ -670,9 +574,9 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
         const int t0 = (blockIdx.x - kFinColBlocks) * kFinThreads + tid, stride = kFinOutBlocks * kFinThreads;
         for (int s = 0; s < kStages; ++s) {
             const StageOff& S = f.L.s[s];
-            const int off = s < 3 ? kOOff0 + s * kOStride : kOOff3, rs_off = kRsO0 + s * kDim;
-            for (int i = t0; i < S.out_dim * kHid; i += stride) g[S.ow + i] = part[off + i];
-            for (int n = t0; n < S.out_dim; n += stride) g[S.ob + n] = part[rs_off + n];
+            const float* __restrict__ O = part + (4 + s) * kSlot;
+            for (int i = t0; i < S.out_dim * kHid; i += stride) g[S.ow + i] = O[(i / kHid) * 128 + (i % kHid)];
+            for (int n = t0; n < S.out_dim; n += stride) g[S.ob + n] = O[n * 128 + kHid];
         }
         return;
     }
@@ -682,19 +586,20 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     const StageOff& S = f.L.s[s];
     const int in = S.in_dim;
     if (tid < kHg) {
-        const float v = part[kRsHg0 + s * kHg + tid];
+        const float v = s == 0 ? part[tid * 128] : part[s * kSlot + tid * 128 + kDim];
         db[tid] = v;
         if (kb == 0) g[((tid & 1) ? S.gb : S.hb) + (tid >> 1)] = v;
     }
     __syncthreads();
     const int kx = tid & 31, ny = tid >> 5, k = kb * 32 + kx;
     const float gamma = p[S.ln_w + k], beta = p[S.ln_b + k];
-    const float* __restrict__ G = s == 0 ? f.g0 : part + kGOff1 + (s - 1) * kGStride;
+    const float* __restrict__ G = s == 0 ? f.g0 : part + s * kSlot;
+    const int ldg = s == 0 ? kIn : 128;
     float Gv[kHg / kFinGroups], Wv[kHg / kFinGroups];
 #pragma unroll
     for (int i = 0; i < kHg / kFinGroups; ++i) {
         const int n = ny + kFinGroups * i;
-        Gv[i] = G[(int64_t)n * in + k];
+        Gv[i] = G[(int64_t)n * ldg + k];
         Wv[i] = p[((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k];
     }
     float dgam = 0.f, dbet = 0.f;
@@ -788,39 +693,33 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     bwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(b);
     HB_LAUNCHED();
 
-    // first layer: G_0 = d_hg0^T xhat_0 on the tensor cores, xhat formed from x and the row statistics in the operand load
-    TfArgs t;
-    t.A = w.dhg[0]; t.lda = kHg;
-    t.B0 = x; t.B1 = nullptr; t.bsplit = 1 << 30; t.ldb = kIn;
-    t.bias0 = nullptr; t.bias1 = nullptr; t.biassplit = 1 << 30;
-    t.C = w.g0part; t.ldc = kIn;
-    t.M = kHg; t.N = kIn; t.K = B;
-    t.mean = w.mean0; t.rstd = w.rstd0;
-    t.splits = g0_slices(B); t.split_stride = (int64_t)kHg * kIn;
-    if ((rc = gemm_tf32x3_launch_batch_major(t, st))) return rc;
-
-    GradArgs g;
-    int np = 0, tile = 0;
-    auto add = [&](const float* A, int lda, int M, const float* Bm, int ldb, int N, int part_off, int rs_off) {
-        GradProb& P = g.pr[np++];
-        P.A = A; P.B = Bm; P.M = M; P.N = N; P.lda = lda; P.ldb = ldb; P.part_off = part_off; P.rs_off = rs_off;
-        P.tile0 = tile; P.tiles_n = std::max(1, ceil_div(N, kGradTN));
-        tile += ceil_div(M, kGradTM) * P.tiles_n;
-    };
-    add(w.dhg[0], kHg, kHg, nullptr, 0, 0, 0, kRsHg0);                                                  // column sums only
-    for (int s = 1; s < kStages; ++s) add(w.dhg[s], kHg, kHg, w.xh[s], kDim, kDim, kGOff1 + (s - 1) * kGStride, kRsHg0 + s * kHg);
-    for (int s = 0; s < kStages - 1; ++s) add(w.dout[s], kDim, kDim, w.a[s], kHid, kHid, kOOff0 + s * kOStride, kRsO0 + s * kDim);
-    add(dz, 1, 1, w.a[3], kHid, kHid, kOOff3, kRsO0 + 3 * kDim);
-    g.nprob = np;
-    g.K = B;
+    // every weight-gradient product of the step in one grouped tcgen05 launch: G_0 = d_hg0^T xhat_0 (xhat formed from x and the row
+    // statistics in the operand load), the 96-wide G_s, the output-linear gradients, and -- as a column of ones in the B operand -- the
+    // column sums that are the bias gradients
     const int slices = grad_slices(B);
-    g.k_per_slice = ceil_div(ceil_div(B, slices), kGradBK) * kGradBK;
-    g.part = w.part;
-    const int used = ceil_div(B, g.k_per_slice);
-    grads_kernel<<<dim3(tile, used), kGradThreads, 0, st>>>(g);
-    HB_LAUNCHED();
+    TfGroup grp;
+    int np = 0;
+    auto add = [&](const float* A, int lda, int M, const float* Bm, int ldb, int N, int ones_col, float* C, int ldc, int store_n, int64_t stride) {
+        TfArgs& t = grp.pr[np++];
+        t.A = A; t.lda = lda;
+        t.B0 = Bm; t.B1 = nullptr; t.bsplit = 1 << 30; t.ldb = ldb;
+        t.bias0 = nullptr; t.bias1 = nullptr; t.biassplit = 1 << 30;
+        t.C = C; t.ldc = ldc;
+        t.M = M; t.N = N; t.K = B;
+        t.mean = nullptr; t.rstd = nullptr;
+        t.splits = slices; t.split_stride = stride;
+        t.ones_col = ones_col; t.store_n = store_n;
+    };
+    add(w.dhg[0], kHg, kHg, x, kIn, kIn, -1, w.g0part, kIn, kIn, (int64_t)kHg * kIn);
+    grp.pr[0].mean = w.mean0; grp.pr[0].rstd = w.rstd0;
+    add(w.dhg[0], kHg, kHg, nullptr, 0, 0, 0, w.part, 128, 4, kSmallFloatsPerSlice);
+    for (int s = 1; s < kStages; ++s) add(w.dhg[s], kHg, kHg, w.xh[s], kDim, kDim, kDim, w.part + s * kSlot, 128, kDim + 4, kSmallFloatsPerSlice);
+    for (int s = 0; s < kStages - 1; ++s) add(w.dout[s], kDim, kDim, w.a[s], kHid, kHid, kHid, w.part + (4 + s) * kSlot, 128, kHid + 4, kSmallFloatsPerSlice);
+    add(dz, 1, 1, w.a[3], kHid, kHid, kHid, w.part + 7 * kSlot, 128, kHid + 4, kSmallFloatsPerSlice);
+    grp.nprob = np;
+    if ((rc = gemm_tf32x3_launch_group(grp, st))) return rc;
 
-    slice_sum_kernel<<<296, 256, 0, st>>>(w.part, kPartFloatsPerSlice, used, kPartFloatsPerSlice, w.g0part, kHg * kIn, t.splits, (int64_t)kHg * kIn);
+    slice_sum_kernel<<<296, 256, 0, st>>>(w.part, kSmallFloatsPerSlice, slices, kSmallFloatsPerSlice, w.g0part, kHg * kIn, slices, (int64_t)kHg * kIn);
     HB_LAUNCHED();
     FinArgs fin;
     fin.p = m->p; fin.g = m->g;
