@@ -300,6 +300,58 @@ __global__ void head_finish_kernel(float* __restrict__ stats, const float* __res
     stats[3] = stats[1] / (float)B;
 }
 
+// The single-device training step's whole head in one CTA: sigmoid, high-loss selection, the selected count as the normaliser, weighted
+// BCE and its gradient, the step's statistics (what memset + head_select + head_grad + head_finish do in four launches when the count
+// has to cross ranks in between).  Sums in a fixed order: the reported loss is deterministic.
+__global__ void __launch_bounds__(1024) head_train_kernel(const float* __restrict__ z, const int64_t* __restrict__ y, float* __restrict__ p,
+                                                          float* __restrict__ dz, float* __restrict__ stats, int B, float thr, float neg_w,
+                                                          float loss_scale, int min_selected) {
+    __shared__ float red[32];
+    __shared__ float total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto block_sum = [&](float v) {
+        v = warp_sum(v);
+        __syncthreads();                // the previous use of red / total is over
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            float t = warp_sum(red[lane]);
+            if (lane == 0) total = t;
+        }
+        __syncthreads();
+        return total;
+    };
+    float cnt = 0.f;
+    for (int i = tid; i < B; i += 1024) {
+        const float pr = 1.f / (1.f + expf(-z[i]));
+        p[i] = pr;
+        cnt += ((y[i] == 0 && pr >= thr) || (y[i] == 1 && pr < 1.f - thr)) ? 1.f : 0.f;
+    }
+    const float n_total = block_sum(cnt);
+    const float n_sel = n_total / loss_scale;
+    float l = 0.f;
+    for (int i = tid; i < B; i += 1024) {
+        const float pr = p[i];
+        const bool pos = y[i] == 1;
+        const bool sel = (!pos && pr >= thr) || (pos && pr < 1.f - thr);
+        float g = 0.f;
+        if (sel && n_sel > 0.f) {
+            const float w = pos ? 1.f : neg_w;
+            const float lp = fmaxf(logf(pr), -100.f), l1p = fmaxf(logf(1.f - pr), -100.f);
+            l += -w * (pos ? lp : l1p) / n_sel;
+            g = w * (pr - (pos ? 1.f : 0.f)) / n_sel;
+        }
+        dz[i] = g;
+    }
+    const float loss = block_sum(l);
+    if (tid == 0) {
+        stats[0] = loss;
+        stats[1] = n_total;
+        stats[2] = n_total >= (float)min_selected ? 1.f : 0.f;
+        stats[3] = n_total / (float)B;
+    }
+}
+
 // Column reductions over the batch, two deterministic passes: blockIdx.y owns a slice of the rows and writes its partial sums to
 // scratch [gridDim.y][2][N]; colred_finish_kernel adds the slices in order.  MODE 0: sum_m X[m,n] (bias gradients);
 // MODE 1: LayerNorm parameter gradients, first = sum_m dy * xhat (gamma), second = sum_m dy (beta).
@@ -995,6 +1047,15 @@ extern "C" int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int6
     Ws w;
     carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
     int rc;
+    if (fused_enabled()) {
+        const float* logits = nullptr;
+        if ((rc = forward_impl(m, x_dev, B, w, st, &logits))) return rc;
+        head_train_kernel<<<1, 1024, 0, st>>>(logits, y_dev, prob_dev, w.dz, stats_dev, B, high_loss_threshold, negative_weight, m->loss_scale,
+                                              min_selected);
+        HB_LAUNCHED();
+        if ((rc = mlp_fused_backward(m, x_dev, B, w.fused, w.dz, st))) return rc;
+        return adam_impl(m, lr, stats_dev, st);
+    }
     if ((rc = select_impl(m, x_dev, y_dev, B, high_loss_threshold, prob_dev, stats_dev, w, st))) return rc;
     // single device: the batch's own selection count is the normaliser
     if ((rc = backward_impl(m, x_dev, y_dev, B, negative_weight, high_loss_threshold, stats_dev + 1, min_selected, prob_dev, stats_dev, w, st)))

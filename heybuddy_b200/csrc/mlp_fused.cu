@@ -107,11 +107,12 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 // ---- prep: first-layer fold (interleaved rows) and the transposed small weights ---------------------------------------------------------
 constexpr int kPrepFoldBlocks = kHg / 8;      // 8 warps per block, one stacked row per warp
-__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ p, const Stages L, float* __restrict__ w0f, float* __restrict__ b0f,
-                                                   float* __restrict__ wt) {
+constexpr int kPrepBlocks = kPrepFoldBlocks + 96;
+__device__ __forceinline__ void prep_body(const int block, const float* __restrict__ p, const Stages& L, float* __restrict__ w0f,
+                                          float* __restrict__ b0f, float* __restrict__ wt) {
     const int tid = threadIdx.x, lane = tid & 31;
-    if (blockIdx.x < kPrepFoldBlocks) {
-        const int n = blockIdx.x * 8 + (tid >> 5), j = n >> 1, gate = n & 1;
+    if (block < kPrepFoldBlocks) {
+        const int n = block * 8 + (tid >> 5), j = n >> 1, gate = n & 1;
         const StageOff& S = L.s[0];
         const float* W = p + (gate ? S.gw : S.hw) + j * kIn;
         const float* gamma = p + S.ln_w;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ p, 
         if (lane == 0) b0f[n] = acc + p[(gate ? S.gb : S.hb) + j];
         return;
     }
-    const int t0 = (blockIdx.x - kPrepFoldBlocks) * 256 + tid, stride = (gridDim.x - kPrepFoldBlocks) * 256;
+    const int t0 = (block - kPrepFoldBlocks) * 256 + tid, stride = (kPrepBlocks - kPrepFoldBlocks) * 256;
     for (int s = 0; s < kStages; ++s) {
         const StageOff& S = L.s[s];
         // WoT[j][n] = Wo[n][j]
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ p, 
 }
 
 // mean and 1/std of every input row (LayerNorm(1536) without the affine), one warp per row, the row read once
-__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int B) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void rowstats_body(const int block, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd, int B) {
+    const int row = block * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= B) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * kIn);
     float4 v[kIn / 128];
@@ -168,6 +169,14 @@ __global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__
     }
     const float rs = rsqrtf(warp_sum_f(q) * (1.f / kIn) + kLnEps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
+// one launch for both: the parameter-only blocks first (they are the long ones), then the row statistics
+__global__ void __launch_bounds__(256) pre_kernel(const float* __restrict__ p, const Stages L, float* __restrict__ w0f, float* __restrict__ b0f,
+                                                  float* __restrict__ wt, const float* __restrict__ x, float* __restrict__ mean,
+                                                  float* __restrict__ rstd, int B) {
+    if (blockIdx.x < kPrepBlocks) prep_body(blockIdx.x, p, L, w0f, b0f, wt);
+    else rowstats_body(blockIdx.x - kPrepBlocks, x, mean, rstd, B);
 }
 
 // ---- tail kernels ----------------------------------------------------------------------------------------------------------------------
@@ -227,6 +236,10 @@ __device__ __forceinline__ void plane_fma4(const float* __restrict__ act, const 
     }
 }
 
+// sigmoid / silu on the exp2 unit (ex2.approx, rcp.approx: ~2 ulp each; the step's tolerances are 1e-3 on logits, 2e-3 on gradients)
+__device__ __forceinline__ float sigmoid_fast(float h) { return __fdividef(1.f, 1.f + __expf(-h)); }
+__device__ __forceinline__ float silu_fast(float h) { return __fdividef(h, 1.f + __expf(-h)); }
+
 template <int N>
 __device__ __forceinline__ void load_row(float (&v)[N], const float* __restrict__ src, bool ok) {
     if (N % 4 == 0) {
@@ -277,6 +290,7 @@ struct FwdArgs {
     const float* p; const float* wt; const float* b0f; const float* hgpart; int splits; int64_t split_stride;
     float* hg[kStages]; float* a[kStages]; float* xh[kStages]; float* rstd[kStages]; float* logit;
     int B; int save;
+    long long* stamps;      // profiling aid: clock64 of CTA 0 / thread 0 at the phase boundaries (nullptr: off)
     Stages L;
 };
 
@@ -308,15 +322,19 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
         wp.issue(ml, 1);
     }
     __syncthreads();
+    int n_stamp = 0;
+    auto stamp = [&]() { if (f.stamps != nullptr && blockIdx.x == 0 && tid == 0) f.stamps[n_stamp++] = clock64(); };
+    stamp();
 
-    for (int s = 0; s < kStages; ++s) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {        // unrolled: every per-stage pointer and offset is a fixed kernel-parameter slot
         const StageOff& S = f.L.s[s];
         float hgv[4][kNjHg];
         if (s == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) load_row(hgv[i], f.b0f + cg * kNjHg, true);
             // all four rows of a K slice in flight together; the slices add up in a fixed order
-#pragma unroll 2
+#pragma unroll 4
             for (int z = 0; z < f.splits; ++z) {
                 float t[4][kNjHg];
 #pragma unroll
@@ -328,17 +346,19 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             }
         } else {
             const float* W = wp.acquire(ml, 2 * s - 1, 6);        // ubuf is complete
+            stamp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) load_row(hgv[i], W + kDim * kHg + cg * kNjHg, true);
             plane_fma4<kDim, kNjHg>(ubuf, W, kHg, cg * kNjHg, r0, hgv);
         }
+        stamp();
         float av[4][kNjA];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < kNjA; ++j) {
                 const float h = hgv[i][2 * j], g = hgv[i][2 * j + 1];
-                av[i][j] = h / (1.f + expf(-h)) * g;
+                av[i][j] = silu_fast(h) * g;
             }
         }
 #pragma unroll
@@ -348,7 +368,9 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
         }
         if (s < kStages - 1) {
             store_plane(abuf, cg * kNjA, r0, av);
+            stamp();
             const float* W = wp.acquire(ml, 2 * s, 6);            // abuf is complete
+            stamp();
             const StageOff& N = f.L.s[s + 1];
             float ov[4][kNjO], gam[kNjO], bet[kNjO];
             load_row(gam, f.p + N.ln_w + cg * kNjO, true);
@@ -356,6 +378,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
 #pragma unroll
             for (int i = 0; i < 4; ++i) load_row(ov[i], f.p + S.ob + cg * kNjO, true);
             plane_fma4<kHid, kNjO>(abuf, W, kDim, cg * kNjO, r0, ov);
+            stamp();
             // LayerNorm of the next stage over each row's 96 features (6 per column group)
             float ps[4], mu[4], rs[4];
 #pragma unroll
@@ -392,6 +415,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
                 }
             }
             store_plane(ubuf, cg * kNjO, r0, ov);
+            stamp();
         } else {
             float ps[4], z[4];
 #pragma unroll
@@ -411,6 +435,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             }
         }
     }
+    stamp();
 }
 
 struct BwdArgs {
@@ -454,6 +479,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
     __syncthreads();
 
     int mat = 0;
+#pragma unroll
     for (int s = kStages - 1; s >= 0; --s) {
         const StageOff& S = f.L.s[s];
         // this stage's saved pre-activations: requested before the product that precedes their use
@@ -482,7 +508,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
 #pragma unroll
             for (int j = 0; j < kNjA; ++j) {
                 const float h = hgv[i][2 * j], g = hgv[i][2 * j + 1];
-                const float sg = 1.f / (1.f + expf(-h));
+                const float sg = sigmoid_fast(h);
                 dhv[i][2 * j] = dav[i][j] * g * (sg * (1.f + h * (1.f - sg)));      // d hidden
                 dhv[i][2 * j + 1] = dav[i][j] * h * sg;                             // d gate
             }
@@ -634,6 +660,12 @@ int configure_tail_smem() {
 
 }  // namespace
 
+static long long* g_fwd_stamps = nullptr;
+}  // namespace hb
+// profiling aid (not in the public header): clock64 stamps of CTA 0 of the next forward-tail launches go to `stamps_dev` (32 values; NULL: off)
+extern "C" int hb_debug_mlp_stamps(long long* stamps_dev) { hb::g_fwd_stamps = stamps_dev; return 0; }
+namespace hb {
+
 int mlp_fused_check_timeout() {
     unsigned int flag = 0;
     HB_CUDA_OK(cudaMemcpyFromSymbol(&flag, g_tc_timeout, sizeof(flag)));
@@ -653,9 +685,7 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     FusedWs w;
     carve(&w, ws, B, training);
     const Stages L = stages();
-    prep_kernel<<<kPrepFoldBlocks + 96, 256, 0, st>>>(m->p, L, w.w0f, w.b0f, w.wt);
-    HB_LAUNCHED();
-    rowstats_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x, w.mean0, w.rstd0, B);
+    pre_kernel<<<kPrepBlocks + ceil_div(B, 8), 256, 0, st>>>(m->p, L, w.w0f, w.b0f, w.wt, x, w.mean0, w.rstd0, B);
     HB_LAUNCHED();
     TfArgs t;
     t.A = x; t.lda = kIn;
@@ -671,6 +701,7 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     for (int s = 0; s < kStages; ++s) { f.hg[s] = w.hg[s]; f.a[s] = w.a[s]; f.xh[s] = w.xh[s]; f.rstd[s] = w.rstd[s]; }
     f.logit = w.logit;
     f.B = B; f.save = training;
+    f.stamps = g_fwd_stamps;
     f.L = L;
     fwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(f);
     HB_LAUNCHED();
