@@ -220,7 +220,8 @@ def run_classifier(args):
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         x_bytes = BATCH * 1536 * 4
         alg_bytes = x_bytes + 4 * 256417 * 4          # input + parameters, gradients, two Adam moments
-        flops = 3 * 2 * BATCH * (1536 * 128 + 64 * 96 + 2 * (96 * 128 + 64 * 96) + 96 * 128 + 64)   # fwd + 2 x bwd
+        p_all = 1536 * 128 + 64 * 96 + 2 * (96 * 128 + 64 * 96) + 96 * 128 + 64
+        flops = 2 * BATCH * (3 * p_all - 1536 * 128)   # forward + weight gradients + input gradients (the 1536-wide input gradient is never formed)
         line = {
             "metric": "classifier training rows/sec (batch 4096 per GPU)", "value": world * BATCH * 1e3 / ms, "unit": "rows/s", "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -235,8 +236,9 @@ def run_classifier(args):
             "roofline": {"kernel": "hb_mlp_train_step (whole step)", "bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": src,
                          "algorithmic_bytes_per_step": alg_bytes, "flops_per_step": flops, "achieved_tflops_fp32": flops / (ms * 1e-3) / 1e12,
-                         "note": "fp32 CUDA-core step (logits must stay within 1e-3 of the reference): FLOP-bound on the fp32 pipes long before the 29 MB of "
-                                 "algorithmic traffic matters; nominal fp32 FMA peak 74 TFLOP/s"},
+                         "note": "10 launches per step (csrc/mlp_fused.cu): the 1536-wide products (forward and every weight gradient) on tcgen05 as three TF32 "
+                                 "passes = fp32 accuracy, the row-local 96-wide remainder in two fp32 FMA kernels; latency bound (K slices of 12-19 steps per CTA, "
+                                 "one warp per scheduler in the row-local kernels), not HBM or FLOP bound: DESIGN.md 5.5"},
             "stages": {"ms_per_step_by_batch": stage_ms,
                        "schedule_projection_s": (5000 * stage_ms["4096"] + 10000 * stage_ms["2048"] + 20000 * stage_ms["1024"]) * 1e-3,
                        "schedule": "steps 5000 / 10000 / 20000, batch 4096 / 2048 / 1024, lr 1e-3 x {1, 1/2, 1/4} (trainer.py:918-926)"},
