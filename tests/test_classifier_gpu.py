@@ -74,6 +74,37 @@ def test_train_step_matches_reference_fixture(cuda_device, golden_dir):
         assert np.abs(grads[k] - want).max() <= 2e-3 * np.abs(want).max() + 1e-9, k
 
 
+@pytest.mark.parametrize("batch", [1, 37, 129, 1000, 4101])
+def test_ragged_batches_against_float64_autograd(cuda_device, batch):
+    """Batches that fill neither a 32-row tile, a 128-row GEMM tile nor a 32-row K step, and parameters whose LayerNorm affine is far
+    from (1, 0) -- the fused step folds it into the first-layer weights and derives four gradients per stage from one product."""
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    rng = np.random.Generator(np.random.PCG64(900 + batch))
+    params = {k: np.asarray(v, dtype=np.float32).copy() for k, v in spec.init_classifier_weights(77).items()}
+    for k in params:
+        scale = 0.3 if ("norm" in k or k.endswith(".0.weight") or k.endswith(".0.bias") or k.endswith("bias")) else 0.02
+        params[k] = (params[k] + scale * rng.standard_normal(params[k].shape)).astype(np.float32)
+    x = rng.standard_normal((batch, 16, 96)).astype(np.float32) * (1.0 + rng.random((batch, 1, 1)).astype(np.float32))
+    x += 0.3 * rng.standard_normal((batch, 1, 96)).astype(np.float32)
+    y = (rng.random(batch) < 0.3).astype(np.int64)
+    model = WakeWordMLPModel(device_id=0)
+    model.load_state_dict(params)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    prob, stats = model.train_step(xt, yt, lr=0.0, negative_weight=0.4, high_loss_threshold=1e-4, min_selected=1)
+    want_prob, want_loss, want_n, want = ocls.forward_backward_torch(x, y, params, 0.4, 1e-4)
+    np.testing.assert_allclose(prob.cpu().numpy().reshape(-1), want_prob.reshape(-1), rtol=1e-3, atol=1e-6)
+    loss, n_sel, stepped, rate = stats.tolist()
+    assert int(n_sel) == want_n
+    np.testing.assert_allclose(loss, want_loss, rtol=1e-4)
+    grads = model.gradients()
+    assert set(grads) == set(want)
+    for k, w in want.items():
+        assert np.abs(grads[k] - w).max() <= 5e-4 * np.abs(w).max() + 1e-9, (k, np.abs(grads[k] - w).max(), np.abs(w).max())
+    # inference entry point on the same rows (no activations kept)
+    np.testing.assert_allclose(model(xt).cpu().numpy().reshape(-1), prob.cpu().numpy().reshape(-1), rtol=1e-6, atol=1e-7)
+
+
 def test_adam_update_and_skip_rule(cuda_device, golden_dir):
     from heybuddy_b200.wakeword import WakeWordMLPModel
 
