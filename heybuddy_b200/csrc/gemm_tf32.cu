@@ -32,6 +32,10 @@ constexpr int kTfStage = 4 * kTfTile;                   // A, A_lo, B, B_lo
 
 
 constexpr int kTfStages = 3;
+#ifndef HB_TF_AHEAD
+#define HB_TF_AHEAD 2
+#endif
+constexpr int kTfAhead = HB_TF_AHEAD;      // K steps of global loads in flight per producer thread (register sets)
 
 struct TfHeader {
     uint64_t full[kTfStages], empty[kTfStages];
@@ -81,7 +85,7 @@ __device__ __forceinline__ void gemm_tf32x3_tile(const TfArgs& a, const int tile
     // thread -> 4 (row, chunk) slots of each operand tile.  kMode 0: slot = tid + 256 i, chunk = slot % 8 (a row's 128 bytes are 8 lanes),
     // row = slot / 8.  kMode 1: chunk = warp, row = lane + 32 i (a warp reads 128 consecutive floats of four k rows).
     constexpr int kSlots = kTfBM * kTfChunks / kTfProducers;    // 4
-    float4 ra[2][kSlots], rb[2][kSlots];                        // two register sets: the loads run TWO steps ahead of their use
+    float4 ra[kTfAhead][kSlots], rb[kTfAhead][kSlots];          // register sets: the loads run kTfAhead steps ahead of their use
     auto slot_c = [&](int i) { return kMode == 0 ? ((tid + i * kTfProducers) & (kTfChunks - 1)) : warp; };
     auto slot_r = [&](int i) { return kMode == 0 ? ((tid + i * kTfProducers) / kTfChunks) : (lane + 32 * i); };
     float mu[kSlots], rs[kSlots];
@@ -144,9 +148,10 @@ __device__ __forceinline__ void gemm_tf32x3_tile(const TfArgs& a, const int tile
 
     if (warp < kTfProducers / 32) {
         // ---- producers: step s lives in shared-memory stage s % 3 and register set s % 2 ------------------------------------------
-        float4 km[2], kr[2];
-        load(kbase, ra[0], rb[0], km[0], kr[0]);
-        if (steps > 1) load(kbase + kTfBK, ra[1], rb[1], km[1], kr[1]);
+        float4 km[kTfAhead], kr[kTfAhead];
+#pragma unroll
+        for (int d = 0; d < kTfAhead; ++d)
+            if (d < steps) load(kbase + d * kTfBK, ra[d], rb[d], km[d], kr[d]);
         auto body = [&](int s, float4 (&xa)[kSlots], float4 (&xb)[kSlots], float4& xm, float4& xr) {
             const int sg = s % kTfStages;
             // the stage is free once the MMAs of step s - 3 have completed: warp 0 polls their commit, the producers meet at a barrier
@@ -155,14 +160,15 @@ __device__ __forceinline__ void gemm_tf32x3_tile(const TfArgs& a, const int tile
                 named_bar_sync(1, kTfProducers);
             }
             store(stage0 + sg * kTfStage, xa, xb, xm, xr);
-            if (s + 2 < steps) load(kbase + (s + 2) * kTfBK, xa, xb, xm, xr);      // two steps ahead, in flight across the next iteration
+            if (s + kTfAhead < steps) load(kbase + (s + kTfAhead) * kTfBK, xa, xb, xm, xr);      // in flight across the next iterations
             fence_proxy_async();                                    // generic-proxy stores -> visible to the tensor core
             named_bar_sync(1, kTfProducers);
             if (tid == 0) mbar_arrive(&hdr.full[sg]);
         };
-        for (int s = 0; s < steps; s += 2) {
-            body(s, ra[0], rb[0], km[0], kr[0]);
-            if (s + 1 < steps) body(s + 1, ra[1], rb[1], km[1], kr[1]);
+        for (int s = 0; s < steps; s += kTfAhead) {
+#pragma unroll
+            for (int d = 0; d < kTfAhead; ++d)
+                if (s + d < steps) body(s + d, ra[d], rb[d], km[d], kr[d]);
         }
     } else {
       if (lane == 0) {
