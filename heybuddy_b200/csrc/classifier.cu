@@ -416,10 +416,12 @@ __global__ void ln_bwd_input_kernel(const float* __restrict__ dy, const float* _
 }
 
 // torch.optim.Adam defaults (betas 0.9/0.999, eps 1e-8, no weight decay); a no-op when stats[2] == 0
+// One launch: every block reads the step counter before it can change -- the last block to finish (a ticket kept next to the counter,
+// step[1]) advances it.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int* __restrict__ step, const float* __restrict__ stats, float lr, int n) {
     if (stats[2] == 0.f) return;
-    const int t = *step + 1;
+    const int t = *reinterpret_cast<volatile int*>(step) + 1;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -430,9 +432,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         v[i] = vi;
         p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
     }
-}
-__global__ void adam_step_inc_kernel(int* step, const float* stats) {
-    if (stats[2] != 0.f) *step += 1;
+    __syncthreads();                                     // every thread of this block has read the counter
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(step + 1);
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0;
+            *step = t;
+        }
+    }
 }
 
 }  // namespace hb
@@ -638,12 +646,12 @@ extern "C" int hb_mlp_create(hb_mlp_model** out, const float* params_host, int64
     HB_CUDA_OK(cudaMalloc(&m->g, bytes));
     HB_CUDA_OK(cudaMalloc(&m->m, bytes));
     HB_CUDA_OK(cudaMalloc(&m->v, bytes));
-    HB_CUDA_OK(cudaMalloc(&m->step, sizeof(int)));
+    HB_CUDA_OK(cudaMalloc(&m->step, 2 * sizeof(int)));      // [step, the Adam kernel's block ticket]
     HB_CUDA_OK(cudaMemcpy(m->p, params_host, bytes, cudaMemcpyHostToDevice));
     HB_CUDA_OK(cudaMemset(m->g, 0, bytes));
     HB_CUDA_OK(cudaMemset(m->m, 0, bytes));
     HB_CUDA_OK(cudaMemset(m->v, 0, bytes));
-    HB_CUDA_OK(cudaMemset(m->step, 0, sizeof(int)));
+    HB_CUDA_OK(cudaMemset(m->step, 0, 2 * sizeof(int)));
     *out = m;
     return HB_OK;
 }
@@ -1029,8 +1037,6 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
 
 static int adam_impl(hb_mlp_model* m, float lr, const float* stats_dev, cudaStream_t st) {
     adam_kernel<<<148, 256, 0, st>>>(m->p, m->g, m->m, m->v, m->step, stats_dev, lr, kLayout.total);
-    HB_LAUNCHED();
-    adam_step_inc_kernel<<<1, 1, 0, st>>>(m->step, stats_dev);
     HB_LAUNCHED();
     return HB_OK;
 }

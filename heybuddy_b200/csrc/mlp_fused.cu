@@ -560,32 +560,16 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
     }
 }
 
-// ---- finish: add the K slices up (in slice order, into slice 0), then turn G and db into the parameter gradients -----------------------------
-__global__ void __launch_bounds__(256) slice_sum_kernel(float* __restrict__ part, int n, int slices, int64_t stride, float* __restrict__ part2, int n2,
-                                                        int slices2, int64_t stride2) {
-    const int n4 = n / 4, m4 = n2 / 4;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4 + m4; i += gridDim.x * 256) {
-        float* base = i < n4 ? part + 4 * (int64_t)i : part2 + 4 * (int64_t)(i - n4);
-        const int nz = i < n4 ? slices : slices2;
-        const int64_t st = i < n4 ? stride : stride2;
-        float4 acc = *reinterpret_cast<const float4*>(base);
-#pragma unroll 8
-        for (int z = 1; z < nz; ++z) {
-            const float4 t = *reinterpret_cast<const float4*>(base + z * st);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-        *reinterpret_cast<float4*>(base) = acc;
-    }
-}
-
+// ---- finish: add the K slices up (in slice order) and turn G and db into the parameter gradients --------------------------------------------
 struct FinArgs {
     const float* p; float* g;
-    const float* part;          // slice 0 of the grouped launch's buffer, summed
-    const float* g0;            // slice 0 of the first-layer G, summed
+    const float* part;          // the grouped launch's small products: [slices][8 slots][128][128]
+    const float* g0;            // the first-layer G: [slices][128][1536]
+    int slices;
     Stages L;
 };
 constexpr int kFinColBlocks = kIn / 32 + 3 * (kDim / 32);    // 32 input columns of one stage per block
-constexpr int kFinOutBlocks = 4;
+constexpr int kFinOutBlocks = 8;
 constexpr int kFinThreads = 1024, kFinGroups = kFinThreads / 32;
 
 __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
@@ -595,14 +579,25 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     const float* __restrict__ part = f.part;
     const float* __restrict__ p = f.p;
     float* __restrict__ g = f.g;
+    const int nz = f.slices;
+    // sum over the K slices of one word, slice order, the loads of all slices in flight together
+    auto zsum = [&](const float* __restrict__ base, int64_t stride) {
+        float v[kGradSlicesMax];
+#pragma unroll
+        for (int z = 0; z < kGradSlicesMax; ++z) v[z] = z < nz ? base[z * stride] : 0.f;
+        float t = v[0];
+#pragma unroll
+        for (int z = 1; z < kGradSlicesMax; ++z) t += v[z];
+        return t;
+    };
     if (blockIdx.x >= kFinColBlocks) {
         // output linears: dW_o = O, db_o = column sums of d_o
         const int t0 = (blockIdx.x - kFinColBlocks) * kFinThreads + tid, stride = kFinOutBlocks * kFinThreads;
         for (int s = 0; s < kStages; ++s) {
             const StageOff& S = f.L.s[s];
             const float* __restrict__ O = part + (4 + s) * kSlot;
-            for (int i = t0; i < S.out_dim * kHid; i += stride) g[S.ow + i] = O[(i / kHid) * 128 + (i % kHid)];
-            for (int n = t0; n < S.out_dim; n += stride) g[S.ob + n] = O[n * 128 + kHid];
+            for (int i = t0; i < S.out_dim * kHid; i += stride) g[S.ow + i] = zsum(O + (i / kHid) * 128 + (i % kHid), kSmallFloatsPerSlice);
+            for (int n = t0; n < S.out_dim; n += stride) g[S.ob + n] = zsum(O + n * 128 + kHid, kSmallFloatsPerSlice);
         }
         return;
     }
@@ -612,7 +607,7 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     const StageOff& S = f.L.s[s];
     const int in = S.in_dim;
     if (tid < kHg) {
-        const float v = s == 0 ? part[tid * 128] : part[s * kSlot + tid * 128 + kDim];
+        const float v = zsum(s == 0 ? part + tid * 128 : part + s * kSlot + tid * 128 + kDim, kSmallFloatsPerSlice);
         db[tid] = v;
         if (kb == 0) g[((tid & 1) ? S.gb : S.hb) + (tid >> 1)] = v;
     }
@@ -621,11 +616,12 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
     const float gamma = p[S.ln_w + k], beta = p[S.ln_b + k];
     const float* __restrict__ G = s == 0 ? f.g0 : part + s * kSlot;
     const int ldg = s == 0 ? kIn : 128;
+    const int64_t zstride = s == 0 ? (int64_t)kHg * kIn : kSmallFloatsPerSlice;
     float Gv[kHg / kFinGroups], Wv[kHg / kFinGroups];
 #pragma unroll
     for (int i = 0; i < kHg / kFinGroups; ++i) {
         const int n = ny + kFinGroups * i;
-        Gv[i] = G[(int64_t)n * ldg + k];
+        Gv[i] = zsum(G + (int64_t)n * ldg + k, zstride);
         Wv[i] = p[((n & 1) ? S.gw : S.hw) + (n >> 1) * in + k];
     }
     float dgam = 0.f, dbet = 0.f;
@@ -750,12 +746,11 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     grp.nprob = np;
     if ((rc = gemm_tf32x3_launch_group(grp, st))) return rc;
 
-    slice_sum_kernel<<<296, 256, 0, st>>>(w.part, kSmallFloatsPerSlice, slices, kSmallFloatsPerSlice, w.g0part, kHg * kIn, slices, (int64_t)kHg * kIn);
-    HB_LAUNCHED();
     FinArgs fin;
     fin.p = m->p; fin.g = m->g;
     fin.part = w.part;
     fin.g0 = w.g0part;
+    fin.slices = slices;
     fin.L = L;
     finish_kernel<<<kFinColBlocks + kFinOutBlocks, kFinThreads, 0, st>>>(fin);
     HB_LAUNCHED();

@@ -10,7 +10,7 @@ for r in rows[hdr + 1:]:
         data.append((r[ki].replace("hb::<unnamed>::", "").replace("hb::", "")[:60], float(r[vi].replace(",", "")), r[gi], r[bi]))
     except Exception:
         pass
-idx = [i for i, d in enumerate(data) if "adam_step_inc" in d[0]]
+idx = [i for i, d in enumerate(data) if d[0].startswith("adam_kernel")]
 start, end = idx[-2] + 1, idx[-1]
 tot = 0.0
 for d in data[start:end + 1]:
