@@ -100,6 +100,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "hb_mlp_select": (c_int, [c_vp, c_vp, c_vp, c_int, c_f, c_vp, c_vp, c_vp, c_i64, c_vp]),
         "hb_mlp_backward": (c_int, [c_vp, c_vp, c_vp, c_int, c_f, c_f, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
         "hb_mlp_grads_copy": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
+        "hb_mlp_local_step": (c_int, [c_vp, c_vp, c_vp, c_int, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+        "hb_mlp_apply_exchange": (c_int, [c_vp, c_vp, c_f, c_int, c_vp, c_vp]),
         "hb_mlp_adam": (c_int, [c_vp, c_f, c_vp, c_vp]),
         "hb_mlp_set_loss_scale": (c_int, [c_vp, c_f]),
         "hb_mlp_get_adam": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64]),

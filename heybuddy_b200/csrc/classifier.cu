@@ -305,7 +305,7 @@ __global__ void head_finish_kernel(float* __restrict__ stats, const float* __res
 // has to cross ranks in between).  Sums in a fixed order: the reported loss is deterministic.
 __global__ void __launch_bounds__(1024) head_train_kernel(const float* __restrict__ z, const int64_t* __restrict__ y, float* __restrict__ p,
                                                           float* __restrict__ dz, float* __restrict__ stats, int B, float thr, float neg_w,
-                                                          float loss_scale, int min_selected) {
+                                                          float loss_scale, int min_selected, float* __restrict__ exchange_tail) {
     __shared__ float red[32];
     __shared__ float total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(1024) head_train_kernel(const float* __restric
         cnt += ((y[i] == 0 && pr >= thr) || (y[i] == 1 && pr < 1.f - thr)) ? 1.f : 0.f;
     }
     const float n_total = block_sum(cnt);
-    const float n_sel = n_total / loss_scale;
+    // exchange_tail: the one-collective data-parallel form -- sums stay unnormalised (normaliser 1), the division follows the all-reduce
+    const float n_sel = (exchange_tail != nullptr ? 1.f : n_total) / loss_scale;
     float l = 0.f;
     for (int i = tid; i < B; i += 1024) {
         const float pr = p[i];
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(1024) head_train_kernel(const float* __restric
         stats[1] = n_total;
         stats[2] = n_total >= (float)min_selected ? 1.f : 0.f;
         stats[3] = n_total / (float)B;
+        if (exchange_tail != nullptr) { exchange_tail[0] = loss; exchange_tail[1] = n_total; }
     }
 }
 
@@ -418,14 +420,37 @@ __global__ void ln_bwd_input_kernel(const float* __restrict__ dy, const float* _
 // torch.optim.Adam defaults (betas 0.9/0.999, eps 1e-8, no weight decay); a no-op when stats[2] == 0
 // One launch: every block reads the step counter before it can change -- the last block to finish (a ticket kept next to the counter,
 // step[1]) advances it.
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int* __restrict__ step, const float* __restrict__ stats, float lr, int n) {
-    if (stats[2] == 0.f) return;
+// exchange != nullptr (the one-collective data-parallel form): the gradients are exchange[0, n) / n_total with n_total = exchange[n + 1]
+// (summed over the ranks), the loss exchange[n] / n_total; the model's gradient buffer and stats[0..2] are filled on the way.
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int* __restrict__ step, float* __restrict__ stats, float lr, int n, const float* __restrict__ exchange,
+                            int min_selected) {
+    float gscale = 1.f;
+    bool stepped;
+    if (exchange != nullptr) {
+        const float n_total = exchange[n + 1];
+        gscale = n_total > 0.f ? 1.f / n_total : 0.f;
+        stepped = n_total >= (float)min_selected;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            stats[0] = exchange[n] * gscale;
+            stats[1] = n_total;
+            stats[2] = stepped ? 1.f : 0.f;
+        }
+    } else {
+        stepped = stats[2] != 0.f;
+    }
+    const float* __restrict__ src = exchange != nullptr ? exchange : g;
+    if (!stepped) {
+        if (exchange != nullptr)
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) g[i] = src[i] * gscale;
+        return;
+    }
     const int t = *reinterpret_cast<volatile int*>(step) + 1;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float gi = g[i];
+        const float gi = src[i] * gscale;
+        if (exchange != nullptr) g[i] = gi;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi;
@@ -1036,7 +1061,7 @@ static int backward_impl(hb_mlp_model* m, const float* x_dev, const int64_t* y_d
 }
 
 static int adam_impl(hb_mlp_model* m, float lr, const float* stats_dev, cudaStream_t st) {
-    adam_kernel<<<148, 256, 0, st>>>(m->p, m->g, m->m, m->v, m->step, stats_dev, lr, kLayout.total);
+    adam_kernel<<<148, 256, 0, st>>>(m->p, m->g, m->m, m->v, m->step, const_cast<float*>(stats_dev), lr, kLayout.total, nullptr, 0);
     HB_LAUNCHED();
     return HB_OK;
 }
@@ -1057,7 +1082,7 @@ extern "C" int hb_mlp_train_step(hb_mlp_model* m, const float* x_dev, const int6
         const float* logits = nullptr;
         if ((rc = forward_impl(m, x_dev, B, w, st, &logits))) return rc;
         head_train_kernel<<<1, 1024, 0, st>>>(logits, y_dev, prob_dev, w.dz, stats_dev, B, high_loss_threshold, negative_weight, m->loss_scale,
-                                              min_selected);
+                                              min_selected, nullptr);
         HB_LAUNCHED();
         if ((rc = mlp_fused_backward(m, x_dev, B, w.fused, w.dz, st))) return rc;
         return adam_impl(m, lr, stats_dev, st);
@@ -1094,6 +1119,35 @@ extern "C" int hb_mlp_grads_copy(hb_mlp_model* m, float* buf_dev, int64_t n_floa
     HB_REQUIRE(m && buf_dev && n_floats == kLayout.total, "hb_mlp_grads_copy: expected %d floats", kLayout.total);
     HB_CUDA_OK(cudaMemcpyAsync(to_model ? m->g : buf_dev, to_model ? buf_dev : m->g, (size_t)n_floats * sizeof(float),
                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HB_OK;
+}
+
+// One-collective data-parallel step, first half: forward, selection, UNNORMALISED weighted-BCE sum and gradients of this shard, packed
+// for the exchange: exchange_dev f32 [hb_mlp_num_params() + 2] = {gradients | loss sum | rows selected}.
+extern "C" int hb_mlp_local_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float negative_weight,
+                                 float high_loss_threshold, float* prob_dev, float* stats_dev, float* exchange_dev, void* workspace_dev,
+                                 int64_t workspace_bytes, void* stream) {
+    HB_REQUIRE(m && x_dev && y_dev && prob_dev && stats_dev && exchange_dev && workspace_dev && B > 0, "hb_mlp_local_step: bad argument");
+    HB_REQUIRE(workspace_bytes >= hb_mlp_workspace_bytes(B, 1), "hb_mlp_local_step: workspace too small");
+    HB_REQUIRE(fused_enabled(), "hb_mlp_local_step: not available with HB_MLP_STAGED / HB_MLP_FMA (use hb_mlp_select / hb_mlp_backward)");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w;
+    carve(&w, reinterpret_cast<float*>(workspace_dev), B, 1);
+    int rc;
+    const float* logits = nullptr;
+    if ((rc = forward_impl(m, x_dev, B, w, st, &logits))) return rc;
+    head_train_kernel<<<1, 1024, 0, st>>>(logits, y_dev, prob_dev, w.dz, stats_dev, B, high_loss_threshold, negative_weight, m->loss_scale, 0,
+                                          exchange_dev + kLayout.total);
+    HB_LAUNCHED();
+    return mlp_fused_backward(m, x_dev, B, w.fused, w.dz, st, exchange_dev);
+}
+
+// Second half, after ONE all-reduce (SUM) of exchange_dev: gradients and loss divided by the global count, stats_dev[0..2] = {mean loss
+// over all selected rows, rows selected on all ranks, stepped}, Adam (skipped below min_selected) -- identical on every rank.
+extern "C" int hb_mlp_apply_exchange(hb_mlp_model* m, const float* exchange_dev, float lr, int min_selected, float* stats_dev, void* stream) {
+    HB_REQUIRE(m && exchange_dev && stats_dev, "hb_mlp_apply_exchange: null pointer");
+    adam_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(m->p, m->g, m->m, m->v, m->step, stats_dev, lr, kLayout.total, exchange_dev, min_selected);
+    HB_LAUNCHED();
     return HB_OK;
 }
 

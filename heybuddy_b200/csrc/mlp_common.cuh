@@ -79,7 +79,7 @@ namespace hb {
 int64_t mlp_fused_ws_floats(int B, int training);
 // logits[B] of the batch; with `training` the activations the backward pass needs stay in `ws`
 int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, int training, const float** logits, cudaStream_t st);
-// dz[B] = d loss / d logit  ->  m->g (every parameter)
-int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const float* dz, cudaStream_t st);
+// dz[B] = d loss / d logit  ->  every parameter's gradient, into g_out (packed like the parameters) or, when NULL, the model's own buffer
+int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const float* dz, cudaStream_t st, float* g_out = nullptr);
 
 }  // namespace hb

@@ -705,7 +705,7 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     return HB_OK;
 }
 
-int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const float* dz, cudaStream_t st) {
+int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const float* dz, cudaStream_t st, float* g_out) {
     int rc;
     if ((rc = configure_tail_smem())) return rc;
     FusedWs w;
@@ -747,7 +747,7 @@ int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const 
     if ((rc = gemm_tf32x3_launch_group(grp, st))) return rc;
 
     FinArgs fin;
-    fin.p = m->p; fin.g = m->g;
+    fin.p = m->p; fin.g = g_out != nullptr ? g_out : m->g;
     fin.part = w.part;
     fin.g0 = w.g0part;
     fin.slices = slices;

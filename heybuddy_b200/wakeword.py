@@ -346,6 +346,39 @@ class WakeWordMLPModel:
                           "hb_mlp_grads_copy")
         return buf
 
+    def dp_local_step(self, x, y, negative_weight: float = 1.0, high_loss_threshold: float = DEFAULT_HIGH_LOSS_THRESHOLD):
+        """
+        First half of the one-collective data-parallel step: forward, selection, unnormalised loss sum and gradients of this shard.
+        Returns (prob [b,1], stats f32[4], exchange f32 [n_params + 2] = {gradients | loss sum | rows selected}); all-reduce (SUM)
+        ``exchange`` over the ranks, then ``dp_apply``.
+        """
+        import torch
+
+        x = x.reshape(x.shape[0], -1).contiguous()
+        assert x.is_cuda and x.dtype == torch.float32 and y.is_cuda and y.dtype == torch.int64
+        b = x.shape[0]
+        lib = _native.load()
+        prob = torch.empty((b, 1), dtype=torch.float32, device=x.device)
+        stats = torch.empty(4, dtype=torch.float32, device=x.device)
+        if getattr(self, "_exchange", None) is None or self._exchange.device != x.device:
+            self._exchange = torch.empty(int(lib.hb_mlp_num_params()) + 2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = self._ws(lib.hb_mlp_workspace_bytes(b, 1))
+            _native.check(lib.hb_mlp_local_step(self._ensure(), x.data_ptr(), y.data_ptr(), b, float(negative_weight), float(high_loss_threshold),
+                                                prob.data_ptr(), stats.data_ptr(), self._exchange.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _native.stream_ptr(x.device)), "hb_mlp_local_step")
+        return prob, stats, self._exchange
+
+    def dp_apply(self, exchange, lr: float, min_selected: int, stats):
+        """Second half: divide by the global count, fill stats[0..2] with the global loss / count / stepped flag, Adam."""
+        import torch
+
+        lib = _native.load()
+        with torch.cuda.device(self.device):
+            _native.check(lib.hb_mlp_apply_exchange(self._ensure(), exchange.data_ptr(), float(lr), int(min_selected), stats.data_ptr(),
+                                                    _native.stream_ptr(self.device)), "hb_mlp_apply_exchange")
+        return stats
+
     def dp_adam(self, lr: float, stats):
         """Adam on the (all-reduced) gradient buffer; skipped on the device when stats[2] == 0."""
         import torch

@@ -232,6 +232,18 @@ int hb_mlp_backward(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, i
                     const float* prob_dev, float* stats_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
 int hb_mlp_grads_copy(hb_mlp_model* m, float* buf_dev, int64_t n_floats, int to_model, void* stream);
 int hb_mlp_adam(hb_mlp_model* m, float lr, const float* stats_dev, void* stream);
+/* The same with ONE collective per step: loss and gradients are linear in 1 / n_total, so a rank computes them unnormalised and the
+ * division follows the exchange.
+ *   hb_mlp_local_step      forward, selection, unnormalised loss sum and gradients of this shard ->
+ *                          exchange_dev f32 [hb_mlp_num_params() + 2] = {gradients | loss sum | rows selected};
+ *                          stats_dev[1] / [3] = this shard's selected rows / high-loss rate
+ *   (all-reduce SUM of exchange_dev over the ranks)
+ *   hb_mlp_apply_exchange  gradients (-> the model's gradient buffer) and loss divided by the global count, stats_dev[0..2] = {mean loss,
+ *                          rows selected on all ranks, stepped}, Adam (skipped when the count is below min_selected)
+ * Replaces trainer.py:405-462 on N devices; not available in the HB_MLP_STAGED / HB_MLP_FMA parity modes. */
+int hb_mlp_local_step(hb_mlp_model* m, const float* x_dev, const int64_t* y_dev, int B, float negative_weight, float high_loss_threshold,
+                      float* prob_dev, float* stats_dev, float* exchange_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+int hb_mlp_apply_exchange(hb_mlp_model* m, const float* exchange_dev, float lr, int min_selected, float* stats_dev, void* stream);
 /* The reference divides the loss of the step that finally fires by its accumulation counter (1 + the number of preceding steps
  * that selected fewer than 128 rows and were skipped, trainer.py:441-458): scale = 1 / accumulation_steps, applied to the loss
  * and its gradients of the following hb_mlp_train_step / hb_mlp_backward calls (default 1). */

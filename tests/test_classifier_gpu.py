@@ -105,6 +105,33 @@ def test_ragged_batches_against_float64_autograd(cuda_device, batch):
     np.testing.assert_allclose(model(xt).cpu().numpy().reshape(-1), prob.cpu().numpy().reshape(-1), rtol=1e-6, atol=1e-7)
 
 
+def test_one_collective_step_equals_the_single_device_step(cuda_device):
+    """dp_local_step (unnormalised sums, packed for ONE all-reduce) + dp_apply == train_step: same statistics, gradients, parameters and
+    Adam state (the division by the selected count moves behind the sum: rounding-level differences only), including the skip rule."""
+    from heybuddy_b200.dp import distributed_train_step
+    from heybuddy_b200.wakeword import WakeWordMLPModel
+
+    rng = np.random.Generator(np.random.PCG64(31))
+    a, b = WakeWordMLPModel(device_id=0, seed=9), WakeWordMLPModel(device_id=0, seed=9)
+    for step, (batch, min_sel) in enumerate([(512, 1), (700, 1), (512, 100000), (333, 1)]):
+        x = torch.from_numpy(rng.standard_normal((batch, 16, 96)).astype(np.float32)).cuda()
+        y = torch.from_numpy((rng.random(batch) < 0.2).astype(np.int64)).cuda()
+        pa, sa = a.train_step(x, y, lr=1e-3, negative_weight=0.3, high_loss_threshold=1e-4, min_selected=min_sel)
+        pb, sb = distributed_train_step(b, x, y, 1e-3, 0.3, 1e-4, min_sel, one_collective=True)
+        if step == 0:
+            assert torch.equal(pa, pb)          # same forward kernels on the same parameters
+        np.testing.assert_allclose(pb.cpu().numpy(), pa.cpu().numpy(), rtol=1e-4)
+        np.testing.assert_allclose(sb.cpu().numpy(), sa.cpu().numpy(), rtol=1e-4)
+        assert sb[2].item() == (0.0 if min_sel > batch else 1.0)
+        ga, gb = a.gradients(), b.gradients()
+        for k in ga:
+            np.testing.assert_allclose(gb[k], ga[k], rtol=1e-5, atol=2e-6 * np.abs(ga[k]).max(), err_msg=f"step {step} {k}")
+    sda, sdb = a.state_dict(), b.state_dict()
+    for k in sda:
+        # Adam divides by sqrt(v): a rounding-level difference in a near-zero gradient moves its parameter by a fraction of lr
+        np.testing.assert_allclose(sdb[k].numpy(), sda[k].numpy(), rtol=1e-4, atol=5e-5, err_msg=k)
+
+
 def test_adam_update_and_skip_rule(cuda_device, golden_dir):
     from heybuddy_b200.wakeword import WakeWordMLPModel
 
