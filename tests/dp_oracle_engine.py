@@ -47,6 +47,31 @@ class OracleEngine:
             return buf
         return torch.from_numpy(np.concatenate([self.grads[k].reshape(-1) for k in self.names]).astype(np.float32))
 
+    # the one-collective form: unnormalised sums [gradients | loss sum | rows selected], divided after the exchange
+    def dp_local_step(self, x, y, negative_weight, thr):
+        prob, stats = self.dp_select(x, y, thr)
+        xn, yn = self._xy
+        _, loss, n_sel, grads = ocls.forward_backward_torch(xn, yn, self.params, negative_weight, thr)
+        self.grads = grads
+        flat = np.concatenate([grads[k].reshape(-1) * n_sel for k in self.names] + [np.array([loss * n_sel, n_sel], dtype=np.float64)])
+        stats[3] = n_sel / xn.shape[0]
+        return prob, stats, torch.from_numpy(flat.astype(np.float32))
+
+    def dp_apply(self, exchange, lr, min_selected, stats):
+        flat = exchange.numpy().astype(np.float64)
+        n_total = flat[-1]
+        scale = 1.0 / n_total if n_total > 0 else 0.0
+        o = 0
+        for k in self.names:
+            n = self.grads[k].size
+            self.grads[k] = flat[o:o + n].reshape(self.grads[k].shape) * scale
+            o += n
+        stats[0] = flat[-2] * scale
+        stats[1] = n_total
+        stats[2] = 1.0 if n_total >= min_selected else 0.0
+        self.dp_adam(lr, stats)
+        return stats
+
     def dp_adam(self, lr, stats):
         if float(stats[2]) == 0.0:
             return

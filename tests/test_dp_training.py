@@ -34,11 +34,16 @@ WORKER = textwrap.dedent("""
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     eng = OracleEngine()
+    packed = OracleEngine()
     single = OracleEngine()
     for step in range(3):
         x, y = _batch(100 + step)
         xs, ys = shard_batch(torch.from_numpy(x), torch.from_numpy(y), rank, world)
-        _, stats = distributed_train_step(eng, xs, ys, 1e-3, negative_weight=0.7, high_loss_threshold=1e-4, min_selected=16)
+        _, stats = distributed_train_step(eng, xs, ys, 1e-3, negative_weight=0.7, high_loss_threshold=1e-4, min_selected=16, one_collective=False)
+        # the one-collective form (unnormalised sums, ONE all-reduce, division afterwards) gives the same global statistics
+        _, stats1 = distributed_train_step(packed, xs, ys, 1e-3, negative_weight=0.7, high_loss_threshold=1e-4, min_selected=16, one_collective=True)
+        assert float(stats1[1]) == float(stats[1]) and float(stats1[2]) == float(stats[2])
+        assert abs(float(stats1[0]) - float(stats[0])) < 1e-5 * max(1.0, abs(float(stats[0])))
         # the same global batch on one "device"
         _, st1 = single.dp_select(torch.from_numpy(x), torch.from_numpy(y), 1e-4)
         st1 = single.dp_backward(st1[1:2].clone(), 0.7, 1e-4, 16)
@@ -48,6 +53,8 @@ WORKER = textwrap.dedent("""
     # the all-reduced gradients travel as f32 (like NCCL on the GPU): agreement to f32 rounding of the update
     d = np.abs(eng.flat_params() - single.flat_params()).max()
     assert d < 2e-6, d
+    d1 = np.abs(packed.flat_params() - single.flat_params()).max()
+    assert d1 < 5e-6, d1
     gathered = [None] * world
     dist.all_gather_object(gathered, float(np.abs(eng.flat_params()).sum()))
     assert len(set(gathered)) == 1, gathered          # replicas identical on every rank
