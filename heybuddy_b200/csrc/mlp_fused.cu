@@ -106,26 +106,30 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 // ---- prep: first-layer fold (interleaved rows) and the transposed small weights ---------------------------------------------------------
-constexpr int kPrepFoldBlocks = kHg / 8;      // 8 warps per block, one stacked row per warp
+constexpr int kPrepFoldBlocks = kHg / 2;      // two stacked rows per block, four warps (a quarter of the 1536 columns each) per row
 constexpr int kPrepBlocks = kPrepFoldBlocks + 96;
 __device__ __forceinline__ void prep_body(const int block, const float* __restrict__ p, const Stages& L, float* __restrict__ w0f,
                                           float* __restrict__ b0f, float* __restrict__ wt) {
     const int tid = threadIdx.x, lane = tid & 31;
     if (block < kPrepFoldBlocks) {
-        const int n = block * 8 + (tid >> 5), j = n >> 1, gate = n & 1;
+        __shared__ float part[8];
+        const int warp = tid >> 5, n = block * 2 + (warp >> 2), j = n >> 1, gate = n & 1, k0 = (warp & 3) * (kIn / 4);
         const StageOff& S = L.s[0];
         const float* W = p + (gate ? S.gw : S.hw) + j * kIn;
         const float* gamma = p + S.ln_w;
         const float* beta = p + S.ln_b;
         float acc = 0.f;
-#pragma unroll 8
-        for (int k = lane; k < kIn; k += 32) {
+#pragma unroll
+        for (int i = 0; i < kIn / 4 / 32; ++i) {
+            const int k = k0 + lane + 32 * i;
             const float w = W[k];
             w0f[n * kIn + k] = w * gamma[k];
             acc = fmaf(w, beta[k], acc);
         }
         acc = warp_sum_f(acc);
-        if (lane == 0) b0f[n] = acc + p[(gate ? S.gb : S.hb) + j];
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if ((warp & 3) == 0 && lane == 0) b0f[n] = ((part[warp] + part[warp + 1]) + (part[warp + 2] + part[warp + 3])) + p[(gate ? S.gb : S.hb) + j];
         return;
     }
     const int t0 = (block - kPrepFoldBlocks) * 256 + tid, stride = (kPrepBlocks - kPrepFoldBlocks) * 256;
