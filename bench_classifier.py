@@ -356,7 +356,9 @@ def run_stream(args):
             "roofline": {"kernel": "hb_mlp_forward_multi (stacked first-layer GEMM + batched remainder)", "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
                          "unit": "GB/s", "frac": None, "traffic": None, "peak_source": src, "classifier_flops_per_step": flops,
                          "classifier_tflops_fp32": flops / (cls_ms * 1e-3) / 1e12,
-                         "note": "fp32 CUDA-core GEMMs: FLOP-bound (nominal fp32 FMA peak 74 TFLOP/s), not HBM-bound"},
+                         "note": "the stacked [64 x 128, 1536] first-layer product (78 % of the FLOPs) runs on tcgen05 as three TF32 passes (150 TFLOP/s "
+                                 "fp32-equivalent); the 96-wide remainder of every model is fp32 FMA GEMMs batched over the models and takes most of the time: "
+                                 "FLOP / latency bound, not HBM bound"},
             "stages": {"featurize_ms": feat_ms, "classifiers_ms": cls_ms, "one_hour_projection_s": 3600.0 / (seg_seconds / (ms * 1e-3))},
             "output_checksum": float(probs.mean().item()),
         }
