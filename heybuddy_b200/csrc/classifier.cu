@@ -797,7 +797,7 @@ extern "C" int hb_mlp_forward(const hb_mlp_model* m, const float* x_dev, float* 
 // models (blockIdx.z = model).  The fold is redone on every call (it reads the models' live parameters; 1 MB per model).
 namespace hb {
 
-constexpr int kMaxPack = 64;
+constexpr int kMaxPack = kMlpMaxPack;
 struct PtrPack { const float* p[kMaxPack]; };
 
 // xhat = (x - mean) * rstd, one warp per row (LayerNorm without the affine)
@@ -912,6 +912,7 @@ __global__ void __launch_bounds__(256) linear_batched_kernel(const float* __rest
 struct MultiWs {
     float *xhat, *Wst, *bst, *hg, *a, *o, *u, *h, *g;
     float* part;
+    float* wt;       // transposed small weights of one pack of models (mlp_fused.cu)
 };
 static int64_t carve_multi(MultiWs* w, float* base, int M, int B) {
     int64_t off = 0;
@@ -926,6 +927,7 @@ static int64_t carve_multi(MultiWs* w, float* base, int M, int B) {
     w->h = take((int64_t)M * B * kHid);
     w->g = take((int64_t)M * B * kHid);
     w->part = take(kPartFloats);
+    w->wt = take(mlp_fused_multi_wt_floats(std::min(M, kMaxPack)));
     return off;
 }
 
@@ -963,6 +965,20 @@ extern "C" int hb_mlp_forward_multi(hb_mlp_model* const* models, int M, const fl
     }
     // 3. ONE stacked GEMM: hidden and gate pre-activations of every model
     if ((rc = linear_fwd(w.xhat, w.Wst, w.bst, w.hg, B, M * 2 * kHid, kIn, st, w.part))) return rc;
+    if (fused_enabled()) {
+        // 4. the 96-wide remainder of every model: one forward-tail CTA per (32 rows, model), the stacked output read in place
+        for (int m0 = 0; m0 < M; m0 += kMaxPack) {
+            const int n = std::min(kMaxPack, M - m0);
+            const float* params[kMaxPack];
+            for (int i = 0; i < n; ++i) params[i] = models[m0 + i]->p;
+            float* logits = w.o + (int64_t)m0 * B;      // [n][B]
+            if ((rc = mlp_fused_multi_tail(params, n, w.hg + (int64_t)m0 * 2 * kHid, (int64_t)M * 2 * kHid, B, w.wt, logits, st))) return rc;
+            const int total = n * B;
+            sigmoid_kernel<<<ceil_div(total, 256), 256, 0, st>>>(logits, prob_dev + (int64_t)m0 * B, total);
+            HB_LAUNCHED();
+        }
+        return HB_OK;
+    }
     const int64_t n_gate = (int64_t)B * M * kHid;
     const int gate_grid = (int)std::min<int64_t>(ceil_div64(n_gate, 256), 2368);
     gate_stacked_kernel<<<gate_grid, 256, 0, st>>>(w.hg, w.a, B, M);

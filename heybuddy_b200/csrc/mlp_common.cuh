@@ -7,6 +7,7 @@ namespace hb {
 
 constexpr int kIn = 1536, kDim = 96, kHid = 64, kStages = 4;  // stages: mlp_in, layers.0, layers.1, mlp_out
 constexpr float kLnEps = 1e-5f;
+constexpr int kMlpMaxPack = 64;                       // models per launch of the multi-model kernels (their pointers travel as kernel arguments)
 
 struct StageOff {     // float offsets into the packed parameter vector
     int ln_w, ln_b, in_dim, out_dim;
@@ -79,6 +80,9 @@ namespace hb {
 int64_t mlp_fused_ws_floats(int B, int training);
 // logits[B] of the batch; with `training` the activations the backward pass needs stay in `ws`
 int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, int training, const float** logits, cudaStream_t st);
+// the multi-model forward's remainder (config 5): see mlp_fused.cu
+int64_t mlp_fused_multi_wt_floats(int n_models);
+int mlp_fused_multi_tail(const float* const* params, int n, const float* hg, int64_t ld, int B, float* wt_all, float* logits, cudaStream_t st);
 // dz[B] = d loss / d logit  ->  every parameter's gradient, into g_out (packed like the parameters) or, when NULL, the model's own buffer
 int mlp_fused_backward(hb_mlp_model* m, const float* x, int B, float* ws, const float* dz, cudaStream_t st, float* g_out = nullptr);
 

@@ -183,6 +183,12 @@ __global__ void __launch_bounds__(256) pre_kernel(const float* __restrict__ p, c
     else rowstats_body(blockIdx.x - kPrepBlocks, x, mean, rstd, B);
 }
 
+// the transposed small weights of n models (blockIdx.y = model) for the multi-model forward tail
+struct ModelList { const float* p[kMlpMaxPack]; };
+__global__ void __launch_bounds__(256) prep_multi_kernel(const ModelList ml, const Stages L, float* __restrict__ wt_all) {
+    prep_body(kPrepFoldBlocks + blockIdx.x, ml.p[blockIdx.y], L, nullptr, nullptr, wt_all + (int64_t)blockIdx.y * kWtFloats);
+}
+
 // ---- tail kernels ----------------------------------------------------------------------------------------------------------------------
 // One CTA = 32 rows; 128 threads, thread (rq, cg) = rows 4 rq .. 4 rq + 3 x one of 16 column groups: a 4 x NJ register tile per product
 // (NJ = 8 pre-activations = 4 gates, 6 outputs, 4 gated activations), so each 16-byte shared-memory read feeds 16 - 32 FMAs (a 1 x NJ tile
@@ -190,17 +196,18 @@ __global__ void __launch_bounds__(256) pre_kernel(const float* __restrict__ p, c
 // [feature][row] planes; the weight matrices arrive by cp.async.bulk into two buffers, matrix i + 1 in flight while matrix i is used.
 constexpr int kMatFloats = kDim * kHg + kHg;              // the largest staged matrix: [96][128] + its bias
 constexpr int kRed = 16 * kRows;
-constexpr int kTailSmemFloats = 2 * kMatFloats + kHg * kRows + kDim * kRows + 2 * kRed;
+constexpr int kSmallMatFloats = kDim * kHid;              // the other matrices: [64][96] / [96][64]; large and small ones alternate in both kernels
+constexpr int kTailSmemFloats = kMatFloats + kSmallMatFloats + kHg * kRows + kDim * kRows + 2 * kRed;      // 107 KB: two CTAs per SM
 constexpr int kTailSmemBytes = 128 + kTailSmemFloats * 4;
 
 struct MatList { const float* src[6]; int floats[6]; };
 
 struct WeightPipe {
     uint64_t* bar;      // [2]
-    float* buf;         // [2][kMatFloats]
+    float* buf[2];      // even / odd matrices of the list (one holds the large ones, the other the small ones)
     __device__ __forceinline__ void issue(const MatList& ml, int i) {
         mbar_expect_tx(&bar[i & 1], (uint32_t)ml.floats[i] * 4u);
-        bulk_g2s(buf + (i & 1) * kMatFloats, ml.src[i], (uint32_t)ml.floats[i] * 4u, &bar[i & 1]);
+        bulk_g2s(buf[i & 1], ml.src[i], (uint32_t)ml.floats[i] * 4u, &bar[i & 1]);
     }
     // matrix i is in its buffer and everything every thread wrote to shared memory before this call is visible; matrix i - 1 is no longer
     // needed by anyone, so its buffer takes matrix i + 1
@@ -208,7 +215,7 @@ struct WeightPipe {
         if (threadIdx.x < 32) mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u, 16u + i);
         __syncthreads();
         if (threadIdx.x == 0 && i >= 1 && i + 1 < n) issue(ml, i + 1);
-        return buf + (i & 1) * kMatFloats;
+        return buf[i & 1];
     }
 };
 
@@ -296,28 +303,36 @@ struct FwdArgs {
     int B; int save;
     long long* stamps;      // profiling aid: clock64 of CTA 0 / thread 0 at the phase boundaries (nullptr: off)
     Stages L;
+    // multi-model form (blockIdx.y = model): parameters of every model, transposed weights at wt + model * kWtFloats, the stacked
+    // first-layer output hgpart [B][ld] with model m's [hidden 64 | gate 64] at column m * 128 (bias included), logits [model][B]
+    const float* plist[kMlpMaxPack];
+    int64_t ld;
 };
 
 // first-layer pre-activations (K slices) -> logits
-__global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs f) {
+template <bool kMulti>
+__global__ void __launch_bounds__(kTailThreads, 2) fwd_tail_kernel(const FwdArgs f) {
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw);
     float* sm = reinterpret_cast<float*>(smraw + 128);
-    float* abuf = sm + 2 * kMatFloats;             // gated activations [64][32]
+    float* abuf = sm + kMatFloats + kSmallMatFloats;   // gated activations [64][32]
     float* ubuf = abuf + kHg * kRows;              // stage input [96][32]
     float* red = ubuf + kDim * kRows;              // [2][16][32]
     const int tid = threadIdx.x, rq = tid & 7, cg = tid >> 3, r0 = 4 * rq;
     const int row0 = blockIdx.x * kRows + r0;
     bool ok[4], save[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ok[i] = row0 + i < f.B; save[i] = ok[i] && f.save; }
+    for (int i = 0; i < 4; ++i) { ok[i] = row0 + i < f.B; save[i] = ok[i] && f.save && !kMulti; }
+    const int model = kMulti ? blockIdx.y : 0;
+    const float* __restrict__ P = kMulti ? f.plist[model] : f.p;
+    const float* __restrict__ WT = f.wt + (int64_t)model * kWtFloats;
 
     MatList ml;
     for (int s = 0; s < 3; ++s) {
-        ml.src[2 * s] = f.wt + wot_off(s); ml.floats[2 * s] = kHid * kDim;
-        ml.src[2 * s + 1] = f.wt + whgt_off(s + 1); ml.floats[2 * s + 1] = kMatFloats;
+        ml.src[2 * s] = WT + wot_off(s); ml.floats[2 * s] = kHid * kDim;
+        ml.src[2 * s + 1] = WT + whgt_off(s + 1); ml.floats[2 * s + 1] = kMatFloats;
     }
-    WeightPipe wp{bars, sm};
+    WeightPipe wp{bars, {sm + kMatFloats, sm}};          // even matrices (W_o) are the small ones
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -334,7 +349,18 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
     for (int s = 0; s < kStages; ++s) {        // unrolled: every per-stage pointer and offset is a fixed kernel-parameter slot
         const StageOff& S = f.L.s[s];
         float hgv[4][kNjHg];
-        if (s == 0) {
+        if (s == 0 && kMulti) {
+            // the stacked product's row: this model's hidden columns, then its gate columns; bias included
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float h[kNjA], g[kNjA];
+                const float* src = f.hgpart + (int64_t)(row0 + i) * f.ld + model * kHg + cg * kNjA;
+                load_row(h, src, ok[i]);
+                load_row(g, src + kHid, ok[i]);
+#pragma unroll
+                for (int j = 0; j < kNjA; ++j) { hgv[i][2 * j] = h[j]; hgv[i][2 * j + 1] = g[j]; }
+            }
+        } else if (s == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) load_row(hgv[i], f.b0f + cg * kNjHg, true);
             // all four rows of a K slice in flight together; the slices add up in a fixed order
@@ -377,10 +403,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             stamp();
             const StageOff& N = f.L.s[s + 1];
             float ov[4][kNjO], gam[kNjO], bet[kNjO];
-            load_row(gam, f.p + N.ln_w + cg * kNjO, true);
-            load_row(bet, f.p + N.ln_b + cg * kNjO, true);
+            load_row(gam, P + N.ln_w + cg * kNjO, true);
+            load_row(bet, P + N.ln_b + cg * kNjO, true);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) load_row(ov[i], f.p + S.ob + cg * kNjO, true);
+            for (int i = 0; i < 4; ++i) load_row(ov[i], P + S.ob + cg * kNjO, true);
             plane_fma4<kHid, kNjO>(abuf, W, kDim, cg * kNjO, r0, ov);
             stamp();
             // LayerNorm of the next stage over each row's 96 features (6 per column group)
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             for (int i = 0; i < 4; ++i) {
                 ps[i] = 0.f;
 #pragma unroll
-                for (int j = 0; j < kNjA; ++j) ps[i] = fmaf(av[i][j], __ldg(f.p + S.ow + cg * kNjA + j), ps[i]);
+                for (int j = 0; j < kNjA; ++j) ps[i] = fmaf(av[i][j], __ldg(P + S.ow + cg * kNjA + j), ps[i]);
             }
             __syncthreads();                       // the previous stage's reads of `red` are over
             red_put(red, cg, r0, ps);
@@ -435,7 +461,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) fwd_tail_kernel(const FwdArgs
             if (cg == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (ok[i]) f.logit[row0 + i] = z[i] + __ldg(f.p + S.ob);
+                    if (ok[i]) f.logit[(int64_t)model * f.B + row0 + i] = z[i] + __ldg(P + S.ob);
             }
         }
     }
@@ -451,11 +477,11 @@ struct BwdArgs {
 };
 
 // d loss / d logit -> d_hg of every stage and d_o of stages 0..2 (what the weight-gradient products read)
-__global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs f) {
+__global__ void __launch_bounds__(kTailThreads, 2) bwd_tail_kernel(const BwdArgs f) {
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smraw);
     float* sm = reinterpret_cast<float*>(smraw + 128);
-    float* dbuf = sm + 2 * kMatFloats;             // d_hg plane [128][32]
+    float* dbuf = sm + kMatFloats + kSmallMatFloats;   // d_hg plane [128][32]
     float* dobuf = dbuf + kHg * kRows;             // d_o plane [96][32]
     float* red = dobuf + kDim * kRows;
     const int tid = threadIdx.x, rq = tid & 7, cg = tid >> 3, r0 = 4 * rq;
@@ -472,7 +498,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) bwd_tail_kernel(const BwdArgs
     ml.src[3] = f.p + f.L.s[1].ow; ml.floats[3] = kDim * kHid;
     ml.src[4] = f.wt + wi_off(1); ml.floats[4] = kHg * kDim;
     ml.src[5] = f.p + f.L.s[0].ow; ml.floats[5] = kDim * kHid;
-    WeightPipe wp{bars, sm};
+    WeightPipe wp{bars, {sm, sm + kMatFloats}};          // even matrices (W_I) are the large ones
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -651,7 +677,8 @@ __global__ void __launch_bounds__(kFinThreads) finish_kernel(const FinArgs f) {
 int configure_tail_smem() {
     static bool done = false;
     if (!done) {
-        HB_CUDA_OK(cudaFuncSetAttribute(fwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        HB_CUDA_OK(cudaFuncSetAttribute(fwd_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        HB_CUDA_OK(cudaFuncSetAttribute(fwd_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
         HB_CUDA_OK(cudaFuncSetAttribute(bwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
         done = true;
     }
@@ -703,9 +730,36 @@ int mlp_fused_forward(const hb_mlp_model* m, const float* x, int B, float* ws, i
     f.B = B; f.save = training;
     f.stamps = g_fwd_stamps;
     f.L = L;
-    fwd_tail_kernel<<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(f);
+    f.ld = 0;
+    fwd_tail_kernel<false><<<ceil_div(B, kRows), kTailThreads, kTailSmemBytes, st>>>(f);
     HB_LAUNCHED();
     *logits = w.logit;
+    return HB_OK;
+}
+
+int64_t mlp_fused_multi_wt_floats(int n_models) { return (int64_t)n_models * kWtFloats; }
+
+// The 96-wide remainder of n <= 64 models behind ONE stacked first-layer product: hg [B][ld], model i's [hidden 64 | gate 64]
+// pre-activations (bias included) at column i * 128  ->  logits [n][B].  One forward-tail CTA per (32 rows, model).
+int mlp_fused_multi_tail(const float* const* params, int n, const float* hg, int64_t ld, int B, float* wt_all, float* logits, cudaStream_t st) {
+    HB_REQUIRE(n >= 1 && n <= kMlpMaxPack && ld % 4 == 0, "classifier (multi): bad model count or row stride");
+    int rc;
+    if ((rc = configure_tail_smem())) return rc;
+    const Stages L = stages();
+    ModelList ml;
+    FwdArgs f;
+    for (int i = 0; i < n; ++i) { ml.p[i] = params[i]; f.plist[i] = params[i]; }
+    prep_multi_kernel<<<dim3(kPrepBlocks - kPrepFoldBlocks, n), 256, 0, st>>>(ml, L, wt_all);
+    HB_LAUNCHED();
+    f.p = nullptr; f.wt = wt_all; f.b0f = nullptr; f.hgpart = hg; f.splits = 1; f.split_stride = 0;
+    for (int s = 0; s < kStages; ++s) { f.hg[s] = nullptr; f.a[s] = nullptr; f.xh[s] = nullptr; f.rstd[s] = nullptr; }
+    f.logit = logits;
+    f.B = B; f.save = 0;
+    f.stamps = nullptr;
+    f.L = L;
+    f.ld = ld;
+    fwd_tail_kernel<true><<<dim3(ceil_div(B, kRows), n), kTailThreads, kTailSmemBytes, st>>>(f);
+    HB_LAUNCHED();
     return HB_OK;
 }
 
