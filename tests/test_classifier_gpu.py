@@ -111,6 +111,8 @@ def test_one_collective_step_equals_the_single_device_step(cuda_device):
     from heybuddy_b200.dp import distributed_train_step
     from heybuddy_b200.wakeword import WakeWordMLPModel
 
+    if os.environ.get("HB_MLP_STAGED", "")[:1] == "1" or os.environ.get("HB_MLP_FMA", "")[:1] == "1":
+        pytest.skip("the one-collective entry points belong to the fused step (not built in the per-operation parity modes)")
     rng = np.random.Generator(np.random.PCG64(31))
     a, b = WakeWordMLPModel(device_id=0, seed=9), WakeWordMLPModel(device_id=0, seed=9)
     for step, (batch, min_sel) in enumerate([(512, 1), (700, 1), (512, 100000), (333, 1)]):
