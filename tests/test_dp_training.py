@@ -75,6 +75,28 @@ def test_two_rank_dp_step_gloo(tmp_path):
     assert "DP OK" in res.stdout
 
 
+def test_one_collective_is_chosen_only_for_engines_that_have_it(monkeypatch):
+    """dp.py picks the packed protocol when the engine offers dp_local_step / dp_apply and no parity mode is requested."""
+    import sys as _sys
+
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dp_oracle_engine import OracleEngine
+
+    from heybuddy_b200 import dp
+
+    class TwoCollectiveOnly:
+        dp_select = dp_backward = dp_grads = dp_adam = None
+
+    monkeypatch.delenv("HB_MLP_STAGED", raising=False)
+    monkeypatch.delenv("HB_MLP_FMA", raising=False)
+    assert dp._one_collective(OracleEngine()) and not dp._one_collective(TwoCollectiveOnly())
+    monkeypatch.setenv("HB_MLP_STAGED", "1")
+    assert not dp._one_collective(OracleEngine())
+    monkeypatch.delenv("HB_MLP_STAGED")
+    monkeypatch.setenv("HB_MLP_FMA", "1")
+    assert not dp._one_collective(OracleEngine())
+
+
 def test_shard_batch_covers_every_row_once():
     import torch
 
