@@ -32,6 +32,18 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert native_lib.hb_mlp_num_params() == 256417
 
 
+def test_workspace_size_queries_are_host_only_and_consistent(native_lib):
+    """Size queries need no device: a training workspace holds what the backward pass reads, so it exceeds the inference one; both grow
+    with the batch; the multi-model one with the model count; bad arguments are errors, not sizes."""
+    inf = [native_lib.hb_mlp_workspace_bytes(b, 0) for b in (1, 64, 4096)]
+    trn = [native_lib.hb_mlp_workspace_bytes(b, 1) for b in (1, 64, 4096)]
+    assert all(a > 0 for a in inf) and inf == sorted(inf) and trn == sorted(trn)
+    assert all(t > i for t, i in zip(trn, inf))
+    assert native_lib.hb_mlp_workspace_bytes(-1, 0) < 0
+    multi = [native_lib.hb_mlp_multi_workspace_bytes(m, 256) for m in (1, 7, 64, 65)]
+    assert all(a > 0 for a in multi) and multi == sorted(multi)
+
+
 def test_binding_covers_header(native_lib):
     from heybuddy_b200 import _native
 
